@@ -1,0 +1,485 @@
+// conv_umma.cu — tcgen05/TMEM/TMA implicit-GEMM Conv3d for sm_100a.
+//
+// Replaces the reference's snt.Conv3D + snt.BatchNorm + ReLU (i3d.py:61-70, cuDNN fp32 in the
+// reference) and the backward-data convolutions autograd builds for
+// compute_gradients(loss, var_list=perturbation) (i3d_adversarial_main_single_video_npy.py:82).
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0    TMA producer  (one elected lane; A box + B box per k-block into a smem ring)
+//   warp 1    TMEM allocator + MMA issuer (one lane issues tcgen05.mma, commits to mbarriers)
+//   warps 2-5 epilogue (tcgen05.ld 32 lanes x 16 cols, bias/ReLU/mask, bf16 NDHWC stores)
+// Two 256-column fp32 accumulators in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "conv_umma.cuh"
+
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+namespace fav {
+
+__device__ int g_fav_timeout_flag = 0;
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kAccCols = 256;   // TMEM columns per accumulator stage
+constexpr int kMaxStages = 8;
+
+struct TileCoord {
+  int b, t0, h0, w0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int tile) {
+  TileCoord c;
+  int nt = tile % g.n_tiles;
+  int m = tile / g.n_tiles;
+  int wi = m % g.tw;
+  m /= g.tw;
+  int hi = m % g.th;
+  m /= g.th;
+  int ti = m % g.tt;
+  c.b = m / g.tt;
+  c.w0 = wi * g.bw;
+  c.h0 = hi * g.bh;
+  c.t0 = ti * g.bt;
+  c.n0 = nt * g.bn;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                 const __grid_constant__ CUtensorMap tmB, const ConvGeom g, const ConvEpilogue e,
+                 const int stages, const int a_bytes, const int b_bytes, const int stage_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* full_bar = bars;                    // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;      // [stages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (g.stem) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmA3);
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        for (int kb = 0; kb < g.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(a_bytes + b_bytes));
+          if (!g.stem) {
+            const int tap = kb / g.cblocks;
+            const int cb = kb - tap * g.cblocks;
+            const int dw = tap % g.kw;
+            const int dh = (tap / g.kw) % g.kh;
+            const int dt = tap / (g.kw * g.kh);
+            tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 + dw + g.ow, tc.h0 + dh + g.oh,
+                        tc.t0 + dt + g.ot, tc.b);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
+          } else {
+            // input index = 2*o + k - pad = 2*(o + q) + parity
+            const int kti = kb / g.kh;
+            const int khi = kb - kti * g.kh;
+            const int offt = kti - g.stem_pt;
+            const int offh = khi - g.stem_ph;
+            const int pt = offt & 1;
+            const int ph = offh & 1;
+            const int qt = (offt - pt) >> 1;
+            const int qh = (offh - ph) >> 1;
+            const int mi = pt * 2 + ph;
+            const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+            tma_load_5d(sa, tm, &full_bar[stage], 0, tc.w0, tc.h0 + qh, tc.t0 + qt, tc.b);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * 32, tc.n0);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+      const uint32_t row_bytes = g.stem ? 64u : 128u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+        for (int kb = 0; kb < g.nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
+          const uint64_t adesc = umma_smem_desc(sa, row_bytes);
+          const uint64_t bdesc = umma_smem_desc(sb, row_bytes);
+          int ksteps;
+          if (g.stem) {
+            ksteps = 2;
+          } else {
+            const int cb = kb % g.cblocks;
+            ksteps = min(4, (g.cin - cb * 64) >> 4);
+          }
+          for (int k = 0; k < ksteps; ++k) {
+            // +32 bytes (16 bf16 of K) inside the swizzled row: +2 in the 16-byte address field
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rw = row % g.bw;
+    const int rh = (row / g.bw) % g.bh;
+    const int rt = row / (g.bw * g.bh);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(g, tile);
+      const int w = tc.w0 + rw, h = tc.h0 + rh, t = tc.t0 + rt;
+      const bool valid = (w < g.W) && (h < g.H) && (t < g.T);
+      const long long pos = ((static_cast<long long>(tc.b) * g.T + t) * g.H + h) * g.W + w;
+      __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
+      const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
+      const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
+      const float* bias_row = nullptr;
+      if (e.bias) {
+        int br = 0;
+        if (e.bias_stem) {
+          const int hc = (h == 0) ? 0 : (h == g.H - 2 ? 2 : (h == g.H - 1 ? 3 : 1));
+          const int wc = (w == 0) ? 0 : (w == g.W - 2 ? 2 : (w == g.W - 1 ? 3 : 1));
+          br = (min(t, g.T - 1) * 4 + hc) * 4 + wc;
+        }
+        bias_row = e.bias + static_cast<long long>(br) * e.bias_ld;
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(acc * kAccCols);
+      for (int c = 0; c < g.bn; c += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r);
+        tmem_ld_wait();
+        const int n = tc.n0 + c;  // first output channel of this chunk
+        if (valid && n < e.cout_store) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (bias_row) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
+              v[j] += bv.x;
+              v[j + 1] += bv.y;
+              v[j + 2] += bv.z;
+              v[j + 3] += bv.w;
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (n + half * 8 + 8 <= e.cout_store) {
+              float* vv = v + half * 8;
+              if (add_row) {
+                const uint4 a = *reinterpret_cast<const uint4*>(add_row + n + half * 8);
+                vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x);
+                vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
+                vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z);
+                vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
+              }
+              if (e.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+              }
+              if (mask_row) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n + half * 8);
+                vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
+                vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
+                vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
+                vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(vv[0], vv[1]);
+              o.y = pack_bf16x2(vv[2], vv[3]);
+              o.z = pack_bf16x2(vv[4], vv[5]);
+              o.w = pack_bf16x2(vv[6], vv[7]);
+              *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+uint16_t f32_to_bf16_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  const uint32_t rounding = 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>((u + rounding) >> 16);
+}
+float bf16_bits_to_f32(uint16_t b) {
+  uint32_t u = static_cast<uint32_t>(b) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+void choose_box(int T, int H, int W, int kt, int kh, int kw, int* bw, int* bh, int* bt) {
+  (void)kt; (void)kh; (void)kw;
+  double best = -1.0;
+  int best_bw = 128, best_bh = 1, best_bt = 1;
+  for (int a = 1; a <= 128; a *= 2) {
+    for (int b = 1; a * b <= 128; b *= 2) {
+      const int c = 128 / (a * b);
+      if (a > 256 || b > 256 || c > 256) continue;
+      const double eff = (static_cast<double>(W) / (ceil_div(W, a) * a)) *
+                         (static_cast<double>(H) / (ceil_div(H, b) * b)) *
+                         (static_cast<double>(T) / (ceil_div(T, c) * c));
+      // prefer wide-in-W boxes on ties (longer contiguous runs per TMA box row group)
+      const double score = eff + 1e-6 * a + 1e-7 * b;
+      if (score > best) {
+        best = score;
+        best_bw = a;
+        best_bh = b;
+        best_bt = c;
+      }
+    }
+  }
+  *bw = best_bw;
+  *bh = best_bh;
+  *bt = best_bt;
+}
+
+static void finish_plan(ConvLaunch* L, int device) {
+  ConvGeom& g = L->g;
+  g.tw = ceil_div(g.W, g.bw);
+  g.th = ceil_div(g.H, g.bh);
+  g.tt = ceil_div(g.T, g.bt);
+  g.m_tiles = g.B * g.tt * g.th * g.tw;
+  const int row_bytes = g.stem ? 64 : 128;
+  L->a_bytes = 128 * row_bytes;
+  L->b_bytes = g.bn * row_bytes;
+  L->stage_bytes = round_up(L->a_bytes + L->b_bytes, 1024);
+  const int budget = 200 * 1024;
+  L->stages = std::max(2, std::min(kMaxStages, budget / L->stage_bytes));
+  L->smem_bytes = static_cast<size_t>(L->stages) * L->stage_bytes + 1024 + 512;
+  const int tiles = g.m_tiles * g.n_tiles;
+  L->grid = std::max(1, std::min(tiles, sm_count(device)));
+}
+
+int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
+                      const void* wpk, int cout_pad, int B, int T, int H, int W, int kt, int kh,
+                      int kw, int flat) {
+  FAV_CHECK_ARG(cin % 16 == 0 && cin > 0, "conv: cin=%d must be a positive multiple of 16", cin);
+  FAV_CHECK_ARG(x_cs % 8 == 0 && x_coff % 8 == 0, "conv: channel stride/offset must be multiples of 8");
+  FAV_CHECK_ARG(cout_pad % 16 == 0 && cout_pad > 0, "conv: padded cout=%d must be a multiple of 16", cout_pad);
+  memset(L, 0, sizeof(*L));
+  ConvGeom& g = L->g;
+  g.stem = 0;
+  g.kt = kt; g.kh = kh; g.kw = kw;
+  g.ot = -((kt - 1) / 2); g.oh = -((kh - 1) / 2); g.ow = -((kw - 1) / 2);
+  g.cin = cin;
+  g.cblocks = ceil_div(cin, 64);
+  g.nkb = kt * kh * kw * g.cblocks;
+  g.n_tiles = ceil_div(cout_pad, 256);
+  g.bn = round_up(ceil_div(cout_pad, g.n_tiles), 16);
+  FAV_CHECK_ARG(g.bn * g.n_tiles == cout_pad, "conv: cout_pad=%d not divisible into %d tiles of %d",
+                cout_pad, g.n_tiles, g.bn);
+
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  const char* base = static_cast<const char*>(x) + static_cast<long long>(x_coff) * 2;
+  if (flat) {
+    FAV_CHECK_ARG(kt == 1 && kh == 1 && kw == 1, "conv: flat tiling needs a 1x1x1 kernel");
+    const long long M = static_cast<long long>(B) * T * H * W;
+    FAV_CHECK_ARG(M < (1ll << 31), "conv: too many positions");
+    g.B = 1; g.T = 1; g.H = 1; g.W = static_cast<int>(M);
+    g.bw = 128; g.bh = 1; g.bt = 1;
+  } else {
+    g.B = B; g.T = T; g.H = H; g.W = W;
+    choose_box(T, H, W, kt, kh, kw, &g.bw, &g.bh, &g.bt);
+  }
+  dims[0] = static_cast<uint64_t>(cin);
+  dims[1] = static_cast<uint64_t>(g.W);
+  dims[2] = static_cast<uint64_t>(g.H);
+  dims[3] = static_cast<uint64_t>(g.T);
+  dims[4] = static_cast<uint64_t>(g.B);
+  strides[0] = static_cast<uint64_t>(x_cs) * 2;
+  strides[1] = strides[0] * g.W;
+  strides[2] = strides[1] * g.H;
+  strides[3] = strides[2] * g.T;
+  box[0] = 64; box[1] = g.bw; box[2] = g.bh; box[3] = g.bt; box[4] = 1;
+  FAV_TRY(make_tmap_bf16(&L->tmA[0], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  L->tmA[1] = L->tmA[0]; L->tmA[2] = L->tmA[0]; L->tmA[3] = L->tmA[0];
+
+  uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cout_pad)};
+  uint64_t bs[1] = {bd[0] * 2};
+  uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  finish_plan(L, device);
+  return FAV_OK;
+}
+
+int conv_plan_stem(ConvLaunch* L, int device, const void* xpad, int B, int T, int H, int W, int Wp,
+                   const void* wpk, int To, int Ho, int Wo, int pt, int ph) {
+  (void)W;
+  memset(L, 0, sizeof(*L));
+  ConvGeom& g = L->g;
+  g.stem = 1;
+  g.stem_pt = pt; g.stem_ph = ph;
+  g.kt = 7; g.kh = 7; g.kw = 1;
+  g.cin = 32; g.cblocks = 1;
+  g.nkb = 49;
+  g.n_tiles = 1; g.bn = 64;
+  g.B = B; g.T = To; g.H = Ho; g.W = Wo;
+  choose_box(To, Ho, Wo, 7, 7, 7, &g.bw, &g.bh, &g.bt);
+  const uint64_t pos_bytes = 8;                       // 4 channels bf16
+  const uint64_t row_pitch = static_cast<uint64_t>(Wp) * pos_bytes;
+  const uint64_t frame_pitch = row_pitch * H;
+  const uint64_t clip_pitch = frame_pitch * T;
+  for (int p_t = 0; p_t < 2; ++p_t) {
+    for (int p_h = 0; p_h < 2; ++p_h) {
+      uint64_t dims[5], strides[4];
+      uint32_t box[5];
+      dims[0] = 32;                                    // 8 W-positions x 4 channels, contiguous
+      dims[1] = static_cast<uint64_t>(Wo);             // output column; window start moves 2 positions
+      dims[2] = static_cast<uint64_t>((H - p_h + 1) / 2);
+      dims[3] = static_cast<uint64_t>((T - p_t + 1) / 2);
+      dims[4] = static_cast<uint64_t>(B);
+      strides[0] = 2 * pos_bytes;                      // 16 B: overlapping windows
+      strides[1] = 2 * row_pitch;
+      strides[2] = 2 * frame_pitch;
+      strides[3] = clip_pitch;
+      box[0] = 32; box[1] = g.bw; box[2] = g.bh; box[3] = g.bt; box[4] = 1;
+      const char* base = static_cast<const char*>(xpad) + p_t * frame_pitch + p_h * row_pitch;
+      FAV_TRY(make_tmap_bf16(&L->tmA[p_t * 2 + p_h], base, 5, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_64B));
+    }
+  }
+  uint64_t bd[2] = {49 * 32, 64};
+  uint64_t bs[1] = {bd[0] * 2};
+  uint32_t bb[2] = {32, 64};
+  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_64B));
+  finish_plan(L, device);
+  return FAV_OK;
+}
+
+int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FAV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  220 * 1024));
+    attr_set = true;
+  }
+  conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(
+      L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
+      L.stage_bytes);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+void pack_weights_fwd(uint16_t* dst, const float* w, const float* scale, int taps, int cin_real,
+                      int cin_k, int cout_real, int n_pad) {
+  const int cblocks = ceil_div(cin_k, 64);
+  const size_t K = static_cast<size_t>(taps) * cblocks * 64;
+  memset(dst, 0, K * n_pad * sizeof(uint16_t));
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ci = 0; ci < cin_real; ++ci) {
+      const size_t kidx = (static_cast<size_t>(tap) * cblocks + ci / 64) * 64 + ci % 64;
+      const float* src = w + (static_cast<size_t>(tap) * cin_real + ci) * cout_real;
+      for (int co = 0; co < cout_real; ++co) {
+        const float s = scale ? scale[co] : 1.0f;
+        dst[static_cast<size_t>(co) * K + kidx] = f32_to_bf16_bits(src[co] * s);
+      }
+    }
+}
+
+void pack_weights_dgrad(uint16_t* dst, const float* w, const float* scale, int taps, int cin_real,
+                        int cout_real, int cout_k, int n_pad) {
+  const int cblocks = ceil_div(cout_k, 64);
+  const size_t K = static_cast<size_t>(taps) * cblocks * 64;
+  memset(dst, 0, K * n_pad * sizeof(uint16_t));
+  for (int tap = 0; tap < taps; ++tap) {
+    const int ftap = taps - 1 - tap;  // flipping all three axes == reversing the flattened tap index
+    for (int ci = 0; ci < cin_real; ++ci) {
+      const float* src = w + (static_cast<size_t>(ftap) * cin_real + ci) * cout_real;
+      for (int co = 0; co < cout_real; ++co) {
+        const float s = scale ? scale[co] : 1.0f;
+        const size_t kidx = (static_cast<size_t>(tap) * cblocks + co / 64) * 64 + co % 64;
+        dst[static_cast<size_t>(ci) * K + kidx] = f32_to_bf16_bits(src[co] * s);
+      }
+    }
+  }
+}
+
+}  // namespace fav

@@ -1,0 +1,950 @@
+// kernels.cu — HBM-bound kernels of the attack loop: flicker apply (a), max-pool fwd/bwd, head,
+// loss, stem backward collapse, and the fused regulariser-gradient + Adam update on delta (c).
+#include "kernels.cuh"
+
+#include <math.h>
+
+namespace fav {
+
+// =============================================================================================
+// (a) flicker apply
+//   reference: x = u8/128 - 1 (utils/pre_process_rgb_flow.py:234);
+//              eps_rgb_clip = clip(eps, +-0.4) (utils/kinetics_i3d_utils.py:104-105);
+//              adv = clip(x + adv_flag*eps_clip, -1, 1) (:139-142);
+//              uint8 view ((adv+1.0)*127.5).astype(uint8) (utils/stats_and_plot/stats_plots.py:57).
+//   Each thread owns 16 consecutive pixels of one row (48 bytes of uint8 = three 128-bit loads).
+//   The stem input written here is x' = adv - delta' (== x wherever the range clip did not fire);
+//   delta' reaches the network as an fp32 per-frame bias of the stem (launch_stem_bias).
+// =============================================================================================
+template <bool kF32>
+__global__ void __launch_bounds__(256)
+apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, float adv_flag,
+             float dclip, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
+             uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
+             uint32_t* __restrict__ sat_list, uint32_t sat_capacity, uint32_t* __restrict__ sat_count,
+             int T, int H, int W, long long groups) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool active = gid < groups;
+  const int gpr = W >> 4;
+  uint32_t sat_mask[16];
+  int nsat = 0;
+  long long row = 0;
+  int wg = 0;
+  if (active) {
+    wg = static_cast<int>(gid % gpr);
+    row = gid / gpr;  // (b*T + t)*H + h
+    const int t = static_cast<int>((row / H) % T);
+    float d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      d[c] = __fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip));
+
+    float x[48];
+    const long long e0 = (row * W + wg * 16) * 3;  // first element of this thread
+    if (kF32) {
+      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(clip) + e0);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const float4 v = __ldg(src + i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(clip) + e0);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint4 v = __ldg(src + i);
+        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            x[16 * i + 4 * j + k] =
+                __fsub_rn(__fmul_rn(static_cast<float>((wds[j] >> (8 * k)) & 0xffu), 0.0078125f), 1.0f);
+      }
+    }
+    float a[48];
+    uint32_t xq[32];  // 16 pixels x (RG, B0) bf16 pairs
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      float q[3];
+      uint32_t m = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float s = __fadd_rn(x[3 * p + c], d[c]);
+        const float av = fminf(fmaxf(s, -1.0f), 1.0f);
+        a[3 * p + c] = av;
+        const bool sat = (s < -1.0f) || (s > 1.0f);
+        q[c] = sat ? __fsub_rn(av, d[c]) : x[3 * p + c];
+        m |= sat ? (1u << c) : 0u;
+      }
+      sat_mask[p] = m;
+      nsat += (m != 0);
+      xq[2 * p] = pack_bf16x2(q[0], q[1]);
+      xq[2 * p + 1] = pack_bf16x2(q[2], 0.0f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(xpad + (row * Wp + padl + wg * 16) * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xq[4 * i], xq[4 * i + 1], xq[4 * i + 2], xq[4 * i + 3]);
+
+    if (adv_u8) {
+      uint32_t o[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float f = __fmul_rn(__fadd_rn(a[4 * i + k], 1.0f), 127.5f);
+          wv |= (__float2uint_rz(f) & 0xffu) << (8 * k);
+        }
+        o[i] = wv;
+      }
+      uint4* du = reinterpret_cast<uint4*>(adv_u8 + e0);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) du[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    if (adv_f32) {
+      float4* df = reinterpret_cast<float4*>(adv_f32 + e0);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) df[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    }
+  }
+  // warp-aggregated append of saturated pixels
+  if (sat_list) {
+    const int lane = threadIdx.x & 31;
+    int incl = nsat;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total > 0) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(sat_count, static_cast<uint32_t>(total));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      uint32_t pos = base + static_cast<uint32_t>(incl - nsat);
+      if (nsat > 0) {
+        const uint32_t pix0 = static_cast<uint32_t>(row * W + wg * 16);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          if (sat_mask[p]) {
+            if (pos < sat_capacity) sat_list[pos] = (pix0 + p) | (sat_mask[p] << 28);
+            ++pos;
+          }
+        }
+      }
+    }
+  }
+}
+
+int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
+                 __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
+                 uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
+                 int W, cudaStream_t s) {
+  FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
+  FAV_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 28), "apply: too many pixels per call");
+  const long long groups = static_cast<long long>(B) * T * H * (W / 16);
+  const int block = 256;
+  const int grid = static_cast<int>(ceil_div64(groups, block));
+  if (sat_count) FAV_CUDA(cudaMemsetAsync(sat_count, 0, sizeof(uint32_t), s));
+  if (in_dtype == FAV_F32)
+    apply_kernel<true><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
+                                              adv_f32, sat_list, sat_capacity, sat_count, T, H, W, groups);
+  else
+    apply_kernel<false><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
+                                               adv_f32, sat_list, sat_capacity, sat_count, T, H, W, groups);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// delta-dependent stem bias: conv(x' + delta') = conv(x') + bias[t_o, hclass, wclass, co]
+// ---------------------------------------------------------------------------------------------
+__global__ void stem_bias_kernel(const float* __restrict__ delta, float adv_flag, float dclip,
+                                 const float* __restrict__ wc, const float* __restrict__ bnbias,
+                                 float* __restrict__ table, int T, int To, int pt) {
+  const int to = blockIdx.x >> 4;
+  const int cls = blockIdx.x & 15;
+  const int co = threadIdx.x;
+  float acc = bnbias[co];
+  for (int kt = 0; kt < 7; ++kt) {
+    const int t = 2 * to + kt - pt;
+    if (t < 0 || t >= T) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = adv_flag * fminf(fmaxf(delta[t * 3 + c], -dclip), dclip);
+      acc = fmaf(d, wc[((kt * 16 + cls) * 3 + c) * 64 + co], acc);
+    }
+  }
+  table[(to * 16 + cls) * 64 + co] = acc;
+  (void)To;
+}
+
+int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc,
+                     const float* bnbias, float* table, int T, int To, int pt, cudaStream_t s) {
+  stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// MaxPool3d, TF SAME semantics (i3d.py:174,189,212,252,398): -inf padding, first arg-max wins.
+// =============================================================================================
+PoolGeom make_pool_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh, int sw) {
+  PoolGeom g;
+  g.B = B; g.T = T; g.H = H; g.W = W; g.C = C;
+  g.kt = kt; g.kh = kh; g.kw = kw; g.st = st; g.sh = sh; g.sw = sw;
+  g.To = ceil_div(T, st); g.Ho = ceil_div(H, sh); g.Wo = ceil_div(W, sw);
+  auto padb = [](int in, int out, int k, int s) {
+    int total = (out - 1) * s + k - in;
+    if (total < 0) total = 0;
+    return total / 2;
+  };
+  g.pt = padb(T, g.To, kt, st); g.ph = padb(H, g.Ho, kh, sh); g.pw = padb(W, g.Wo, kw, sw);
+  return g;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                   uint8_t* __restrict__ idx, const PoolGeom g, long long total) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = g.C >> 3;
+  const int c8 = static_cast<int>(gid % cg);
+  long long p = gid / cg;
+  const int wo = static_cast<int>(p % g.Wo); p /= g.Wo;
+  const int ho = static_cast<int>(p % g.Ho); p /= g.Ho;
+  const int to = static_cast<int>(p % g.To);
+  const int b = static_cast<int>(p / g.To);
+  float best[8];
+  int bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+  for (int dt = 0; dt < g.kt; ++dt) {
+    const int t = to * g.st + dt - g.pt;
+    if (t < 0 || t >= g.T) continue;
+    for (int dh = 0; dh < g.kh; ++dh) {
+      const int h = ho * g.sh + dh - g.ph;
+      if (h < 0 || h >= g.H) continue;
+      for (int dw = 0; dw < g.kw; ++dw) {
+        const int w = wo * g.sw + dw - g.pw;
+        if (w < 0 || w >= g.W) continue;
+        const int tap = (dt * g.kh + dh) * g.kw + dw;
+        const long long off = (((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * g.C + c8 * 8;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + off));
+        const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                            bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > best[j]) { best[j] = f[j]; bi[j] = tap; }
+      }
+    }
+  }
+  const long long ooff = gid * 8;
+  uint4 o;
+  o.x = pack_bf16x2(best[0], best[1]); o.y = pack_bf16x2(best[2], best[3]);
+  o.z = pack_bf16x2(best[4], best[5]); o.w = pack_bf16x2(best[6], best[7]);
+  *reinterpret_cast<uint4*>(y + ooff) = o;
+  if (idx) {
+    uint2 iv;
+    iv.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    iv.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + ooff) = iv;
+  }
+}
+
+int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
+                       cudaStream_t s) {
+  FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
+  const long long total = static_cast<long long>(g.B) * g.To * g.Ho * g.Wo * (g.C / 8);
+  maxpool_fwd_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(x, y, idx, g, total);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// backward in gather form: every input element sums the windows whose recorded arg-max is itself
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                   const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
+                   __nv_bfloat16* __restrict__ dx, const PoolGeom g, long long total) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = g.C >> 3;
+  const int c8 = static_cast<int>(gid % cg);
+  long long p = gid / cg;
+  const int w = static_cast<int>(p % g.W); p /= g.W;
+  const int h = static_cast<int>(p % g.H); p /= g.H;
+  const int t = static_cast<int>(p % g.T);
+  const int b = static_cast<int>(p / g.T);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  if (addend) {
+    const uint4 a = *reinterpret_cast<const uint4*>(addend + gid * 8);
+    acc[0] = bf16_lo(a.x); acc[1] = bf16_hi(a.x); acc[2] = bf16_lo(a.y); acc[3] = bf16_hi(a.y);
+    acc[4] = bf16_lo(a.z); acc[5] = bf16_hi(a.z); acc[6] = bf16_lo(a.w); acc[7] = bf16_hi(a.w);
+  }
+  // windows (to) containing t: to*st - pt <= t <= to*st - pt + kt - 1
+  const int tp = t + g.pt, hp = h + g.ph, wp = w + g.pw;
+  int to_lo = (tp - g.kt + 1 + g.st - 1); to_lo = to_lo < 0 ? 0 : to_lo / g.st;
+  int ho_lo = (hp - g.kh + 1 + g.sh - 1); ho_lo = ho_lo < 0 ? 0 : ho_lo / g.sh;
+  int wo_lo = (wp - g.kw + 1 + g.sw - 1); wo_lo = wo_lo < 0 ? 0 : wo_lo / g.sw;
+  const int to_hi = min(tp / g.st, g.To - 1);
+  const int ho_hi = min(hp / g.sh, g.Ho - 1);
+  const int wo_hi = min(wp / g.sw, g.Wo - 1);
+  for (int to = to_lo; to <= to_hi; ++to) {
+    const int dt = tp - to * g.st;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      const int dh = hp - ho * g.sh;
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int dw = wp - wo * g.sw;
+        const uint32_t tap = static_cast<uint32_t>((dt * g.kh + dh) * g.kw + dw);
+        const long long off = (((static_cast<long long>(b) * g.To + to) * g.Ho + ho) * g.Wo + wo) * g.C + c8 * 8;
+        const uint2 iv = __ldg(reinterpret_cast<const uint2*>(idx + off));
+        const uint32_t eqx = iv.x ^ (tap * 0x01010101u);
+        const uint32_t eqy = iv.y ^ (tap * 0x01010101u);
+        if (((eqx & 0xffu) && (eqx & 0xff00u) && (eqx & 0xff0000u) && (eqx & 0xff000000u)) &&
+            ((eqy & 0xffu) && (eqy & 0xff00u) && (eqy & 0xff0000u) && (eqy & 0xff000000u)))
+          continue;  // none of the 8 channels picked this element
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dy + off));
+        const float f[8] = {bf16_lo(d.x), bf16_hi(d.x), bf16_lo(d.y), bf16_hi(d.y),
+                            bf16_lo(d.z), bf16_hi(d.z), bf16_lo(d.w), bf16_hi(d.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (((eqx >> (8 * j)) & 0xffu) == 0) acc[j] += f[j];
+          if (((eqy >> (8 * j)) & 0xffu) == 0) acc[4 + j] += f[4 + j];
+        }
+      }
+    }
+  }
+  if (relu_src) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(relu_src + gid * 8));
+    const float f[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
+                        bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = f[j] > 0.0f ? acc[j] : 0.0f;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(dx + gid * 8) = o;
+}
+
+int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
+                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
+                       cudaStream_t s) {
+  FAV_CHECK_ARG(g.C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", g.C);
+  const long long total = static_cast<long long>(g.B) * g.T * g.H * g.W * (g.C / 8);
+  maxpool_bwd_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(dy, idx, addend, relu_src,
+                                                                             dx, g, total);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// head: avg_pool3d [2,7,7] VALID s1 -> 1x1x1 conv + bias -> mean over T' (i3d.py:459-472).
+// All linear, so logits = bl + Wl^T * feat with feat[b,c] = sum_t coef[t] sum_hw Y / (HW*2*(T5-1)),
+// coef[t] = number of length-2 windows containing frame t.
+// =============================================================================================
+__device__ __forceinline__ float head_coef(int t, int T5) {
+  if (T5 == 1) return 1.0f;
+  return (t == 0 || t == T5 - 1) ? 1.0f : 2.0f;
+}
+__device__ __forceinline__ float head_scale(int T5, int HW) {
+  return T5 == 1 ? 1.0f / HW : 1.0f / (static_cast<float>(HW) * 2.0f * (T5 - 1));
+}
+
+__global__ void __launch_bounds__(256)
+head_feat_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ feat, int T5, int HW, int C) {
+  __shared__ float red[8][32][8];
+  const int b = blockIdx.y;
+  const int cgp = blockIdx.x * 32 + (threadIdx.x & 31);  // 8-channel group
+  const int pl = threadIdx.x >> 5;                        // position lane 0..7
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  const int npos = T5 * HW;
+  if (cgp * 8 < C) {
+    for (int p = pl; p < npos; p += 8) {
+      const float cf = head_coef(p / HW, T5);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + (static_cast<long long>(b) * npos + p) * C + cgp * 8));
+      acc[0] += cf * bf16_lo(v.x); acc[1] += cf * bf16_hi(v.x);
+      acc[2] += cf * bf16_lo(v.y); acc[3] += cf * bf16_hi(v.y);
+      acc[4] += cf * bf16_lo(v.z); acc[5] += cf * bf16_hi(v.z);
+      acc[6] += cf * bf16_lo(v.w); acc[7] += cf * bf16_hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pl][threadIdx.x & 31][j] = acc[j];
+  __syncthreads();
+  if (pl == 0 && cgp * 8 < C) {
+    const float sc = head_scale(T5, HW);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x & 31][j];
+      feat[static_cast<long long>(b) * C + cgp * 8 + j] = sum * sc;
+    }
+  }
+}
+
+__global__ void head_logits_kernel(const float* __restrict__ feat, const float* __restrict__ wl,
+                                   const float* __restrict__ bl, float* __restrict__ logits, int C, int K) {
+  extern __shared__ float sfeat[];
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sfeat[c] = feat[static_cast<long long>(b) * C + c];
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc = bl[k];
+    for (int c = 0; c < C; ++c) acc = fmaf(sfeat[c], wl[static_cast<long long>(c) * K + k], acc);
+    logits[static_cast<long long>(b) * K + k] = acc;
+  }
+}
+
+int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float* feat, const float* wl,
+                    const float* bl, int K, float* logits, cudaStream_t s) {
+  FAV_CHECK_ARG(C % 8 == 0, "head: C must be a multiple of 8");
+  dim3 grid(ceil_div(C / 8, 32), B);
+  head_feat_kernel<<<grid, 256, 0, s>>>(y, feat, T5, HW, C);
+  FAV_CUDA(cudaGetLastError());
+  head_logits_kernel<<<B, 512, C * sizeof(float), s>>>(feat, wl, bl, logits, C, K);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+__global__ void head_dfeat_kernel(const float* __restrict__ dlogits, const float* __restrict__ wl,
+                                  float* __restrict__ dfeat, int C, int K) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float acc = 0.0f;
+  for (int k = lane; k < K; k += 32)
+    acc = fmaf(dlogits[static_cast<long long>(b) * K + k], wl[static_cast<long long>(c) * K + k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) dfeat[static_cast<long long>(b) * C + c] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+head_gy_kernel(const float* __restrict__ dfeat, const __nv_bfloat16* __restrict__ y,
+               __nv_bfloat16* __restrict__ gy, int T5, int HW, int C, long long total) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = C >> 3;
+  const int c8 = static_cast<int>(gid % cg);
+  const long long p = gid / cg;
+  const int npos = T5 * HW;
+  const int b = static_cast<int>(p / npos);
+  const int t = static_cast<int>((p % npos) / HW);
+  const float sc = head_scale(T5, HW) * head_coef(t, T5);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + gid * 8));
+  const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                      bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+  const float* df = dfeat + static_cast<long long>(b) * C + c8 * 8;
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = f[j] > 0.0f ? sc * df[j] : 0.0f;
+  uint4 ov;
+  ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+  ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+  *reinterpret_cast<uint4*>(gy + gid * 8) = ov;
+}
+
+int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfloat16* y,
+                    __nv_bfloat16* gy, float* dfeat, int B, int T5, int HW, int C, cudaStream_t s) {
+  dim3 grid(ceil_div(C, 8), B);
+  head_dfeat_kernel<<<grid, 256, 0, s>>>(dlogits, wl, dfeat, C, K);
+  FAV_CUDA(cudaGetLastError());
+  const long long total = static_cast<long long>(B) * T5 * HW * (C / 8);
+  head_gy_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(dfeat, y, gy, T5, HW, C, total);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// softmax + adversarial loss + dloss/dlogits
+//   improve_adversarial_loss: utils/kinetics_i3d_utils.py:253-288 (TF) / model.py:216-250 (torch)
+//   ce_adversarial_loss:      utils/kinetics_i3d_utils.py:290-307 (TF) / model.py:177-196 (torch)
+// One block; clips are processed in order so the batch sums are deterministic.
+// =============================================================================================
+template <typename T>
+__device__ __forceinline__ T block_reduce(T v, T* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? (u > v ? u : v) : v + u;
+  }
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  T r = sh[0];
+  for (int i = 1; i < nw; ++i) r = is_max ? (sh[i] > r ? sh[i] : r) : r + sh[i];
+  return r;
+}
+
+// arg-max with lowest-index tie-break over values val(k), k in [0,K)
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax block_argmax(float v, int i, ArgMax* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float uv = __shfl_xor_sync(0xffffffffu, v, o);
+    const int ui = __shfl_xor_sync(0xffffffffu, i, o);
+    if (uv > v || (uv == v && ui < i)) { v = uv; i = ui; }
+  }
+  __syncthreads();
+  if (lane == 0) { sh[wid].v = v; sh[wid].i = i; }
+  __syncthreads();
+  ArgMax r = sh[0];
+  const int nw = blockDim.x >> 5;
+  for (int k = 1; k < nw; ++k)
+    if (sh[k].v > r.v || (sh[k].v == r.v && sh[k].i < r.i)) r = sh[k];
+  return r;
+}
+
+__global__ void __launch_bounds__(512)
+loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const fav_loss_params p,
+            int B, int K, float* __restrict__ probs, float* __restrict__ dlogits,
+            float* __restrict__ scalars) {
+  __shared__ float shf[16];
+  __shared__ float stash[4];
+  __shared__ ArgMax sha[16];
+  extern __shared__ float sp[];  // [K] probabilities, [K] dL/dp
+  float* prob = sp;
+  float* dp = sp + K;
+  float adv_sum = 0.0f, fooled = 0.0f, sum_min = 0.0f, sum_max = 0.0f;
+  const float bdiv = static_cast<float>(p.global_batch > 0 ? p.global_batch : B);
+  const bool torch_stack = p.stack == FAV_STACK_TORCH;
+  for (int b = 0; b < B; ++b) {
+    const float* z = logits + static_cast<long long>(b) * K;
+    const int y = static_cast<int>(labels[b]);
+    float mx = -INFINITY;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, z[k]);
+    mx = block_reduce<float>(mx, shf, true);
+    float se = 0.0f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float e = expf(z[k] - mx);
+      prob[k] = e;
+      se += e;
+    }
+    se = block_reduce<float>(se, shf, false);
+    const float inv = 1.0f / se;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      prob[k] *= inv;
+      dp[k] = 0.0f;
+      if (probs) probs[static_cast<long long>(b) * K + k] = prob[k];
+    }
+    __syncthreads();
+    // selections
+    float bv = -INFINITY; int bi = K;       // arg-max prob (prediction)
+    float nv = -INFINITY; int ni = K;       // max non-label prob
+    float lv = -INFINITY; int li = K;       // max "non-label" logit
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float pk = prob[k];
+      if (pk > bv) { bv = pk; bi = k; }
+      const float pn = torch_stack ? (k == y ? -INFINITY : pk) : pk - (k == y ? 1.0f : 0.0f);
+      if (pn > nv) { nv = pn; ni = k; }
+      const float zn = torch_stack ? (k == y ? -INFINITY : z[k]) : z[k] - (k == y ? 1.0f : 0.0f);
+      if (zn > lv) { lv = zn; li = k; }
+    }
+    const ArgMax pred = block_argmax(bv, bi, sha);
+    const ArgMax nonl = block_argmax(nv, ni, sha);
+    const ArgMax nonz = block_argmax(lv, li, sha);
+    const float py = prob[y];
+    const float pmaxnl = nonl.v;  // TF: value of (p - onehot) at its arg-max == p[k*] when k* != y
+
+    if (threadIdx.x == 0) {
+      float loss = 0.0f;
+      float dd_logit = 0.0f;   // direct logit gradient: +dd at ia, -dd at ib (logits mode only)
+      int ia = -1, ib = -1;
+      if (p.improve_loss) {
+        float a, bb, mm;
+        float dmm_dp = 0.0f; int mm_idx = -1;  // in logits mode the margin depends on one probability
+        if (!p.targeted) {
+          if (p.use_logits) {
+            a = z[y]; bb = nonz.v; ia = y; ib = nonz.i;
+            const float pm = torch_stack ? py : pmaxnl;
+            mm = logf(1.0f + p.margin * (1.0f / (0.00001f + pm)));
+            dmm_dp = -p.margin / ((0.00001f + pm) * (0.00001f + pm) * (1.0f + p.margin / (0.00001f + pm)));
+            mm_idx = torch_stack ? y : nonl.i;
+          } else {
+            a = py; bb = pmaxnl; mm = p.margin; ia = y; ib = nonl.i;
+          }
+          sum_min += py; sum_max += pmaxnl;
+        } else {
+          if (p.use_logits) {
+            a = nonz.v; bb = z[y]; ia = nonz.i; ib = y;
+            mm = logf(1.0f + p.margin * (1.0f / py));
+            dmm_dp = -p.margin / (py * py * (1.0f + p.margin / py));
+            mm_idx = y;
+          } else {
+            a = pmaxnl; bb = py; mm = p.margin; ia = nonl.i; ib = y;
+          }
+          sum_min += pmaxnl; sum_max += py;
+        }
+        const float d = a - (bb - mm);
+        const float l2 = d * d / mm, l3 = d;
+        const float mn = fminf(l2, l3);
+        float dd = 0.0f, dmm = 0.0f;
+        if (mn > 0.0f) {   // tf.maximum(0.0, x) passes the gradient to x only when x > 0
+          loss = mn;
+          if (l2 <= l3) { dd = 2.0f * d / mm; dmm = dd - d * d / (mm * mm); }
+          else { dd = 1.0f; dmm = 1.0f; }
+        }
+        if (p.use_logits) {
+          dd_logit = dd;
+          if (mm_idx >= 0) dp[mm_idx] += dmm * dmm_dp;
+        } else {
+          dp[ia] += dd;
+          dp[ib] -= dd;
+        }
+        adv_sum += loss;
+      } else {
+        if (!p.targeted) {
+          loss = -logf(1.0f - py + 1e-6f);
+          dp[y] += 1.0f / (1.0f - py + 1e-6f) / bdiv;
+          sum_min += py; sum_max += pmaxnl;
+        } else if (torch_stack) {
+          loss = -logf(py + 1e-6f);
+          dp[y] += -1.0f / (py + 1e-6f) / bdiv;
+          sum_min += pmaxnl; sum_max += py;
+        } else {
+          loss = -logf(fmaxf(py, 1e-38f));  // sparse softmax cross entropy
+          dp[y] += -1.0f / fmaxf(py, 1e-38f) / bdiv;
+          sum_min += pmaxnl; sum_max += py;
+        }
+        adv_sum += loss / bdiv;
+      }
+      stash[0] = dd_logit;
+      stash[1] = __int_as_float(ia);
+      stash[2] = __int_as_float(ib);
+      const bool is_fooled = p.targeted ? (pred.i == y) : (pred.i != y);
+      fooled += is_fooled ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    // softmax backward: dz_k = p_k * (dp_k - sum_j dp_j p_j)  (+ direct logit terms)
+    float dot = 0.0f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) dot += dp[k] * prob[k];
+    const float ddl = stash[0];
+    const int ia = __float_as_int(stash[1]), ib = __float_as_int(stash[2]);
+    dot = block_reduce<float>(dot, shf, false);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float g = prob[k] * (dp[k] - dot);
+      if (p.use_logits && p.improve_loss) g += (k == ia ? ddl : 0.0f) - (k == ib ? ddl : 0.0f);
+      dlogits[static_cast<long long>(b) * K + k] = g * p.grad_scale;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    scalars[FAV_S_ADV_LOSS] = adv_sum;
+    scalars[FAV_S_FOOLED] = fooled;
+    scalars[FAV_S_SUM_P_MIN] = sum_min;
+    scalars[FAV_S_SUM_P_MAX] = sum_max;
+  }
+}
+
+int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
+                float* probs, float* dlogits, float* scalars, cudaStream_t s) {
+  loss_kernel<<<1, 512, 2 * K * sizeof(float), s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// stem backward without materialising dL/dx:
+//   g[t,c] = sum_{b,h,w} mask * dX  with dX = stem^T(G1).  By linearity the unmasked sum only needs
+//   the per-(t_o, border-class) sums S of G1; the (few) saturated entries are corrected exactly.
+// =============================================================================================
+__device__ __forceinline__ int border_class(int i, int n) {
+  return i == 0 ? 0 : (i == n - 2 ? 2 : (i == n - 1 ? 3 : 1));
+}
+
+__global__ void __launch_bounds__(128)
+stem_class_sums_kernel(const __nv_bfloat16* __restrict__ g1, float* __restrict__ S, int To, int Ho, int Wo) {
+  __shared__ float red[16][4][64];
+  const int ho = blockIdx.x % Ho;
+  const int to = blockIdx.x / Ho;
+  const int b = blockIdx.y;
+  const int cgp = threadIdx.x & 7;   // 8-channel group
+  const int pl = threadIdx.x >> 3;   // position lane 0..15
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.0f;
+  const __nv_bfloat16* rowp = g1 + (((static_cast<long long>(b) * To + to) * Ho + ho) * Wo) * 64;
+  for (int w = pl; w < Wo; w += 16) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(w) * 64 + cgp * 8));
+    const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                        bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+    const int wc = border_class(w, Wo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k == wc) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] += f[j];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[pl][k][cgp * 8 + j] = acc[k][j];
+  __syncthreads();
+  const int hc = border_class(ho, Ho);
+  for (int i = threadIdx.x; i < 256; i += 128) {
+    const int k = i >> 6, co = i & 63;
+    float sum = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sum += red[q][k][co];
+    if (sum != 0.0f) atomicAdd(&S[((to * 4 + hc) * 4 + k) * 64 + co], sum);
+  }
+}
+
+int launch_stem_class_sums(const __nv_bfloat16* g1, float* S, int B, int To, int Ho, int Wo, cudaStream_t s) {
+  FAV_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(To) * 16 * 64 * sizeof(float), s));
+  dim3 grid(To * Ho, B);
+  stem_class_sums_kernel<<<grid, 128, 0, s>>>(g1, S, To, Ho, Wo);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+__global__ void __launch_bounds__(256)
+stem_grad_delta_kernel(const float* __restrict__ S, const float* __restrict__ wc, float* __restrict__ grad,
+                       int T, int To, int pt) {
+  __shared__ float sh[8];
+  const int t = blockIdx.x / 3, c = blockIdx.x % 3;
+  float acc = 0.0f;
+  for (int kt = 0; kt < 7; ++kt) {
+    const int tt = t + pt - kt;
+    if (tt < 0 || (tt & 1)) continue;
+    const int to = tt >> 1;
+    if (to >= To) continue;
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+      const int cls = i >> 6, co = i & 63;
+      acc = fmaf(wc[((kt * 16 + cls) * 3 + c) * 64 + co], S[(to * 16 + cls) * 64 + co], acc);
+    }
+  }
+  acc = block_reduce<float>(acc, sh, false);
+  if (threadIdx.x == 0) grad[t * 3 + c] = acc;
+  (void)T;
+}
+
+int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, int To, int pt,
+                           cudaStream_t s) {
+  stem_grad_delta_kernel<<<T * 3, 256, 0, s>>>(S, wc, grad, T, To, pt);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// one warp per saturated pixel: recompute dX there exactly (gather over the <= 64 valid taps) and
+// subtract it from g[t,c]
+__global__ void __launch_bounds__(256)
+stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ w,
+                           const uint32_t* __restrict__ sat_list, const uint32_t* __restrict__ sat_count,
+                           uint32_t sat_capacity, float* __restrict__ grad, int T, int H, int W, int To,
+                           int Ho, int Wo, int pt, int ph, int pw) {
+  extern __shared__ float sacc[];  // [T*3]
+  for (int i = threadIdx.x; i < T * 3; i += blockDim.x) sacc[i] = 0.0f;
+  __syncthreads();
+  const uint32_t n = min(*sat_count, sat_capacity);
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
+    const uint32_t ent = sat_list[e];
+    const uint32_t cm = ent >> 28;
+    uint32_t pix = ent & 0x0fffffffu;
+    const int wx = pix % W; pix /= W;
+    const int hx = pix % H; pix /= H;
+    const int tx = pix % T;
+    const int b = pix / T;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    for (int kt = 0; kt < 7; ++kt) {
+      const int tt = tx + pt - kt;
+      if (tt < 0 || (tt & 1) || (tt >> 1) >= To) continue;
+      for (int kh = 0; kh < 7; ++kh) {
+        const int hh = hx + ph - kh;
+        if (hh < 0 || (hh & 1) || (hh >> 1) >= Ho) continue;
+        for (int kw = 0; kw < 7; ++kw) {
+          const int ww = wx + pw - kw;
+          if (ww < 0 || (ww & 1) || (ww >> 1) >= Wo) continue;
+          const long long off = (((static_cast<long long>(b) * To + (tt >> 1)) * Ho + (hh >> 1)) * Wo + (ww >> 1)) * 64;
+          const uint32_t gv = __ldg(reinterpret_cast<const uint32_t*>(g1 + off) + lane);
+          const float gx = bf16_lo(gv), gy = bf16_hi(gv);
+          const float* wp = w + static_cast<long long>((kt * 7 + kh) * 7 + kw) * 3 * 64 + lane * 2;
+          if (cm & 1u) { const float2 wv = __ldg(reinterpret_cast<const float2*>(wp)); a0 = fmaf(gx, wv.x, fmaf(gy, wv.y, a0)); }
+          if (cm & 2u) { const float2 wv = __ldg(reinterpret_cast<const float2*>(wp + 64)); a1 = fmaf(gx, wv.x, fmaf(gy, wv.y, a1)); }
+          if (cm & 4u) { const float2 wv = __ldg(reinterpret_cast<const float2*>(wp + 128)); a2 = fmaf(gx, wv.x, fmaf(gy, wv.y, a2)); }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      if (cm & 1u) atomicAdd(&sacc[tx * 3 + 0], -a0);
+      if (cm & 2u) atomicAdd(&sacc[tx * 3 + 1], -a1);
+      if (cm & 4u) atomicAdd(&sacc[tx * 3 + 2], -a2);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * 3; i += blockDim.x)
+    if (sacc[i] != 0.0f) atomicAdd(&grad[i], sacc[i]);
+}
+
+int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const uint32_t* sat_list,
+                               const uint32_t* sat_count, uint32_t sat_capacity, float* grad, int B, int T,
+                               int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw, cudaStream_t s) {
+  (void)B;
+  stem_sat_correction_kernel<<<296, 256, T * 3 * sizeof(float), s>>>(g1, w, sat_list, sat_count, sat_capacity,
+                                                                     grad, T, H, W, To, Ho, Wo, pt, ph, pw);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// (c) regulariser gradients + clip mask + Adam + metrics on delta [T,3]
+//   norm_reg / diff_norm_reg / laplacian_norm_reg, thickness, roughness:
+//     utils/kinetics_i3d_utils.py:177-200 (TF, on the raw delta);  model.py:198-209 (torch, on the
+//     clamped delta, weights beta1 / (1-beta1) passed in as beta1/beta2/beta3)
+//   loss = adv + beta0*(beta1*thick + beta2*diff + beta3*lap): single_video_npy.py:56-59
+//   Adam: tf.train.AdamOptimizer (single_video_npy.py:79-84) or torch.optim.Adam (model.py:542)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+delta_update_kernel(float* __restrict__ delta, const float* __restrict__ grad, float* __restrict__ m,
+                    float* __restrict__ v, int64_t* __restrict__ step, const fav_reg_params reg,
+                    const fav_adam_params adam, float adv_flag, float* __restrict__ scalars, int T) {
+  extern __shared__ float sd[];  // [T*3] regularised copy of delta
+  __shared__ float sh[8];
+  const int N = T * 3;
+  const bool torch_stack = adam.stack == FAV_STACK_TORCH;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float d = delta[i];
+    sd[i] = torch_stack ? fminf(fmaxf(d, -reg.delta_clip), reg.delta_clip) : d;
+  }
+  __syncthreads();
+  float s_norm = 0.0f, s_diff = 0.0f, s_lap = 0.0f, s_abs = 0.0f, s_rough = 0.0f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int t = i / 3, c = i % 3;
+    const float d0 = sd[i];
+    const float dm = sd[((t + T - 1) % T) * 3 + c];
+    const float dp = sd[((t + 1) % T) * 3 + c];
+    const float df = d0 - dm;
+    const float lp = -2.0f * d0 + dm + dp;
+    s_norm += d0 * d0;
+    s_diff += df * df;
+    s_lap += lp * lp;
+    // metrics: TF on the raw delta, torch on the clamped one (model.py:1114-1116)
+    s_abs += fabsf(d0);
+    s_rough += fabsf(df);
+  }
+  s_norm = block_reduce<float>(s_norm, sh, false);
+  s_diff = block_reduce<float>(s_diff, sh, false);
+  s_lap = block_reduce<float>(s_lap, sh, false);
+  s_abs = block_reduce<float>(s_abs, sh, false);
+  s_rough = block_reduce<float>(s_rough, sh, false);
+  const float invN = 1.0f / static_cast<float>(N);
+  const int64_t tstep = *step + 1;
+  const float b1t = powf(adam.b1, static_cast<float>(tstep));
+  const float b2t = powf(adam.b2, static_cast<float>(tstep));
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int t = i / 3, c = i % 3;
+    const int tm = (t + T - 1) % T, tp = (t + 1) % T;
+    const int tmm = (t + T - 2) % T, tpp = (t + 2) % T;
+    const float d0 = sd[i], dm = sd[tm * 3 + c], dp = sd[tp * 3 + c];
+    const float dmm = sd[tmm * 3 + c], dpp = sd[tpp * 3 + c];
+    // d/d delta_t of sum_s (d_s - d_{s-1})^2 = 2 (D_t - D_{t+1}),  D_t = d_t - d_{t-1}
+    const float g_diff = 2.0f * ((d0 - dm) - (dp - d0));
+    // d/d delta_t of sum_s L_s^2 = 2 (-2 L_t + L_{t-1} + L_{t+1}),  L_t = -2 d_t + d_{t-1} + d_{t+1}
+    const float l0 = -2.0f * d0 + dm + dp;
+    const float lm = -2.0f * dm + dmm + d0;
+    const float lp = -2.0f * dp + d0 + dpp;
+    const float g_lap = 2.0f * (-2.0f * l0 + lm + lp);
+    const float g_norm = 2.0f * d0;
+    float g_reg = reg.beta0 * invN * (reg.beta1 * g_norm + reg.beta2 * g_diff + reg.beta3 * g_lap);
+    const float raw = delta[i];
+    const bool inside = fabsf(raw) <= reg.delta_clip;  // clip_by_value / clamp pass the gradient inclusively
+    if (torch_stack && !inside) g_reg = 0.0f;
+    const float g_data = inside ? adv_flag * grad[i] : 0.0f;
+    const float g = g_data + g_reg;
+    const float mi = adam.b1 * m[i] + (1.0f - adam.b1) * g;
+    const float vi = adam.b2 * v[i] + (1.0f - adam.b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    float upd;
+    if (torch_stack) {
+      upd = (adam.lr / (1.0f - b1t)) * mi / (sqrtf(vi) / sqrtf(1.0f - b2t) + adam.eps);
+    } else {
+      const float lr_t = adam.lr * sqrtf(1.0f - b2t) / (1.0f - b1t);
+      upd = lr_t * mi / (sqrtf(vi) + adam.eps);
+    }
+    delta[i] = raw - upd;
+  }
+  if (threadIdx.x == 0) {
+    *step = tstep;
+    const float nr = s_norm * invN + 1e-12f, dr = s_diff * invN + 1e-12f, lr_ = s_lap * invN + 1e-12f;
+    scalars[FAV_S_NORM_REG] = nr;
+    scalars[FAV_S_DIFF_REG] = dr;
+    scalars[FAV_S_LAP_REG] = lr_;
+    scalars[FAV_S_THICKNESS] = s_abs * invN;
+    scalars[FAV_S_ROUGHNESS] = s_rough * invN;
+    scalars[FAV_S_TOTAL_LOSS] =
+        scalars[FAV_S_ADV_LOSS] + reg.beta0 * (reg.beta1 * nr + reg.beta2 * dr + reg.beta3 * lr_);
+  }
+}
+
+int launch_delta_update(float* delta, const float* grad, float* m, float* v, int64_t* step,
+                        const fav_reg_params& reg, const fav_adam_params& adam, float adv_flag,
+                        float* scalars, int T, cudaStream_t s) {
+  delta_update_kernel<<<1, 256, T * 3 * sizeof(float), s>>>(delta, grad, m, v, step, reg, adam, adv_flag,
+                                                            scalars, T);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers for tests / debug reads
+// ---------------------------------------------------------------------------------------------
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, long long cs, int coff, int C,
+                                   long long total, float* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i / C;
+  const int c = static_cast<int>(i % C);
+  dst[i] = __bfloat162float(src[p * cs + coff + c]);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                   long long cs, int coff, int C, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i / C;
+  const int c = static_cast<int>(i % C);
+  dst[p * cs + coff + c] = __float2bfloat16_rn(src[i]);
+}
+int launch_bf16_to_f32(const __nv_bfloat16* src, long long cs, int coff, int C, long long npos, float* dst,
+                       cudaStream_t s) {
+  const long long total = npos * C;
+  bf16_to_f32_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(src, cs, coff, C, total, dst);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long cs, int coff, int C, long long npos,
+                       cudaStream_t s) {
+  const long long total = npos * C;
+  f32_to_bf16_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(src, dst, cs, coff, C, total);
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+}  // namespace fav

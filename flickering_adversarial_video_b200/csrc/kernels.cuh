@@ -1,0 +1,60 @@
+// kernels.cuh — HBM-bound kernels of the attack loop (everything that is not a GEMM).
+#pragma once
+#include "fav_common.cuh"
+
+namespace fav {
+
+struct PoolGeom {
+  int B, T, H, W, C;       // input
+  int To, Ho, Wo;          // output (TF SAME: ceil(in/stride))
+  int kt, kh, kw, st, sh, sw;
+  int pt, ph, pw;          // pad_before (TF SAME: floor(pad_total/2))
+};
+PoolGeom make_pool_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh, int sw);
+
+// (a) flicker apply. Writes the stem input x' (bf16 RGBX, W padded) and optionally the uint8 /
+// fp32 adversarial video; appends saturated entries to sat_list (count in *sat_count).
+int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
+                 __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
+                 uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
+                 int W, cudaStream_t s);
+
+// delta-dependent stem bias table [To][4][4][64]
+int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc /*[7][16][3][64]*/,
+                     const float* bnbias /*[64]*/, float* table, int T, int To, int pt, cudaStream_t s);
+
+int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
+                       cudaStream_t s);
+int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
+                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
+                       cudaStream_t s);
+
+// head: feat[b,c] = sum_t coef[t]*sum_hw Y / (HW*2*(T5-1)); logits = feat @ Wl + bl
+int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float* feat,
+                    const float* wl /*[C][K]*/, const float* bl, int K, float* logits, cudaStream_t s);
+int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfloat16* y,
+                    __nv_bfloat16* gy, float* dfeat, int B, int T5, int HW, int C, cudaStream_t s);
+
+int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
+                float* probs, float* dlogits, float* scalars, cudaStream_t s);
+
+// stem backward: class sums of G1, then g[T,3], then saturated-entry corrections
+int launch_stem_class_sums(const __nv_bfloat16* g1, float* S /*[To][16][64]*/, int B, int To, int Ho,
+                           int Wo, cudaStream_t s);
+int launch_stem_grad_delta(const float* S, const float* wc, float* grad /*[T][3]*/, int T, int To, int pt,
+                           cudaStream_t s);
+int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w /*[343][3][64] folded*/,
+                               const uint32_t* sat_list, const uint32_t* sat_count, uint32_t sat_capacity,
+                               float* grad, int B, int T, int H, int W, int To, int Ho, int Wo, int pt,
+                               int ph, int pw, cudaStream_t s);
+
+int launch_delta_update(float* delta, const float* grad, float* m, float* v, int64_t* step,
+                        const fav_reg_params& reg, const fav_adam_params& adam, float adv_flag,
+                        float* scalars, int T, cudaStream_t s);
+
+int launch_bf16_to_f32(const __nv_bfloat16* src, long long cs, int coff, int C, long long npos, float* dst,
+                       cudaStream_t s);
+int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long cs, int coff, int C, long long npos,
+                       cudaStream_t s);
+
+}  // namespace fav

@@ -1,0 +1,149 @@
+"""Thin host-side wrapper of the libfav C-ABI: one `FlickerEngine` per GPU (per rank).
+
+PyTorch is used for device memory and streams only; every kernel on the hot path lives in
+libfav.so.  Replaces the TF session + graph of utils/kinetics_i3d_utils.py:76-208.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class FlickerEngine:
+    def __init__(self, batch, frames, height=224, width=224, num_classes=400, device=0):
+        if not torch.cuda.is_available():
+            raise L.FavError("FlickerEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device("cuda", device)
+        self.B, self.T, self.H, self.W, self.K = batch, frames, height, width, num_classes
+        desc = L.NetDesc(L.FAV_NET_I3D, batch, frames, height, width, num_classes)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.fav_create(C.byref(h), device, C.byref(desc)), "fav_create")
+        self.h = h
+        self.scalars = torch.zeros(L.S_COUNT, dtype=torch.float32, device=self.device)
+        self.logits = torch.zeros((batch, num_classes), dtype=torch.float32, device=self.device)
+        self.probs = torch.zeros((batch, num_classes), dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros((frames, 3), dtype=torch.float32, device=self.device)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.fav_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.fav_device_bytes(self.h))
+
+    def load_weights(self, weights):
+        """weights: {tf variable name: float32 ndarray} (reference ckpt naming/layout)."""
+        n = len(weights)
+        arr = (L.Tensor * n)()
+        keep = []
+        for i, (name, a) in enumerate(weights.items()):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            arr[i].name = name.encode()
+            arr[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
+            arr[i].ndim = min(a.ndim, 5)
+            dims = list(a.shape)[:5] + [1] * (5 - min(a.ndim, 5))
+            for j in range(5):
+                arr[i].dims[j] = dims[j]
+        with torch.cuda.device(self.device):
+            L.check(self.lib.fav_load_weights(self.h, arr, n), "fav_load_weights")
+
+    # ---- hot path ------------------------------------------------------------------------
+    def apply(self, clip, delta, adv_flag=1.0, delta_clip=0.4, adv_u8=None, adv_f32=None, stream=None):
+        assert clip.is_cuda and clip.is_contiguous() and tuple(clip.shape) == (self.B, self.T, self.H, self.W, 3)
+        assert delta.is_cuda and delta.dtype == torch.float32 and delta.numel() == self.T * 3
+        dt = L.FAV_U8 if clip.dtype == torch.uint8 else L.FAV_F32
+        if dt == L.FAV_F32:
+            assert clip.dtype == torch.float32
+        L.check(self.lib.fav_apply_flicker(self.h, L.ptr(clip), dt, L.ptr(delta), adv_flag, delta_clip,
+                                           L.ptr(adv_u8), L.ptr(adv_f32), L.stream_ptr(stream)), "fav_apply_flicker")
+
+    def forward(self, stream=None):
+        L.check(self.lib.fav_forward(self.h, L.ptr(self.logits), L.stream_ptr(stream)), "fav_forward")
+        return self.logits
+
+    def loss(self, labels, improve_loss=True, targeted=False, use_logits=False, margin=0.05, grad_scale=1.0,
+             global_batch=0, stack=L.FAV_STACK_TF, stream=None):
+        assert labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == self.B
+        p = L.LossParams(int(improve_loss), int(targeted), int(use_logits), margin, grad_scale, global_batch, stack)
+        L.check(self.lib.fav_loss(self.h, L.ptr(labels), C.byref(p), L.ptr(self.probs), L.ptr(self.scalars),
+                                  L.stream_ptr(stream)), "fav_loss")
+        return self.scalars
+
+    def backward(self, stream=None):
+        L.check(self.lib.fav_backward_delta(self.h, L.ptr(self.grad), L.stream_ptr(stream)), "fav_backward_delta")
+        return self.grad
+
+    def update(self, delta, grad, m, v, step, beta0, beta1, beta2, beta3, lr=1e-3, delta_clip=0.4,
+               b1=0.9, b2=0.999, eps=1e-8, stack=L.FAV_STACK_TF, stream=None):
+        reg = L.RegParams(beta0, beta1, beta2, beta3, delta_clip)
+        adam = L.AdamParams(lr, b1, b2, eps, stack)
+        L.check(self.lib.fav_delta_update(self.h, L.ptr(delta), L.ptr(grad), L.ptr(m), L.ptr(v), L.ptr(step),
+                                          C.byref(reg), C.byref(adam), L.ptr(self.scalars), L.stream_ptr(stream)),
+                "fav_delta_update")
+        return self.scalars
+
+    def read(self, name, shape):
+        """Debug read of an internal activation / gradient buffer as fp32 [B,T,H,W,C]."""
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        n = self.lib.fav_debug_read(self.h, name.encode(), L.ptr(out), out.numel(), L.stream_ptr())
+        if n < 0:
+            raise L.FavError(f"fav_debug_read({name}): {L.last_error()}")
+        assert n == out.numel(), (name, n, out.numel())
+        return out
+
+
+# ---- op-level wrappers used by the parity tests ---------------------------------------------
+def op_conv3d(x_bf16, w_tf, bias=None, relu=False, dgrad=False, relu_src=None, y=None, y_coff=0, x_coff=0,
+              cin=None, cout=None):
+    """x_bf16 [B,T,H,W,Cs] bf16 cuda; w_tf [kt,kh,kw,cin,cout] float32 (TF layout)."""
+    lib = L.load()
+    B, T, H, W, xcs = x_bf16.shape
+    kt, kh, kw, wcin, wcout = w_tf.shape
+    cin = wcin if cin is None else cin
+    cout = wcout if cout is None else cout
+    n_out = cin if dgrad else cout
+    if y is None:
+        y = torch.zeros((B, T, H, W, n_out), dtype=torch.bfloat16, device=x_bf16.device)
+    w_host = np.ascontiguousarray(w_tf.detach().cpu().numpy(), dtype=np.float32)
+    b_host = None if bias is None else np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
+    st = lib.fav_op_conv3d(
+        x_bf16.device.index or 0, L.ptr(x_bf16), xcs, x_coff,
+        w_host.ctypes.data_as(C.c_void_p), None if b_host is None else b_host.ctypes.data_as(C.c_void_p),
+        kt, kh, kw, cin, cout, L.ptr(y), y.shape[-1], y_coff, B, T, H, W, int(relu), int(dgrad),
+        L.ptr(relu_src), 0 if relu_src is None else relu_src.shape[-1], 0, L.stream_ptr())
+    L.check(st, "fav_op_conv3d")
+    return y
+
+
+def op_maxpool3d(x_bf16, k, s):
+    lib = L.load()
+    B, T, H, W, Cc = x_bf16.shape
+    To, Ho, Wo = -(-T // s[0]), -(-H // s[1]), -(-W // s[2])
+    y = torch.empty((B, To, Ho, Wo, Cc), dtype=torch.bfloat16, device=x_bf16.device)
+    idx = torch.empty((B, To, Ho, Wo, Cc), dtype=torch.uint8, device=x_bf16.device)
+    L.check(lib.fav_op_maxpool3d(x_bf16.device.index or 0, L.ptr(x_bf16), L.ptr(y), L.ptr(idx), B, T, H, W, Cc,
+                                 k[0], k[1], k[2], s[0], s[1], s[2], L.stream_ptr()), "fav_op_maxpool3d")
+    return y, idx
+
+
+def op_maxpool3d_bwd(dy, idx, in_shape, k, s, add=None, relu_src=None):
+    lib = L.load()
+    B, T, H, W, Cc = in_shape
+    dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    L.check(lib.fav_op_maxpool3d_bwd(dy.device.index or 0, L.ptr(dy), L.ptr(idx), L.ptr(add), L.ptr(relu_src),
+                                     L.ptr(dx), B, T, H, W, Cc, k[0], k[1], k[2], s[0], s[1], s[2],
+                                     L.stream_ptr()), "fav_op_maxpool3d_bwd")
+    return dx

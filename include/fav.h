@@ -1,0 +1,190 @@
+/*
+ * fav.h — C-ABI of the B200-native flickering-attack engine (libfav.so).
+ *
+ * The reference (roiponytch/Flickering_Adversarial_Video) has no FFI: its hot path is a Python
+ * attribute bag of TF tensors (`utils/kinetics_i3d_utils.py:76-307`, class kinetics_i3d) driven by
+ * `sess.run(train_op …)` (`i3d_adversarial_main_single_video_npy.py:211-215`).  This header is the
+ * boundary a maintainer binds with ctypes; every entry point names the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - every `void*`/`float*` marked DEVICE is a caller-owned device pointer on the handle's GPU
+ *     (e.g. a torch tensor's data_ptr()); HOST pointers are plain host memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all hot-path calls are
+ *     asynchronous on it and are CUDA-graph capturable (no allocation, no sync inside);
+ *   - return value: 0 (FAV_OK) or a negative fav_status; never throws across the boundary;
+ *     `fav_last_error` returns a thread-local message for the last failing call;
+ *   - a handle is bound to one device and is not thread-safe (one handle per rank);
+ *   - the library owns only its activation/gradient arena and packed weights (allocated in
+ *     fav_create / fav_load_weights).
+ *
+ * Activation layout inside the library: NDHWC bf16, channel stride padded to a multiple of 8.
+ */
+#ifndef FAV_H_
+#define FAV_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fav_handle fav_handle;
+
+typedef enum {
+  FAV_OK = 0,
+  FAV_ERR_ARG = -1,      /* bad argument / unsupported shape */
+  FAV_ERR_CUDA = -2,     /* a CUDA runtime/driver call failed */
+  FAV_ERR_STATE = -3,    /* call order violated (e.g. forward before load_weights) */
+  FAV_ERR_NOGPU = -4,    /* no CUDA device / not an sm_100 device */
+  FAV_ERR_MISSING = -5   /* a required named tensor was not supplied */
+} fav_status;
+
+typedef enum { FAV_NET_I3D = 0 } fav_arch;
+typedef enum { FAV_U8 = 0, FAV_F32 = 1 } fav_dtype;
+
+/* Which framework's semantics to follow where the two reference stacks differ
+ * (SURVEY App. B.5/B.6): regulariser weighting, Adam epsilon placement. */
+typedef enum { FAV_STACK_TF = 0, FAV_STACK_TORCH = 1 } fav_stack;
+
+typedef struct {
+  int32_t arch;         /* fav_arch */
+  int32_t batch;        /* clips resident per step on this GPU */
+  int32_t frames;       /* T  (reference constant _SAMPLE_VIDEO_FRAMES=90, kinetics_i3d_utils.py:12) */
+  int32_t height;       /* 224 */
+  int32_t width;        /* 224 */
+  int32_t num_classes;  /* 400 (kinetics_i3d_utils.py:19) */
+} fav_net_desc;
+
+/* A named fp32 HOST tensor in the reference's native layout (TF ckpt variable names,
+ * `RGB/inception_i3d/<unit>/conv_3d/w` [kt,kh,kw,Cin,Cout], `…/batch_norm/{beta,moving_mean,
+ * moving_variance}` [1,1,1,1,C] or [C], `…/Logits/Conv3d_0c_1x1/conv_3d/{w,b}`), cf.
+ * utils/kinetics_i3d_utils.py:41-62. */
+typedef struct {
+  const char* name;
+  const float* data;   /* HOST */
+  int32_t ndim;
+  int64_t dims[5];
+} fav_tensor;
+
+/* Adversarial-loss selection: improve_adversarial_loss (kinetics_i3d_utils.py:253-288) or
+ * ce_adversarial_loss (:290-307). */
+typedef struct {
+  int32_t improve_loss;   /* IMPROVE_ADV_LOSS */
+  int32_t targeted;       /* TARGETED_ATTACK  */
+  int32_t use_logits;     /* USE_LOGITS       */
+  float   margin;         /* PROB_MARGIN      */
+  float   grad_scale;     /* multiplies dloss/dlogits (1/n_ranks for the mean-reduced CE loss when sharded) */
+  int32_t global_batch;   /* batch over all ranks (CE mean divisor); 0 => local batch */
+  int32_t stack;          /* fav_stack: which reference stack's selection rules */
+} fav_loss_params;
+
+/* Regulariser weights: loss = adv + beta0*(beta1*thick + beta2*diff + beta3*lap)
+ * (i3d_adversarial_main_single_video_npy.py:56-59). */
+typedef struct {
+  float beta0, beta1, beta2, beta3;
+  float delta_clip;       /* 0.4  (kinetics_i3d_utils.py:104-105) */
+} fav_reg_params;
+
+typedef struct {
+  float lr, b1, b2, eps;  /* tf.train.AdamOptimizer defaults 1e-3, .9, .999, 1e-8 */
+  int32_t stack;          /* fav_stack: TF => eps outside the bias correction */
+} fav_adam_params;
+
+/* Layout of the per-step device scalar block written by fav_loss / fav_delta_update
+ * (floats; indices below).  Reference fetch list: single_video_npy.py:213-215. */
+enum {
+  FAV_S_ADV_LOSS = 0,     /* adversarial loss (sum or mean over the local batch) */
+  FAV_S_FOOLED = 1,       /* # local clips with argmax != label (or == target) */
+  FAV_S_SUM_P_MIN = 2,    /* sum of to_min_prob */
+  FAV_S_SUM_P_MAX = 3,    /* sum of to_max_prob */
+  FAV_S_NORM_REG = 4,     /* norm_reg        (+1e-12) */
+  FAV_S_DIFF_REG = 5,     /* diff_norm_reg   (+1e-12) */
+  FAV_S_LAP_REG = 6,      /* laplacian_norm_reg (+1e-12) */
+  FAV_S_THICKNESS = 7,    /* mean|delta|  (before the update, as the reference fetches) */
+  FAV_S_ROUGHNESS = 8,    /* mean|delta - roll(delta,1)| */
+  FAV_S_TOTAL_LOSS = 9,   /* adv + beta0*reg (local adv term) */
+  FAV_S_SAT_COUNT = 10,   /* # (pixel,channel) entries where the [-1,1] clip fired */
+  FAV_S_COUNT = 16
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int fav_create(fav_handle** out, int device, const fav_net_desc* desc);
+int fav_destroy(fav_handle* h);
+const char* fav_last_error(void);
+/* bytes of device memory owned by the handle (arena + weights) */
+int64_t fav_device_bytes(const fav_handle* h);
+
+/* Fold BN into conv weights, cast to bf16, pack for the tensor-core kernels.
+ * Replaces tf.train.Saver.restore (kinetics_i3d_utils.py:41-62) + snt.BatchNorm inference
+ * (i3d.py:66-68). */
+int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n);
+
+/* ---- hot path -------------------------------------------------------------------------- */
+/* K1: adv = clip(x + adv_flag*clip(delta,+-delta_clip), -1, 1) with x = u8/128-1
+ * (pre_process_rgb_flow.py:234; kinetics_i3d_utils.py:104-105,139-142).
+ *   clip     DEVICE [B,T,H,W,3] u8 or f32 (already normalised, cf. single_video_npy.py:121)
+ *   delta    DEVICE [T,3] f32 (the reference's eps_rgb [T,1,1,3])
+ *   adv_u8   DEVICE [B,T,H,W,3] or NULL — ((adv+1.0)*127.5).astype(uint8)  (stats_plots.py:57), bit-exact
+ *   adv_f32  DEVICE [B,T,H,W,3] or NULL — the reference's `adversarial_inputs_rgb`
+ * Also fills the engine's stem input and the saturated-entry list used by the backward pass. */
+int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, const float* delta,
+                      float adv_flag, float delta_clip, uint8_t* adv_u8, float* adv_f32, void* stream);
+
+/* Forward of the frozen network on the last applied input; logits DEVICE [B,num_classes] f32.
+ * Replaces rgb_model(adversarial_inputs_rgb) (kinetics_i3d_utils.py:150; i3d.py:144-474). */
+int fav_forward(fav_handle* h, float* logits, void* stream);
+
+/* softmax + adversarial loss + dloss/dlogits (kept inside the handle).
+ *   labels DEVICE [B] int64;  probs DEVICE [B,num_classes] f32 or NULL;
+ *   scalars DEVICE [FAV_S_COUNT] f32. */
+int fav_loss(fav_handle* h, const int64_t* labels, const fav_loss_params* p, float* probs,
+             float* scalars, void* stream);
+
+/* Backward-to-input and the H*W*B collapse: grad DEVICE [T,3] f32 receives
+ * sum_{b,h,w} mask * dL/dx  (the data term of compute_gradients(loss, var_list=perturbation),
+ * single_video_npy.py:82), *before* the |delta|<=clip mask and regulariser terms. */
+int fav_backward_delta(fav_handle* h, float* grad, void* stream);
+
+/* (c) regulariser gradients + clip mask + Adam + metrics on delta [T,3]
+ * (kinetics_i3d_utils.py:177-200; single_video_npy.py:56-59,79-84).
+ *   grad is the (all-reduced) data gradient from fav_backward_delta;
+ *   step DEVICE int64 counter (incremented), m/v DEVICE [T,3] Adam slots. */
+int fav_delta_update(fav_handle* h, float* delta, const float* grad, float* m, float* v,
+                     int64_t* step, const fav_reg_params* reg, const fav_adam_params* adam,
+                     float* scalars, void* stream);
+
+/* ---- op-level entry points (layer-wise parity tests; same kernels the engine runs) ------- */
+/* stride-1 SAME Conv3d (+bias, +ReLU) on NDHWC bf16 via the tcgen05 implicit-GEMM kernel.
+ *   x [B,T,H,W,x_cs] (channels x_coff..x_coff+cin), w HOST f32 [kt,kh,kw,cin,cout] (TF layout),
+ *   bias HOST f32 [cout] or NULL, y [B,T,H,W,y_cs] (channels y_coff..y_coff+cout).
+ *   dgrad != 0: computes the data gradient instead (x is dY with cout channels, y is dX with cin);
+ *   relu_src (DEVICE bf16, same geometry as y, stride relu_cs/offset relu_coff) != NULL multiplies
+ *   the result by (relu_src > 0). */
+int fav_op_conv3d(int device, const void* x, int64_t x_cs, int64_t x_coff,
+                  const float* w, const float* bias, int kt, int kh, int kw, int cin, int cout,
+                  void* y, int64_t y_cs, int64_t y_coff, int B, int T, int H, int W,
+                  int relu, int dgrad, const void* relu_src, int64_t relu_cs, int64_t relu_coff,
+                  void* stream);
+
+/* tf.nn.max_pool3d SAME on NDHWC bf16 (i3d.py:174 etc.); idx receives the arg-max tap (u8). */
+int fav_op_maxpool3d(int device, const void* x, void* y, uint8_t* idx, int B, int T, int H, int W,
+                     int C, int kt, int kh, int kw, int st, int sh, int sw, void* stream);
+/* its backward: dx = (add ? add : 0) + scatter(dy) ; then * (relu_src>0) if relu_src != NULL */
+int fav_op_maxpool3d_bwd(int device, const void* dy, const uint8_t* idx, const void* add,
+                         const void* relu_src, void* dx, int B, int T, int H, int W, int C,
+                         int kt, int kh, int kw, int st, int sh, int sw, void* stream);
+
+/* debug/introspection: copy a named internal activation (bf16 -> f32, NDHWC, unpadded channels)
+ * to a DEVICE f32 buffer; returns element count or <0.  Names follow i3d.py end points
+ * ("Conv3d_1a_7x7", "Mixed_3b", ...), prefix "grad:" for the gradient buffer. */
+int64_t fav_debug_read(fav_handle* h, const char* name, float* out, int64_t capacity, void* stream);
+
+/* library build info: "sm_100a;<compile date>" */
+const char* fav_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FAV_H_ */

@@ -1,0 +1,159 @@
+"""-m gpu: whole-path parity of the engine (through the C-ABI) against the CPU oracle on identical
+seeded inputs and random-init weights (north_star gates: uint8 adversarial video bit-exact; logits
+within 1e-2 relative with identical top-1; dL/d-delta cosine >= 0.999)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+T_SMALL = 16   # smallest clip length the head accepts (T5 = 2); keeps the CPU oracle at seconds
+
+
+def _report(line):
+    print(line)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "i3d_parity.log"), "a") as f:
+            f.write(line + "\n")
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.engine import FlickerEngine
+    from oracle import oracle_i3d
+    torch.manual_seed(0)
+    weights = synthetic.i3d_weights(seed=0)
+    B = 2
+    clip = synthetic.clips_u8(B, T_SMALL, seed=1001)
+    delta = synthetic.delta_uniform(T_SMALL, seed=7, lo=-0.05, hi=0.05)
+    eng = FlickerEngine(B, T_SMALL)
+    eng.load_weights(weights)
+    model = oracle_i3d.OracleI3D(weights)
+    return dict(weights=weights, clip=clip, delta=delta, eng=eng, model=model, B=B)
+
+
+def test_apply_bit_exact(setup):
+    """uint8 adversarial video == ((clip(x/128-1+clip(d,+-0.4),-1,1)+1.0)*127.5).astype(uint8)"""
+    from flickering_adversarial_video_b200 import synthetic
+    from oracle import oracle_i3d
+    eng = setup["eng"]
+    for name, clip, delta in [
+        ("lowpass", setup["clip"], synthetic.delta_uniform(T_SMALL, seed=7)),          # |delta| up to 0.5 > clip
+        ("extreme", synthetic.clips_u8_extreme(setup["B"], T_SMALL), synthetic.delta_uniform(T_SMALL, seed=8)),
+    ]:
+        adv_u8 = torch.zeros_like(clip, device="cuda")
+        adv_f32 = torch.zeros(clip.shape, dtype=torch.float32, device="cuda")
+        eng.apply(clip.cuda(), delta.cuda(), adv_u8=adv_u8, adv_f32=adv_f32)
+        torch.cuda.synchronize()
+        ref = oracle_i3d.apply_flicker(oracle_i3d.normalize_u8(clip), delta)
+        ref_u8 = oracle_i3d.quantize_u8(ref)
+        assert np.array_equal(adv_u8.cpu().numpy(), ref_u8), f"{name}: uint8 adversarial video not bit-exact"
+        assert torch.equal(adv_f32.cpu(), ref), f"{name}: fp32 adversarial video not bit-exact"
+
+
+def test_forward_logits_and_layers(setup):
+    eng, model = setup["eng"], setup["model"]
+    from oracle import oracle_i3d
+    clip, delta = setup["clip"], setup["delta"]
+    eng.apply(clip.cuda(), delta.cuda())
+    logits = eng.forward().cpu()
+    torch.cuda.synchronize()
+    eps = {}
+    with torch.no_grad():
+        ref_logits = model.forward(oracle_i3d.apply_flicker(oracle_i3d.normalize_u8(clip), delta), endpoints=eps)
+    worst = 0.0
+    for name, ref in eps.items():
+        got = eng.read(name, tuple(ref.shape)).cpu()
+        rel = float((got - ref).norm() / (ref.norm() + 1e-12))
+        mx = float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
+        _report(f"layer {name:20s} rel_l2={rel:.4e} max_rel={mx:.4e} ref_rms={float(ref.pow(2).mean().sqrt()):.4g}")
+        worst = max(worst, rel)
+    rel = float((logits - ref_logits).abs().max() / ref_logits.abs().max())
+    _report(f"logits max rel err {rel:.4e}; top1 engine {logits.argmax(-1).tolist()} oracle {ref_logits.argmax(-1).tolist()}"
+            f" logits std {float(ref_logits.std()):.3g}")
+    assert worst < 2e-2, f"layer-wise relative L2 error {worst}"
+    assert rel <= 1e-2
+    assert logits.argmax(-1).tolist() == ref_logits.argmax(-1).tolist()
+
+
+@pytest.mark.parametrize("loss_kind", ["improve_prob", "ce"])
+def test_delta_gradient_cosine(setup, loss_kind):
+    eng, model = setup["eng"], setup["model"]
+    from oracle import oracle_i3d
+    clip, delta = setup["clip"], setup["delta"]
+    x = oracle_i3d.normalize_u8(clip)
+    with torch.no_grad():
+        labels = model.forward(x).argmax(-1)   # the reference skips clean-misclassified clips
+    cfg = dict(improve_loss=loss_kind == "improve_prob", targeted=False, use_logits=False, margin=0.05,
+               beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5, lr=1e-3)
+    ref = oracle_i3d.attack_step(model, x, labels, delta, cfg)
+    eng.apply(clip.cuda(), delta.cuda())
+    eng.forward()
+    sc = eng.loss(labels.cuda(), improve_loss=cfg["improve_loss"], margin=0.05)
+    g = eng.backward().cpu()
+    torch.cuda.synchronize()
+    sc = sc.cpu()
+    gr = ref["grad_data"]
+    cos = float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30))
+    _report(f"[{loss_kind}] adv_loss engine {float(sc[0]):.6f} oracle {ref['adv_loss']:.6f}; "
+            f"|g| engine {float(g.norm()):.4e} oracle {float(gr.norm()):.4e}; cosine {cos:.6f}")
+    assert abs(float(sc[0]) - ref["adv_loss"]) <= 1e-2 * max(1e-3, abs(ref["adv_loss"]))
+    assert cos >= 0.999
+    assert abs(float(g.norm()) / float(gr.norm()) - 1.0) < 0.05
+
+
+def test_saturated_pixels_gradient(setup):
+    """many range-clipped pixels: the exact per-entry corrections must keep the gradient right"""
+    eng, model = setup["eng"], setup["model"]
+    from flickering_adversarial_video_b200 import synthetic
+    from oracle import oracle_i3d
+    clip = synthetic.clips_u8_extreme(setup["B"], T_SMALL)
+    delta = synthetic.delta_uniform(T_SMALL, seed=11, lo=-0.3, hi=0.3)
+    x = oracle_i3d.normalize_u8(clip)
+    with torch.no_grad():
+        labels = model.forward(x).argmax(-1)
+    cfg = dict(improve_loss=False, beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5)
+    ref = oracle_i3d.attack_step(model, x, labels, delta, cfg, data_grad_only=True)
+    eng.apply(clip.cuda(), delta.cuda())
+    eng.forward()
+    eng.loss(labels.cuda(), improve_loss=False)
+    g = eng.backward().cpu()
+    gr = ref["grad_data"]
+    cos = float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30))
+    _report(f"[saturated] |g| engine {float(g.norm()):.4e} oracle {float(gr.norm()):.4e}; cosine {cos:.6f}")
+    assert cos >= 0.999
+
+
+def test_delta_update_matches_oracle(setup):
+    """regulariser gradients + clip mask + TF Adam + metrics (kernel c) for a few steps"""
+    eng = setup["eng"]
+    from oracle import oracle_i3d
+    T = T_SMALL
+    g = torch.Generator().manual_seed(3)
+    delta = (torch.rand((T, 3), generator=g) - 0.5) * 0.9      # some |delta| > 0.4
+    cfg = dict(beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5, lr=1e-3)
+    opt = oracle_i3d.TFAdam((T, 3))
+    d_ref = delta.clone()
+    d_dev = delta.clone().cuda()
+    m = torch.zeros((T, 3), device="cuda")
+    v = torch.zeros((T, 3), device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(5):
+        gd = torch.randn((T, 3), generator=g) * 0.01
+        # oracle: total gradient = clip-masked data gradient + regulariser gradient on the raw delta
+        dd = d_ref.clone().requires_grad_(True)
+        nr, dr, lr_, th, ro = oracle_i3d.regularizers(dd)
+        reg = cfg["beta0"] * (cfg["beta1"] * nr + cfg["beta2"] * dr + cfg["beta3"] * lr_)
+        (g_reg,) = torch.autograd.grad(reg, dd)
+        g_tot = gd * (d_ref.abs() <= 0.4) + g_reg
+        d_ref = opt.step(d_ref, g_tot)
+        sc = eng.update(d_dev, gd.cuda(), m, v, step, 1.0, 0.5, 0.5, 0.5).cpu()
+        assert torch.allclose(d_dev.cpu(), d_ref, rtol=1e-5, atol=1e-7), f"delta diverged at step {it}"
+        assert abs(float(sc[4]) - float(nr)) < 1e-6 and abs(float(sc[5]) - float(dr)) < 1e-6
+        assert abs(float(sc[6]) - float(lr_)) < 1e-6
+        assert abs(float(sc[7]) - float(th)) < 1e-6 and abs(float(sc[8]) - float(ro)) < 1e-6
+    assert int(step.item()) == 5
