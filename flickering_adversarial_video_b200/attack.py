@@ -1,0 +1,157 @@
+"""The flickering-attack optimisation loop: one `FlickerAttack.step()` == one
+`sess.run([train_op, loss, …])` of the reference (i3d_adversarial_main_single_video_npy.py:213-215,
+i3d_adversarial_main_single_class_gen.py:245-247, i3d_adversarial_main_universal.py:163-175):
+apply delta -> forward -> adversarial loss -> backward to delta -> (sum over ranks) -> regulariser
+gradients + Adam.  1 forward + 1 backward-to-input per step; no weight gradients, no extra forwards.
+
+Multi-GPU (universal / class-generalisation attacks): one process per GPU, the clip batch is sharded
+on dim 0, delta / Adam state are replicated and the packed `[T,3] + scalars` buffer is sum-all-reduced
+once per step (torch.distributed, NCCL over NVLink).  The margin loss is a SUM over samples
+(utils/kinetics_i3d_utils.py:285) so the global gradient is the plain sum of the rank gradients; the
+CE loss is a MEAN (:305) and each rank divides by the global batch.  Regulariser gradients depend on
+delta only and are added once, after the all-reduce, identically on every rank.
+"""
+import torch
+
+from . import _lib as L
+from .engine import FlickerEngine
+
+
+class FlickerAttack:
+    def __init__(self, weights, batch, frames, attack_cfg=None, height=224, width=224, num_classes=400,
+                 device=0, lr=1e-3, stack="tf", delta_clip=0.4, process_group=None):
+        self.eng = FlickerEngine(batch, frames, height, width, num_classes, device)
+        self.eng.load_weights(weights)
+        self.device = self.eng.device
+        self.B, self.T, self.K = batch, frames, num_classes
+        self.stack = L.FAV_STACK_TF if stack == "tf" else L.FAV_STACK_TORCH
+        self.lr = lr
+        self.delta_clip = delta_clip
+        cfg = dict(attack_cfg or {})
+        self.improve_loss = bool(cfg.get("IMPROVE_ADV_LOSS", True))
+        self.targeted = bool(cfg.get("TARGETED_ATTACK", False))
+        self.use_logits = bool(cfg.get("USE_LOGITS", False))
+        self.margin = float(cfg.get("PROB_MARGIN", 0.05))
+        self.beta0 = float(cfg.get("LAMBDA", 1.0))
+        self.beta1 = float(cfg.get("BETA_1", 0.5))
+        self.beta2 = float(cfg.get("BETA_2", 0.5))
+        self.beta3 = float(cfg.get("BETA_2", 0.5))   # the drivers set _beta_3 = BETA_2 (single_video_npy.py:98)
+        # distributed
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.global_batch = batch * self.world
+        # state: delta (eps_rgb, utils/kinetics_i3d_utils.py:100 — zeros), Adam slots, step
+        n = frames * 3
+        self.delta = torch.zeros((frames, 3), dtype=torch.float32, device=self.device)
+        self.m = torch.zeros_like(self.delta)
+        self.v = torch.zeros_like(self.delta)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # packed communication buffer: [T*3 gradient | FAV_S_COUNT scalars]
+        self.comm = torch.zeros(n + L.S_COUNT, dtype=torch.float32, device=self.device)
+        self.grad = self.comm[:n].view(frames, 3)
+        self.scalars = self.comm[n:]
+        self.eng.grad = self.grad
+        self.eng.scalars = self.scalars
+        # host staging for the end-to-end path
+        self._stage = None
+        self._copy_stream = None
+        self._host_scalars = None
+
+    # ---- state ---------------------------------------------------------------------------
+    def reset(self):
+        """sess.run(eps_rgb.initializer) + re-initialise the optimizer slots
+        (single_video_npy.py:205-206)."""
+        self.delta.zero_()
+        self.m.zero_()
+        self.v.zero_()
+        self.step_count.zero_()
+
+    @property
+    def perturbation(self):
+        """the reference's eps_rgb, shape [T,1,1,3]"""
+        return self.delta.view(self.T, 1, 1, 3)
+
+    def state_dict(self):
+        return {"delta": self.delta.cpu(), "m": self.m.cpu(), "v": self.v.cpu(), "step": int(self.step_count.item())}
+
+    def load_state_dict(self, sd):
+        self.delta.copy_(sd["delta"])
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.step_count.fill_(int(sd["step"]))
+
+    # ---- one optimisation step -------------------------------------------------------------
+    def step(self, clips, labels, adv_flag=1.0, lr=None):
+        """clips: DEVICE uint8/float32 [B,T,H,W,3]; labels: DEVICE int64 [B] (the target class ids
+        for a targeted attack).  Asynchronous; returns the device scalar block (see _lib.S_*)."""
+        e = self.eng
+        e.apply(clips, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        e.forward()
+        gscale = 1.0
+        e.loss(labels, improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
+               margin=self.margin, grad_scale=gscale, global_batch=self.global_batch, stack=self.stack)
+        e.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.comm, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        e.update(self.delta, self.grad, self.m, self.v, self.step_count, self.beta0, self.beta1, self.beta2,
+                 self.beta3, lr=self.lr if lr is None else lr, delta_clip=self.delta_clip, stack=self.stack)
+        return self.scalars
+
+    # ---- end-to-end path: host buffers in, host scalars out ----------------------------------
+    def _ensure_staging(self, like):
+        if self._stage is None:
+            self._stage = [torch.empty(like.shape, dtype=like.dtype, device=self.device) for _ in range(2)]
+            self._stage_labels = [torch.empty((self.B,), dtype=torch.int64, device=self.device) for _ in range(2)]
+            self._stage_events = [torch.cuda.Event() for _ in range(2)]
+            self._done_events = [torch.cuda.Event() for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._host_scalars = [torch.empty(L.S_COUNT, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._slot = 0
+
+    def prefetch(self, host_clips, host_labels):
+        """Start the host->device copy of the NEXT batch (pinned host memory) on the copy stream."""
+        self._ensure_staging(host_clips)
+        slot = self._slot
+        cs = self._copy_stream
+        # the buffer may still be read by the step that used it two steps ago
+        cs.wait_event(self._done_events[slot])
+        with torch.cuda.stream(cs):
+            self._stage[slot].copy_(host_clips, non_blocking=True)
+            self._stage_labels[slot].copy_(host_labels, non_blocking=True)
+            self._stage_events[slot].record(cs)
+        self._slot ^= 1
+        return slot
+
+    def step_staged(self, slot, adv_flag=1.0, lr=None):
+        """Run one step on a prefetched batch and start the device->host read of its scalars.
+        Returns the pinned host tensor and the event that marks it valid."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._stage_events[slot])
+        self.step(self._stage[slot], self._stage_labels[slot], adv_flag=adv_flag, lr=lr)
+        self._host_scalars[slot].copy_(self.scalars, non_blocking=True)
+        self._done_events[slot].record(cur)
+        return self._host_scalars[slot], self._done_events[slot]
+
+    # ---- evaluation helpers (forward only) ---------------------------------------------------
+    def predict(self, clips, adv_flag=1.0):
+        """softmax [B,K] for clean (adv_flag=0) or perturbed clips — the reference's
+        `k_i3d(inputs, adv_flag)` (utils/kinetics_i3d_utils.py:210-212)."""
+        self.eng.apply(clips, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        logits = self.eng.forward()
+        return torch.softmax(logits, dim=-1)
+
+    def adversarial_video(self, clips, as_uint8=False):
+        """`adversarial_inputs_rgb` (fp32, utils/kinetics_i3d_utils.py:139-142) or its uint8 view
+        ((adv+1.0)*127.5).astype(uint8) (utils/stats_and_plot/stats_plots.py:57)."""
+        if as_uint8:
+            out = torch.empty(clips.shape, dtype=torch.uint8, device=self.device)
+            self.eng.apply(clips, self.delta, delta_clip=self.delta_clip, adv_u8=out)
+        else:
+            out = torch.empty(clips.shape, dtype=torch.float32, device=self.device)
+            self.eng.apply(clips, self.delta, delta_clip=self.delta_clip, adv_f32=out)
+        return out
+
+    def close(self):
+        self.eng.close()

@@ -444,6 +444,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(
       L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
       L.stage_bytes);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }

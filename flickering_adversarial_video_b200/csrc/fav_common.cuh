@@ -41,6 +41,9 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 int sm_count(int device);
+// number of kernels this library has launched in this process (bench.py reports it)
+extern unsigned long long g_launch_count;
+#define FAV_COUNT_LAUNCH() (++fav::g_launch_count)
 
 // ---- TMA descriptor creation (driver entry point fetched at run time: no libcuda link) -------
 // rank-5 bf16 tensor map; dims/strides innermost first; strides in BYTES for dims 1..4.

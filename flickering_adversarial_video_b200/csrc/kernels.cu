@@ -153,6 +153,7 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
   else
     apply_kernel<false><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
                                                adv_f32, sat_list, sat_capacity, sat_count, T, H, W, groups);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -183,6 +184,7 @@ __global__ void stem_bias_kernel(const float* __restrict__ delta, float adv_flag
 int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc,
                      const float* bnbias, float* table, int T, int To, int pt, cudaStream_t s) {
   stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -258,6 +260,7 @@ int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
   const long long total = static_cast<long long>(g.B) * g.To * g.Ho * g.Wo * (g.C / 8);
   maxpool_fwd_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(x, y, idx, g, total);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -337,6 +340,7 @@ int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
   const long long total = static_cast<long long>(g.B) * g.T * g.H * g.W * (g.C / 8);
   maxpool_bwd_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(dy, idx, addend, relu_src,
                                                                              dx, g, total);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -407,8 +411,10 @@ int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float*
   FAV_CHECK_ARG(C % 8 == 0, "head: C must be a multiple of 8");
   dim3 grid(ceil_div(C / 8, 32), B);
   head_feat_kernel<<<grid, 256, 0, s>>>(y, feat, T5, HW, C);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   head_logits_kernel<<<B, 512, C * sizeof(float), s>>>(feat, wl, bl, logits, C, K);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -456,9 +462,11 @@ int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfl
                     __nv_bfloat16* gy, float* dfeat, int B, int T5, int HW, int C, cudaStream_t s) {
   dim3 grid(ceil_div(C, 8), B);
   head_dfeat_kernel<<<grid, 256, 0, s>>>(dlogits, wl, dfeat, C, K);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   const long long total = static_cast<long long>(B) * T5 * HW * (C / 8);
   head_gy_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(dfeat, y, gy, T5, HW, C, total);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -654,6 +662,7 @@ loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels
 int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
                 float* probs, float* dlogits, float* scalars, cudaStream_t s) {
   loss_kernel<<<1, 512, 2 * K * sizeof(float), s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -712,6 +721,7 @@ int launch_stem_class_sums(const __nv_bfloat16* g1, float* S, int B, int To, int
   FAV_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(To) * 16 * 64 * sizeof(float), s));
   dim3 grid(To * Ho, B);
   stem_class_sums_kernel<<<grid, 128, 0, s>>>(g1, S, To, Ho, Wo);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -740,6 +750,7 @@ stem_grad_delta_kernel(const float* __restrict__ S, const float* __restrict__ wc
 int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, int To, int pt,
                            cudaStream_t s) {
   stem_grad_delta_kernel<<<T * 3, 256, 0, s>>>(S, wc, grad, T, To, pt);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -808,6 +819,7 @@ int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const ui
   (void)B;
   stem_sat_correction_kernel<<<296, 256, T * 3 * sizeof(float), s>>>(g1, w, sat_list, sat_count, sat_capacity,
                                                                      grad, T, H, W, To, Ho, Wo, pt, ph, pw);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -909,6 +921,7 @@ int launch_delta_update(float* delta, const float* grad, float* m, float* v, int
                         float* scalars, int T, cudaStream_t s) {
   delta_update_kernel<<<1, 256, T * 3 * sizeof(float), s>>>(delta, grad, m, v, step, reg, adam, adv_flag,
                                                             scalars, T);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -936,6 +949,7 @@ int launch_bf16_to_f32(const __nv_bfloat16* src, long long cs, int coff, int C, 
                        cudaStream_t s) {
   const long long total = npos * C;
   bf16_to_f32_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(src, cs, coff, C, total, dst);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
@@ -943,6 +957,7 @@ int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long cs, int c
                        cudaStream_t s) {
   const long long total = npos * C;
   f32_to_bf16_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(src, dst, cs, coff, C, total);
+  FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }

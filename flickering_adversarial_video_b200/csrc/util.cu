@@ -7,6 +7,7 @@
 namespace fav {
 
 static thread_local char t_err[1024] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -80,5 +81,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }  // namespace fav
 
 extern "C" const char* fav_last_error(void) { return fav::get_error(); }
+
+extern "C" int64_t fav_launch_count(void) { return static_cast<int64_t>(fav::g_launch_count); }
 
 extern "C" const char* fav_build_info(void) { return "sm_100a;" __DATE__ " " __TIME__; }

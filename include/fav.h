@@ -181,6 +181,9 @@ int fav_op_maxpool3d_bwd(int device, const void* dy, const uint8_t* idx, const v
  * ("Conv3d_1a_7x7", "Mixed_3b", ...), prefix "grad:" for the gradient buffer. */
 int64_t fav_debug_read(fav_handle* h, const char* name, float* out, int64_t capacity, void* stream);
 
+/* number of CUDA kernels libfav has launched in this process (bench.py `gpu_launches`) */
+int64_t fav_launch_count(void);
+
 /* library build info: "sm_100a;<compile date>" */
 const char* fav_build_info(void);
 

@@ -80,14 +80,42 @@ def maxpool3d_same(x, k, s):
     return F.max_pool3d(_pad_ndhwc_as_ncdhw(x, k, s, value=float("-inf")), kernel_size=k, stride=s)
 
 
-class OracleI3D:
-    """InceptionI3d(final_endpoint='Logits') forward, differentiable w.r.t. its input."""
+def _bf16_round(t):
+    """value-rounding to bf16 with a straight-through gradient (the engine rounds activations to
+    bf16 between layers; its backward treats the rounding as identity)."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
 
-    def __init__(self, weights, dtype=torch.float32):
+
+class OracleI3D:
+    """InceptionI3d(final_endpoint='Logits') forward, differentiable w.r.t. its input.
+
+    emulate_bf16=True restates the ENGINE's arithmetic instead of the reference's fp32: BN folded
+    into the weights, folded weights and every layer output rounded to bf16, fp32 accumulation,
+    delta entering the stem in fp32.  It exists to separate kernel correctness from the precision
+    effect of bf16 storage (ReLU masks of a random-init network flip under 0.5 % activation noise);
+    see DESIGN.md §Precision."""
+
+    def __init__(self, weights, dtype=torch.float32, emulate_bf16=False):
         self.dtype = dtype
+        self.emulate = emulate_bf16
         self.w = {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in weights.items()}
 
-    def unit(self, x, scope, stride=(1, 1, 1)):
+    def folded(self, scope):
+        w = self.w[ROOT + scope + "/conv_3d/w"]
+        beta = self.w[ROOT + scope + "/batch_norm/beta"].reshape(-1)
+        mean = self.w[ROOT + scope + "/batch_norm/moving_mean"].reshape(-1)
+        var = self.w[ROOT + scope + "/batch_norm/moving_variance"].reshape(-1)
+        scale = 1.0 / torch.sqrt(var + 1e-3)
+        return w * scale, beta - mean * scale
+
+    def unit(self, x, scope, stride=(1, 1, 1), delta_img=None):
+        if self.emulate:
+            wf, bias = self.folded(scope)
+            wq = wf.to(torch.bfloat16).to(self.dtype)
+            y = conv3d_same(x, wq, stride) + bias.reshape(1, -1, 1, 1, 1)
+            if delta_img is not None:   # stem: delta contributes through the unrounded folded weights
+                y = y + conv3d_same(delta_img, wf, stride)
+            return _bf16_round(F.relu(y))
         w = self.w[ROOT + scope + "/conv_3d/w"]
         y = conv3d_same(x, w, stride)
         beta = self.w[ROOT + scope + "/batch_norm/beta"].reshape(1, -1, 1, 1, 1)
@@ -96,16 +124,32 @@ class OracleI3D:
         y = (y - mean) / torch.sqrt(var + 1e-3) + beta     # snt.BatchNorm: eps=1e-3, no scale
         return F.relu(y)
 
-    def forward(self, x_ndhwc, endpoints=None):
+    def forward_split(self, x_clean, delta, adv_flag=1.0, delta_clip=0.4, endpoints=None):
+        """Engine-style evaluation (emulate_bf16 only): the clean clip goes through the bf16 stem
+        operand, delta through the fp32 side path; saturated pixels carry clip(x+d)-d."""
+        assert self.emulate
+        d = adv_flag * torch.clamp(delta.reshape(-1, 1, 1, 3).to(self.dtype), -delta_clip, delta_clip)
+        s = x_clean.to(self.dtype) + d
+        adv = torch.clamp(s, -1.0, 1.0)
+        sat = (s < -1.0) | (s > 1.0)
+        # x' = x where the clip did not fire, clip(x+d) - d elsewhere; d/d(delta) of (x' + d) is the clip mask
+        xprime = torch.where(sat, (adv - d).detach(), x_clean.to(self.dtype))
+        xprime = xprime.to(torch.bfloat16).to(self.dtype)
+        dimg = torch.where(sat, d.detach().expand_as(s), d.expand_as(s))
+        return self.forward(xprime, endpoints=endpoints, delta_img=dimg)
+
+    def forward(self, x_ndhwc, endpoints=None, delta_img=None):
         """x [B,T,H,W,3] -> logits [B,400]; optionally records end points (NDHWC)."""
         x = x_ndhwc.to(self.dtype).permute(0, 4, 1, 2, 3)
+        if delta_img is not None:
+            delta_img = delta_img.to(self.dtype).permute(0, 4, 1, 2, 3)
 
         def rec(name, t):
             if endpoints is not None:
                 endpoints[name] = t.permute(0, 2, 3, 4, 1)
             return t
 
-        net = rec("Conv3d_1a_7x7", self.unit(x, "Conv3d_1a_7x7", (2, 2, 2)))
+        net = rec("Conv3d_1a_7x7", self.unit(x, "Conv3d_1a_7x7", (2, 2, 2), delta_img=delta_img))
         net = rec("MaxPool3d_2a_3x3", maxpool3d_same(net, (1, 3, 3), (1, 2, 2)))
         net = rec("Conv3d_2b_1x1", self.unit(net, "Conv3d_2b_1x1"))
         net = rec("Conv3d_2c_3x3", self.unit(net, "Conv3d_2c_3x3"))
@@ -235,15 +279,18 @@ def attack_step(model, x, labels, delta, cfg, opt=None, data_grad_only=False):
     gradient [T,3], the total gradient and (if opt) the updated delta."""
     dtype = model.dtype
     d = delta.detach().clone().to(dtype).requires_grad_(True)
-    adv = apply_flicker(x.to(dtype), d, cfg.get("adv_flag", 1.0), cfg.get("delta_clip", 0.4))
-    logits = model.forward(adv)
+    if getattr(model, "emulate", False):
+        logits = model.forward_split(x, d, cfg.get("adv_flag", 1.0), cfg.get("delta_clip", 0.4))
+    else:
+        adv = apply_flicker(x.to(dtype), d, cfg.get("adv_flag", 1.0), cfg.get("delta_clip", 0.4))
+        logits = model.forward(adv)
     if cfg.get("improve_loss", True):
         adv_loss, p_min, p_max = improve_adversarial_loss(
             logits, labels, cfg.get("margin", 0.05), cfg.get("targeted", False), cfg.get("use_logits", False))
     else:
         adv_loss, p_min, p_max = ce_adversarial_loss(logits, labels, cfg.get("targeted", False))
     (g_data,) = torch.autograd.grad(adv_loss, d, retain_graph=False)
-    out = {"logits": logits.detach(), "softmax": F.softmax(logits.detach(), -1), "adv_loss": float(adv_loss),
+    out = {"logits": logits.detach(), "softmax": F.softmax(logits.detach(), -1), "adv_loss": float(adv_loss.detach()),
            "grad_data": g_data.detach().reshape(-1, 3), "to_min_prob": p_min.detach(), "to_max_prob": p_max.detach()}
     if data_grad_only:
         return out
