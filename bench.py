@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 try:
@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.ok:
             self.join(timeout=2)
         s = sorted(self.samples)

@@ -124,7 +124,7 @@ class OracleI3D:
         y = (y - mean) / torch.sqrt(var + 1e-3) + beta     # snt.BatchNorm: eps=1e-3, no scale
         return F.relu(y)
 
-    def forward_split(self, x_clean, delta, adv_flag=1.0, delta_clip=0.4, endpoints=None):
+    def forward_split(self, x_clean, delta, adv_flag=1.0, delta_clip=0.4, endpoints=None, raw_endpoints=None):
         """Engine-style evaluation (emulate_bf16 only): the clean clip goes through the bf16 stem
         operand, delta through the fp32 side path; saturated pixels carry clip(x+d)-d."""
         assert self.emulate
@@ -136,10 +136,11 @@ class OracleI3D:
         xprime = torch.where(sat, (adv - d).detach(), x_clean.to(self.dtype))
         xprime = xprime.to(torch.bfloat16).to(self.dtype)
         dimg = torch.where(sat, d.detach().expand_as(s), d.expand_as(s))
-        return self.forward(xprime, endpoints=endpoints, delta_img=dimg)
+        return self.forward(xprime, endpoints=endpoints, delta_img=dimg, raw_endpoints=raw_endpoints)
 
-    def forward(self, x_ndhwc, endpoints=None, delta_img=None):
-        """x [B,T,H,W,3] -> logits [B,400]; optionally records end points (NDHWC)."""
+    def forward(self, x_ndhwc, endpoints=None, delta_img=None, raw_endpoints=None):
+        """x [B,T,H,W,3] -> logits [B,400]; optionally records end points (NDHWC views in
+        `endpoints`; the graph tensors themselves, NCDHW, in `raw_endpoints` for retain_grad)."""
         x = x_ndhwc.to(self.dtype).permute(0, 4, 1, 2, 3)
         if delta_img is not None:
             delta_img = delta_img.to(self.dtype).permute(0, 4, 1, 2, 3)
@@ -147,6 +148,8 @@ class OracleI3D:
         def rec(name, t):
             if endpoints is not None:
                 endpoints[name] = t.permute(0, 2, 3, 4, 1)
+            if raw_endpoints is not None:
+                raw_endpoints[name] = t
             return t
 
         net = rec("Conv3d_1a_7x7", self.unit(x, "Conv3d_1a_7x7", (2, 2, 2), delta_img=delta_img))
