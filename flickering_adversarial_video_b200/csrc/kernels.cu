@@ -206,51 +206,65 @@ PoolGeom make_pool_geom(int B, int T, int H, int W, int C, int kt, int kh, int k
   return g;
 }
 
+// forward: one thread = one output position x 8 channels, packed bf16x2 compare/select
+// (3 ALU ops per tap per channel pair); 2-D grid so the only runtime division is by C/8.
+template <int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                   uint8_t* __restrict__ idx, const PoolGeom g, long long total) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
+                   uint8_t* __restrict__ idx, const PoolGeom gg) {
+  PoolGeom g = gg;
+  if (KT > 0) { g.kt = KT; g.kh = KH; g.kw = KW; g.st = ST; g.sh = SH; g.sw = SW; }
   const int cg = g.C >> 3;
-  const int c8 = static_cast<int>(gid % cg);
-  long long p = gid / cg;
-  const int wo = static_cast<int>(p % g.Wo); p /= g.Wo;
-  const int ho = static_cast<int>(p % g.Ho); p /= g.Ho;
-  const int to = static_cast<int>(p % g.To);
-  const int b = static_cast<int>(p / g.To);
-  float best[8];
-  int bi[8];
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= g.Wo * cg) return;
+  const int wo = i / cg;
+  const int c8 = i - wo * cg;
+  int row = blockIdx.x;
+  const int ho = row % g.Ho; row /= g.Ho;
+  const int to = row % g.To;
+  const int b = row / g.To;
+  __nv_bfloat162 best[4];
+  uint32_t bidx[4];
+  const __nv_bfloat162 ninf = __halves2bfloat162(__ushort_as_bfloat16(0xFF80), __ushort_as_bfloat16(0xFF80));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+  for (int j = 0; j < 4; ++j) { best[j] = ninf; bidx[j] = 0; }
+  const int t0 = to * g.st - g.pt, h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
+#pragma unroll
   for (int dt = 0; dt < g.kt; ++dt) {
-    const int t = to * g.st + dt - g.pt;
+    const int t = t0 + dt;
     if (t < 0 || t >= g.T) continue;
-    for (int dh = 0; dh < g.kh; ++dh) {
-      const int h = ho * g.sh + dh - g.ph;
-      if (h < 0 || h >= g.H) continue;
-      for (int dw = 0; dw < g.kw; ++dw) {
-        const int w = wo * g.sw + dw - g.pw;
-        if (w < 0 || w >= g.W) continue;
-        const int tap = (dt * g.kh + dh) * g.kw + dw;
-        const long long off = (((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * g.C + c8 * 8;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + off));
-        const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                            bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (f[j] > best[j]) { best[j] = f[j]; bi[j] = tap; }
+    for (int dh = 0; dh < g.kh; ++dh) {
+      const int h = h0 + dh;
+      if (h < 0 || h >= g.H) continue;
+      const __nv_bfloat16* rowp = x + ((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W * g.C + c8 * 8;
+      const uint32_t tap0 = static_cast<uint32_t>((dt * g.kh + dh) * g.kw);
+#pragma unroll
+      for (int dw = 0; dw < g.kw; ++dw) {
+        const int w = w0 + dw;
+        if (w < 0 || w >= g.W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + w * g.C));
+        const uint32_t tap2 = (tap0 + dw) * 0x00010001u;
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(&wv[j]);
+          const uint32_t m = __hgt2_mask(vv, best[j]);   // strict >: the first arg-max wins
+          best[j] = __hmax2(best[j], vv);
+          bidx[j] = (bidx[j] & ~m) | (tap2 & m);
+        }
       }
     }
   }
-  const long long ooff = gid * 8;
+  const long long ooff = ((static_cast<long long>(blockIdx.x) * g.Wo + wo) * cg + c8) * 8;
   uint4 o;
-  o.x = pack_bf16x2(best[0], best[1]); o.y = pack_bf16x2(best[2], best[3]);
-  o.z = pack_bf16x2(best[4], best[5]); o.w = pack_bf16x2(best[6], best[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&best[0]); o.y = *reinterpret_cast<uint32_t*>(&best[1]);
+  o.z = *reinterpret_cast<uint32_t*>(&best[2]); o.w = *reinterpret_cast<uint32_t*>(&best[3]);
   *reinterpret_cast<uint4*>(y + ooff) = o;
   if (idx) {
-    uint2 iv;
-    iv.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-    iv.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    uint2 iv;   // 2 x u16 -> 2 bytes per word
+    iv.x = __byte_perm(bidx[0], bidx[1], 0x6420);
+    iv.y = __byte_perm(bidx[2], bidx[3], 0x6420);
     *reinterpret_cast<uint2*>(idx + ooff) = iv;
   }
 }
@@ -258,40 +272,52 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s) {
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
-  const long long total = static_cast<long long>(g.B) * g.To * g.Ho * g.Wo * (g.C / 8);
-  maxpool_fwd_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(x, y, idx, g, total);
+  FAV_CHECK_ARG(g.kt * g.kh * g.kw <= 255, "maxpool: window too large");
+  dim3 grid(g.B * g.To * g.Ho, ceil_div(g.Wo * (g.C / 8), 256));
+  const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
+  switch (key) {
+    case 133122: maxpool_fwd_kernel<1, 3, 3, 1, 2, 2><<<grid, 256, 0, s>>>(x, y, idx, g); break;
+    case 333111: maxpool_fwd_kernel<3, 3, 3, 1, 1, 1><<<grid, 256, 0, s>>>(x, y, idx, g); break;
+    case 333222: maxpool_fwd_kernel<3, 3, 3, 2, 2, 2><<<grid, 256, 0, s>>>(x, y, idx, g); break;
+    case 222222: maxpool_fwd_kernel<2, 2, 2, 2, 2, 2><<<grid, 256, 0, s>>>(x, y, idx, g); break;
+    default: maxpool_fwd_kernel<0, 0, 0, 0, 0, 0><<<grid, 256, 0, s>>>(x, y, idx, g); break;
+  }
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
 
 // backward in gather form: every input element sums the windows whose recorded arg-max is itself
+template <int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
-                   __nv_bfloat16* __restrict__ dx, const PoolGeom g, long long total) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
+                   __nv_bfloat16* __restrict__ dx, const PoolGeom gg) {
+  PoolGeom g = gg;
+  if (KT > 0) { g.kt = KT; g.kh = KH; g.kw = KW; g.st = ST; g.sh = SH; g.sw = SW; }
   const int cg = g.C >> 3;
-  const int c8 = static_cast<int>(gid % cg);
-  long long p = gid / cg;
-  const int w = static_cast<int>(p % g.W); p /= g.W;
-  const int h = static_cast<int>(p % g.H); p /= g.H;
-  const int t = static_cast<int>(p % g.T);
-  const int b = static_cast<int>(p / g.T);
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= g.W * cg) return;
+  const int w = i / cg;
+  const int c8 = i - w * cg;
+  int row = blockIdx.x;
+  const int h = row % g.H; row /= g.H;
+  const int t = row % g.T;
+  const int b = row / g.T;
+  const long long eoff = ((static_cast<long long>(blockIdx.x) * g.W + w) * cg + c8) * 8;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
   if (addend) {
-    const uint4 a = *reinterpret_cast<const uint4*>(addend + gid * 8);
+    const uint4 a = *reinterpret_cast<const uint4*>(addend + eoff);
     acc[0] = bf16_lo(a.x); acc[1] = bf16_hi(a.x); acc[2] = bf16_lo(a.y); acc[3] = bf16_hi(a.y);
     acc[4] = bf16_lo(a.z); acc[5] = bf16_hi(a.z); acc[6] = bf16_lo(a.w); acc[7] = bf16_hi(a.w);
   }
   // windows (to) containing t: to*st - pt <= t <= to*st - pt + kt - 1
   const int tp = t + g.pt, hp = h + g.ph, wp = w + g.pw;
-  int to_lo = (tp - g.kt + 1 + g.st - 1); to_lo = to_lo < 0 ? 0 : to_lo / g.st;
-  int ho_lo = (hp - g.kh + 1 + g.sh - 1); ho_lo = ho_lo < 0 ? 0 : ho_lo / g.sh;
-  int wo_lo = (wp - g.kw + 1 + g.sw - 1); wo_lo = wo_lo < 0 ? 0 : wo_lo / g.sw;
+  int to_lo = tp - g.kt + g.st; to_lo = to_lo < 0 ? 0 : to_lo / g.st;
+  int ho_lo = hp - g.kh + g.sh; ho_lo = ho_lo < 0 ? 0 : ho_lo / g.sh;
+  int wo_lo = wp - g.kw + g.sw; wo_lo = wo_lo < 0 ? 0 : wo_lo / g.sw;
   const int to_hi = min(tp / g.st, g.To - 1);
   const int ho_hi = min(hp / g.sh, g.Ho - 1);
   const int wo_hi = min(wp / g.sw, g.Wo - 1);
@@ -299,29 +325,27 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
     const int dt = tp - to * g.st;
     for (int ho = ho_lo; ho <= ho_hi; ++ho) {
       const int dh = hp - ho * g.sh;
+      const long long rbase = (((static_cast<long long>(b) * g.To + to) * g.Ho + ho) * g.Wo) * g.C + c8 * 8;
+#pragma unroll 3
       for (int wo = wo_lo; wo <= wo_hi; ++wo) {
         const int dw = wp - wo * g.sw;
-        const uint32_t tap = static_cast<uint32_t>((dt * g.kh + dh) * g.kw + dw);
-        const long long off = (((static_cast<long long>(b) * g.To + to) * g.Ho + ho) * g.Wo + wo) * g.C + c8 * 8;
+        const uint32_t tap4 = static_cast<uint32_t>((dt * g.kh + dh) * g.kw + dw) * 0x01010101u;
+        const long long off = rbase + wo * g.C;
         const uint2 iv = __ldg(reinterpret_cast<const uint2*>(idx + off));
-        const uint32_t eqx = iv.x ^ (tap * 0x01010101u);
-        const uint32_t eqy = iv.y ^ (tap * 0x01010101u);
-        if (((eqx & 0xffu) && (eqx & 0xff00u) && (eqx & 0xff0000u) && (eqx & 0xff000000u)) &&
-            ((eqy & 0xffu) && (eqy & 0xff00u) && (eqy & 0xff0000u) && (eqy & 0xff000000u)))
-          continue;  // none of the 8 channels picked this element
+        const uint32_t ex = __vcmpeq4(iv.x, tap4);   // 0xff per channel whose arg-max is this element
+        const uint32_t ey = __vcmpeq4(iv.y, tap4);
+        if ((ex | ey) == 0u) continue;
         const uint4 d = __ldg(reinterpret_cast<const uint4*>(dy + off));
-        const float f[8] = {bf16_lo(d.x), bf16_hi(d.x), bf16_lo(d.y), bf16_hi(d.y),
-                            bf16_lo(d.z), bf16_hi(d.z), bf16_lo(d.w), bf16_hi(d.w)};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (((eqx >> (8 * j)) & 0xffu) == 0) acc[j] += f[j];
-          if (((eqy >> (8 * j)) & 0xffu) == 0) acc[4 + j] += f[4 + j];
-        }
+        const uint32_t m0 = __byte_perm(ex, 0, 0x1100), m1 = __byte_perm(ex, 0, 0x3322);
+        const uint32_t m2 = __byte_perm(ey, 0, 0x1100), m3 = __byte_perm(ey, 0, 0x3322);
+        const uint32_t d0 = d.x & m0, d1 = d.y & m1, d2 = d.z & m2, d3 = d.w & m3;
+        acc[0] += bf16_lo(d0); acc[1] += bf16_hi(d0); acc[2] += bf16_lo(d1); acc[3] += bf16_hi(d1);
+        acc[4] += bf16_lo(d2); acc[5] += bf16_hi(d2); acc[6] += bf16_lo(d3); acc[7] += bf16_hi(d3);
       }
     }
   }
   if (relu_src) {
-    const uint4 r = __ldg(reinterpret_cast<const uint4*>(relu_src + gid * 8));
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(relu_src + eoff));
     const float f[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
                         bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
 #pragma unroll
@@ -330,16 +354,22 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   uint4 o;
   o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
   o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-  *reinterpret_cast<uint4*>(dx + gid * 8) = o;
+  *reinterpret_cast<uint4*>(dx + eoff) = o;
 }
 
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
                        const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
                        cudaStream_t s) {
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", g.C);
-  const long long total = static_cast<long long>(g.B) * g.T * g.H * g.W * (g.C / 8);
-  maxpool_bwd_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(dy, idx, addend, relu_src,
-                                                                             dx, g, total);
+  dim3 grid(g.B * g.T * g.H, ceil_div(g.W * (g.C / 8), 256));
+  const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
+  switch (key) {
+    case 133122: maxpool_bwd_kernel<1, 3, 3, 1, 2, 2><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
+    case 333111: maxpool_bwd_kernel<3, 3, 3, 1, 1, 1><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
+    case 333222: maxpool_bwd_kernel<3, 3, 3, 2, 2, 2><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
+    case 222222: maxpool_bwd_kernel<2, 2, 2, 2, 2, 2><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
+    default: maxpool_bwd_kernel<0, 0, 0, 0, 0, 0><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
+  }
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -756,53 +786,69 @@ int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, 
 }
 
 // one warp per saturated pixel: recompute dX there exactly (gather over the <= 64 valid taps) and
-// subtract it from g[t,c]
-__global__ void __launch_bounds__(256)
+// subtract it from g[t,c].  The folded stem weights sit in shared memory as fp32 pairs per lane.
+__global__ void __launch_bounds__(1024, 1)
 stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ w,
                            const uint32_t* __restrict__ sat_list, const uint32_t* __restrict__ sat_count,
                            uint32_t sat_capacity, float* __restrict__ grad, int T, int H, int W, int To,
                            int Ho, int Wo, int pt, int ph, int pw) {
-  extern __shared__ float sacc[];  // [T*3]
+  extern __shared__ float smem_f[];
+  __nv_bfloat162* sw = reinterpret_cast<__nv_bfloat162*>(smem_f);   // [343][3][32] channel pairs
+  float* sacc = smem_f + 343 * 3 * 32;                                // [T*3]
+  const uint32_t n = min(*sat_count, sat_capacity);
+  if (blockIdx.x * (blockDim.x >> 4) >= n) return;                   // nothing for this block
+  for (int i = threadIdx.x; i < 343 * 3 * 32; i += blockDim.x)
+    sw[i] = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
   for (int i = threadIdx.x; i < T * 3; i += blockDim.x) sacc[i] = 0.0f;
   __syncthreads();
-  const uint32_t n = min(*sat_count, sat_capacity);
-  const int lane = threadIdx.x & 31;
-  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
-    const uint32_t ent = sat_list[e];
+  // half a warp per entry: 16 lanes x 4 channels; two entries in flight per warp
+  const int hl = threadIdx.x & 15;
+  const uint32_t halves_total = gridDim.x * (blockDim.x >> 4);
+  const uint32_t n_round = (n + 1u) & ~1u;   // both halves of a warp iterate the same number of times
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); e < n_round; e += halves_total) {
+    const bool live = e < n;
+    const uint32_t ent = live ? sat_list[e] : 0u;
     const uint32_t cm = ent >> 28;
     uint32_t pix = ent & 0x0fffffffu;
     const int wx = pix % W; pix /= W;
     const int hx = pix % H; pix /= H;
     const int tx = pix % T;
     const int b = pix / T;
+    const int at = tx + pt, ah = hx + ph, aw = wx + pw;
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-    for (int kt = 0; kt < 7; ++kt) {
-      const int tt = tx + pt - kt;
-      if (tt < 0 || (tt & 1) || (tt >> 1) >= To) continue;
-      for (int kh = 0; kh < 7; ++kh) {
-        const int hh = hx + ph - kh;
-        if (hh < 0 || (hh & 1) || (hh >> 1) >= Ho) continue;
-        for (int kw = 0; kw < 7; ++kw) {
-          const int ww = wx + pw - kw;
-          if (ww < 0 || (ww & 1) || (ww >> 1) >= Wo) continue;
-          const long long off = (((static_cast<long long>(b) * To + (tt >> 1)) * Ho + (hh >> 1)) * Wo + (ww >> 1)) * 64;
-          const uint32_t gv = __ldg(reinterpret_cast<const uint32_t*>(g1 + off) + lane);
-          const float gx = bf16_lo(gv), gy = bf16_hi(gv);
-          const float* wp = w + static_cast<long long>((kt * 7 + kh) * 7 + kw) * 3 * 64 + lane * 2;
-          if (cm & 1u) { const float2 wv = __ldg(reinterpret_cast<const float2*>(wp)); a0 = fmaf(gx, wv.x, fmaf(gy, wv.y, a0)); }
-          if (cm & 2u) { const float2 wv = __ldg(reinterpret_cast<const float2*>(wp + 64)); a1 = fmaf(gx, wv.x, fmaf(gy, wv.y, a1)); }
-          if (cm & 4u) { const float2 wv = __ldg(reinterpret_cast<const float2*>(wp + 128)); a2 = fmaf(gx, wv.x, fmaf(gy, wv.y, a2)); }
+    if (live) {
+      for (int kt = at & 1; kt < 7 && kt <= at; kt += 2) {
+        const int to = (at - kt) >> 1;
+        if (to >= To) continue;
+        for (int kh = ah & 1; kh < 7 && kh <= ah; kh += 2) {
+          const int ho = (ah - kh) >> 1;
+          if (ho >= Ho) continue;
+          const __nv_bfloat16* grow = g1 + (((static_cast<long long>(b) * To + to) * Ho + ho) * Wo) * 64;
+#pragma unroll 4
+          for (int kw = aw & 1; kw < 7 && kw <= aw; kw += 2) {
+            const int wo = (aw - kw) >> 1;
+            if (wo >= Wo) continue;
+            const uint2 gv = __ldg(reinterpret_cast<const uint2*>(grow + wo * 64) + hl);
+            const float g0 = bf16_lo(gv.x), g1v = bf16_hi(gv.x), g2 = bf16_lo(gv.y), g3 = bf16_hi(gv.y);
+            const __nv_bfloat162* wp = sw + ((kt * 7 + kh) * 7 + kw) * 96 + hl * 2;
+            float2 u, v;
+            u = __bfloat1622float2(wp[0]); v = __bfloat1622float2(wp[1]);
+            a0 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a0))));
+            u = __bfloat1622float2(wp[32]); v = __bfloat1622float2(wp[33]);
+            a1 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a1))));
+            u = __bfloat1622float2(wp[64]); v = __bfloat1622float2(wp[65]);
+            a2 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a2))));
+          }
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 8; o > 0; o >>= 1) {
       a0 += __shfl_xor_sync(0xffffffffu, a0, o);
       a1 += __shfl_xor_sync(0xffffffffu, a1, o);
       a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
-    if (lane == 0) {
+    if (hl == 0 && live) {
       if (cm & 1u) atomicAdd(&sacc[tx * 3 + 0], -a0);
       if (cm & 2u) atomicAdd(&sacc[tx * 3 + 1], -a1);
       if (cm & 4u) atomicAdd(&sacc[tx * 3 + 2], -a2);
@@ -817,8 +863,15 @@ int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const ui
                                const uint32_t* sat_count, uint32_t sat_capacity, float* grad, int B, int T,
                                int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw, cudaStream_t s) {
   (void)B;
-  stem_sat_correction_kernel<<<296, 256, T * 3 * sizeof(float), s>>>(g1, w, sat_list, sat_count, sat_capacity,
-                                                                     grad, T, H, W, To, Ho, Wo, pt, ph, pw);
+  const size_t smem = static_cast<size_t>(343) * 3 * 32 * sizeof(float) + static_cast<size_t>(T) * 3 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FAV_CUDA(cudaFuncSetAttribute(stem_sat_correction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  FAV_CHECK_ARG(smem <= 160 * 1024, "sat correction: T=%d too large", T);
+  stem_sat_correction_kernel<<<148, 1024, smem, s>>>(g1, w, sat_list, sat_count, sat_capacity, grad, T, H, W, To,
+                                                     Ho, Wo, pt, ph, pw);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
