@@ -68,6 +68,8 @@ SIGNATURES = {
                            _i, _i, _i, _i, _i, _i, _vp, _i64, _i64, _vp]),
     "fav_op_maxpool3d": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fav_op_maxpool3d_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fav_op_loss": (_i, [_i, _vp, _vp, C.POINTER(LossParams), _i, _i, _vp, _vp, _vp, _vp]),
+    "fav_op_delta_update": (_i, [_i, _vp, _vp, _vp, _vp, _vp, C.POINTER(RegParams), C.POINTER(AdamParams), _f, _vp, _i, _vp]),
     "fav_debug_read": (_i64, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "fav_launch_count": (_i64, []),
     "fav_build_info": (C.c_char_p, []),

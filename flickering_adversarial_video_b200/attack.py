@@ -14,6 +14,7 @@ delta only and are added once, after the all-reduce, identically on every rank.
 import torch
 
 from . import _lib as L
+from . import dist as fdist
 from .engine import FlickerEngine
 
 
@@ -94,7 +95,7 @@ class FlickerAttack:
                margin=self.margin, grad_scale=gscale, global_batch=self.global_batch, stack=self.stack)
         e.backward()
         if self.world > 1:
-            torch.distributed.all_reduce(self.comm, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            fdist.allreduce_sum_(self.comm, self.pg)
         e.update(self.delta, self.grad, self.m, self.v, self.step_count, self.beta0, self.beta1, self.beta2,
                  self.beta3, lr=self.lr if lr is None else lr, delta_clip=self.delta_clip, stack=self.stack)
         return self.scalars

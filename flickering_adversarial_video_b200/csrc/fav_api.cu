@@ -728,3 +728,19 @@ extern "C" int fav_op_maxpool3d_bwd(int device, const void* dy, const uint8_t* i
                             static_cast<const __nv_bfloat16*>(relu_src), static_cast<__nv_bfloat16*>(dx), g,
                             static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int fav_op_loss(int device, const float* logits, const int64_t* labels, const fav_loss_params* p, int B,
+                           int K, float* probs, float* dlogits, float* scalars, void* stream) {
+  FAV_CHECK_ARG(logits && labels && p && dlogits && scalars, "fav_op_loss: null argument");
+  FAV_CUDA(cudaSetDevice(device));
+  return launch_loss(logits, labels, *p, B, K, probs, dlogits, scalars, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fav_op_delta_update(int device, float* delta, const float* grad, float* m, float* v, int64_t* step,
+                                   const fav_reg_params* reg, const fav_adam_params* adam, float adv_flag,
+                                   float* scalars, int T, void* stream) {
+  FAV_CHECK_ARG(delta && grad && m && v && step && reg && adam && scalars, "fav_op_delta_update: null argument");
+  FAV_CUDA(cudaSetDevice(device));
+  return launch_delta_update(delta, grad, m, v, step, *reg, *adam, adv_flag, scalars, T,
+                             static_cast<cudaStream_t>(stream));
+}

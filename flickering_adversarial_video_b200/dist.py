@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing for the sharded (universal / class-generalisation) attacks: one process per
+GPU, clips sharded on dim 0, delta replicated, ONE sum-all-reduce of the packed [T*3 | scalars] buffer
+per step.  The reference never had a working collective on this path (the TF
+MirroredStrategy is disabled at i3d_adversarial_main_universal.py:309-312, torch uses single-process
+nn.DataParallel, model.py:576-578); the semantics preserved are "sum of per-sample gradients" for the
+margin loss and "mean over the global batch" for the CE loss."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, **kw)
+    return rank, local_rank, world
+
+
+def shard_range(global_batch, rank, world):
+    """Contiguous equal shards; the reference drops remainders (`drop_remainder=True`,
+    i3d_adversarial_main_universal.py:241), so the global batch must divide evenly."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by {world} ranks")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_sum_(t, group=None):
+    """In-place sum over ranks of the packed gradient/scalar buffer (no-op for one rank)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def ce_grad_divisor(local_batch, world):
+    """The CE loss is a mean over the GLOBAL batch (utils/kinetics_i3d_utils.py:305): every rank
+    divides its per-sample terms by local_batch*world so that the sum over ranks is the global mean."""
+    return local_batch * world

@@ -1,0 +1,181 @@
+"""Attack loops of the three TF drivers, on top of the `kinetics_i3d` mirror.
+
+  single_video_attack  — i3d_adversarial_main_single_video_npy.py:115-337  (SINGLE_VIDEO_ATTACK)
+  class_gen_attack     — i3d_adversarial_main_single_class_gen.py:176-373  (CLASS_GEN_ATTACK)
+  universal_attack     — i3d_adversarial_main_universal.py:45-203,353-380  (UNIVERSAL_ATTACK)
+
+Differences kept on purpose: one forward + one backward per step instead of the
+reference's three forwards; BATCH_SIZE and MAX_NUM_STEP from the YAML are honoured; data arrives as
+iterables of (clip batch, labels) — TFRecord / .npy readers are SURVEY §8(f1).
+"""
+import os
+import pickle
+
+import numpy as np
+
+
+def _attack_kwargs(cfg):
+    return dict(learning_rate=0.001, beta_0=cfg.LAMBDA, beta_1=cfg.BETA_1, beta_2=cfg.BETA_2, beta_3=cfg.BETA_2,
+                cyclic_flag=float(cfg.CYCLIC_ATTACK))
+
+
+def _select_loss(k_i3d, cfg):
+    if cfg.IMPROVE_ADV_LOSS:
+        k_i3d.improve_adversarial_loss(margin=cfg.PROB_MARGIN, targeted=cfg.TARGETED_ATTACK, logits=cfg.USE_LOGITS)
+    else:
+        k_i3d.ce_adversarial_loss(targeted=cfg.TARGETED_ATTACK)
+
+
+def single_video_attack(k_i3d, rgb_sample, correct_cls_id, cfg, result_path=None, max_extra_steps=None,
+                        keep_history=True, log_every=0):
+    """Attack one clip until `step > MAX_NUM_STEP and adversarial`
+    (i3d_adversarial_main_single_video_npy.py:211-337).  Returns the result dict of App. D
+    (and writes `{cls}_beta1_{b1}_th_{:.2f}%_rg_{:.2f}%.pkl` when result_path is given), or None when
+    the clean clip is misclassified (the reference skips those: :137-139)."""
+    classes = k_i3d.get_kinetics_classes()
+    rgb_sample = np.asarray(rgb_sample)
+    model_softmax = k_i3d(rgb_sample, adv_flag=0)
+    top_id = int(model_softmax.argmax())
+    if top_id != int(correct_cls_id):
+        return None
+    _select_loss(k_i3d, cfg)
+    if cfg.TARGETED_ATTACK:
+        target_class_id = classes.index(cfg.TARGETED_CLASS)
+    else:
+        target_class_id = int(correct_cls_id)
+    kw = _attack_kwargs(cfg)
+    res = {"correct_cls_prob": float(model_softmax.max()), "correct_cls": classes[int(correct_cls_id)],
+           "correct_cls_id": int(correct_cls_id), "softmax_init": model_softmax, "rgb_sample": rgb_sample}
+    hist = {k: [] for k in ("total_loss_l", "adv_loss_l", "reg_loss_l", "norm_reg_loss_l", "diff_norm_reg_loss_l",
+                            "perturbation", "softmax", "fatness", "smoothness")}
+    k_i3d.reset()
+    step, max_step = 0, int(cfg.MAX_NUM_STEP)
+    hard_stop = None if max_extra_steps is None else max_step + int(max_extra_steps)
+    while True:
+        out = k_i3d.train_step(rgb_sample, [target_class_id], **kw)
+        # adversarial test on the UPDATED perturbation (the reference's second sess.run, :217)
+        soft = k_i3d(rgb_sample, adv_flag=1) if (step > max_step or keep_history) else out["softmax"]
+        pred = int(soft.argmax(-1)[0])
+        is_adv = (pred == target_class_id) if cfg.TARGETED_ATTACK else (pred != target_class_id)
+        if keep_history:
+            hist["total_loss_l"].append(out["loss"])
+            hist["adv_loss_l"].append(out["adversarial_loss"])
+            hist["reg_loss_l"].append(out["regularizer_loss"])
+            hist["norm_reg_loss_l"].append(out["norm_reg"])
+            hist["diff_norm_reg_loss_l"].append(out["diff_norm_reg"])
+            hist["perturbation"].append(k_i3d.eps_rgb.copy())
+            hist["softmax"].append(soft)
+            hist["fatness"].append(out["thickness"] / 2.0 * 100)
+            hist["smoothness"].append(out["roughness"] / 2.0 * 100)
+        if log_every and step % log_every == 0:
+            print("Step: {:05d}, Total Loss: {:.5f}, Cls Loss: {:.5f}, Total Reg Loss: {:.5f}, thickness: {:.5f} "
+                  "({:.2f} %), roughness: {:.5f} ({:.2f} %)".format(
+                      step, out["loss"], out["adversarial_loss"], out["regularizer_loss"], out["thickness"],
+                      out["thickness"] / 2.0 * 100, out["roughness"], out["roughness"] / 2.0 * 100))
+        if (step > max_step and is_adv) or (hard_stop is not None and step >= hard_stop):
+            if not keep_history:
+                hist["perturbation"].append(k_i3d.eps_rgb.copy())
+                hist["softmax"].append(soft)
+                hist["fatness"].append(out["thickness"] / 2.0 * 100)
+                hist["smoothness"].append(out["roughness"] / 2.0 * 100)
+            res.update(hist)
+            res["adv_video"] = k_i3d.adversarial_inputs_rgb_of(rgb_sample)
+            res["total_steps"] = step
+            res["beta_0"], res["beta_1"], res["beta_2"], res["beta_3"] = kw["beta_0"], kw["beta_1"], kw["beta_2"], kw["beta_3"]
+            res["is_adversarial"] = bool(is_adv)
+            if result_path:
+                os.makedirs(result_path, exist_ok=True)
+                fn = "{}_beta1_{}_th_{:.2f}%_rg_{:.2f}%.pkl".format(
+                    classes[int(correct_cls_id)].replace(" ", "_"), kw["beta_1"], res["fatness"][-1], res["smoothness"][-1])
+                with open(os.path.join(result_path, fn), "wb") as f:
+                    pickle.dump(res, f)
+                res["pkl_path"] = os.path.join(result_path, fn)
+            return res
+        step += 1
+
+
+def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, epochs=1, log_every=0):
+    """One perturbation over batches of one class; fooling rate on the validation set after every
+    pass; `res.pkl` layout of i3d_adversarial_main_single_class_gen.py:358-372.  `train_batches` /
+    `val_batches` are callables returning a fresh iterator of (clips, labels) (the reference re-inits
+    its tf.data iterators on OutOfRangeError, :334-337).  Stops at MAX_NUM_STEP."""
+    classes = k_i3d.get_kinetics_classes()
+    _select_loss(k_i3d, cfg)
+    kw = _attack_kwargs(cfg)
+    target_class_id = classes.index(cfg.TARGETED_CLASS) if cfg.TARGETED_ATTACK else None
+    res = {k: [] for k in ("total_loss_l", "adv_loss_l", "reg_loss_l", "norm_reg_loss_l", "diff_norm_reg_loss_l",
+                           "perturbation", "fatness", "smoothness", "fool_rate")}
+    step, max_step = 0, int(cfg.MAX_NUM_STEP)
+    miss_rate, _ = k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK, target_class_id=target_class_id)
+    res["fool_rate"].append(miss_rate)
+    for _ in range(epochs):
+        for rgb_sample, sample_label in train_batches():
+            labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
+            out = k_i3d.train_step(rgb_sample, labels, **kw)
+            res["total_loss_l"].append(out["loss"])
+            res["adv_loss_l"].append(out["adversarial_loss"])
+            res["reg_loss_l"].append(out["regularizer_loss"])
+            res["norm_reg_loss_l"].append(out["norm_reg"])
+            res["diff_norm_reg_loss_l"].append(out["diff_norm_reg"])
+            res["fatness"].append(out["thickness"] / 2.0 * 100)
+            res["smoothness"].append(out["roughness"] / 2.0 * 100)
+            res["perturbation"].append(k_i3d.eps_rgb.copy())
+            if log_every and step % log_every == 0:
+                print("Step: {:05d}, Total Loss: {:.5f}, Cls Loss: {:.5f}".format(step, out["loss"], out["adversarial_loss"]))
+            step += 1
+            if step >= max_step:
+                break
+        miss_rate, _ = k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK, target_class_id=target_class_id)
+        res["fool_rate"].append(miss_rate)
+        res["total_steps"], res["beta_1"], res["beta_2"] = step, kw["beta_1"], kw["beta_2"]
+        if result_path:
+            os.makedirs(result_path, exist_ok=True)
+            with open(os.path.join(result_path, "res.pkl"), "wb") as f:
+                pickle.dump(res, f)
+        if step >= max_step:
+            break
+    return res
+
+
+def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eval_every=None, log_every=0):
+    """UNIVERSAL_ATTACK with FLICKERING_ATTACK=True: same step as class-gen over all classes; returns
+    {'perturbation': [T,1,1,3], 'fool_rate': [...], 'scalars': TensorBoard-tag -> list}
+    (tags of i3d_adversarial_main_universal.py:176-196)."""
+    if not getattr(k_i3d, "flickering", True):
+        raise NotImplementedError("FLICKERING_ATTACK=False needs kinetics_i3d_L12 (not built yet)")
+    classes = k_i3d.get_kinetics_classes()
+    _select_loss(k_i3d, cfg)
+    kw = _attack_kwargs(cfg)
+    kw["cyclic_pert_flag"] = float(cfg.get("CYCLIC_PERTURBATION_ATTACK", False))
+    kw["beta_3"] = cfg.BETA_2                      # universal.py:130 weights the laplacian term by beta_2
+    target_class_id = classes.index(cfg.TARGETED_CLASS) if cfg.TARGETED_ATTACK else None
+    max_steps = int(cfg.MAX_NUM_STEP if max_steps is None else max_steps)
+    tags = {t: [] for t in ("Loss/total", "Loss/adversarial_loss", "Loss/regularizer_loss", "Loss/thickness",
+                            "Loss/first_order_temporal_diff", "Loss/second_order_temporal_diff",
+                            "Perturbation/thickness_%", "Perturbation/roughness_%", "Perturbation/max",
+                            "Perturbation/min", "Probability/prob_to_min", "Probability/prob_to_max")}
+    fool = []
+    step = 0
+    while step < max_steps:
+        for rgb_sample, sample_label in train_batches():
+            labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
+            out = k_i3d.train_step(rgb_sample, labels, **kw)
+            if step % 50 == 0:      # SummarySaverHook(save_steps=50) universal.py:198-201
+                eps = k_i3d.eps_rgb
+                vals = (out["loss"], out["adversarial_loss"], out["regularizer_loss"], out["norm_reg"],
+                        out["diff_norm_reg"], out["laplacian_norm_reg"], out["thickness_relative"],
+                        out["roughness_relative"], float(eps.max()), float(eps.min()),
+                        float(np.mean(out["to_min_prob"])), float(np.mean(out["to_max_prob"])))
+                for t, v in zip(tags, vals):
+                    tags[t].append((step, v))
+            if log_every and step % log_every == 0:
+                print("step {:05d} loss {:.5f}".format(step, out["loss"]))
+            step += 1
+            if eval_every and step % eval_every == 0:
+                fool.append((step, k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK,
+                                                  target_class_id=target_class_id)[0]))
+            if step >= max_steps:
+                break
+    fool.append((step, k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK,
+                                      target_class_id=target_class_id)[0]))
+    return {"perturbation": k_i3d.eps_rgb, "fool_rate": fool, "scalars": tags, "total_steps": step}

@@ -147,3 +147,30 @@ def op_maxpool3d_bwd(dy, idx, in_shape, k, s, add=None, relu_src=None):
                                      L.ptr(dx), B, T, H, W, Cc, k[0], k[1], k[2], s[0], s[1], s[2],
                                      L.stream_ptr()), "fav_op_maxpool3d_bwd")
     return dx
+
+
+def op_loss(logits, labels, improve_loss=True, targeted=False, use_logits=False, margin=0.05, stack=L.FAV_STACK_TF,
+            global_batch=0):
+    """returns (probs, dlogits, scalars) — the loss kernel on caller tensors"""
+    lib = L.load()
+    B, K = logits.shape
+    probs = torch.empty_like(logits)
+    dlogits = torch.empty_like(logits)
+    scalars = torch.zeros(L.S_COUNT, dtype=torch.float32, device=logits.device)
+    p = L.LossParams(int(improve_loss), int(targeted), int(use_logits), margin, 1.0, global_batch, stack)
+    L.check(lib.fav_op_loss(logits.device.index or 0, L.ptr(logits), L.ptr(labels), C.byref(p), B, K, L.ptr(probs),
+                            L.ptr(dlogits), L.ptr(scalars), L.stream_ptr()), "fav_op_loss")
+    return probs, dlogits, scalars
+
+
+def op_delta_update(delta, grad, m, v, step, beta0, beta1, beta2, beta3, lr=1e-3, delta_clip=0.4, stack=L.FAV_STACK_TF,
+                    adv_flag=1.0, scalars=None):
+    lib = L.load()
+    if scalars is None:
+        scalars = torch.zeros(L.S_COUNT, dtype=torch.float32, device=delta.device)
+    reg = L.RegParams(beta0, beta1, beta2, beta3, delta_clip)
+    adam = L.AdamParams(lr, 0.9, 0.999, 1e-8, stack)
+    L.check(lib.fav_op_delta_update(delta.device.index or 0, L.ptr(delta), L.ptr(grad), L.ptr(m), L.ptr(v), L.ptr(step),
+                                    C.byref(reg), C.byref(adam), adv_flag, L.ptr(scalars), delta.shape[0],
+                                    L.stream_ptr()), "fav_op_delta_update")
+    return scalars

@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's TF attack operator surface (utils/kinetics_i3d_utils.py:76-307),
+eager instead of graph-mode: the same constructor keywords, attribute names and methods, backed by
+the libfav engine.
+
+Reference execution model: drivers build a loss from the object's tensor handles, create Adam on
+`eps_rgb`, then `sess.run(fetches, feed_dict)` (i3d_adversarial_main_single_video_npy.py:37-84,
+211-215).  Here `improve_adversarial_loss(...)` / `ce_adversarial_loss(...)` select the loss,
+`train_step(...)` is one `sess.run([train_op, loss, ...])`, and the attribute names the drivers fetch
+(`softmax`, `model_logits`, `norm_reg`, `thickness`, `to_min_prob`, …) are properties holding the
+values of the last step as numpy arrays, exactly what `sess.run` returned.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .attack import FlickerAttack
+
+_IMAGE_SIZE = 224
+_SAMPLE_VIDEO_FRAMES = 90     # utils/kinetics_i3d_utils.py:12 (a parameter here: `frames=`)
+NUM_CLASSES = 400
+_LABEL_MAP_PATH = "data/label_map.txt"
+
+
+def load_kinetics_classes(eval_type="rgb", label_map_path=_LABEL_MAP_PATH):
+    """utils/kinetics_i3d_utils.py:67-74 (rgb600 was never functional in the reference: :70)."""
+    if eval_type == "rgb600":
+        raise ValueError("rgb600 is not supported (the reference's _LABEL_MAP_PATH_600 is undefined)")
+    if not os.path.exists(label_map_path):
+        return [f"class_{i:03d}" for i in range(NUM_CLASSES)]
+    return [x.strip() for x in open(label_map_path)]
+
+
+def load_weights(ckpt_path):
+    """Weights as {tf variable name: float32 array}.  Accepts an .npz with the reference checkpoint's
+    variable names (`RGB/inception_i3d/...`); TF1 checkpoint ingest itself is SURVEY §8(f2)."""
+    if isinstance(ckpt_path, dict):
+        return ckpt_path
+    if ckpt_path and os.path.exists(ckpt_path) and ckpt_path.endswith(".npz"):
+        with np.load(ckpt_path) as z:
+            return {k: z[k].astype(np.float32) for k in z.files}
+    raise FileNotFoundError(
+        f"checkpoint '{ckpt_path}' not found or not an .npz of TF variable names; "
+        "pass weights=<dict> (e.g. synthetic.i3d_weights()) — there is no network to fetch the Kinetics ckpt")
+
+
+class kinetics_i3d:
+    """Drop-in for ki3du.kinetics_i3d(ckpt_path, batch_size, init_model, rgb_input, labels,
+    cyclic_flag_default_c, cyclic_pert_flag_default_c, default_adv_flag_c)."""
+
+    flickering = True
+
+    def __init__(self, ckpt_path="data/checkpoints/rgb_imagenet/model.ckpt", batch_size=1, init_model=True,
+                 rgb_input=None, labels=None, cyclic_flag_default_c=0.0, cyclic_pert_flag_default_c=0.0,
+                 default_adv_flag_c=1.0, frames=_SAMPLE_VIDEO_FRAMES, weights=None, device=0,
+                 label_map_path=_LABEL_MAP_PATH, seed=0):
+        self.ckpt_path = ckpt_path
+        self.batch_size = batch_size
+        self.frames = frames
+        self.adv_flag = float(default_adv_flag_c)
+        self.cyclic_flag = float(cyclic_flag_default_c)
+        self.cyclic_pert_flag = float(cyclic_pert_flag_default_c)
+        self.kinetics_classes = load_kinetics_classes(label_map_path=label_map_path)
+        w = load_weights(weights if weights is not None else ckpt_path)
+        self._atk = FlickerAttack(w, batch_size, frames, {}, device=device)
+        self.device = self._atk.device
+        self._rng = np.random.RandomState(seed)
+        self._loss_cfg = dict(improve=True, margin=0.05, targeted=False, logits=False)
+        self._last = {}
+        self.rgb_input = rgb_input
+        self.labels = labels
+
+    # ---- the handles the drivers read (values of the last run) ------------------------------
+    @property
+    def eps_rgb(self):
+        return self._atk.perturbation.detach().cpu().numpy()
+
+    perturbation = eps_rgb
+
+    def set_perturbation(self, value):
+        self._atk.delta.copy_(torch.as_tensor(np.asarray(value), dtype=torch.float32).reshape(self.frames, 3))
+
+    def __getattr__(self, name):
+        last = self.__dict__.get("_last", {})
+        if name in last:
+            return last[name]
+        raise AttributeError(name)
+
+    def get_kinetics_classes(self):
+        return self.kinetics_classes
+
+    # ---- loss selection (utils/kinetics_i3d_utils.py:253-307) --------------------------------
+    def improve_adversarial_loss(self, margin=0.05, targeted=False, logits=False):
+        self._loss_cfg = dict(improve=True, margin=float(margin), targeted=bool(targeted), logits=bool(logits))
+        return "adversarial_loss_total"
+
+    def ce_adversarial_loss(self, targeted=False):
+        self._loss_cfg = dict(improve=False, margin=0.05, targeted=bool(targeted), logits=False)
+        return "adversarial_loss_total"
+
+    def _configure(self):
+        a, c = self._atk, self._loss_cfg
+        a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
+
+    def _to_device_clip(self, inputs):
+        t = torch.as_tensor(inputs)
+        if t.dtype not in (torch.uint8, torch.float32):
+            t = t.to(torch.float32)
+        t = t.reshape(self.batch_size, self.frames, _IMAGE_SIZE, _IMAGE_SIZE, 3)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    # ---- sess.run equivalents ----------------------------------------------------------------
+    def __call__(self, inputs, adv_flag=0):
+        """softmax for `inputs` (utils/kinetics_i3d_utils.py:210-212)."""
+        clips = self._to_device_clip(inputs)
+        self.prob = self._atk.predict(clips, adv_flag=float(adv_flag)).cpu().numpy()
+        return self.prob
+
+    def train_step(self, inputs, labels, learning_rate=1e-3, beta_0=1.0, beta_1=0.1, beta_2=0.1, beta_3=0.1,
+                   cyclic_flag=None, cyclic_pert_flag=None, adv_flag=None):
+        """One `sess.run([train_op, loss, adversarial_loss, regularizer_loss, norm_reg, diff_norm_reg,
+        laplacian_norm_reg, thickness, roughness, prob_to_max, prob_to_min], feed_dict)`.
+        The fetched values describe the perturbation BEFORE the update, the returned softmax is
+        evaluated AFTER it (the reference's second sess.run, single_video_npy.py:217) only on request
+        via `softmax_after_update`."""
+        self._configure()
+        a = self._atk
+        clips = self._to_device_clip(inputs)
+        lab = torch.as_tensor(np.asarray(labels), dtype=torch.int64).reshape(-1).to(self.device)
+        cyc = self.cyclic_flag if cyclic_flag is None else float(cyclic_flag)
+        cycp = self.cyclic_pert_flag if cyclic_pert_flag is None else float(cyclic_pert_flag)
+        flag = self.adv_flag if adv_flag is None else float(adv_flag)
+        shift_p = 0
+        if cyc:       # tf.roll(rgb_input, random_shift, axis=1)   (kinetics_i3d_utils.py:115-116,135)
+            clips = torch.roll(clips, int(self._rng.randint(0, self.frames)), dims=1).contiguous()
+        if cycp:      # tf.roll(input_pert, random_shift_2, axis=0) (:130-131,137)
+            shift_p = int(self._rng.randint(0, self.frames))
+        a.beta0, a.beta1, a.beta2, a.beta3 = float(beta_0), float(beta_1), float(beta_2), float(beta_3)
+        if shift_p:
+            self._step_rolled(clips, lab, flag, float(learning_rate), shift_p)
+        else:
+            a.step(clips, lab, adv_flag=flag, lr=float(learning_rate))
+        sc = a.scalars.cpu().numpy()
+        B = self.batch_size
+        logits = a.eng.logits.cpu().numpy()
+        probs = a.eng.probs.cpu().numpy()
+        reg = beta_1 * sc[L.S_NORM_REG] + beta_2 * sc[L.S_DIFF_REG] + beta_3 * sc[L.S_LAP_REG]
+        lab_np = lab.cpu().numpy()
+        label_prob = probs[np.arange(B), lab_np]
+        onehot = np.eye(probs.shape[1], dtype=np.float32)[lab_np]
+        max_non_label_prob = (probs - onehot).max(-1)
+        tmin, tmax = (max_non_label_prob, label_prob) if self._loss_cfg["targeted"] else (label_prob, max_non_label_prob)
+        self._last = dict(
+            loss=float(sc[L.S_ADV_LOSS] + beta_0 * reg), adversarial_loss=float(sc[L.S_ADV_LOSS]),
+            adversarial_loss_total=float(sc[L.S_ADV_LOSS]), regularizer_loss=float(reg),
+            norm_reg=float(sc[L.S_NORM_REG]), diff_norm_reg=float(sc[L.S_DIFF_REG]),
+            laplacian_norm_reg=float(sc[L.S_LAP_REG]), thickness=float(sc[L.S_THICKNESS]),
+            roughness=float(sc[L.S_ROUGHNESS]), thickness_relative=float(sc[L.S_THICKNESS]) / 2.0 * 100,
+            roughness_relative=float(sc[L.S_ROUGHNESS]) / 2.0 * 100, to_min_prob=tmin, to_max_prob=tmax,
+            model_logits=logits, softmax=probs, label_prob=label_prob, max_non_label_prob=max_non_label_prob,
+            fooled_count=int(sc[L.S_FOOLED]))
+        return self._last
+
+    def _step_rolled(self, clips, lab, flag, lr, shift):
+        """cyclic perturbation attack: the network sees roll(delta, shift); the gradient is rolled back."""
+        a, e = self._atk, self._atk.eng
+        rolled = torch.roll(a.delta, shift, dims=0).contiguous()
+        e.apply(clips, rolled, adv_flag=flag, delta_clip=a.delta_clip)
+        e.forward()
+        e.loss(lab, improve_loss=a.improve_loss, targeted=a.targeted, use_logits=a.use_logits, margin=a.margin,
+               global_batch=a.global_batch, stack=a.stack)
+        e.backward()
+        # d/d(delta) = roll^-1 of d/d(rolled); the +-0.4 clip mask commutes with the roll
+        a.grad.copy_(torch.roll(a.grad, -shift, dims=0))
+        if a.world > 1:
+            torch.distributed.all_reduce(a.comm, group=a.pg)
+        e.update(a.delta, a.grad, a.m, a.v, a.step_count, a.beta0, a.beta1, a.beta2, a.beta3, lr=lr,
+                 delta_clip=a.delta_clip, stack=a.stack)
+
+    def adversarial_inputs_rgb_of(self, inputs):
+        """sess.run(adversarial_inputs_rgb, {inputs: rgb_sample}) — fp32 [B,T,224,224,3]."""
+        return self._atk.adversarial_video(self._to_device_clip(inputs)).cpu().numpy()
+
+    def adversarial_video_uint8(self, inputs):
+        """((adv+1.0)*127.5).astype(uint8) — utils/stats_and_plot/stats_plots.py:57, bit-exact."""
+        return self._atk.adversarial_video(self._to_device_clip(inputs), as_uint8=True).cpu().numpy()
+
+    def reset(self):
+        """sess.run(eps_rgb.initializer); sess.run(tf.variables_initializer(optimizer.variables()))"""
+        self._atk.reset()
+
+    def evaluate(self, next_element_val, targeted_attack=False, target_class_id=None, cyclic=0,
+                 exclude_misclassify=True):
+        """Fooling ratio over a validation iterable of (rgb_sample, sample_label) batches
+        (utils/kinetics_i3d_utils.py:217-250).  Returns (miss_rate, total_val_vid)."""
+        miss, total = 0, 0
+        for rgb_sample, sample_label in next_element_val:
+            clips = self._to_device_clip(rgb_sample)
+            if cyclic:
+                clips = torch.roll(clips, int(self._rng.randint(0, self.frames)), dims=1).contiguous()
+            sample_label = np.asarray(sample_label).reshape(-1)
+            prob = self._atk.predict(clips, adv_flag=1.0).cpu().numpy()
+            pred = prob.argmax(-1)
+            miss_cond = (pred == target_class_id) if targeted_attack else (pred != sample_label)
+            if exclude_misclassify:
+                prob_clean = self._atk.predict(self._to_device_clip(rgb_sample), adv_flag=0.0).cpu().numpy()
+                valid = prob_clean.argmax(-1) == sample_label
+                miss += int(np.logical_and(miss_cond, valid).sum())
+                total += int(valid.sum())
+            else:
+                miss += int(miss_cond.sum())
+                total += int(miss_cond.shape[0])
+        return (miss / total if total else 0.0), total
+
+    def close(self):
+        self._atk.close()
+
+
+class kinetics_i3d_L12:
+    """Sparse per-pixel baseline (utils/kinetics_i3d_utils.py:308-521, FLICKERING_ATTACK=False).
+    SURVEY §8 row a16; not built in round 1 (needs the dense stem data-gradient kernel)."""
+
+    flickering = False
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError(
+            "kinetics_i3d_L12 (per-pixel perturbation, FLICKERING_ATTACK=False) is not built yet: "
+            "see DESIGN.md §Scope (row a16)")

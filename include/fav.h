@@ -176,6 +176,16 @@ int fav_op_maxpool3d_bwd(int device, const void* dy, const uint8_t* idx, const v
                          const void* relu_src, void* dx, int B, int T, int H, int W, int C,
                          int kt, int kh, int kw, int st, int sh, int sw, void* stream);
 
+/* softmax + adversarial loss + dloss/dlogits on caller buffers (same kernel as fav_loss):
+ * logits DEVICE [B,K] f32, labels DEVICE [B] i64, probs DEVICE [B,K] or NULL, dlogits DEVICE [B,K],
+ * scalars DEVICE [FAV_S_COUNT].  Torch-stack rules (model.py:177-250) when p->stack == FAV_STACK_TORCH. */
+int fav_op_loss(int device, const float* logits, const int64_t* labels, const fav_loss_params* p, int B, int K,
+                float* probs, float* dlogits, float* scalars, void* stream);
+/* kernel (c) on caller buffers (same kernel as fav_delta_update); delta/grad/m/v DEVICE [T,3]. */
+int fav_op_delta_update(int device, float* delta, const float* grad, float* m, float* v, int64_t* step,
+                        const fav_reg_params* reg, const fav_adam_params* adam, float adv_flag, float* scalars,
+                        int T, void* stream);
+
 /* debug/introspection: copy a named internal activation (bf16 -> f32, NDHWC, unpadded channels)
  * to a DEVICE f32 buffer; returns element count or <0.  Names follow i3d.py end points
  * ("Conv3d_1a_7x7", "Mixed_3b", ...), prefix "grad:" for the gradient buffer. */

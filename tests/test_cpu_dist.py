@@ -1,0 +1,79 @@
+"""not gpu: the N>1 host logic on CPU with the gloo backend, world_size 2.  Each rank evaluates the
+oracle's data gradient on its shard of the clip batch; the packed buffer is sum-all-reduced exactly as
+FlickerAttack.step does; rank 0 checks it against the single-process full-batch gradient."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, loss_kind, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    from flickering_adversarial_video_b200 import dist as fdist, synthetic
+    from oracle import oracle_i3d as O
+    r, _, w = fdist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    T, GB = 16, 2
+    weights = synthetic.i3d_weights(0)
+    model = O.OracleI3D(weights)
+    clips = synthetic.clips_u8(GB, T, seed=1001)
+    labels_all = torch.tensor([156, 156])
+    delta = synthetic.delta_uniform(T, seed=7, lo=-0.05, hi=0.05)
+    lo, hi = fdist.shard_range(GB, rank, world)
+    x = O.normalize_u8(clips[lo:hi])
+    d = delta.clone().requires_grad_(True)
+    logits = model.forward(O.apply_flicker(x, d))
+    if loss_kind == "improve":
+        loss, _, _ = O.improve_adversarial_loss(logits, labels_all[lo:hi])          # SUM over samples
+    else:
+        ce, _, _ = O.ce_adversarial_loss(logits, labels_all[lo:hi])                  # local mean ...
+        loss = ce * (hi - lo) / fdist.ce_grad_divisor(hi - lo, world)              # ... -> share of the global mean
+    (g,) = torch.autograd.grad(loss, d)
+    comm = torch.cat([g.reshape(-1), loss.detach().reshape(1)])
+    fdist.allreduce_sum_(comm)
+    if rank == 0:
+        ret["grad"] = comm[:-1].reshape(T, 3).clone()
+        ret["loss"] = float(comm[-1])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("loss_kind", ["improve", "ce"])
+def test_sharded_gradient_equals_full_batch(loss_kind):
+    from flickering_adversarial_video_b200 import synthetic
+    from oracle import oracle_i3d as O
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), loss_kind, ret), nprocs=2, join=True)
+    T = 16
+    model = O.OracleI3D(synthetic.i3d_weights(0))
+    x = O.normalize_u8(synthetic.clips_u8(2, T, seed=1001))
+    labels = torch.tensor([156, 156])
+    d = synthetic.delta_uniform(T, seed=7, lo=-0.05, hi=0.05).requires_grad_(True)
+    logits = model.forward(O.apply_flicker(x, d))
+    loss = O.improve_adversarial_loss(logits, labels)[0] if loss_kind == "improve" else O.ce_adversarial_loss(logits, labels)[0]
+    (g,) = torch.autograd.grad(loss, d)
+    assert abs(ret["loss"] - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
+    rel = float((ret["grad"] - g.reshape(T, 3)).norm() / g.norm())
+    assert rel < 1e-2, rel      # fp32 summation order (and a few ReLU masks) differ between the sharded and the full-batch run
+
+
+def test_shard_range_rules():
+    from flickering_adversarial_video_b200 import dist as fdist
+    assert fdist.shard_range(64, 3, 8) == (24, 32)
+    with pytest.raises(ValueError):
+        fdist.shard_range(10, 0, 4)
+    assert fdist.ce_grad_divisor(8, 8) == 64

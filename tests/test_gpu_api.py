@@ -1,0 +1,112 @@
+"""-m gpu: the host-side mirror of the reference's operator surface (kinetics_i3d object, drivers,
+result layouts) and attack-outcome parity against the oracle."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+T = 16
+
+
+@pytest.fixture(scope="module")
+def k_i3d():
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.kinetics_i3d import kinetics_i3d
+    k = kinetics_i3d(ckpt_path="", batch_size=1, frames=T, weights=synthetic.i3d_weights(0))
+    yield k
+    k.close()
+
+
+def test_reference_attribute_surface(k_i3d):
+    from flickering_adversarial_video_b200 import synthetic
+    clip = synthetic.clips_u8(1, T, seed=1001).numpy()
+    prob = k_i3d(clip, adv_flag=0)
+    assert prob.shape == (1, 400) and abs(prob.sum() - 1) < 1e-4
+    k_i3d.improve_adversarial_loss(margin=0.05, targeted=False, logits=False)
+    k_i3d.reset()
+    out = k_i3d.train_step(clip, [int(prob.argmax())], learning_rate=1e-3, beta_0=1.0, beta_1=0.5, beta_2=0.5, beta_3=0.5)
+    # names the reference drivers fetch (i3d_adversarial_main_single_video_npy.py:61-77, universal.py:90-109)
+    for name in ("softmax", "model_logits", "norm_reg", "diff_norm_reg", "laplacian_norm_reg", "thickness", "roughness",
+                 "thickness_relative", "roughness_relative", "to_min_prob", "to_max_prob"):
+        assert getattr(k_i3d, name) is not None and name in out
+    assert k_i3d.eps_rgb.shape == (T, 1, 1, 3) and k_i3d.perturbation.shape == (T, 1, 1, 3)
+    assert np.abs(k_i3d.eps_rgb).max() <= 1.001e-3          # first Adam step moves every element by <= lr
+    assert len(k_i3d.get_kinetics_classes()) == 400
+    adv8 = k_i3d.adversarial_video_uint8(clip)
+    advf = k_i3d.adversarial_inputs_rgb_of(clip)
+    assert adv8.dtype == np.uint8 and np.array_equal(adv8, ((advf + np.float32(1.0)) * np.float32(127.5)).astype(np.uint8))
+
+
+def test_single_video_driver_and_pkl_layout(k_i3d, tmp_path):
+    from flickering_adversarial_video_b200 import config, synthetic
+    from flickering_adversarial_video_b200.drivers import single_video_attack
+    cfg = config.default_config().SINGLE_VIDEO_ATTACK
+    cfg.MAX_NUM_STEP = 3
+    clip_u8 = synthetic.clips_u8(1, T, seed=1001)
+    rgb_sample = (clip_u8.float() / 128.0 - 1.0).numpy()    # the .npy clips are stored normalised (single_video_npy.py:121)
+    label = int(k_i3d(rgb_sample, adv_flag=0).argmax())
+    res = single_video_attack(k_i3d, rgb_sample, label, cfg, result_path=str(tmp_path), max_extra_steps=4)
+    assert res is not None and os.path.exists(res["pkl_path"])
+    with open(res["pkl_path"], "rb") as f:
+        d = pickle.load(f)
+    # keys written by the reference (single_video_npy.py:177-181,314-334) and read by its viewer
+    for key in ("correct_cls_prob", "correct_cls", "correct_cls_id", "softmax_init", "rgb_sample", "total_loss_l",
+                "adv_loss_l", "reg_loss_l", "norm_reg_loss_l", "diff_norm_reg_loss_l", "perturbation", "adv_video",
+                "softmax", "total_steps", "beta_0", "beta_1", "beta_2", "beta_3", "fatness", "smoothness"):
+        assert key in d, key
+    assert d["adv_video"].shape == (1, T, 224, 224, 3) and d["perturbation"][-1].shape == (T, 1, 1, 3)
+    assert len(d["total_loss_l"]) == d["total_steps"] + 1
+    # wrong label -> the reference skips the clip
+    assert single_video_attack(k_i3d, rgb_sample, (label + 1) % 400, cfg) is None
+
+
+def test_attack_outcome_parity(k_i3d):
+    """north_star gate: same fooled / not-fooled outcome, thickness and roughness within 5 % of the
+    oracle after the same number of Adam steps on the same clip."""
+    from flickering_adversarial_video_b200 import synthetic
+    from oracle import oracle_i3d as O
+    steps = 12
+    clip_u8 = synthetic.clips_u8(1, T, seed=1001)
+    x = O.normalize_u8(clip_u8)
+    model = O.OracleI3D(synthetic.i3d_weights(0))
+    with torch.no_grad():
+        label = model.forward(x).argmax(-1)
+    cfg = dict(improve_loss=True, margin=0.05, beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5, lr=1e-3)
+    opt = O.TFAdam((T, 3))
+    delta = torch.zeros((T, 3))
+    for _ in range(steps):
+        out = O.attack_step(model, x, label, delta, cfg, opt=opt)
+        delta = out["delta_new"]
+    _, _, _, th_ref, ro_ref = O.regularizers(delta)
+    with torch.no_grad():
+        fooled_ref = bool(model.forward(O.apply_flicker(x, delta)).argmax(-1) != label)
+    k_i3d.improve_adversarial_loss(margin=0.05)
+    k_i3d.reset()
+    for _ in range(steps):
+        k_i3d.train_step(clip_u8.numpy(), label.numpy(), learning_rate=1e-3, beta_0=1.0, beta_1=0.5, beta_2=0.5, beta_3=0.5)
+    d = torch.tensor(k_i3d.eps_rgb.reshape(T, 3))
+    _, _, _, th, ro = O.regularizers(d)
+    fooled = bool(k_i3d(clip_u8.numpy(), adv_flag=1).argmax(-1)[0] != int(label))
+    print(f"after {steps} steps: thickness engine {float(th):.5f} oracle {float(th_ref):.5f}; roughness engine "
+          f"{float(ro):.5f} oracle {float(ro_ref):.5f}; fooled engine {fooled} oracle {fooled_ref}")
+    assert fooled == fooled_ref
+    assert abs(float(th) / float(th_ref) - 1) < 0.05
+    assert abs(float(ro) / float(ro_ref) - 1) < 0.05
+
+
+def test_class_gen_driver(k_i3d):
+    from flickering_adversarial_video_b200 import config, synthetic
+    from flickering_adversarial_video_b200.drivers import class_gen_attack
+    cfg = config.default_config().CLASS_GEN_ATTACK
+    cfg.MAX_NUM_STEP = 2
+    clips = [synthetic.clips_u8(1, T, seed=1001 + i).numpy() for i in range(2)]
+    labels = [[int(k_i3d(c, adv_flag=0).argmax())] for c in clips]
+    batches = lambda: iter(list(zip(clips, labels)))
+    res = class_gen_attack(k_i3d, batches, batches, cfg)
+    for key in ("total_loss_l", "adv_loss_l", "reg_loss_l", "norm_reg_loss_l", "diff_norm_reg_loss_l", "perturbation",
+                "total_steps", "beta_1", "beta_2", "fatness", "smoothness", "fool_rate"):
+        assert key in res, key
+    assert res["total_steps"] == 2 and len(res["fool_rate"]) == 2
