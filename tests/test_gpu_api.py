@@ -68,7 +68,7 @@ def test_attack_outcome_parity(k_i3d):
     oracle after the same number of Adam steps on the same clip."""
     from flickering_adversarial_video_b200 import synthetic
     from oracle import oracle_i3d as O
-    steps = 12
+    steps = 60
     clip_u8 = synthetic.clips_u8(1, T, seed=1001)
     x = O.normalize_u8(clip_u8)
     model = O.OracleI3D(synthetic.i3d_weights(0))
