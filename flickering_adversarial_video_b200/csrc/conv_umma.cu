@@ -12,6 +12,7 @@
 #include "conv_umma.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -44,6 +45,64 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int tile) {
   c.t0 = ti * g.bt;
   c.n0 = nt * g.bn;
   return c;
+}
+
+// Epilogue of one accumulator row: TMEM -> registers (16 fp32 columns at a time) -> bias / addend /
+// ReLU / ReLU-mask -> bf16 -> 16-byte stores into the NDHWC channel slice.
+__device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
+                                                 __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
+                                                 const __nv_bfloat16* add_row, const float* bias_row) {
+  for (int c = 0; c < bn; c += 16) {
+  uint32_t r[16];
+  tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r);
+  tmem_ld_wait();
+  const int n = n0 + c;  // first output channel of this chunk
+  if (valid && n < e.cout_store) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias_row) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
+        v[j] += bv.x;
+        v[j + 1] += bv.y;
+        v[j + 2] += bv.z;
+        v[j + 3] += bv.w;
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (n + half * 8 + 8 <= e.cout_store) {
+        float* vv = v + half * 8;
+        if (add_row) {
+          const uint4 a = *reinterpret_cast<const uint4*>(add_row + n + half * 8);
+          vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x);
+          vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
+          vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z);
+          vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+        }
+        if (mask_row) {
+          const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n + half * 8);
+          vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
+          vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
+          vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
+          vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(vv[0], vv[1]);
+        o.y = pack_bf16x2(vv[2], vv[3]);
+        o.z = pack_bf16x2(vv[4], vv[5]);
+        o.w = pack_bf16x2(vv[6], vv[7]);
+        *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
+      }
+    }
+  }
+}
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -112,19 +171,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         tc.t0 + dt + g.ot, tc.b);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
           } else {
+            // stage = one temporal tap kt: the 7 kh taps are 7 (A,B) sub-tiles.
             // input index = 2*o + k - pad = 2*(o + q) + parity
-            const int kti = kb / g.kh;
-            const int khi = kb - kti * g.kh;
-            const int offt = kti - g.stem_pt;
-            const int offh = khi - g.stem_ph;
+            const int offt = kb - g.stem_pt;
             const int pt = offt & 1;
-            const int ph = offh & 1;
             const int qt = (offt - pt) >> 1;
-            const int qh = (offh - ph) >> 1;
-            const int mi = pt * 2 + ph;
-            const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-            tma_load_5d(sa, tm, &full_bar[stage], 0, tc.w0, tc.h0 + qh, tc.t0 + qt, tc.b);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * 32, tc.n0);
+            for (int khi = 0; khi < g.kh; ++khi) {
+              const int offh = khi - g.stem_ph;
+              const int ph = offh & 1;
+              const int qh = (offh - ph) >> 1;
+              const int mi = pt * 2 + ph;
+              const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+              tma_load_5d(sa + khi * (128 * 64), tm, &full_bar[stage], 0, tc.w0, tc.h0 + qh, tc.t0 + qt, tc.b);
+              tma_load_2d(sb + khi * (g.bn * 64), &tmB, &full_bar[stage], (kb * g.kh + khi) * 32, tc.n0);
+            }
           }
           if (++stage == stages) {
             stage = 0;
@@ -135,46 +195,55 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, g.bn);
-      const uint32_t row_bytes = g.stem ? 64u : 128u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // The whole warp walks the pipeline in lock-step (warp-uniform state stays in uniform registers);
+    // one elected lane issues the tcgen05 instructions.  The issue loop is the critical resource for
+    // small tiles: every instruction in it costs tensor-pipe idle time.
+    const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+    const uint32_t row_bytes = g.stem ? 64u : 128u;
+    const uint32_t desc_hi = umma_desc_hi(row_bytes);
+    const int sub = g.stem ? g.kh : 1;                 // (A,B) operand pairs per pipeline stage
+    const uint32_t a_sub = 128u * row_bytes;           // bytes per A sub-tile
+    const uint32_t b_sub = static_cast<uint32_t>(g.bn) * row_bytes;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+      uint32_t accum = 0;
+      int cb = 0;
+      for (int kb = 0; kb < g.nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
-        for (int kb = 0; kb < g.nkb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
-          const uint64_t adesc = umma_smem_desc(sa, row_bytes);
-          const uint64_t bdesc = umma_smem_desc(sb, row_bytes);
-          int ksteps;
-          if (g.stem) {
-            ksteps = 2;
-          } else {
-            const int cb = kb % g.cblocks;
-            ksteps = min(4, (g.cin - cb * 64) >> 4);
-          }
-          for (int k = 0; k < ksteps; ++k) {
-            // +32 bytes (16 bf16 of K) inside the swizzled row: +2 in the 16-byte address field
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
+        const int ksteps = g.stem ? 2 : min(4, (g.cin - cb * 64) >> 4);
+        if (elect_one()) {
+          for (int su = 0; su < sub; ++su) {
+            const uint32_t a_lo = umma_desc_lo(sa + su * a_sub);
+            const uint32_t b_lo = umma_desc_lo(sb + su * b_sub);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
+                accum = 1;
+              }
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == g.nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++cb == g.cblocks) cb = 0;
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -208,57 +277,193 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * kAccCols);
-      for (int c = 0; c < g.bn; c += 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r);
-        tmem_ld_wait();
-        const int n = tc.n0 + c;  // first output channel of this chunk
-        if (valid && n < e.cout_store) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (bias_row) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
-              v[j] += bv.x;
-              v[j + 1] += bv.y;
-              v[j + 2] += bv.z;
-              v[j + 3] += bv.w;
-            }
+      epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, bias_row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Halo kernel: 3x3x3, stride 1, SAME.  The per-tap kernel above streams a fresh 16 KB A box through
+// L2 for each of the 27 taps; here one TMA box per (64-channel block, dt) brings (nrows+2) x (W+2)
+// zero-padded positions into shared memory once and the 9 in-plane taps are row windows of it.
+// ---------------------------------------------------------------------------------------------
+struct HaloTile {
+  int b, t, h0, n0;
+};
+__device__ __forceinline__ HaloTile decode_halo_tile(const ConvGeom& g, int tile) {
+  HaloTile c;
+  const int nt = tile % g.n_tiles;
+  int m = tile / g.n_tiles;
+  const int hi = m % g.th;
+  m /= g.th;
+  c.t = m % g.T;
+  c.b = m / g.T;
+  c.h0 = hi * g.nrows;
+  c.n0 = nt * g.bn;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGeom g, const ConvEpilogue e, const int b_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + static_cast<size_t>(g.na) * g.slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(g.nb) * b_bytes);
+  uint64_t* a_full = bars;            // [4]
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* b_full = bars + 8;        // [8]
+  uint64_t* b_empty = bars + 16;      // [8]
+  uint64_t* tfull_bar = bars + 24;    // [2]
+  uint64_t* tempty_bar = bars + 26;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int slabs_per_tile = g.cblocks * 3;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < g.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      // A slabs run one slab ahead of the B tiles that consume them
+      auto issue_slab = [&](const HaloTile& tc, int sidx) {
+        const int cb = sidx / 3;
+        const int dt = sidx - cb * 3;
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(g.slab_tx));
+        tma_load_5d(smem_a + static_cast<size_t>(sa) * g.slab_bytes, &tmA, &a_full[sa], cb * 64, -1, tc.h0 - 1,
+                    tc.t + dt - 1, tc.b);
+        if (++sa == g.na) { sa = 0; pa ^= 1; }
+      };
+      bool first = true;
+      HaloTile cur{};
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        cur = decode_halo_tile(g, tile);
+        if (first) { issue_slab(cur, 0); first = false; }
+        for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
+          // prefetch the next slab (of this tile or of the next tile of this CTA)
+          if (sidx + 1 < slabs_per_tile) {
+            issue_slab(cur, sidx + 1);
+          } else if (tile + static_cast<int>(gridDim.x) < total_tiles) {
+            issue_slab(decode_halo_tile(g, tile + gridDim.x), 0);
           }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (n + half * 8 + 8 <= e.cout_store) {
-              float* vv = v + half * 8;
-              if (add_row) {
-                const uint4 a = *reinterpret_cast<const uint4*>(add_row + n + half * 8);
-                vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x);
-                vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
-                vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z);
-                vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
-              }
-              if (e.relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
-              }
-              if (mask_row) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n + half * 8);
-                vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
-                vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
-                vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
-                vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(vv[0], vv[1]);
-              o.y = pack_bf16x2(vv[2], vv[3]);
-              o.z = pack_bf16x2(vv[4], vv[5]);
-              o.w = pack_bf16x2(vv[6], vv[7]);
-              *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
-            }
+          const int cb = sidx / 3;
+          const int dt = sidx - cb * 3;
+          for (int j = 0; j < 9; ++j) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes));
+            const int tap = dt * 9 + j;
+            tma_load_2d(smem_b + static_cast<size_t>(sb) * b_bytes, &tmB, &b_full[sb], (tap * g.cblocks + cb) * 64,
+                        cur.n0);
+            if (++sb == g.nb) { sb = 0; pb ^= 1; }
           }
         }
       }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
+    const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+    const uint32_t desc_hi = umma_desc_hi(128);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t wp16 = static_cast<uint32_t>(g.Wp) * 8u;   // one padded row in 16-byte units
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+      uint32_t accum = 0;
+      int cb = 0, dt = 0;
+      for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
+        const int ksteps = min(4, (g.cin - cb * 64) >> 4);
+        mbar_wait(&a_full[sa], pa);
+        const uint32_t slab_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.slab_bytes));
+        uint32_t row_lo = slab_lo;     // + dh * Wp rows
+        for (int dh = 0; dh < 3; ++dh) {
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * b_bytes));
+            const uint32_t a_lo = row_lo + 8u * dw;        // one position = 128 B = 8 x 16 B
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
+                  accum = 1;
+                }
+              }
+              umma_commit(&b_empty[sb]);
+              if (dh == 2 && dw == 2) {
+                umma_commit(&a_empty[sa]);
+                if (sidx == slabs_per_tile - 1) umma_commit(&tfull_bar[acc]);
+              }
+            }
+            __syncwarp();
+            if (++sb == g.nb) { sb = 0; pb ^= 1; }
+          }
+          row_lo += wp16;
+        }
+        if (++sa == g.na) { sa = 0; pa ^= 1; }
+        if (++dt == 3) { dt = 0; ++cb; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int hm = row / g.Wp;
+    const int wm = row - hm * g.Wp;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const HaloTile tc = decode_halo_tile(g, tile);
+      const int h = tc.h0 + hm;
+      const bool valid = (wm < g.W) && (hm < g.nrows) && (h < g.H);
+      const long long pos = ((static_cast<long long>(tc.b) * g.T + tc.t) * g.H + h) * g.W + wm;
+      __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
+      const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
+      const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
+      epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -327,8 +532,9 @@ static void finish_plan(ConvLaunch* L, int device) {
   g.tt = ceil_div(g.T, g.bt);
   g.m_tiles = g.B * g.tt * g.th * g.tw;
   const int row_bytes = g.stem ? 64 : 128;
-  L->a_bytes = 128 * row_bytes;
-  L->b_bytes = g.bn * row_bytes;
+  const int sub = g.stem ? g.kh : 1;   // stem: one stage carries the 7 kh taps of one kt
+  L->a_bytes = 128 * row_bytes * sub;
+  L->b_bytes = g.bn * row_bytes * sub;
   L->stage_bytes = round_up(L->a_bytes + L->b_bytes, 1024);
   const int budget = 200 * 1024;
   L->stages = std::max(2, std::min(kMaxStages, budget / L->stage_bytes));
@@ -399,7 +605,7 @@ int conv_plan_stem(ConvLaunch* L, int device, const void* xpad, int B, int T, in
   g.stem_pt = pt; g.stem_ph = ph;
   g.kt = 7; g.kh = 7; g.kw = 1;
   g.cin = 32; g.cblocks = 1;
-  g.nkb = 49;
+  g.nkb = 7;                         // pipeline stages per tile: one per kt
   g.n_tiles = 1; g.bn = 64;
   g.B = B; g.T = To; g.H = Ho; g.W = Wo;
   choose_box(To, Ho, Wo, 7, 7, 7, &g.bw, &g.bh, &g.bt);
@@ -434,12 +640,98 @@ int conv_plan_stem(ConvLaunch* L, int device, const void* xpad, int B, int T, in
   return FAV_OK;
 }
 
+
+bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw) {
+  (void)T;
+  if (kt != 3 || kh != 3 || kw != 3) return false;
+  const int Wp = W + 2;
+  if (Wp > 64) return false;                 // at least two output rows per 128-row tile
+  const int nrows = std::min(128 / Wp, H);
+  // useful rows per tile vs the per-tap path's box efficiency (~0.9): keep halo when >= 60 %
+  return nrows * W * 10 >= 128 * 6;
+}
+
+int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
+                   const void* wpk, int cout_pad, int B, int T, int H, int W) {
+  FAV_CHECK_ARG(cin % 16 == 0 && cin > 0, "conv: cin=%d must be a positive multiple of 16", cin);
+  FAV_CHECK_ARG(cout_pad % 16 == 0 && cout_pad > 0, "conv: padded cout=%d must be a multiple of 16", cout_pad);
+  memset(L, 0, sizeof(*L));
+  ConvGeom& g = L->g;
+  g.halo = 1;
+  g.kt = g.kh = g.kw = 3;
+  g.ot = g.oh = g.ow = -1;
+  g.cin = cin;
+  g.cblocks = ceil_div(cin, 64);
+  g.nkb = 27 * g.cblocks;
+  g.n_tiles = ceil_div(cout_pad, 256);
+  g.bn = round_up(ceil_div(cout_pad, g.n_tiles), 16);
+  FAV_CHECK_ARG(g.bn * g.n_tiles == cout_pad, "conv: cout_pad=%d not divisible into %d tiles of %d", cout_pad,
+                g.n_tiles, g.bn);
+  g.B = B; g.T = T; g.H = H; g.W = W;
+  g.Wp = W + 2;
+  g.nrows = std::min(128 / g.Wp, H);
+  FAV_CHECK_ARG(g.nrows >= 1, "conv halo: W=%d too wide", W);
+  g.th = ceil_div(H, g.nrows);
+  g.tw = 1; g.tt = T;
+  g.m_tiles = B * T * g.th;
+  g.slab_tx = (g.nrows + 2) * g.Wp * 128;
+  g.slab_bytes = round_up(std::max((130 + 2 * g.Wp) * 128, g.slab_tx), 1024);
+  // Measured on B200: tcgen05.mma applies the 128-byte swizzle as a function of the absolute shared
+  // memory address, so a window that starts at any 128-byte row of a TMA-written slab reads correctly
+  // with base_offset = 0 (setting it to (start>>7)&7 double-counts the phase and fails parity).
+  g.swz_base_offset = 0;
+  const int b_bytes = g.bn * 128;
+  L->b_bytes = b_bytes;
+  L->a_bytes = g.slab_bytes;
+  const int budget = 222 * 1024;
+  g.na = 3;
+  g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
+  if (g.nb < 3) {
+    g.na = 2;
+    g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
+  }
+  FAV_CHECK_ARG(g.nb >= 2, "conv halo: shared memory budget exceeded (slab %d B, B tile %d B)", g.slab_bytes, b_bytes);
+  L->stages = g.nb;
+  L->stage_bytes = b_bytes;
+  L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * b_bytes + 1024 + 512;
+
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  const char* base = static_cast<const char*>(x) + static_cast<long long>(x_coff) * 2;
+  dims[0] = static_cast<uint64_t>(cin); dims[1] = W; dims[2] = H; dims[3] = T; dims[4] = B;
+  strides[0] = static_cast<uint64_t>(x_cs) * 2;
+  strides[1] = strides[0] * W;
+  strides[2] = strides[1] * H;
+  strides[3] = strides[2] * T;
+  box[0] = 64; box[1] = g.Wp; box[2] = g.nrows + 2; box[3] = 1; box[4] = 1;
+  FAV_TRY(make_tmap_bf16(&L->tmA[0], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  L->tmA[1] = L->tmA[0]; L->tmA[2] = L->tmA[0]; L->tmA[3] = L->tmA[0];
+  uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cout_pad)};
+  uint64_t bs[1] = {bd[0] * 2};
+  uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  const int tiles = g.m_tiles * g.n_tiles;
+  L->grid = std::max(1, std::min(tiles, sm_count(device)));
+  return FAV_OK;
+}
+
 int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     FAV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   220 * 1024));
     attr_set = true;
+  }
+  if (L.g.halo) {
+    static bool attr2 = false;
+    if (!attr2) {
+      FAV_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      attr2 = true;
+    }
+    conv_halo_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmB, L.g, L.e, L.b_bytes);
+    FAV_COUNT_LAUNCH();
+    FAV_CUDA(cudaGetLastError());
+    return FAV_OK;
   }
   conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(
       L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,

@@ -26,6 +26,14 @@ struct ConvGeom {
   int m_tiles;
   int stem;            // 1: stem path (SW64 rows, parity maps)
   int stem_pt, stem_ph;  // pad_before in T and H of the stride-2 stem
+  // halo path (3x3x3, stride 1): one A slab per (channel block, dt) holds nrows+2 zero-padded rows of
+  // width Wp = W+2; the 9 (dh,dw) taps are 128-row windows of that slab at row offset dw + Wp*dh.
+  int halo;            // 1: halo path
+  int Wp, nrows;       // padded row pitch and output rows per tile (nrows*Wp <= 128)
+  int slab_bytes;      // bytes reserved per slab (>= (130 + 2*Wp) rows, multiple of 1024)
+  int slab_tx;         // bytes one slab TMA delivers = (nrows+2)*Wp*128
+  int na, nb;          // A-slab ring depth, B-tile ring depth
+  int swz_base_offset; // 1: put (start>>7)&7 into the descriptor's base_offset field
 };
 
 struct ConvEpilogue {
@@ -64,6 +72,12 @@ void choose_box(int T, int H, int W, int kt, int kh, int kw, int* bw, int* bh, i
 int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
                       const void* wpk, int cout_pad, int B, int T, int H, int W, int kt, int kh,
                       int kw, int flat);
+
+// 3x3x3 stride-1 SAME conv with shared-memory halo reuse (same packed weights as conv_plan_generic).
+int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
+                   const void* wpk, int cout_pad, int B, int T, int H, int W);
+// true when the halo path applies and beats the per-tap path for this shape
+bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw);
 
 // Stem: x is the padded RGBX buffer [B,T,H,Wp,4]; output positions [B,To,Ho,Wo]; wpk [64][49*32].
 int conv_plan_stem(ConvLaunch* L, int device, const void* xpad, int B, int T, int H, int W, int Wp,

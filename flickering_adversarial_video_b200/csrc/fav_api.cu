@@ -13,6 +13,7 @@
 #include <vector>
 #include <memory>
 #include <cmath>
+#include <cstdlib>
 
 using namespace fav;
 
@@ -174,6 +175,15 @@ int same_pad_before(int in, int k, int s) {
   return total / 2;
 }
 
+bool use_halo(int T, int H, int W, int kt, int kh, int kw) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* ev = getenv("FAV_DISABLE_HALO");
+    disabled = (ev && atoi(ev)) ? 1 : 0;
+  }
+  return !disabled && conv_halo_applicable(T, H, W, kt, kh, kw);
+}
+
 int plan_conv(fav_handle* h, ConvOp& c) {
   const Buf& bi = h->bufs[c.in];
   const Buf& bo = h->bufs[c.out];
@@ -185,8 +195,12 @@ int plan_conv(fav_handle* h, ConvOp& c) {
     c.w_fwd_elems = static_cast<size_t>(c.cout_pad) * taps * cblocks * 64;
     FAV_TRY(dev_alloc(h, &c.w_fwd, c.w_fwd_elems));
     FAV_TRY(dev_alloc(h, &c.bias, static_cast<size_t>(c.cout_pad)));
-    FAV_TRY(conv_plan_generic(&c.fwd, h->device, bi.p, bi.cs, c.in_coff, c.cin_k, c.w_fwd, c.cout_pad,
-                              h->B, bi.T, bi.H, bi.W, c.kt, c.kh, c.kw, flat));
+    if (use_halo(bi.T, bi.H, bi.W, c.kt, c.kh, c.kw))
+      FAV_TRY(conv_plan_halo(&c.fwd, h->device, bi.p, bi.cs, c.in_coff, c.cin_k, c.w_fwd, c.cout_pad, h->B, bi.T,
+                             bi.H, bi.W));
+    else
+      FAV_TRY(conv_plan_generic(&c.fwd, h->device, bi.p, bi.cs, c.in_coff, c.cin_k, c.w_fwd, c.cout_pad,
+                                h->B, bi.T, bi.H, bi.W, c.kt, c.kh, c.kw, flat));
     ConvEpilogue& e = c.fwd.e;
     e.out = bo.p; e.out_cs = bo.cs; e.out_coff = c.out_coff; e.cout_store = c.cout_pad;
     e.bias = c.bias; e.bias_ld = c.cout_pad; e.bias_stem = 0; e.relu = c.relu ? 1 : 0;
@@ -197,8 +211,12 @@ int plan_conv(fav_handle* h, ConvOp& c) {
     const int cblocks = ceil_div(c.cout_pad, 64);
     c.w_dg_elems = static_cast<size_t>(c.cin_k) * taps * cblocks * 64;
     FAV_TRY(dev_alloc(h, &c.w_dg, c.w_dg_elems));
-    FAV_TRY(conv_plan_generic(&c.dg, h->device, bo.g, bo.cs, c.out_coff, c.cout_pad, c.w_dg, c.cin_k,
-                              h->B, bi.T, bi.H, bi.W, c.kt, c.kh, c.kw, flat));
+    if (use_halo(bi.T, bi.H, bi.W, c.kt, c.kh, c.kw))
+      FAV_TRY(conv_plan_halo(&c.dg, h->device, bo.g, bo.cs, c.out_coff, c.cout_pad, c.w_dg, c.cin_k, h->B, bi.T,
+                             bi.H, bi.W));
+    else
+      FAV_TRY(conv_plan_generic(&c.dg, h->device, bo.g, bo.cs, c.out_coff, c.cout_pad, c.w_dg, c.cin_k,
+                                h->B, bi.T, bi.H, bi.W, c.kt, c.kh, c.kw, flat));
     ConvEpilogue& e = c.dg.e;
     e.out = bi.g; e.out_cs = bi.cs; e.out_coff = c.in_coff; e.cout_store = c.cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0;
@@ -688,8 +706,12 @@ extern "C" int fav_op_conv3d(int device, const void* x, int64_t x_cs, int64_t x_
     FAV_CUDA(cudaStreamSynchronize(s));
   }
   ConvLaunch L;
-  int st = conv_plan_generic(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W, kt, kh, kw,
-                             taps == 1);
+  int st;
+  if (use_halo(T, H, W, kt, kh, kw))
+    st = conv_plan_halo(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W);
+  else
+    st = conv_plan_generic(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W, kt, kh, kw,
+                           taps == 1);
   if (st == FAV_OK) {
     L.e.out = static_cast<__nv_bfloat16*>(y); L.e.out_cs = y_cs; L.e.out_coff = static_cast<int>(y_coff);
     L.e.cout_store = n_real;

@@ -216,6 +216,23 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   d |= layout << 61;
   return d;
 }
+// Split form for tight issue loops: the high word is constant per layout, the low word is
+// (address >> 4) | LBO.  K-advance / row-advance are plain integer adds on the low word.
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  return ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3ffffu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// Same, for an operand whose start is 128-byte aligned but not 1024-byte aligned (a row window of a
+// larger swizzled slab): base_offset (bits [49,52)) carries the phase of the swizzle pattern.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr, uint32_t use_base_offset) {
+  uint64_t d = umma_smem_desc(saddr, 128);
+  if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
+  return d;
+}
 // Instruction descriptor for kind::f16, A=B=bf16, D=f32, both K-major (InstrDescriptor).
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
   uint32_t d = 0;

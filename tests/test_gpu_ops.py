@@ -55,6 +55,10 @@ CONV_CASES = [
     (1, 3, 28, 28, 3, 32, 96),
     (1, 4, 14, 14, 3, 160, 320),    # two N tiles of 160
     (1, 3, 7, 7, 3, 192, 384),
+    (1, 3, 56, 56, 3, 64, 192),     # halo path: 2 rows per tile
+    (2, 4, 28, 28, 3, 96, 128),     # halo path: 4 rows per tile, partial k-block
+    (1, 5, 14, 14, 3, 112, 224),    # halo path: 8 + 6 rows
+    (1, 3, 28, 28, 3, 16, 32),      # halo path, tiny cin
 ]
 
 
