@@ -200,8 +200,21 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    use_graph = not args.no_graph
+    l0 = lib.fav_launch_count()
+    atk.step(clips[0], labels[0])
+    launches_per_step = lib.fav_launch_count() - l0       # kernels one step launches (a graph replays the same nodes)
+    if use_graph:
+        # one CUDA graph per resident batch (the graph is bound to the batch's device buffers)
+        graphs = []
+        for i in range(pool):
+            graphs.append(atk.capture(clips[i], labels[i]))
+        atk.reset()
+        step_fn = lambda i: graphs[i % pool].replay()
+    else:
+        step_fn = lambda i: atk.step(clips[i % pool], labels[i % pool])
     for i in range(args.warmup):
-        atk.step(clips[i % pool], labels[i % pool])
+        step_fn(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -209,10 +222,10 @@ def run_engine(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        atk.step(clips[i % pool], labels[i % pool])
+        step_fn(i)
     ev1.record()
     barrier()
-    launches = lib.fav_launch_count() - launches0
+    launches = launches_per_step * args.steps if use_graph else lib.fav_launch_count() - launches0
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     if world > 1:
@@ -272,6 +285,7 @@ def run_engine(args):
         "config": {"workload": f"I3D class-generalisation flickering attack (BASELINE.json configs[1]), "
                                f"{B} x {T}x224x224x3 uint8 clips per GPU, random-init weights",
                    "batch_per_gpu": B, "global_batch": B * world, "frames": T, "resident_batches": pool,
+                   "cuda_graph": use_graph,
                    "l2": f"each step touches ~{atk.eng.device_bytes / 2**30:.1f} GiB of activations/gradients "
                          f"(>> 126 MB L2) and a different clip batch"},
         "clocks": clocks,
@@ -304,6 +318,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--pool", type=int, default=3, help="resident clip batches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = max(args.warmup, 1)

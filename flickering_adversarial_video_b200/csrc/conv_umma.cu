@@ -311,7 +311,7 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const ConvGeom& g, int tile
   m /= g.th;
   c.t = m % g.T;
   c.b = m / g.T;
-  c.h0 = hi * g.nrows;
+  c.h0 = hi * g.nrows * g.mt;
   c.n0 = nt * g.bn;
   return c;
 }
@@ -401,10 +401,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t wp16 = static_cast<uint32_t>(g.Wp) * 8u;   // one padded row in 16-byte units
+    const uint32_t tile16 = wp16 * static_cast<uint32_t>(g.nrows);
+    const int acc_cols = g.acc_stages == 2 ? kAccCols : 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
       uint32_t accum = 0;
       int cb = 0, dt = 0;
       for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
@@ -420,13 +422,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * b_bytes));
             const uint32_t a_lo = row_lo + 8u * dw;        // one position = 128 B = 8 x 16 B
             if (elect_one()) {
+              uint32_t a_i = a_lo, d_i = d_tmem;
+              for (int i = 0; i < g.mt; ++i) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ksteps) {
-                  umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
-                  accum = 1;
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) umma_bf16(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum | (k > 0 ? 1u : 0u));
                 }
+                a_i += tile16;                       // next M tile: nrows padded rows further down the slab
+                d_i += static_cast<uint32_t>(g.bn);
               }
+              accum = 1;
               umma_commit(&b_empty[sb]);
               if (dh == 2 && dw == 2) {
                 umma_commit(&a_empty[sa]);
@@ -441,8 +446,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++sa == g.na) { sa = 0; pa ^= 1; }
         if (++dt == 3) { dt = 0; ++cb; }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (g.acc_stages == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -454,21 +463,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const HaloTile tc = decode_halo_tile(g, tile);
-      const int h = tc.h0 + hm;
-      const bool valid = (wm < g.W) && (hm < g.nrows) && (h < g.H);
-      const long long pos = ((static_cast<long long>(tc.b) * g.T + tc.t) * g.H + h) * g.W + wm;
-      __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
-      const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
-      const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
-      epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
+      const int acc_cols = g.acc_stages == 2 ? kAccCols : 0;
+      for (int i = 0; i < g.mt; ++i) {
+        const int h = tc.h0 + i * g.nrows + hm;
+        const bool valid = (wm < g.W) && (hm < g.nrows) && (h < g.H);
+        const long long pos = ((static_cast<long long>(tc.b) * g.T + tc.t) * g.H + h) * g.W + wm;
+        __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
+        const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * acc_cols + i * g.bn);
+        epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (g.acc_stages == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
     }
   }
 
@@ -671,11 +688,26 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   g.Wp = W + 2;
   g.nrows = std::min(128 / g.Wp, H);
   FAV_CHECK_ARG(g.nrows >= 1, "conv halo: W=%d too wide", W);
-  g.th = ceil_div(H, g.nrows);
+  // M tiles per CTA step that share each B tile: as many as fit TMEM (512 fp32 columns), double-buffered
+  // when 2*mt*bn <= 512; never more row groups than the plane has.
+  {
+    const int groups = ceil_div(H, g.nrows);
+    int mt = g.bn <= 128 ? std::min(4, 256 / g.bn) : 1;   // single-buffered accumulators cost more than the shared B saves
+    mt = std::max(1, std::min(mt, groups));
+    static int force_mt = -1;
+    if (force_mt < 0) {
+      const char* ev = getenv("FAV_HALO_MT");
+      force_mt = ev ? atoi(ev) : 0;
+    }
+    if (force_mt > 0) mt = std::max(1, std::min(std::min(force_mt, groups), 512 / g.bn));
+    g.mt = mt;
+    g.acc_stages = (2 * mt * g.bn <= 512) ? 2 : 1;
+  }
+  g.th = ceil_div(H, g.nrows * g.mt);
   g.tw = 1; g.tt = T;
   g.m_tiles = B * T * g.th;
-  g.slab_tx = (g.nrows + 2) * g.Wp * 128;
-  g.slab_bytes = round_up(std::max((130 + 2 * g.Wp) * 128, g.slab_tx), 1024);
+  g.slab_tx = (g.mt * g.nrows + 2) * g.Wp * 128;
+  g.slab_bytes = round_up(std::max(((g.mt - 1) * g.nrows * g.Wp + 130 + 2 * g.Wp) * 128, g.slab_tx), 1024);
   // Measured on B200: tcgen05.mma applies the 128-byte swizzle as a function of the absolute shared
   // memory address, so a window that starts at any 128-byte row of a TMA-written slab reads correctly
   // with base_offset = 0 (setting it to (start>>7)&7 double-counts the phase and fails parity).
@@ -686,8 +718,18 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   const int budget = 222 * 1024;
   g.na = 3;
   g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
-  if (g.nb < 3) {
+  if (g.nb < 4) {
     g.na = 2;
+    g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
+  }
+  while (g.nb < 3 && g.mt > 1) {   // shrink the super-tile until the rings fit
+    g.mt -= 1;
+    g.acc_stages = (2 * g.mt * g.bn <= 512) ? 2 : 1;
+    g.th = ceil_div(H, g.nrows * g.mt);
+    g.m_tiles = B * T * g.th;
+    g.slab_tx = (g.mt * g.nrows + 2) * g.Wp * 128;
+    g.slab_bytes = round_up(std::max(((g.mt - 1) * g.nrows * g.Wp + 130 + 2 * g.Wp) * 128, g.slab_tx), 1024);
+    L->a_bytes = g.slab_bytes;
     g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
   }
   FAV_CHECK_ARG(g.nb >= 2, "conv halo: shared memory budget exceeded (slab %d B, B tile %d B)", g.slab_bytes, b_bytes);
@@ -703,7 +745,8 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   strides[1] = strides[0] * W;
   strides[2] = strides[1] * H;
   strides[3] = strides[2] * T;
-  box[0] = 64; box[1] = g.Wp; box[2] = g.nrows + 2; box[3] = 1; box[4] = 1;
+  box[0] = 64; box[1] = g.Wp; box[2] = g.mt * g.nrows + 2; box[3] = 1; box[4] = 1;
+  FAV_CHECK_ARG(box[2] <= 256, "conv halo: box too tall");
   FAV_TRY(make_tmap_bf16(&L->tmA[0], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   L->tmA[1] = L->tmA[0]; L->tmA[2] = L->tmA[0]; L->tmA[3] = L->tmA[0];
   uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cout_pad)};

@@ -33,6 +33,8 @@ struct ConvGeom {
   int slab_bytes;      // bytes reserved per slab (>= (130 + 2*Wp) rows, multiple of 1024)
   int slab_tx;         // bytes one slab TMA delivers = (nrows+2)*Wp*128
   int na, nb;          // A-slab ring depth, B-tile ring depth
+  int mt;              // M tiles (of nrows rows each) that share every B tile load: mt accumulators of bn columns
+  int acc_stages;      // 2: accumulators double-buffered (2*mt*bn <= 512), 1: single-buffered
   int swz_base_offset; // 1: put (start>>7)&7 into the descriptor's base_offset field
 };
 
