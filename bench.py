@@ -302,9 +302,14 @@ def run_engine(args):
                                           f"torch CPU fp32, {threads} threads), {sec:.2f} s/iter"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    atk.close()
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # all ranks are past their last collective; leave without the NCCL / CUDA-graph teardown,
+        # which can block on process-group destruction when captured collectives are still referenced
+        barrier()
+        os._exit(0)
+    atk.close()
     return 0
 
 
