@@ -1,0 +1,302 @@
+// conv_stem.cu — the strided RGB stem as a tcgen05 implicit GEMM with shared-memory halo reuse.
+//
+// Replaces Conv3d_1a_7x7 (7x7x7, stride 2, SAME; i3d.py:168-171) and, with KT/st/pads as parameters,
+// the torchvision video stems ((3,7,7) and (1,7,7), stride (1,2,2), padding 3).
+//
+// Input is the RGBX buffer the apply kernel writes: [B,T,H,Wp,4] bf16 with W physically padded, so the
+// 7 W taps x RGB of output column wo are the 8 positions x 4 channels = 32 contiguous bf16 starting at
+// column 2*wo: one 64-byte K row per output position per (kt,kh) tap.  A tensor map whose W stride is
+// 16 bytes (two positions) exposes those overlapping rows directly; four maps cover the (T,H)
+// parities, so that "input row 2*ho + kh - pad" is row ho + qh of the parity-(kh-pad)&1 map.
+//
+// A CTA tile is 16 output columns x 8*mt output rows of one output frame.  Per temporal tap kt (one
+// pipeline stage) the producer brings, for each H parity, ONE slab of 8*mt + span rows x 16 columns
+// x 64 B; the 7 kh taps are 1024-byte-aligned row windows of those two slabs (2*8*mt + 5 slab rows
+// instead of 7*8*mt per stage), and the stage's 7 weight sub-tiles are shared by the mt M tiles.
+#include "conv_umma.cuh"
+
+#include <string.h>
+#include <algorithm>
+
+namespace fav {
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+
+struct StemTile {
+  int b, t, h0, w0;
+};
+__device__ __forceinline__ StemTile decode_stem_tile(const StemGeom& g, int tile) {
+  StemTile c;
+  const int wi = tile % g.tw;
+  int m = tile / g.tw;
+  const int hi = m % g.th;
+  m /= g.th;
+  c.t = m % g.To;
+  c.b = m / g.To;
+  c.h0 = hi * 8 * g.mt;
+  c.w0 = wi * 16;
+  return c;
+}
+__device__ __forceinline__ int border_cls(int o, int n, int nlo, int nhi) {
+  return o < nlo ? o : (o >= n - nhi ? nlo + 1 + (o - (n - nhi)) : nlo);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                 const __grid_constant__ CUtensorMap tmB, const StemGeom g, const ConvEpilogue e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(g.stages) * g.stage_bytes);
+  uint64_t* full_bar = bars;                    // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;      // [stages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int acc_cols = g.mt * g.bn;             // TMEM columns per accumulator stage
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+        const StemTile tc = decode_stem_tile(g, tile);
+        for (int kt = 0; kt < g.KT; ++kt) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.a_bytes + g.b_bytes));
+          // input frame = st*t + kt - pt = st*(t + qt) + parity
+          int par_t = 0, tcoord;
+          if (g.st == 2) {
+            const int offt = kt - g.pt;
+            par_t = offt & 1;
+            tcoord = tc.t + ((offt - par_t) >> 1);
+          } else {
+            tcoord = tc.t + kt - g.pt;
+          }
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int rows_p = p ? g.rows[1] : g.rows[0];
+            if (rows_p == 0) continue;
+            const int mi = par_t * 2 + p;
+            const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+            tma_load_5d(sa + (p ? g.slab_off[1] : g.slab_off[0]), tm, &full_bar[stage], 0, tc.w0,
+                        tc.h0 + (p ? g.qmin[1] : g.qmin[0]), tcoord, tc.b);
+          }
+          tma_load_3d(sa + g.a_bytes, &tmB, &full_bar[stage], 0, 0, kt * g.KH);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+    const uint32_t desc_hi = umma_desc_hi(64);
+    const uint32_t b_sub = static_cast<uint32_t>(g.bn) * 64u;   // bytes per kh weight sub-tile
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
+      for (int kt = 0; kt < g.KT; ++kt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+        const uint32_t sb = sa + static_cast<uint32_t>(g.a_bytes);
+        if (elect_one()) {
+          for (int kh = 0; kh < g.KH; ++kh) {
+            const int offh = kh - g.ph;
+            const int p = offh & 1;
+            const int qh = (offh - p) >> 1;
+            const int so = p ? g.slab_off[1] : g.slab_off[0];
+            const int q0 = p ? g.qmin[1] : g.qmin[0];
+            const uint32_t a_lo = umma_desc_lo(sa + static_cast<uint32_t>(so + (qh - q0) * 1024));
+            const uint32_t b_lo = umma_desc_lo(sb + kh * b_sub);
+            const uint32_t accum = (kt | kh) ? 1u : 0u;
+            for (int i = 0; i < g.mt; ++i) {
+              const uint32_t a_i = a_lo + static_cast<uint32_t>(i) * 512u;   // 8 rows x 1024 B, in 16-byte units
+              const uint32_t d_i = d_tmem + static_cast<uint32_t>(i * g.bn);
+              umma_bf16(d_i, make_desc(desc_hi, a_i), make_desc(desc_hi, b_lo), idesc, accum);
+              umma_bf16(d_i, make_desc(desc_hi, a_i + 2), make_desc(desc_hi, b_lo + 2), idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kt == g.KT - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rw = row & 15;
+    const int rh = row >> 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      const StemTile tc = decode_stem_tile(g, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int w = tc.w0 + rw;
+      for (int i = 0; i < g.mt; ++i) {
+        const int h = tc.h0 + i * 8 + rh;
+        const bool valid = (w < g.Wo) && (h < g.Ho);
+        const long long pos = ((static_cast<long long>(tc.b) * g.To + tc.t) * g.Ho + h) * g.Wo + w;
+        __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const float* bias_row = nullptr;
+        if (e.bias) {
+          int br = 0;
+          if (e.bias_stem) {
+            const int hc = border_cls(min(h, g.Ho - 1), g.Ho, g.nlo_h, g.nhi_h);
+            const int wc = border_cls(min(w, g.Wo - 1), g.Wo, g.nlo_w, g.nhi_w);
+            br = (tc.t * 4 + hc) * 4 + wc;
+          }
+          bias_row = e.bias + static_cast<long long>(br) * e.bias_ld;
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * acc_cols + i * g.bn);
+        epilogue_columns(e, g.bn, 0, taddr, valid, out_row, nullptr, nullptr, bias_row);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
+              int To, int Ho, int Wo, int KT, int KH, int st, int pt, int ph) {
+  FAV_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "stem: cout=%d must be a multiple of 16 <= 256", bn);
+  FAV_CHECK_ARG(st == 1 || st == 2, "stem: temporal stride %d", st);
+  FAV_CHECK_ARG(KT >= 1 && KT <= 7 && KH >= 1 && KH <= 7, "stem: taps %dx%d", KT, KH);
+  memset(L, 0, sizeof(*L));
+  StemGeom& g = L->g;
+  g.B = B; g.To = To; g.Ho = Ho; g.Wo = Wo;
+  g.KT = KT; g.KH = KH; g.st = st; g.pt = pt; g.ph = ph; g.bn = bn;
+  // M tiles per CTA tile: two accumulator stages of mt*bn columns must fit the 512 TMEM columns
+  g.mt = std::max(1, std::min(2, 256 / bn));
+  if (Ho <= 8) g.mt = 1;
+  g.th = ceil_div(Ho, 8 * g.mt);
+  g.tw = ceil_div(Wo, 16);
+  g.m_tiles = B * To * g.th * g.tw;
+  // per-parity slabs
+  int qlo[2] = {1 << 20, 1 << 20}, qhi[2] = {-(1 << 20), -(1 << 20)};
+  for (int kh = 0; kh < KH; ++kh) {
+    const int offh = kh - ph;
+    const int p = offh & 1;
+    const int qh = (offh - p) / 2;
+    qlo[p] = std::min(qlo[p], qh);
+    qhi[p] = std::max(qhi[p], qh);
+  }
+  int off = 0;
+  for (int p = 0; p < 2; ++p) {
+    if (qhi[p] < qlo[p]) { g.qmin[p] = 0; g.rows[p] = 0; g.slab_off[p] = off; continue; }
+    g.qmin[p] = qlo[p];
+    g.rows[p] = 8 * g.mt + (qhi[p] - qlo[p]);
+    g.slab_off[p] = off;
+    off += g.rows[p] * 1024;
+  }
+  g.a_bytes = off;
+  g.b_bytes = KH * bn * 64;
+  g.stage_bytes = round_up(g.a_bytes + g.b_bytes, 1024);
+  g.stages = std::max(2, std::min(kMaxStages, (216 * 1024) / g.stage_bytes));
+  FAV_CHECK_ARG(g.stages * g.stage_bytes <= 220 * 1024, "stem: stage of %d bytes does not fit", g.stage_bytes);
+  L->smem_bytes = static_cast<size_t>(g.stages) * g.stage_bytes + 1024 + 512;
+  // border classes of the delta-bias table: output rows whose window touches the zero padding
+  auto classes = [](int in, int out, int k, int s, int pad, int* nlo, int* nhi) {
+    *nlo = ceil_div(pad, s);
+    const int pad_after = std::max(0, (out - 1) * s + k - pad - in);
+    *nhi = ceil_div(pad_after, s);
+  };
+  classes(H, Ho, KH, 2, ph, &g.nlo_h, &g.nhi_h);
+  {
+    const int W = 2 * Wo;   // the engine requires even W; the W pad equals the H pad for square kernels
+    classes(W, Wo, 7, 2, ph, &g.nlo_w, &g.nhi_w);
+  }
+  FAV_CHECK_ARG(g.nlo_h + g.nhi_h <= 3 && g.nlo_w + g.nhi_w <= 3, "stem: more than 4 border classes");
+
+  const uint64_t pos_bytes = 8;                       // 4 channels bf16
+  const uint64_t row_pitch = static_cast<uint64_t>(Wp) * pos_bytes;
+  const uint64_t frame_pitch = row_pitch * H;
+  const uint64_t clip_pitch = frame_pitch * T;
+  for (int p_t = 0; p_t < 2; ++p_t) {
+    for (int p_h = 0; p_h < 2; ++p_h) {
+      if (g.rows[p_h] == 0 || (st == 1 && p_t == 1)) { L->tmA[p_t * 2 + p_h] = L->tmA[0]; continue; }
+      uint64_t dims[5], strides[4];
+      uint32_t box[5];
+      dims[0] = 32;                                    // 8 W-positions x 4 channels, contiguous
+      dims[1] = static_cast<uint64_t>(Wo);             // output column; window start moves 2 positions
+      dims[2] = static_cast<uint64_t>((H - p_h + 1) / 2);
+      dims[3] = static_cast<uint64_t>(st == 2 ? (T - p_t + 1) / 2 : T);
+      dims[4] = static_cast<uint64_t>(B);
+      strides[0] = 2 * pos_bytes;                      // 16 B: overlapping windows
+      strides[1] = 2 * row_pitch;
+      strides[2] = st * frame_pitch;
+      strides[3] = clip_pitch;
+      box[0] = 32; box[1] = 16; box[2] = static_cast<uint32_t>(g.rows[p_h]); box[3] = 1; box[4] = 1;
+      const char* base = static_cast<const char*>(xpad) + (st == 2 ? p_t : 0) * frame_pitch + p_h * row_pitch;
+      FAV_TRY(make_tmap_bf16(&L->tmA[p_t * 2 + p_h], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
+    }
+  }
+  if (g.rows[0] == 0) L->tmA[0] = L->tmA[1];
+  // weights [KT*KH taps][bn][32]: one box = the KH sub-tiles of one kt
+  uint64_t bd[3] = {32, static_cast<uint64_t>(bn), static_cast<uint64_t>(KT) * KH};
+  uint64_t bs[2] = {64, static_cast<uint64_t>(bn) * 64};
+  uint32_t bb[3] = {32, static_cast<uint32_t>(bn), static_cast<uint32_t>(KH)};
+  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 3, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_64B));
+  L->grid = std::max(1, std::min(g.m_tiles, sm_count(device)));
+  return FAV_OK;
+}
+
+int stem_launch(const StemLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FAV_CUDA(cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    attr_set = true;
+  }
+  conv_stem_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g,
+                                                                L.e);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+}  // namespace fav

@@ -47,68 +47,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int tile) {
   return c;
 }
 
-// Epilogue of one accumulator row: TMEM -> registers (16 fp32 columns at a time) -> bias / addend /
-// ReLU / ReLU-mask -> bf16 -> 16-byte stores into the NDHWC channel slice.
-__device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
-                                                 __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
-                                                 const __nv_bfloat16* add_row, const float* bias_row) {
-  for (int c = 0; c < bn; c += 16) {
-  uint32_t r[16];
-  tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r);
-  tmem_ld_wait();
-  const int n = n0 + c;  // first output channel of this chunk
-  if (valid && n < e.cout_store) {
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-    if (bias_row) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
-        v[j] += bv.x;
-        v[j + 1] += bv.y;
-        v[j + 2] += bv.z;
-        v[j + 3] += bv.w;
-      }
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (n + half * 8 + 8 <= e.cout_store) {
-        float* vv = v + half * 8;
-        if (add_row) {
-          const uint4 a = *reinterpret_cast<const uint4*>(add_row + n + half * 8);
-          vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x);
-          vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
-          vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z);
-          vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
-        }
-        if (e.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
-        }
-        if (mask_row) {
-          const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n + half * 8);
-          vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
-          vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
-          vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
-          vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
-        }
-        uint4 o;
-        o.x = pack_bf16x2(vv[0], vv[1]);
-        o.y = pack_bf16x2(vv[2], vv[3]);
-        o.z = pack_bf16x2(vv[4], vv[5]);
-        o.w = pack_bf16x2(vv[6], vv[7]);
-        *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
-      }
-    }
-  }
-}
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                 const __grid_constant__ CUtensorMap tmB, const ConvGeom g, const ConvEpilogue e,
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB, const ConvGeom g, const ConvEpilogue e,
                  const int stages, const int a_bytes, const int b_bytes, const int stage_bytes) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
@@ -128,11 +68,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
-    if (g.stem) {
-      tma_prefetch_desc(&tmA1);
-      tma_prefetch_desc(&tmA2);
-      tma_prefetch_desc(&tmA3);
-    }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -161,7 +96,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(a_bytes + b_bytes));
-          if (!g.stem) {
+          {
             const int tap = kb / g.cblocks;
             const int cb = kb - tap * g.cblocks;
             const int dw = tap % g.kw;
@@ -170,21 +105,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 + dw + g.ow, tc.h0 + dh + g.oh,
                         tc.t0 + dt + g.ot, tc.b);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
-          } else {
-            // stage = one temporal tap kt: the 7 kh taps are 7 (A,B) sub-tiles.
-            // input index = 2*o + k - pad = 2*(o + q) + parity
-            const int offt = kb - g.stem_pt;
-            const int pt = offt & 1;
-            const int qt = (offt - pt) >> 1;
-            for (int khi = 0; khi < g.kh; ++khi) {
-              const int offh = khi - g.stem_ph;
-              const int ph = offh & 1;
-              const int qh = (offh - ph) >> 1;
-              const int mi = pt * 2 + ph;
-              const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-              tma_load_5d(sa + khi * (128 * 64), tm, &full_bar[stage], 0, tc.w0, tc.h0 + qh, tc.t0 + qt, tc.b);
-              tma_load_2d(sb + khi * (g.bn * 64), &tmB, &full_bar[stage], (kb * g.kh + khi) * 32, tc.n0);
-            }
           }
           if (++stage == stages) {
             stage = 0;
@@ -199,11 +119,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // one elected lane issues the tcgen05 instructions.  The issue loop is the critical resource for
     // small tiles: every instruction in it costs tensor-pipe idle time.
     const uint32_t idesc = umma_idesc_bf16(128, g.bn);
-    const uint32_t row_bytes = g.stem ? 64u : 128u;
-    const uint32_t desc_hi = umma_desc_hi(row_bytes);
-    const int sub = g.stem ? g.kh : 1;                 // (A,B) operand pairs per pipeline stage
-    const uint32_t a_sub = 128u * row_bytes;           // bytes per A sub-tile
-    const uint32_t b_sub = static_cast<uint32_t>(g.bn) * row_bytes;
+    const uint32_t desc_hi = umma_desc_hi(128);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -219,17 +135,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
         const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
-        const int ksteps = g.stem ? 2 : min(4, (g.cin - cb * 64) >> 4);
+        const int ksteps = min(4, (g.cin - cb * 64) >> 4);
         if (elect_one()) {
-          for (int su = 0; su < sub; ++su) {
-            const uint32_t a_lo = umma_desc_lo(sa + su * a_sub);
-            const uint32_t b_lo = umma_desc_lo(sb + su * b_sub);
+          const uint32_t a_lo = umma_desc_lo(sa);
+          const uint32_t b_lo = umma_desc_lo(sb);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) {
-                umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
-                accum = 1;
-              }
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
+              accum = 1;
             }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -262,16 +176,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
       const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
       const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
-      const float* bias_row = nullptr;
-      if (e.bias) {
-        int br = 0;
-        if (e.bias_stem) {
-          const int hc = (h == 0) ? 0 : (h == g.H - 2 ? 2 : (h == g.H - 1 ? 3 : 1));
-          const int wc = (w == 0) ? 0 : (w == g.W - 2 ? 2 : (w == g.W - 1 ? 3 : 1));
-          br = (min(t, g.T - 1) * 4 + hc) * 4 + wc;
-        }
-        bias_row = e.bias + static_cast<long long>(br) * e.bias_ld;
-      }
+      const float* bias_row = e.bias;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -548,10 +453,8 @@ static void finish_plan(ConvLaunch* L, int device) {
   g.th = ceil_div(g.H, g.bh);
   g.tt = ceil_div(g.T, g.bt);
   g.m_tiles = g.B * g.tt * g.th * g.tw;
-  const int row_bytes = g.stem ? 64 : 128;
-  const int sub = g.stem ? g.kh : 1;   // stem: one stage carries the 7 kh taps of one kt
-  L->a_bytes = 128 * row_bytes * sub;
-  L->b_bytes = g.bn * row_bytes * sub;
+  L->a_bytes = 128 * 128;
+  L->b_bytes = g.bn * 128;
   L->stage_bytes = round_up(L->a_bytes + L->b_bytes, 1024);
   const int budget = 200 * 1024;
   L->stages = std::max(2, std::min(kMaxStages, budget / L->stage_bytes));
@@ -568,7 +471,6 @@ int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, 
   FAV_CHECK_ARG(cout_pad % 16 == 0 && cout_pad > 0, "conv: padded cout=%d must be a multiple of 16", cout_pad);
   memset(L, 0, sizeof(*L));
   ConvGeom& g = L->g;
-  g.stem = 0;
   g.kt = kt; g.kh = kh; g.kw = kw;
   g.ot = -((kt - 1) / 2); g.oh = -((kh - 1) / 2); g.ow = -((kw - 1) / 2);
   g.cin = cin;
@@ -612,51 +514,6 @@ int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, 
   finish_plan(L, device);
   return FAV_OK;
 }
-
-int conv_plan_stem(ConvLaunch* L, int device, const void* xpad, int B, int T, int H, int W, int Wp,
-                   const void* wpk, int To, int Ho, int Wo, int pt, int ph) {
-  (void)W;
-  memset(L, 0, sizeof(*L));
-  ConvGeom& g = L->g;
-  g.stem = 1;
-  g.stem_pt = pt; g.stem_ph = ph;
-  g.kt = 7; g.kh = 7; g.kw = 1;
-  g.cin = 32; g.cblocks = 1;
-  g.nkb = 7;                         // pipeline stages per tile: one per kt
-  g.n_tiles = 1; g.bn = 64;
-  g.B = B; g.T = To; g.H = Ho; g.W = Wo;
-  choose_box(To, Ho, Wo, 7, 7, 7, &g.bw, &g.bh, &g.bt);
-  const uint64_t pos_bytes = 8;                       // 4 channels bf16
-  const uint64_t row_pitch = static_cast<uint64_t>(Wp) * pos_bytes;
-  const uint64_t frame_pitch = row_pitch * H;
-  const uint64_t clip_pitch = frame_pitch * T;
-  for (int p_t = 0; p_t < 2; ++p_t) {
-    for (int p_h = 0; p_h < 2; ++p_h) {
-      uint64_t dims[5], strides[4];
-      uint32_t box[5];
-      dims[0] = 32;                                    // 8 W-positions x 4 channels, contiguous
-      dims[1] = static_cast<uint64_t>(Wo);             // output column; window start moves 2 positions
-      dims[2] = static_cast<uint64_t>((H - p_h + 1) / 2);
-      dims[3] = static_cast<uint64_t>((T - p_t + 1) / 2);
-      dims[4] = static_cast<uint64_t>(B);
-      strides[0] = 2 * pos_bytes;                      // 16 B: overlapping windows
-      strides[1] = 2 * row_pitch;
-      strides[2] = 2 * frame_pitch;
-      strides[3] = clip_pitch;
-      box[0] = 32; box[1] = g.bw; box[2] = g.bh; box[3] = g.bt; box[4] = 1;
-      const char* base = static_cast<const char*>(xpad) + p_t * frame_pitch + p_h * row_pitch;
-      FAV_TRY(make_tmap_bf16(&L->tmA[p_t * 2 + p_h], base, 5, dims, strides, box,
-                             CU_TENSOR_MAP_SWIZZLE_64B));
-    }
-  }
-  uint64_t bd[2] = {49 * 32, 64};
-  uint64_t bs[1] = {bd[0] * 2};
-  uint32_t bb[2] = {32, 64};
-  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_64B));
-  finish_plan(L, device);
-  return FAV_OK;
-}
-
 
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw) {
   (void)T;
@@ -777,7 +634,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
     return FAV_OK;
   }
   conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(
-      L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
+      L.tmA[0], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
       L.stage_bytes);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());

@@ -24,8 +24,6 @@ struct ConvGeom {
   int nkb;             // k-blocks per tile
   int bn, n_tiles;     // N tiling (bn % 16 == 0)
   int m_tiles;
-  int stem;            // 1: stem path (SW64 rows, parity maps)
-  int stem_pt, stem_ph;  // pad_before in T and H of the stride-2 stem
   // halo path (3x3x3, stride 1): one A slab per (channel block, dt) holds nrows+2 zero-padded rows of
   // width Wp = W+2; the 9 (dh,dw) taps are 128-row windows of that slab at row offset dw + Wp*dh.
   int halo;            // 1: halo path
@@ -66,6 +64,68 @@ struct ConvLaunch {
   int grid;
 };
 
+
+#ifdef __CUDACC__
+// Epilogue of one accumulator row: TMEM -> registers (16 fp32 columns at a time) -> bias / addend /
+// ReLU / ReLU-mask -> bf16 -> 16-byte stores into the NDHWC channel slice.
+__device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
+                                                 __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
+                                                 const __nv_bfloat16* add_row, const float* bias_row) {
+  for (int c = 0; c < bn; c += 16) {
+  uint32_t r[16];
+  tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r);
+  tmem_ld_wait();
+  const int n = n0 + c;  // first output channel of this chunk
+  if (valid && n < e.cout_store) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias_row) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
+        v[j] += bv.x;
+        v[j + 1] += bv.y;
+        v[j + 2] += bv.z;
+        v[j + 3] += bv.w;
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (n + half * 8 + 8 <= e.cout_store) {
+        float* vv = v + half * 8;
+        if (add_row) {
+          const uint4 a = *reinterpret_cast<const uint4*>(add_row + n + half * 8);
+          vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x);
+          vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
+          vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z);
+          vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+        }
+        if (mask_row) {
+          const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n + half * 8);
+          vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
+          vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
+          vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
+          vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(vv[0], vv[1]);
+        o.y = pack_bf16x2(vv[2], vv[3]);
+        o.z = pack_bf16x2(vv[4], vv[5]);
+        o.w = pack_bf16x2(vv[6], vv[7]);
+        *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
+      }
+    }
+  }
+}
+}
+
+#endif
+
 // Pick the M-tile box for a [T,H,W] volume and a kt x kh x kw kernel.
 void choose_box(int T, int H, int W, int kt, int kh, int kw, int* bw, int* bh, int* bt);
 
@@ -81,11 +141,36 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
 // true when the halo path applies and beats the per-tap path for this shape
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw);
 
-// Stem: x is the padded RGBX buffer [B,T,H,Wp,4]; output positions [B,To,Ho,Wo]; wpk [64][49*32].
-int conv_plan_stem(ConvLaunch* L, int device, const void* xpad, int B, int T, int H, int W, int Wp,
-                   const void* wpk, int To, int Ho, int Wo, int pt, int ph);
-
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
+
+// ---- stem (strided 7x7 spatial, Cin = 3): shared-memory halo reuse over kh, see conv_stem.cu ----
+struct StemGeom {
+  int B, To, Ho, Wo;      // output positions
+  int KT, KH;             // taps in T and H (the 7 W taps x RGBX are the K = 32 of one sub-tile)
+  int st;                 // temporal stride (2: I3D, 1: torchvision stems); spatial stride is 2
+  int pt, ph;             // pad_before in T and H
+  int mt;                 // 128-row M tiles (16 w x 8 h) per CTA tile that share every weight load
+  int bn;                 // output channels (multiple of 16)
+  int th, tw;             // CTA tiles per plane: th = ceil(Ho / (8*mt)), tw = ceil(Wo / 16)
+  int m_tiles;            // B * To * th * tw
+  int qmin[2], rows[2];   // per H-parity input slab: first q-row relative to the tile, rows in the slab
+  int slab_off[2];        // byte offset of each slab inside a stage
+  int a_bytes, b_bytes, stage_bytes, stages;
+  int nlo_h, nhi_h, nlo_w, nhi_w;   // border classes of the delta-bias table (rows touching the zero padding)
+};
+struct StemLaunch {
+  CUtensorMap tmA[4];     // [T-parity][H-parity]
+  CUtensorMap tmB;        // [32][cout][taps]
+  StemGeom g;
+  ConvEpilogue e;
+  size_t smem_bytes;
+  int grid;
+};
+// x is the padded RGBX buffer [B,T,H,Wp,4]; wpk [KT*KH][bn][32] bf16
+int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
+              int To, int Ho, int Wo, int KT, int KH, int st, int pt, int ph);
+int stem_launch(const StemLaunch& L, cudaStream_t stream);
+
 
 // Host-side weight packing (bf16 bits in uint16_t).
 // fwd: w [taps][cin_real][cout_real] (TF layout flattened), scale[cout] (BN fold) or nullptr.

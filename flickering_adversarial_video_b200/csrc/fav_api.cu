@@ -79,7 +79,7 @@ struct fav_handle {
   uint32_t* sat_list = nullptr;
   uint32_t* sat_count = nullptr;
   uint32_t sat_capacity = 0;
-  ConvLaunch stem_fwd;
+  StemLaunch stem_fwd;
   int y1 = -1;                    // buffer id of the stem output
   float last_adv_flag = 1.0f;
   float last_delta_clip = 0.4f;
@@ -262,8 +262,8 @@ int build_i3d(fav_handle* h) {
 
   h->y1 = add_buf(h, "Conv3d_1a_7x7", h->To, h->Ho, h->Wo, 64, false);
   if (h->y1 < 0) return FAV_ERR_CUDA;
-  FAV_TRY(conv_plan_stem(&h->stem_fwd, h->device, h->xpad, B, T, H, W, h->Wp, h->stem_w, h->To, h->Ho,
-                         h->Wo, h->pt, h->ph));
+  FAV_TRY(stem_plan(&h->stem_fwd, h->device, h->xpad, B, T, H, h->Wp, h->stem_w, 64, h->To, h->Ho, h->Wo, 7, 7, 2,
+                    h->pt, h->ph));
   {
     ConvEpilogue& e = h->stem_fwd.e;
     const Buf& bo = h->bufs[h->y1];
@@ -471,14 +471,14 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
       for (int c = 0; c < 3; ++c)
         for (int co = 0; co < 64; ++co)
           wf[(tap * 3 + c) * 64 + co] = w->data[(tap * 3 + c) * 64 + co] * scale[co];
-    // packed bf16 B operand: [co][kb=(kt,kh)][j=(kw8,c4)], kw==7 and c==3 are zero columns
+    // packed bf16 B operand: [tap=(kt,kh)][co][j=(kw8,c4)], kw==7 and c==3 are zero columns
     std::vector<uint16_t> sp(static_cast<size_t>(64) * 49 * 32, 0);
     for (int kt = 0; kt < 7; ++kt)
       for (int kh = 0; kh < 7; ++kh)
         for (int kw = 0; kw < 7; ++kw)
           for (int c = 0; c < 3; ++c)
             for (int co = 0; co < 64; ++co)
-              sp[static_cast<size_t>(co) * 49 * 32 + (kt * 7 + kh) * 32 + kw * 4 + c] =
+              sp[(static_cast<size_t>(kt * 7 + kh) * 64 + co) * 32 + kw * 4 + c] =
                   f32_to_bf16_bits(wf[(((kt * 7 + kh) * 7 + kw) * 3 + c) * 64 + co]);
     FAV_CUDA(cudaMemcpy(h->stem_w, sp.data(), sp.size() * 2, cudaMemcpyHostToDevice));
     // The delta path (bias table, gradient collapse, saturation corrections) keeps the folded
@@ -565,7 +565,7 @@ extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
     return FAV_ERR_STATE;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  FAV_TRY(conv_launch(h->stem_fwd, s));
+  FAV_TRY(stem_launch(h->stem_fwd, s));
   FAV_TRY(run_pool_fwd(h, h->pool2a, s));
   FAV_TRY(conv_launch(h->convs[h->conv2b].fwd, s));
   FAV_TRY(conv_launch(h->convs[h->conv2c].fwd, s));

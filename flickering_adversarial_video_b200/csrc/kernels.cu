@@ -273,6 +273,7 @@ int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
                        cudaStream_t s) {
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
   FAV_CHECK_ARG(g.kt * g.kh * g.kw <= 255, "maxpool: window too large");
+  if (idx && pool3s1_applicable(g)) return launch_pool3s1_fwd(x, y, idx, g, s);
   dim3 grid(g.B * g.To * g.Ho, ceil_div(g.Wo * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
   switch (key) {
@@ -361,6 +362,8 @@ int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
                        const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
                        cudaStream_t s) {
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", g.C);
+  if (pool3s1_applicable(g)) return launch_pool3s1_bwd(dy, idx, addend, relu_src, dx, g, s);
+  if (pool_s2_applicable(g)) return launch_pool_s2_bwd(dy, idx, addend, relu_src, dx, g, s);
   dim3 grid(g.B * g.T * g.H, ceil_div(g.W * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
   switch (key) {

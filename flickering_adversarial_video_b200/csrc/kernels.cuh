@@ -29,6 +29,18 @@ int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
                        const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
                        cudaStream_t s);
 
+// 3x3x3 / stride 1 / SAME pools: separable streaming kernels (pool3.cu).  idx holds three 2-bit stage
+// codes per element instead of a 27-tap index; launch_maxpool_fwd/bwd dispatch to them when applicable.
+bool pool3s1_applicable(const PoolGeom& g);
+int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s);
+int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
+                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s);
+
+// stride-2 pools ([1,3,3]/[1,2,2], 3x3x3/2x2x2): patch-per-thread backward (pool3.cu), standard 27-tap idx
+bool pool_s2_applicable(const PoolGeom& g);
+int launch_pool_s2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
+                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s);
+
 // head: feat[b,c] = sum_t coef[t]*sum_hw Y / (HW*2*(T5-1)); logits = feat @ Wl + bl
 int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float* feat,
                     const float* wl /*[C][K]*/, const float* bl, int K, float* logits, cudaStream_t s);

@@ -1,0 +1,433 @@
+// pool3.cu — MaxPool3d 3x3x3 / stride 1 / SAME (the Branch_3 pool of every Inception block,
+// i3d.py:212 and its eight siblings), forward and backward, in separable streaming form.
+//
+// max over a 3x3x3 window = max_t(max_h(max_w x)), and "first arg-max in (t,h,w) scan order" (where TF
+// and torch route the gradient) is exactly what three first-wins 1-D stages select.  The forward
+// therefore keeps three 2-bit codes per element (a1 | a2<<2 | a3<<4: which of the 3 W / H / T
+// candidates won the stage *centred on this element*), and the backward pulls through three 3-tap
+// stages: 9 masked accumulates per element instead of 27.
+//
+// One CTA owns a whole HxW plane of a channel group and streams over T: the W and H stages go through
+// shared memory once per frame, the T stage is a register ring, so nothing is re-read from global
+// memory except the two frames at the ends of a T segment.
+#include "kernels.cuh"
+
+namespace fav {
+namespace {
+
+constexpr uint32_t kNegInf2 = 0xFF80FF80u;   // bf16x2 (-inf, -inf)
+constexpr int kPoolThreads = 800;
+
+__device__ __forceinline__ void first_max(uint32_t (&best)[4], uint32_t (&code)[4], const uint4 v, const uint32_t d2) {
+  const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&vv[j]);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&best[j]);
+    const uint32_t m = __hgt2_mask(a, b);          // strict >: the earlier candidate keeps ties
+    const __nv_bfloat162 mx = __hmax2(b, a);
+    best[j] = *reinterpret_cast<const uint32_t*>(&mx);
+    code[j] = (code[j] & ~m) | (d2 & m);
+  }
+}
+
+// forward.  grid (C/(8*cgn), T segments, B); one thread = one (h, w, 8-channel group) item.
+__global__ void __launch_bounds__(kPoolThreads)
+pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+                   const int T, const int H, const int W, const int C, const int cgn, const int tseg) {
+  extern __shared__ uint4 smem4[];
+  uint4* X = smem4;                                   // [H][W+2][cgn]
+  uint4* M1 = smem4 + H * (W + 2) * cgn;              // [H+2][W][cgn]
+  const int items = H * W * cgn;
+  const int it = threadIdx.x;
+  const bool live = it < items;
+  const int cgi = it % cgn;
+  const int pos = it / cgn;
+  const int h = pos / W, w = pos - h * W;
+  const uint4 ninf = make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
+  // -inf borders (never overwritten afterwards)
+  for (int i = threadIdx.x; i < H * 2 * cgn; i += blockDim.x) {
+    const int hh = i / (2 * cgn), r = i - hh * 2 * cgn;
+    X[(hh * (W + 2) + (r < cgn ? 0 : W + 1)) * cgn + (r % cgn)] = ninf;
+  }
+  for (int i = threadIdx.x; i < 2 * W * cgn; i += blockDim.x) {
+    const int side = i / (W * cgn), r = i - side * W * cgn;
+    M1[(side ? (H + 1) * W * cgn : 0) + r] = ninf;
+  }
+  const int b = blockIdx.z;
+  const int t_begin = blockIdx.y * tseg;
+  const int t_end = min(t_begin + tseg, T);
+  const long long plane = static_cast<long long>(H) * W * C;
+  const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (blockIdx.x * cgn + cgi) * 8 : 0;
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * plane + eoff;
+  __nv_bfloat16* yb = y + static_cast<long long>(b) * T * plane + eoff;
+  uint8_t* ib = idx + static_cast<long long>(b) * T * plane + eoff;
+  const int xs = (h * (W + 2) + w + 1) * cgn + cgi;   // own cell in X
+  const int ms = ((h + 1) * W + w) * cgn + cgi;       // own cell in M1
+
+  uint32_t p2[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};   // in-plane max of frame to-1
+  uint32_t p1[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};   // in-plane max of frame to
+  uint2 pcode = make_uint2(0u, 0u);                             // a1|a2<<2 bytes of frame to
+  uint4 nxt = ninf;
+  if (live && t_begin - 1 >= 0) nxt = __ldg(reinterpret_cast<const uint4*>(xb + (t_begin - 1) * plane));
+  for (int tt = t_begin - 1; tt <= t_end; ++tt) {
+    uint32_t m2[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
+    uint2 ccode = make_uint2(0u, 0u);
+    const uint4 cur = nxt;
+    if (live && tt + 1 <= t_end && tt + 1 < T) nxt = __ldg(reinterpret_cast<const uint4*>(xb + (tt + 1) * plane));
+    if (tt >= 0 && tt < T) {   // CTA-uniform
+      if (live) X[xs] = cur;
+      __syncthreads();
+      uint32_t cw[4] = {0u, 0u, 0u, 0u}, ch[4] = {0u, 0u, 0u, 0u};
+      if (live) {
+        uint32_t m1[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
+        first_max(m1, cw, X[xs - cgn], 0x00000000u);
+        first_max(m1, cw, cur, 0x00010001u);
+        first_max(m1, cw, X[xs + cgn], 0x00020002u);
+        M1[ms] = make_uint4(m1[0], m1[1], m1[2], m1[3]);
+      }
+      __syncthreads();
+      if (live) {
+        first_max(m2, ch, M1[ms - W * cgn], 0x00000000u);
+        first_max(m2, ch, M1[ms], 0x00040004u);
+        first_max(m2, ch, M1[ms + W * cgn], 0x00080008u);
+      }
+      ccode.x = __byte_perm(cw[0] | ch[0], cw[1] | ch[1], 0x6420);
+      ccode.y = __byte_perm(cw[2] | ch[2], cw[3] | ch[3], 0x6420);
+    }
+    const int to = tt - 1;
+    if (live && to >= t_begin && to < t_end) {
+      uint32_t best[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
+      uint32_t c3[4] = {0u, 0u, 0u, 0u};
+      first_max(best, c3, make_uint4(p2[0], p2[1], p2[2], p2[3]), 0x00000000u);
+      first_max(best, c3, make_uint4(p1[0], p1[1], p1[2], p1[3]), 0x00100010u);
+      first_max(best, c3, make_uint4(m2[0], m2[1], m2[2], m2[3]), 0x00200020u);
+      *reinterpret_cast<uint4*>(yb + to * plane) = make_uint4(best[0], best[1], best[2], best[3]);
+      uint2 o;
+      o.x = pcode.x | __byte_perm(c3[0], c3[1], 0x6420);
+      o.y = pcode.y | __byte_perm(c3[2], c3[3], 0x6420);
+      *reinterpret_cast<uint2*>(ib + to * plane) = o;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { p2[j] = p1[j]; p1[j] = m2[j]; }
+    pcode = ccode;
+  }
+}
+
+// ---- backward helpers: acc[j] += v[j] where the 2-bit code field of channel j equals d ----------
+__device__ __forceinline__ uint2 code_match(const uint2 code, const int shift, const uint32_t d) {
+  uint2 m;
+  m.x = __vcmpeq4((code.x >> shift) & 0x03030303u, d * 0x01010101u);
+  m.y = __vcmpeq4((code.y >> shift) & 0x03030303u, d * 0x01010101u);
+  return m;
+}
+__device__ __forceinline__ void acc_bf16(float (&acc)[8], const uint4 v, const uint2 m) {
+  const uint32_t d0 = v.x & __byte_perm(m.x, 0, 0x1100), d1 = v.y & __byte_perm(m.x, 0, 0x3322);
+  const uint32_t d2 = v.z & __byte_perm(m.y, 0, 0x1100), d3 = v.w & __byte_perm(m.y, 0, 0x3322);
+  acc[0] += bf16_lo(d0); acc[1] += bf16_hi(d0); acc[2] += bf16_lo(d1); acc[3] += bf16_hi(d1);
+  acc[4] += bf16_lo(d2); acc[5] += bf16_hi(d2); acc[6] += bf16_lo(d3); acc[7] += bf16_hi(d3);
+}
+__device__ __forceinline__ void acc_f32(float (&acc)[8], const float4 a, const float4 b, const uint2 m) {
+  if (m.x & 0x00000001u) acc[0] += a.x;
+  if (m.x & 0x00000100u) acc[1] += a.y;
+  if (m.x & 0x00010000u) acc[2] += a.z;
+  if (m.x & 0x01000000u) acc[3] += a.w;
+  if (m.y & 0x00000001u) acc[4] += b.x;
+  if (m.y & 0x00000100u) acc[5] += b.y;
+  if (m.y & 0x00010000u) acc[6] += b.z;
+  if (m.y & 0x01000000u) acc[7] += b.w;
+}
+
+// backward.  dx = relu_mask(addend + pool^T(dy)); same grid / item mapping as the forward.
+__global__ void __launch_bounds__(kPoolThreads)
+pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                   const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
+                   __nv_bfloat16* __restrict__ dx, const int T, const int H, const int W, const int C,
+                   const int cgn, const int tseg) {
+  extern __shared__ uint4 smem4[];
+  const int n2 = (H + 2) * W * cgn, n1 = H * (W + 2) * cgn, nc = (H + 2) * (W + 2) * cgn;
+  float4* G2a = reinterpret_cast<float4*>(smem4);     // [H+2][W][cgn]   channels 0-3
+  float4* G2b = G2a + n2;                             //                 channels 4-7
+  float4* G1a = G2b + n2;                             // [H][W+2][cgn]
+  float4* G1b = G1a + n1;
+  uint2* CD = reinterpret_cast<uint2*>(G1b + n1);     // [2][H+2][W+2][cgn]
+  const int items = H * W * cgn;
+  const int it = threadIdx.x;
+  const bool live = it < items;
+  const int cgi = it % cgn;
+  const int pos = it / cgn;
+  const int h = pos / W, w = pos - h * W;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < 2 * W * cgn; i += blockDim.x) {       // zero border rows of G2
+    const int side = i / (W * cgn), r = i - side * W * cgn;
+    const int o = (side ? (H + 1) * W * cgn : 0) + r;
+    G2a[o] = z4; G2b[o] = z4;
+  }
+  for (int i = threadIdx.x; i < H * 2 * cgn; i += blockDim.x) {       // zero border columns of G1
+    const int hh = i / (2 * cgn), r = i - hh * 2 * cgn;
+    const int o = (hh * (W + 2) + (r < cgn ? 0 : W + 1)) * cgn + (r % cgn);
+    G1a[o] = z4; G1b[o] = z4;
+  }
+  for (int i = threadIdx.x; i < 2 * nc; i += blockDim.x) CD[i] = make_uint2(0u, 0u);
+  __syncthreads();
+
+  const int b = blockIdx.z;
+  const int t_begin = blockIdx.y * tseg;
+  const int t_end = min(t_begin + tseg, T);
+  const long long plane = static_cast<long long>(H) * W * C;
+  const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (blockIdx.x * cgn + cgi) * 8 : 0;
+  const long long boff = static_cast<long long>(b) * T * plane + eoff;
+  const __nv_bfloat16* dyb = dy + boff;
+  const uint8_t* ib = idx + boff;
+  const int g2s = ((h + 1) * W + w) * cgn + cgi;
+  const int g1s = (h * (W + 2) + w + 1) * cgn + cgi;
+  const int cds = ((h + 1) * (W + 2) + w + 1) * cgn + cgi;
+  const int crow = (W + 2) * cgn;
+
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  auto ld_dy = [&](int t) { return (live && t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint4*>(dyb + t * plane)) : z; };
+  auto ld_cd = [&](int t) {
+    return (live && t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint2*>(ib + t * plane)) : make_uint2(0u, 0u);
+  };
+  uint4 dA = ld_dy(t_begin - 1), dB = ld_dy(t_begin), dC = ld_dy(t_begin + 1);
+  uint2 cA = ld_cd(t_begin - 1), cB = ld_cd(t_begin), cC = ld_cd(t_begin + 1);
+  for (int t = t_begin; t < t_end; ++t) {
+    // prefetch: next frame of the ring, and this frame's epilogue operands
+    const uint4 dN = ld_dy(t + 2);
+    const uint2 cN = ld_cd(t + 2);
+    uint4 av = z, rv = z;
+    if (live) {
+      if (addend) av = __ldg(reinterpret_cast<const uint4*>(addend + boff + t * plane));
+      if (relu_src) rv = __ldg(reinterpret_cast<const uint4*>(relu_src + boff + t * plane));
+    }
+    uint2* cd = CD + (t & 1) * nc;
+    // T stage: the window centred on frame t+1-d selected frame t iff its a3 == d
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.0f;
+    acc_bf16(g, dC, code_match(cC, 4, 0u));
+    acc_bf16(g, dB, code_match(cB, 4, 1u));
+    acc_bf16(g, dA, code_match(cA, 4, 2u));
+    if (live) {
+      G2a[g2s] = make_float4(g[0], g[1], g[2], g[3]);
+      G2b[g2s] = make_float4(g[4], g[5], g[6], g[7]);
+      cd[cds] = cB;
+    }
+    __syncthreads();
+    // H stage: the window centred on row h+1-d selected row h iff its a2 == d
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.0f;
+    if (live) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int o2 = g2s + (1 - d) * W * cgn;
+        acc_f32(g, G2a[o2], G2b[o2], code_match(cd[cds + (1 - d) * crow], 2, static_cast<uint32_t>(d)));
+      }
+      G1a[g1s] = make_float4(g[0], g[1], g[2], g[3]);
+      G1b[g1s] = make_float4(g[4], g[5], g[6], g[7]);
+    }
+    __syncthreads();
+    // W stage: the window centred on column w+1-d selected column w iff its a1 == d
+    if (live) {
+      if (addend) {
+        g[0] = bf16_lo(av.x); g[1] = bf16_hi(av.x); g[2] = bf16_lo(av.y); g[3] = bf16_hi(av.y);
+        g[4] = bf16_lo(av.z); g[5] = bf16_hi(av.z); g[6] = bf16_lo(av.w); g[7] = bf16_hi(av.w);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.0f;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int o1 = g1s + (1 - d) * cgn;
+        acc_f32(g, G1a[o1], G1b[o1], code_match(cd[cds + (1 - d) * cgn], 0, static_cast<uint32_t>(d)));
+      }
+      if (relu_src) {
+        const float f[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
+                            bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = f[j] > 0.0f ? g[j] : 0.0f;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+      o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(dx + boff + t * plane) = o;
+    }
+    dA = dB; dB = dC; dC = dN;
+    cA = cB; cB = cC; cC = cN;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the stride-2 pools ([1,3,3]/[1,2,2] at i3d.py:174,189 and 3x3x3/2x2x2 at :252).
+// One thread owns a 2x2(x2) patch of input elements x 8 channels: the patch is covered by at most
+// 2x2(x2) windows, so every arg-max byte and every dy value is loaded once per patch (all loads are
+// issued before the first use) instead of once per input element.
+// padded coordinate hp = h + pad_before; patch q holds hp = 2q, 2q+1; window ho = q contains both
+// (tap dh = 0 / 1), window ho = q-1 contains only hp = 2q (tap dh = 2).
+// ---------------------------------------------------------------------------------------------
+template <int KT>   // temporal kernel: 1 (stride 1) or 3 (stride 2)
+__global__ void __launch_bounds__(256)
+pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                   const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
+                   __nv_bfloat16* __restrict__ dx, const PoolGeom g, const int Qt, const int Qh, const int Qw) {
+  constexpr int NA = KT == 3 ? 2 : 1;
+  const int cg = g.C >> 3;
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= Qw * cg) return;
+  const int qw = i / cg;
+  const int c8 = i - qw * cg;
+  int row = blockIdx.x;
+  const int qh = row % Qh; row /= Qh;
+  const int qt = row % Qt;
+  const int b = row / Qt;
+  // ---- all window loads first ----
+  uint2 iv[NA][2][2];
+  uint4 dv[NA][2][2];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int to = qt - a, ho = qh - bb, wo = qw - c;
+        const bool ok = to >= 0 && to < g.To && ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo;
+        const long long off = ((((static_cast<long long>(b) * g.To + to) * g.Ho + ho) * g.Wo + wo) * cg + c8) * 8;
+        iv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint2*>(idx + off)) : make_uint2(0xffffffffu, 0xffffffffu);
+        dv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint4*>(dy + off)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+  for (int et = 0; et < NA; ++et) {
+    const int t = KT == 3 ? 2 * qt - g.pt + et : qt;
+    if (t < 0 || t >= g.T) continue;
+    // epilogue operands of the four in-plane patch elements
+    uint4 rv[2][2], av[2][2];
+    long long eo[2][2];
+    bool live[2][2];
+#pragma unroll
+    for (int eh = 0; eh < 2; ++eh)
+#pragma unroll
+      for (int ew = 0; ew < 2; ++ew) {
+        const int h = 2 * qh - g.ph + eh, w = 2 * qw - g.pw + ew;
+        live[eh][ew] = h >= 0 && h < g.H && w >= 0 && w < g.W;
+        eo[eh][ew] = ((((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * cg + c8) * 8;
+        rv[eh][ew] = (live[eh][ew] && relu_src) ? __ldg(reinterpret_cast<const uint4*>(relu_src + eo[eh][ew]))
+                                                 : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        av[eh][ew] = (live[eh][ew] && addend) ? __ldg(reinterpret_cast<const uint4*>(addend + eo[eh][ew]))
+                                               : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+    for (int eh = 0; eh < 2; ++eh)
+#pragma unroll
+      for (int ew = 0; ew < 2; ++ew) {
+        if (!live[eh][ew]) continue;
+        float acc[8];
+        const uint4 a4 = av[eh][ew];
+        acc[0] = bf16_lo(a4.x); acc[1] = bf16_hi(a4.x); acc[2] = bf16_lo(a4.y); acc[3] = bf16_hi(a4.y);
+        acc[4] = bf16_lo(a4.z); acc[5] = bf16_hi(a4.z); acc[6] = bf16_lo(a4.w); acc[7] = bf16_hi(a4.w);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          if (a == 1 && et != 0) continue;
+          const int dt = KT == 3 ? (a ? 2 : et) : 0;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            if (bb == 1 && eh != 0) continue;
+            const int dh = bb ? 2 : eh;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (c == 1 && ew != 0) continue;
+              const int dw = c ? 2 : ew;
+              const uint32_t tap4 = static_cast<uint32_t>((dt * 3 + dh) * 3 + dw) * 0x01010101u;
+              uint2 m;
+              m.x = __vcmpeq4(iv[a][bb][c].x, tap4);
+              m.y = __vcmpeq4(iv[a][bb][c].y, tap4);
+              acc_bf16(acc, dv[a][bb][c], m);
+            }
+          }
+        }
+        const uint4 r = rv[eh][ew];
+        const float f[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
+                            bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = f[j] > 0.0f ? acc[j] : 0.0f;
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(dx + eo[eh][ew]) = o;
+      }
+  }
+}
+
+// channel groups per CTA: the largest divisor of C/8 whose plane fits one CTA
+int pick_cgn(int H, int W, int C) {
+  const int hw = H * W;
+  if (hw > kPoolThreads || C % 8) return 0;
+  int best = 0;
+  for (int c = 1; c <= 16 && c * hw <= kPoolThreads; ++c)
+    if ((C / 8) % c == 0) best = c;
+  return best;
+}
+
+}  // namespace
+
+bool pool3s1_applicable(const PoolGeom& g) {
+  return g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 && pick_cgn(g.H, g.W, g.C) > 0;
+}
+
+int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
+  const int cgn = pick_cgn(g.H, g.W, g.C);
+  FAV_CHECK_ARG(cgn > 0 && idx, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
+  const int tseg = g.T >= 32 ? 8 : (g.T >= 8 ? 8 : g.T);
+  const size_t smem = (static_cast<size_t>(g.H) * (g.W + 2) + static_cast<size_t>(g.H + 2) * g.W) * cgn * 16;
+  static bool attr = false;
+  if (!attr) {
+    FAV_CUDA(cudaFuncSetAttribute(pool3s1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const int threads = round_up(g.H * g.W * cgn, 32);
+  dim3 grid(g.C / (8 * cgn), ceil_div(g.T, tseg), g.B);
+  pool3s1_fwd_kernel<<<grid, threads, smem, s>>>(x, y, idx, g.T, g.H, g.W, g.C, cgn, tseg);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
+                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
+  const int cgn = pick_cgn(g.H, g.W, g.C);
+  FAV_CHECK_ARG(cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
+  const int tseg = g.T >= 32 ? 8 : (g.T >= 8 ? 4 : g.T);
+  const size_t smem = (static_cast<size_t>(g.H + 2) * g.W * 2 + static_cast<size_t>(g.H) * (g.W + 2) * 2) * cgn * 16 +
+                      static_cast<size_t>(2) * (g.H + 2) * (g.W + 2) * cgn * 8;
+  static bool attr = false;
+  if (!attr) {
+    FAV_CUDA(cudaFuncSetAttribute(pool3s1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  const int threads = round_up(g.H * g.W * cgn, 32);
+  dim3 grid(g.C / (8 * cgn), ceil_div(g.T, tseg), g.B);
+  pool3s1_bwd_kernel<<<grid, threads, smem, s>>>(dy, idx, addend, relu_src, dx, g.T, g.H, g.W, g.C, cgn, tseg);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+bool pool_s2_applicable(const PoolGeom& g) {
+  const bool hw = g.kh == 3 && g.kw == 3 && g.sh == 2 && g.sw == 2;
+  return hw && ((g.kt == 1 && g.st == 1) || (g.kt == 3 && g.st == 2)) && g.C % 8 == 0;
+}
+
+int launch_pool_s2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
+                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
+  FAV_CHECK_ARG(pool_s2_applicable(g), "pool_s2_bwd: unsupported geometry");
+  const int Qt = g.kt == 3 ? (g.T - 1 + g.pt) / 2 + 1 : g.T;
+  const int Qh = (g.H - 1 + g.ph) / 2 + 1, Qw = (g.W - 1 + g.pw) / 2 + 1;
+  dim3 grid(g.B * Qt * Qh, ceil_div(Qw * (g.C / 8), 256));
+  if (g.kt == 3) pool_s2_bwd_kernel<3><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw);
+  else pool_s2_bwd_kernel<1><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+}  // namespace fav

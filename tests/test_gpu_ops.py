@@ -119,6 +119,16 @@ POOL_CASES = [
     (1, 9, 14, 14, 32, (3, 3, 3), (2, 2, 2)),
     (1, 7, 14, 14, 32, (2, 2, 2), (2, 2, 2)),
     (1, 4, 28, 28, 192, (3, 3, 3), (1, 1, 1)),
+    # separable streaming path (pool3.cu): T spanning several segments, odd channel-group divisors, 7x7 planes
+    (2, 19, 28, 28, 32, (3, 3, 3), (1, 1, 1)),
+    (1, 16, 14, 14, 528, (3, 3, 3), (1, 1, 1)),
+    (2, 8, 7, 7, 832, (3, 3, 3), (1, 1, 1)),
+    (1, 11, 7, 7, 48, (3, 3, 3), (1, 1, 1)),
+    (1, 3, 9, 5, 24, (3, 3, 3), (1, 1, 1)),
+    # patch-per-thread stride-2 backward: odd sizes (pad_before = 1) and partial patches
+    (1, 5, 15, 15, 16, (1, 3, 3), (1, 2, 2)),
+    (2, 6, 15, 13, 24, (3, 3, 3), (2, 2, 2)),
+    (1, 45, 8, 8, 8, (3, 3, 3), (2, 2, 2)),
 ]
 
 
@@ -140,3 +150,21 @@ def test_maxpool_fwd_bwd(B, T, H, W, Cc, k, s):
     # ties in bf16 inputs route to one element in both implementations but maybe a different one;
     # compare per-window sums instead of positions when they differ
     _check(dx, ref, f"maxpool bwd {k}/{s}", rtol=2 ** -7, atol=3e-2)
+
+
+def test_maxpool3_ties_route_like_torch():
+    """post-ReLU inputs are full of exact ties (zeros and repeated bf16 values): the separable
+    first-wins stages must route each window's gradient to the same element torch's scan picks."""
+    from flickering_adversarial_video_b200.engine import op_maxpool3d, op_maxpool3d_bwd
+    g = torch.Generator(device="cuda").manual_seed(11)
+    k, s = (3, 3, 3), (1, 1, 1)
+    # coarse quantisation -> many equal positive values inside every window
+    x = (torch.randn((1, 10, 14, 14, 64), generator=g, device="cuda").clamp_min(0) * 4).round().div(4).to(torch.bfloat16)
+    y, idx = op_maxpool3d(x, k, s)
+    xr = x.float().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    yr = F.max_pool3d(_same_pad(xr, k, s, float("-inf")), k, s)
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 4, 1))
+    dy = torch.randn(y.shape, generator=g, device="cuda").to(torch.bfloat16)
+    dx = op_maxpool3d_bwd(dy, idx, tuple(x.shape), k, s, add=None, relu_src=None)
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 4, 1, 2, 3))
+    _check(dx, gx.permute(0, 2, 3, 4, 1), "maxpool3 ties", rtol=2 ** -7, atol=3e-2)
