@@ -19,6 +19,8 @@
 namespace fav {
 
 __device__ int g_fav_timeout_flag = 0;
+// debug: cycles the halo MMA warp spent waiting [tempty, a_full, b_full, total, tiles] summed over CTAs (FAV_HALO_PROF=1)
+__device__ unsigned long long g_halo_prof[8];
 
 namespace {
 
@@ -221,7 +223,9 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const ConvGeom& g, int tile
   return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kHaloThreads = 224;   // + warp 6: weight-tile producer (A slabs and B tiles must not block each other)
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGeom g, const ConvEpilogue e, const int b_bytes) {
   extern __shared__ uint8_t smem_raw[];
@@ -229,7 +233,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + static_cast<size_t>(g.na) * g.slab_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(g.nb) * b_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(g.nb) * g.bgroup * b_bytes);
   uint64_t* a_full = bars;            // [4]
   uint64_t* a_empty = bars + 4;       // [4]
   uint64_t* b_full = bars + 8;        // [8]
@@ -258,40 +262,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: activation slabs =====================
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      // A slabs run one slab ahead of the B tiles that consume them
-      auto issue_slab = [&](const HaloTile& tc, int sidx) {
-        const int cb = sidx / 3;
-        const int dt = sidx - cb * 3;
-        mbar_wait(&a_empty[sa], pa ^ 1);
-        mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(g.slab_tx));
-        tma_load_5d(smem_a + static_cast<size_t>(sa) * g.slab_bytes, &tmA, &a_full[sa], cb * 64, -1, tc.h0 - 1,
-                    tc.t + dt - 1, tc.b);
-        if (++sa == g.na) { sa = 0; pa ^= 1; }
-      };
-      bool first = true;
-      HaloTile cur{};
+      int sa = 0;
+      uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        cur = decode_halo_tile(g, tile);
-        if (first) { issue_slab(cur, 0); first = false; }
+        const HaloTile tc = decode_halo_tile(g, tile);
         for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
-          // prefetch the next slab (of this tile or of the next tile of this CTA)
-          if (sidx + 1 < slabs_per_tile) {
-            issue_slab(cur, sidx + 1);
-          } else if (tile + static_cast<int>(gridDim.x) < total_tiles) {
-            issue_slab(decode_halo_tile(g, tile + gridDim.x), 0);
-          }
           const int cb = sidx / 3;
           const int dt = sidx - cb * 3;
-          for (int j = 0; j < 9; ++j) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(g.slab_tx));
+          tma_load_5d(smem_a + static_cast<size_t>(sa) * g.slab_bytes, &tmA, &a_full[sa], cb * 64, -1, tc.h0 - 1,
+                      tc.t + dt - 1, tc.b);
+          if (++sa == g.na) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== TMA producer: weight tiles =====================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % g.n_tiles) * g.bn;
+        for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
+          const int cb = sidx / 3;
+          const int dt = sidx - cb * 3;
+          for (int j = 0; j < 9; j += g.bgroup) {
             mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes));
-            const int tap = dt * 9 + j;
-            tma_load_2d(smem_b + static_cast<size_t>(sb) * b_bytes, &tmB, &b_full[sb], (tap * g.cblocks + cb) * 64,
-                        cur.n0);
+            mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes * g.bgroup));
+            for (int u = 0; u < g.bgroup; ++u) {
+              const int tap = dt * 9 + j + u;
+              tma_load_2d(smem_b + (static_cast<size_t>(sb) * g.bgroup + u) * b_bytes, &tmB, &b_full[sb],
+                          (tap * g.cblocks + cb) * 64, n0);
+            }
             if (++sb == g.nb) { sb = 0; pb ^= 1; }
           }
         }
@@ -308,37 +313,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t wp16 = static_cast<uint32_t>(g.Wp) * 8u;   // one padded row in 16-byte units
     const uint32_t tile16 = wp16 * static_cast<uint32_t>(g.nrows);
     const int acc_cols = g.acc_stages == 2 ? kAccCols : 0;
+    long long w_te = 0, w_a = 0, w_b = 0, n_tiles_done = 0;
+    const long long t_start = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      long long c0 = g.prof ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (g.prof) { w_te += clock64() - c0; ++n_tiles_done; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
       uint32_t accum = 0;
       int cb = 0, dt = 0;
       for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
         const int ksteps = min(4, (g.cin - cb * 64) >> 4);
+        c0 = g.prof ? clock64() : 0;
         mbar_wait(&a_full[sa], pa);
+        if (g.prof) w_a += clock64() - c0;
         const uint32_t slab_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.slab_bytes));
         uint32_t row_lo = slab_lo;     // + dh * Wp rows
         for (int dh = 0; dh < 3; ++dh) {
-#pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
+          for (int dw0 = 0; dw0 < 3; dw0 += g.bgroup) {
+            c0 = g.prof ? clock64() : 0;
             mbar_wait(&b_full[sb], pb);
+            if (g.prof) w_b += clock64() - c0;
             tc_fence_after();
-            const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * b_bytes));
-            const uint32_t a_lo = row_lo + 8u * dw;        // one position = 128 B = 8 x 16 B
+            const uint32_t b_grp = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * g.bgroup * b_bytes));
             if (elect_one()) {
-              uint32_t a_i = a_lo, d_i = d_tmem;
-              for (int i = 0; i < g.mt; ++i) {
+              for (int u = 0; u < g.bgroup; ++u) {
+                const uint32_t b_lo = b_grp + static_cast<uint32_t>(u) * static_cast<uint32_t>(b_bytes >> 4);
+                uint32_t a_i = row_lo + 8u * static_cast<uint32_t>(dw0 + u);   // one position = 128 B = 8 x 16 B
+                uint32_t d_i = d_tmem;
+                for (int i = 0; i < g.mt; ++i) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < ksteps) umma_bf16(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum | (k > 0 ? 1u : 0u));
+                  for (int k = 0; k < 4; ++k) {
+                    if (k < ksteps) umma_bf16(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum | (k > 0 ? 1u : 0u));
+                  }
+                  a_i += tile16;                       // next M tile: nrows padded rows further down the slab
+                  d_i += static_cast<uint32_t>(g.bn);
                 }
-                a_i += tile16;                       // next M tile: nrows padded rows further down the slab
-                d_i += static_cast<uint32_t>(g.bn);
+                accum = 1;
               }
-              accum = 1;
               umma_commit(&b_empty[sb]);
-              if (dh == 2 && dw == 2) {
+              if (dh == 2 && dw0 + g.bgroup == 3) {
                 umma_commit(&a_empty[sa]);
                 if (sidx == slabs_per_tile - 1) umma_commit(&tfull_bar[acc]);
               }
@@ -357,6 +372,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         acc_phase ^= 1;
       }
+    }
+    if (g.prof && lane == 0) {
+      atomicAdd(&g_halo_prof[0], static_cast<unsigned long long>(w_te));
+      atomicAdd(&g_halo_prof[1], static_cast<unsigned long long>(w_a));
+      atomicAdd(&g_halo_prof[2], static_cast<unsigned long long>(w_b));
+      atomicAdd(&g_halo_prof[3], static_cast<unsigned long long>(clock64() - t_start));
+      atomicAdd(&g_halo_prof[4], static_cast<unsigned long long>(n_tiles_done));
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -537,62 +559,92 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   g.cin = cin;
   g.cblocks = ceil_div(cin, 64);
   g.nkb = 27 * g.cblocks;
-  g.n_tiles = ceil_div(cout_pad, 256);
-  g.bn = round_up(ceil_div(cout_pad, g.n_tiles), 16);
-  FAV_CHECK_ARG(g.bn * g.n_tiles == cout_pad, "conv: cout_pad=%d not divisible into %d tiles of %d", cout_pad,
-                g.n_tiles, g.bn);
   g.B = B; g.T = T; g.H = H; g.W = W;
   g.Wp = W + 2;
   g.nrows = std::min(128 / g.Wp, H);
   FAV_CHECK_ARG(g.nrows >= 1, "conv halo: W=%d too wide", W);
-  // M tiles per CTA step that share each B tile: as many as fit TMEM (512 fp32 columns), double-buffered
-  // when 2*mt*bn <= 512; never more row groups than the plane has.
+  g.swz_base_offset = 0;   // tcgen05 applies the 128-byte swizzle on absolute smem addresses (measured)
+  // ---- choose the N split and the number of M tiles that share every weight tile ----
+  // Cost model from measurements on B200 (tools/ubench/, FAV_HALO_PROF, profiles/): shared-memory bandwidth
+  // (operand reads + TMA refills) and L2 -> SM bandwidth (~41 B/cycle/SM with all SMs pulling) bound these
+  // kernels, not the tensor pipe.
   {
     const int groups = ceil_div(H, g.nrows);
-    int mt = g.bn <= 128 ? std::min(4, 256 / g.bn) : 1;   // single-buffered accumulators cost more than the shared B saves
-    mt = std::max(1, std::min(mt, groups));
-    static int force_mt = -1;
+    const int budget = 222 * 1024;
+    const int sms = sm_count(device);
+    static int force_mt = -1, force_nt = -1;
     if (force_mt < 0) {
       const char* ev = getenv("FAV_HALO_MT");
       force_mt = ev ? atoi(ev) : 0;
+      ev = getenv("FAV_HALO_NT");
+      force_nt = ev ? atoi(ev) : 0;
     }
-    if (force_mt > 0) mt = std::max(1, std::min(std::min(force_mt, groups), 512 / g.bn));
-    g.mt = mt;
-    g.acc_stages = (2 * mt * g.bn <= 512) ? 2 : 1;
+    double best = 1e30;
+    int best_nt = 0, best_mt = 0, best_na = 0, best_nb = 0, best_bg = 1;
+    for (int nt = 1; nt <= 6; ++nt) {
+      if (cout_pad % (nt * 16)) continue;
+      const int bn = cout_pad / nt;
+      if (bn > 256) continue;
+      if (force_nt > 0 && nt != force_nt) continue;
+      for (int mt = 1; mt <= 4 && mt <= groups; ++mt) {
+        if (mt * bn > 512) break;
+        if (force_mt > 0 && mt != std::min(force_mt, groups)) continue;
+        const int slab_tx = (mt * g.nrows + 2) * g.Wp * 128;
+        const int slab_bytes = round_up(std::max(((mt - 1) * g.nrows * g.Wp + 130 + 2 * g.Wp) * 128, slab_tx), 1024);
+        const int b_bytes = bn * 128;
+        // weight tiles travel in groups of 3 taps (one dh row) per barrier when two groups fit: the issuing
+        // thread pays ~100 cycles per mbarrier wait and ~70 per commit, so fewer handshakes per MMA matter
+        int na = 3, bgroup = 3;
+        int nb = std::min(4, (budget - na * slab_bytes) / (3 * b_bytes));
+        if (nb < 2) { na = 2; nb = std::min(4, (budget - na * slab_bytes) / (3 * b_bytes)); }
+        if (nb < 2) {
+          bgroup = 1; na = 3;
+          nb = std::min(8, (budget - na * slab_bytes) / b_bytes);
+          if (nb < 4) { na = 2; nb = std::min(8, (budget - na * slab_bytes) / b_bytes); }
+          if (nb < 3) continue;
+        }
+        const int acc_stages = (2 * mt * bn <= 512) ? 2 : 1;
+        const double ksteps = std::min(4.0, cin / 16.0 / g.cblocks);   // average k-steps per 64-channel block
+        // cycles per 128 x bn x 16 MMA (measured, tools/ubench/umma_rate.cu + FAV_HALO_PROF): the tensor pipe needs
+        // bn/2; shared memory moves 128 B/cycle and must serve the operand reads (4 KB of A + 32*bn of B) AND the
+        // TMA writes that refill them (weight tile shared by mt M tiles, slab shared by 9 taps); the issuing
+        // thread needs ~45 cycles per tcgen05.mma plus ~200 per mbarrier wait + commit pair.
+        const double per_mma = std::max(std::max(bn / 2.0, (4096.0 + 32.0 * bn * (1.0 + 1.0 / mt) +
+                                                            slab_tx / (9.0 * ksteps * mt)) / 128.0),
+                                        45.0 + 200.0 / (bgroup * ksteps * mt));
+        const double mma = 27.0 * g.cblocks * ksteps * mt * per_mma;
+        const double l2 = (27.0 * g.cblocks * b_bytes + 3.0 * g.cblocks * slab_tx) / 41.0;
+        const double epi = mt * (bn / 16.0) * 400.0;   // epilogue of one tile; exposed (and slower: nothing to overlap) when single-buffered
+        const double per_tile = acc_stages == 2 ? std::max(std::max(mma, l2), epi) : std::max(mma, l2) + 1.5 * epi;
+        const long long tiles = static_cast<long long>(B) * T * ceil_div(H, g.nrows * mt) * nt;
+        const double waves = static_cast<double>(ceil_div64(tiles, sms));
+        const double cost = waves * per_tile;
+        if (cost < best) { best = cost; best_nt = nt; best_mt = mt; best_na = na; best_nb = nb; best_bg = bgroup; }
+      }
+    }
+    FAV_CHECK_ARG(best_nt > 0, "conv halo: no tiling fits (cout_pad=%d, W=%d)", cout_pad, W);
+    g.n_tiles = best_nt;
+    g.bn = cout_pad / best_nt;
+    g.mt = best_mt;
+    g.na = best_na;
+    g.nb = best_nb;
+    g.bgroup = best_bg;
+    g.acc_stages = (2 * g.mt * g.bn <= 512) ? 2 : 1;
+    if (getenv("FAV_DEBUG_PLAN"))
+      fprintf(stderr, "[fav] halo %dx%dx%d cin=%d cout=%d: bn=%d x%d, mt=%d, na=%d nb=%dx%d acc_stages=%d (model %.0f kclk)\n",
+              T, H, W, cin, cout_pad, g.bn, g.n_tiles, g.mt, g.na, g.nb, g.bgroup, g.acc_stages, best / 1e3);
   }
   g.th = ceil_div(H, g.nrows * g.mt);
   g.tw = 1; g.tt = T;
   g.m_tiles = B * T * g.th;
   g.slab_tx = (g.mt * g.nrows + 2) * g.Wp * 128;
   g.slab_bytes = round_up(std::max(((g.mt - 1) * g.nrows * g.Wp + 130 + 2 * g.Wp) * 128, g.slab_tx), 1024);
-  // Measured on B200: tcgen05.mma applies the 128-byte swizzle as a function of the absolute shared
-  // memory address, so a window that starts at any 128-byte row of a TMA-written slab reads correctly
-  // with base_offset = 0 (setting it to (start>>7)&7 double-counts the phase and fails parity).
-  g.swz_base_offset = 0;
   const int b_bytes = g.bn * 128;
   L->b_bytes = b_bytes;
   L->a_bytes = g.slab_bytes;
-  const int budget = 222 * 1024;
-  g.na = 3;
-  g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
-  if (g.nb < 4) {
-    g.na = 2;
-    g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
-  }
-  while (g.nb < 3 && g.mt > 1) {   // shrink the super-tile until the rings fit
-    g.mt -= 1;
-    g.acc_stages = (2 * g.mt * g.bn <= 512) ? 2 : 1;
-    g.th = ceil_div(H, g.nrows * g.mt);
-    g.m_tiles = B * T * g.th;
-    g.slab_tx = (g.mt * g.nrows + 2) * g.Wp * 128;
-    g.slab_bytes = round_up(std::max(((g.mt - 1) * g.nrows * g.Wp + 130 + 2 * g.Wp) * 128, g.slab_tx), 1024);
-    L->a_bytes = g.slab_bytes;
-    g.nb = std::min(8, (budget - g.na * g.slab_bytes) / b_bytes);
-  }
-  FAV_CHECK_ARG(g.nb >= 2, "conv halo: shared memory budget exceeded (slab %d B, B tile %d B)", g.slab_bytes, b_bytes);
   L->stages = g.nb;
   L->stage_bytes = b_bytes;
-  L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * b_bytes + 1024 + 512;
+  L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * b_bytes + 1024 + 512;
 
   uint64_t dims[5], strides[4];
   uint32_t box[5];
@@ -628,7 +680,24 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
       FAV_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr2 = true;
     }
-    conv_halo_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmB, L.g, L.e, L.b_bytes);
+    static int prof = -1;
+    if (prof < 0) prof = getenv("FAV_HALO_PROF") ? 1 : 0;
+    if (prof) {
+      ConvGeom gp = L.g;
+      gp.prof = 1;
+      unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
+      cudaMemcpyToSymbol(g_halo_prof, z, sizeof(z));
+      conv_halo_kernel<<<L.grid, kHaloThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmB, gp, L.e, L.b_bytes);
+      cudaStreamSynchronize(stream);
+      cudaMemcpyFromSymbol(r, g_halo_prof, sizeof(r));
+      const double n = L.grid;
+      fprintf(stderr, "[fav] halo prof T%d H%d W%d cin=%d bn=%dx%d mt=%d: per-CTA kclk total %.0f, wait tempty %.0f, a_full %.0f, b_full %.0f, tiles %.1f\n",
+              L.g.T, L.g.H, L.g.W, L.g.cin, L.g.bn, L.g.n_tiles, L.g.mt, r[3] / n / 1e3, r[0] / n / 1e3, r[1] / n / 1e3,
+              r[2] / n / 1e3, r[4] / n);
+      FAV_COUNT_LAUNCH();
+      return FAV_OK;
+    }
+    conv_halo_kernel<<<L.grid, kHaloThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmB, L.g, L.e, L.b_bytes);
     FAV_COUNT_LAUNCH();
     FAV_CUDA(cudaGetLastError());
     return FAV_OK;

@@ -30,10 +30,12 @@ struct ConvGeom {
   int Wp, nrows;       // padded row pitch and output rows per tile (nrows*Wp <= 128)
   int slab_bytes;      // bytes reserved per slab (>= (130 + 2*Wp) rows, multiple of 1024)
   int slab_tx;         // bytes one slab TMA delivers = (nrows+2)*Wp*128
-  int na, nb;          // A-slab ring depth, B-tile ring depth
+  int na, nb;          // A-slab ring depth, B ring depth (in groups of bgroup weight tiles)
+  int bgroup;          // weight tiles (taps) per mbarrier handshake: 3 (one dh row) or 1
   int mt;              // M tiles (of nrows rows each) that share every B tile load: mt accumulators of bn columns
   int acc_stages;      // 2: accumulators double-buffered (2*mt*bn <= 512), 1: single-buffered
   int swz_base_offset; // 1: put (start>>7)&7 into the descriptor's base_offset field
+  int prof;            // 1: the MMA warp records its barrier wait cycles (debug, FAV_HALO_PROF)
 };
 
 struct ConvEpilogue {
@@ -66,52 +68,65 @@ struct ConvLaunch {
 
 
 #ifdef __CUDACC__
-// Epilogue of one accumulator row: TMEM -> registers (16 fp32 columns at a time) -> bias / addend /
-// ReLU / ReLU-mask -> bf16 -> 16-byte stores into the NDHWC channel slice.
+// Epilogue of one accumulator row: TMEM -> registers -> bias / addend / ReLU / ReLU-mask -> bf16 -> 16-byte
+// stores into the NDHWC channel slice.  Columns are processed 64 at a time with every load of the group
+// (4 tcgen05.ld, the mask / addend rows, the bias) issued before the first use: the epilogue is a chain of
+// memory latencies per group, so the fewer groups the better.
 __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
                                                  __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
                                                  const __nv_bfloat16* add_row, const float* bias_row) {
-  for (int c = 0; c < bn; c += 16) {
-  uint32_t r[16];
-  tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r);
-  tmem_ld_wait();
-  const int n = n0 + c;  // first output channel of this chunk
-  if (valid && n < e.cout_store) {
-    float v[16];
+  for (int c0 = 0; c0 < bn; c0 += 64) {
+    uint32_t r[4][16];
+    uint4 av[4][2], mv[4][2];
+    bool live[4][2];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-    if (bias_row) {
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + q * 16;
+      if (c < bn) tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r[q]);   // warp-uniform condition
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
-        v[j] += bv.x;
-        v[j + 1] += bv.y;
-        v[j + 2] += bv.z;
-        v[j + 3] += bv.w;
+      for (int half = 0; half < 2; ++half) {
+        const int n = n0 + c + half * 8;
+        live[q][half] = valid && c < bn && n + 8 <= e.cout_store;
+        av[q][half] = make_uint4(0u, 0u, 0u, 0u);
+        mv[q][half] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        if (live[q][half]) {
+          if (add_row) av[q][half] = *reinterpret_cast<const uint4*>(add_row + n);
+          if (mask_row) mv[q][half] = __ldg(reinterpret_cast<const uint4*>(mask_row + n));
+        }
       }
     }
+    tmem_ld_wait();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (n + half * 8 + 8 <= e.cout_store) {
-        float* vv = v + half * 8;
-        if (add_row) {
-          const uint4 a = *reinterpret_cast<const uint4*>(add_row + n + half * 8);
-          vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x);
-          vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
-          vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z);
-          vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + q * 16;
+      if (c >= bn) break;
+      const int n = n0 + c;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[q][j]);
+      if (bias_row && valid && n < e.cout_store) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));
+          v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
         }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (!live[q][half]) continue;
+        float* vv = v + half * 8;
+        const uint4 a = av[q][half];
+        vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x); vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
+        vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z); vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
         if (e.relu) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
         }
-        if (mask_row) {
-          const uint4 mk = *reinterpret_cast<const uint4*>(mask_row + n + half * 8);
-          vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
-          vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
-          vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
-          vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
-        }
+        const uint4 mk = mv[q][half];
+        vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
+        vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
+        vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
+        vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
         uint4 o;
         o.x = pack_bf16x2(vv[0], vv[1]);
         o.y = pack_bf16x2(vv[2], vv[3]);
@@ -121,7 +136,6 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
       }
     }
   }
-}
 }
 
 #endif

@@ -426,16 +426,28 @@ head_feat_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ feat, 
   }
 }
 
-__global__ void head_logits_kernel(const float* __restrict__ feat, const float* __restrict__ wl,
-                                   const float* __restrict__ bl, float* __restrict__ logits, int C, int K) {
-  extern __shared__ float sfeat[];
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) sfeat[c] = feat[static_cast<long long>(b) * C + c];
+// logits[b,k] = bl[k] + sum_c feat[b,c] * wl[c,k]; one block = 64 classes x 8 channel slices of one clip
+__global__ void __launch_bounds__(512)
+head_logits_kernel(const float* __restrict__ feat, const float* __restrict__ wl, const float* __restrict__ bl,
+                   float* __restrict__ logits, int C, int K) {
+  __shared__ float red[8][64];
+  const int b = blockIdx.y;
+  const int kl = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int k = blockIdx.x * 64 + kl;
+  float acc = 0.0f;
+  if (k < K) {
+    const int c0 = sl * ((C + 7) / 8), c1 = min(C, c0 + (C + 7) / 8);
+    const float* f = feat + static_cast<long long>(b) * C;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) acc = fmaf(__ldg(f + c), __ldg(wl + static_cast<long long>(c) * K + k), acc);
+  }
+  red[sl][kl] = acc;
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float acc = bl[k];
-    for (int c = 0; c < C; ++c) acc = fmaf(sfeat[c], wl[static_cast<long long>(c) * K + k], acc);
-    logits[static_cast<long long>(b) * K + k] = acc;
+  if (sl == 0 && k < K) {
+    float sum = bl[k];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red[i][kl];
+    logits[static_cast<long long>(b) * K + k] = sum;
   }
 }
 
@@ -446,7 +458,7 @@ int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float*
   head_feat_kernel<<<grid, 256, 0, s>>>(y, feat, T5, HW, C);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
-  head_logits_kernel<<<B, 512, C * sizeof(float), s>>>(feat, wl, bl, logits, C, K);
+  head_logits_kernel<<<dim3(ceil_div(K, 64), B), 512, 0, s>>>(feat, wl, bl, logits, C, K);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -708,52 +720,78 @@ int launch_loss(const float* logits, const int64_t* labels, const fav_loss_param
 __device__ __forceinline__ int border_class(int i, int n) {
   return i == 0 ? 0 : (i == n - 2 ? 2 : (i == n - 1 ? 3 : 1));
 }
+// general form: the first nlo and the last nhi outputs touch the zero padding (nlo + nhi <= 3)
+__device__ __forceinline__ int stem_border_class(int o, int n, int nlo, int nhi) {
+  return o < nlo ? o : (o >= n - nhi ? nlo + 1 + (o - (n - nhi)) : nlo);
+}
 
-__global__ void __launch_bounds__(128)
-stem_class_sums_kernel(const __nv_bfloat16* __restrict__ g1, float* __restrict__ S, int To, int Ho, int Wo) {
-  __shared__ float red[16][4][64];
-  const int ho = blockIdx.x % Ho;
-  const int to = blockIdx.x / Ho;
+// block = (b, t_o, chunk of kClassRows output rows); thread = (8-channel group, position lane).
+// Rows of one H class accumulate in registers; a class change (only at the plane borders) flushes.
+constexpr int kClassRows = 8;
+__global__ void __launch_bounds__(256)
+stem_class_sums_kernel(const __nv_bfloat16* __restrict__ g1, float* __restrict__ S, int To, int Ho, int Wo,
+                       int nlo_h, int nhi_h, int nlo_w, int nhi_w) {
+  __shared__ float red[32][4][64];
+  const int chunks = (Ho + kClassRows - 1) / kClassRows;
+  const int hchunk = blockIdx.x % chunks;
+  const int to = blockIdx.x / chunks;
   const int b = blockIdx.y;
   const int cgp = threadIdx.x & 7;   // 8-channel group
-  const int pl = threadIdx.x >> 3;   // position lane 0..15
+  const int pl = threadIdx.x >> 3;   // position lane 0..31
   float acc[4][8];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[k][j] = 0.0f;
-  const __nv_bfloat16* rowp = g1 + (((static_cast<long long>(b) * To + to) * Ho + ho) * Wo) * 64;
-  for (int w = pl; w < Wo; w += 16) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(w) * 64 + cgp * 8));
-    const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                        bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
-    const int wc = border_class(w, Wo);
+  auto zero = [&]() {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k == wc) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[k][j] += f[j];
-      }
+      for (int j = 0; j < 8; ++j) acc[k][j] = 0.0f;
+  };
+  auto flush = [&](int hc) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[pl][k][cgp * 8 + j] = acc[k][j];
+    __syncthreads();
+    {
+      const int k = threadIdx.x >> 6, co = threadIdx.x & 63;
+      float sum = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) sum += red[q][k][co];
+      if (sum != 0.0f) atomicAdd(&S[((to * 4 + hc) * 4 + k) * 64 + co], sum);
+    }
+    __syncthreads();
+  };
+  zero();
+  const int h_begin = hchunk * kClassRows, h_end = min(Ho, h_begin + kClassRows);
+  int cur = stem_border_class(h_begin, Ho, nlo_h, nhi_h);
+  for (int ho = h_begin; ho < h_end; ++ho) {
+    const int hc = stem_border_class(ho, Ho, nlo_h, nhi_h);
+    if (hc != cur) {   // block-uniform
+      flush(cur);
+      zero();
+      cur = hc;
+    }
+    const __nv_bfloat16* rowp = g1 + (((static_cast<long long>(b) * To + to) * Ho + ho) * Wo) * 64;
+#pragma unroll 4
+    for (int w = pl; w < Wo; w += 32) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(w) * 64 + cgp * 8));
+      const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                          bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+      const int wc = stem_border_class(w, Wo, nlo_w, nhi_w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k == wc) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k][j] += f[j];
+        }
+    }
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[pl][k][cgp * 8 + j] = acc[k][j];
-  __syncthreads();
-  const int hc = border_class(ho, Ho);
-  for (int i = threadIdx.x; i < 256; i += 128) {
-    const int k = i >> 6, co = i & 63;
-    float sum = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) sum += red[q][k][co];
-    if (sum != 0.0f) atomicAdd(&S[((to * 4 + hc) * 4 + k) * 64 + co], sum);
-  }
+  flush(cur);
 }
 
 int launch_stem_class_sums(const __nv_bfloat16* g1, float* S, int B, int To, int Ho, int Wo, cudaStream_t s) {
   FAV_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(To) * 16 * 64 * sizeof(float), s));
-  dim3 grid(To * Ho, B);
-  stem_class_sums_kernel<<<grid, 128, 0, s>>>(g1, S, To, Ho, Wo);
+  dim3 grid(To * ceil_div(Ho, kClassRows), B);
+  stem_class_sums_kernel<<<grid, 256, 0, s>>>(g1, S, To, Ho, Wo, 1, 2, 1, 2);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
