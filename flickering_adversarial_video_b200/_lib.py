@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libfav.so")
 FAV_OK = 0
 FAV_U8, FAV_F32 = 0, 1
 FAV_STACK_TF, FAV_STACK_TORCH = 0, 1
-FAV_NET_I3D = 0
+FAV_NET_I3D, FAV_NET_R3D_18, FAV_NET_MC3_18, FAV_NET_R2PLUS1D_18 = 0, 1, 2, 3
+ARCHS = {"i3d": FAV_NET_I3D, "r3d_18": FAV_NET_R3D_18, "mc3_18": FAV_NET_MC3_18, "r2plus1d_18": FAV_NET_R2PLUS1D_18}
 
 # indices into the device scalar block (include/fav.h)
 S_ADV_LOSS, S_FOOLED, S_SUM_P_MIN, S_SUM_P_MAX = 0, 1, 2, 3

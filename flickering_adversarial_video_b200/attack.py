@@ -19,10 +19,18 @@ from .engine import FlickerEngine
 
 
 class FlickerAttack:
-    def __init__(self, weights, batch, frames, attack_cfg=None, height=224, width=224, num_classes=400,
-                 device=0, lr=1e-3, stack="tf", delta_clip=0.4, process_group=None):
-        self.eng = FlickerEngine(batch, frames, height, width, num_classes, device)
+    def __init__(self, weights, batch, frames, attack_cfg=None, height=None, width=None, num_classes=400,
+                 device=0, lr=1e-3, stack=None, delta_clip=None, process_group=None, arch="i3d"):
+        """arch "i3d": TF-stack rules, delta_clip 0.4 (utils/kinetics_i3d_utils.py:104-105).
+        arch "r3d_18"/"mc3_18"/"r2plus1d_18": torch-stack rules (model.py:58-250): delta_clip is
+        l_inf_pert_norm, the regulariser is beta_1*thick + (1-beta_1)*(diff+lap) on the clamped delta."""
+        self.eng = FlickerEngine(batch, frames, height, width, num_classes, device, arch=arch)
         self.eng.load_weights(weights)
+        self.arch = arch
+        if stack is None:
+            stack = "torch" if self.eng.torch_stack else "tf"
+        if delta_clip is None:
+            delta_clip = 0.1 if self.eng.torch_stack else 0.4   # r2plus1d_main_universal_attack.py:45
         self.device = self.eng.device
         self.B, self.T, self.K = batch, frames, num_classes
         self.stack = L.FAV_STACK_TF if stack == "tf" else L.FAV_STACK_TORCH
@@ -37,6 +45,9 @@ class FlickerAttack:
         self.beta1 = float(cfg.get("BETA_1", 0.5))
         self.beta2 = float(cfg.get("BETA_2", 0.5))
         self.beta3 = float(cfg.get("BETA_2", 0.5))   # the drivers set _beta_3 = BETA_2 (single_video_npy.py:98)
+        if self.stack == L.FAV_STACK_TORCH:
+            # Losses.flickering_regularization_loss (model.py:198-209): beta_1*norm + (1-beta_1)*(diff + lap)
+            self.beta2 = self.beta3 = 1.0 - self.beta1
         # distributed
         self.pg = process_group
         self.world = 1

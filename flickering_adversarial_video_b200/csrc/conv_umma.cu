@@ -104,8 +104,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int dw = tap % g.kw;
             const int dh = (tap / g.kw) % g.kh;
             const int dt = tap / (g.kw * g.kh);
-            tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 + dw + g.ow, tc.h0 + dh + g.oh,
-                        tc.t0 + dt + g.ot, tc.b);
+            tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 * g.sw + dw + g.ow, tc.h0 * g.sh + dh + g.oh,
+                        tc.t0 * g.st + dt + g.ot, tc.b);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
           }
           if (++stage == stages) {
@@ -174,7 +174,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const TileCoord tc = decode_tile(g, tile);
       const int w = tc.w0 + rw, h = tc.h0 + rh, t = tc.t0 + rt;
       const bool valid = (w < g.W) && (h < g.H) && (t < g.T);
-      const long long pos = ((static_cast<long long>(tc.b) * g.T + t) * g.H + h) * g.W + w;
+      // output position (identity for plain convs; strided scatter for the parity classes of a strided dgrad)
+      const long long pos = ((static_cast<long long>(tc.b) * g.oT + (t * g.est + g.eot)) * g.oH + (h * g.esh + g.eoh)) * g.oW +
+                            (w * g.esw + g.eow);
       __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
       const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
       const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
@@ -485,57 +487,80 @@ static void finish_plan(ConvLaunch* L, int device) {
   L->grid = std::max(1, std::min(tiles, sm_count(device)));
 }
 
+int conv_plan_ex(ConvLaunch* L, int device, const ConvSpec& sp) {
+  FAV_CHECK_ARG(sp.cin % 16 == 0 && sp.cin > 0, "conv: cin=%d must be a positive multiple of 16", sp.cin);
+  FAV_CHECK_ARG(sp.x_cs % 8 == 0 && sp.x_coff % 8 == 0, "conv: channel stride/offset must be multiples of 8");
+  FAV_CHECK_ARG(sp.cout_pad % 16 == 0 && sp.cout_pad > 0, "conv: padded cout=%d must be a multiple of 16", sp.cout_pad);
+  FAV_CHECK_ARG(sp.st >= 1 && sp.sh >= 1 && sp.sw >= 1 && sp.st <= 8 && sp.sh <= 8 && sp.sw <= 8, "conv: bad strides");
+  memset(L, 0, sizeof(*L));
+  ConvGeom& g = L->g;
+  g.kt = sp.kt; g.kh = sp.kh; g.kw = sp.kw;
+  g.ot = sp.ot; g.oh = sp.oh; g.ow = sp.ow;
+  g.st = sp.st; g.sh = sp.sh; g.sw = sp.sw;
+  g.cin = sp.cin;
+  g.cblocks = ceil_div(sp.cin, 64);
+  g.nkb = sp.kt * sp.kh * sp.kw * g.cblocks;
+  g.n_tiles = ceil_div(sp.cout_pad, 256);
+  g.bn = round_up(ceil_div(sp.cout_pad, g.n_tiles), 16);
+  // the last N tile may be partial: weight rows past cout_pad are TMA out-of-bounds zeros and the epilogue
+  // stores only channels below cout_store
+  g.B = sp.B; g.T = sp.T; g.H = sp.H; g.W = sp.W;
+  g.oT = sp.oT; g.oH = sp.oH; g.oW = sp.oW;
+  g.est = sp.est; g.esh = sp.esh; g.esw = sp.esw;
+  g.eot = sp.eot; g.eoh = sp.eoh; g.eow = sp.eow;
+  choose_box(sp.T, sp.H, sp.W, sp.kt, sp.kh, sp.kw, &g.bw, &g.bh, &g.bt);
+  // element-strided boxes traverse bw*sw elements (<= 256)
+  while (g.bw * sp.sw > 256) { g.bw /= 2; g.bh *= 2; }
+  while (g.bh * sp.sh > 256) { g.bh /= 2; g.bt *= 2; }
+  FAV_CHECK_ARG(g.bt * sp.st <= 256, "conv: strided box too large");
+  uint64_t dims[5], strides[4];
+  uint32_t box[5], estr[5];
+  const char* base = static_cast<const char*>(sp.x) + static_cast<long long>(sp.x_coff) * 2;
+  dims[0] = static_cast<uint64_t>(sp.cin);
+  dims[1] = static_cast<uint64_t>(sp.aW);
+  dims[2] = static_cast<uint64_t>(sp.aH);
+  dims[3] = static_cast<uint64_t>(sp.aT);
+  dims[4] = static_cast<uint64_t>(sp.B);
+  strides[0] = static_cast<uint64_t>(sp.x_cs) * 2;
+  strides[1] = strides[0] * sp.aW;
+  strides[2] = strides[1] * sp.aH;
+  strides[3] = strides[2] * sp.aT;
+  box[0] = 64; box[1] = g.bw * sp.sw; box[2] = g.bh * sp.sh; box[3] = g.bt * sp.st; box[4] = 1;
+  estr[0] = 1; estr[1] = sp.sw; estr[2] = sp.sh; estr[3] = sp.st; estr[4] = 1;
+  FAV_TRY(make_tmap_bf16(&L->tmA[0], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr));
+  L->tmA[1] = L->tmA[0]; L->tmA[2] = L->tmA[0]; L->tmA[3] = L->tmA[0];
+  uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(sp.cout_pad)};
+  uint64_t bs[1] = {bd[0] * 2};
+  uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+  FAV_TRY(make_tmap_bf16(&L->tmB, sp.wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  finish_plan(L, device);
+  return FAV_OK;
+}
+
 int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
                       const void* wpk, int cout_pad, int B, int T, int H, int W, int kt, int kh,
                       int kw, int flat) {
-  FAV_CHECK_ARG(cin % 16 == 0 && cin > 0, "conv: cin=%d must be a positive multiple of 16", cin);
-  FAV_CHECK_ARG(x_cs % 8 == 0 && x_coff % 8 == 0, "conv: channel stride/offset must be multiples of 8");
-  FAV_CHECK_ARG(cout_pad % 16 == 0 && cout_pad > 0, "conv: padded cout=%d must be a multiple of 16", cout_pad);
-  memset(L, 0, sizeof(*L));
-  ConvGeom& g = L->g;
-  g.kt = kt; g.kh = kh; g.kw = kw;
-  g.ot = -((kt - 1) / 2); g.oh = -((kh - 1) / 2); g.ow = -((kw - 1) / 2);
-  g.cin = cin;
-  g.cblocks = ceil_div(cin, 64);
-  g.nkb = kt * kh * kw * g.cblocks;
-  g.n_tiles = ceil_div(cout_pad, 256);
-  g.bn = round_up(ceil_div(cout_pad, g.n_tiles), 16);
-  FAV_CHECK_ARG(g.bn * g.n_tiles == cout_pad, "conv: cout_pad=%d not divisible into %d tiles of %d",
-                cout_pad, g.n_tiles, g.bn);
-
-  uint64_t dims[5], strides[4];
-  uint32_t box[5];
-  const char* base = static_cast<const char*>(x) + static_cast<long long>(x_coff) * 2;
+  ConvSpec sp{};
+  sp.x = x; sp.x_cs = x_cs; sp.x_coff = x_coff; sp.cin = cin;
+  sp.wpk = wpk; sp.cout_pad = cout_pad;
+  sp.kt = kt; sp.kh = kh; sp.kw = kw;
+  sp.ot = -((kt - 1) / 2); sp.oh = -((kh - 1) / 2); sp.ow = -((kw - 1) / 2);
+  sp.st = sp.sh = sp.sw = 1;
+  sp.est = sp.esh = sp.esw = 1;
+  sp.eot = sp.eoh = sp.eow = 0;
   if (flat) {
     FAV_CHECK_ARG(kt == 1 && kh == 1 && kw == 1, "conv: flat tiling needs a 1x1x1 kernel");
     const long long M = static_cast<long long>(B) * T * H * W;
     FAV_CHECK_ARG(M < (1ll << 31), "conv: too many positions");
-    g.B = 1; g.T = 1; g.H = 1; g.W = static_cast<int>(M);
-    g.bw = 128; g.bh = 1; g.bt = 1;
+    sp.B = 1; sp.T = 1; sp.H = 1; sp.W = static_cast<int>(M);
   } else {
-    g.B = B; g.T = T; g.H = H; g.W = W;
-    choose_box(T, H, W, kt, kh, kw, &g.bw, &g.bh, &g.bt);
+    sp.B = B; sp.T = T; sp.H = H; sp.W = W;
   }
-  dims[0] = static_cast<uint64_t>(cin);
-  dims[1] = static_cast<uint64_t>(g.W);
-  dims[2] = static_cast<uint64_t>(g.H);
-  dims[3] = static_cast<uint64_t>(g.T);
-  dims[4] = static_cast<uint64_t>(g.B);
-  strides[0] = static_cast<uint64_t>(x_cs) * 2;
-  strides[1] = strides[0] * g.W;
-  strides[2] = strides[1] * g.H;
-  strides[3] = strides[2] * g.T;
-  box[0] = 64; box[1] = g.bw; box[2] = g.bh; box[3] = g.bt; box[4] = 1;
-  FAV_TRY(make_tmap_bf16(&L->tmA[0], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
-  L->tmA[1] = L->tmA[0]; L->tmA[2] = L->tmA[0]; L->tmA[3] = L->tmA[0];
-
-  uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cout_pad)};
-  uint64_t bs[1] = {bd[0] * 2};
-  uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
-  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
-  finish_plan(L, device);
-  return FAV_OK;
+  sp.aT = sp.T; sp.aH = sp.H; sp.aW = sp.W;
+  sp.oT = sp.T; sp.oH = sp.H; sp.oW = sp.W;
+  return conv_plan_ex(L, device, sp);
 }
+
 
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw) {
   (void)T;
@@ -582,9 +607,8 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     double best = 1e30;
     int best_nt = 0, best_mt = 0, best_na = 0, best_nb = 0, best_bg = 1;
     for (int nt = 1; nt <= 6; ++nt) {
-      if (cout_pad % (nt * 16)) continue;
-      const int bn = cout_pad / nt;
-      if (bn > 256) continue;
+      const int bn = round_up(ceil_div(cout_pad, nt), 16);   // the last N tile may be partial (TMA zero fill)
+      if (bn > 256 || bn * (nt - 1) >= cout_pad) continue;
       if (force_nt > 0 && nt != force_nt) continue;
       for (int mt = 1; mt <= 4 && mt <= groups; ++mt) {
         if (mt * bn > 512) break;
@@ -624,7 +648,7 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     }
     FAV_CHECK_ARG(best_nt > 0, "conv halo: no tiling fits (cout_pad=%d, W=%d)", cout_pad, W);
     g.n_tiles = best_nt;
-    g.bn = cout_pad / best_nt;
+    g.bn = round_up(ceil_div(cout_pad, best_nt), 16);
     g.mt = best_mt;
     g.na = best_na;
     g.nb = best_nb;
@@ -708,6 +732,23 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
+}
+
+void pack_weights_taps(uint16_t* dst, const float* w, const float* scale, const int* src, int ntaps, int cin_real,
+                       int cout_real, int kch, int n_pad, bool dgrad) {
+  const int cblocks = ceil_div(kch, 64);
+  const size_t K = static_cast<size_t>(ntaps) * cblocks * 64;
+  memset(dst, 0, K * n_pad * sizeof(uint16_t));
+  for (int j = 0; j < ntaps; ++j) {
+    const float* wt = w + static_cast<size_t>(src[j]) * cin_real * cout_real;
+    for (int ci = 0; ci < cin_real; ++ci)
+      for (int co = 0; co < cout_real; ++co) {
+        const float v = wt[static_cast<size_t>(ci) * cout_real + co] * (scale ? scale[co] : 1.0f);
+        const int kc = dgrad ? co : ci, n = dgrad ? ci : co;
+        const size_t kidx = (static_cast<size_t>(j) * cblocks + kc / 64) * 64 + kc % 64;
+        dst[static_cast<size_t>(n) * K + kidx] = f32_to_bf16_bits(v);
+      }
+  }
 }
 
 void pack_weights_fwd(uint16_t* dst, const float* w, const float* scale, int taps, int cin_real,

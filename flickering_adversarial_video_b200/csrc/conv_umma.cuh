@@ -19,6 +19,9 @@ struct ConvGeom {
   int tw, th, tt;      // tiles per dim
   int kt, kh, kw;      // taps
   int ot, oh, ow;      // coordinate offset of tap 0 (= -pad_before)
+  int st, sh, sw;      // A coordinate stride per position (generic path; TMA element strides)
+  int oT, oH, oW;      // output tensor dims; output position = pos * es + eo (generic path)
+  int est, esh, esw, eot, eoh, eow;
   int cin;             // K channels per tap as seen by the kernel (multiple of 16)
   int cblocks;         // ceil(cin / 64)
   int nkb;             // k-blocks per tile
@@ -143,6 +146,20 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
 // Pick the M-tile box for a [T,H,W] volume and a kt x kh x kw kernel.
 void choose_box(int T, int H, int W, int kt, int kh, int kw, int* bw, int* bh, int* bt);
 
+// General form of the per-tap path.  GEMM rows are the positions of a [B,T,H,W] grid; tap (dt,dh,dw) of position
+// (t,h,w) reads A at (t*st + dt + ot, ...) of the [B,aT,aH,aW,x_cs] tensor (out of range = zero), and the result
+// row is stored at (t*est + eot, ...) of the [B,oT,oH,oW] output.  Strided forward convs use st/sh/sw, the parity
+// classes of a strided data gradient use est/eot (see fav_api.cu::plan_dgrad_classes).
+struct ConvSpec {
+  const void* x; long long x_cs; int x_coff; int cin;
+  int aT, aH, aW;
+  const void* wpk; int cout_pad;
+  int B, T, H, W;
+  int kt, kh, kw, ot, oh, ow, st, sh, sw;
+  int oT, oH, oW, est, esh, esw, eot, eoh, eow;
+};
+int conv_plan_ex(ConvLaunch* L, int device, const ConvSpec& sp);
+
 // Fill geometry-derived fields + tensor maps for a stride-1 SAME conv whose A operand is
 // `x` [B,T,H,W,x_cs] (channels x_coff .. x_coff+cin) and whose packed weights are wpk [n_pad][nkb*64].
 int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
@@ -193,6 +210,11 @@ void pack_weights_fwd(uint16_t* dst, const float* w, const float* scale, int tap
 // dgrad: roles swapped and taps flipped; K runs over cout_k (>= cout_real), N over cin_pad.
 void pack_weights_dgrad(uint16_t* dst, const float* w, const float* scale, int taps, int cin_real,
                         int cout_real, int cout_k, int n_pad);
+
+// general form: packed tap j takes source tap src[j] of w [taps][cin_real][cout_real]; forward: K = cin, N = cout;
+// dgrad: K = cout, N = cin (no flip here: the tap list encodes it).  kch = K channels padded to a multiple of 16.
+void pack_weights_taps(uint16_t* dst, const float* w, const float* scale, const int* src, int ntaps, int cin_real,
+                       int cout_real, int kch, int n_pad, bool dgrad);
 
 uint16_t f32_to_bf16_bits(float f);
 float bf16_bits_to_f32(uint16_t b);

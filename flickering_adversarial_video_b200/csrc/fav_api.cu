@@ -14,8 +14,11 @@
 #include <memory>
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 
 using namespace fav;
+
+#include "resnet_plan.cuh"
 
 namespace {
 
@@ -96,6 +99,11 @@ struct fav_handle {
   float* dfeat = nullptr;    // [B][1024]
   float* logits = nullptr;   // [B][K] (internal copy)
   float* dlogits = nullptr;  // [B][K]
+
+  // torch stack (video ResNets)
+  ResNet rn;
+  fav_norm_params nrm{};
+  const uint8_t* last_clip_u8 = nullptr;
 };
 
 namespace {
@@ -377,6 +385,8 @@ int bn_fold(const NamedTensors& nt, const std::string& unit, int cout, std::vect
 
 }  // namespace
 
+#include "resnet_impl.cuh"
+
 // =============================================================================================
 // C-ABI
 // =============================================================================================
@@ -398,14 +408,15 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
     set_error("fav_create: device %d is sm_%d%d; libfav is built for sm_100a only", device, prop.major, prop.minor);
     return FAV_ERR_NOGPU;
   }
-  FAV_CHECK_ARG(desc->arch == FAV_NET_I3D, "fav_create: unsupported arch %d", desc->arch);
-  FAV_CHECK_ARG(desc->batch >= 1 && desc->frames >= 9 && desc->num_classes >= 1, "fav_create: bad shape");
+  FAV_CHECK_ARG(desc->arch >= FAV_NET_I3D && desc->arch <= FAV_NET_R2PLUS1D_18, "fav_create: unsupported arch %d", desc->arch);
+  FAV_CHECK_ARG(desc->batch >= 1 && desc->frames >= (desc->arch == FAV_NET_I3D ? 9 : 1) && desc->num_classes >= 1,
+                "fav_create: bad shape");
   FAV_CUDA(cudaSetDevice(device));
   std::unique_ptr<fav_handle> h(new fav_handle());
   h->device = device;
   h->d = *desc;
   h->B = desc->batch; h->T = desc->frames; h->H = desc->height; h->W = desc->width; h->K = desc->num_classes;
-  int st = build_i3d(h.get());
+  int st = desc->arch == FAV_NET_I3D ? build_i3d(h.get()) : build_resnet(h.get());
   if (st != FAV_OK) {
     for (void* p : h->allocs) cudaFree(p);
     return st;
@@ -430,6 +441,11 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
   FAV_CUDA(cudaSetDevice(h->device));
   NamedTensors nt;
   for (int i = 0; i < n; ++i) nt.m[tensors[i].name] = &tensors[i];
+  if (h->d.arch != FAV_NET_I3D) {
+    FAV_TRY(load_weights_resnet(h, nt));
+    h->weights_loaded = true;
+    return FAV_OK;
+  }
   const std::string root = "RGB/inception_i3d/";
   std::vector<float> scale, bias;
   std::vector<uint16_t> pk;
@@ -534,6 +550,22 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
   h->last_adv_flag = adv_flag;
   h->last_delta_clip = delta_clip;
   h->last_delta = delta;
+  h->last_clip_u8 = in_dtype == FAV_U8 ? static_cast<const uint8_t*>(clip) : nullptr;
+  if (h->d.arch != FAV_NET_I3D) {
+    // torch stack: Perturbation.forward (model.py:80-96); adv_f32 is NCTHW like the reference's tensors
+    FAV_CHECK_ARG(in_dtype == FAV_U8 && adv_u8 == nullptr, "torch-stack apply takes a uint8 clip and has no uint8 output");
+    FAV_TRY(launch_apply_torch(static_cast<const uint8_t*>(clip), delta, adv_flag, delta_clip, h->nrm, h->xpad, h->Wp,
+                               h->pw, adv_f32, h->B, h->T, h->H, h->W, s));
+    const int C1 = round_up(h->rn.stem_C, 16);
+    float cst[3], ds[3];
+    for (int c = 0; c < 3; ++c) {
+      cst[c] = (128.0f / 255.0f - h->nrm.mean[c]) / h->nrm.std[c];   // the stem input is u - 128
+      ds[c] = 1.0f / h->nrm.std[c];
+    }
+    FAV_TRY(launch_stem_bias_ex(delta, adv_flag, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T, h->To,
+                                h->pt, h->rn.stem_KT, 1, C1, cst, ds, s));
+    return FAV_OK;
+  }
   FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32,
                        h->sat_list, h->sat_capacity, h->sat_count, h->B, h->T, h->H, h->W, s));
   FAV_TRY(launch_stem_bias(delta, adv_flag, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T,
@@ -565,6 +597,12 @@ extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
     return FAV_ERR_STATE;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->d.arch != FAV_NET_I3D) {
+    FAV_TRY(resnet_forward(h, s));
+    if (logits)
+      FAV_CUDA(cudaMemcpyAsync(logits, h->logits, static_cast<size_t>(h->B) * h->K * 4, cudaMemcpyDeviceToDevice, s));
+    return FAV_OK;
+  }
   FAV_TRY(stem_launch(h->stem_fwd, s));
   FAV_TRY(run_pool_fwd(h, h->pool2a, s));
   FAV_TRY(conv_launch(h->convs[h->conv2b].fwd, s));
@@ -616,6 +654,7 @@ static int run_pool_bwd(fav_handle* h, int pid, cudaStream_t s) {
 extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   FAV_CHECK_ARG(h && grad, "fav_backward_delta: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->d.arch != FAV_NET_I3D) return resnet_backward(h, grad, s);
   const Buf& fb = h->bufs[h->final_buf];
   FAV_TRY(launch_head_bwd(h->dlogits, h->head_w, h->K, fb.p, fb.g, h->dfeat, h->B, fb.T, fb.H * fb.W, fb.C, s));
   FAV_TRY(run_block_bwd(h, h->blocks[8], s));

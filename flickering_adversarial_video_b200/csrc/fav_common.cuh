@@ -48,7 +48,8 @@ extern unsigned long long g_launch_count;
 // ---- TMA descriptor creation (driver entry point fetched at run time: no libcuda link) -------
 // rank-5 bf16 tensor map; dims/strides innermost first; strides in BYTES for dims 1..4.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                   const uint32_t* elem_strides = nullptr);
 
 #ifdef __CUDACC__
 // ---- device helpers --------------------------------------------------------------------------

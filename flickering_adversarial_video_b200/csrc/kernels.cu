@@ -161,33 +161,215 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
 // ---------------------------------------------------------------------------------------------
 // delta-dependent stem bias: conv(x' + delta') = conv(x') + bias[t_o, hclass, wclass, co]
 // ---------------------------------------------------------------------------------------------
+// table[to][cls][co] = bnbias[co] + sum_{kt valid} sum_c (cst[c] + dscale[c] * delta'[t,c]) * wc[kt][cls][c][co],
+// t = st*to + kt - pt.  I3D: cst = 0, dscale = 1.  Torch stack: cst = -mean/std (the stem input is kept in
+// uint8 units), dscale = 1/std (F.normalize(delta, 0, std), model.py:89).
 __global__ void stem_bias_kernel(const float* __restrict__ delta, float adv_flag, float dclip,
                                  const float* __restrict__ wc, const float* __restrict__ bnbias,
-                                 float* __restrict__ table, int T, int To, int pt) {
+                                 float* __restrict__ table, int T, int To, int pt, int KT, int st, int C1,
+                                 float cst0, float cst1, float cst2, float ds0, float ds1, float ds2) {
   const int to = blockIdx.x >> 4;
   const int cls = blockIdx.x & 15;
   const int co = threadIdx.x;
+  if (co >= C1) return;
+  const float cst[3] = {cst0, cst1, cst2}, ds[3] = {ds0, ds1, ds2};
   float acc = bnbias[co];
-  for (int kt = 0; kt < 7; ++kt) {
-    const int t = 2 * to + kt - pt;
+  for (int kt = 0; kt < KT; ++kt) {
+    const int t = st * to + kt - pt;
     if (t < 0 || t >= T) continue;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float d = adv_flag * fminf(fmaxf(delta[t * 3 + c], -dclip), dclip);
-      acc = fmaf(d, wc[((kt * 16 + cls) * 3 + c) * 64 + co], acc);
+      const float d = cst[c] + ds[c] * (adv_flag * fminf(fmaxf(delta[t * 3 + c], -dclip), dclip));
+      acc = fmaf(d, wc[((kt * 16 + cls) * 3 + c) * C1 + co], acc);
     }
   }
-  table[(to * 16 + cls) * 64 + co] = acc;
+  table[(to * 16 + cls) * C1 + co] = acc;
   (void)To;
 }
 
 int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc,
                      const float* bnbias, float* table, int T, int To, int pt, cudaStream_t s) {
-  stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt);
+  stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt, 7, 2, 64,
+                                          0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
 }
+
+int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, const float* wc, const float* bnbias,
+                        float* table, int T, int To, int pt, int KT, int st, int C1, const float* cst3,
+                        const float* dscale3, cudaStream_t s) {
+  FAV_CHECK_ARG(C1 <= 64, "stem bias: at most 64 stem channels");
+  stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt, KT, st, C1,
+                                          cst3[0], cst3[1], cst3[2], dscale3[0], dscale3[1], dscale3[2]);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// torch-stack flicker apply (Perturbation.forward, utils_cv/action_recognition/model.py:80-96):
+//   x = (u8/255 - mean_c)/std_c  (functional_video.py:65-97, dataset.py:28-29)
+//   adv = clamp(x + adv_flag*clamp(delta, +-max_norm)/std_c, min_value, max_value)   (scalar bounds :72-75)
+// The stem input is written in centred uint8 units (u - 128, exact in bf16): x' = u - 128 where the clamp did not
+// fire, else the value that reproduces adv under the folded normalisation; delta and the -mean/std constant reach the
+// network through the fp32 stem bias table.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ delta, float adv_flag, float dclip,
+                   const fav_norm_params nrm, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
+                   float* __restrict__ adv_f32, int T, int H, int W, long long groups) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= groups) return;
+  const int gpr = W >> 4;
+  const int wg = static_cast<int>(gid % gpr);
+  const long long row = gid / gpr;  // (b*T + t)*H + h
+  const int h = static_cast<int>(row % H);
+  const int t = static_cast<int>((row / H) % T);
+  const long long b = row / (static_cast<long long>(H) * T);
+  float d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    d[c] = __fdiv_rn(__fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip)), nrm.std[c]);
+  const long long e0 = (row * W + wg * 16) * 3;
+  uint32_t wds[12];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(clip + e0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4 v = __ldg(src + i);
+      wds[4 * i] = v.x; wds[4 * i + 1] = v.y; wds[4 * i + 2] = v.z; wds[4 * i + 3] = v.w;
+    }
+  }
+  uint32_t xq[32];
+  float a[48];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    float q[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int e = 3 * p + c;
+      const float u = static_cast<float>((wds[e >> 2] >> (8 * (e & 3))) & 0xffu);
+      const float x = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c]);
+      const float sv = __fadd_rn(x, d[c]);
+      const float av = fminf(fmaxf(sv, nrm.lo), nrm.hi);
+      a[e] = av;
+      const bool sat = (sv < nrm.lo) || (sv > nrm.hi);
+      q[c] = (sat ? ((av - d[c]) * nrm.std[c] + nrm.mean[c]) * 255.0f : u) - 128.0f;   // centred uint8 units
+    }
+    xq[2 * p] = pack_bf16x2(q[0], q[1]);
+    xq[2 * p + 1] = pack_bf16x2(q[2], 0.0f);
+  }
+  // torch pads 3 columns on the left: positions are 8 bytes, so the run starts 8-byte (not 16-byte) aligned
+  uint2* dst = reinterpret_cast<uint2*>(xpad + (row * Wp + padl + wg * 16) * 4);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dst[i] = make_uint2(xq[2 * i], xq[2 * i + 1]);
+  if (adv_f32) {   // NCTHW like the torch tensors of the reference
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float* o = adv_f32 + (((b * 3 + c) * T + t) * H + h) * static_cast<long long>(W) + wg * 16;
+#pragma unroll
+      for (int p = 0; p < 16; p += 4)
+        *reinterpret_cast<float4*>(o + p) = make_float4(a[3 * p + c], a[3 * (p + 1) + c], a[3 * (p + 2) + c], a[3 * (p + 3) + c]);
+    }
+  }
+}
+
+int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
+                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32, int B,
+                       int T, int H, int W, cudaStream_t s) {
+  FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
+  const long long groups = static_cast<long long>(B) * T * H * (W / 16);
+  apply_torch_kernel<<<static_cast<int>(ceil_div64(groups, 256)), 256, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm,
+                                                                                xpad, Wp, padl, adv_f32, T, H, W, groups);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// (c) dense reduce: g[t,c] = dscale_c * sum_{b,h,w} mask(b,t,h,w,c) * dX[b,t,h,w,c]
+//   dX is the stem data gradient (bf16, NDHWC with 16-channel pixels, channels 0-2 used); the range-clip
+//   mask (lo <= x + delta' <= hi, inclusive like tf.clip_by_value / torch.clamp) is recomputed from the
+//   uint8 clip.  Warp-shuffle + shared-memory tree per block, then a fixed-order second pass: deterministic.
+//   reference: compute_gradients(loss, var_list=perturbation) single_video_npy.py:82 / loss.backward() model.py:732
+// =============================================================================================
+constexpr int kRedRows = 8;
+__global__ void __launch_bounds__(256)
+stem_dx_reduce_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __restrict__ clip,
+                      const float* __restrict__ delta, float adv_flag, float dclip, const fav_norm_params nrm,
+                      int torch_mode, float* __restrict__ partial, int T, int H, int W, int chunks) {
+  __shared__ float red[8][3];
+  const int chunk = blockIdx.x % chunks;
+  const int t = blockIdx.x / chunks;
+  const int b = blockIdx.y;
+  float d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float dc = __fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip));
+    d[c] = torch_mode ? __fdiv_rn(dc, nrm.std[c]) : dc;
+  }
+  float acc[3] = {0.f, 0.f, 0.f};
+  const int h0 = chunk * kRedRows, h1 = min(H, h0 + kRedRows);
+  const long long base = ((static_cast<long long>(b) * T + t) * H) * W;
+  const int npx = (h1 - h0) * W;
+  for (int i = threadIdx.x; i < npx; i += blockDim.x) {
+    const long long px = base + static_cast<long long>(h0) * W + i;
+    const uint2 g = __ldg(reinterpret_cast<const uint2*>(dx + px * 16));   // channels 0..3
+    const float gv[3] = {bf16_lo(g.x), bf16_hi(g.x), bf16_lo(g.y)};
+    const uint8_t* up = clip + px * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float u = static_cast<float>(__ldg(up + c));
+      const float x = torch_mode ? __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c])
+                                 : __fsub_rn(__fmul_rn(u, 0.0078125f), 1.0f);
+      const float sv = __fadd_rn(x, d[c]);
+      if (sv >= nrm.lo && sv <= nrm.hi) acc[c] += gv[c];
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (lane == 0) red[wid][c] = acc[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+    partial[((static_cast<long long>(b) * T + t) * chunks + chunk) * 3 + threadIdx.x] = sum;
+  }
+}
+
+__global__ void stem_dx_final_kernel(const float* __restrict__ partial, float* __restrict__ grad, int B, int T,
+                                     int chunks, float s0, float s1, float s2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * 3) return;
+  const int t = i / 3, c = i - t * 3;
+  float sum = 0.f;
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < chunks; ++k) sum += partial[((static_cast<long long>(b) * T + t) * chunks + k) * 3 + c];
+  grad[i] = sum * (c == 0 ? s0 : (c == 1 ? s1 : s2));
+}
+
+int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
+                          float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
+                          int B, int T, int H, int W, cudaStream_t s) {
+  const int chunks = ceil_div(H, kRedRows);
+  stem_dx_reduce_kernel<<<dim3(T * chunks, B), 256, 0, s>>>(dx, clip, delta, adv_flag, delta_clip, nrm, torch_mode,
+                                                            partial, T, H, W, chunks);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  const float s0 = torch_mode ? 1.0f / nrm.std[0] : 1.0f, s1 = torch_mode ? 1.0f / nrm.std[1] : 1.0f,
+              s2 = torch_mode ? 1.0f / nrm.std[2] : 1.0f;
+  stem_dx_final_kernel<<<ceil_div(T * 3, 128), 128, 0, s>>>(partial, grad, B, T, chunks, s0, s1, s2);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+int stem_dx_reduce_chunks(int H) { return ceil_div(H, kRedRows); }
 
 // =============================================================================================
 // MaxPool3d, TF SAME semantics (i3d.py:174,189,212,252,398): -inf padding, first arg-max wins.
@@ -383,11 +565,13 @@ int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
 // All linear, so logits = bl + Wl^T * feat with feat[b,c] = sum_t coef[t] sum_hw Y / (HW*2*(T5-1)),
 // coef[t] = number of length-2 windows containing frame t.
 // =============================================================================================
+// T5 < 0 encodes the uniform mean over all -T5 frames (AdaptiveAvgPool3d(1) of the torchvision video ResNets)
 __device__ __forceinline__ float head_coef(int t, int T5) {
-  if (T5 == 1) return 1.0f;
+  if (T5 <= 1) return 1.0f;
   return (t == 0 || t == T5 - 1) ? 1.0f : 2.0f;
 }
 __device__ __forceinline__ float head_scale(int T5, int HW) {
+  if (T5 < 0) return 1.0f / (static_cast<float>(HW) * static_cast<float>(-T5));
   return T5 == 1 ? 1.0f / HW : 1.0f / (static_cast<float>(HW) * 2.0f * (T5 - 1));
 }
 
@@ -400,7 +584,7 @@ head_feat_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ feat, 
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-  const int npos = T5 * HW;
+  const int npos = (T5 < 0 ? -T5 : T5) * HW;
   if (cgp * 8 < C) {
     for (int p = pl; p < npos; p += 8) {
       const float cf = head_coef(p / HW, T5);
@@ -486,7 +670,7 @@ head_gy_kernel(const float* __restrict__ dfeat, const __nv_bfloat16* __restrict_
   const int cg = C >> 3;
   const int c8 = static_cast<int>(gid % cg);
   const long long p = gid / cg;
-  const int npos = T5 * HW;
+  const int npos = (T5 < 0 ? -T5 : T5) * HW;
   const int b = static_cast<int>(p / npos);
   const int t = static_cast<int>((p % npos) / HW);
   const float sc = head_scale(T5, HW) * head_coef(t, T5);
@@ -509,7 +693,7 @@ int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfl
   head_dfeat_kernel<<<grid, 256, 0, s>>>(dlogits, wl, dfeat, C, K);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
-  const long long total = static_cast<long long>(B) * T5 * HW * (C / 8);
+  const long long total = static_cast<long long>(B) * (T5 < 0 ? -T5 : T5) * HW * (C / 8);
   head_gy_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(dfeat, y, gy, T5, HW, C, total);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());

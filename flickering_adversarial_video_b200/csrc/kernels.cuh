@@ -23,6 +23,21 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
 int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc /*[7][16][3][64]*/,
                      const float* bnbias /*[64]*/, float* table, int T, int To, int pt, cudaStream_t s);
 
+int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, const float* wc, const float* bnbias,
+                        float* table, int T, int To, int pt, int KT, int st, int C1, const float* cst3,
+                        const float* dscale3, cudaStream_t s);
+
+// torch-stack apply (uint8 NTHWC clip -> stem input in uint8 units; adv_f32 optional, NCTHW)
+int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
+                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32, int B,
+                       int T, int H, int W, cudaStream_t s);
+
+// (c) dense reduce of the stem data gradient dX [B,T,H,W,16] bf16 into grad [T,3] with the recomputed clip mask
+int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
+                          float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
+                          int B, int T, int H, int W, cudaStream_t s);
+int stem_dx_reduce_chunks(int H);
+
 int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s);
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,

@@ -12,13 +12,21 @@ from . import _lib as L
 
 
 class FlickerEngine:
-    def __init__(self, batch, frames, height=224, width=224, num_classes=400, device=0):
+    def __init__(self, batch, frames, height=None, width=None, num_classes=400, device=0, arch="i3d"):
+        """arch: "i3d" (TF stack, 224x224) or "r3d_18" / "mc3_18" / "r2plus1d_18" (torch stack, 112x112)."""
         if not torch.cuda.is_available():
             raise L.FavError("FlickerEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        if arch not in L.ARCHS:
+            raise ValueError(f"unknown arch {arch!r}; expected one of {sorted(L.ARCHS)}")
         self.lib = L.load()
         self.device = torch.device("cuda", device)
+        self.arch = arch
+        self.torch_stack = arch != "i3d"
+        side = 112 if self.torch_stack else 224
+        height = side if height is None else height
+        width = side if width is None else width
         self.B, self.T, self.H, self.W, self.K = batch, frames, height, width, num_classes
-        desc = L.NetDesc(L.FAV_NET_I3D, batch, frames, height, width, num_classes)
+        desc = L.NetDesc(L.ARCHS[arch], batch, frames, height, width, num_classes)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self.lib.fav_create(C.byref(h), device, C.byref(desc)), "fav_create")
@@ -44,11 +52,16 @@ class FlickerEngine:
         return int(self.lib.fav_device_bytes(self.h))
 
     def load_weights(self, weights):
-        """weights: {tf variable name: float32 ndarray} (reference ckpt naming/layout)."""
+        """weights: {tf variable name: float32 ndarray} (reference ckpt naming/layout) for I3D, or a
+        torchvision `state_dict()` (names and [Cout,Cin,kt,kh,kw] layout as torch stores them) for the
+        video ResNets; integer entries (num_batches_tracked) are ignored."""
+        weights = {k: v for k, v in weights.items() if not k.endswith("num_batches_tracked")}
         n = len(weights)
         arr = (L.Tensor * n)()
         keep = []
         for i, (name, a) in enumerate(weights.items()):
+            if isinstance(a, torch.Tensor):
+                a = a.detach().cpu().numpy()
             a = np.ascontiguousarray(a, dtype=np.float32)
             keep.append(a)
             arr[i].name = name.encode()
@@ -62,6 +75,8 @@ class FlickerEngine:
 
     # ---- hot path ------------------------------------------------------------------------
     def apply(self, clip, delta, adv_flag=1.0, delta_clip=0.4, adv_u8=None, adv_f32=None, stream=None):
+        """clip [B,T,H,W,3] uint8 (or float32 for I3D); delta [T,3].  Torch-stack archs: delta_clip is the
+        Perturbation's dynamic_max_norm and adv_f32, when given, is NCTHW [B,3,T,H,W] (normalised)."""
         assert clip.is_cuda and clip.is_contiguous() and tuple(clip.shape) == (self.B, self.T, self.H, self.W, 3)
         assert delta.is_cuda and delta.dtype == torch.float32 and delta.numel() == self.T * 3
         dt = L.FAV_U8 if clip.dtype == torch.uint8 else L.FAV_F32

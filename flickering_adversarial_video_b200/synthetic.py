@@ -94,3 +94,24 @@ def delta_uniform(frames, seed=7, lo=-0.5, hi=0.5):
     """delta ~ U(lo,hi) [T,3]; the default range exceeds +-0.4 so the inner clip fires."""
     g = torch.Generator().manual_seed(seed)
     return torch.rand((frames, 3), generator=g) * (hi - lo) + lo
+
+
+# ---- torch stack: torchvision video ResNets (utils_cv/action_recognition/model.py:403-441) -------------
+def resnet_model(arch, seed=0, num_classes=400, head_gain=10.0):
+    """Random-init torchvision.models.video.<arch> in eval mode: torchvision's own initialisers under a
+    fixed seed, plus non-trivial BatchNorm statistics (so the fold is exercised) and a head scaled so the
+    softmax is not degenerate.  Its `state_dict()` is what `FlickerEngine.load_weights` ingests."""
+    import torchvision
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        model = getattr(torchvision.models.video, arch)(weights=None, num_classes=num_classes)
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.BatchNorm3d):
+            n = mod.num_features
+            mod.weight.data = 0.8 + 0.4 * torch.rand(n, generator=g)
+            mod.bias.data = 0.1 * torch.randn(n, generator=g)
+            mod.running_mean = 0.1 * torch.randn(n, generator=g)
+            mod.running_var = 0.5 + torch.rand(n, generator=g)
+    model.fc.weight.data *= head_gain
+    return model.eval()

@@ -41,7 +41,9 @@ typedef enum {
   FAV_ERR_MISSING = -5   /* a required named tensor was not supplied */
 } fav_status;
 
-typedef enum { FAV_NET_I3D = 0 } fav_arch;
+/* I3D (i3d.py) and the torchvision video ResNets the torch stack attacks
+ * (utils_cv/action_recognition/model.py:403-441: r3d_18 / mc3_18 / r2plus1d_18). */
+typedef enum { FAV_NET_I3D = 0, FAV_NET_R3D_18 = 1, FAV_NET_MC3_18 = 2, FAV_NET_R2PLUS1D_18 = 3 } fav_arch;
 typedef enum { FAV_U8 = 0, FAV_F32 = 1 } fav_dtype;
 
 /* Which framework's semantics to follow where the two reference stacks differ
@@ -67,6 +69,15 @@ typedef struct {
   int32_t ndim;
   int64_t dims[5];
 } fav_tensor;
+
+/* Input normalisation and range clamp of the torch stack: x = (u8/255 - mean)/std
+ * (references/functional_video.py:65-97, dataset.py:28-29), adv = clamp(x + delta/std, lo, hi)
+ * with the scalar bounds of Perturbation (model.py:72-75). */
+typedef struct {
+  float mean[3];
+  float std[3];
+  float lo, hi;
+} fav_norm_params;
 
 /* Adversarial-loss selection: improve_adversarial_loss (kinetics_i3d_utils.py:253-288) or
  * ce_adversarial_loss (:290-307). */

@@ -1,0 +1,78 @@
+"""-m gpu: torch-stack parity — the engine (C-ABI) on the torchvision video ResNets against the reference's own
+model class (torchvision) + the pinned restatement of Perturbation / Losses / Adam, same seeded inputs.
+Gates (north_star): logits within 1e-2 relative with identical top-1; dL/d-delta cosine (logged; bf16 storage
+limits it the same way as on I3D, see test_gpu_i3d.py); delta after one Adam step."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+T_CLIP = 8
+
+
+def _report(line):
+    print(line)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "resnet_parity.log"), "a") as f:
+            f.write(line + "\n")
+
+
+@pytest.mark.parametrize("arch", ["r3d_18", "mc3_18", "r2plus1d_18"])
+def test_resnet_step_parity(arch):
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200 import _lib as L
+    from flickering_adversarial_video_b200.engine import FlickerEngine
+    from oracle import oracle_resnet
+    B, T, max_norm = 2, T_CLIP, 0.1
+    model = synthetic.resnet_model(arch, seed=0)
+    clip = synthetic.clips_u8(B, T, 112, 112, seed=1003)
+    delta = synthetic.delta_uniform(T, seed=9, lo=-0.12, hi=0.12)     # exceeds max_norm: the delta clamp fires
+    with torch.no_grad():
+        labels = model(oracle_resnet.normalize_u8(clip)).argmax(-1)
+    eps = {}
+    ref = oracle_resnet.attack_step(model, clip, labels, delta, max_norm=max_norm, endpoints=eps)
+
+    eng = FlickerEngine(B, T, arch=arch)
+    eng.load_weights(model.state_dict())
+    d = delta.cuda()
+    adv = torch.zeros((B, 3, T, 112, 112), dtype=torch.float32, device="cuda")
+    eng.apply(clip.cuda(), d, delta_clip=max_norm, adv_f32=adv)
+    logits = eng.forward().cpu()
+    sc = eng.loss(labels.cuda(), improve_loss=True, margin=0.05, stack=L.FAV_STACK_TORCH)
+    g = eng.backward().cpu()
+    torch.cuda.synchronize()
+    # adversarial input: same fp32 op sequence as torch
+    err_adv = float((adv.cpu() - ref["adv"]).abs().max())
+    _report(f"[{arch}] adversarial input max abs err {err_adv:.3e}")
+    assert err_adv <= 1e-5
+    names = {"stem": "stem" if arch == "r2plus1d_18" else "stem.conv"}
+    for name, r in eps.items():
+        got = eng.read(names.get(name, name), tuple(r.shape)).cpu()
+        rel = float((got - r).norm() / (r.norm() + 1e-12))
+        _report(f"[{arch}] layer {name:10s} rel_l2={rel:.4e} ref_rms={float(r.pow(2).mean().sqrt()):.4g}")
+        assert rel < 2e-2, f"{arch} {name}: relative L2 error {rel}"
+    rel = float((logits - ref["logits"]).abs().max() / ref["logits"].abs().max())
+    _report(f"[{arch}] logits max rel err {rel:.4e}; top1 engine {logits.argmax(-1).tolist()} oracle "
+            f"{ref['logits'].argmax(-1).tolist()}; logits std {float(ref['logits'].std()):.3g}")
+    assert rel <= 1e-2
+    assert logits.argmax(-1).tolist() == ref["logits"].argmax(-1).tolist()
+    gr = ref["grad_data"]
+    cos = float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30))
+    _report(f"[{arch}] adv_loss engine {float(sc.cpu()[0]):.6f} oracle {ref['adv_loss']:.6f}; |g| engine {float(g.norm()):.4e} "
+            f"oracle {float(gr.norm()):.4e}; dL/d-delta cosine {cos:.6f}")
+    # the margin loss is quadratic in a difference of probabilities: a 3e-3 logit error moves it by a few percent
+    assert abs(float(sc.cpu()[0]) - ref["adv_loss"]) <= max(2e-3, 5e-2 * abs(ref["adv_loss"]))
+    assert cos >= 0.97
+    # Adam step with the torch rules (regulariser on the clamped delta, clamp mask, eps inside the bias correction)
+    m = torch.zeros_like(d)
+    v = torch.zeros_like(d)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    eng.update(d, eng.grad, m, v, step, 1.0, 0.5, 0.5, 0.5, lr=1e-3, delta_clip=max_norm, stack=L.FAV_STACK_TORCH)
+    torch.cuda.synchronize()
+    dd = float((d.cpu() - ref["delta_new"]).abs().max())
+    _report(f"[{arch}] max |delta - oracle| after one Adam step {dd:.3e}")
+    assert dd <= 2.5e-3
+    eng.close()
