@@ -65,6 +65,10 @@ SIGNATURES = {
     "fav_loss": (_i, [_vp, _vp, C.POINTER(LossParams), _vp, _vp, _vp]),
     "fav_backward_delta": (_i, [_vp, _vp, _vp]),
     "fav_delta_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(RegParams), C.POINTER(AdamParams), _vp, _vp]),
+    "fav_pixels_enable": (_i, [_vp]),
+    "fav_apply_pixels": (_i, [_vp, _vp, _vp, _f, _f, _vp, _vp]),
+    "fav_backward_pixels": (_i, [_vp, _vp, _vp]),
+    "fav_pixels_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, C.POINTER(AdamParams), _vp, _vp]),
     "fav_op_conv3d": (_i, [_i, _vp, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i64, _i64,
                            _i, _i, _i, _i, _i, _i, _vp, _i64, _i64, _vp]),
     "fav_op_maxpool3d": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -184,3 +184,68 @@ class FlickerAttack:
 
     def close(self):
         self.eng.close()
+
+
+class SparseAttack:
+    """Per-pixel attack (FLICKERING_ATTACK = False): the reference's `kinetics_i3d_L12` graph
+    (utils/kinetics_i3d_utils.py:308-521, eps [T,224,224,3] initialised to 1e-8, no +-0.4 clip, loss =
+    adv + beta_1 * loss_L12, i3d_adversarial_main_universal.py:133) and the torch stack with
+    attack_type "L12" (pert_size [3,T,112,112], loss = adv + lambda_ * L12, model.py:169-175,211-214).
+    One `step()` = apply -> forward -> loss -> backward to every pixel -> L1,2 gradient + Adam."""
+
+    def __init__(self, weights, batch, frames, attack_cfg=None, num_classes=400, device=0, lr=1e-3, arch="i3d",
+                 delta_clip=None, init=None):
+        self.eng = FlickerEngine(batch, frames, None, None, num_classes, device, arch=arch)
+        self.eng.load_weights(weights)
+        self.eng.pixels_enable()
+        self.arch = arch
+        self.device = self.eng.device
+        self.B, self.T, self.H, self.W = batch, frames, self.eng.H, self.eng.W
+        torch_stack = self.eng.torch_stack
+        self.stack = L.FAV_STACK_TORCH if torch_stack else L.FAV_STACK_TF
+        cfg = dict(attack_cfg or {})
+        self.improve_loss = bool(cfg.get("IMPROVE_ADV_LOSS", True))
+        self.targeted = bool(cfg.get("TARGETED_ATTACK", False))
+        self.use_logits = bool(cfg.get("USE_LOGITS", False))
+        self.margin = float(cfg.get("PROB_MARGIN", 0.05))
+        # TF: regularizer_loss = beta_1 * L12 (universal.py:133); torch: lambda_ * L12 (model.py:173)
+        self.reg_weight = float(cfg.get("LAMBDA", 1.0)) if torch_stack else float(cfg.get("BETA_1", 0.5))
+        self.delta_clip = (0.2 if torch_stack else 0.0) if delta_clip is None else delta_clip
+        self.lr = lr
+        shape = (frames, self.H, self.W, 3)
+        if init is None:
+            # TF: constant 1e-8 (kinetics_i3d_utils.py:333); torch: U(-1,1)*1e-6 (model.py:71)
+            if torch_stack:
+                self.delta = (torch.rand(shape, device=self.device) * 2 - 1) * 1e-6
+            else:
+                self.delta = torch.full(shape, 1e-8, dtype=torch.float32, device=self.device)
+        else:
+            self.delta = init.to(self.device, torch.float32).contiguous()
+        self.m = torch.zeros_like(self.delta)
+        self.v = torch.zeros_like(self.delta)
+        self.grad = torch.zeros_like(self.delta)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.scalars = self.eng.scalars
+
+    @property
+    def perturbation(self):
+        """[T,H,W,3] (I3D, the reference's eps_rgb) or [3,T,H,W] (torch stack, Perturbation.perturbation)"""
+        return self.delta.permute(3, 0, 1, 2) if self.eng.torch_stack else self.delta
+
+    def step(self, clips_u8, labels, adv_flag=1.0, lr=None):
+        e = self.eng
+        e.apply_pixels(clips_u8, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        e.forward()
+        e.loss(labels, improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
+               margin=self.margin, stack=self.stack)
+        e.backward_pixels(self.grad)
+        e.update_pixels(self.delta, self.grad, self.m, self.v, self.step_count, self.reg_weight,
+                        delta_clip=self.delta_clip, lr=self.lr if lr is None else lr, stack=self.stack)
+        return self.scalars
+
+    def predict(self, clips_u8, adv_flag=1.0):
+        self.eng.apply_pixels(clips_u8, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        return torch.softmax(self.eng.forward(), dim=-1)
+
+    def close(self):
+        self.eng.close()

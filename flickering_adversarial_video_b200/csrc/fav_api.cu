@@ -101,9 +101,16 @@ struct fav_handle {
   float* dlogits = nullptr;  // [B][K]
 
   // torch stack (video ResNets)
-  ResNet rn;
+  ResNet rn;                       // rn.dx / rn.stem_dg also serve the I3D per-pixel attack
   fav_norm_params nrm{};
   const uint8_t* last_clip_u8 = nullptr;
+
+  // sparse per-pixel attack
+  bool pixels_enabled = false;
+  std::vector<float> stem_w_host;  // I3D: folded fp32 stem weights [343][3][64] (dense stem data gradient)
+  const float* last_delta_px = nullptr;
+  float* zero_delta = nullptr;     // [T,3] zeros: the stem bias table without a per-frame delta
+  float* pix_partial = nullptr;
 };
 
 namespace {
@@ -500,6 +507,7 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
     // The delta path (bias table, gradient collapse, saturation corrections) keeps the folded
     // weights in fp32: delta never passes through a bf16 rounding.
     const std::vector<float>& wq = wf;
+    h->stem_w_host = wf;
     FAV_CUDA(cudaMemcpy(h->stem_w_f32, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice));
     // class-summed weights: Wc[kt][hc][wc][c][co] = sum over kh valid for hc, kw valid for wc
     std::vector<float> wcs(static_cast<size_t>(7) * 16 * 3 * 64, 0.0f);
@@ -651,10 +659,23 @@ static int run_pool_bwd(fav_handle* h, int pid, cudaStream_t s) {
   return launch_maxpool_bwd(h->bufs[p.out].g, h->bufs[p.out].idx, nullptr, bi.p, bi.g, p.g, s);
 }
 
+static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s);
+
 extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   FAV_CHECK_ARG(h && grad, "fav_backward_delta: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->d.arch != FAV_NET_I3D) return resnet_backward(h, grad, s);
+  FAV_TRY(i3d_backward_to_stem(h, s));
+  // stem: collapse over B,H,W without materialising dL/dx
+  const Buf& y1 = h->bufs[h->y1];
+  FAV_TRY(launch_stem_class_sums(y1.g, h->stem_S, h->B, h->To, h->Ho, h->Wo, s));
+  FAV_TRY(launch_stem_grad_delta(h->stem_S, h->stem_wc, grad, h->T, h->To, h->pt, s));
+  FAV_TRY(launch_stem_sat_correction(y1.g, h->stem_w_f32, h->sat_list, h->sat_count, h->sat_capacity, grad,
+                                     h->B, h->T, h->H, h->W, h->To, h->Ho, h->Wo, h->pt, h->ph, h->pw, s));
+  return FAV_OK;
+}
+
+static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s) {
   const Buf& fb = h->bufs[h->final_buf];
   FAV_TRY(launch_head_bwd(h->dlogits, h->head_w, h->K, fb.p, fb.g, h->dfeat, h->B, fb.T, fb.H * fb.W, fb.C, s));
   FAV_TRY(run_block_bwd(h, h->blocks[8], s));
@@ -668,13 +689,100 @@ extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   FAV_TRY(run_dgrad(h, h->conv2c, true, false, s));
   FAV_TRY(run_dgrad(h, h->conv2b, false, false, s));
   FAV_TRY(run_pool_bwd(h, h->pool2a, s));
-  // stem: collapse over B,H,W without materialising dL/dx
-  const Buf& y1 = h->bufs[h->y1];
-  FAV_TRY(launch_stem_class_sums(y1.g, h->stem_S, h->B, h->To, h->Ho, h->Wo, s));
-  FAV_TRY(launch_stem_grad_delta(h->stem_S, h->stem_wc, grad, h->T, h->To, h->pt, s));
-  FAV_TRY(launch_stem_sat_correction(y1.g, h->stem_w_f32, h->sat_list, h->sat_count, h->sat_capacity, grad,
-                                     h->B, h->T, h->H, h->W, h->To, h->Ho, h->Wo, h->pt, h->ph, h->pw, s));
   return FAV_OK;
+}
+
+// ---- sparse per-pixel attack (kinetics_i3d_L12, utils/kinetics_i3d_utils.py:308-521; torch attack_type "L12") ----
+extern "C" int fav_pixels_enable(fav_handle* h) {
+  FAV_CHECK_ARG(h, "fav_pixels_enable: null handle");
+  if (h->pixels_enabled) return FAV_OK;
+  if (!h->weights_loaded) {
+    set_error("fav_pixels_enable: weights not loaded");
+    return FAV_ERR_STATE;
+  }
+  FAV_CUDA(cudaSetDevice(h->device));
+  if (h->d.arch == FAV_NET_I3D) {
+    // dense data gradient of Conv3d_1a_7x7 (7^3, stride 2, TF SAME pad_before 2): 8 parity classes
+    ResNet& rn = h->rn;
+    FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(h->B) * h->T * h->H * h->W * 16));
+    const Buf& y1 = h->bufs[h->y1];
+    FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, y1.g, y1.cs, 64, y1.T, y1.H, y1.W, rn.dx, 16, 16, h->T, h->H, h->W, 7, 7, 7,
+                               2, 2, 2, h->pt, h->ph, h->pw));
+    std::vector<uint16_t> pk;
+    for (auto& d : rn.stem_dg) {
+      pk.resize(d.elems);
+      pack_weights_taps(pk.data(), h->stem_w_host.data(), nullptr, d.src.data(), static_cast<int>(d.src.size()), 3, 64, 64,
+                        16, true);
+      FAV_CUDA(cudaMemcpy(d.w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    }
+    h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
+    for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
+  }
+  FAV_TRY(dev_alloc(h, &h->zero_delta, static_cast<size_t>(h->T) * 3));
+  FAV_TRY(dev_alloc(h, &h->pix_partial, static_cast<size_t>(pixels_partial_floats(h->T, h->H, h->W))));
+  h->pixels_enabled = true;
+  return FAV_OK;
+}
+
+extern "C" int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float* delta_px, float adv_flag,
+                                float delta_clip, float* adv_f32, void* stream) {
+  FAV_CHECK_ARG(h && clip_u8 && delta_px, "fav_apply_pixels: null argument");
+  if (!h->pixels_enabled) {
+    set_error("fav_apply_pixels: call fav_pixels_enable first");
+    return FAV_ERR_STATE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int torch_mode = h->d.arch != FAV_NET_I3D;
+  h->last_adv_flag = adv_flag;
+  h->last_delta_clip = delta_clip;
+  h->last_delta_px = delta_px;
+  h->last_delta = nullptr;
+  h->last_clip_u8 = static_cast<const uint8_t*>(clip_u8);
+  FAV_TRY(launch_apply_pixels(h->last_clip_u8, delta_px, adv_flag, delta_clip, h->nrm, torch_mode, h->xpad, h->Wp, h->pw,
+                              adv_f32, h->B, h->T, h->H, h->W, s));
+  if (torch_mode) {
+    const int C1 = round_up(h->rn.stem_C, 16);
+    float cst[3], ds[3];
+    for (int c = 0; c < 3; ++c) {
+      cst[c] = (128.0f / 255.0f - h->nrm.mean[c]) / h->nrm.std[c];
+      ds[c] = 1.0f / h->nrm.std[c];
+    }
+    FAV_TRY(launch_stem_bias_ex(h->zero_delta, 0.0f, 1.0f, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T, h->To, h->pt,
+                                h->rn.stem_KT, 1, C1, cst, ds, s));
+  } else {
+    FAV_TRY(launch_stem_bias(h->zero_delta, 0.0f, 1.0f, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T, h->To, h->pt, s));
+  }
+  return FAV_OK;
+}
+
+extern "C" int fav_backward_pixels(fav_handle* h, float* grad_px, void* stream) {
+  FAV_CHECK_ARG(h && grad_px, "fav_backward_pixels: null argument");
+  if (!h->pixels_enabled || !h->last_delta_px || !h->last_clip_u8) {
+    set_error("fav_backward_pixels: no per-pixel apply preceded this call");
+    return FAV_ERR_STATE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int torch_mode = h->d.arch != FAV_NET_I3D;
+  if (torch_mode) {
+    FAV_TRY(resnet_backward_to_dx(h, s));
+  } else {
+    FAV_TRY(i3d_backward_to_stem(h, s));
+    FAV_TRY(run_dgrad_classes(h->rn.stem_dg, nullptr, nullptr, s));
+  }
+  return launch_stem_dx_pixels(h->rn.dx, h->last_clip_u8, h->last_delta_px, h->last_adv_flag, h->last_delta_clip, h->nrm,
+                               torch_mode, grad_px, h->B, h->T, h->H, h->W, s);
+}
+
+extern "C" int fav_pixels_update(fav_handle* h, float* delta_px, const float* grad_px, float* m, float* v, int64_t* step,
+                                 float reg_weight, float delta_clip, const fav_adam_params* adam, float* scalars,
+                                 void* stream) {
+  FAV_CHECK_ARG(h && delta_px && grad_px && m && v && step && adam && scalars, "fav_pixels_update: null argument");
+  if (!h->pixels_enabled) {
+    set_error("fav_pixels_update: call fav_pixels_enable first");
+    return FAV_ERR_STATE;
+  }
+  return launch_pixels_update(delta_px, grad_px, m, v, step, h->pix_partial, reg_weight, delta_clip, *adam, scalars, h->T,
+                              h->H, h->W, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fav_delta_update(fav_handle* h, float* delta, const float* grad, float* m, float* v,

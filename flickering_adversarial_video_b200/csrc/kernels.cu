@@ -1204,6 +1204,234 @@ int launch_delta_update(float* delta, const float* grad, float* m, float* v, int
   return FAV_OK;
 }
 
+// =============================================================================================
+// sparse per-pixel attack (FLICKERING_ATTACK = False): kinetics_i3d_L12 (utils/kinetics_i3d_utils.py:308-521,
+// delta [T,H,W,3], no +-0.4 clip) and the torch stack with attack_type "L12" (pert_size [3,T,112,112],
+// model.py:383-384).  delta is per pixel, so it is added in fp32 and the sum is what the stem reads.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+apply_pixels_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ dpx, float adv_flag, float dclip,
+                    const fav_norm_params nrm, int torch_mode, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
+                    float* __restrict__ adv_f32, int T, int H, int W, long long groups) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= groups) return;
+  const int gpr = W >> 4;
+  const int wg = static_cast<int>(gid % gpr);
+  const long long row = gid / gpr;  // (b*T + t)*H + h
+  const int h = static_cast<int>(row % H);
+  const int t = static_cast<int>((row / H) % T);
+  const long long b = row / (static_cast<long long>(H) * T);
+  const long long e0 = (row * W + wg * 16) * 3;
+  const float* dp = dpx + ((static_cast<long long>(t) * H + h) * W + wg * 16) * 3;
+  uint2* dst = reinterpret_cast<uint2*>(xpad + (row * Wp + padl + wg * 16) * 4);
+#pragma unroll 4
+  for (int p = 0; p < 16; ++p) {
+    float q[3], a[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float u = static_cast<float>(__ldg(clip + e0 + 3 * p + c));
+      float dv = __ldg(dp + 3 * p + c);
+      if (dclip > 0.0f) dv = fminf(fmaxf(dv, -dclip), dclip);
+      dv = __fmul_rn(adv_flag, dv);
+      float x;
+      if (torch_mode) {
+        x = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c]);
+        dv = __fdiv_rn(dv, nrm.std[c]);
+      } else {
+        x = __fsub_rn(__fmul_rn(u, 0.0078125f), 1.0f);
+      }
+      const float av = fminf(fmaxf(__fadd_rn(x, dv), nrm.lo), nrm.hi);
+      a[c] = av;
+      q[c] = torch_mode ? (av * nrm.std[c] + nrm.mean[c]) * 255.0f - 128.0f : av;
+    }
+    dst[p] = make_uint2(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], 0.0f));
+    if (adv_f32) {
+      if (torch_mode) {   // NCTHW
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          adv_f32[(((b * 3 + c) * T + t) * H + h) * static_cast<long long>(W) + wg * 16 + p] = a[c];
+      } else {            // NTHWC
+#pragma unroll
+        for (int c = 0; c < 3; ++c) adv_f32[e0 + 3 * p + c] = a[c];
+      }
+    }
+  }
+}
+
+int launch_apply_pixels(const uint8_t* clip, const float* delta_px, float adv_flag, float delta_clip,
+                        const fav_norm_params& nrm, int torch_mode, __nv_bfloat16* xpad, int Wp, int padl,
+                        float* adv_f32, int B, int T, int H, int W, cudaStream_t s) {
+  FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
+  const long long groups = static_cast<long long>(B) * T * H * (W / 16);
+  apply_pixels_kernel<<<static_cast<int>(ceil_div64(groups, 256)), 256, 0, s>>>(clip, delta_px, adv_flag, delta_clip, nrm,
+                                                                                 torch_mode, xpad, Wp, padl, adv_f32, T, H,
+                                                                                 W, groups);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// grad[t,h,w,c] = scale_c * sum_b mask(b,t,h,w,c) * dX[b,t,h,w,c]   (one thread per pixel)
+__global__ void __launch_bounds__(256)
+stem_dx_pixels_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __restrict__ clip,
+                      const float* __restrict__ dpx, float adv_flag, float dclip, const fav_norm_params nrm,
+                      int torch_mode, float* __restrict__ grad, int B, long long npix) {
+  const long long px = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (px >= npix) return;
+  float d[3], acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float dv = __ldg(dpx + px * 3 + c);
+    if (dclip > 0.0f) dv = fminf(fmaxf(dv, -dclip), dclip);
+    dv = __fmul_rn(adv_flag, dv);
+    d[c] = torch_mode ? __fdiv_rn(dv, nrm.std[c]) : dv;
+  }
+  for (int b = 0; b < B; ++b) {
+    const long long q = b * npix + px;
+    const uint2 g = __ldg(reinterpret_cast<const uint2*>(dx + q * 16));
+    const float gv[3] = {bf16_lo(g.x), bf16_hi(g.x), bf16_lo(g.y)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float u = static_cast<float>(__ldg(clip + q * 3 + c));
+      const float x = torch_mode ? __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c])
+                                 : __fsub_rn(__fmul_rn(u, 0.0078125f), 1.0f);
+      const float sv = __fadd_rn(x, d[c]);
+      if (sv >= nrm.lo && sv <= nrm.hi) acc[c] += gv[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) grad[px * 3 + c] = acc[c] * (torch_mode ? 1.0f / nrm.std[c] : 1.0f);
+}
+
+int launch_stem_dx_pixels(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta_px, float adv_flag,
+                          float delta_clip, const fav_norm_params& nrm, int torch_mode, float* grad, int B, int T, int H,
+                          int W, cudaStream_t s) {
+  const long long npix = static_cast<long long>(T) * H * W;
+  stem_dx_pixels_kernel<<<static_cast<int>(ceil_div64(npix, 256)), 256, 0, s>>>(dx, clip, delta_px, adv_flag, delta_clip,
+                                                                                 nrm, torch_mode, grad, B, npix);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// L1,2 regulariser + Adam on the per-pixel delta.
+//   L12 = sum_t sqrt(mean_{h,w,c} delta_t^2) + 1e-12  (kinetics_i3d_utils.py:409; Losses.L12_regularization_loss
+//   model.py:211-214, on the clamped delta);  d L12 / d delta = delta / (n * sqrt(mean_t)).
+// pass 1: per-frame partial sums (sum d^2, sum |d|, sum |d - d_prev|); pass 2: fixed-order totals + update.
+constexpr int kPixChunk = 4096;
+__global__ void __launch_bounds__(256)
+pixels_stats_kernel(const float* __restrict__ dpx, float dclip, float* __restrict__ partial, int T, int n_frame,
+                    int chunks) {
+  __shared__ float red[8][3];
+  const int t = blockIdx.y, chunk = blockIdx.x;
+  const int tp = (t + T - 1) % T;
+  float ssq = 0.f, sab = 0.f, sro = 0.f;
+  const int i1 = min(n_frame, (chunk + 1) * kPixChunk);
+  for (int i = chunk * kPixChunk + threadIdx.x; i < i1; i += blockDim.x) {
+    float d = dpx[static_cast<long long>(t) * n_frame + i];
+    float dprev = dpx[static_cast<long long>(tp) * n_frame + i];
+    if (dclip > 0.0f) {
+      d = fminf(fmaxf(d, -dclip), dclip);
+      dprev = fminf(fmaxf(dprev, -dclip), dclip);
+    }
+    ssq += d * d;
+    sab += fabsf(d);
+    sro += fabsf(d - dprev);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+    sab += __shfl_xor_sync(0xffffffffu, sab, o);
+    sro += __shfl_xor_sync(0xffffffffu, sro, o);
+  }
+  if (lane == 0) { red[wid][0] = ssq; red[wid][1] = sab; red[wid][2] = sro; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+    partial[(static_cast<long long>(t) * chunks + chunk) * 3 + threadIdx.x] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pixels_update_kernel(float* __restrict__ dpx, const float* __restrict__ grad, float* __restrict__ m,
+                     float* __restrict__ v, const int64_t* __restrict__ step, const float* __restrict__ partial,
+                     float reg_weight, float dclip, const fav_adam_params adam, float* __restrict__ scalars, int T,
+                     int n_frame, int chunks) {
+  __shared__ float s_mean;
+  const int t = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float ssq = 0.f;
+    for (int k = 0; k < chunks; ++k) ssq += partial[(static_cast<long long>(t) * chunks + k) * 3];
+    s_mean = ssq / static_cast<float>(n_frame);
+  }
+  __syncthreads();
+  const float rms = sqrtf(s_mean);
+  const float gcoef = rms > 0.0f ? reg_weight / (static_cast<float>(n_frame) * rms) : 0.0f;
+  const int64_t tstep = *step + 1;
+  const float b1t = powf(adam.b1, static_cast<float>(tstep)), b2t = powf(adam.b2, static_cast<float>(tstep));
+  const bool torch_stack = adam.stack == FAV_STACK_TORCH;
+  const int i1 = min(n_frame, (chunk + 1) * kPixChunk);
+  for (int i = chunk * kPixChunk + threadIdx.x; i < i1; i += blockDim.x) {
+    const long long e = static_cast<long long>(t) * n_frame + i;
+    const float raw = dpx[e];
+    const bool inside = dclip <= 0.0f || fabsf(raw) <= dclip;
+    const float dc = dclip > 0.0f ? fminf(fmaxf(raw, -dclip), dclip) : raw;
+    const float g = inside ? grad[e] + gcoef * dc : 0.0f;
+    const float mi = adam.b1 * m[e] + (1.0f - adam.b1) * g;
+    const float vi = adam.b2 * v[e] + (1.0f - adam.b2) * g * g;
+    m[e] = mi;
+    v[e] = vi;
+    float upd;
+    if (torch_stack) {
+      upd = (adam.lr / (1.0f - b1t)) * mi / (sqrtf(vi) / sqrtf(1.0f - b2t) + adam.eps);
+    } else {
+      upd = adam.lr * sqrtf(1.0f - b2t) / (1.0f - b1t) * mi / (sqrtf(vi) + adam.eps);
+    }
+    dpx[e] = raw - upd;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    // metrics of the delta this step was computed with (fixed summation order)
+    float l12 = 0.f, sab = 0.f, sro = 0.f;
+    for (int tt = 0; tt < T; ++tt) {
+      float ssq = 0.f;
+      for (int k = 0; k < chunks; ++k) {
+        const float* p = partial + (static_cast<long long>(tt) * chunks + k) * 3;
+        ssq += p[0]; sab += p[1]; sro += p[2];
+      }
+      l12 += sqrtf(ssq / static_cast<float>(n_frame));
+    }
+    const float inv = 1.0f / (static_cast<float>(T) * static_cast<float>(n_frame));
+    scalars[FAV_S_NORM_REG] = l12 + 1e-12f;
+    scalars[FAV_S_DIFF_REG] = 0.0f;
+    scalars[FAV_S_LAP_REG] = 0.0f;
+    scalars[FAV_S_THICKNESS] = sab * inv;
+    scalars[FAV_S_ROUGHNESS] = sro * inv;
+    scalars[FAV_S_TOTAL_LOSS] = scalars[FAV_S_ADV_LOSS] + reg_weight * (l12 + 1e-12f);
+  }
+}
+
+__global__ void step_increment_kernel(int64_t* step) { *step += 1; }
+
+int launch_pixels_update(float* delta_px, const float* grad_px, float* m, float* v, int64_t* step, float* partial,
+                         float reg_weight, float delta_clip, const fav_adam_params& adam, float* scalars, int T, int H,
+                         int W, cudaStream_t s) {
+  const int n_frame = H * W * 3;
+  const int chunks = ceil_div(n_frame, kPixChunk);
+  pixels_stats_kernel<<<dim3(chunks, T), 256, 0, s>>>(delta_px, delta_clip, partial, T, n_frame, chunks);
+  FAV_COUNT_LAUNCH();
+  pixels_update_kernel<<<dim3(chunks, T), 256, 0, s>>>(delta_px, grad_px, m, v, step, partial, reg_weight, delta_clip, adam,
+                                                       scalars, T, n_frame, chunks);
+  FAV_COUNT_LAUNCH();
+  step_increment_kernel<<<1, 1, 0, s>>>(step);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+int pixels_partial_floats(int T, int H, int W) { return T * ceil_div(H * W * 3, kPixChunk) * 3; }
+
 // ---------------------------------------------------------------------------------------------
 // layout helpers for tests / debug reads
 // ---------------------------------------------------------------------------------------------

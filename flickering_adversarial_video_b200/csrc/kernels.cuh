@@ -38,6 +38,18 @@ int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const fl
                           int B, int T, int H, int W, cudaStream_t s);
 int stem_dx_reduce_chunks(int H);
 
+// sparse per-pixel attack: apply with delta [T,H,W,3], per-pixel gradient, L1,2 regulariser + Adam
+int launch_apply_pixels(const uint8_t* clip, const float* delta_px, float adv_flag, float delta_clip,
+                        const fav_norm_params& nrm, int torch_mode, __nv_bfloat16* xpad, int Wp, int padl,
+                        float* adv_f32, int B, int T, int H, int W, cudaStream_t s);
+int launch_stem_dx_pixels(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta_px, float adv_flag,
+                          float delta_clip, const fav_norm_params& nrm, int torch_mode, float* grad, int B, int T, int H,
+                          int W, cudaStream_t s);
+int launch_pixels_update(float* delta_px, const float* grad_px, float* m, float* v, int64_t* step, float* partial,
+                         float reg_weight, float delta_clip, const fav_adam_params& adam, float* scalars, int T, int H,
+                         int W, cudaStream_t s);
+int pixels_partial_floats(int T, int H, int W);
+
 int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s);
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,

@@ -415,7 +415,7 @@ int resnet_forward(fav_handle* h, cudaStream_t s) {
   return FAV_OK;
 }
 
-int resnet_backward(fav_handle* h, float* grad, cudaStream_t s) {
+int resnet_backward_to_dx(fav_handle* h, cudaStream_t s) {
   ResNet& rn = h->rn;
   const Buf& fb = h->bufs[rn.final_buf];
   FAV_TRY(launch_head_bwd(h->dlogits, h->head_w, h->K, fb.p, fb.g, h->dfeat, h->B, -fb.T, fb.H * fb.W, fb.C, s));
@@ -441,10 +441,15 @@ int resnet_backward(fav_handle* h, float* grad, cudaStream_t s) {
     const RConv& c = rn.convs[rn.pre[i]];
     FAV_TRY(run_dgrad_classes(c.dg, &h->bufs[c.in], nullptr, s));
   }
-  FAV_TRY(run_dgrad_classes(rn.stem_dg, nullptr, nullptr, s));
-  FAV_CHECK_ARG(h->last_clip_u8 != nullptr, "fav_backward_delta: apply a uint8 clip first");
-  FAV_TRY(launch_stem_dx_reduce(rn.dx, h->last_clip_u8, h->last_delta, h->last_adv_flag, h->last_delta_clip, h->nrm, 1,
-                                rn.partial, grad, h->B, h->T, h->H, h->W, s));
+  FAV_TRY(run_dgrad_classes(rn.stem_dg, nullptr, nullptr, s));   // dense dL/d(adv) -> rn.dx
+  return FAV_OK;
+}
+
+int resnet_backward(fav_handle* h, float* grad, cudaStream_t s) {
+  FAV_TRY(resnet_backward_to_dx(h, s));
+  FAV_CHECK_ARG(h->last_clip_u8 != nullptr && h->last_delta != nullptr, "fav_backward_delta: apply a uint8 clip first");
+  FAV_TRY(launch_stem_dx_reduce(h->rn.dx, h->last_clip_u8, h->last_delta, h->last_adv_flag, h->last_delta_clip, h->nrm, 1,
+                                h->rn.partial, grad, h->B, h->T, h->H, h->W, s));
   return FAV_OK;
 }
 

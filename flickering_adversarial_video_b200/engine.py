@@ -110,6 +110,32 @@ class FlickerEngine:
                 "fav_delta_update")
         return self.scalars
 
+    # ---- sparse per-pixel attack (kinetics_i3d_L12 / torch attack_type "L12") ------------------
+    def pixels_enable(self):
+        with torch.cuda.device(self.device):
+            L.check(self.lib.fav_pixels_enable(self.h), "fav_pixels_enable")
+
+    def apply_pixels(self, clip_u8, delta_px, adv_flag=1.0, delta_clip=0.0, adv_f32=None, stream=None):
+        """delta_px [T,H,W,3] float32 (the torch stack's [3,T,H,W] permuted); delta_clip <= 0: no clamp."""
+        assert clip_u8.is_cuda and clip_u8.dtype == torch.uint8 and clip_u8.is_contiguous()
+        assert tuple(clip_u8.shape) == (self.B, self.T, self.H, self.W, 3)
+        assert delta_px.is_cuda and delta_px.dtype == torch.float32 and tuple(delta_px.shape) == (self.T, self.H, self.W, 3)
+        L.check(self.lib.fav_apply_pixels(self.h, L.ptr(clip_u8), L.ptr(delta_px), adv_flag, delta_clip, L.ptr(adv_f32),
+                                          L.stream_ptr(stream)), "fav_apply_pixels")
+
+    def backward_pixels(self, grad_px, stream=None):
+        assert grad_px.is_cuda and grad_px.dtype == torch.float32 and tuple(grad_px.shape) == (self.T, self.H, self.W, 3)
+        L.check(self.lib.fav_backward_pixels(self.h, L.ptr(grad_px), L.stream_ptr(stream)), "fav_backward_pixels")
+        return grad_px
+
+    def update_pixels(self, delta_px, grad_px, m, v, step, reg_weight, delta_clip=0.0, lr=1e-3, b1=0.9, b2=0.999,
+                      eps=1e-8, stack=L.FAV_STACK_TF, stream=None):
+        adam = L.AdamParams(lr, b1, b2, eps, stack)
+        L.check(self.lib.fav_pixels_update(self.h, L.ptr(delta_px), L.ptr(grad_px), L.ptr(m), L.ptr(v), L.ptr(step),
+                                           reg_weight, delta_clip, C.byref(adam), L.ptr(self.scalars),
+                                           L.stream_ptr(stream)), "fav_pixels_update")
+        return self.scalars
+
     def read(self, name, shape):
         """Debug read of an internal activation / gradient buffer as fp32 [B,T,H,W,C]."""
         out = torch.empty(shape, dtype=torch.float32, device=self.device)

@@ -166,6 +166,26 @@ int fav_delta_update(fav_handle* h, float* delta, const float* grad, float* m, f
                      int64_t* step, const fav_reg_params* reg, const fav_adam_params* adam,
                      float* scalars, void* stream);
 
+/* ---- sparse per-pixel attack (FLICKERING_ATTACK = False) -------------------------------------
+ * kinetics_i3d_L12 (utils/kinetics_i3d_utils.py:308-521: eps [T,224,224,3], no +-0.4 clip, regulariser
+ * beta_1 * loss_L12, i3d_adversarial_main_universal.py:133) and the torch stack with attack_type "L12"
+ * (pert_size [3,T,112,112], model.py:383-384; Losses.L12_regularization_loss :211-214).
+ * delta_px / grad_px / m / v are DEVICE f32 [T,H,W,3] (the torch stack's [3,T,H,W] permuted by the caller). */
+/* allocate the dense stem data-gradient buffer and plan its kernels (once, after fav_load_weights) */
+int fav_pixels_enable(fav_handle* h);
+/* adv = clamp(x + adv_flag*delta) (TF: [-1,1]; torch: clamp(delta,+-delta_clip)/std and the scalar bounds);
+ * delta_clip <= 0 disables the delta clamp (kinetics_i3d_utils.py:336).  adv_f32 (or NULL): NTHWC (I3D) /
+ * NCTHW (torch stack).  clip_u8 DEVICE [B,T,H,W,3]. */
+int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float* delta_px, float adv_flag, float delta_clip,
+                     float* adv_f32, void* stream);
+/* grad_px[t,h,w,c] = sum_b mask * dL/d(adv) (times 1/std_c on the torch stack): the full backward-to-input,
+ * with the stem data gradient as parity-class tensor-core GEMMs. */
+int fav_backward_pixels(fav_handle* h, float* grad_px, void* stream);
+/* L1,2 regulariser gradient (reg_weight * d/d delta sum_t sqrt(mean delta_t^2)) + clamp mask + Adam on the
+ * per-pixel delta; scalars: FAV_S_NORM_REG <- L12, thickness, roughness, total loss. */
+int fav_pixels_update(fav_handle* h, float* delta_px, const float* grad_px, float* m, float* v, int64_t* step,
+                      float reg_weight, float delta_clip, const fav_adam_params* adam, float* scalars, void* stream);
+
 /* ---- op-level entry points (layer-wise parity tests; same kernels the engine runs) ------- */
 /* stride-1 SAME Conv3d (+bias, +ReLU) on NDHWC bf16 via the tcgen05 implicit-GEMM kernel.
  *   x [B,T,H,W,x_cs] (channels x_coff..x_coff+cin), w HOST f32 [kt,kh,kw,cin,cout] (TF layout),

@@ -310,3 +310,19 @@ def attack_step(model, x, labels, delta, cfg, opt=None, data_grad_only=False):
     if opt is not None:
         out["delta_new"] = opt.step(delta.detach().to(dtype).reshape(-1, 3), g.detach(), cfg.get("lr", 1e-3))
     return out
+
+
+def sparse_attack_step(model, x, labels, delta_thwc, beta1=0.5, margin=0.05, lr=1e-3, opt=None):
+    """kinetics_i3d_L12 (utils/kinetics_i3d_utils.py:308-521): eps [T,H,W,3] without the +-0.4 clip,
+    adv = clip(x + eps, -1, 1), loss = adv_loss + beta_1 * (sum_t sqrt(mean_{h,w,c} eps_t^2) + 1e-12)
+    (i3d_adversarial_main_universal.py:133)."""
+    d = delta_thwc.detach().clone().requires_grad_(True)
+    adv = torch.clamp(x + d.unsqueeze(0), -1.0, 1.0)
+    logits = model.forward(adv)
+    adv_loss, _, _ = improve_adversarial_loss(logits, labels, margin, False, False)
+    l12 = torch.sum(torch.sqrt(torch.mean(d ** 2, dim=[1, 2, 3]))) + 1e-12
+    (g_data,) = torch.autograd.grad(adv_loss, d, retain_graph=True)
+    (g_tot,) = torch.autograd.grad(adv_loss + beta1 * l12, d)
+    opt = opt or TFAdam(tuple(d.shape), lr=lr)
+    return dict(logits=logits.detach(), adv_loss=float(adv_loss.detach()), l12=float(l12.detach()), grad_data=g_data.detach(),
+                grad_total=g_tot.detach(), delta_new=opt.step(delta_thwc.detach(), g_tot.detach(), lr))

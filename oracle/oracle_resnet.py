@@ -54,3 +54,30 @@ def attack_step(model, clips_u8, labels, delta_t3, max_norm=0.1, beta_1=0.5, lam
     delta_new = opt.step(delta_t3, grad_total)
     return dict(adv=adv.detach(), logits=logits.detach(), prob=prob.detach(), loss=float(loss), adv_loss=float(adv_loss),
                 reg_loss=float(reg_loss), grad_data=grad_data, grad_total=grad_total, delta_new=delta_new)
+
+
+def sparse_attack_step(model, clips_u8, labels, delta_thwc, max_norm=0.2, lambda_=1.0, margin=0.05, lr=1e-3, opt=None):
+    """attack_type "L12" (model.py:383-384, 211-214): per-pixel perturbation [3,T,H,W] (here [T,H,W,3]),
+    loss = adv + lambda_ * sum_t sqrt(mean_{c,h,w} clamp(delta)^2)."""
+    x = normalize_u8(clips_u8)
+    pert = delta_thwc.permute(3, 0, 1, 2).clone().requires_grad_(True)      # [3,T,H,W]
+    pc = pert.clamp(-max_norm, max_norm)
+    pc.retain_grad()
+    lo, hi = ots.value_bounds()
+    std = torch.tensor(ots.DEFAULT_STD, dtype=torch.float32).reshape(3, 1, 1, 1)
+    adv = (x + pc / std).clamp(lo, hi)
+    logits = model(adv)
+    prob = torch.softmax(logits, dim=1)
+    adv_loss = ots.improve_adversarial_loss(labels, logits, prob, margin, False)
+    reg = torch.sum(torch.sqrt(torch.mean(pc ** 2, [0, 2, 3]))) + 1e-12
+    loss = adv_loss + lambda_ * reg
+    adv_loss.backward(retain_graph=True)
+    grad_data = pc.grad.detach().permute(1, 2, 3, 0).clone()
+    pert.grad = None
+    pc.grad = None
+    loss.backward()
+    grad_total = pert.grad.detach().permute(1, 2, 3, 0).clone()
+    opt = opt or ots.TorchAdam(tuple(delta_thwc.shape), lr=lr)
+    delta_new = opt.step(delta_thwc, grad_total)
+    return dict(logits=logits.detach(), adv_loss=float(adv_loss.detach()), reg_loss=float(reg.detach()),
+                grad_data=grad_data, grad_total=grad_total, delta_new=delta_new)
