@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's torch attack stack (utils_cv/action_recognition/model.py) on top of
+the libfav engine: same class names, constructor arguments and result layouts, so the drivers
+`r2plus1d_main_universal_attack.py` / `r2plus1d_main_statistics_single_video_attack.py` read the same.
+
+  Perturbation            model.py:58-130   (size [3,T,1,1] flickering / [3,T,H,W] sparse)
+  Losses                  model.py:132-250  (+ .label_prob after a call)
+  Adversarial_metrics     model.py:253-330
+  VideoLearnerAdversarial model.py:337-347 (ctor), fit :460-628 / train_an_epoch :630-788,
+                          fit_many_videos / single-video loop :791-1203
+
+What differs on purpose: the frozen network never computes weight gradients; the clean
+prediction of a clip is computed once, not every step; data arrives as iterables of (uint8 clips
+[B,T,H,W,3], labels) — the decord / DataLoader pipeline is SURVEY §8(f1).  The network, the apply, the loss
+gradient, the backward-to-input and Adam all run in libfav kernels; torch tensors are device memory only.
+"""
+import os
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .attack import FlickerAttack, SparseAttack
+from .engine import op_loss
+
+DEFAULT_MEAN = (0.43216, 0.394666, 0.37645)     # utils_cv/action_recognition/dataset.py:28
+DEFAULT_STD = (0.22803, 0.22145, 0.216989)      # :29
+
+
+class Perturbation:
+    """model.py:58-130.  The tensor lives on the device; `forward([x, adversarial])` takes the uint8 clip batch
+    [B,T,H,W,3] the engine consumes and returns the normalised adversarial input [B,3,T,H,W] the reference's
+    module would hand to the network (the engine fuses it into its stem, so the drivers below never call it)."""
+
+    def __init__(self, size, requires_grad=True, device="cuda", max_value=None, min_value=None, max_norm=1.0,
+                 cyclic_pert=False):
+        self.size = tuple(size)
+        self.device = device
+        self.requires_grad = requires_grad
+        self.perturbation = (torch.rand(self.size, device=device) * 2 - 1) * 0.000001       # model.py:71
+        mean, std = np.array(DEFAULT_MEAN), np.array(DEFAULT_STD)
+        self.max_value = np.min((1 - mean) / std) if max_value is None else max_value        # :72-73
+        self.min_value = np.max((0.0 - mean) / std) if min_value is None else min_value      # :74-75
+        self.max_norm = max_norm
+        self.dynamic_max_norm = max_norm
+        self.cyclic_pert = cyclic_pert
+        self._engine = None
+
+    def bind(self, engine):
+        self._engine = engine
+        return self
+
+    # engine layout <-> reference layout
+    def as_engine(self):
+        """[3,T,1,1] -> [T,3]; [3,T,H,W] -> [T,H,W,3] (contiguous float32)"""
+        p = self.perturbation
+        if p.shape[2] == 1 and p.shape[3] == 1:
+            return p.reshape(3, -1).t().contiguous()
+        return p.permute(1, 2, 3, 0).contiguous()
+
+    def from_engine(self, t):
+        if t.dim() == 2:
+            self.perturbation = t.t().reshape(3, -1, 1, 1).contiguous()
+        else:
+            self.perturbation = t.permute(3, 0, 1, 2).contiguous()
+
+    def forward(self, *input):
+        x, adversarial = input[0]
+        if self._engine is None:
+            raise L.FavError("Perturbation.forward needs an engine: call .bind(engine) (there is no CPU fallback)")
+        e = self._engine
+        adv = torch.empty((e.B, 3, e.T, e.H, e.W), dtype=torch.float32, device=e.device)
+        d = self.as_engine()
+        if d.dim() == 2:
+            e.apply(x, d, adv_flag=1.0 if adversarial else 0.0, delta_clip=self.dynamic_max_norm, adv_f32=adv)
+        else:
+            e.apply_pixels(x, d, adv_flag=1.0 if adversarial else 0.0, delta_clip=self.dynamic_max_norm, adv_f32=adv)
+        return adv
+
+    __call__ = forward
+
+    def clamp_perturbation(self):
+        return self.perturbation.clamp(-1.0 * self.dynamic_max_norm, self.dynamic_max_norm)   # model.py:98-101
+
+    def convert_adversarial_video_zero_one(self, adv_vid):
+        x = adv_vid.detach().cpu().numpy()
+        return (x.transpose([0, 2, 3, 4, 1]) + np.array(DEFAULT_MEAN) / np.array(DEFAULT_STD)) * np.array(DEFAULT_STD)
+
+    def apply_perturbation(self, x):
+        return self.convert_adversarial_video_zero_one(self.forward([x, True]))               # model.py:109-112
+
+    def metric_calc(self):
+        thickness = self.perturbation.abs().mean() * 100.0
+        roughness = (torch.roll(self.perturbation, 1, dims=1) - self.perturbation).abs().mean() * 100.0
+        return thickness, roughness
+
+    def init_perturbation(self, perturbation=(), requires_grad=True, device="cuda"):
+        if len(perturbation) == 0:
+            self.perturbation = (torch.rand(self.size, device=self.device) * 2 - 1) * 0.000001
+        else:
+            self.perturbation = torch.from_numpy(np.asarray(perturbation, dtype=np.float32)).to(self.device)
+
+    def get_perturbation(self):
+        return self.clamp_perturbation(), self.perturbation
+
+
+class Losses:
+    """model.py:132-250.  `__call__(labels, model_logits, model_prob, perturbation)` -> [loss, adv_loss, reg_loss];
+    the adversarial term runs in libfav's loss kernel (torch selection rules), which also yields dloss/dlogits."""
+
+    def __init__(self, beta_1=0.5, lambda_=1.0, targeted=False, target_class=None, margin=0.05, improve_loss=False,
+                 logits=False, attack_type="flickering"):
+        self.beta_1 = beta_1
+        self.lambda_ = lambda_
+        self.targeted = targeted
+        self.target_class = target_class
+        self.margin = margin
+        self.logits = logits
+        self.improve_loss = improve_loss
+        self.attack_type = attack_type
+        self.regularization_loss = (self.flickering_regularization_loss if attack_type == "flickering"
+                                    else self.L12_regularization_loss)
+        self.label_prob = None
+        self.dlogits = None
+
+    def flickering_regularization_loss(self, perturbation):                                   # model.py:198-209
+        norm_reg = torch.mean(perturbation ** 2) + 1e-12
+        right, left = torch.roll(perturbation, 1, dims=1), torch.roll(perturbation, -1, dims=1)
+        diff = torch.mean((perturbation - right) ** 2) + 1e-12
+        lap = torch.mean((-2 * perturbation + right + left) ** 2) + 1e-12
+        return self.beta_1 * norm_reg + (1 - self.beta_1) * (diff + lap)
+
+    def L12_regularization_loss(self, perturbation):                                          # model.py:211-214
+        return torch.sum(torch.sqrt(torch.mean(perturbation ** 2, [0, 2, 3]))) + 1e-12
+
+    def adv_loss(self, labels, model_logits, model_prob=None):
+        lab = labels if not self.targeted else torch.full_like(labels, int(self.target_class))
+        probs, dlogits, scalars = op_loss(model_logits.contiguous(), lab.contiguous(), improve_loss=self.improve_loss,
+                                          targeted=self.targeted, use_logits=self.logits, margin=self.margin,
+                                          stack=L.FAV_STACK_TORCH)
+        self.label_prob = probs.gather(1, lab.view(-1, 1))
+        self.dlogits = dlogits
+        return scalars[L.S_ADV_LOSS]
+
+    def __call__(self, labels, model_logits, model_prob, perturbation):
+        reg_loss = self.regularization_loss(perturbation)
+        adv_loss = self.adv_loss(labels, model_logits, model_prob)
+        return [adv_loss + self.lambda_ * reg_loss, adv_loss, reg_loss]
+
+
+class Adversarial_metrics:
+    """model.py:253-330 (host logic on [B,K] tensors)."""
+
+    def __init__(self, targeted=False, target_class=None):
+        self.targeted = targeted
+        self.target_class = target_class
+
+    def accuracy_for_eval(self, output, ground_truth, topk=(1,), clean_pred=None):
+        with torch.no_grad():
+            batch_size = ground_truth.size(0)
+            maxk = max(topk)
+            _, pred = output.topk(maxk, 1, True, True)
+            pred = pred.t()
+            if self.targeted:
+                correct = pred.eq(self.target_class).view(-1).float().sum(0, keepdim=True)
+                return [correct[0].mul_(100.0 / batch_size)]
+            correct = pred.eq(ground_truth.view(1, -1).expand_as(pred))
+            _, pred_no_adv = clean_pred.topk(maxk, 1, True, True)
+            correct_no_adv = pred_no_adv.t().eq(ground_truth.view(1, -1).expand_as(pred))
+            miss = num = None
+            for k in topk:
+                miss = (torch.logical_not(correct[:k]) * correct_no_adv[:k]).view(-1).float().sum(0, keepdim=True)
+                num = correct_no_adv[:k].view(-1).float().sum()
+            return miss, num
+
+    def adversarial_metric(self, perturbation):
+        thickness = perturbation.abs().mean() * 100.0
+        roughness = (torch.roll(perturbation, 1, dims=1) - perturbation).abs().mean() * 100.0
+        return thickness, roughness
+
+
+class VideoLearnerAdversarial:
+    """model.py:337-347.  `weights` is the torchvision state_dict of `base_model` (the reference downloads the
+    pretrained one, :421; there is no network here)."""
+
+    def __init__(self, dataset=None, num_classes=400, base_model="r2plus1d_18", sample_length=16, cyclic_pert=False,
+                 l_inf_pert_norm=1.0, attack_type="flickering", labaels_id_to_text=None, weights=None, batch_size=8,
+                 device=0):
+        if base_model not in ("r3d_18", "mc3_18", "r2plus1d_18"):
+            raise ValueError(f"base_model {base_model!r}: the engine implements r3d_18 / mc3_18 / r2plus1d_18")
+        if weights is None:
+            raise ValueError("weights (a torchvision state_dict) are required: there is no checkpoint download")
+        self.results = []
+        self.num_classes = num_classes
+        self.attack_type = attack_type
+        self.label_id_to_text = labaels_id_to_text
+        self.dataset = dataset
+        self.sample_length = sample_length
+        self.model_name = base_model
+        self.batch_size = batch_size
+        self._weights, self._device = weights, device
+        pert_size = (3, sample_length, 1, 1) if attack_type == "flickering" else (3, sample_length, 112, 112)
+        self.pert_model = Perturbation(size=pert_size, device=torch.device("cuda", device), max_norm=l_inf_pert_norm,
+                                       cyclic_pert=cyclic_pert)
+        self._atk = None
+
+    def _attack(self, lr, loss_params_dict, batch):
+        cfg = {"LAMBDA": loss_params_dict["lambda_"], "BETA_1": loss_params_dict["beta_1"],
+               "TARGETED_ATTACK": loss_params_dict["targeted_attack"], "IMPROVE_ADV_LOSS": loss_params_dict["improve_loss"],
+               "USE_LOGITS": loss_params_dict["use_logits"], "PROB_MARGIN": 0.05}
+        if self.attack_type == "flickering":
+            atk = FlickerAttack(self._weights, batch, self.sample_length, cfg, num_classes=self.num_classes,
+                                device=self._device, lr=lr, arch=self.model_name,
+                                delta_clip=self.pert_model.dynamic_max_norm)
+            atk.delta.copy_(self.pert_model.as_engine())
+        else:
+            atk = SparseAttack(self._weights, batch, self.sample_length, cfg, num_classes=self.num_classes,
+                               device=self._device, lr=lr, arch=self.model_name,
+                               delta_clip=self.pert_model.dynamic_max_norm, init=self.pert_model.as_engine())
+        self.pert_model.bind(atk.eng)
+        return atk
+
+    def _sync_pert(self, atk):
+        self.pert_model.from_engine(atk.delta)
+
+    # ---- universal attack: fit (model.py:460-628) with train_an_epoch (:630-788) --------------------------
+    def fit(self, lr, epochs, train_batches, valid_batches, model_dir="checkpoints", model_name=None,
+            loss_params_dict=None, save_model=True, start_epoch=0):
+        """train_batches / valid_batches: callables returning an iterable of (uint8 clips [B,T,H,W,3] DEVICE,
+        labels [B] DEVICE) per epoch.  Writes `{model_name}_{epoch:03d}.npy` (pickled list of per-epoch
+        OrderedDicts, model.py:619-623) and returns it."""
+        lp = dict(loss_params_dict)
+        metric = Adversarial_metrics(lp["targeted_attack"], lp.get("target_class_id"))
+        atk = self._attack(lr, lp, self.batch_size)
+        self._atk = atk
+        os.makedirs(model_dir, exist_ok=True)
+        model_name = model_name or self.model_name
+        target = lp.get("target_class_id")
+        for e in range(start_epoch, start_epoch + epochs):
+            result = OrderedDict()
+            for phase, batches in (("train", train_batches), ("valid", valid_batches)):
+                t0 = time.time()
+                miss_rate = total = 0.0
+                loss_sum = n_seen = 0.0
+                for clips, labels in batches():
+                    lab = labels if not lp["targeted_attack"] else torch.full_like(labels, int(target))
+                    clean = atk.predict(clips, adv_flag=0.0).clone()
+                    if phase == "train":
+                        sc = atk.step(clips, lab)
+                        loss = float(sc[L.S_TOTAL_LOSS])
+                        # scores of the delta the step was computed with are still in the engine
+                        adv_logits = atk.eng.logits.clone()
+                    else:
+                        atk.predict(clips, adv_flag=1.0)
+                        sc = atk.eng.loss(lab, improve_loss=lp["improve_loss"], targeted=lp["targeted_attack"],
+                                          use_logits=lp["use_logits"], margin=0.05, stack=L.FAV_STACK_TORCH)
+                        self._sync_pert(atk)
+                        reg = Losses(lp["beta_1"], lp["lambda_"], attack_type=self.attack_type).regularization_loss(
+                            self.pert_model.get_perturbation()[0])
+                        loss = float(sc[L.S_ADV_LOSS]) + lp["lambda_"] * float(reg)
+                        adv_logits = atk.eng.logits.clone()
+                    out = metric.accuracy_for_eval(adv_logits, labels, topk=(1,), clean_pred=clean)
+                    if lp["targeted_attack"]:
+                        miss_rate += float(out[0]) * labels.numel() / 100.0
+                        total += labels.numel()
+                    else:
+                        miss_rate += float(out[0][0])
+                        total += float(out[1])
+                    loss_sum += loss * labels.numel()
+                    n_seen += labels.numel()
+                self._sync_pert(atk)
+                pert = self.pert_model.get_perturbation()[0].detach().cpu().numpy()
+                result[f"{phase}/time"] = time.time() - t0
+                result[f"{phase}/loss"] = loss_sum / max(n_seen, 1.0)
+                result[f"{phase}/fooling_ratio"] = miss_rate / max(total, 1.0)
+                result[f"{phase}/pert_thickness"] = np.abs(pert).mean()
+                result[f"{phase}/pert_roughness"] = np.abs(np.roll(pert, 1, 1) - pert).mean()
+                result[f"{phase}/inf_norm"] = np.abs(pert).max()
+                result[f"{phase}/perturbation"] = pert
+            self.results.append(result)
+            if save_model:
+                np.save(os.path.join(model_dir, "{}_{:03d}.npy".format(model_name, e + 1)),
+                        np.array(self.results, dtype=object), allow_pickle=True)
+        return self.results
+
+    # ---- single-video attack (model.py:918-1203) --------------------------------------------------------------
+    def fit_single_video(self, lr, n_iter, clip_u8, label, video_name="video", class_name=None, model_dir=None,
+                         loss_params_dict=None, max_restarts=4, restart_after=3000):
+        """One clip until `step >= n_iter and adversarial`; every `restart_after` steps without success
+        dynamic_max_norm *= 1.3 (at most `max_restarts` times, model.py:1061-1066).  Returns the result dict the
+        reference saves as `{vid}_@{class}.npy` (:1194-1203), or None when the clean clip is misclassified."""
+        lp = dict(loss_params_dict)
+        atk = self._attack(lr, lp, 1)
+        self._atk = atk
+        clips = clip_u8.reshape(1, *clip_u8.shape[-4:]).contiguous()
+        labels = torch.as_tensor([int(label)], dtype=torch.int64, device=atk.device)
+        clean = atk.predict(clips, adv_flag=0.0).clone()
+        if int(clean.argmax()) != int(label):
+            return None
+        tgt = labels if not lp["targeted_attack"] else torch.full_like(labels, int(lp["target_class_id"]))
+        res = {"loss/total": [], "loss/adv_loss": [], "loss/reg_loss": [], "perturbation/thickness": [],
+               "perturbation/roughness": [], "perturbation/inf_norm": [], "perturbation": [],
+               "prob_clean_input": clean.cpu().numpy(), "label": int(label), "is_adversarial": []}
+        step = new_chance = 0
+        is_adv = False
+        while step < n_iter or not is_adv:
+            if step > restart_after:
+                new_chance += 1
+                self.pert_model.dynamic_max_norm *= 1.3
+                atk.delta_clip = self.pert_model.dynamic_max_norm
+                step = 0
+            if new_chance == max_restarts:
+                break
+            sc = atk.step(clips, tgt).clone()
+            pred = int(atk.eng.logits.argmax())
+            is_adv = (pred == int(lp["target_class_id"])) if lp["targeted_attack"] else (pred != int(label))
+            self._sync_pert(atk)
+            pert = self.pert_model.get_perturbation()[0].detach().cpu().numpy()
+            sc = sc.cpu()
+            res["loss/total"].append(float(sc[L.S_TOTAL_LOSS]))
+            res["loss/adv_loss"].append(float(sc[L.S_ADV_LOSS]))
+            res["loss/reg_loss"].append(float(sc[L.S_TOTAL_LOSS] - sc[L.S_ADV_LOSS]))
+            res["perturbation/thickness"].append(np.abs(pert).mean())
+            res["perturbation/roughness"].append(np.abs(np.roll(pert, 1, 1) - pert).mean())
+            res["perturbation/inf_norm"].append(np.abs(pert).max())
+            res["perturbation"].append(pert)
+            res["is_adversarial"].append(bool(is_adv))
+            step += 1
+        if model_dir is not None:
+            os.makedirs(model_dir, exist_ok=True)
+            np.save(os.path.join(model_dir, "{}_@{}.npy".format(video_name, class_name if class_name else label)), res,
+                    allow_pickle=True)
+        return res
