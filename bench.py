@@ -269,14 +269,46 @@ def run_engine(args):
     h2d = host_clips[0].numel() * host_clips[0].element_size() + host_labels[0].numel() * 8
     d2h = _lib.S_COUNT * 4
 
-    # ---------------- roofline (whole step vs the bf16 tensor-core roofline) ----------------
+    # ---------------- per-kernel-family timing, live, CUDA events on the launch stream ----------------
+    import ctypes
+    prof_steps = 3
+    lib.fav_profile_begin()
+    for i in range(prof_steps):
+        atk.step(clips[i % pool], labels[i % pool])
+    buf = (ctypes.c_double * (4 * len(_lib.PROF_KINDS)))()
+    lib.fav_profile_end(buf, len(buf))
     peaks = load_peaks()
+    kernels = {}
+    for k, name in enumerate(_lib.PROF_KINDS):
+        kms, n, fl, by = buf[4 * k], buf[4 * k + 1], buf[4 * k + 2], buf[4 * k + 3]
+        if n == 0:
+            continue
+        ent = {"ms_per_step": kms / prof_steps, "launches_per_step": n / prof_steps, "avg_launch_us": 1e3 * kms / n}
+        if fl > 0:
+            ent["tflops"] = fl / kms / 1e9
+            ent["frac_of_tensor_peak"] = ent["tflops"] / peaks["tflops"]
+        if by > 0:
+            ent["gbs"] = by / kms / 1e6
+            ent["frac_of_hbm_peak"] = ent["gbs"] / peaks["hbm"]
+        kernels[name] = ent
+
+    # ---------------- roofline: the dominant kernel (conv_halo_kernel) + the whole step ----------------
     flop_per_clip_iter = 4.0 * i3d_forward_macs(T)
-    achieved_tflops = iters_per_sec * B * flop_per_clip_iter / 1e12      # per GPU
-    roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved_tflops / peaks["tflops"], "traffic": None,
-                "note": f"algorithmic FLOPs = 4 x forward conv MACs = {flop_per_clip_iter / 1e9:.2f} GFLOP per clip-iteration "
-                        f"x {B} clips per step, over the whole step time; peak = {peaks['source']}"}
+    step_tflops = iters_per_sec * B * flop_per_clip_iter / 1e12      # per GPU, whole step
+    dom = max((k for k in kernels if "tflops" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peaks["tflops"], "traffic": traffic,
+                "avg_launch_us": kernels[dom]["avg_launch_us"], "launches_per_step": kernels[dom]["launches_per_step"],
+                "share_of_step": kernels[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
+                "step": {"achieved": step_tflops, "frac": step_tflops / peaks["tflops"]},
+                "note": f"kernel: algorithmic FLOPs (2 x MACs, real channels) of its launches / their CUDA-event time, "
+                        f"{prof_steps} un-graphed steps; step: 4 x forward conv MACs = {flop_per_clip_iter / 1e9:.2f} "
+                        f"GFLOP per clip-iteration x {B} clips over the whole step time; peak = {peaks['source']}; "
+                        f"traffic = ncu dram bytes per launch (profiles/r01_traffic.json)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -293,6 +325,7 @@ def run_engine(args):
                 "ms_per_step": ms_e2e / args.steps, "last_total_loss": losses[-1]},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))

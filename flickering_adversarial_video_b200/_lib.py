@@ -20,6 +20,8 @@ ARCHS = {"i3d": FAV_NET_I3D, "r3d_18": FAV_NET_R3D_18, "mc3_18": FAV_NET_MC3_18,
 S_ADV_LOSS, S_FOOLED, S_SUM_P_MIN, S_SUM_P_MAX = 0, 1, 2, 3
 S_NORM_REG, S_DIFF_REG, S_LAP_REG, S_THICKNESS, S_ROUGHNESS, S_TOTAL_LOSS, S_SAT_COUNT = 4, 5, 6, 7, 8, 9, 10
 S_COUNT = 16
+PROF_KINDS = ["apply", "stem_conv", "conv_halo", "conv_tap", "pool_fwd", "pool_bwd", "head_loss", "stem_bwd_reduce",
+              "delta_update", "other"]
 
 
 class FavError(RuntimeError):
@@ -76,6 +78,8 @@ SIGNATURES = {
     "fav_op_loss": (_i, [_i, _vp, _vp, C.POINTER(LossParams), _i, _i, _vp, _vp, _vp, _vp]),
     "fav_op_delta_update": (_i, [_i, _vp, _vp, _vp, _vp, _vp, C.POINTER(RegParams), C.POINTER(AdamParams), _f, _vp, _i, _vp]),
     "fav_debug_read": (_i64, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "fav_profile_begin": (_i, []),
+    "fav_profile_end": (_i, [C.POINTER(C.c_double), _i]),
     "fav_launch_count": (_i64, []),
     "fav_build_info": (C.c_char_p, []),
 }

@@ -292,6 +292,7 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream) {
     FAV_CUDA(cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
+  ProfScope ps(PK_STEM, stream, L.flops);
   conv_stem_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g,
                                                                 L.e);
   FAV_COUNT_LAUNCH();

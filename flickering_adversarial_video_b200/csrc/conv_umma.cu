@@ -698,6 +698,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
                                   220 * 1024));
     attr_set = true;
   }
+  ProfScope ps(L.g.halo ? PK_CONV_HALO : PK_CONV_TAP, stream, L.flops);
   if (L.g.halo) {
     static bool attr2 = false;
     if (!attr2) {

@@ -67,6 +67,7 @@ struct ConvLaunch {
   int a_bytes, b_bytes, stage_bytes;
   size_t smem_bytes;
   int grid;
+  double flops;   // algorithmic FLOPs of this launch (real channels / positions; set by the plan's owner)
 };
 
 
@@ -196,6 +197,7 @@ struct StemLaunch {
   ConvEpilogue e;
   size_t smem_bytes;
   int grid;
+  double flops;
 };
 // x is the padded RGBX buffer [B,T,H,Wp,4]; wpk [KT*KH][bn][32] bf16
 int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,

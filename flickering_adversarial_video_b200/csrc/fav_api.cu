@@ -220,6 +220,7 @@ int plan_conv(fav_handle* h, ConvOp& c) {
     e.out = bo.p; e.out_cs = bo.cs; e.out_coff = c.out_coff; e.cout_store = c.cout_pad;
     e.bias = c.bias; e.bias_ld = c.cout_pad; e.bias_stem = 0; e.relu = c.relu ? 1 : 0;
     e.mask = nullptr; e.addend = nullptr;
+    c.fwd.flops = 2.0 * static_cast<double>(h->B) * bi.T * bi.H * bi.W * taps * c.cin_real * c.cout_real;
   }
   // ---- backward data: A = grad of out slice, N = cin_k ----
   {
@@ -236,6 +237,7 @@ int plan_conv(fav_handle* h, ConvOp& c) {
     e.out = bi.g; e.out_cs = bi.cs; e.out_coff = c.in_coff; e.cout_store = c.cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0;
     e.mask = nullptr; e.addend = nullptr;
+    c.dg.flops = 2.0 * static_cast<double>(h->B) * bi.T * bi.H * bi.W * taps * c.cin_real * c.cout_real;
   }
   return FAV_OK;
 }
@@ -285,6 +287,7 @@ int build_i3d(fav_handle* h) {
     e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = 64;
     e.bias = h->stem_bias_tab; e.bias_ld = 64; e.bias_stem = 1; e.relu = 1;
     e.mask = nullptr; e.addend = nullptr;
+    h->stem_fwd.flops = 2.0 * static_cast<double>(B) * h->To * h->Ho * h->Wo * 343.0 * 3.0 * 64.0;
   }
   // ---- MaxPool3d_2a_3x3 [1,3,3]/[1,2,2] (i3d.py:173-175) ----
   const Buf y1 = h->bufs[h->y1];
@@ -707,7 +710,7 @@ extern "C" int fav_pixels_enable(fav_handle* h) {
     FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(h->B) * h->T * h->H * h->W * 16));
     const Buf& y1 = h->bufs[h->y1];
     FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, y1.g, y1.cs, 64, y1.T, y1.H, y1.W, rn.dx, 16, 16, h->T, h->H, h->W, 7, 7, 7,
-                               2, 2, 2, h->pt, h->ph, h->pw));
+                               2, 2, 2, h->pt, h->ph, h->pw, 3.0, 64.0));
     std::vector<uint16_t> pk;
     for (auto& d : rn.stem_dg) {
       pk.resize(d.elems);

@@ -45,6 +45,21 @@ int sm_count(int device);
 extern unsigned long long g_launch_count;
 #define FAV_COUNT_LAUNCH() (++fav::g_launch_count)
 
+// ---- per-kernel-family timing with CUDA events on the launching stream (fav_profile_begin / _end) ----------
+enum ProfKind {
+  PK_APPLY = 0, PK_STEM, PK_CONV_HALO, PK_CONV_TAP, PK_POOL_FWD, PK_POOL_BWD, PK_HEAD_LOSS, PK_STEM_BWD,
+  PK_DELTA_UPDATE, PK_OTHER, PK_COUNT
+};
+extern bool g_prof_on;
+void prof_record(int kind, cudaStream_t s, bool end, double flops, double bytes);
+struct ProfScope {
+  int kind; cudaStream_t s; double flops, bytes;
+  ProfScope(int k, cudaStream_t st, double fl = 0.0, double by = 0.0) : kind(k), s(st), flops(fl), bytes(by) {
+    if (g_prof_on) prof_record(kind, s, false, 0.0, 0.0);
+  }
+  ~ProfScope() { if (g_prof_on) prof_record(kind, s, true, flops, bytes); }
+};
+
 // ---- TMA descriptor creation (driver entry point fetched at run time: no libcuda link) -------
 // rank-5 bf16 tensor map; dims/strides innermost first; strides in BYTES for dims 1..4.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

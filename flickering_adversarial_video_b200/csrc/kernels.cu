@@ -141,6 +141,7 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
                  __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
                  uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
                  int W, cudaStream_t s) {
+  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 * (in_dtype == FAV_F32 ? 4 : 1) + 8.0 + (adv_u8 ? 3.0 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   FAV_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 28), "apply: too many pixels per call");
   const long long groups = static_cast<long long>(B) * T * H * (W / 16);
@@ -189,6 +190,7 @@ __global__ void stem_bias_kernel(const float* __restrict__ delta, float adv_flag
 
 int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc,
                      const float* bnbias, float* table, int T, int To, int pt, cudaStream_t s) {
+  ProfScope ps(PK_OTHER, s);
   stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt, 7, 2, 64,
                                           0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
   FAV_COUNT_LAUNCH();
@@ -199,6 +201,7 @@ int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const
 int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, const float* wc, const float* bnbias,
                         float* table, int T, int To, int pt, int KT, int st, int C1, const float* cst3,
                         const float* dscale3, cudaStream_t s) {
+  ProfScope ps(PK_OTHER, s);
   FAV_CHECK_ARG(C1 <= 64, "stem bias: at most 64 stem channels");
   stem_bias_kernel<<<To * 16, 64, 0, s>>>(delta, adv_flag, delta_clip, wc, bnbias, table, T, To, pt, KT, st, C1,
                                           cst3[0], cst3[1], cst3[2], dscale3[0], dscale3[1], dscale3[2]);
@@ -278,6 +281,7 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
 int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
                        const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32, int B,
                        int T, int H, int W, cudaStream_t s) {
+  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   const long long groups = static_cast<long long>(B) * T * H * (W / 16);
   apply_torch_kernel<<<static_cast<int>(ceil_div64(groups, 256)), 256, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm,
@@ -357,6 +361,7 @@ __global__ void stem_dx_final_kernel(const float* __restrict__ partial, float* _
 int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
                           float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
                           int B, int T, int H, int W, cudaStream_t s) {
+  ProfScope ps(PK_STEM_BWD, s, 0.0, static_cast<double>(B) * T * H * W * 9.0);
   const int chunks = ceil_div(H, kRedRows);
   stem_dx_reduce_kernel<<<dim3(T * chunks, B), 256, 0, s>>>(dx, clip, delta, adv_flag, delta_clip, nrm, torch_mode,
                                                             partial, T, H, W, chunks);
@@ -453,6 +458,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 
 int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s) {
+  ProfScope ps(PK_POOL_FWD, s, 0.0, static_cast<double>(g.B) * g.C * (2.0 * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
   FAV_CHECK_ARG(g.kt * g.kh * g.kw <= 255, "maxpool: window too large");
   if (idx && pool3s1_applicable(g)) return launch_pool3s1_fwd(x, y, idx, g, s);
@@ -543,6 +549,7 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
                        const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
                        cudaStream_t s) {
+  ProfScope ps(PK_POOL_BWD, s, 0.0, static_cast<double>(g.B) * g.C * ((addend ? 6.0 : 4.0) * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", g.C);
   if (pool3s1_applicable(g)) return launch_pool3s1_bwd(dy, idx, addend, relu_src, dx, g, s);
   if (pool_s2_applicable(g)) return launch_pool_s2_bwd(dy, idx, addend, relu_src, dx, g, s);
@@ -637,6 +644,7 @@ head_logits_kernel(const float* __restrict__ feat, const float* __restrict__ wl,
 
 int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float* feat, const float* wl,
                     const float* bl, int K, float* logits, cudaStream_t s) {
+  ProfScope ps(PK_HEAD_LOSS, s);
   FAV_CHECK_ARG(C % 8 == 0, "head: C must be a multiple of 8");
   dim3 grid(ceil_div(C / 8, 32), B);
   head_feat_kernel<<<grid, 256, 0, s>>>(y, feat, T5, HW, C);
@@ -689,6 +697,7 @@ head_gy_kernel(const float* __restrict__ dfeat, const __nv_bfloat16* __restrict_
 
 int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfloat16* y,
                     __nv_bfloat16* gy, float* dfeat, int B, int T5, int HW, int C, cudaStream_t s) {
+  ProfScope ps(PK_HEAD_LOSS, s);
   dim3 grid(ceil_div(C, 8), B);
   head_dfeat_kernel<<<grid, 256, 0, s>>>(dlogits, wl, dfeat, C, K);
   FAV_COUNT_LAUNCH();
@@ -890,6 +899,7 @@ loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels
 
 int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
                 float* probs, float* dlogits, float* scalars, cudaStream_t s) {
+  ProfScope ps(PK_HEAD_LOSS, s);
   loss_kernel<<<1, 512, 2 * K * sizeof(float), s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
@@ -973,6 +983,7 @@ stem_class_sums_kernel(const __nv_bfloat16* __restrict__ g1, float* __restrict__
 }
 
 int launch_stem_class_sums(const __nv_bfloat16* g1, float* S, int B, int To, int Ho, int Wo, cudaStream_t s) {
+  ProfScope ps(PK_STEM_BWD, s, 0.0, static_cast<double>(B) * To * Ho * Wo * 128.0);
   FAV_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(To) * 16 * 64 * sizeof(float), s));
   dim3 grid(To * ceil_div(Ho, kClassRows), B);
   stem_class_sums_kernel<<<grid, 256, 0, s>>>(g1, S, To, Ho, Wo, 1, 2, 1, 2);
@@ -1004,6 +1015,7 @@ stem_grad_delta_kernel(const float* __restrict__ S, const float* __restrict__ wc
 
 int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, int To, int pt,
                            cudaStream_t s) {
+  ProfScope ps(PK_STEM_BWD, s);
   stem_grad_delta_kernel<<<T * 3, 256, 0, s>>>(S, wc, grad, T, To, pt);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
@@ -1087,6 +1099,7 @@ stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __
 int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const uint32_t* sat_list,
                                const uint32_t* sat_count, uint32_t sat_capacity, float* grad, int B, int T,
                                int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw, cudaStream_t s) {
+  ProfScope ps(PK_STEM_BWD, s);
   (void)B;
   const size_t smem = static_cast<size_t>(343) * 3 * 32 * sizeof(float) + static_cast<size_t>(T) * 3 * sizeof(float);
   static bool attr_set = false;
@@ -1197,6 +1210,7 @@ delta_update_kernel(float* __restrict__ delta, const float* __restrict__ grad, f
 int launch_delta_update(float* delta, const float* grad, float* m, float* v, int64_t* step,
                         const fav_reg_params& reg, const fav_adam_params& adam, float adv_flag,
                         float* scalars, int T, cudaStream_t s) {
+  ProfScope ps(PK_DELTA_UPDATE, s);
   delta_update_kernel<<<1, 256, T * 3 * sizeof(float), s>>>(delta, grad, m, v, step, reg, adam, adv_flag,
                                                             scalars, T);
   FAV_COUNT_LAUNCH();
@@ -1261,6 +1275,7 @@ apply_pixels_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ 
 int launch_apply_pixels(const uint8_t* clip, const float* delta_px, float adv_flag, float delta_clip,
                         const fav_norm_params& nrm, int torch_mode, __nv_bfloat16* xpad, int Wp, int padl,
                         float* adv_f32, int B, int T, int H, int W, cudaStream_t s) {
+  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (adv_f32 ? 12.0 : 0.0)) + static_cast<double>(T) * H * W * 12.0);
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   const long long groups = static_cast<long long>(B) * T * H * (W / 16);
   apply_pixels_kernel<<<static_cast<int>(ceil_div64(groups, 256)), 256, 0, s>>>(clip, delta_px, adv_flag, delta_clip, nrm,
@@ -1306,6 +1321,7 @@ stem_dx_pixels_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __res
 int launch_stem_dx_pixels(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta_px, float adv_flag,
                           float delta_clip, const fav_norm_params& nrm, int torch_mode, float* grad, int B, int T, int H,
                           int W, cudaStream_t s) {
+  ProfScope ps(PK_STEM_BWD, s, 0.0, static_cast<double>(B) * T * H * W * 9.0 + static_cast<double>(T) * H * W * 24.0);
   const long long npix = static_cast<long long>(T) * H * W;
   stem_dx_pixels_kernel<<<static_cast<int>(ceil_div64(npix, 256)), 256, 0, s>>>(dx, clip, delta_px, adv_flag, delta_clip,
                                                                                  nrm, torch_mode, grad, B, npix);
@@ -1418,6 +1434,7 @@ __global__ void step_increment_kernel(int64_t* step) { *step += 1; }
 int launch_pixels_update(float* delta_px, const float* grad_px, float* m, float* v, int64_t* step, float* partial,
                          float reg_weight, float delta_clip, const fav_adam_params& adam, float* scalars, int T, int H,
                          int W, cudaStream_t s) {
+  ProfScope ps(PK_DELTA_UPDATE, s, 0.0, static_cast<double>(T) * H * W * 3.0 * 28.0);
   const int n_frame = H * W * 3;
   const int chunks = ceil_div(n_frame, kPixChunk);
   pixels_stats_kernel<<<dim3(chunks, T), 256, 0, s>>>(delta_px, delta_clip, partial, T, n_frame, chunks);

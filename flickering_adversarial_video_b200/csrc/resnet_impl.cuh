@@ -9,7 +9,8 @@ int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 // ---- data-gradient planning: one stride-1 GEMM per input-parity class ------------------------------------
 int plan_dgrad_classes(fav_handle* h, std::vector<DgradClass>* out, const __nv_bfloat16* gout, long long gout_cs,
                        int kch, int To, int Ho, int Wo, __nv_bfloat16* gin, long long gin_cs, int n_pad, int T, int H,
-                       int W, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw) {
+                       int W, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                       double flops_cin = 0.0, double flops_cout = 0.0) {
   const std::vector<DimClass> ct = dim_classes(kt, st, pt, T), chh = dim_classes(kh, sh, ph, H),
                               cw = dim_classes(kw, sw, pw, W);
   for (const DimClass& a : ct)
@@ -39,6 +40,7 @@ int plan_dgrad_classes(fav_handle* h, std::vector<DgradClass>* out, const __nv_b
         ConvEpilogue& e = d.L.e;
         e.out = gin; e.out_cs = gin_cs; e.out_coff = 0; e.cout_store = n_pad;
         e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr;
+        d.L.flops = 2.0 * static_cast<double>(h->B) * a.Q * b.Q * c.Q * ntaps * flops_cin * flops_cout;
         out->push_back(std::move(d));
       }
   return FAV_OK;
@@ -112,6 +114,7 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
                     c.wname.c_str());
       e.addend = br.p; e.add_cs = br.cs; e.add_coff = 0;
     }
+    c.fwd.flops = 2.0 * static_cast<double>(h->B) * bo.T * bo.H * bo.W * taps * c.cin_real * c.cout_real;
   }
   // ---- backward data ----
   c.halo_dg = halo;
@@ -125,10 +128,11 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
     ConvEpilogue& e = d.L.e;
     e.out = bi.g; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = c.cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr;
+    d.L.flops = 2.0 * static_cast<double>(h->B) * bo.T * bo.H * bo.W * 27.0 * c.cin_real * c.cout_real;
     c.dg.push_back(std::move(d));
   } else {
     FAV_TRY(plan_dgrad_classes(h, &c.dg, bg.g, bg.cs, c.cout_pad, bo.T, bo.H, bo.W, bi.g, bi.cs, c.cin_k, bi.T, bi.H,
-                               bi.W, c.kt, c.kh, c.kw, c.st, c.sh, c.sw, c.pt, c.ph, c.pw));
+                               bi.W, c.kt, c.kh, c.kw, c.st, c.sh, c.sw, c.pt, c.ph, c.pw, c.cin_real, c.cout_real));
   }
   return FAV_OK;
 }
@@ -165,6 +169,7 @@ int build_resnet(fav_handle* h) {
     e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = C1;
     e.bias = h->stem_bias_tab; e.bias_ld = C1; e.bias_stem = 1; e.relu = 1;
     e.mask = nullptr; e.addend = nullptr;
+    h->stem_fwd.flops = 2.0 * static_cast<double>(B) * h->To * h->Ho * h->Wo * rn.stem_KT * 49.0 * 3.0 * rn.stem_C;
   }
   int x = rn.stem_out;
   if (r21) {   // R2Plus1dStem: Conv3d(45, 64, (3,1,1), padding (1,0,0)) + BN + ReLU
@@ -237,7 +242,7 @@ int build_resnet(fav_handle* h) {
   {
     const Buf& bs = h->bufs[rn.stem_out];
     FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, bs.g, bs.cs, C1, bs.T, bs.H, bs.W, rn.dx, 16, 16, T, H, W, rn.stem_KT, 7, 7,
-                               1, 2, 2, rn.stem_pt, 3, 3));
+                               1, 2, 2, rn.stem_pt, 3, 3, 3.0, rn.stem_C));
   }
   FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(B) * T * stem_dx_reduce_chunks(H) * 3));
   // ---- head: AdaptiveAvgPool3d(1) + Linear(512, K) ----

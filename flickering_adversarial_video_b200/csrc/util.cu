@@ -3,11 +3,32 @@
 
 #include <stdarg.h>
 #include <mutex>
+#include <vector>
 
 namespace fav {
 
 static thread_local char t_err[1024] = "";
 unsigned long long g_launch_count = 0;
+
+bool g_prof_on = false;
+namespace {
+struct ProfRec { int kind; cudaEvent_t e0, e1; double flops, bytes; };
+std::vector<ProfRec> g_prof_recs;
+cudaEvent_t g_prof_open = nullptr;
+}  // namespace
+void prof_record(int kind, cudaStream_t s, bool end, double flops, double bytes) {
+  if (!end) {
+    cudaEventCreate(&g_prof_open);
+    cudaEventRecord(g_prof_open, s);
+    return;
+  }
+  ProfRec r;
+  r.kind = kind; r.e0 = g_prof_open; r.flops = flops; r.bytes = bytes;
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e1, s);
+  g_prof_recs.push_back(r);
+  g_prof_open = nullptr;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -80,6 +101,32 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }
 
 }  // namespace fav
+
+extern "C" int fav_profile_begin(void) {
+  fav::g_prof_recs.clear();
+  fav::g_prof_on = true;
+  return 0;
+}
+// out[kind*4 + {0: ms, 1: launches, 2: algorithmic flops, 3: algorithmic bytes}], kinds in fav.h order
+extern "C" int fav_profile_end(double* out, int capacity) {
+  fav::g_prof_on = false;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < capacity; ++i) out[i] = 0.0;
+  for (auto& r : fav::g_prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (r.kind * 4 + 3 < capacity) {
+      out[r.kind * 4 + 0] += ms;
+      out[r.kind * 4 + 1] += 1.0;
+      out[r.kind * 4 + 2] += r.flops;
+      out[r.kind * 4 + 3] += r.bytes;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  fav::g_prof_recs.clear();
+  return 0;
+}
 
 extern "C" const char* fav_last_error(void) { return fav::get_error(); }
 

@@ -222,6 +222,14 @@ int fav_op_delta_update(int device, float* delta, const float* grad, float* m, f
  * ("Conv3d_1a_7x7", "Mixed_3b", ...), prefix "grad:" for the gradient buffer. */
 int64_t fav_debug_read(fav_handle* h, const char* name, float* out, int64_t capacity, void* stream);
 
+/* Per-kernel-family timing with CUDA events on the launching stream (bench.py's live roofline numbers).
+ * Between _begin and _end every launch is bracketed by an event pair; _end synchronises and writes
+ * out[kind*4 + {0: ms, 1: launches, 2: algorithmic FLOPs, 3: algorithmic bytes}] (HOST doubles). */
+enum { FAV_PK_APPLY = 0, FAV_PK_STEM, FAV_PK_CONV_HALO, FAV_PK_CONV_TAP, FAV_PK_POOL_FWD, FAV_PK_POOL_BWD,
+       FAV_PK_HEAD_LOSS, FAV_PK_STEM_BWD, FAV_PK_DELTA_UPDATE, FAV_PK_OTHER, FAV_PK_COUNT };
+int fav_profile_begin(void);
+int fav_profile_end(double* out, int capacity);
+
 /* number of CUDA kernels libfav has launched in this process (bench.py `gpu_launches`) */
 int64_t fav_launch_count(void);
 
