@@ -50,7 +50,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int tile) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB, const ConvGeom g, const ConvEpilogue e,
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
+                 const ConvEpilogue e,
                  const int stages, const int a_bytes, const int b_bytes, const int stage_bytes) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
@@ -70,6 +72,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
+    if (g.nsrc > 1) { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -98,7 +101,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(a_bytes + b_bytes));
-          {
+          if (g.nsrc > 1) {
+            // 1x1x1 with K concatenated from several tensors: k-block -> (source, local block)
+            int src = 0, cb = kb;
+            if (cb >= g.src_blocks[0]) { cb -= g.src_blocks[0]; src = 1; }
+            if (src == 1 && cb >= g.src_blocks[1]) { cb -= g.src_blocks[1]; src = 2; }
+            const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : &tmA2);
+            tma_load_5d(sa, tm, &full_bar[stage], cb * 64, tc.w0, tc.h0, tc.t0, tc.b);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
+          } else {
             const int tap = kb / g.cblocks;
             const int cb = kb - tap * g.cblocks;
             const int dw = tap % g.kw;
@@ -137,7 +148,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
         const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
-        const int ksteps = min(4, (g.cin - cb * 64) >> 4);
+        int ksteps = min(4, (g.cin - cb * 64) >> 4);
+        if (g.nsrc > 1) {
+          int src = 0, lb = kb;
+          if (lb >= g.src_blocks[0]) { lb -= g.src_blocks[0]; src = 1; }
+          if (src == 1 && lb >= g.src_blocks[1]) { lb -= g.src_blocks[1]; src = 2; }
+          const int cs_ = src == 0 ? g.src_cin[0] : (src == 1 ? g.src_cin[1] : g.src_cin[2]);
+          ksteps = min(4, (cs_ - lb * 64) >> 4);
+        }
         if (elect_one()) {
           const uint32_t a_lo = umma_desc_lo(sa);
           const uint32_t b_lo = umma_desc_lo(sb);
@@ -186,7 +204,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * kAccCols);
-      epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, bias_row);
+      if (e.nseg > 1) {
+        // column segments of this N tile go to different tensors (fused same-input 1x1x1 convs)
+        const int n_lo = tc.n0, n_hi = tc.n0 + g.bn;
+#pragma unroll
+        for (int sgi = 0; sgi < 3; ++sgi) {
+          if (sgi >= e.nseg) break;
+          const int a = max(n_lo, e.seg_n0[sgi]), b = min(n_hi, e.seg_n0[sgi + 1]);
+          if (a >= b) continue;   // warp-uniform
+          __nv_bfloat16* srow = e.seg_out[sgi] + pos * e.seg_cs[sgi] + e.seg_coff[sgi];
+          epilogue_columns(e, b - a, a - e.seg_n0[sgi], taddr + static_cast<uint32_t>(a - n_lo), valid, srow, nullptr,
+                           nullptr, bias_row ? bias_row + e.seg_n0[sgi] : nullptr, e.seg_n0[sgi + 1] - e.seg_n0[sgi]);
+        }
+      } else {
+        epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, bias_row);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -728,7 +760,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
     return FAV_OK;
   }
   conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(
-      L.tmA[0], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
+      L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
       L.stage_bytes);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());

@@ -27,6 +27,10 @@ struct ConvGeom {
   int nkb;             // k-blocks per tile
   int bn, n_tiles;     // N tiling (bn % 16 == 0)
   int m_tiles;
+  // K concatenated from up to 3 A tensors (fused 1x1x1 data gradients of an Inception block); nsrc <= 1: plain
+  int nsrc;
+  int src_blocks[3];   // 64-channel k-blocks per source
+  int src_cin[3];      // channels per source (multiple of 16)
   // halo path (3x3x3, stride 1): one A slab per (channel block, dt) holds nrows+2 zero-padded rows of
   // width Wp = W+2; the 9 (dh,dw) taps are 128-row windows of that slab at row offset dw + Wp*dh.
   int halo;            // 1: halo path
@@ -56,6 +60,12 @@ struct ConvEpilogue {
   const __nv_bfloat16* addend;  // added before the mask (may alias out)
   long long add_cs;
   int add_coff;
+  // GEMM column segments routed to different tensors (fused same-input 1x1x1 convs); nseg <= 1: `out` only
+  int nseg;
+  int seg_n0[4];             // first GEMM column of segment i; seg_n0[nseg] = total columns
+  __nv_bfloat16* seg_out[3];
+  long long seg_cs[3];
+  int seg_coff[3];
 };
 
 struct ConvLaunch {
@@ -78,7 +88,9 @@ struct ConvLaunch {
 // memory latencies per group, so the fewer groups the better.
 __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
                                                  __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
-                                                 const __nv_bfloat16* add_row, const float* bias_row) {
+                                                 const __nv_bfloat16* add_row, const float* bias_row,
+                                                 int cout_store = -1) {
+  if (cout_store < 0) cout_store = e.cout_store;
   for (int c0 = 0; c0 < bn; c0 += 64) {
     uint32_t r[4][16];
     uint4 av[4][2], mv[4][2];
@@ -90,7 +102,7 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int n = n0 + c + half * 8;
-        live[q][half] = valid && c < bn && n + 8 <= e.cout_store;
+        live[q][half] = valid && c < bn && n + 8 <= cout_store;
         av[q][half] = make_uint4(0u, 0u, 0u, 0u);
         mv[q][half] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
         if (live[q][half]) {
@@ -108,7 +120,7 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[q][j]);
-      if (bias_row && valid && n < e.cout_store) {
+      if (bias_row && valid && n < cout_store) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n + j));

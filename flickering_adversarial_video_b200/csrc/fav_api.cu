@@ -53,6 +53,15 @@ struct Block {
   int in, out, pool_buf;
   int b0, b1a, b1b, b2a, b2b, b3b;  // conv ids
   int pool;                          // pool id
+  // the three 1x1x1 units that read the block input (Branch_0, Branch_1/0a, Branch_2/0a; i3d.py:196-208) run as ONE
+  // GEMM with concatenated output channels, their data gradients as ONE GEMM with concatenated K
+  bool fused = false;
+  int n_tot = 0;                     // concatenated (16-padded) output channels
+  uint16_t* wf = nullptr;            // [n_tot][cblocks(cin)*64]
+  uint16_t* wd = nullptr;            // [cin_k][(sum of source k-blocks)*64]
+  float* bias = nullptr;             // [n_tot]
+  size_t wf_elems = 0, wd_elems = 0;
+  ConvLaunch fwd, dg;
 };
 
 }  // namespace
@@ -242,6 +251,77 @@ int plan_conv(fav_handle* h, ConvOp& c) {
   return FAV_OK;
 }
 
+int make_flat_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long long cs, int coff, int cin, long long M) {
+  uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(M), 1, 1, 1};
+  uint64_t strides[4] = {static_cast<uint64_t>(cs) * 2, static_cast<uint64_t>(cs) * 2 * M, static_cast<uint64_t>(cs) * 2 * M,
+                         static_cast<uint64_t>(cs) * 2 * M};
+  uint32_t box[5] = {64, 128, 1, 1, 1};
+  return make_tmap_bf16(tm, reinterpret_cast<const char*>(base) + static_cast<long long>(coff) * 2, 5, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int plan_block_fused(fav_handle* h, Block& b) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* ev = getenv("FAV_NO_FUSE");
+    disabled = (ev && atoi(ev)) ? 1 : 0;
+  }
+  if (disabled) return FAV_OK;
+  const ConvOp& c0 = h->convs[b.b0];
+  const ConvOp& c1 = h->convs[b.b1a];
+  const ConvOp& c2 = h->convs[b.b2a];
+  const Buf& bi = h->bufs[b.in];
+  const Buf& bo = h->bufs[b.out];
+  const Buf& t1 = h->bufs[c1.out];
+  const Buf& t2 = h->bufs[c2.out];
+  const long long M = bi.npos(h->B);
+  const int cin_k = c0.cin_k;
+  b.n_tot = c0.cout_pad + c1.cout_pad + c2.cout_pad;
+  // ---- forward: N = [c0 | c1a | c2a] ----
+  b.wf_elems = static_cast<size_t>(b.n_tot) * ceil_div(cin_k, 64) * 64;
+  FAV_TRY(dev_alloc(h, &b.wf, b.wf_elems));
+  FAV_TRY(dev_alloc(h, &b.bias, static_cast<size_t>(b.n_tot)));
+  FAV_TRY(conv_plan_generic(&b.fwd, h->device, bi.p, bi.cs, 0, cin_k, b.wf, b.n_tot, h->B, bi.T, bi.H, bi.W, 1, 1, 1, 1));
+  {
+    ConvEpilogue& e = b.fwd.e;
+    e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = c0.cout_pad;
+    e.bias = b.bias; e.bias_ld = b.n_tot; e.bias_stem = 0; e.relu = 1; e.mask = nullptr; e.addend = nullptr;
+    e.nseg = 3;
+    e.seg_n0[0] = 0; e.seg_n0[1] = c0.cout_pad; e.seg_n0[2] = c0.cout_pad + c1.cout_pad; e.seg_n0[3] = b.n_tot;
+    e.seg_out[0] = bo.p; e.seg_cs[0] = bo.cs; e.seg_coff[0] = c0.out_coff;
+    e.seg_out[1] = t1.p; e.seg_cs[1] = t1.cs; e.seg_coff[1] = 0;
+    e.seg_out[2] = t2.p; e.seg_cs[2] = t2.cs; e.seg_coff[2] = 0;
+    b.fwd.flops = c0.fwd.flops + c1.fwd.flops + c2.fwd.flops;
+  }
+  // ---- backward data: K = [g(out)[:, :c0] | g(t1) | g(t2)], N = cin ----
+  const int nb0 = ceil_div(c0.cout_pad, 64), nb1 = ceil_div(c1.cout_pad, 64), nb2 = ceil_div(c2.cout_pad, 64);
+  b.wd_elems = static_cast<size_t>(cin_k) * (nb0 + nb1 + nb2) * 64;
+  FAV_TRY(dev_alloc(h, &b.wd, b.wd_elems));
+  FAV_TRY(conv_plan_generic(&b.dg, h->device, bo.g, bo.cs, c0.out_coff, c0.cout_pad, b.wd, cin_k, h->B, bi.T, bi.H, bi.W, 1,
+                            1, 1, 1));
+  {
+    ConvGeom& g = b.dg.g;
+    g.nsrc = 3;
+    g.src_blocks[0] = nb0; g.src_blocks[1] = nb1; g.src_blocks[2] = nb2;
+    g.src_cin[0] = c0.cout_pad; g.src_cin[1] = c1.cout_pad; g.src_cin[2] = c2.cout_pad;
+    g.nkb = nb0 + nb1 + nb2;
+    g.cblocks = g.nkb;
+    FAV_TRY(make_flat_tmap(&b.dg.tmA[1], t1.g, t1.cs, 0, c1.cout_pad, M));
+    FAV_TRY(make_flat_tmap(&b.dg.tmA[2], t2.g, t2.cs, 0, c2.cout_pad, M));
+    // the weight map must span the concatenated K
+    uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cin_k)};
+    uint64_t bs[1] = {bd[0] * 2};
+    uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+    FAV_TRY(make_tmap_bf16(&b.dg.tmB, b.wd, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+    ConvEpilogue& e = b.dg.e;
+    e.out = bi.g; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = cin_k;
+    e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr; e.nseg = 0;
+    b.dg.flops = c0.dg.flops + c1.dg.flops + c2.dg.flops;
+  }
+  b.fused = true;
+  return FAV_OK;
+}
+
 // dgrad launch with epilogue options chosen by the caller
 int run_dgrad(fav_handle* h, int conv_id, bool mask_with_input, bool accumulate, cudaStream_t s) {
   ConvOp& c = h->convs[conv_id];
@@ -343,6 +423,7 @@ int build_i3d(fav_handle* h) {
                   bx.T, bx.H, bx.W);
   }
   for (auto& c : h->convs) FAV_TRY(plan_conv(h, c));
+  for (auto& b : h->blocks) FAV_TRY(plan_block_fused(h, b));
   // ---- head (i3d.py:459-472) ----
   const int C5 = h->bufs[h->final_buf].C;
   FAV_TRY(dev_alloc(h, &h->head_w, static_cast<size_t>(C5) * h->K));
@@ -482,6 +563,35 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
     for (int i = 0; i < c.cout_real; ++i) bpad[i] = bias[i];
     FAV_CUDA(cudaMemcpy(c.bias, bpad.data(), bpad.size() * 4, cudaMemcpyHostToDevice));
   }
+  // ---- fused 1x1x1 heads of the Inception blocks ----
+  for (auto& b : h->blocks) {
+    if (!b.fused) continue;
+    const int ids[3] = {b.b0, b.b1a, b.b2a};
+    const int cin_k = h->convs[b.b0].cin_k, cin_real = h->convs[b.b0].cin_real;
+    const int cbl = ceil_div(cin_k, 64);
+    const size_t Kf = static_cast<size_t>(cbl) * 64;
+    std::vector<uint16_t> wf(b.wf_elems, 0), wd(b.wd_elems, 0);
+    std::vector<float> bf(b.n_tot, 0.0f);
+    const size_t Kd = b.wd_elems / cin_k;
+    int n0 = 0, kb0 = 0;
+    for (int i = 0; i < 3; ++i) {
+      const ConvOp& c = h->convs[ids[i]];
+      const fav_tensor* w = nt.find(root + c.name + "/conv_3d/w");
+      FAV_TRY(bn_fold(nt, root + c.name, c.cout_real, &scale, &bias));
+      for (int ci = 0; ci < cin_real; ++ci)
+        for (int co = 0; co < c.cout_real; ++co) {
+          const uint16_t v = f32_to_bf16_bits(w->data[static_cast<size_t>(ci) * c.cout_real + co] * scale[co]);
+          wf[static_cast<size_t>(n0 + co) * Kf + (ci / 64) * 64 + ci % 64] = v;
+          wd[static_cast<size_t>(ci) * Kd + (static_cast<size_t>(kb0) + co / 64) * 64 + co % 64] = v;
+        }
+      for (int co = 0; co < c.cout_real; ++co) bf[n0 + co] = bias[co];
+      n0 += c.cout_pad;
+      kb0 += ceil_div(c.cout_pad, 64);
+    }
+    FAV_CUDA(cudaMemcpy(b.wf, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
+    FAV_CUDA(cudaMemcpy(b.wd, wd.data(), wd.size() * 2, cudaMemcpyHostToDevice));
+    FAV_CUDA(cudaMemcpy(b.bias, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice));
+  }
   // ---- stem ----
   {
     const std::string unit = root + "Conv3d_1a_7x7";
@@ -585,9 +695,13 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
 }
 
 static int run_block_fwd(fav_handle* h, const Block& b, cudaStream_t s) {
-  FAV_TRY(conv_launch(h->convs[b.b0].fwd, s));
-  FAV_TRY(conv_launch(h->convs[b.b1a].fwd, s));
-  FAV_TRY(conv_launch(h->convs[b.b2a].fwd, s));
+  if (b.fused) {
+    FAV_TRY(conv_launch(b.fwd, s));
+  } else {
+    FAV_TRY(conv_launch(h->convs[b.b0].fwd, s));
+    FAV_TRY(conv_launch(h->convs[b.b1a].fwd, s));
+    FAV_TRY(conv_launch(h->convs[b.b2a].fwd, s));
+  }
   const PoolOp& p = h->pools[b.pool];
   FAV_TRY(launch_maxpool_fwd(h->bufs[p.in].p, h->bufs[p.out].p, h->bufs[p.out].idx, p.g, s));
   FAV_TRY(conv_launch(h->convs[b.b1b].fwd, s));
@@ -646,9 +760,13 @@ static int run_block_bwd(fav_handle* h, const Block& b, cudaStream_t s) {
   FAV_TRY(run_dgrad(h, b.b1b, /*mask*/ true, /*acc*/ false, s));   // -> g(b1a), masked by b1a > 0
   FAV_TRY(run_dgrad(h, b.b2b, true, false, s));                    // -> g(b2a)
   FAV_TRY(run_dgrad(h, b.b3b, false, false, s));                   // -> g(pool)
-  FAV_TRY(run_dgrad(h, b.b0, false, false, s));                    // -> g(in)  (first writer)
-  FAV_TRY(run_dgrad(h, b.b1a, false, true, s));                    // +=
-  FAV_TRY(run_dgrad(h, b.b2a, false, true, s));                    // +=
+  if (b.fused) {
+    FAV_TRY(conv_launch(b.dg, s));                                 // -> g(in): the three 1x1x1 data gradients at once
+  } else {
+    FAV_TRY(run_dgrad(h, b.b0, false, false, s));                  // -> g(in)  (first writer)
+    FAV_TRY(run_dgrad(h, b.b1a, false, true, s));                  // +=
+    FAV_TRY(run_dgrad(h, b.b2a, false, true, s));                  // +=
+  }
   const PoolOp& p = h->pools[b.pool];
   const Buf& bi = h->bufs[b.in];
   // g(in) = (g(in) + maxpool^T(g(pool))) * (in > 0)
