@@ -1024,7 +1024,7 @@ int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, 
 
 // one warp per saturated pixel: recompute dX there exactly (gather over the <= 64 valid taps) and
 // subtract it from g[t,c].  The folded stem weights sit in shared memory as fp32 pairs per lane.
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ w,
                            const uint32_t* __restrict__ sat_list, const uint32_t* __restrict__ sat_count,
                            uint32_t sat_capacity, float* __restrict__ grad, int T, int H, int W, int To,
@@ -1054,28 +1054,35 @@ stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __
     const int at = tx + pt, ah = hx + ph, aw = wx + pw;
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
     if (live) {
+      // the <= 4x4 in-plane taps of one temporal tap are gathered with all 16 loads in flight (the kernel is a
+      // chain of L2 latencies otherwise)
       for (int kt = at & 1; kt < 7 && kt <= at; kt += 2) {
         const int to = (at - kt) >> 1;
         if (to >= To) continue;
-        for (int kh = ah & 1; kh < 7 && kh <= ah; kh += 2) {
-          const int ho = (ah - kh) >> 1;
-          if (ho >= Ho) continue;
-          const __nv_bfloat16* grow = g1 + (((static_cast<long long>(b) * To + to) * Ho + ho) * Wo) * 64;
-#pragma unroll 4
-          for (int kw = aw & 1; kw < 7 && kw <= aw; kw += 2) {
-            const int wo = (aw - kw) >> 1;
-            if (wo >= Wo) continue;
-            const uint2 gv = __ldg(reinterpret_cast<const uint2*>(grow + wo * 64) + hl);
-            const float g0 = bf16_lo(gv.x), g1v = bf16_hi(gv.x), g2 = bf16_lo(gv.y), g3 = bf16_hi(gv.y);
-            const __nv_bfloat162* wp = sw + ((kt * 7 + kh) * 7 + kw) * 96 + hl * 2;
-            float2 u, v;
-            u = __bfloat1622float2(wp[0]); v = __bfloat1622float2(wp[1]);
-            a0 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a0))));
-            u = __bfloat1622float2(wp[32]); v = __bfloat1622float2(wp[33]);
-            a1 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a1))));
-            u = __bfloat1622float2(wp[64]); v = __bfloat1622float2(wp[65]);
-            a2 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a2))));
-          }
+        const __nv_bfloat16* gplane = g1 + ((static_cast<long long>(b) * To + to) * Ho) * Wo * 64;
+        uint2 gv[16];
+        bool ok[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int kh = (ah & 1) + 2 * (j >> 2), kw = (aw & 1) + 2 * (j & 3);
+          const int ho = (ah - kh) >> 1, wo = (aw - kw) >> 1;
+          ok[j] = kh < 7 && kh <= ah && ho < Ho && kw < 7 && kw <= aw && wo < Wo;
+          gv[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(gplane + (static_cast<long long>(ho) * Wo + wo) * 64) + hl)
+                        : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (!ok[j]) continue;
+          const int kh = (ah & 1) + 2 * (j >> 2), kw = (aw & 1) + 2 * (j & 3);
+          const float g0 = bf16_lo(gv[j].x), g1v = bf16_hi(gv[j].x), g2 = bf16_lo(gv[j].y), g3 = bf16_hi(gv[j].y);
+          const __nv_bfloat162* wp = sw + ((kt * 7 + kh) * 7 + kw) * 96 + hl * 2;
+          float2 u, v;
+          u = __bfloat1622float2(wp[0]); v = __bfloat1622float2(wp[1]);
+          a0 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a0))));
+          u = __bfloat1622float2(wp[32]); v = __bfloat1622float2(wp[33]);
+          a1 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a1))));
+          u = __bfloat1622float2(wp[64]); v = __bfloat1622float2(wp[65]);
+          a2 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a2))));
         }
       }
     }
@@ -1108,7 +1115,7 @@ int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const ui
     attr_set = true;
   }
   FAV_CHECK_ARG(smem <= 160 * 1024, "sat correction: T=%d too large", T);
-  stem_sat_correction_kernel<<<148, 1024, smem, s>>>(g1, w, sat_list, sat_count, sat_capacity, grad, T, H, W, To,
+  stem_sat_correction_kernel<<<148, 512, smem, s>>>(g1, w, sat_list, sat_count, sat_capacity, grad, T, H, W, To,
                                                      Ho, Wo, pt, ph, pw);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());

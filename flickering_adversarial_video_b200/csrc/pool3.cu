@@ -12,6 +12,8 @@
 // memory except the two frames at the ends of a T segment.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace fav {
 namespace {
 
@@ -31,39 +33,45 @@ __device__ __forceinline__ void first_max(uint32_t (&best)[4], uint32_t (&code)[
   }
 }
 
-// forward.  grid (C/(8*cgn), T segments, B); one thread = one (h, w, 8-channel group) item.
-__global__ void __launch_bounds__(kPoolThreads)
+// forward.  grid (channel blocks x row tiles, T segments, B); one thread = one (row, w, 8-channel group) item.
+// Small planes are owned whole (halo = 0, R = H); large ones are cut into tiles of R rows that also load one halo
+// row above and below (W stage only), so that cgn consecutive lanes cover 16*cgn contiguous bytes per position.
+__global__ void __launch_bounds__(1024)
 pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
-                   const int T, const int H, const int W, const int C, const int cgn, const int tseg) {
+                   const int T, const int H, const int W, const int C, const int cgn, const int tseg, const int R,
+                   const int nth, const int halo) {
   extern __shared__ uint4 smem4[];
-  uint4* X = smem4;                                   // [H][W+2][cgn]
-  uint4* M1 = smem4 + H * (W + 2) * cgn;              // [H+2][W][cgn]
-  const int items = H * W * cgn;
+  const int Rt = R + 2 * halo;
+  uint4* X = smem4;                                   // [Rt][W+2][cgn]
+  uint4* M1 = smem4 + Rt * (W + 2) * cgn;             // [R+2][W][cgn], row index = local row + 1
+  const int tile = blockIdx.x % nth, cblk = blockIdx.x / nth;
+  const int r0 = tile * R;
   const int it = threadIdx.x;
-  const bool live = it < items;
   const int cgi = it % cgn;
   const int pos = it / cgn;
-  const int h = pos / W, w = pos - h * W;
+  const int lr = pos / W, w = pos - lr * W;
+  const int lrow = lr - halo;
+  const int h = r0 + lrow;
+  const bool live = lr < Rt && h >= 0 && h < H;
+  const bool core = live && lrow >= 0 && lrow < R;
   const uint4 ninf = make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
-  // -inf borders (never overwritten afterwards)
-  for (int i = threadIdx.x; i < H * 2 * cgn; i += blockDim.x) {
+  // -inf borders / rows outside the image (never overwritten afterwards)
+  for (int i = threadIdx.x; i < Rt * 2 * cgn; i += blockDim.x) {
     const int hh = i / (2 * cgn), r = i - hh * 2 * cgn;
     X[(hh * (W + 2) + (r < cgn ? 0 : W + 1)) * cgn + (r % cgn)] = ninf;
   }
-  for (int i = threadIdx.x; i < 2 * W * cgn; i += blockDim.x) {
-    const int side = i / (W * cgn), r = i - side * W * cgn;
-    M1[(side ? (H + 1) * W * cgn : 0) + r] = ninf;
-  }
+  for (int i = threadIdx.x; i < (R + 2) * W * cgn; i += blockDim.x) M1[i] = ninf;
+  __syncthreads();
   const int b = blockIdx.z;
   const int t_begin = blockIdx.y * tseg;
   const int t_end = min(t_begin + tseg, T);
   const long long plane = static_cast<long long>(H) * W * C;
-  const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (blockIdx.x * cgn + cgi) * 8 : 0;
+  const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (cblk * cgn + cgi) * 8 : 0;
   const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * plane + eoff;
   __nv_bfloat16* yb = y + static_cast<long long>(b) * T * plane + eoff;
   uint8_t* ib = idx + static_cast<long long>(b) * T * plane + eoff;
-  const int xs = (h * (W + 2) + w + 1) * cgn + cgi;   // own cell in X
-  const int ms = ((h + 1) * W + w) * cgn + cgi;       // own cell in M1
+  const int xs = (lr * (W + 2) + w + 1) * cgn + cgi;       // own cell in X
+  const int ms = ((lrow + 1) * W + w) * cgn + cgi;         // own cell in M1
 
   uint32_t p2[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};   // in-plane max of frame to-1
   uint32_t p1[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};   // in-plane max of frame to
@@ -87,7 +95,7 @@ pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
         M1[ms] = make_uint4(m1[0], m1[1], m1[2], m1[3]);
       }
       __syncthreads();
-      if (live) {
+      if (core) {
         first_max(m2, ch, M1[ms - W * cgn], 0x00000000u);
         first_max(m2, ch, M1[ms], 0x00040004u);
         first_max(m2, ch, M1[ms + W * cgn], 0x00080008u);
@@ -96,7 +104,7 @@ pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
       ccode.y = __byte_perm(cw[2] | ch[2], cw[3] | ch[3], 0x6420);
     }
     const int to = tt - 1;
-    if (live && to >= t_begin && to < t_end) {
+    if (core && to >= t_begin && to < t_end) {
       uint32_t best[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
       uint32_t c3[4] = {0u, 0u, 0u, 0u};
       first_max(best, c3, make_uint4(p2[0], p2[1], p2[2], p2[3]), 0x00000000u);
@@ -138,36 +146,33 @@ __device__ __forceinline__ void acc_f32(float (&acc)[8], const float4 a, const f
   if (m.y & 0x01000000u) acc[7] += b.w;
 }
 
-// backward.  dx = relu_mask(addend + pool^T(dy)); same grid / item mapping as the forward.
+// backward.  dx = relu_mask(addend + pool^T(dy)); same grid / item mapping as the forward (halo rows run the T stage only).
 __global__ void __launch_bounds__(kPoolThreads)
 pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
                    __nv_bfloat16* __restrict__ dx, const int T, const int H, const int W, const int C,
-                   const int cgn, const int tseg) {
+                   const int cgn, const int tseg, const int R, const int nth, const int halo) {
   extern __shared__ uint4 smem4[];
-  const int n2 = (H + 2) * W * cgn, n1 = H * (W + 2) * cgn, nc = (H + 2) * (W + 2) * cgn;
-  float4* G2a = reinterpret_cast<float4*>(smem4);     // [H+2][W][cgn]   channels 0-3
+  const int Rt = R + 2 * halo;
+  const int n2 = (R + 2) * W * cgn, n1 = R * (W + 2) * cgn, nc = (R + 2) * (W + 2) * cgn;
+  float4* G2a = reinterpret_cast<float4*>(smem4);     // [R+2][W][cgn]   channels 0-3, row index = local row + 1
   float4* G2b = G2a + n2;                             //                 channels 4-7
-  float4* G1a = G2b + n2;                             // [H][W+2][cgn]
+  float4* G1a = G2b + n2;                             // [R][W+2][cgn]
   float4* G1b = G1a + n1;
-  uint2* CD = reinterpret_cast<uint2*>(G1b + n1);     // [2][H+2][W+2][cgn]
-  const int items = H * W * cgn;
+  uint2* CD = reinterpret_cast<uint2*>(G1b + n1);     // [2][R+2][W+2][cgn]
+  const int tile = blockIdx.x % nth, cblk = blockIdx.x / nth;
+  const int r0 = tile * R;
   const int it = threadIdx.x;
-  const bool live = it < items;
   const int cgi = it % cgn;
   const int pos = it / cgn;
-  const int h = pos / W, w = pos - h * W;
+  const int lr = pos / W, w = pos - lr * W;
+  const int lrow = lr - halo;
+  const int h = r0 + lrow;
+  const bool live = lr < Rt && h >= 0 && h < H;
+  const bool core = live && lrow >= 0 && lrow < R;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = threadIdx.x; i < 2 * W * cgn; i += blockDim.x) {       // zero border rows of G2
-    const int side = i / (W * cgn), r = i - side * W * cgn;
-    const int o = (side ? (H + 1) * W * cgn : 0) + r;
-    G2a[o] = z4; G2b[o] = z4;
-  }
-  for (int i = threadIdx.x; i < H * 2 * cgn; i += blockDim.x) {       // zero border columns of G1
-    const int hh = i / (2 * cgn), r = i - hh * 2 * cgn;
-    const int o = (hh * (W + 2) + (r < cgn ? 0 : W + 1)) * cgn + (r % cgn);
-    G1a[o] = z4; G1b[o] = z4;
-  }
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) { G2a[i] = z4; G2b[i] = z4; }   // rows outside the image stay 0
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) { G1a[i] = z4; G1b[i] = z4; }   // incl. the border columns
   for (int i = threadIdx.x; i < 2 * nc; i += blockDim.x) CD[i] = make_uint2(0u, 0u);
   __syncthreads();
 
@@ -175,13 +180,13 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   const int t_begin = blockIdx.y * tseg;
   const int t_end = min(t_begin + tseg, T);
   const long long plane = static_cast<long long>(H) * W * C;
-  const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (blockIdx.x * cgn + cgi) * 8 : 0;
+  const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (cblk * cgn + cgi) * 8 : 0;
   const long long boff = static_cast<long long>(b) * T * plane + eoff;
   const __nv_bfloat16* dyb = dy + boff;
   const uint8_t* ib = idx + boff;
-  const int g2s = ((h + 1) * W + w) * cgn + cgi;
-  const int g1s = (h * (W + 2) + w + 1) * cgn + cgi;
-  const int cds = ((h + 1) * (W + 2) + w + 1) * cgn + cgi;
+  const int g2s = ((lrow + 1) * W + w) * cgn + cgi;
+  const int g1s = (lrow * (W + 2) + w + 1) * cgn + cgi;
+  const int cds = ((lrow + 1) * (W + 2) + w + 1) * cgn + cgi;
   const int crow = (W + 2) * cgn;
 
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -196,7 +201,7 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
     const uint4 dN = ld_dy(t + 2);
     const uint2 cN = ld_cd(t + 2);
     uint4 av = z, rv = z;
-    if (live) {
+    if (core) {
       if (addend) av = __ldg(reinterpret_cast<const uint4*>(addend + boff + t * plane));
       if (relu_src) rv = __ldg(reinterpret_cast<const uint4*>(relu_src + boff + t * plane));
     }
@@ -217,7 +222,7 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
     // H stage: the window centred on row h+1-d selected row h iff its a2 == d
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.0f;
-    if (live) {
+    if (core) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         const int o2 = g2s + (1 - d) * W * cgn;
@@ -228,7 +233,7 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
     }
     __syncthreads();
     // W stage: the window centred on column w+1-d selected column w iff its a1 == d
-    if (live) {
+    if (core) {
       if (addend) {
         g[0] = bf16_lo(av.x); g[1] = bf16_hi(av.x); g[2] = bf16_lo(av.y); g[3] = bf16_hi(av.y);
         g[4] = bf16_lo(av.z); g[5] = bf16_hi(av.z); g[6] = bf16_lo(av.w); g[7] = bf16_hi(av.w);
@@ -358,35 +363,51 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   }
 }
 
-// channel groups per CTA: the largest divisor of C/8 whose plane fits one CTA
-int pick_cgn(int H, int W, int C) {
-  const int hw = H * W;
-  if (hw > kPoolThreads || C % 8) return 0;
-  int best = 0;
-  for (int c = 1; c <= 16 && c * hw <= kPoolThreads; ++c)
-    if ((C / 8) % c == 0) best = c;
-  return best;
+// tiling of a plane: whole plane per CTA when it fits with >= 4 channel groups side by side (64 contiguous bytes per
+// position), else row tiles of R rows (+1 halo row each side) with cgn = 4 (or the largest divisor of C/8 below)
+struct PoolTiling { int cgn, R, nth, halo, threads; };
+PoolTiling pick_tiling(int H, int W, int C, int max_threads, int max_tiled = 0) {
+  if (max_tiled <= 0) max_tiled = max_threads;
+  PoolTiling t{0, 0, 0, 0, 0};
+  if (C % 8) return t;
+  const int cg = C / 8, hw = H * W;
+  int full = 0;
+  for (int c = 1; c <= 16 && c * hw <= max_threads; ++c)
+    if (cg % c == 0) full = c;
+  int tc = 0;
+  for (int c = 4; c >= 1; --c)
+    if (cg % c == 0) { tc = c; break; }
+  const int Rtile = tc > 0 ? max_tiled / (W * tc) - 2 : 0;
+  if (full >= 4 || (full > 0 && (Rtile < 2 || tc <= full))) {
+    t.cgn = full; t.R = H; t.nth = 1; t.halo = 0; t.threads = round_up(hw * full, 32);
+  } else if (Rtile >= 2) {
+    t.cgn = tc; t.R = std::min(Rtile, H); t.nth = ceil_div(H, t.R); t.halo = 1;
+    t.threads = round_up((t.R + 2) * W * tc, 32);
+  } else if (full > 0) {
+    t.cgn = full; t.R = H; t.nth = 1; t.halo = 0; t.threads = round_up(hw * full, 32);
+  }
+  return t;
 }
 
 }  // namespace
 
 bool pool3s1_applicable(const PoolGeom& g) {
-  return g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 && pick_cgn(g.H, g.W, g.C) > 0;
+  return g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 &&
+         pick_tiling(g.H, g.W, g.C, kPoolThreads).cgn > 0;
 }
 
 int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
-  const int cgn = pick_cgn(g.H, g.W, g.C);
-  FAV_CHECK_ARG(cgn > 0 && idx, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
-  const int tseg = g.T >= 32 ? 8 : (g.T >= 8 ? 8 : g.T);
-  const size_t smem = (static_cast<size_t>(g.H) * (g.W + 2) + static_cast<size_t>(g.H + 2) * g.W) * cgn * 16;
+  const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads, 1024);
+  FAV_CHECK_ARG(t.cgn > 0 && idx, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
+  const int tseg = g.T >= 8 ? 8 : g.T;
+  const size_t smem = (static_cast<size_t>(t.R + 2 * t.halo) * (g.W + 2) + static_cast<size_t>(t.R + 2) * g.W) * t.cgn * 16;
   static bool attr = false;
   if (!attr) {
     FAV_CUDA(cudaFuncSetAttribute(pool3s1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  const int threads = round_up(g.H * g.W * cgn, 32);
-  dim3 grid(g.C / (8 * cgn), ceil_div(g.T, tseg), g.B);
-  pool3s1_fwd_kernel<<<grid, threads, smem, s>>>(x, y, idx, g.T, g.H, g.W, g.C, cgn, tseg);
+  dim3 grid(g.C / (8 * t.cgn) * t.nth, ceil_div(g.T, tseg), g.B);
+  pool3s1_fwd_kernel<<<grid, t.threads, smem, s>>>(x, y, idx, g.T, g.H, g.W, g.C, t.cgn, tseg, t.R, t.nth, t.halo);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -394,19 +415,19 @@ int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
 
 int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
                        const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
-  const int cgn = pick_cgn(g.H, g.W, g.C);
-  FAV_CHECK_ARG(cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
+  const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads);
+  FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = g.T >= 32 ? 8 : (g.T >= 8 ? 4 : g.T);
-  const size_t smem = (static_cast<size_t>(g.H + 2) * g.W * 2 + static_cast<size_t>(g.H) * (g.W + 2) * 2) * cgn * 16 +
-                      static_cast<size_t>(2) * (g.H + 2) * (g.W + 2) * cgn * 8;
+  const size_t smem = (static_cast<size_t>(t.R + 2) * g.W * 2 + static_cast<size_t>(t.R) * (g.W + 2) * 2) * t.cgn * 16 +
+                      static_cast<size_t>(2) * (t.R + 2) * (g.W + 2) * t.cgn * 8;
   static bool attr = false;
   if (!attr) {
     FAV_CUDA(cudaFuncSetAttribute(pool3s1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  const int threads = round_up(g.H * g.W * cgn, 32);
-  dim3 grid(g.C / (8 * cgn), ceil_div(g.T, tseg), g.B);
-  pool3s1_bwd_kernel<<<grid, threads, smem, s>>>(dy, idx, addend, relu_src, dx, g.T, g.H, g.W, g.C, cgn, tseg);
+  dim3 grid(g.C / (8 * t.cgn) * t.nth, ceil_div(g.T, tseg), g.B);
+  pool3s1_bwd_kernel<<<grid, t.threads, smem, s>>>(dy, idx, addend, relu_src, dx, g.T, g.H, g.W, g.C, t.cgn, tseg, t.R,
+                                                   t.nth, t.halo);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
