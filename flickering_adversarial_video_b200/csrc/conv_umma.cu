@@ -534,6 +534,17 @@ int conv_plan_ex(ConvLaunch* L, int device, const ConvSpec& sp) {
   g.nkb = sp.kt * sp.kh * sp.kw * g.cblocks;
   g.n_tiles = ceil_div(sp.cout_pad, 256);
   g.bn = round_up(ceil_div(sp.cout_pad, g.n_tiles), 16);
+  {
+    // few M tiles (7x7 planes): split N further so that the persistent grid covers the machine; every CTA then
+    // streams 1/n of the weights and the per-SM L2 ingest (the bound of these launches) drops with it
+    const long long m_tiles_est = ceil_div64(static_cast<long long>(sp.B) * sp.T * sp.H * sp.W, 128);
+    const int sms = sm_count(device);
+    while (m_tiles_est * g.n_tiles * 2 <= sms && g.bn > 64) {
+      g.n_tiles += 1;
+      g.bn = round_up(ceil_div(sp.cout_pad, g.n_tiles), 16);
+    }
+    while (g.bn * (g.n_tiles - 1) >= sp.cout_pad) g.n_tiles -= 1;
+  }
   // the last N tile may be partial: weight rows past cout_pad are TMA out-of-bounds zeros and the epilogue
   // stores only channels below cout_store
   g.B = sp.B; g.T = sp.T; g.H = sp.H; g.W = sp.W;
@@ -600,6 +611,14 @@ bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw) {
   const int Wp = W + 2;
   if (Wp > 64) return false;                 // at least two output rows per 128-row tile
   const int nrows = std::min(128 / Wp, H);
+  // tiny planes (7x7): the launch is a chain of TMA / barrier latencies, not throughput: one slab + three 3-tap
+  // weight groups per (channel block, dt) is 3x fewer round trips than 27 per-tap stages (FAV_HALO_SMALL=0 disables)
+  static int small_ok = -1;
+  if (small_ok < 0) {
+    const char* ev = getenv("FAV_HALO_SMALL");
+    small_ok = (ev && !atoi(ev)) ? 0 : 1;
+  }
+  if (small_ok && H * W <= 64) return true;
   // useful rows per tile vs the per-tap path's box efficiency (~0.9): keep halo when >= 60 %
   return nrows * W * 10 >= 128 * 6;
 }
