@@ -108,6 +108,19 @@ def main():
         (2.0 * reg + (dc * gd[i]).sum()).backward()     # data term: gradient gd[i] w.r.t. the clamped delta
         opt.step()
         traj.append(d.detach().clone().numpy())
+    # Adversarial_metrics.accuracy_for_eval (model.py:293-323) and Losses.L12_regularization_loss (:211-214)
+    met = ref.Adversarial_metrics(targeted=False, target_class=None)
+    adv_out = torch.randn((B, K), generator=g)
+    clean_out = torch.randn((B, K), generator=g)
+    gt = torch.randint(0, K, (B,), generator=g)
+    clean_out[torch.arange(4), gt[:4]] = 20.0          # four clips clean-correct
+    adv_out[torch.arange(2), gt[:2]] = 20.0            # two of them survive the attack
+    miss, num = met.accuracy_for_eval(adv_out, gt, topk=(1,), clean_pred=clean_out)
+    out["metrics/adv_out"], out["metrics/clean_out"], out["metrics/gt"] = adv_out.numpy(), clean_out.numpy(), gt.numpy()
+    out["metrics/miss"], out["metrics/num"] = np.float32(miss.item()), np.float32(num.item())
+    psp = (torch.rand((3, 5, 6, 7), generator=g) - 0.5) * 0.3
+    l12 = ref.Losses(attack_type="L12").L12_regularization_loss(psp)
+    out["l12/pert"], out["l12/value"] = psp.numpy(), np.float32(l12.item())
     out["adam/data_grads"] = gd.numpy()
     out["adam/traj"] = np.stack(traj)
     np.savez_compressed(OUT, **out)
