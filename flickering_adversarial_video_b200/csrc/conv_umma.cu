@@ -733,10 +733,38 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   FAV_CHECK_ARG(box[2] <= 256, "conv halo: box too tall");
   FAV_TRY(make_tmap_bf16(&L->tmA[0], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   L->tmA[1] = L->tmA[0]; L->tmA[2] = L->tmA[0]; L->tmA[3] = L->tmA[0];
+  // CTA pairs (tcgen05 cta_group::2, conv_halo2.cu): each CTA loads bn/2 rows of every weight tile
+  {
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+      const char* ev = getenv("FAV_HALO_2CTA");
+      pair_mode = ev ? atoi(ev) : 1;
+    }
+    // Pairs pay off where the tile is shared-memory bound and the weight tiles are small enough for deep rings
+    // (measured with FAV_HALO_PROF: Conv3d_2c data gradient, N = 64: 1136 -> 717 kclk; N = 192 tiles are bound by the
+    // weight supply either way).  FAV_HALO_2CTA=0 disables, =2 forces pairs on small problems too (tests).
+    g.pair = (pair_mode && g.bn % 16 == 0 &&
+              (pair_mode == 2 ? g.m_tiles >= 2 : (g.bn <= 128 && g.m_tiles >= 2 * sm_count(device)))) ? 1 : 0;
+    if (getenv("FAV_DEBUG_PLAN")) fprintf(stderr, "[fav]   -> %s\n", g.pair ? "CTA pairs (cta_group::2)" : "single CTA");
+  }
   uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cout_pad)};
   uint64_t bs[1] = {bd[0] * 2};
-  uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+  uint32_t bb[2] = {64, static_cast<uint32_t>(g.pair ? g.bn / 2 : g.bn)};
   FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (g.pair) {
+    // half-size weight tiles: re-derive the ring depths (deeper rings hide the longer cross-CTA signalling latency)
+    const int hb = (g.bn / 2) * 128;
+    L->b_bytes = hb;
+    const int budget = 222 * 1024;
+    int na = 3, bg = 3;
+    int nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb));
+    if (nb < 3) { na = 2; nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb)); }
+    if (nb >= 2) {
+      g.na = na; g.nb = nb; g.bgroup = bg;
+      L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * hb + 1024 + 512;
+    }
+    if (getenv("FAV_DEBUG_PLAN")) fprintf(stderr, "[fav]      pair rings: na=%d nb=%dx%d\n", g.na, g.nb, g.bgroup);
+  }
   const int tiles = g.m_tiles * g.n_tiles;
   L->grid = std::max(1, std::min(tiles, sm_count(device)));
   return FAV_OK;
@@ -750,6 +778,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   ProfScope ps(L.g.halo ? PK_CONV_HALO : PK_CONV_TAP, stream, L.flops);
+  if (L.g.halo && L.g.pair) return conv_launch_halo_pair(L, stream);
   if (L.g.halo) {
     static bool attr2 = false;
     if (!attr2) {

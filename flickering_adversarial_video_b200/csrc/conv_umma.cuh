@@ -43,6 +43,7 @@ struct ConvGeom {
   int acc_stages;      // 2: accumulators double-buffered (2*mt*bn <= 512), 1: single-buffered
   int swz_base_offset; // 1: put (start>>7)&7 into the descriptor's base_offset field
   int prof;            // 1: the MMA warp records its barrier wait cycles (debug, FAV_HALO_PROF)
+  int pair;            // 1: CTA-pair kernel (tcgen05 cta_group::2, conv_halo2.cu)
 };
 
 struct ConvEpilogue {
@@ -186,6 +187,7 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw);
 
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
+int conv_launch_halo_pair(const ConvLaunch& L, cudaStream_t stream);   // conv_halo2.cu
 
 // ---- stem (strided 7x7 spatial, Cin = 3): shared-memory halo reuse over kh, see conv_stem.cu ----
 struct StemGeom {
