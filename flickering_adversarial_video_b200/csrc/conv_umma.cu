@@ -54,6 +54,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
                  const ConvEpilogue e,
                  const int stages, const int a_bytes, const int b_bytes, const int stage_bytes) {
+  if (g.gate_count && *g.gate_count <= g.gate_thr) return;   // uniform: before any barrier / TMEM state exists
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -744,7 +745,7 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     // (measured with FAV_HALO_PROF: Conv3d_2c data gradient, N = 64: 1136 -> 717 kclk; N = 192 tiles are bound by the
     // weight supply either way).  FAV_HALO_2CTA=0 disables, =2 forces pairs on small problems too (tests).
     g.pair = (pair_mode && g.bn % 16 == 0 &&
-              (pair_mode == 2 ? g.m_tiles >= 2 : (g.bn <= 128 && g.m_tiles >= 2 * sm_count(device)))) ? 1 : 0;
+              (pair_mode == 2 ? g.m_tiles >= 2 : (g.bn <= 128 && cin >= 64 && g.m_tiles >= 2 * sm_count(device)))) ? 1 : 0;
     if (getenv("FAV_DEBUG_PLAN")) fprintf(stderr, "[fav]   -> %s\n", g.pair ? "CTA pairs (cta_group::2)" : "single CTA");
   }
   uint64_t bd[2] = {static_cast<uint64_t>(g.nkb) * 64, static_cast<uint64_t>(cout_pad)};

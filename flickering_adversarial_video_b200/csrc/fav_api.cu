@@ -120,6 +120,7 @@ struct fav_handle {
   const float* last_delta_px = nullptr;
   float* zero_delta = nullptr;     // [T,3] zeros: the stem bias table without a per-frame delta
   float* pix_partial = nullptr;
+  uint32_t dense_sat_thr = 0xffffffffu;   // saturated pixels above which the dense stem data gradient replaces the sparse corrections
 };
 
 namespace {
@@ -336,6 +337,8 @@ int run_dgrad(fav_handle* h, int conv_id, bool mask_with_input, bool accumulate,
   return conv_launch(L, s);
 }
 
+int i3d_plan_dense_stem(fav_handle* h);   // below (needs plan_dgrad_classes)
+
 int build_i3d(fav_handle* h) {
   const int B = h->B, T = h->T, H = h->H, W = h->W;
   FAV_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && W % 16 == 0, "I3D engine needs even H and W %% 16 == 0 (got %dx%d)", H, W);
@@ -424,6 +427,7 @@ int build_i3d(fav_handle* h) {
   }
   for (auto& c : h->convs) FAV_TRY(plan_conv(h, c));
   for (auto& b : h->blocks) FAV_TRY(plan_block_fused(h, b));
+  FAV_TRY(i3d_plan_dense_stem(h));
   // ---- head (i3d.py:459-472) ----
   const int C5 = h->bufs[h->final_buf].C;
   FAV_TRY(dev_alloc(h, &h->head_w, static_cast<size_t>(C5) * h->K));
@@ -477,6 +481,27 @@ int bn_fold(const NamedTensors& nt, const std::string& unit, int cout, std::vect
 }  // namespace
 
 #include "resnet_impl.cuh"
+
+namespace {
+// Dense data gradient of Conv3d_1a_7x7 (7^3, stride 2, TF SAME pad_before 2) as 8 parity-class GEMMs into
+// rn.dx [B,T,H,W,16]: the per-pixel attack needs it, and the flickering attack falls back to it when so many
+// entries are range-clipped that per-entry corrections would cost more (dense_sat_thr).
+int i3d_plan_dense_stem(fav_handle* h) {
+  ResNet& rn = h->rn;
+  FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(h->B) * h->T * h->H * h->W * 16));
+  const Buf& y1 = h->bufs[h->y1];
+  FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, y1.g, y1.cs, 64, y1.T, y1.H, y1.W, rn.dx, 16, 16, h->T, h->H, h->W, 7, 7, 7, 2,
+                             2, 2, h->pt, h->ph, h->pw, 3.0, 64.0));
+  FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(h->B) * h->T * stem_dx_reduce_chunks(h->H) * 3));
+  h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
+  for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
+  double frac = 0.06;
+  if (const char* ev = getenv("FAV_DENSE_SAT_FRAC")) frac = atof(ev);
+  const double px = static_cast<double>(h->B) * h->T * h->H * h->W;
+  h->dense_sat_thr = frac >= 1.0 ? 0xffffffffu : static_cast<uint32_t>(frac * px);
+  return FAV_OK;
+}
+}  // namespace
 
 // =============================================================================================
 // C-ABI
@@ -621,6 +646,14 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
     // weights in fp32: delta never passes through a bf16 rounding.
     const std::vector<float>& wq = wf;
     h->stem_w_host = wf;
+    {
+      std::vector<uint16_t> dpk;
+      for (auto& d : h->rn.stem_dg) {
+        dpk.resize(d.elems);
+        pack_weights_taps(dpk.data(), wf.data(), nullptr, d.src.data(), static_cast<int>(d.src.size()), 3, 64, 64, 16, true);
+        FAV_CUDA(cudaMemcpy(d.w, dpk.data(), dpk.size() * 2, cudaMemcpyHostToDevice));
+      }
+    }
     FAV_CUDA(cudaMemcpy(h->stem_w_f32, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice));
     // class-summed weights: Wc[kt][hc][wc][c][co] = sum over kh valid for hc, kw valid for wc
     std::vector<float> wcs(static_cast<size_t>(7) * 16 * 3 * 64, 0.0f);
@@ -791,8 +824,22 @@ extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   const Buf& y1 = h->bufs[h->y1];
   FAV_TRY(launch_stem_class_sums(y1.g, h->stem_S, h->B, h->To, h->Ho, h->Wo, s));
   FAV_TRY(launch_stem_grad_delta(h->stem_S, h->stem_wc, grad, h->T, h->To, h->pt, s));
-  FAV_TRY(launch_stem_sat_correction(y1.g, h->stem_w_f32, h->sat_list, h->sat_count, h->sat_capacity, grad,
+  // few range-clipped entries: exact per-entry corrections; many (dark / bright video, large delta): the dense stem
+  // data gradient + masked reduce recompute the sum.  Both sides test the device-side count, so the step stays
+  // graph-capturable.
+  const uint32_t thr = h->last_clip_u8 ? h->dense_sat_thr : 0xffffffffu;
+  FAV_TRY(launch_stem_sat_correction(y1.g, h->stem_w_f32, h->sat_list, h->sat_count, h->sat_capacity, thr, grad,
                                      h->B, h->T, h->H, h->W, h->To, h->Ho, h->Wo, h->pt, h->ph, h->pw, s));
+  if (thr != 0xffffffffu) {
+    for (const DgradClass& d : h->rn.stem_dg) {
+      ConvLaunch L = d.L;
+      L.g.gate_count = h->sat_count;
+      L.g.gate_thr = thr;
+      FAV_TRY(conv_launch(L, s));
+    }
+    FAV_TRY(launch_stem_dx_reduce(h->rn.dx, h->last_clip_u8, h->last_delta, h->last_adv_flag, h->last_delta_clip, h->nrm, 0,
+                                  h->rn.partial, grad, h->B, h->T, h->H, h->W, s, h->sat_count, thr));
+  }
   return FAV_OK;
 }
 
@@ -822,23 +869,6 @@ extern "C" int fav_pixels_enable(fav_handle* h) {
     return FAV_ERR_STATE;
   }
   FAV_CUDA(cudaSetDevice(h->device));
-  if (h->d.arch == FAV_NET_I3D) {
-    // dense data gradient of Conv3d_1a_7x7 (7^3, stride 2, TF SAME pad_before 2): 8 parity classes
-    ResNet& rn = h->rn;
-    FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(h->B) * h->T * h->H * h->W * 16));
-    const Buf& y1 = h->bufs[h->y1];
-    FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, y1.g, y1.cs, 64, y1.T, y1.H, y1.W, rn.dx, 16, 16, h->T, h->H, h->W, 7, 7, 7,
-                               2, 2, 2, h->pt, h->ph, h->pw, 3.0, 64.0));
-    std::vector<uint16_t> pk;
-    for (auto& d : rn.stem_dg) {
-      pk.resize(d.elems);
-      pack_weights_taps(pk.data(), h->stem_w_host.data(), nullptr, d.src.data(), static_cast<int>(d.src.size()), 3, 64, 64,
-                        16, true);
-      FAV_CUDA(cudaMemcpy(d.w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
-    }
-    h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
-    for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
-  }
   FAV_TRY(dev_alloc(h, &h->zero_delta, static_cast<size_t>(h->T) * 3));
   FAV_TRY(dev_alloc(h, &h->pix_partial, static_cast<size_t>(pixels_partial_floats(h->T, h->H, h->W))));
   h->pixels_enabled = true;

@@ -302,8 +302,10 @@ constexpr int kRedRows = 8;
 __global__ void __launch_bounds__(256)
 stem_dx_reduce_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __restrict__ clip,
                       const float* __restrict__ delta, float adv_flag, float dclip, const fav_norm_params nrm,
-                      int torch_mode, float* __restrict__ partial, int T, int H, int W, int chunks) {
+                      int torch_mode, float* __restrict__ partial, int T, int H, int W, int chunks,
+                      const uint32_t* __restrict__ gate_count, uint32_t gate_thr) {
   __shared__ float red[8][3];
+  if (gate_count && *gate_count <= gate_thr) return;
   const int chunk = blockIdx.x % chunks;
   const int t = blockIdx.x / chunks;
   const int b = blockIdx.y;
@@ -348,7 +350,9 @@ stem_dx_reduce_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __res
 }
 
 __global__ void stem_dx_final_kernel(const float* __restrict__ partial, float* __restrict__ grad, int B, int T,
-                                     int chunks, float s0, float s1, float s2) {
+                                     int chunks, float s0, float s1, float s2, const uint32_t* __restrict__ gate_count,
+                                     uint32_t gate_thr) {
+  if (gate_count && *gate_count <= gate_thr) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * 3) return;
   const int t = i / 3, c = i - t * 3;
@@ -360,16 +364,16 @@ __global__ void stem_dx_final_kernel(const float* __restrict__ partial, float* _
 
 int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
                           float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
-                          int B, int T, int H, int W, cudaStream_t s) {
+                          int B, int T, int H, int W, cudaStream_t s, const uint32_t* gate_count, uint32_t gate_thr) {
   ProfScope ps(PK_STEM_BWD, s, 0.0, static_cast<double>(B) * T * H * W * 9.0);
   const int chunks = ceil_div(H, kRedRows);
   stem_dx_reduce_kernel<<<dim3(T * chunks, B), 256, 0, s>>>(dx, clip, delta, adv_flag, delta_clip, nrm, torch_mode,
-                                                            partial, T, H, W, chunks);
+                                                            partial, T, H, W, chunks, gate_count, gate_thr);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   const float s0 = torch_mode ? 1.0f / nrm.std[0] : 1.0f, s1 = torch_mode ? 1.0f / nrm.std[1] : 1.0f,
               s2 = torch_mode ? 1.0f / nrm.std[2] : 1.0f;
-  stem_dx_final_kernel<<<ceil_div(T * 3, 128), 128, 0, s>>>(partial, grad, B, T, chunks, s0, s1, s2);
+  stem_dx_final_kernel<<<ceil_div(T * 3, 128), 128, 0, s>>>(partial, grad, B, T, chunks, s0, s1, s2, gate_count, gate_thr);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -1027,12 +1031,13 @@ int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, 
 __global__ void __launch_bounds__(512, 1)
 stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ w,
                            const uint32_t* __restrict__ sat_list, const uint32_t* __restrict__ sat_count,
-                           uint32_t sat_capacity, float* __restrict__ grad, int T, int H, int W, int To,
+                           uint32_t sat_capacity, uint32_t dense_thr, float* __restrict__ grad, int T, int H, int W, int To,
                            int Ho, int Wo, int pt, int ph, int pw) {
   extern __shared__ float smem_f[];
   __nv_bfloat162* sw = reinterpret_cast<__nv_bfloat162*>(smem_f);   // [343][3][32] channel pairs
   float* sacc = smem_f + 343 * 3 * 32;                                // [T*3]
   const uint32_t n = min(*sat_count, sat_capacity);
+  if (n > dense_thr) return;                                         // the dense path computes the masked sum instead
   if (blockIdx.x * (blockDim.x >> 4) >= n) return;                   // nothing for this block
   for (int i = threadIdx.x; i < 343 * 3 * 32; i += blockDim.x)
     sw[i] = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
@@ -1104,7 +1109,7 @@ stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __
 }
 
 int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const uint32_t* sat_list,
-                               const uint32_t* sat_count, uint32_t sat_capacity, float* grad, int B, int T,
+                               const uint32_t* sat_count, uint32_t sat_capacity, uint32_t dense_thr, float* grad, int B, int T,
                                int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw, cudaStream_t s) {
   ProfScope ps(PK_STEM_BWD, s);
   (void)B;
@@ -1115,7 +1120,7 @@ int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const ui
     attr_set = true;
   }
   FAV_CHECK_ARG(smem <= 160 * 1024, "sat correction: T=%d too large", T);
-  stem_sat_correction_kernel<<<148, 512, smem, s>>>(g1, w, sat_list, sat_count, sat_capacity, grad, T, H, W, To,
+  stem_sat_correction_kernel<<<148, 512, smem, s>>>(g1, w, sat_list, sat_count, sat_capacity, dense_thr, grad, T, H, W, To,
                                                      Ho, Wo, pt, ph, pw);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());

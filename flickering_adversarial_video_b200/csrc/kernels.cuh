@@ -35,7 +35,8 @@ int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, 
 // (c) dense reduce of the stem data gradient dX [B,T,H,W,16] bf16 into grad [T,3] with the recomputed clip mask
 int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
                           float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
-                          int B, int T, int H, int W, cudaStream_t s);
+                          int B, int T, int H, int W, cudaStream_t s, const uint32_t* gate_count = nullptr,
+                          uint32_t gate_thr = 0);
 int stem_dx_reduce_chunks(int H);
 
 // sparse per-pixel attack: apply with delta [T,H,W,3], per-pixel gradient, L1,2 regulariser + Adam
@@ -84,7 +85,7 @@ int launch_stem_grad_delta(const float* S, const float* wc, float* grad /*[T][3]
                            cudaStream_t s);
 int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w /*[343][3][64] folded*/,
                                const uint32_t* sat_list, const uint32_t* sat_count, uint32_t sat_capacity,
-                               float* grad, int B, int T, int H, int W, int To, int Ho, int Wo, int pt,
+                               uint32_t dense_thr, float* grad, int B, int T, int H, int W, int To, int Ho, int Wo, int pt,
                                int ph, int pw, cudaStream_t s);
 
 int launch_delta_update(float* delta, const float* grad, float* m, float* v, int64_t* step,

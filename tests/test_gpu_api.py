@@ -110,3 +110,37 @@ def test_class_gen_driver(k_i3d):
                 "total_steps", "beta_1", "beta_2", "fatness", "smoothness", "fool_rate"):
         assert key in res, key
     assert res["total_steps"] == 2 and len(res["fool_rate"]) == 2
+
+
+def test_single_video_90_frames_parity():
+    """BASELINE.json configs[0]: one 1x90x224x224x3 clip (odd temporal sizes 45 -> 23 -> 12 through the pools)."""
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.engine import FlickerEngine
+    from oracle import oracle_i3d
+    B, T = 1, 90
+    weights = synthetic.i3d_weights(seed=0)
+    clip = synthetic.clips_u8(B, T, seed=1090)
+    delta = synthetic.delta_uniform(T, seed=17, lo=-0.05, hi=0.05)
+    model = oracle_i3d.OracleI3D(weights)
+    x = oracle_i3d.normalize_u8(clip)
+    with torch.no_grad():
+        labels = model.forward(x).argmax(-1)
+    cfg = dict(improve_loss=True, margin=0.05, beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5, lr=1e-3)
+    ref = oracle_i3d.attack_step(model, x, labels, delta, cfg, data_grad_only=True)
+    eng = FlickerEngine(B, T)
+    eng.load_weights(weights)
+    eng.apply(clip.cuda(), delta.cuda())
+    logits = eng.forward().cpu()
+    eng.loss(labels.cuda(), improve_loss=True, margin=0.05)
+    g = eng.backward().cpu()
+    torch.cuda.synchronize()
+    rel = float((logits - ref["logits"]).abs().max() / ref["logits"].abs().max())
+    gr = ref["grad_data"]
+    cos = float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30))
+    print(f"T=90 single video: logits rel err {rel:.3e}, top1 {logits.argmax(-1).tolist()} vs {ref['logits'].argmax(-1).tolist()}, "
+          f"dL/d-delta cosine {cos:.5f}")
+    assert rel <= 1e-2 and logits.argmax(-1).tolist() == ref["logits"].argmax(-1).tolist()
+    # one clip, 270 gradient entries of ~1e-3: bf16 storage alone gives 0.91 here (the bf16-emulating CPU oracle has
+    # the same cosine against the fp32 oracle, tools/debug_t90.py); kernels are gated stage by stage elsewhere
+    assert cos >= 0.85
+    eng.close()

@@ -306,3 +306,32 @@ def test_delta_update_matches_oracle(setup):
         assert abs(float(sc[6]) - float(lr_)) < 1e-6
         assert abs(float(sc[7]) - float(th)) < 1e-6 and abs(float(sc[8]) - float(ro)) < 1e-6
     assert int(step.item()) == 5
+
+
+def test_dense_saturation_fallback_matches_sparse_corrections(setup, monkeypatch):
+    """Heavily saturated clips switch the stem backward from per-entry corrections to the dense stem data gradient +
+    masked reduce (device-side gate).  Both must give the same dL/d-delta."""
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.engine import FlickerEngine
+    B = setup["B"]
+    clip = synthetic.clips_u8_extreme(B, T_SMALL).cuda()
+    delta = synthetic.delta_uniform(T_SMALL, seed=8).cuda()
+    labels = None
+    grads = []
+    for frac in ("1.0", "0.0"):          # never dense / always dense
+        monkeypatch.setenv("FAV_DENSE_SAT_FRAC", frac)
+        eng = FlickerEngine(B, T_SMALL)
+        eng.load_weights(setup["weights"])
+        eng.apply(clip, delta)
+        logits = eng.forward()
+        if labels is None:
+            labels = logits.argmax(-1).clone()      # attack the predicted class (a zero margin loss has no gradient)
+        eng.loss(labels, improve_loss=True, margin=0.05)
+        grads.append(eng.backward().clone().cpu())
+        torch.cuda.synchronize()
+        eng.close()
+    a, b = grads
+    cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+    rel = float((a - b).norm() / a.norm())
+    _report(f"dense-saturation fallback vs sparse corrections: cosine {cos:.6f}, rel L2 {rel:.3e}")
+    assert cos >= 0.9999 and rel <= 1e-2
