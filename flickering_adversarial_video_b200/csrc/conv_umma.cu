@@ -25,6 +25,7 @@ __device__ unsigned long long g_halo_prof[8];
 namespace {
 
 constexpr int kThreads = 192;
+constexpr int kTapThreads = 320;   // generic kernel: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kAccCols = 256;   // TMEM columns per accumulator stage
 constexpr int kMaxStages = 8;
 
@@ -49,7 +50,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int tile) {
   return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTapThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
                  const ConvEpilogue e,
@@ -65,6 +66,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 2 * kMaxStages + 8);   // 8 epilogue warps x 32 rows x 5 uint4
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +82,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -138,14 +140,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_te = 0, w_f = 0, c0 = 0, ntile = 0;
+    const long long t_start = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      c0 = g.prof ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (g.prof) { w_te += clock64() - c0; ++ntile; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
       uint32_t accum = 0;
       int cb = 0;
       for (int kb = 0; kb < g.nkb; ++kb) {
+        c0 = g.prof ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
+        if (g.prof) w_f += clock64() - c0;
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
         const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
@@ -180,9 +188,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (g.prof && lane == 0) {
+      atomicAdd(&g_halo_prof[0], static_cast<unsigned long long>(w_te));
+      atomicAdd(&g_halo_prof[1], static_cast<unsigned long long>(w_f));
+      atomicAdd(&g_halo_prof[3], static_cast<unsigned long long>(clock64() - t_start));
+      atomicAdd(&g_halo_prof[4], static_cast<unsigned long long>(ntile));
+    }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // two warps per TMEM lane quarter, each draining half of the tile's columns: the epilogue is a chain of TMEM /
+    // global-memory latencies and bounds the 1x1x1 launches (FAV_TAP_PROF), so it gets the spare warps
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int rw = row % g.bw;
     const int rh = (row / g.bw) % g.bh;
@@ -205,20 +222,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * kAccCols);
+      // this warp's column range of the tile (multiples of 16)
+      const int half_cols = ((g.bn >> 4) + 1) / 2 * 16;
+      const int c_lo = chalf * half_cols, c_hi = min(g.bn, c_lo + half_cols);
       if (e.nseg > 1) {
         // column segments of this N tile go to different tensors (fused same-input 1x1x1 convs)
-        const int n_lo = tc.n0, n_hi = tc.n0 + g.bn;
+        const int n_lo = tc.n0 + c_lo, n_hi = tc.n0 + c_hi;
 #pragma unroll
         for (int sgi = 0; sgi < 3; ++sgi) {
           if (sgi >= e.nseg) break;
           const int a = max(n_lo, e.seg_n0[sgi]), b = min(n_hi, e.seg_n0[sgi + 1]);
           if (a >= b) continue;   // warp-uniform
           __nv_bfloat16* srow = e.seg_out[sgi] + pos * e.seg_cs[sgi] + e.seg_coff[sgi];
-          epilogue_columns(e, b - a, a - e.seg_n0[sgi], taddr + static_cast<uint32_t>(a - n_lo), valid, srow, nullptr,
-                           nullptr, bias_row ? bias_row + e.seg_n0[sgi] : nullptr, e.seg_n0[sgi + 1] - e.seg_n0[sgi]);
+          epilogue_columns_staged(e, b - a, a - e.seg_n0[sgi], taddr + static_cast<uint32_t>(a - tc.n0), valid, srow,
+                                  bias_row ? bias_row + e.seg_n0[sgi] : nullptr, e.seg_n0[sgi + 1] - e.seg_n0[sgi],
+                                  stage_all + (warp - 2) * 160, lane);
         }
-      } else {
-        epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, bias_row);
+      } else if (c_lo < c_hi) {
+        if (mask_row == nullptr && add_row == nullptr)
+          epilogue_columns_staged(e, c_hi - c_lo, tc.n0 + c_lo, taddr + static_cast<uint32_t>(c_lo), valid, out_row, bias_row,
+                                  e.cout_store, stage_all + (warp - 2) * 160, lane);
+        else
+          epilogue_columns<2>(e, c_hi - c_lo, tc.n0 + c_lo, taddr + static_cast<uint32_t>(c_lo), valid, out_row, mask_row,
+                              add_row, bias_row);
       }
       tc_fence_before();
       __syncwarp();
@@ -513,9 +539,9 @@ static void finish_plan(ConvLaunch* L, int device) {
   L->a_bytes = 128 * 128;
   L->b_bytes = g.bn * 128;
   L->stage_bytes = round_up(L->a_bytes + L->b_bytes, 1024);
-  const int budget = 200 * 1024;
+  const int budget = 180 * 1024;
   L->stages = std::max(2, std::min(kMaxStages, budget / L->stage_bytes));
-  L->smem_bytes = static_cast<size_t>(L->stages) * L->stage_bytes + 1024 + 512;
+  L->smem_bytes = static_cast<size_t>(L->stages) * L->stage_bytes + 1024 + 512 + 8 * 32 * 5 * 16;   // + epilogue staging
   const int tiles = g.m_tiles * g.n_tiles;
   L->grid = std::max(1, std::min(tiles, sm_count(device)));
 }
@@ -808,7 +834,27 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
     FAV_CUDA(cudaGetLastError());
     return FAV_OK;
   }
-  conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(
+  {
+    static int prof = -1;
+    if (prof < 0) prof = getenv("FAV_TAP_PROF") ? 1 : 0;
+    if (prof) {
+      ConvGeom gp = L.g;
+      gp.prof = 1;
+      unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
+      cudaMemcpyToSymbol(g_halo_prof, z, sizeof(z));
+      conv_umma_kernel<<<L.grid, kTapThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, gp, L.e, L.stages,
+                                                                   L.a_bytes, L.b_bytes, L.stage_bytes);
+      cudaStreamSynchronize(stream);
+      cudaMemcpyFromSymbol(r, g_halo_prof, sizeof(r));
+      const double n = L.grid;
+      fprintf(stderr, "[fav] tap prof M %dx%dx%dx%d k%dx%dx%d cin=%d nkb=%d bn=%dx%d stages=%d grid=%d: per-CTA kclk total %.1f, wait tempty %.1f, full %.1f, tiles %.1f\n",
+              L.g.B, L.g.T, L.g.H, L.g.W, L.g.kt, L.g.kh, L.g.kw, L.g.cin, L.g.nkb, L.g.bn, L.g.n_tiles, L.stages, L.grid,
+              r[3] / n / 1e3, r[0] / n / 1e3, r[1] / n / 1e3, r[4] / n);
+      FAV_COUNT_LAUNCH();
+      return FAV_OK;
+    }
+  }
+  conv_umma_kernel<<<L.grid, kTapThreads, L.smem_bytes, stream>>>(
       L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
       L.stage_bytes);
   FAV_COUNT_LAUNCH();

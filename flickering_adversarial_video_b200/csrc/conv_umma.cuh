@@ -90,17 +90,18 @@ struct ConvLaunch {
 // stores into the NDHWC channel slice.  Columns are processed 64 at a time with every load of the group
 // (4 tcgen05.ld, the mask / addend rows, the bias) issued before the first use: the epilogue is a chain of
 // memory latencies per group, so the fewer groups the better.
+template <int NQ = 4>   // 16-column chunks per batch (4: 64 columns; 2: 32 columns, for kernels with less register room)
 __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
                                                  __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
                                                  const __nv_bfloat16* add_row, const float* bias_row,
                                                  int cout_store = -1) {
   if (cout_store < 0) cout_store = e.cout_store;
-  for (int c0 = 0; c0 < bn; c0 += 64) {
-    uint32_t r[4][16];
-    uint4 av[4][2], mv[4][2];
-    bool live[4][2];
+  for (int c0 = 0; c0 < bn; c0 += 16 * NQ) {
+    uint32_t r[NQ][16];
+    uint4 av[NQ][2], mv[NQ][2];
+    bool live[NQ][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int c = c0 + q * 16;
       if (c < bn) tmem_ld_32x16(taddr + static_cast<uint32_t>(c), r[q]);   // warp-uniform condition
 #pragma unroll
@@ -117,7 +118,7 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
     }
     tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int c = c0 + q * 16;
       if (c >= bn) break;
       const int n = n0 + c;
@@ -155,6 +156,58 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
         *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
       }
     }
+  }
+}
+
+// Same epilogue for launches without mask / addend operands, with warp-coalesced stores: every lane's 16-byte store to
+// its own row is a separate L1 wavefront (32 per instruction; measured: the 1x1x1 launches were bound by exactly
+// that), so the warp stages 32 rows x 32 columns in shared memory and writes 8 rows x 64 contiguous bytes per
+// instruction instead.  `stage` = this warp's 32 x 5 uint4 scratch.
+__device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, int ncols, int n0, uint32_t taddr,
+                                                        bool valid, __nv_bfloat16* out_row, const float* bias_row,
+                                                        int cout_store, uint4* stage, int lane) {
+  const unsigned long long row_ptr = reinterpret_cast<unsigned long long>(out_row);
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t r[2][16];
+    tmem_ld_32x16(taddr + static_cast<uint32_t>(c0), r[0]);
+    if (c0 + 16 < ncols) tmem_ld_32x16(taddr + static_cast<uint32_t>(c0 + 16), r[1]);   // warp-uniform
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = c0 + q * 16;
+      if (c >= ncols) break;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[q][j]);
+      if (bias_row) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n0 + c + j));
+          v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+        }
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+      stage[lane * 5 + q * 2] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                           pack_bf16x2(v[6], v[7]));
+      stage[lane * 5 + q * 2 + 1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                               pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    }
+    __syncwarp();
+    const int k = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = (lane >> 2) + 8 * j;
+      const uint4 val = stage[rr * 5 + k];
+      const unsigned long long p = __shfl_sync(0xffffffffu, row_ptr, rr);
+      const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr);
+      const int c = c0 + 8 * k;
+      if (ok && c < ncols && n0 + c + 8 <= cout_store)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + n0 + c) = val;
+    }
+    __syncwarp();
   }
 }
 

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace fav {
 namespace {
@@ -375,7 +376,12 @@ PoolTiling pick_tiling(int H, int W, int C, int max_threads, int max_tiled = 0) 
   for (int c = 1; c <= 16 && c * hw <= max_threads; ++c)
     if (cg % c == 0) full = c;
   int tc = 0;
-  for (int c = 4; c >= 1; --c)
+  static int cg_pref = -1;
+  if (cg_pref < 0) {
+    const char* ev = getenv("FAV_POOL_CGN");
+    cg_pref = ev ? atoi(ev) : 4;
+  }
+  for (int c = cg_pref; c >= 1; --c)
     if (cg % c == 0) { tc = c; break; }
   const int Rtile = tc > 0 ? max_tiled / (W * tc) - 2 : 0;
   if (full >= 4 || (full > 0 && (Rtile < 2 || tc <= full))) {
