@@ -126,7 +126,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int npairs = gridDim.x >> 1;
   const int m_pairs = (g.m_tiles + 1) >> 1;
   const int total = m_pairs * g.n_tiles;         // pair tiles
-  const int slabs_per_tile = g.cblocks * 3;
+  const int slabs_per_tile = g.cblocks * g.kt;   // kt = 3 (3x3x3) or 1 ((1,3,3) convs)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -151,12 +151,12 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int pt = pair; pt < total; pt += npairs) {
         const HaloTile tc = decode_pair_tile(g, (pt / g.n_tiles) * 2 + static_cast<int>(rank), pt % g.n_tiles);
         for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
-          const int cb = sidx / 3;
-          const int dt = sidx - cb * 3;
+          const int cb = sidx / g.kt;
+          const int dt = sidx - cb * g.kt;
           mbar_wait(&a_empty[sa], pa ^ 1);
           const uint32_t lead = mapa_u32(smem_u32(&a_full[sa]), 0);
           mbar_expect_tx_cluster(lead, static_cast<uint32_t>(g.slab_tx));
-          tma_load_5d_pair(smem_a + static_cast<size_t>(sa) * g.slab_bytes, &tmA, lead, cb * 64, -1, tc.h0 - 1, tc.t + dt - 1,
+          tma_load_5d_pair(smem_a + static_cast<size_t>(sa) * g.slab_bytes, &tmA, lead, cb * 64, -1, tc.h0 - 1, tc.t + dt + g.ot,
                            tc.b);
           if (++sa == g.na) { sa = 0; pa ^= 1; }
         }
@@ -170,8 +170,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int pt = pair; pt < total; pt += npairs) {
         const int n0 = (pt % g.n_tiles) * g.bn + static_cast<int>(rank) * (g.bn >> 1);
         for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
-          const int cb = sidx / 3;
-          const int dt = sidx - cb * 3;
+          const int cb = sidx / g.kt;
+          const int dt = sidx - cb * g.kt;
           for (int j = 0; j < 9; j += g.bgroup) {
             mbar_wait(&b_empty[sb], pb ^ 1);
             const uint32_t lead = mapa_u32(smem_u32(&b_full[sb]), 0);
@@ -251,7 +251,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             row_lo += wp16;
           }
           if (++sa == g.na) { sa = 0; pa ^= 1; }
-          if (++dt == 3) { dt = 0; ++cb; }
+          if (++dt == g.kt) { dt = 0; ++cb; }
         }
         if (g.acc_stages == 2) {
           acc ^= 1;

@@ -306,7 +306,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = g.m_tiles * g.n_tiles;
-  const int slabs_per_tile = g.cblocks * 3;
+  const int slabs_per_tile = g.cblocks * g.kt;   // kt = 3 (3x3x3) or 1 ((1,3,3) convs)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -330,12 +330,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const HaloTile tc = decode_halo_tile(g, tile);
         for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
-          const int cb = sidx / 3;
-          const int dt = sidx - cb * 3;
+          const int cb = sidx / g.kt;
+          const int dt = sidx - cb * g.kt;
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(g.slab_tx));
           tma_load_5d(smem_a + static_cast<size_t>(sa) * g.slab_bytes, &tmA, &a_full[sa], cb * 64, -1, tc.h0 - 1,
-                      tc.t + dt - 1, tc.b);
+                      tc.t + dt + g.ot, tc.b);
           if (++sa == g.na) { sa = 0; pa ^= 1; }
         }
       }
@@ -348,8 +348,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % g.n_tiles) * g.bn;
         for (int sidx = 0; sidx < slabs_per_tile; ++sidx) {
-          const int cb = sidx / 3;
-          const int dt = sidx - cb * 3;
+          const int cb = sidx / g.kt;
+          const int dt = sidx - cb * g.kt;
           for (int j = 0; j < 9; j += g.bgroup) {
             mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes * g.bgroup));
@@ -425,7 +425,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           row_lo += wp16;
         }
         if (++sa == g.na) { sa = 0; pa ^= 1; }
-        if (++dt == 3) { dt = 0; ++cb; }
+        if (++dt == g.kt) { dt = 0; ++cb; }
       }
       if (g.acc_stages == 2) {
         acc ^= 1;
@@ -634,7 +634,9 @@ int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, 
 
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw) {
   (void)T;
-  if (kt != 3 || kh != 3 || kw != 3) return false;
+  if ((kt != 3 && kt != 1) || kh != 3 || kw != 3) return false;
+  // (1,3,3): only 9 taps share a slab, which pays on the large planes only (measured on mc3_18 / r2plus1d_18)
+  if (kt == 1 && H * W < 28 * 28) return false;
   const int Wp = W + 2;
   if (Wp > 64) return false;                 // at least two output rows per 128-row tile
   const int nrows = std::min(128 / Wp, H);
@@ -651,17 +653,18 @@ bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw) {
 }
 
 int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
-                   const void* wpk, int cout_pad, int B, int T, int H, int W) {
+                   const void* wpk, int cout_pad, int B, int T, int H, int W, int kt) {
+  FAV_CHECK_ARG(kt == 1 || kt == 3, "conv halo: temporal taps %d", kt);
   FAV_CHECK_ARG(cin % 16 == 0 && cin > 0, "conv: cin=%d must be a positive multiple of 16", cin);
   FAV_CHECK_ARG(cout_pad % 16 == 0 && cout_pad > 0, "conv: padded cout=%d must be a multiple of 16", cout_pad);
   memset(L, 0, sizeof(*L));
   ConvGeom& g = L->g;
   g.halo = 1;
-  g.kt = g.kh = g.kw = 3;
-  g.ot = g.oh = g.ow = -1;
+  g.kt = kt; g.kh = g.kw = 3;
+  g.ot = -(kt / 2); g.oh = g.ow = -1;
   g.cin = cin;
   g.cblocks = ceil_div(cin, 64);
-  g.nkb = 27 * g.cblocks;
+  g.nkb = 9 * kt * g.cblocks;
   g.B = B; g.T = T; g.H = H; g.W = W;
   g.Wp = W + 2;
   g.nrows = std::min(128 / g.Wp, H);
@@ -714,8 +717,8 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
         const double per_mma = std::max(std::max(bn / 2.0, (4096.0 + 32.0 * bn * (1.0 + 1.0 / mt) +
                                                             slab_tx / (9.0 * ksteps * mt)) / 128.0),
                                         45.0 + 200.0 / (bgroup * ksteps * mt));
-        const double mma = 27.0 * g.cblocks * ksteps * mt * per_mma;
-        const double l2 = (27.0 * g.cblocks * b_bytes + 3.0 * g.cblocks * slab_tx) / 41.0;
+        const double mma = 9.0 * kt * g.cblocks * ksteps * mt * per_mma;
+        const double l2 = (9.0 * kt * g.cblocks * b_bytes + 1.0 * kt * g.cblocks * slab_tx) / 41.0;
         const double epi = mt * (bn / 16.0) * 400.0;   // epilogue of one tile; exposed (and slower: nothing to overlap) when single-buffered
         const double per_tile = acc_stages == 2 ? std::max(std::max(mma, l2), epi) : std::max(mma, l2) + 1.5 * epi;
         const long long tiles = static_cast<long long>(B) * T * ceil_div(H, g.nrows * mt) * nt;

@@ -237,8 +237,9 @@ int conv_plan_generic(ConvLaunch* L, int device, const void* x, long long x_cs, 
                       int kw, int flat);
 
 // 3x3x3 stride-1 SAME conv with shared-memory halo reuse (same packed weights as conv_plan_generic).
+// kt = 3: 3x3x3; kt = 1: (1,3,3) (Conv3DNoTemporal / the spatial half of Conv2Plus1D)
 int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int x_coff, int cin,
-                   const void* wpk, int cout_pad, int B, int T, int H, int W);
+                   const void* wpk, int cout_pad, int B, int T, int H, int W, int kt = 3);
 // true when the halo path applies and beats the per-tap path for this shape
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw);
 

@@ -1006,7 +1006,7 @@ extern "C" int fav_op_conv3d(int device, const void* x, int64_t x_cs, int64_t x_
   ConvLaunch L;
   int st;
   if (use_halo(T, H, W, kt, kh, kw))
-    st = conv_plan_halo(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W);
+    st = conv_plan_halo(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W, kt);
   else
     st = conv_plan_generic(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W, kt, kh, kw,
                            taps == 1);

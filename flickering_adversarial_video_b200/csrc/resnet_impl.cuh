@@ -81,13 +81,14 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
   const int taps = c.kt * c.kh * c.kw;
   const bool s1 = c.st == 1 && c.sh == 1 && c.sw == 1;
   const bool k333 = c.kt == 3 && c.kh == 3 && c.kw == 3 && c.pt == 1 && c.ph == 1 && c.pw == 1;
-  const bool halo = s1 && k333 && use_halo(bi.T, bi.H, bi.W, 3, 3, 3);
+  const bool k133 = c.kt == 1 && c.kh == 3 && c.kw == 3 && c.pt == 0 && c.ph == 1 && c.pw == 1;
+  const bool halo = s1 && (k333 || k133) && use_halo(bi.T, bi.H, bi.W, c.kt, 3, 3);
   // ---- forward ----
   c.w_fwd_elems = static_cast<size_t>(c.cout_pad) * taps * ceil_div(c.cin_k, 64) * 64;
   FAV_TRY(dev_alloc(h, &c.w_fwd, c.w_fwd_elems));
   FAV_TRY(dev_alloc(h, &c.bias, static_cast<size_t>(c.cout_pad)));
   if (halo) {
-    FAV_TRY(conv_plan_halo(&c.fwd, h->device, bi.p, bi.cs, 0, c.cin_k, c.w_fwd, c.cout_pad, h->B, bi.T, bi.H, bi.W));
+    FAV_TRY(conv_plan_halo(&c.fwd, h->device, bi.p, bi.cs, 0, c.cin_k, c.w_fwd, c.cout_pad, h->B, bi.T, bi.H, bi.W, c.kt));
   } else {
     ConvSpec sp{};
     sp.x = bi.p; sp.x_cs = bi.cs; sp.x_coff = 0; sp.cin = c.cin_k;
@@ -121,14 +122,14 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
   if (halo) {
     DgradClass d;
     d.class0 = true;
-    for (int j = 0; j < 27; ++j) d.src.push_back(26 - j);
-    d.elems = static_cast<size_t>(c.cin_k) * 27 * ceil_div(c.cout_pad, 64) * 64;
+    for (int j = 0; j < taps; ++j) d.src.push_back(taps - 1 - j);
+    d.elems = static_cast<size_t>(c.cin_k) * taps * ceil_div(c.cout_pad, 64) * 64;
     FAV_TRY(dev_alloc(h, &d.w, d.elems));
-    FAV_TRY(conv_plan_halo(&d.L, h->device, bg.g, bg.cs, 0, c.cout_pad, d.w, c.cin_k, h->B, bi.T, bi.H, bi.W));
+    FAV_TRY(conv_plan_halo(&d.L, h->device, bg.g, bg.cs, 0, c.cout_pad, d.w, c.cin_k, h->B, bi.T, bi.H, bi.W, c.kt));
     ConvEpilogue& e = d.L.e;
     e.out = bi.g; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = c.cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr;
-    d.L.flops = 2.0 * static_cast<double>(h->B) * bo.T * bo.H * bo.W * 27.0 * c.cin_real * c.cout_real;
+    d.L.flops = 2.0 * static_cast<double>(h->B) * bo.T * bo.H * bo.W * taps * c.cin_real * c.cout_real;
     c.dg.push_back(std::move(d));
   } else {
     FAV_TRY(plan_dgrad_classes(h, &c.dg, bg.g, bg.cs, c.cout_pad, bo.T, bo.H, bo.W, bi.g, bi.cs, c.cin_k, bi.T, bi.H,
