@@ -672,14 +672,16 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   g.swz_base_offset = 0;   // tcgen05 applies the 128-byte swizzle on absolute smem addresses (measured)
   // ---- choose the N split and the number of M tiles that share every weight tile ----
   // Cost model from measurements on B200 (tools/ubench/, FAV_HALO_PROF, profiles/): shared-memory bandwidth
-  // (operand reads + TMA refills) and L2 -> SM bandwidth (~41 B/cycle/SM with all SMs pulling) bound these
+  // (operand reads + TMA refills) and L2 -> SM bandwidth (41 B/cycle/SM in a pure-load microbenchmark; the planner uses 70, which fits whole-step timings) bound these
   // kernels, not the tensor pipe.
   {
     const int groups = ceil_div(H, g.nrows);
     const int budget = 222 * 1024;
     const int sms = sm_count(device);
     static int force_mt = -1, force_nt = -1;
+    static double l2_rate = 70.0;   // B per cycle per SM; measured on whole steps (41 -> 70: 7.44 -> 7.35 ms/step)
     if (force_mt < 0) {
+      if (const char* lr = getenv("FAV_HALO_L2RATE")) l2_rate = atof(lr);
       const char* ev = getenv("FAV_HALO_MT");
       force_mt = ev ? atoi(ev) : 0;
       ev = getenv("FAV_HALO_NT");
@@ -718,7 +720,7 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
                                                             slab_tx / (9.0 * ksteps * mt)) / 128.0),
                                         45.0 + 200.0 / (bgroup * ksteps * mt));
         const double mma = 9.0 * kt * g.cblocks * ksteps * mt * per_mma;
-        const double l2 = (9.0 * kt * g.cblocks * b_bytes + 1.0 * kt * g.cblocks * slab_tx) / 41.0;
+        const double l2 = (9.0 * kt * g.cblocks * b_bytes + 1.0 * kt * g.cblocks * slab_tx) / l2_rate;
         const double epi = mt * (bn / 16.0) * 400.0;   // epilogue of one tile; exposed (and slower: nothing to overlap) when single-buffered
         const double per_tile = acc_stages == 2 ? std::max(std::max(mma, l2), epi) : std::max(mma, l2) + 1.5 * epi;
         const long long tiles = static_cast<long long>(B) * T * ceil_div(H, g.nrows * mt) * nt;

@@ -276,6 +276,24 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
 int stem_launch(const StemLaunch& L, cudaStream_t stream);
 
 
+// ---- stem gradient collapse on the tensor cores (stem_grad.cu) ----
+struct StemGradLaunch {
+  CUtensorMap tmA;        // g1 as a flat [positions][64] matrix
+  CUtensorMap tmB;        // weights [7 * 160][64]
+  const uint32_t* bits;   // pass nibbles written by the apply kernel
+  int B, T, To, Ho, Wo, pt, ph, pw;
+  int tiles_per_plane, m_tiles, bits_rows, bits_pitch;
+  size_t smem_bytes;
+  int grid;
+  int ready;
+  double flops, bytes;
+};
+size_t stem_grad_bitmap_words(int B, int T, int H, int W);
+void stem_grad_pack_weights(uint16_t* dst /*[7][160][64]*/, const float* wq /*[343][3][64]*/);
+int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, const void* wpk, const uint32_t* bits, int B, int T,
+                   int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw);
+int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream);
+
 // Host-side weight packing (bf16 bits in uint16_t).
 // fwd: w [taps][cin_real][cout_real] (TF layout flattened), scale[cout] (BN fold) or nullptr.
 void pack_weights_fwd(uint16_t* dst, const float* w, const float* scale, int taps, int cin_real,

@@ -120,6 +120,9 @@ struct fav_handle {
   const float* last_delta_px = nullptr;
   float* zero_delta = nullptr;     // [T,3] zeros: the stem bias table without a per-frame delta
   float* pix_partial = nullptr;
+  uint32_t* pass_bits = nullptr;  // I3D: pass nibbles of the range clip (stem_grad.cu)
+  uint16_t* stem_gw = nullptr;    // I3D: stem weights as the [7*160][64] B operand of the gradient collapse
+  StemGradLaunch stem_gd;         // I3D: tensor-core gradient collapse (FAV_STEM_GRAD_LEGACY=1 restores class sums + corrections)
   uint32_t dense_sat_thr = 0xffffffffu;   // saturated pixels above which the dense stem data gradient replaces the sparse corrections
 };
 
@@ -495,6 +498,13 @@ int i3d_plan_dense_stem(fav_handle* h) {
   FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(h->B) * h->T * stem_dx_reduce_chunks(h->H) * 3));
   h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
   for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
+  h->stem_gd.ready = 0;
+  if (!getenv("FAV_STEM_GRAD_LEGACY")) {
+    FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(h->B, h->T, h->H, h->W)));
+    FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(7) * 160 * 64));
+    FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
+                           h->Wo, h->pt, h->ph, h->pw));
+  }
   double frac = 0.06;
   if (const char* ev = getenv("FAV_DENSE_SAT_FRAC")) frac = atof(ev);
   const double px = static_cast<double>(h->B) * h->T * h->H * h->W;
@@ -655,6 +665,11 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
       }
     }
     FAV_CUDA(cudaMemcpy(h->stem_w_f32, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice));
+    if (h->stem_gd.ready) {
+      std::vector<uint16_t> gw(static_cast<size_t>(7) * 160 * 64);
+      stem_grad_pack_weights(gw.data(), wq.data());
+      FAV_CUDA(cudaMemcpy(h->stem_gw, gw.data(), gw.size() * 2, cudaMemcpyHostToDevice));
+    }
     // class-summed weights: Wc[kt][hc][wc][c][co] = sum over kh valid for hc, kw valid for wc
     std::vector<float> wcs(static_cast<size_t>(7) * 16 * 3 * 64, 0.0f);
     auto valid = [](int cls, int n_out, int k, int pad, int n_in) {
@@ -720,8 +735,12 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
                                 h->pt, h->rn.stem_KT, 1, C1, cst, ds, s));
     return FAV_OK;
   }
-  FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32,
-                       h->sat_list, h->sat_capacity, h->sat_count, h->B, h->T, h->H, h->W, s));
+  if (h->stem_gd.ready)
+    FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32,
+                         nullptr, 0, nullptr, h->B, h->T, h->H, h->W, s, h->pass_bits));
+  else
+    FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32,
+                         h->sat_list, h->sat_capacity, h->sat_count, h->B, h->T, h->H, h->W, s));
   FAV_TRY(launch_stem_bias(delta, adv_flag, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T,
                            h->To, h->pt, s));
   return FAV_OK;
@@ -821,6 +840,7 @@ extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   if (h->d.arch != FAV_NET_I3D) return resnet_backward(h, grad, s);
   FAV_TRY(i3d_backward_to_stem(h, s));
   // stem: collapse over B,H,W without materialising dL/dx
+  if (h->stem_gd.ready) return stem_grad_launch(h->stem_gd, grad, s);
   const Buf& y1 = h->bufs[h->y1];
   FAV_TRY(launch_stem_class_sums(y1.g, h->stem_S, h->B, h->To, h->Ho, h->Wo, s));
   FAV_TRY(launch_stem_grad_delta(h->stem_S, h->stem_wc, grad, h->T, h->To, h->pt, s));

@@ -22,7 +22,7 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
              float dclip, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
              uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
              uint32_t* __restrict__ sat_list, uint32_t sat_capacity, uint32_t* __restrict__ sat_count,
-             int T, int H, int W, long long groups) {
+             uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = gid < groups;
   const int gpr = W >> 4;
@@ -86,6 +86,20 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
 #pragma unroll
     for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xq[4 * i], xq[4 * i + 1], xq[4 * i + 2], xq[4 * i + 3]);
 
+    if (pass_bits) {
+      // one nibble per pixel, bit c = entry (pixel, c) passes the gradient; 8 zero nibbles left of w = 0, 3 zero rows above h = 0
+      uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        w0 |= (~sat_mask[p] & 7u) << (4 * p);
+        w1 |= (~sat_mask[p + 8] & 7u) << (4 * p);
+      }
+      const long long bt = row / H;
+      const int hh = static_cast<int>(row - bt * H);
+      uint32_t* dstb = pass_bits + (bt * (H + 7) + hh + 3) * ((W + 16) >> 3) + 1 + 2 * wg;
+      dstb[0] = w0;
+      dstb[1] = w1;
+    }
     if (adv_u8) {
       uint32_t o[12];
 #pragma unroll
@@ -140,7 +154,7 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
 int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
                  __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
                  uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
-                 int W, cudaStream_t s) {
+                 int W, cudaStream_t s, uint32_t* pass_bits) {
   ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 * (in_dtype == FAV_F32 ? 4 : 1) + 8.0 + (adv_u8 ? 3.0 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   FAV_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 28), "apply: too many pixels per call");
@@ -150,10 +164,10 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
   if (sat_count) FAV_CUDA(cudaMemsetAsync(sat_count, 0, sizeof(uint32_t), s));
   if (in_dtype == FAV_F32)
     apply_kernel<true><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
-                                              adv_f32, sat_list, sat_capacity, sat_count, T, H, W, groups);
+                                              adv_f32, sat_list, sat_capacity, sat_count, pass_bits, T, H, W, groups);
   else
     apply_kernel<false><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
-                                               adv_f32, sat_list, sat_capacity, sat_count, T, H, W, groups);
+                                               adv_f32, sat_list, sat_capacity, sat_count, pass_bits, T, H, W, groups);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -13,11 +13,12 @@ struct PoolGeom {
 PoolGeom make_pool_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh, int sw);
 
 // (a) flicker apply. Writes the stem input x' (bf16 RGBX, W padded) and optionally the uint8 /
-// fp32 adversarial video; appends saturated entries to sat_list (count in *sat_count).
+// fp32 adversarial video; appends saturated entries to sat_list (count in *sat_count) and / or writes the pass
+// nibbles of stem_grad.cu (pass_bits: rows of (W + 16) / 8 words, H + 7 rows per frame, zero borders).
 int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
                  __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
                  uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
-                 int W, cudaStream_t s);
+                 int W, cudaStream_t s, uint32_t* pass_bits = nullptr);
 
 // delta-dependent stem bias table [To][4][4][64]
 int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc /*[7][16][3][64]*/,

@@ -1,0 +1,302 @@
+// Stem gradient collapse on the tensor cores: dL/d delta[t,c] = sum_{b,h,w} pass(b,t,h,w,c) * dL/dX(b,t,h,w,c) without
+// ever materialising dL/dX and with a cost that does not depend on how many entries the range clip saturated.
+//
+// Reference: tf.gradients of the loss w.r.t. the perturbation through tf.clip_by_value(x + delta, -1, 1) and the
+// Conv3d_1a_7x7 unit (single_video_npy.py:66-84, utils/kinetics_i3d_utils.py:165-171, i3d.py:275-279).
+//
+//   dL/dX(b,t,h,w,c) = sum over output positions o = (to,ho,wo) and taps k = (kt,kh,kw) with 2*o + k - pad = (t,h,w)
+//                      of sum_co g1[b,o,co] * w[k,c,co]
+//
+// For one output position the 7*7*7*3 = 1029 products P[o,(k,c)] = sum_co g1[o,co] w[k,c,co] are a GEMM row
+// (K = 64 output channels, N = 1029): 128 positions x 64 channels of g1 are the A tile (one TMA box of the flat
+// [positions, 64] matrix), the weights [N][64] stay resident in shared memory, and the N dimension is walked in 7 chunks
+// of 160 columns (one temporal tap kt each: 3 channels x 49 in-plane taps = 147 live columns).  Every column of a chunk
+// lands on the same frame t = 2*to + kt - pad_t, so the epilogue reduces a chunk to three numbers per row: it adds
+// P[o,col] where the pass bit of the input entry that column touches is set.  The pass bits come from the apply kernel as
+// one nibble per pixel (bit c = entry (pixel, c) was not range-clipped) in a zero-padded bitmap, so taps that fall into
+// the convolution's zero padding read zeros and need no bounds logic.
+//
+// Roofline (B=8, T=64, 224x224): 2 * 3.2 M positions * 64 * 1120 = 0.46 TFLOP of bf16 MMA; g1 is read once (411 MB).
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace fav {
+
+namespace {
+
+constexpr int kSgSets = 2;         // epilogue warp sets; set s owns the temporal taps kt = s, s + kSgSets, ...
+constexpr int kSgOwn = (7 + kSgSets - 1) / kSgSets;   // taps per set (upper bound)
+constexpr int kSgThreads = 64 + kSgSets * 128;   // warp 0: TMA, warp 1: MMA issue, then 4 warps (one per TMEM lane quarter) per set
+constexpr int kSgChunkN = 160;     // columns per temporal tap: 147 live + 13 zero
+constexpr int kSgStages = 3;       // A tiles in flight
+constexpr int kSgAcc = 3;          // TMEM accumulators (3 x 160 columns)
+constexpr int kSgABytes = 128 * 128;
+constexpr int kSgBBytes = kSgChunkN * 128;
+
+struct StemGradGeom {
+  int B, T, To, Ho, Wo;
+  int pt, ph, pw;
+  int tiles_per_plane;   // ceil(Ho*Wo / 128)
+  int m_tiles;           // B * To * tiles_per_plane
+  int bits_rows;         // bitmap rows per frame (H + 7: 3 zero rows above, 4 below)
+  int bits_pitch;        // 32-bit words per bitmap row ((W + 16) / 8: 8 zero nibbles left, 8 right)
+};
+
+// contiguous tile range of a CTA: consecutive tiles share (b, to), so the epilogue keeps its sums in registers
+__device__ __forceinline__ void sg_tile_range(const StemGradGeom& g, int* first, int* last) {
+  const int q = g.m_tiles / gridDim.x, r = g.m_tiles % gridDim.x;
+  const int bx = blockIdx.x;
+  *first = bx * q + min(bx, r);
+  *last = *first + q + (bx < r ? 1 : 0);
+}
+
+// one accumulator chunk (temporal tap KT of this tile): add the columns whose pass bit is set
+__device__ __forceinline__ void sg_chunk(uint32_t taddr, const uint32_t (&m)[7], float (&a)[3]) {
+  float a6[3][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
+  uint32_t v[16];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    tmem_ld_32x16(taddr + j * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = j * 16 + i;
+      if (col < 147) {
+        const int c = col / 49, rem = col % 49, kh = rem / 7, kw = rem % 7;
+        if (m[kh] & (1u << (4 * kw + c))) a6[c][col & 1] += __uint_as_float(v[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a[c] += a6[c][0] + a6[c][1];
+}
+
+__global__ void __launch_bounds__(kSgThreads, 1)
+stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StemGradGeom g,
+                 const uint32_t* __restrict__ bits, float* __restrict__ grad) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sB = smem;                                  // 7 chunks x [160][64] bf16, SW128
+  uint8_t* sA = smem + 7 * kSgBBytes;                  // kSgStages x [128][64] bf16, SW128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kSgStages * kSgABytes);
+  uint64_t* a_full = bars;                 // [3]
+  uint64_t* a_empty = bars + 3;            // [3]
+  uint64_t* t_full = bars + 6;             // [3]
+  uint64_t* t_empty = bars + 9;            // [3]
+  uint64_t* b_full = bars + 12;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* sacc = reinterpret_cast<float*>(bars + 14);   // [T*3]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int tile_first, tile_last;
+  sg_tile_range(g, &tile_first, &tile_last);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kSgStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kSgAcc; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    mbar_init(b_full, 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < g.T * 3; i += kSgThreads) sacc[i] = 0.0f;
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, 7 * kSgBBytes);
+      for (int kt = 0; kt < 7; ++kt) tma_load_2d(sB + kt * kSgBBytes, &tmB, b_full, 0, kt * kSgChunkN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_first; tile < tile_last; ++tile) {
+        const int plane = tile / g.tiles_per_plane;
+        const int pos0 = (tile - plane * g.tiles_per_plane) * 128;
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        mbar_expect_tx(&a_full[stage], kSgABytes);
+        tma_load_2d(sA + stage * kSgABytes, &tmA, &a_full[stage], 0, plane * g.Ho * g.Wo + pos0);
+        if (++stage == kSgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(128, kSgChunkN);
+    const uint32_t desc_hi = umma_desc_hi(128);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    mbar_wait(b_full, 0);
+    for (int tile = tile_first; tile < tile_last; ++tile) {
+      const int plane = tile / g.tiles_per_plane;
+      const int to = plane % g.To;
+      const int kt_lo = max(0, g.pt - 2 * to), kt_hi = min(6, g.T - 1 + g.pt - 2 * to);
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_lo = umma_desc_lo(smem_u32(sA + stage * kSgABytes));
+      for (int kt = kt_lo; kt <= kt_hi; ++kt) {
+        mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_lo = umma_desc_lo(smem_u32(sB + kt * kSgBBytes));
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kSgChunkN);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, k > 0 ? 1u : 0u);
+          umma_commit(&t_full[acc]);
+          if (kt == kt_hi) umma_commit(&a_empty[stage]);
+        }
+        __syncwarp();
+        if (++acc == kSgAcc) { acc = 0; acc_phase ^= 1; }
+      }
+      if (++stage == kSgStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue: masked row sums =====================
+    const int set = (warp - 2) >> 2;                    // owns kt = set, set + kSgSets, ...
+    const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int HW = g.Ho * g.Wo;
+    float a[kSgOwn][3];                                      // [owned tap j][channel]: sums of the current plane
+#pragma unroll
+    for (int j = 0; j < kSgOwn; ++j) a[j][0] = a[j][1] = a[j][2] = 0.0f;
+    int cur_plane = -1;
+    int nchunk = 0;                                     // chunks the MMA warp has issued before this tile
+    auto flush = [&](int plane) {
+      const int to = plane % g.To;
+#pragma unroll
+      for (int j = 0; j < kSgOwn; ++j) {
+        const int t = 2 * to + set + kSgSets * j - g.pt;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float s = a[j][c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0 && set + kSgSets * j < 7 && t >= 0 && t < g.T) atomicAdd(&sacc[t * 3 + c], s);
+          a[j][c] = 0.0f;
+        }
+      }
+    };
+    for (int tile = tile_first; tile < tile_last; ++tile) {
+      const int plane = tile / g.tiles_per_plane;
+      if (plane != cur_plane) {
+        if (cur_plane >= 0) flush(cur_plane);
+        cur_plane = plane;
+      }
+      const int pos = (tile - plane * g.tiles_per_plane) * 128 + r;
+      const int b = plane / g.To, to = plane - b * g.To;
+      const bool valid = pos < HW;
+      const int ho = valid ? pos / g.Wo : 0;
+      const int wo = valid ? pos - ho * g.Wo : 0;
+      const int bit0 = 8 * wo + 32 - 4 * g.pw;          // nibble 2*wo - pw + 8 of the bitmap row
+      const int word0 = bit0 >> 5, shift = bit0 & 31;
+      const int kt_lo = max(0, g.pt - 2 * to), kt_hi = min(6, g.T - 1 + g.pt - 2 * to);
+      // pass nibbles of the 7 x 7 windows this output position reads in the frames of the owned taps (all loads in flight
+      // before the first accumulator wait)
+      uint32_t m[kSgOwn][7];
+#pragma unroll
+      for (int j = 0; j < kSgOwn; ++j) {
+        const int kt = set + kSgSets * j;
+        const bool live = valid && kt >= kt_lo && kt <= kt_hi;
+        const int t = live ? 2 * to + kt - g.pt : 0;
+        const uint32_t* brow = bits + (static_cast<long long>(b * g.T + t) * g.bits_rows + (2 * ho - g.ph + 3)) * g.bits_pitch + word0;
+#pragma unroll
+        for (int kh = 0; kh < 7; ++kh) {
+          const uint32_t lo = live ? __ldg(brow + kh * g.bits_pitch) : 0u, hi = live ? __ldg(brow + kh * g.bits_pitch + 1) : 0u;
+          m[j][kh] = __funnelshift_r(lo, hi, shift) & 0x0fffffffu;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kSgOwn; ++j) {
+        const int kt = set + kSgSets * j;
+        if (kt >= kt_lo && kt <= kt_hi) {
+          const int n = nchunk + kt - kt_lo;            // running chunk number -> accumulator and barrier phase
+          const int acc = n % kSgAcc;
+          mbar_wait(&t_full[acc], static_cast<uint32_t>(n / kSgAcc) & 1u);
+          tc_fence_after();
+          sg_chunk(tmem_base + lane_addr + static_cast<uint32_t>(acc * kSgChunkN), m[j], a[j]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
+      }
+      nchunk += kt_hi - kt_lo + 1;
+    }
+    if (cur_plane >= 0) flush(cur_plane);
+    // the epilogue warps publish the CTA's partial sums
+    asm volatile("bar.sync 1, %0;" ::"n"(kSgSets * 128) : "memory");
+    for (int i = threadIdx.x - 64; i < g.T * 3; i += kSgSets * 128)
+      if (sacc[i] != 0.0f) atomicAdd(&grad[i], sacc[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// wq: folded fp32 stem weights [7*7*7][3][64]; dst: [7][160][64] bf16 rows (kt, c*49 + kh*7 + kw), K = co
+void stem_grad_pack_weights(uint16_t* dst, const float* wq) {
+  memset(dst, 0, static_cast<size_t>(7) * kSgChunkN * 64 * sizeof(uint16_t));
+  for (int kt = 0; kt < 7; ++kt)
+    for (int c = 0; c < 3; ++c)
+      for (int kh = 0; kh < 7; ++kh)
+        for (int kw = 0; kw < 7; ++kw)
+          for (int co = 0; co < 64; ++co)
+            dst[(static_cast<size_t>(kt) * kSgChunkN + c * 49 + kh * 7 + kw) * 64 + co] =
+                f32_to_bf16_bits(wq[(((kt * 7 + kh) * 7 + kw) * 3 + c) * 64 + co]);
+}
+
+int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, const void* wpk, const uint32_t* bits, int B, int T,
+                   int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw) {
+  memset(L, 0, sizeof(*L));
+  FAV_CHECK_ARG(W % 8 == 0, "stem grad: W=%d must be a multiple of 8", W);
+  FAV_CHECK_ARG(ph >= 0 && ph <= 3 && pw >= 0 && pw <= 8, "stem grad: unsupported padding");
+  FAV_CHECK_ARG(2 * (Ho - 1) + 6 - ph + 3 < H + 7 && ((8 * (Wo - 1) + 32 - 4 * pw) >> 5) + 2 <= (W + 16) / 8,
+                "stem grad: bitmap too small");
+  FAV_CHECK_ARG(T * 3 * 4 <= 8192, "stem grad: T=%d too large", T);
+  L->B = B; L->T = T; L->To = To; L->Ho = Ho; L->Wo = Wo; L->pt = pt; L->ph = ph; L->pw = pw;
+  L->tiles_per_plane = ceil_div(Ho * Wo, 128);
+  L->m_tiles = B * To * L->tiles_per_plane;
+  L->bits_rows = H + 7;
+  L->bits_pitch = (W + 16) / 8;
+  L->bits = bits;
+  uint64_t dims[2] = {64, static_cast<uint64_t>(B) * To * Ho * Wo};
+  uint64_t strides[1] = {128};
+  uint32_t box[2] = {64, 128};
+  FAV_TRY(make_tmap_bf16(&L->tmA, g1, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  uint64_t bd[2] = {64, 7 * kSgChunkN};
+  uint32_t bb[2] = {64, kSgChunkN};
+  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, strides, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  L->smem_bytes = 7 * kSgBBytes + kSgStages * kSgABytes + 14 * 8 + static_cast<size_t>(T) * 3 * 4 + 1024 + 64;
+  L->grid = std::max(1, std::min(L->m_tiles, sm_count(device)));   // contiguous tile ranges: every CTA gets >= 1 tile
+  L->flops = 2.0 * static_cast<double>(B) * To * Ho * Wo * 64.0 * 7 * kSgChunkN;
+  L->bytes = static_cast<double>(B) * To * Ho * Wo * 128.0;
+  L->ready = 1;
+  return FAV_OK;
+}
+
+size_t stem_grad_bitmap_words(int B, int T, int H, int W) {
+  return static_cast<size_t>(B) * T * (H + 7) * ((W + 16) / 8);
+}
+
+int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FAV_CUDA(cudaFuncSetAttribute(stem_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  ProfScope ps(PK_STEM_BWD, stream, L.flops, L.bytes);
+  FAV_CUDA(cudaMemsetAsync(grad, 0, static_cast<size_t>(L.T) * 3 * sizeof(float), stream));
+  StemGradGeom g;
+  g.B = L.B; g.T = L.T; g.To = L.To; g.Ho = L.Ho; g.Wo = L.Wo; g.pt = L.pt; g.ph = L.ph; g.pw = L.pw;
+  g.tiles_per_plane = L.tiles_per_plane; g.m_tiles = L.m_tiles; g.bits_rows = L.bits_rows; g.bits_pitch = L.bits_pitch;
+  stem_grad_kernel<<<L.grid, kSgThreads, L.smem_bytes, stream>>>(L.tmA, L.tmB, g, L.bits, grad);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+}  // namespace fav
