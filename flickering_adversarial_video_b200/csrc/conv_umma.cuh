@@ -282,7 +282,7 @@ struct StemGradLaunch {
   CUtensorMap tmB;        // weights [7 * 160][64]
   const uint32_t* bits;   // pass nibbles written by the apply kernel
   int B, T, To, Ho, Wo, pt, ph, pw;
-  int tiles_per_plane, m_tiles, bits_rows, bits_pitch;
+  int tiles_per_plane, m_tiles, bits_rows, bits_pitch, mrows, mbytes;
   size_t smem_bytes;
   int grid;
   int ready;

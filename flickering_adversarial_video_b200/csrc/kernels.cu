@@ -96,7 +96,7 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
       }
       const long long bt = row / H;
       const int hh = static_cast<int>(row - bt * H);
-      uint32_t* dstb = pass_bits + (bt * (H + 7) + hh + 3) * ((W + 16) >> 3) + 1 + 2 * wg;
+      uint32_t* dstb = pass_bits + (bt * (H + 7) + hh + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + 2 * wg;
       dstb[0] = w0;
       dstb[1] = w1;
     }

@@ -44,6 +44,13 @@ int main() {
   cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 2000;
+  for (int N = 16; N <= 256; N += 16) {   // N sweep, aligned A, SW128
+    rate_kernel<<<148, 128, 50 * 1024 + 1024>>>(N, iters, 1, 0, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(148);
+    cudaMemcpy(h.data(), d, 148 * 8, cudaMemcpyDeviceToHost);
+    printf("N sweep: N=%3d: %.1f clk per 128xNx16 MMA (N/2 = %d)  [%s]\n", N, double(h[0]) / (iters * 4.0), N / 2, cudaGetErrorString(e));
+  }
   for (int off : {0, 1, 4, 8})
   for (int swz = 1; swz >= 0; --swz)
     for (int N : {64, 128, 192, 256}) {
