@@ -20,7 +20,7 @@ ARCHS = {"i3d": FAV_NET_I3D, "r3d_18": FAV_NET_R3D_18, "mc3_18": FAV_NET_MC3_18,
 S_ADV_LOSS, S_FOOLED, S_SUM_P_MIN, S_SUM_P_MAX = 0, 1, 2, 3
 S_NORM_REG, S_DIFF_REG, S_LAP_REG, S_THICKNESS, S_ROUGHNESS, S_TOTAL_LOSS, S_SAT_COUNT = 4, 5, 6, 7, 8, 9, 10
 S_COUNT = 16
-PROF_KINDS = ["apply", "stem_conv", "conv_halo", "conv_tap", "pool_fwd", "pool_bwd", "head_loss", "stem_bwd_reduce",
+PROF_KINDS = ["apply", "stem_conv", "conv_halo", "conv_tap", "pool_fwd", "pool_bwd", "head_loss", "stem_grad",
               "delta_update", "other"]
 
 

@@ -55,7 +55,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
                  const ConvEpilogue e,
                  const int stages, const int a_bytes, const int b_bytes, const int stage_bytes) {
-  if (g.gate_count && *g.gate_count <= g.gate_thr) return;   // uniform: before any barrier / TMEM state exists
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &

@@ -44,9 +44,6 @@ struct ConvGeom {
   int swz_base_offset; // 1: put (start>>7)&7 into the descriptor's base_offset field
   int prof;            // 1: the MMA warp records its barrier wait cycles (debug, FAV_HALO_PROF)
   int pair;            // 1: CTA-pair kernel (tcgen05 cta_group::2, conv_halo2.cu)
-  // device-side gate (generic path): the launch is a no-op unless *gate_count > gate_thr
-  const uint32_t* gate_count;
-  uint32_t gate_thr;
 };
 
 struct ConvEpilogue {

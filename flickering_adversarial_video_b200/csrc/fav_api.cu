@@ -83,14 +83,9 @@ struct fav_handle {
   // stem
   __nv_bfloat16* xpad = nullptr;
   uint16_t* stem_w = nullptr;     // packed bf16 [64][49*32]
-  float* stem_w_f32 = nullptr;    // folded fp32 [343][3][64]  (saturation corrections)
   float* stem_wc = nullptr;       // class-summed folded weights [7][16][3][64]
   float* stem_bnbias = nullptr;   // [64]
   float* stem_bias_tab = nullptr; // [To][16][64]
-  float* stem_S = nullptr;        // [To][16][64]
-  uint32_t* sat_list = nullptr;
-  uint32_t* sat_count = nullptr;
-  uint32_t sat_capacity = 0;
   StemLaunch stem_fwd;
   int y1 = -1;                    // buffer id of the stem output
   float last_adv_flag = 1.0f;
@@ -122,8 +117,8 @@ struct fav_handle {
   float* pix_partial = nullptr;
   uint32_t* pass_bits = nullptr;  // I3D: pass nibbles of the range clip (stem_grad.cu)
   uint16_t* stem_gw = nullptr;    // I3D: stem weights as the [7*160][64] B operand of the gradient collapse
-  StemGradLaunch stem_gd;         // I3D: tensor-core gradient collapse (FAV_STEM_GRAD_LEGACY=1 restores class sums + corrections)
-  uint32_t dense_sat_thr = 0xffffffffu;   // saturated pixels above which the dense stem data gradient replaces the sparse corrections
+  StemGradLaunch stem_gd;         // I3D: tensor-core gradient collapse
+  bool stem_grad_dense = false;   // FAV_STEM_GRAD_DENSE=1 (tests): dense stem data gradient + masked reduce instead
 };
 
 namespace {
@@ -354,14 +349,9 @@ int build_i3d(fav_handle* h) {
   h->Wp = round_up(h->Wp, 2);
   FAV_TRY(dev_alloc(h, &h->xpad, static_cast<size_t>(B) * T * H * h->Wp * 4));
   FAV_TRY(dev_alloc(h, &h->stem_w, static_cast<size_t>(64) * 49 * 32));
-  FAV_TRY(dev_alloc(h, &h->stem_w_f32, static_cast<size_t>(343) * 3 * 64));
   FAV_TRY(dev_alloc(h, &h->stem_wc, static_cast<size_t>(7) * 16 * 3 * 64));
   FAV_TRY(dev_alloc(h, &h->stem_bnbias, 64));
   FAV_TRY(dev_alloc(h, &h->stem_bias_tab, static_cast<size_t>(h->To) * 16 * 64));
-  FAV_TRY(dev_alloc(h, &h->stem_S, static_cast<size_t>(h->To) * 16 * 64));
-  h->sat_capacity = static_cast<uint32_t>(static_cast<long long>(B) * T * H * W);
-  FAV_TRY(dev_alloc(h, &h->sat_list, static_cast<size_t>(h->sat_capacity), false));
-  FAV_TRY(dev_alloc(h, &h->sat_count, 4));
 
   h->y1 = add_buf(h, "Conv3d_1a_7x7", h->To, h->Ho, h->Wo, 64, false);
   if (h->y1 < 0) return FAV_ERR_CUDA;
@@ -487,8 +477,8 @@ int bn_fold(const NamedTensors& nt, const std::string& unit, int cout, std::vect
 
 namespace {
 // Dense data gradient of Conv3d_1a_7x7 (7^3, stride 2, TF SAME pad_before 2) as 8 parity-class GEMMs into
-// rn.dx [B,T,H,W,16]: the per-pixel attack needs it, and the flickering attack falls back to it when so many
-// entries are range-clipped that per-entry corrections would cost more (dense_sat_thr).
+// rn.dx [B,T,H,W,16]: the per-pixel attack needs dL/dX itself.  The flickering attack never materialises it
+// (stem_grad.cu); FAV_STEM_GRAD_DENSE=1 routes it through this path + the masked reduce as an independent check.
 int i3d_plan_dense_stem(fav_handle* h) {
   ResNet& rn = h->rn;
   FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(h->B) * h->T * h->H * h->W * 16));
@@ -498,17 +488,11 @@ int i3d_plan_dense_stem(fav_handle* h) {
   FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(h->B) * h->T * stem_dx_reduce_chunks(h->H) * 3));
   h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
   for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
-  h->stem_gd.ready = 0;
-  if (!getenv("FAV_STEM_GRAD_LEGACY")) {
-    FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(h->B, h->T, h->H, h->W)));
-    FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(7) * 160 * 64));
-    FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
-                           h->Wo, h->pt, h->ph, h->pw));
-  }
-  double frac = 0.06;
-  if (const char* ev = getenv("FAV_DENSE_SAT_FRAC")) frac = atof(ev);
-  const double px = static_cast<double>(h->B) * h->T * h->H * h->W;
-  h->dense_sat_thr = frac >= 1.0 ? 0xffffffffu : static_cast<uint32_t>(frac * px);
+  FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(h->B, h->T, h->H, h->W)));
+  FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(7) * 160 * 64));
+  FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
+                         h->Wo, h->pt, h->ph, h->pw));
+  h->stem_grad_dense = getenv("FAV_STEM_GRAD_DENSE") != nullptr;
   return FAV_OK;
 }
 }  // namespace
@@ -664,8 +648,7 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
         FAV_CUDA(cudaMemcpy(d.w, dpk.data(), dpk.size() * 2, cudaMemcpyHostToDevice));
       }
     }
-    FAV_CUDA(cudaMemcpy(h->stem_w_f32, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice));
-    if (h->stem_gd.ready) {
+    {
       std::vector<uint16_t> gw(static_cast<size_t>(7) * 160 * 64);
       stem_grad_pack_weights(gw.data(), wq.data());
       FAV_CUDA(cudaMemcpy(h->stem_gw, gw.data(), gw.size() * 2, cudaMemcpyHostToDevice));
@@ -735,12 +718,8 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
                                 h->pt, h->rn.stem_KT, 1, C1, cst, ds, s));
     return FAV_OK;
   }
-  if (h->stem_gd.ready)
-    FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32,
-                         nullptr, 0, nullptr, h->B, h->T, h->H, h->W, s, h->pass_bits));
-  else
-    FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32,
-                         h->sat_list, h->sat_capacity, h->sat_count, h->B, h->T, h->H, h->W, s));
+  FAV_TRY(launch_apply(clip, in_dtype, delta, adv_flag, delta_clip, h->xpad, h->Wp, h->pw, adv_u8, adv_f32, h->pass_bits,
+                       h->B, h->T, h->H, h->W, s));
   FAV_TRY(launch_stem_bias(delta, adv_flag, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T,
                            h->To, h->pt, s));
   return FAV_OK;
@@ -839,28 +818,13 @@ extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->d.arch != FAV_NET_I3D) return resnet_backward(h, grad, s);
   FAV_TRY(i3d_backward_to_stem(h, s));
-  // stem: collapse over B,H,W without materialising dL/dx
-  if (h->stem_gd.ready) return stem_grad_launch(h->stem_gd, grad, s);
-  const Buf& y1 = h->bufs[h->y1];
-  FAV_TRY(launch_stem_class_sums(y1.g, h->stem_S, h->B, h->To, h->Ho, h->Wo, s));
-  FAV_TRY(launch_stem_grad_delta(h->stem_S, h->stem_wc, grad, h->T, h->To, h->pt, s));
-  // few range-clipped entries: exact per-entry corrections; many (dark / bright video, large delta): the dense stem
-  // data gradient + masked reduce recompute the sum.  Both sides test the device-side count, so the step stays
-  // graph-capturable.
-  const uint32_t thr = h->last_clip_u8 ? h->dense_sat_thr : 0xffffffffu;
-  FAV_TRY(launch_stem_sat_correction(y1.g, h->stem_w_f32, h->sat_list, h->sat_count, h->sat_capacity, thr, grad,
-                                     h->B, h->T, h->H, h->W, h->To, h->Ho, h->Wo, h->pt, h->ph, h->pw, s));
-  if (thr != 0xffffffffu) {
-    for (const DgradClass& d : h->rn.stem_dg) {
-      ConvLaunch L = d.L;
-      L.g.gate_count = h->sat_count;
-      L.g.gate_thr = thr;
-      FAV_TRY(conv_launch(L, s));
-    }
-    FAV_TRY(launch_stem_dx_reduce(h->rn.dx, h->last_clip_u8, h->last_delta, h->last_adv_flag, h->last_delta_clip, h->nrm, 0,
-                                  h->rn.partial, grad, h->B, h->T, h->H, h->W, s, h->sat_count, thr));
-  }
-  return FAV_OK;
+  // stem: collapse over B,H,W without materialising dL/dx (stem_grad.cu)
+  if (!h->stem_grad_dense) return stem_grad_launch(h->stem_gd, grad, s);
+  // test switch: dense stem data gradient + masked reduce (an independent formulation of the same sum)
+  FAV_CHECK_ARG(h->last_clip_u8 != nullptr, "FAV_STEM_GRAD_DENSE needs a uint8 clip");
+  for (const DgradClass& d : h->rn.stem_dg) FAV_TRY(conv_launch(d.L, s));
+  return launch_stem_dx_reduce(h->rn.dx, h->last_clip_u8, h->last_delta, h->last_adv_flag, h->last_delta_clip, h->nrm, 0,
+                               h->rn.partial, grad, h->B, h->T, h->H, h->W, s);
 }
 
 static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s) {

@@ -21,13 +21,11 @@ __global__ void __launch_bounds__(256)
 apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, float adv_flag,
              float dclip, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
              uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
-             uint32_t* __restrict__ sat_list, uint32_t sat_capacity, uint32_t* __restrict__ sat_count,
              uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = gid < groups;
   const int gpr = W >> 4;
   uint32_t sat_mask[16];
-  int nsat = 0;
   long long row = 0;
   int wg = 0;
   if (active) {
@@ -78,7 +76,6 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
         m |= sat ? (1u << c) : 0u;
       }
       sat_mask[p] = m;
-      nsat += (m != 0);
       xq[2 * p] = pack_bf16x2(q[0], q[1]);
       xq[2 * p + 1] = pack_bf16x2(q[2], 0.0f);
     }
@@ -122,52 +119,23 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
       for (int i = 0; i < 12; ++i) df[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
     }
   }
-  // warp-aggregated append of saturated pixels
-  if (sat_list) {
-    const int lane = threadIdx.x & 31;
-    int incl = nsat;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total > 0) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(sat_count, static_cast<uint32_t>(total));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      uint32_t pos = base + static_cast<uint32_t>(incl - nsat);
-      if (nsat > 0) {
-        const uint32_t pix0 = static_cast<uint32_t>(row * W + wg * 16);
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          if (sat_mask[p]) {
-            if (pos < sat_capacity) sat_list[pos] = (pix0 + p) | (sat_mask[p] << 28);
-            ++pos;
-          }
-        }
-      }
-    }
-  }
 }
 
 int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
                  __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
-                 uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
-                 int W, cudaStream_t s, uint32_t* pass_bits) {
+                 uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s) {
   ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 * (in_dtype == FAV_F32 ? 4 : 1) + 8.0 + (adv_u8 ? 3.0 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   FAV_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 28), "apply: too many pixels per call");
   const long long groups = static_cast<long long>(B) * T * H * (W / 16);
   const int block = 256;
   const int grid = static_cast<int>(ceil_div64(groups, block));
-  if (sat_count) FAV_CUDA(cudaMemsetAsync(sat_count, 0, sizeof(uint32_t), s));
   if (in_dtype == FAV_F32)
     apply_kernel<true><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
-                                              adv_f32, sat_list, sat_capacity, sat_count, pass_bits, T, H, W, groups);
+                                              adv_f32, pass_bits, T, H, W, groups);
   else
     apply_kernel<false><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
-                                               adv_f32, sat_list, sat_capacity, sat_count, pass_bits, T, H, W, groups);
+                                               adv_f32, pass_bits, T, H, W, groups);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -316,10 +284,8 @@ constexpr int kRedRows = 8;
 __global__ void __launch_bounds__(256)
 stem_dx_reduce_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __restrict__ clip,
                       const float* __restrict__ delta, float adv_flag, float dclip, const fav_norm_params nrm,
-                      int torch_mode, float* __restrict__ partial, int T, int H, int W, int chunks,
-                      const uint32_t* __restrict__ gate_count, uint32_t gate_thr) {
+                      int torch_mode, float* __restrict__ partial, int T, int H, int W, int chunks) {
   __shared__ float red[8][3];
-  if (gate_count && *gate_count <= gate_thr) return;
   const int chunk = blockIdx.x % chunks;
   const int t = blockIdx.x / chunks;
   const int b = blockIdx.y;
@@ -364,9 +330,7 @@ stem_dx_reduce_kernel(const __nv_bfloat16* __restrict__ dx, const uint8_t* __res
 }
 
 __global__ void stem_dx_final_kernel(const float* __restrict__ partial, float* __restrict__ grad, int B, int T,
-                                     int chunks, float s0, float s1, float s2, const uint32_t* __restrict__ gate_count,
-                                     uint32_t gate_thr) {
-  if (gate_count && *gate_count <= gate_thr) return;
+                                     int chunks, float s0, float s1, float s2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * 3) return;
   const int t = i / 3, c = i - t * 3;
@@ -378,16 +342,16 @@ __global__ void stem_dx_final_kernel(const float* __restrict__ partial, float* _
 
 int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
                           float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
-                          int B, int T, int H, int W, cudaStream_t s, const uint32_t* gate_count, uint32_t gate_thr) {
+                          int B, int T, int H, int W, cudaStream_t s) {
   ProfScope ps(PK_STEM_BWD, s, 0.0, static_cast<double>(B) * T * H * W * 9.0);
   const int chunks = ceil_div(H, kRedRows);
   stem_dx_reduce_kernel<<<dim3(T * chunks, B), 256, 0, s>>>(dx, clip, delta, adv_flag, delta_clip, nrm, torch_mode,
-                                                            partial, T, H, W, chunks, gate_count, gate_thr);
+                                                            partial, T, H, W, chunks);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   const float s0 = torch_mode ? 1.0f / nrm.std[0] : 1.0f, s1 = torch_mode ? 1.0f / nrm.std[1] : 1.0f,
               s2 = torch_mode ? 1.0f / nrm.std[2] : 1.0f;
-  stem_dx_final_kernel<<<ceil_div(T * 3, 128), 128, 0, s>>>(partial, grad, B, T, chunks, s0, s1, s2, gate_count, gate_thr);
+  stem_dx_final_kernel<<<ceil_div(T * 3, 128), 128, 0, s>>>(partial, grad, B, T, chunks, s0, s1, s2);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -919,223 +883,6 @@ int launch_loss(const float* logits, const int64_t* labels, const fav_loss_param
                 float* probs, float* dlogits, float* scalars, cudaStream_t s) {
   ProfScope ps(PK_HEAD_LOSS, s);
   loss_kernel<<<1, 512, 2 * K * sizeof(float), s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
-  FAV_COUNT_LAUNCH();
-  FAV_CUDA(cudaGetLastError());
-  return FAV_OK;
-}
-
-// =============================================================================================
-// stem backward without materialising dL/dx:
-//   g[t,c] = sum_{b,h,w} mask * dX  with dX = stem^T(G1).  By linearity the unmasked sum only needs
-//   the per-(t_o, border-class) sums S of G1; the (few) saturated entries are corrected exactly.
-// =============================================================================================
-__device__ __forceinline__ int border_class(int i, int n) {
-  return i == 0 ? 0 : (i == n - 2 ? 2 : (i == n - 1 ? 3 : 1));
-}
-// general form: the first nlo and the last nhi outputs touch the zero padding (nlo + nhi <= 3)
-__device__ __forceinline__ int stem_border_class(int o, int n, int nlo, int nhi) {
-  return o < nlo ? o : (o >= n - nhi ? nlo + 1 + (o - (n - nhi)) : nlo);
-}
-
-// block = (b, t_o, chunk of kClassRows output rows); thread = (8-channel group, position lane).
-// Rows of one H class accumulate in registers; a class change (only at the plane borders) flushes.
-constexpr int kClassRows = 8;
-__global__ void __launch_bounds__(256)
-stem_class_sums_kernel(const __nv_bfloat16* __restrict__ g1, float* __restrict__ S, int To, int Ho, int Wo,
-                       int nlo_h, int nhi_h, int nlo_w, int nhi_w) {
-  __shared__ float red[32][4][64];
-  const int chunks = (Ho + kClassRows - 1) / kClassRows;
-  const int hchunk = blockIdx.x % chunks;
-  const int to = blockIdx.x / chunks;
-  const int b = blockIdx.y;
-  const int cgp = threadIdx.x & 7;   // 8-channel group
-  const int pl = threadIdx.x >> 3;   // position lane 0..31
-  float acc[4][8];
-  auto zero = [&]() {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[k][j] = 0.0f;
-  };
-  auto flush = [&](int hc) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) red[pl][k][cgp * 8 + j] = acc[k][j];
-    __syncthreads();
-    {
-      const int k = threadIdx.x >> 6, co = threadIdx.x & 63;
-      float sum = 0.0f;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) sum += red[q][k][co];
-      if (sum != 0.0f) atomicAdd(&S[((to * 4 + hc) * 4 + k) * 64 + co], sum);
-    }
-    __syncthreads();
-  };
-  zero();
-  const int h_begin = hchunk * kClassRows, h_end = min(Ho, h_begin + kClassRows);
-  int cur = stem_border_class(h_begin, Ho, nlo_h, nhi_h);
-  for (int ho = h_begin; ho < h_end; ++ho) {
-    const int hc = stem_border_class(ho, Ho, nlo_h, nhi_h);
-    if (hc != cur) {   // block-uniform
-      flush(cur);
-      zero();
-      cur = hc;
-    }
-    const __nv_bfloat16* rowp = g1 + (((static_cast<long long>(b) * To + to) * Ho + ho) * Wo) * 64;
-#pragma unroll 4
-    for (int w = pl; w < Wo; w += 32) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long long>(w) * 64 + cgp * 8));
-      const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                          bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
-      const int wc = stem_border_class(w, Wo, nlo_w, nhi_w);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k == wc) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[k][j] += f[j];
-        }
-    }
-  }
-  flush(cur);
-}
-
-int launch_stem_class_sums(const __nv_bfloat16* g1, float* S, int B, int To, int Ho, int Wo, cudaStream_t s) {
-  ProfScope ps(PK_STEM_BWD, s, 0.0, static_cast<double>(B) * To * Ho * Wo * 128.0);
-  FAV_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(To) * 16 * 64 * sizeof(float), s));
-  dim3 grid(To * ceil_div(Ho, kClassRows), B);
-  stem_class_sums_kernel<<<grid, 256, 0, s>>>(g1, S, To, Ho, Wo, 1, 2, 1, 2);
-  FAV_COUNT_LAUNCH();
-  FAV_CUDA(cudaGetLastError());
-  return FAV_OK;
-}
-
-__global__ void __launch_bounds__(256)
-stem_grad_delta_kernel(const float* __restrict__ S, const float* __restrict__ wc, float* __restrict__ grad,
-                       int T, int To, int pt) {
-  __shared__ float sh[8];
-  const int t = blockIdx.x / 3, c = blockIdx.x % 3;
-  float acc = 0.0f;
-  for (int kt = 0; kt < 7; ++kt) {
-    const int tt = t + pt - kt;
-    if (tt < 0 || (tt & 1)) continue;
-    const int to = tt >> 1;
-    if (to >= To) continue;
-    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
-      const int cls = i >> 6, co = i & 63;
-      acc = fmaf(wc[((kt * 16 + cls) * 3 + c) * 64 + co], S[(to * 16 + cls) * 64 + co], acc);
-    }
-  }
-  acc = block_reduce<float>(acc, sh, false);
-  if (threadIdx.x == 0) grad[t * 3 + c] = acc;
-  (void)T;
-}
-
-int launch_stem_grad_delta(const float* S, const float* wc, float* grad, int T, int To, int pt,
-                           cudaStream_t s) {
-  ProfScope ps(PK_STEM_BWD, s);
-  stem_grad_delta_kernel<<<T * 3, 256, 0, s>>>(S, wc, grad, T, To, pt);
-  FAV_COUNT_LAUNCH();
-  FAV_CUDA(cudaGetLastError());
-  return FAV_OK;
-}
-
-// one warp per saturated pixel: recompute dX there exactly (gather over the <= 64 valid taps) and
-// subtract it from g[t,c].  The folded stem weights sit in shared memory as fp32 pairs per lane.
-__global__ void __launch_bounds__(512, 1)
-stem_sat_correction_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ w,
-                           const uint32_t* __restrict__ sat_list, const uint32_t* __restrict__ sat_count,
-                           uint32_t sat_capacity, uint32_t dense_thr, float* __restrict__ grad, int T, int H, int W, int To,
-                           int Ho, int Wo, int pt, int ph, int pw) {
-  extern __shared__ float smem_f[];
-  __nv_bfloat162* sw = reinterpret_cast<__nv_bfloat162*>(smem_f);   // [343][3][32] channel pairs
-  float* sacc = smem_f + 343 * 3 * 32;                                // [T*3]
-  const uint32_t n = min(*sat_count, sat_capacity);
-  if (n > dense_thr) return;                                         // the dense path computes the masked sum instead
-  if (blockIdx.x * (blockDim.x >> 4) >= n) return;                   // nothing for this block
-  for (int i = threadIdx.x; i < 343 * 3 * 32; i += blockDim.x)
-    sw[i] = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
-  for (int i = threadIdx.x; i < T * 3; i += blockDim.x) sacc[i] = 0.0f;
-  __syncthreads();
-  // half a warp per entry: 16 lanes x 4 channels; two entries in flight per warp
-  const int hl = threadIdx.x & 15;
-  const uint32_t halves_total = gridDim.x * (blockDim.x >> 4);
-  const uint32_t n_round = (n + 1u) & ~1u;   // both halves of a warp iterate the same number of times
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); e < n_round; e += halves_total) {
-    const bool live = e < n;
-    const uint32_t ent = live ? sat_list[e] : 0u;
-    const uint32_t cm = ent >> 28;
-    uint32_t pix = ent & 0x0fffffffu;
-    const int wx = pix % W; pix /= W;
-    const int hx = pix % H; pix /= H;
-    const int tx = pix % T;
-    const int b = pix / T;
-    const int at = tx + pt, ah = hx + ph, aw = wx + pw;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-    if (live) {
-      // the <= 4x4 in-plane taps of one temporal tap are gathered with all 16 loads in flight (the kernel is a
-      // chain of L2 latencies otherwise)
-      for (int kt = at & 1; kt < 7 && kt <= at; kt += 2) {
-        const int to = (at - kt) >> 1;
-        if (to >= To) continue;
-        const __nv_bfloat16* gplane = g1 + ((static_cast<long long>(b) * To + to) * Ho) * Wo * 64;
-        uint2 gv[16];
-        bool ok[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int kh = (ah & 1) + 2 * (j >> 2), kw = (aw & 1) + 2 * (j & 3);
-          const int ho = (ah - kh) >> 1, wo = (aw - kw) >> 1;
-          ok[j] = kh < 7 && kh <= ah && ho < Ho && kw < 7 && kw <= aw && wo < Wo;
-          gv[j] = ok[j] ? __ldg(reinterpret_cast<const uint2*>(gplane + (static_cast<long long>(ho) * Wo + wo) * 64) + hl)
-                        : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (!ok[j]) continue;
-          const int kh = (ah & 1) + 2 * (j >> 2), kw = (aw & 1) + 2 * (j & 3);
-          const float g0 = bf16_lo(gv[j].x), g1v = bf16_hi(gv[j].x), g2 = bf16_lo(gv[j].y), g3 = bf16_hi(gv[j].y);
-          const __nv_bfloat162* wp = sw + ((kt * 7 + kh) * 7 + kw) * 96 + hl * 2;
-          float2 u, v;
-          u = __bfloat1622float2(wp[0]); v = __bfloat1622float2(wp[1]);
-          a0 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a0))));
-          u = __bfloat1622float2(wp[32]); v = __bfloat1622float2(wp[33]);
-          a1 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a1))));
-          u = __bfloat1622float2(wp[64]); v = __bfloat1622float2(wp[65]);
-          a2 = fmaf(g0, u.x, fmaf(g1v, u.y, fmaf(g2, v.x, fmaf(g3, v.y, a2))));
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (hl == 0 && live) {
-      if (cm & 1u) atomicAdd(&sacc[tx * 3 + 0], -a0);
-      if (cm & 2u) atomicAdd(&sacc[tx * 3 + 1], -a1);
-      if (cm & 4u) atomicAdd(&sacc[tx * 3 + 2], -a2);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * 3; i += blockDim.x)
-    if (sacc[i] != 0.0f) atomicAdd(&grad[i], sacc[i]);
-}
-
-int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w, const uint32_t* sat_list,
-                               const uint32_t* sat_count, uint32_t sat_capacity, uint32_t dense_thr, float* grad, int B, int T,
-                               int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw, cudaStream_t s) {
-  ProfScope ps(PK_STEM_BWD, s);
-  (void)B;
-  const size_t smem = static_cast<size_t>(343) * 3 * 32 * sizeof(float) + static_cast<size_t>(T) * 3 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FAV_CUDA(cudaFuncSetAttribute(stem_sat_correction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
-  FAV_CHECK_ARG(smem <= 160 * 1024, "sat correction: T=%d too large", T);
-  stem_sat_correction_kernel<<<148, 512, smem, s>>>(g1, w, sat_list, sat_count, sat_capacity, dense_thr, grad, T, H, W, To,
-                                                     Ho, Wo, pt, ph, pw);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

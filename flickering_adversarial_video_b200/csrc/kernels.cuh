@@ -13,12 +13,11 @@ struct PoolGeom {
 PoolGeom make_pool_geom(int B, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh, int sw);
 
 // (a) flicker apply. Writes the stem input x' (bf16 RGBX, W padded) and optionally the uint8 /
-// fp32 adversarial video; appends saturated entries to sat_list (count in *sat_count) and / or writes the pass
-// nibbles of stem_grad.cu (pass_bits: rows of (W + 16) / 8 words, H + 7 rows per frame, zero borders).
+// fp32 adversarial video; with pass_bits, the pass nibbles of stem_grad.cu (bit c of pixel nibble = entry (pixel, c)
+// was not range-clipped; rows of round_up((W + 16) / 8, 4) words, H + 7 rows per frame, zero borders).
 int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
                  __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
-                 uint32_t* sat_list, uint32_t sat_capacity, uint32_t* sat_count, int B, int T, int H,
-                 int W, cudaStream_t s, uint32_t* pass_bits = nullptr);
+                 uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s);
 
 // delta-dependent stem bias table [To][4][4][64]
 int launch_stem_bias(const float* delta, float adv_flag, float delta_clip, const float* wc /*[7][16][3][64]*/,
@@ -36,8 +35,7 @@ int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, 
 // (c) dense reduce of the stem data gradient dX [B,T,H,W,16] bf16 into grad [T,3] with the recomputed clip mask
 int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,
                           float delta_clip, const fav_norm_params& nrm, int torch_mode, float* partial, float* grad,
-                          int B, int T, int H, int W, cudaStream_t s, const uint32_t* gate_count = nullptr,
-                          uint32_t gate_thr = 0);
+                          int B, int T, int H, int W, cudaStream_t s);
 int stem_dx_reduce_chunks(int H);
 
 // sparse per-pixel attack: apply with delta [T,H,W,3], per-pixel gradient, L1,2 regulariser + Adam
@@ -78,16 +76,6 @@ int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfl
 
 int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
                 float* probs, float* dlogits, float* scalars, cudaStream_t s);
-
-// stem backward: class sums of G1, then g[T,3], then saturated-entry corrections
-int launch_stem_class_sums(const __nv_bfloat16* g1, float* S /*[To][16][64]*/, int B, int To, int Ho,
-                           int Wo, cudaStream_t s);
-int launch_stem_grad_delta(const float* S, const float* wc, float* grad /*[T][3]*/, int T, int To, int pt,
-                           cudaStream_t s);
-int launch_stem_sat_correction(const __nv_bfloat16* g1, const float* w /*[343][3][64] folded*/,
-                               const uint32_t* sat_list, const uint32_t* sat_count, uint32_t sat_capacity,
-                               uint32_t dense_thr, float* grad, int B, int T, int H, int W, int To, int Ho, int Wo, int pt,
-                               int ph, int pw, cudaStream_t s);
 
 int launch_delta_update(float* delta, const float* grad, float* m, float* v, int64_t* step,
                         const fav_reg_params& reg, const fav_adam_params& adam, float adv_flag,

@@ -308,9 +308,10 @@ def test_delta_update_matches_oracle(setup):
     assert int(step.item()) == 5
 
 
-def test_dense_saturation_fallback_matches_sparse_corrections(setup, monkeypatch):
-    """Heavily saturated clips switch the stem backward from per-entry corrections to the dense stem data gradient +
-    masked reduce (device-side gate).  Both must give the same dL/d-delta."""
+def test_stem_gradient_collapse_matches_dense_data_gradient(setup, monkeypatch):
+    """dL/d-delta through the stem comes from one tensor-core kernel that never materialises dL/dX (stem_grad.cu).
+    FAV_STEM_GRAD_DENSE=1 computes the same sum the long way (dense stem data gradient, then a masked reduce that
+    re-derives the range-clip mask from the uint8 clip).  Heavily saturated clips: both must agree."""
     from flickering_adversarial_video_b200 import synthetic
     from flickering_adversarial_video_b200.engine import FlickerEngine
     B = setup["B"]
@@ -318,8 +319,11 @@ def test_dense_saturation_fallback_matches_sparse_corrections(setup, monkeypatch
     delta = synthetic.delta_uniform(T_SMALL, seed=8).cuda()
     labels = None
     grads = []
-    for frac in ("1.0", "0.0"):          # never dense / always dense
-        monkeypatch.setenv("FAV_DENSE_SAT_FRAC", frac)
+    for dense in (False, True):
+        if dense:
+            monkeypatch.setenv("FAV_STEM_GRAD_DENSE", "1")
+        else:
+            monkeypatch.delenv("FAV_STEM_GRAD_DENSE", raising=False)
         eng = FlickerEngine(B, T_SMALL)
         eng.load_weights(setup["weights"])
         eng.apply(clip, delta)
@@ -333,5 +337,5 @@ def test_dense_saturation_fallback_matches_sparse_corrections(setup, monkeypatch
     a, b = grads
     cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
     rel = float((a - b).norm() / a.norm())
-    _report(f"dense-saturation fallback vs sparse corrections: cosine {cos:.6f}, rel L2 {rel:.3e}")
+    _report(f"stem gradient collapse vs dense data gradient + masked reduce: cosine {cos:.6f}, rel L2 {rel:.3e}")
     assert cos >= 0.9999 and rel <= 1e-2
