@@ -276,9 +276,10 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream);
 // ---- stem gradient collapse on the tensor cores (stem_grad.cu) ----
 struct StemGradLaunch {
   CUtensorMap tmA;        // g1 as a flat [positions][64] matrix
-  CUtensorMap tmB;        // weights [7 * 160][64]
+  CUtensorMap tmB;        // weights [KT * 160][64]
   const uint32_t* bits;   // pass nibbles written by the apply kernel
-  int B, T, To, Ho, Wo, pt, ph, pw;
+  int B, T, To, Ho, Wo, pt, ph, pw, KT, st;
+  float scale[3];
   int tiles_per_plane, m_tiles, bits_rows, bits_pitch, mrows, mbytes;
   size_t smem_bytes;
   int grid;
@@ -286,9 +287,9 @@ struct StemGradLaunch {
   double flops, bytes;
 };
 size_t stem_grad_bitmap_words(int B, int T, int H, int W);
-void stem_grad_pack_weights(uint16_t* dst /*[7][160][64]*/, const float* wq /*[343][3][64]*/);
-int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, const void* wpk, const uint32_t* bits, int B, int T,
-                   int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw);
+void stem_grad_pack_weights(uint16_t* dst /*[KT][160][64]*/, const float* wq /*[KT*49][3][C]*/, int KT, int C);
+int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, int g1_cs, const void* wpk, const uint32_t* bits, int B,
+                   int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3);
 int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream);
 
 // Host-side weight packing (bf16 bits in uint16_t).

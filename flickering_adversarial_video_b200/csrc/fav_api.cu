@@ -115,9 +115,9 @@ struct fav_handle {
   const float* last_delta_px = nullptr;
   float* zero_delta = nullptr;     // [T,3] zeros: the stem bias table without a per-frame delta
   float* pix_partial = nullptr;
-  uint32_t* pass_bits = nullptr;  // I3D: pass nibbles of the range clip (stem_grad.cu)
-  uint16_t* stem_gw = nullptr;    // I3D: stem weights as the [7*160][64] B operand of the gradient collapse
-  StemGradLaunch stem_gd;         // I3D: tensor-core gradient collapse
+  uint32_t* pass_bits = nullptr;  // pass nibbles of the range clip (stem_grad.cu)
+  uint16_t* stem_gw = nullptr;    // stem weights as the [KT*160][64] B operand of the gradient collapse
+  StemGradLaunch stem_gd;         // tensor-core gradient collapse through the stem
   bool stem_grad_dense = false;   // FAV_STEM_GRAD_DENSE=1 (tests): dense stem data gradient + masked reduce instead
 };
 
@@ -490,8 +490,8 @@ int i3d_plan_dense_stem(fav_handle* h) {
   for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
   FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(h->B, h->T, h->H, h->W)));
   FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(7) * 160 * 64));
-  FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
-                         h->Wo, h->pt, h->ph, h->pw));
+  FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, y1.cs, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
+                         h->Wo, 7, 2, h->pt, h->ph, h->pw, nullptr));
   h->stem_grad_dense = getenv("FAV_STEM_GRAD_DENSE") != nullptr;
   return FAV_OK;
 }
@@ -650,7 +650,7 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
     }
     {
       std::vector<uint16_t> gw(static_cast<size_t>(7) * 160 * 64);
-      stem_grad_pack_weights(gw.data(), wq.data());
+      stem_grad_pack_weights(gw.data(), wq.data(), 7, 64);
       FAV_CUDA(cudaMemcpy(h->stem_gw, gw.data(), gw.size() * 2, cudaMemcpyHostToDevice));
     }
     // class-summed weights: Wc[kt][hc][wc][c][co] = sum over kh valid for hc, kw valid for wc
@@ -707,7 +707,7 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
     // torch stack: Perturbation.forward (model.py:80-96); adv_f32 is NCTHW like the reference's tensors
     FAV_CHECK_ARG(in_dtype == FAV_U8 && adv_u8 == nullptr, "torch-stack apply takes a uint8 clip and has no uint8 output");
     FAV_TRY(launch_apply_torch(static_cast<const uint8_t*>(clip), delta, adv_flag, delta_clip, h->nrm, h->xpad, h->Wp,
-                               h->pw, adv_f32, h->B, h->T, h->H, h->W, s));
+                               h->pw, adv_f32, h->pass_bits, h->B, h->T, h->H, h->W, s));
     const int C1 = round_up(h->rn.stem_C, 16);
     float cst[3], ds[3];
     for (int c = 0; c < 3; ++c) {

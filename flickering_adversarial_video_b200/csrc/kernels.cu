@@ -203,7 +203,7 @@ int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, co
 __global__ void __launch_bounds__(256)
 apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ delta, float adv_flag, float dclip,
                    const fav_norm_params nrm, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
-                   float* __restrict__ adv_f32, int T, int H, int W, long long groups) {
+                   float* __restrict__ adv_f32, uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= groups) return;
   const int gpr = W >> 4;
@@ -228,6 +228,7 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
   }
   uint32_t xq[32];
   float a[48];
+  uint32_t pw0 = 0, pw1 = 0;   // pass nibbles of pixels 0-7 / 8-15
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     float q[3];
@@ -241,6 +242,7 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
       a[e] = av;
       const bool sat = (sv < nrm.lo) || (sv > nrm.hi);
       q[c] = (sat ? ((av - d[c]) * nrm.std[c] + nrm.mean[c]) * 255.0f : u) - 128.0f;   // centred uint8 units
+      if (!sat) { if (p < 8) pw0 |= 1u << (4 * p + c); else pw1 |= 1u << (4 * (p - 8) + c); }
     }
     xq[2 * p] = pack_bf16x2(q[0], q[1]);
     xq[2 * p + 1] = pack_bf16x2(q[2], 0.0f);
@@ -249,6 +251,11 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
   uint2* dst = reinterpret_cast<uint2*>(xpad + (row * Wp + padl + wg * 16) * 4);
 #pragma unroll
   for (int i = 0; i < 16; ++i) dst[i] = make_uint2(xq[2 * i], xq[2 * i + 1]);
+  if (pass_bits) {   // same bitmap as apply_kernel (stem_grad.cu)
+    uint32_t* dstb = pass_bits + ((b * T + t) * (H + 7) + h + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + 2 * wg;
+    dstb[0] = pw0;
+    dstb[1] = pw1;
+  }
   if (adv_f32) {   // NCTHW like the torch tensors of the reference
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -261,13 +268,13 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
 }
 
 int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
-                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32, int B,
-                       int T, int H, int W, cudaStream_t s) {
+                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32,
+                       uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s) {
   ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   const long long groups = static_cast<long long>(B) * T * H * (W / 16);
   apply_torch_kernel<<<static_cast<int>(ceil_div64(groups, 256)), 256, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm,
-                                                                                xpad, Wp, padl, adv_f32, T, H, W, groups);
+                                                                                xpad, Wp, padl, adv_f32, pass_bits, T, H, W, groups);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -29,8 +29,8 @@ int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, co
 
 // torch-stack apply (uint8 NTHWC clip -> stem input in uint8 units; adv_f32 optional, NCTHW)
 int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
-                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32, int B,
-                       int T, int H, int W, cudaStream_t s);
+                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32,
+                       uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s);
 
 // (c) dense reduce of the stem data gradient dX [B,T,H,W,16] bf16 into grad [T,3] with the recomputed clip mask
 int launch_stem_dx_reduce(const __nv_bfloat16* dx, const uint8_t* clip, const float* delta, float adv_flag,

@@ -246,14 +246,6 @@ int build_resnet(fav_handle* h) {
                                1, 2, 2, rn.stem_pt, 3, 3, 3.0, rn.stem_C));
   }
   FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(B) * T * stem_dx_reduce_chunks(H) * 3));
-  // ---- head: AdaptiveAvgPool3d(1) + Linear(512, K) ----
-  const int C5 = h->bufs[rn.final_buf].C;
-  FAV_TRY(dev_alloc(h, &h->head_w, static_cast<size_t>(C5) * h->K));
-  FAV_TRY(dev_alloc(h, &h->head_b, static_cast<size_t>(h->K)));
-  FAV_TRY(dev_alloc(h, &h->feat, static_cast<size_t>(B) * C5));
-  FAV_TRY(dev_alloc(h, &h->dfeat, static_cast<size_t>(B) * C5));
-  FAV_TRY(dev_alloc(h, &h->logits, static_cast<size_t>(B) * h->K));
-  FAV_TRY(dev_alloc(h, &h->dlogits, static_cast<size_t>(B) * h->K));
   // torch-stack defaults (dataset.py:28-29; Perturbation scalar bounds model.py:72-75)
   const float mean[3] = {0.43216f, 0.394666f, 0.37645f}, sd[3] = {0.22803f, 0.22145f, 0.216989f};
   float lo = -1e30f, hi = 1e30f;
@@ -263,6 +255,24 @@ int build_resnet(fav_handle* h) {
     hi = std::min(hi, (1.0f - mean[c]) / sd[c]);
   }
   h->nrm.lo = lo; h->nrm.hi = hi;
+  // ---- flicker gradient through the stem without dX (stem_grad.cu); delta enters the network as delta / std_c ----
+  {
+    const Buf& bs = h->bufs[rn.stem_out];
+    const float sc[3] = {1.0f / h->nrm.std[0], 1.0f / h->nrm.std[1], 1.0f / h->nrm.std[2]};
+    FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(B, T, H, W)));
+    FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(rn.stem_KT) * 160 * 64));
+    FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, bs.g, bs.cs, h->stem_gw, h->pass_bits, B, T, H, W, h->To, h->Ho, h->Wo,
+                           rn.stem_KT, 1, rn.stem_pt, 3, 3, sc));
+    h->stem_grad_dense = getenv("FAV_STEM_GRAD_DENSE") != nullptr;
+  }
+  // ---- head: AdaptiveAvgPool3d(1) + Linear(512, K) ----
+  const int C5 = h->bufs[rn.final_buf].C;
+  FAV_TRY(dev_alloc(h, &h->head_w, static_cast<size_t>(C5) * h->K));
+  FAV_TRY(dev_alloc(h, &h->head_b, static_cast<size_t>(h->K)));
+  FAV_TRY(dev_alloc(h, &h->feat, static_cast<size_t>(B) * C5));
+  FAV_TRY(dev_alloc(h, &h->dfeat, static_cast<size_t>(B) * C5));
+  FAV_TRY(dev_alloc(h, &h->logits, static_cast<size_t>(B) * h->K));
+  FAV_TRY(dev_alloc(h, &h->dlogits, static_cast<size_t>(B) * h->K));
   return FAV_OK;
 }
 
@@ -381,6 +391,11 @@ int load_weights_resnet(fav_handle* h, const NamedTensors& nt) {
     std::vector<float> bpad(C1, 0.0f);
     for (int i = 0; i < C; ++i) bpad[i] = bias[i];
     FAV_CUDA(cudaMemcpy(h->stem_bnbias, bpad.data(), bpad.size() * 4, cudaMemcpyHostToDevice));
+    {
+      std::vector<uint16_t> gw(static_cast<size_t>(KT) * 160 * 64);
+      stem_grad_pack_weights(gw.data(), wt.data(), KT, C);
+      FAV_CUDA(cudaMemcpy(h->stem_gw, gw.data(), gw.size() * 2, cudaMemcpyHostToDevice));
+    }
     // dense data gradient (x-space weights)
     for (auto& d : rn.stem_dg) {
       pk.resize(d.elems);
@@ -421,7 +436,7 @@ int resnet_forward(fav_handle* h, cudaStream_t s) {
   return FAV_OK;
 }
 
-int resnet_backward_to_dx(fav_handle* h, cudaStream_t s) {
+int resnet_backward_to_dx(fav_handle* h, cudaStream_t s, bool with_dx = true) {
   ResNet& rn = h->rn;
   const Buf& fb = h->bufs[rn.final_buf];
   FAV_TRY(launch_head_bwd(h->dlogits, h->head_w, h->K, fb.p, fb.g, h->dfeat, h->B, -fb.T, fb.H * fb.W, fb.C, s));
@@ -447,12 +462,17 @@ int resnet_backward_to_dx(fav_handle* h, cudaStream_t s) {
     const RConv& c = rn.convs[rn.pre[i]];
     FAV_TRY(run_dgrad_classes(c.dg, &h->bufs[c.in], nullptr, s));
   }
-  FAV_TRY(run_dgrad_classes(rn.stem_dg, nullptr, nullptr, s));   // dense dL/d(adv) -> rn.dx
+  if (with_dx) FAV_TRY(run_dgrad_classes(rn.stem_dg, nullptr, nullptr, s));   // dense dL/d(adv) -> rn.dx
   return FAV_OK;
 }
 
 int resnet_backward(fav_handle* h, float* grad, cudaStream_t s) {
-  FAV_TRY(resnet_backward_to_dx(h, s));
+  if (!h->stem_grad_dense) {
+    FAV_TRY(resnet_backward_to_dx(h, s, /*with_dx=*/false));
+    return stem_grad_launch(h->stem_gd, grad, s);
+  }
+  // test switch: dense stem data gradient + masked reduce (an independent formulation of the same sum)
+  FAV_TRY(resnet_backward_to_dx(h, s, true));
   FAV_CHECK_ARG(h->last_clip_u8 != nullptr && h->last_delta != nullptr, "fav_backward_delta: apply a uint8 clip first");
   FAV_TRY(launch_stem_dx_reduce(h->rn.dx, h->last_clip_u8, h->last_delta, h->last_adv_flag, h->last_delta_clip, h->nrm, 1,
                                 h->rn.partial, grad, h->B, h->T, h->H, h->W, s));

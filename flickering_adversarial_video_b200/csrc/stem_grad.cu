@@ -41,7 +41,9 @@ struct StemGradGeom {
   int bits_rows;         // bitmap rows per frame (H + 7: 3 zero rows above, 4 below)
   int bits_pitch;        // 32-bit words per bitmap row (8 zero nibbles left of w = 0; a multiple of 4 words)
   int mrows;             // bitmap rows one tile can touch per frame: 2 * (output rows spanned - 1) + 7
-  int mbytes;            // shared-memory bytes of one bitmap stage: 7 * mrows * bits_pitch * 4
+  int mbytes;            // shared-memory bytes of one bitmap stage: KT * mrows * bits_pitch * 4
+  int KT, st;            // temporal taps (7: I3D, 3 / 1: torchvision stems) and temporal stride (2 / 1); in-plane 7x7 / 2
+  float scale[3];        // per-channel factor of the result (torch stack: 1/std_c, delta enters as delta/std)
   int dbg;               // FAV_SG_DBG (timing experiments only): bit 0 = epilogue skips the accumulator reads, 2 = print MMA-warp wait cycles
 };
 
@@ -86,8 +88,8 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const uint32_t* __restrict__ bits, float* __restrict__ grad) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sB = smem;                                  // 7 chunks x [160][64] bf16, SW128
-  uint8_t* sA = smem + 7 * kSgBBytes;                  // kSgStages x [128][64] bf16, SW128
+  uint8_t* sB = smem;                                  // KT chunks x [160][64] bf16, SW128
+  uint8_t* sA = smem + g.KT * kSgBBytes;               // kSgStages x [128][64] bf16, SW128
   uint8_t* sM = sA + kSgStages * kSgABytes;            // kSgStages x [7][mrows][pitch] bitmap windows
   uint64_t* bars = reinterpret_cast<uint64_t*>(sM + kSgStages * g.mbytes);
   uint64_t* a_full = bars;                 // [3]
@@ -127,15 +129,15 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(b_full, 7 * kSgBBytes);
-      for (int kt = 0; kt < 7; ++kt) tma_load_2d(sB + kt * kSgBBytes, &tmB, b_full, 0, kt * kSgChunkN);
+      mbar_expect_tx(b_full, g.KT * kSgBBytes);
+      for (int kt = 0; kt < g.KT; ++kt) tma_load_2d(sB + kt * kSgBBytes, &tmB, b_full, 0, kt * kSgChunkN);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < tile_last; ++tile) {
         const int plane = tile / g.tiles_per_plane;
         const int pos0 = (tile - plane * g.tiles_per_plane) * 128;
         const int b = plane / g.To, to = plane - b * g.To;
-        const int kt_lo = max(0, g.pt - 2 * to), kt_hi = min(6, g.T - 1 + g.pt - 2 * to);
+        const int kt_lo = max(0, g.pt - g.st * to), kt_hi = min(g.KT - 1, g.T - 1 + g.pt - g.st * to);
         const int ho0 = pos0 / g.Wo, ho1 = min(g.Ho - 1, (pos0 + 127) / g.Wo);
         const uint32_t wbytes = static_cast<uint32_t>((2 * (ho1 - ho0) + 7) * g.bits_pitch * 4);
         mbar_wait(&a_empty[stage], phase ^ 1);
@@ -145,7 +147,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&m_empty[stage], phase ^ 1);
         mbar_expect_tx(&m_full[stage], wbytes * static_cast<uint32_t>(kt_hi - kt_lo + 1));
         for (int kt = kt_lo; kt <= kt_hi; ++kt) {
-          const int t = 2 * to + kt - g.pt;
+          const int t = g.st * to + kt - g.pt;
           const uint32_t* src = bits + (static_cast<long long>(b * g.T + t) * g.bits_rows + (2 * ho0 - g.ph + 3)) * g.bits_pitch;
           bulk_load_1d(sM + stage * g.mbytes + kt * g.mrows * g.bits_pitch * 4, src, wbytes, &m_full[stage]);
         }
@@ -168,7 +170,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = tile_first; tile < tile_last; ++tile) {
       const int plane = tile / g.tiles_per_plane;
       const int to = plane % g.To;
-      const int kt_lo = max(0, g.pt - 2 * to), kt_hi = min(6, g.T - 1 + g.pt - 2 * to);
+      const int kt_lo = max(0, g.pt - g.st * to), kt_hi = min(g.KT - 1, g.T - 1 + g.pt - g.st * to);
       if (prof) c0 = clock64();
       mbar_wait(&a_full[stage], phase);
       if (prof) w_a += clock64() - c0;
@@ -214,14 +216,14 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int to = plane % g.To;
       for (int j = 0; j < 4; ++j) {
         const int kt = 2 * j + set;
-        const int t = 2 * to + kt - g.pt;
+        const int t = g.st * to + kt - g.pt;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float sum = my[(j * 3 + c) * 32];
           my[(j * 3 + c) * 32] = 0.0f;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0 && kt < 7 && t >= 0 && t < g.T) atomicAdd(&sacc[t * 3 + c], sum);
+          if (lane == 0 && kt < g.KT && t >= 0 && t < g.T) atomicAdd(&sacc[t * 3 + c], sum);
         }
       }
     };
@@ -240,7 +242,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int wo = valid ? pos - ho * g.Wo : 0;
       const int bit0 = 8 * wo + 32 - 4 * g.pw;          // nibble 2*wo - pw + 8 of the bitmap row
       const int shift = bit0 & 31;
-      const int kt_lo = max(0, g.pt - 2 * to), kt_hi = min(6, g.T - 1 + g.pt - 2 * to);
+      const int kt_lo = max(0, g.pt - g.st * to), kt_hi = min(g.KT - 1, g.T - 1 + g.pt - g.st * to);
       // this thread's 7 x 7 window inside the staged bitmap rows (row 0 of the stage = input row 2*ho0 - ph)
       const uint32_t mrow0 = smem_u32(sM + stage * g.mbytes) + static_cast<uint32_t>((2 * (ho - ho0) * g.bits_pitch + (bit0 >> 5)) * 4);
       mbar_wait(&m_full[stage], phase);
@@ -277,7 +279,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the epilogue warps publish the CTA's partial sums
     asm volatile("bar.sync 1, %0;" ::"n"(kSgEpiThreads) : "memory");
     for (int i = threadIdx.x - 64; i < g.T * 3; i += kSgEpiThreads)
-      if (sacc[i] != 0.0f) atomicAdd(&grad[i], sacc[i]);
+      if (sacc[i] != 0.0f) atomicAdd(&grad[i], sacc[i] * g.scale[i % 3]);
   }
   tc_fence_before();
   __syncthreads();
@@ -286,21 +288,25 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 }  // namespace
 
-// wq: folded fp32 stem weights [7*7*7][3][64]; dst: [7][160][64] bf16 rows (kt, c*49 + kh*7 + kw), K = co
-void stem_grad_pack_weights(uint16_t* dst, const float* wq) {
-  memset(dst, 0, static_cast<size_t>(7) * kSgChunkN * 64 * sizeof(uint16_t));
-  for (int kt = 0; kt < 7; ++kt)
+// wq: folded fp32 stem weights [KT*7*7][3][C]; dst: [KT][160][64] bf16 rows (kt, c*49 + kh*7 + kw), K = co (zero beyond C)
+void stem_grad_pack_weights(uint16_t* dst, const float* wq, int KT, int C) {
+  memset(dst, 0, static_cast<size_t>(KT) * kSgChunkN * 64 * sizeof(uint16_t));
+  for (int kt = 0; kt < KT; ++kt)
     for (int c = 0; c < 3; ++c)
       for (int kh = 0; kh < 7; ++kh)
         for (int kw = 0; kw < 7; ++kw)
-          for (int co = 0; co < 64; ++co)
+          for (int co = 0; co < C; ++co)
             dst[(static_cast<size_t>(kt) * kSgChunkN + c * 49 + kh * 7 + kw) * 64 + co] =
-                f32_to_bf16_bits(wq[(((kt * 7 + kh) * 7 + kw) * 3 + c) * 64 + co]);
+                f32_to_bf16_bits(wq[(static_cast<size_t>((kt * 7 + kh) * 7 + kw) * 3 + c) * C + co]);
 }
 
-int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, const void* wpk, const uint32_t* bits, int B, int T,
-                   int H, int W, int To, int Ho, int Wo, int pt, int ph, int pw) {
+int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, int g1_cs, const void* wpk, const uint32_t* bits, int B,
+                   int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3) {
   memset(L, 0, sizeof(*L));
+  FAV_CHECK_ARG(KT >= 1 && KT <= 7 && (st == 1 || st == 2), "stem grad: unsupported temporal kernel %d / stride %d", KT, st);
+  FAV_CHECK_ARG(g1_cs % 8 == 0 && g1_cs <= 64, "stem grad: at most 64 stem channels (row stride %d)", g1_cs);
+  L->KT = KT; L->st = st;
+  for (int c = 0; c < 3; ++c) L->scale[c] = scale3 ? scale3[c] : 1.0f;
   FAV_CHECK_ARG(W % 8 == 0, "stem grad: W=%d must be a multiple of 8", W);
   FAV_CHECK_ARG(ph >= 0 && ph <= 3 && pw >= 0 && pw <= 8, "stem grad: unsupported padding");
   FAV_CHECK_ARG(2 * (Ho - 1) + 6 - ph + 3 < H + 7 && ((8 * (Wo - 1) + 32 - 4 * pw) >> 5) + 2 <= round_up((W + 16) / 8, 4),
@@ -312,21 +318,23 @@ int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, const void* wp
   L->bits_rows = H + 7;
   L->bits_pitch = round_up((W + 16) / 8, 4);   // rows start 16-byte aligned (bulk copies)
   L->mrows = 2 * ((127 + Wo - 1) / Wo) + 7;
-  L->mbytes = round_up(7 * L->mrows * L->bits_pitch * 4, 128);
+  L->mbytes = round_up(KT * L->mrows * L->bits_pitch * 4, 128);
   L->bits = bits;
-  uint64_t dims[2] = {64, static_cast<uint64_t>(B) * To * Ho * Wo};
-  uint64_t strides[1] = {128};
+  // rows narrower than 64 channels (r2plus1d_18: 48) are zero-filled to the 128-byte swizzle span by TMA
+  uint64_t dims[2] = {static_cast<uint64_t>(g1_cs), static_cast<uint64_t>(B) * To * Ho * Wo};
+  uint64_t strides[1] = {static_cast<uint64_t>(g1_cs) * 2};
   uint32_t box[2] = {64, 128};
   FAV_TRY(make_tmap_bf16(&L->tmA, g1, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
-  uint64_t bd[2] = {64, 7 * kSgChunkN};
+  uint64_t bd[2] = {64, static_cast<uint64_t>(KT) * kSgChunkN};
+  uint64_t bstr[1] = {128};
   uint32_t bb[2] = {64, kSgChunkN};
-  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, strides, bb, CU_TENSOR_MAP_SWIZZLE_128B));
-  L->smem_bytes = 7 * kSgBBytes + kSgStages * (kSgABytes + L->mbytes) + 20 * 8 + static_cast<size_t>(T) * 3 * 4 + 128 +
+  FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 2, bd, bstr, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  L->smem_bytes = KT * kSgBBytes + kSgStages * (kSgABytes + L->mbytes) + 20 * 8 + static_cast<size_t>(T) * 3 * 4 + 128 +
                   kSgSets * 4 * 4 * 3 * 32 * 4 + 1024 + 64;
   FAV_CHECK_ARG(L->smem_bytes <= 227 * 1024, "stem grad: Wo=%d needs %zu bytes of shared memory", Wo, L->smem_bytes);
   L->grid = std::max(1, std::min(L->m_tiles, sm_count(device)));   // contiguous tile ranges: every CTA gets >= 1 tile
-  L->flops = 2.0 * static_cast<double>(B) * To * Ho * Wo * 64.0 * 7 * kSgChunkN;
-  L->bytes = static_cast<double>(B) * To * Ho * Wo * 128.0;
+  L->flops = 2.0 * static_cast<double>(B) * To * Ho * Wo * 64.0 * KT * kSgChunkN;
+  L->bytes = static_cast<double>(B) * To * Ho * Wo * g1_cs * 2.0;
   L->ready = 1;
   return FAV_OK;
 }
@@ -346,7 +354,8 @@ int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream) 
   StemGradGeom g;
   g.B = L.B; g.T = L.T; g.To = L.To; g.Ho = L.Ho; g.Wo = L.Wo; g.pt = L.pt; g.ph = L.ph; g.pw = L.pw;
   g.tiles_per_plane = L.tiles_per_plane; g.m_tiles = L.m_tiles; g.bits_rows = L.bits_rows; g.bits_pitch = L.bits_pitch;
-  g.mrows = L.mrows; g.mbytes = L.mbytes;
+  g.mrows = L.mrows; g.mbytes = L.mbytes; g.KT = L.KT; g.st = L.st;
+  for (int c = 0; c < 3; ++c) g.scale[c] = L.scale[c];
   static int dbg = -1;
   if (dbg < 0) dbg = getenv("FAV_SG_DBG") ? atoi(getenv("FAV_SG_DBG")) : 0;
   g.dbg = dbg;

@@ -76,3 +76,43 @@ def test_resnet_step_parity(arch):
     _report(f"[{arch}] max |delta - oracle| after one Adam step {dd:.3e}")
     assert dd <= 2.5e-3
     eng.close()
+
+
+@pytest.mark.parametrize("arch", ["r3d_18", "r2plus1d_18"])
+def test_stem_gradient_collapse_matches_dense_data_gradient(arch, monkeypatch):
+    """Torch stack: dL/d-delta through the stem from the tensor-core collapse (stem_grad.cu, pass bitmap written by the
+    apply kernel) against the dense stem data gradient + masked reduce (FAV_STEM_GRAD_DENSE=1), on a clip whose dark and
+    bright pixels hit the scalar clamp bounds of Perturbation.forward (model.py:72-75)."""
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200 import _lib as L
+    from flickering_adversarial_video_b200.engine import FlickerEngine
+    B, T = 2, T_CLIP
+    model = synthetic.resnet_model(arch, seed=0)
+    clip = synthetic.clips_u8(B, T, 112, 112, seed=77)
+    clip[:, :, :40] = (clip[:, :, :40] // 16)            # dark band: clamps at the lower bound
+    clip[:, :, 80:] = 255 - (clip[:, :, 80:] // 16)      # bright band: clamps at the upper bound
+    delta = synthetic.delta_uniform(T, seed=5, lo=-0.1, hi=0.1)
+    labels = None
+    grads = []
+    for dense in (False, True):
+        if dense:
+            monkeypatch.setenv("FAV_STEM_GRAD_DENSE", "1")
+        else:
+            monkeypatch.delenv("FAV_STEM_GRAD_DENSE", raising=False)
+        eng = FlickerEngine(B, T, arch=arch)
+        eng.load_weights(model.state_dict())
+        eng.apply(clip.cuda(), delta.cuda(), delta_clip=0.1)
+        logits = eng.forward()
+        if labels is None:
+            labels = logits.argmax(-1).clone()
+        eng.loss(labels, improve_loss=True, margin=0.05, stack=L.FAV_STACK_TORCH)
+        grads.append(eng.backward().clone().cpu())
+        torch.cuda.synchronize()
+        eng.close()
+    a, b = grads
+    cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+    rel = float((a - b).norm() / (b.norm() + 1e-30))
+    _report(f"[{arch}] stem gradient collapse vs dense data gradient + masked reduce: cosine {cos:.6f}, rel L2 {rel:.3e}, "
+            f"|g| {float(a.norm()):.4e}")
+    assert float(b.norm()) > 0
+    assert cos >= 0.9999 and rel <= 1e-2
