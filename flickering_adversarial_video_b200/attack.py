@@ -208,8 +208,9 @@ class SparseAttack:
         self.targeted = bool(cfg.get("TARGETED_ATTACK", False))
         self.use_logits = bool(cfg.get("USE_LOGITS", False))
         self.margin = float(cfg.get("PROB_MARGIN", 0.05))
-        # TF: regularizer_loss = beta_1 * L12 (universal.py:133); torch: lambda_ * L12 (model.py:173)
-        self.reg_weight = float(cfg.get("LAMBDA", 1.0)) if torch_stack else float(cfg.get("BETA_1", 0.5))
+        # TF: loss = adv + beta_0 * (beta_1 * L12), beta_0 = LAMBDA (universal.py:130-135); torch: lambda_ * L12 (model.py:173)
+        self.reg_weight = (float(cfg.get("LAMBDA", 1.0)) if torch_stack
+                           else float(cfg.get("LAMBDA", 1.0)) * float(cfg.get("BETA_1", 0.5)))
         self.delta_clip = (0.2 if torch_stack else 0.0) if delta_clip is None else delta_clip
         self.lr = lr
         shape = (frames, self.H, self.W, 3)

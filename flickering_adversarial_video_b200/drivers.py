@@ -141,13 +141,15 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
     """UNIVERSAL_ATTACK with FLICKERING_ATTACK=True: same step as class-gen over all classes; returns
     {'perturbation': [T,1,1,3], 'fool_rate': [...], 'scalars': TensorBoard-tag -> list}
     (tags of i3d_adversarial_main_universal.py:176-196)."""
-    if not getattr(k_i3d, "flickering", True):
-        raise NotImplementedError("FLICKERING_ATTACK=False needs kinetics_i3d_L12 (not built yet)")
+    sparse = not getattr(k_i3d, "flickering", True)     # FLICKERING_ATTACK=False: kinetics_i3d_L12, loss = adv + beta_0*beta_1*L12
     classes = k_i3d.get_kinetics_classes()
     _select_loss(k_i3d, cfg)
-    kw = _attack_kwargs(cfg)
-    kw["cyclic_pert_flag"] = float(cfg.get("CYCLIC_PERTURBATION_ATTACK", False))
-    kw["beta_3"] = cfg.BETA_2                      # universal.py:130 weights the laplacian term by beta_2
+    if sparse:
+        kw = dict(learning_rate=0.001, beta_1=float(cfg.LAMBDA) * float(cfg.BETA_1), cyclic_flag=float(cfg.CYCLIC_ATTACK))
+    else:
+        kw = _attack_kwargs(cfg)
+        kw["cyclic_pert_flag"] = float(cfg.get("CYCLIC_PERTURBATION_ATTACK", False))
+        kw["beta_3"] = cfg.BETA_2                      # universal.py:130 weights the laplacian term by beta_2
     target_class_id = classes.index(cfg.TARGETED_CLASS) if cfg.TARGETED_ATTACK else None
     max_steps = int(cfg.MAX_NUM_STEP if max_steps is None else max_steps)
     tags = {t: [] for t in ("Loss/total", "Loss/adversarial_loss", "Loss/regularizer_loss", "Loss/thickness",
@@ -162,8 +164,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
             out = k_i3d.train_step(rgb_sample, labels, **kw)
             if step % 50 == 0:      # SummarySaverHook(save_steps=50) universal.py:198-201
                 eps = k_i3d.eps_rgb
-                vals = (out["loss"], out["adversarial_loss"], out["regularizer_loss"], out["norm_reg"],
-                        out["diff_norm_reg"], out["laplacian_norm_reg"], out["thickness_relative"],
+                vals = (out["loss"], out["adversarial_loss"], out["regularizer_loss"], out.get("norm_reg", float("nan")),
+                        out.get("diff_norm_reg", float("nan")), out.get("laplacian_norm_reg", float("nan")), out["thickness_relative"],
                         out["roughness_relative"], float(eps.max()), float(eps.min()),
                         float(np.mean(out["to_min_prob"])), float(np.mean(out["to_max_prob"])))
                 for t, v in zip(tags, vals):

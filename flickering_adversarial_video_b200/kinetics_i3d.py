@@ -218,12 +218,127 @@ class kinetics_i3d:
 
 
 class kinetics_i3d_L12:
-    """Sparse per-pixel baseline (utils/kinetics_i3d_utils.py:308-521, FLICKERING_ATTACK=False).
-    SURVEY §8 row a16; not built in round 1 (needs the dense stem data-gradient kernel)."""
+    """Drop-in for ki3du.kinetics_i3d_L12(ckpt_path, batch_size, init_model, rgb_input, labels,
+    cyclic_flag_default_c, default_adv_flag_c): the sparse per-pixel baseline (utils/kinetics_i3d_utils.py:308-521,
+    FLICKERING_ATTACK=False).  eps_rgb is [T,224,224,3], initialised to 1e-8 (:333), not clipped (:336); the drivers
+    minimise adversarial_loss + beta_1 * loss_L12 (i3d_adversarial_main_universal.py:133).  Same eager execution
+    model as `kinetics_i3d` above."""
 
     flickering = False
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError(
-            "kinetics_i3d_L12 (per-pixel perturbation, FLICKERING_ATTACK=False) is not built yet: "
-            "see DESIGN.md §Scope (row a16)")
+    def __init__(self, ckpt_path="data/checkpoints/rgb_imagenet/model.ckpt", batch_size=1, init_model=True,
+                 rgb_input=None, labels=None, cyclic_flag_default_c=0.0, default_adv_flag_c=1.0,
+                 frames=_SAMPLE_VIDEO_FRAMES, weights=None, device=0, label_map_path=_LABEL_MAP_PATH, seed=0):
+        from .attack import SparseAttack
+        self.ckpt_path = ckpt_path
+        self.batch_size = batch_size
+        self.frames = frames
+        self.adv_flag = float(default_adv_flag_c)
+        self.cyclic_flag = float(cyclic_flag_default_c)
+        self.kinetics_classes = load_kinetics_classes(label_map_path=label_map_path)
+        w = load_weights(weights if weights is not None else ckpt_path)
+        self._atk = SparseAttack(w, batch_size, frames, {}, device=device)
+        self.device = self._atk.device
+        self._rng = np.random.RandomState(seed)
+        self._loss_cfg = dict(improve=True, margin=0.05, targeted=False, logits=False)
+        self._last = {}
+        self.rgb_input = rgb_input
+        self.labels = labels
+
+    @property
+    def eps_rgb(self):
+        return self._atk.perturbation.detach().cpu().numpy()
+
+    perturbation = eps_rgb
+
+    def __getattr__(self, name):
+        last = self.__dict__.get("_last", {})
+        if name in last:
+            return last[name]
+        raise AttributeError(name)
+
+    def get_kinetics_classes(self):
+        return self.kinetics_classes
+
+    def improve_adversarial_loss(self, margin=0.05, targeted=False, logits=False):
+        """utils/kinetics_i3d_utils.py:467-493"""
+        self._loss_cfg = dict(improve=True, margin=float(margin), targeted=bool(targeted), logits=bool(logits))
+        return "adversarial_loss_total"
+
+    def ce_adversarial_loss(self, targeted=False):
+        """utils/kinetics_i3d_utils.py:495-521"""
+        self._loss_cfg = dict(improve=False, margin=0.05, targeted=bool(targeted), logits=False)
+        return "adversarial_loss_total"
+
+    def _configure(self):
+        a, c = self._atk, self._loss_cfg
+        a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
+
+    def _to_device_clip(self, inputs):
+        """The sparse engine path takes uint8 clips (the reference feeds (u8/127.5 - 1) floats: pass the uint8 video)."""
+        t = torch.as_tensor(inputs)
+        if t.dtype != torch.uint8:
+            t = ((t.to(torch.float32) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+        t = t.reshape(self.batch_size, self.frames, _IMAGE_SIZE, _IMAGE_SIZE, 3)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    def __call__(self, inputs, adv_flag=0):
+        """softmax for `inputs` (utils/kinetics_i3d_utils.py:424-426)."""
+        self.prob = self._atk.predict(self._to_device_clip(inputs), adv_flag=float(adv_flag)).cpu().numpy()
+        return self.prob
+
+    def train_step(self, inputs, labels, learning_rate=1e-3, beta_1=0.5, cyclic_flag=None, adv_flag=None):
+        """One `sess.run([train_op, loss, adversarial_loss, regularizer_loss, thickness, roughness, ...])` with
+        loss = adversarial_loss + beta_1 * loss_L12 (i3d_adversarial_main_universal.py:126-140)."""
+        self._configure()
+        a = self._atk
+        clips = self._to_device_clip(inputs)
+        lab = torch.as_tensor(np.asarray(labels), dtype=torch.int64).reshape(-1).to(self.device)
+        cyc = self.cyclic_flag if cyclic_flag is None else float(cyclic_flag)
+        if cyc:       # tf.roll(rgb_input, random_shift, axis=1)   (kinetics_i3d_utils.py:349-350,357)
+            clips = torch.roll(clips, int(self._rng.randint(0, self.frames)), dims=1).contiguous()
+        a.reg_weight = float(beta_1)
+        a.step(clips, lab, adv_flag=self.adv_flag if adv_flag is None else float(adv_flag), lr=float(learning_rate))
+        sc = a.scalars.cpu().numpy()
+        B = self.batch_size
+        logits = a.eng.logits.cpu().numpy()
+        probs = a.eng.probs.cpu().numpy()
+        lab_np = lab.cpu().numpy()
+        label_prob = probs[np.arange(B), lab_np]
+        onehot = np.eye(probs.shape[1], dtype=np.float32)[lab_np]
+        max_non_label_prob = (probs - onehot).max(-1)
+        tmin, tmax = (max_non_label_prob, label_prob) if self._loss_cfg["targeted"] else (label_prob, max_non_label_prob)
+        l12 = float(sc[L.S_NORM_REG])            # fav_pixels_update: FAV_S_NORM_REG <- loss_L12
+        self._last = dict(
+            loss=float(sc[L.S_TOTAL_LOSS]), adversarial_loss=float(sc[L.S_ADV_LOSS]),
+            adversarial_loss_total=float(sc[L.S_ADV_LOSS]), loss_L12=l12, regularizer_loss=float(beta_1) * l12,
+            thickness=float(sc[L.S_THICKNESS]), roughness=float(sc[L.S_ROUGHNESS]),
+            thickness_relative=float(sc[L.S_THICKNESS]) / 2.0 * 100,
+            roughness_relative=float(sc[L.S_ROUGHNESS]) / 2.0 * 100, to_min_prob=tmin, to_max_prob=tmax,
+            model_logits=logits, softmax=probs, label_prob=label_prob, max_non_label_prob=max_non_label_prob,
+            fooled_count=int(sc[L.S_FOOLED]))
+        return self._last
+
+    def evaluate(self, next_element_val, targeted_attack=False, target_class_id=None, cyclic=0,
+                 exclude_misclassify=True):
+        """Fooling ratio over a validation iterable (utils/kinetics_i3d_utils.py:431-464)."""
+        miss, total = 0, 0
+        for rgb_sample, sample_label in next_element_val:
+            clips = self._to_device_clip(rgb_sample)
+            if cyclic:
+                clips = torch.roll(clips, int(self._rng.randint(0, self.frames)), dims=1).contiguous()
+            sample_label = np.asarray(sample_label).reshape(-1)
+            pred = self._atk.predict(clips, adv_flag=1.0).cpu().numpy().argmax(-1)
+            miss_cond = (pred == target_class_id) if targeted_attack else (pred != sample_label)
+            if exclude_misclassify:
+                clean = self._atk.predict(self._to_device_clip(rgb_sample), adv_flag=0.0).cpu().numpy().argmax(-1)
+                valid = clean == sample_label
+                miss += int(np.logical_and(miss_cond, valid).sum())
+                total += int(valid.sum())
+            else:
+                miss += int(miss_cond.sum())
+                total += int(miss_cond.shape[0])
+        return (miss / total if total else 0.0), total
+
+    def close(self):
+        self._atk.close()

@@ -139,7 +139,7 @@ int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n);
  *   delta    DEVICE [T,3] f32 (the reference's eps_rgb [T,1,1,3])
  *   adv_u8   DEVICE [B,T,H,W,3] or NULL — ((adv+1.0)*127.5).astype(uint8)  (stats_plots.py:57), bit-exact
  *   adv_f32  DEVICE [B,T,H,W,3] or NULL — the reference's `adversarial_inputs_rgb`
- * Also fills the engine's stem input and the saturated-entry list used by the backward pass. */
+ * Also fills the engine's stem input and the pass bitmap of the range clip used by the backward pass. */
 int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, const float* delta,
                       float adv_flag, float delta_clip, uint8_t* adv_u8, float* adv_f32, void* stream);
 

@@ -144,3 +144,27 @@ def test_single_video_90_frames_parity():
     # the same cosine against the fp32 oracle, tools/debug_t90.py); kernels are gated stage by stage elsewhere
     assert cos >= 0.85
     eng.close()
+
+
+def test_sparse_universal_driver_with_kinetics_i3d_L12():
+    """FLICKERING_ATTACK=False: the reference's kinetics_i3d_L12 object (per-pixel eps_rgb [T,224,224,3], initialised to
+    1e-8, loss = adv + beta_0 * beta_1 * L12) behind the universal driver (i3d_adversarial_main_universal.py:126-135)."""
+    from flickering_adversarial_video_b200 import config, synthetic
+    from flickering_adversarial_video_b200.drivers import universal_attack
+    from flickering_adversarial_video_b200.kinetics_i3d import kinetics_i3d_L12
+    k = kinetics_i3d_L12(ckpt_path="", batch_size=1, frames=T, weights=synthetic.i3d_weights(0))
+    try:
+        assert k.flickering is False
+        assert k.eps_rgb.shape == (T, 224, 224, 3) and np.allclose(k.eps_rgb, 1e-8)
+        cfg = config.default_config().UNIVERSAL_ATTACK
+        clips = [synthetic.clips_u8(1, T, seed=2001 + i).numpy() for i in range(2)]
+        labels = [[int(k(c, adv_flag=0).argmax())] for c in clips]
+        batches = lambda: iter(list(zip(clips, labels)))
+        res = universal_attack(k, batches, batches, cfg, max_steps=3)
+        assert res["total_steps"] == 3 and res["perturbation"].shape == (T, 224, 224, 3)
+        assert np.abs(res["perturbation"]).max() > 1e-6          # Adam moved the pixels
+        step0 = dict((t, v[0][1]) for t, v in res["scalars"].items())
+        assert abs(step0["Loss/total"] - (step0["Loss/adversarial_loss"] + step0["Loss/regularizer_loss"])) < 1e-5
+        assert 0.0 <= res["fool_rate"][-1][1] <= 1.0
+    finally:
+        k.close()
