@@ -137,7 +137,8 @@ def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, e
     return res
 
 
-def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eval_every=None, log_every=0):
+def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eval_every=None, log_every=0,
+                     summary_dir=None):
     """UNIVERSAL_ATTACK with FLICKERING_ATTACK=True: same step as class-gen over all classes; returns
     {'perturbation': [T,1,1,3], 'fool_rate': [...], 'scalars': TensorBoard-tag -> list}
     (tags of i3d_adversarial_main_universal.py:176-196)."""
@@ -158,6 +159,10 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
                             "Perturbation/min", "Probability/prob_to_min", "Probability/prob_to_max")}
     fool = []
     step = 0
+    writer = None
+    if summary_dir:                 # <model_dir>/train/events.out.tfevents.* like SummarySaverHook (universal.py:198-201)
+        from .records import SummaryWriter
+        writer = SummaryWriter(os.path.join(summary_dir, "train"))
     while step < max_steps:
         for rgb_sample, sample_label in train_batches():
             labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
@@ -170,6 +175,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
                         float(np.mean(out["to_min_prob"])), float(np.mean(out["to_max_prob"])))
                 for t, v in zip(tags, vals):
                     tags[t].append((step, v))
+                    if writer is not None and v == v:
+                        writer.add_scalar(t, v, step)
             if log_every and step % log_every == 0:
                 print("step {:05d} loss {:.5f}".format(step, out["loss"]))
             step += 1
@@ -180,4 +187,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
                 break
     fool.append((step, k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK,
                                       target_class_id=target_class_id)[0]))
+    if writer is not None:
+        for st, fr in fool:        # eval metric 'ACC: 1- FOOLING_RATIO' (universal.py:160-161) is 1 - fool rate
+            writer.add_scalar("ACC: 1- FOOLING_RATIO", 1.0 - fr, st)
+        writer.close()
     return {"perturbation": k_i3d.eps_rgb, "fool_rate": fool, "scalars": tags, "total_steps": step}

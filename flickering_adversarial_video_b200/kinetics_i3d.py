@@ -33,15 +33,20 @@ def load_kinetics_classes(eval_type="rgb", label_map_path=_LABEL_MAP_PATH):
 
 
 def load_weights(ckpt_path):
-    """Weights as {tf variable name: float32 array}.  Accepts an .npz with the reference checkpoint's
-    variable names (`RGB/inception_i3d/...`); TF1 checkpoint ingest itself is SURVEY §8(f2)."""
+    """Weights as {tf variable name: float32 array}: a TF1 checkpoint prefix (`<prefix>.index` +
+    `<prefix>.data-*`, what the reference's Saver restores — utils/kinetics_i3d_utils.py:41-62; read by ckpt.py) or
+    an .npz with the same variable names (`RGB/inception_i3d/...`)."""
     if isinstance(ckpt_path, dict):
         return ckpt_path
+    if ckpt_path and os.path.exists(ckpt_path + ".index"):
+        from .ckpt import read_tf_checkpoint
+        return {k: v.astype(np.float32) for k, v in read_tf_checkpoint(ckpt_path).items()
+                if k.startswith("RGB/inception_i3d/")}
     if ckpt_path and os.path.exists(ckpt_path) and ckpt_path.endswith(".npz"):
         with np.load(ckpt_path) as z:
             return {k: z[k].astype(np.float32) for k in z.files}
     raise FileNotFoundError(
-        f"checkpoint '{ckpt_path}' not found or not an .npz of TF variable names; "
+        f"checkpoint '{ckpt_path}' not found (neither a TF checkpoint prefix nor an .npz of TF variable names); "
         "pass weights=<dict> (e.g. synthetic.i3d_weights()) — there is no network to fetch the Kinetics ckpt")
 
 

@@ -1,0 +1,106 @@
+"""CPU: TFRecord clip input and TensorBoard scalar output — checksum known answers, the
+protobuf encodings against hand-derived wire bytes, framing errors, and the reference's record schema
+(kinetics_to_tf_record_uint8.py:90-94 -> utils/pre_process_rgb_flow.py:211-236) as a round trip."""
+import struct
+
+import numpy as np
+import pytest
+
+from flickering_adversarial_video_b200 import records as R
+
+
+def test_crc32c_known_answers():
+    # RFC 3720 appendix B.4 / the CRC catalogue's check value
+    assert R.crc32c(b"123456789") == 0xE3069283
+    assert R.crc32c(bytes(32)) == 0x8A9136AA
+    assert R.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
+    assert R.crc32c(bytes(range(32))) == 0x46DD794E
+    # running form and unaligned starts
+    data = bytes(range(256)) * 5
+    assert R.crc32c(data[100:], R.crc32c(data[:100])) == R.crc32c(data)
+    assert R.crc32c(np.frombuffer(data, np.uint8)[3:77]) == R.crc32c(data[3:77])
+    # TensorFlow's mask: rotate right 15, add 0xa282ead8
+    c = 0xE3069283
+    assert R.masked_crc32c(b"123456789") == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_example_wire_bytes():
+    # features { feature { key: "train/label" value { int64_list { value: 7 } } } }, packed repeated int64 (proto3)
+    want = bytes([0x0A, 0x16, 0x0A, 0x14, 0x0A, 0x0B]) + b"train/label" + bytes([0x12, 0x05, 0x1A, 0x03, 0x0A, 0x01, 0x07])
+    assert R.encode_example({"train/label": 7}) == want
+    assert R.decode_example(want) == {"train/label": [7]}
+    # unpacked int64 (older writers) and negative values decode too
+    unpacked = bytes([0x0A, 0x15, 0x0A, 0x13, 0x0A, 0x0B]) + b"train/label" + bytes([0x12, 0x04, 0x1A, 0x02, 0x08, 0x07])
+    assert R.decode_example(unpacked) == {"train/label": [7]}
+    assert R.decode_example(R.encode_example({"x": [-1, 2 ** 40]}))["x"] == [-1, 2 ** 40]
+    ex = R.decode_example(R.encode_example({"f": [0.5, -2.0], "b": [b"ab", b""]}))
+    assert ex["f"] == [0.5, -2.0] and [bytes(x) for x in ex["b"]] == [b"ab", b""]
+
+
+def test_tfrecord_framing_and_corruption(tmp_path):
+    path = str(tmp_path / "a.tfrecord")
+    payloads = [b"", b"x", bytes(range(200)) * 50]
+    with R.TFRecordWriter(path) as w:
+        for p in payloads:
+            w.write(p)
+    raw = open(path, "rb").read()
+    # u64 length | masked crc(length) | payload | masked crc(payload)
+    assert raw[:8] == struct.pack("<Q", 0) and len(raw) == sum(16 + len(p) for p in payloads)
+    assert struct.unpack("<I", raw[8:12])[0] == R.masked_crc32c(struct.pack("<Q", 0))
+    assert [bytes(p) for p in R.tfrecord_iterator(path)] == payloads
+    bad = bytearray(raw)
+    bad[16 + 12 + 0] ^= 1                                  # payload byte of record 1
+    open(path, "wb").write(bad)
+    with pytest.raises(IOError, match="record 1"):
+        list(R.tfrecord_iterator(path))
+    assert len(list(R.tfrecord_iterator(path, verify=False))) == 3      # like the reference, payload CRC optional
+    open(path, "wb").write(raw[:-3])                       # truncated
+    with pytest.raises(IOError):
+        list(R.tfrecord_iterator(path))
+    open(path, "wb").write(b"")
+    assert list(R.tfrecord_iterator(path)) == []
+
+
+def test_clip_records_round_trip_and_batching(tmp_path):
+    rng = np.random.RandomState(0)
+    paths, clips, labels = [], [], []
+    for f in range(2):
+        p = str(tmp_path / f"kinetics_{f}.tfrecords")
+        with R.TFRecordWriter(p) as w:
+            for i in range(3):
+                v = rng.randint(0, 256, size=(6, 224, 224, 3), dtype=np.uint8)
+                R.write_clip_record(w, v, 100 * f + i)
+                clips.append(v)
+                labels.append(100 * f + i)
+        paths.append(p)
+    ds = R.ClipRecordDataset(paths, batch_size=2, frames=4)
+    got = list(ds)
+    assert len(got) == 3                                   # 6 records, batch 2, drop_remainder
+    for b, (v, l) in enumerate(got):
+        assert v.dtype == np.uint8 and v.shape == (2, 4, 224, 224, 3) and l.dtype == np.int64
+        for j in range(2):
+            assert np.array_equal(v[j], clips[2 * b + j][-4:]) and l[j] == labels[2 * b + j]
+    assert len(list(R.ClipRecordDataset(paths, batch_size=4, repeat=2, prefetch=0))) == 3   # repeat(2): 12 records / 4
+    ds5 = R.ClipRecordDataset(paths, batch_size=5)
+    assert len(list(ds5)) == 1                             # remainder dropped
+
+
+def test_tensorboard_scalars(tmp_path):
+    w = R.SummaryWriter(str(tmp_path))
+    tags = {"Loss/total": 1.25, "Perturbation/thickness_%": 0.5, "Probability/prob_to_min": 0.03125}
+    for step in (0, 50, 100):
+        w.add_scalars({k: v + step for k, v in tags.items()}, step)
+    w.close()
+    got = R.read_scalars(w.path)
+    assert len(got) == 9
+    assert got[0] == (0, "Loss/total", 1.25) and got[-1] == (100, "Probability/prob_to_min", 100.03125)
+    # first record: file_version "brain.Event:2"
+    first = bytes(next(iter(R.tfrecord_iterator(w.path))))
+    assert first[0] == 0x09 and first[9:] == bytes([0x1A, 13]) + b"brain.Event:2"
+    # one scalar event, hand-derived: step = 50, Summary{Value{tag "a", simple_value 1.0}}
+    w2 = R.SummaryWriter(str(tmp_path / "x"))
+    w2.add_scalar("a", 1.0, 50, wall_time=0.0)
+    w2.close()
+    ev = [bytes(p) for p in R.tfrecord_iterator(w2.path)][1]
+    assert ev == bytes([0x09]) + bytes(8) + bytes([0x10, 50, 0x2A, 0x0A, 0x0A, 0x08, 0x0A, 0x01]) + b"a" + \
+        bytes([0x15]) + struct.pack("<f", 1.0)

@@ -146,7 +146,7 @@ def test_single_video_90_frames_parity():
     eng.close()
 
 
-def test_sparse_universal_driver_with_kinetics_i3d_L12():
+def test_sparse_universal_driver_with_kinetics_i3d_L12(tmp_path):
     """FLICKERING_ATTACK=False: the reference's kinetics_i3d_L12 object (per-pixel eps_rgb [T,224,224,3], initialised to
     1e-8, loss = adv + beta_0 * beta_1 * L12) behind the universal driver (i3d_adversarial_main_universal.py:126-135)."""
     from flickering_adversarial_video_b200 import config, synthetic
@@ -160,8 +160,12 @@ def test_sparse_universal_driver_with_kinetics_i3d_L12():
         clips = [synthetic.clips_u8(1, T, seed=2001 + i).numpy() for i in range(2)]
         labels = [[int(k(c, adv_flag=0).argmax())] for c in clips]
         batches = lambda: iter(list(zip(clips, labels)))
-        res = universal_attack(k, batches, batches, cfg, max_steps=3)
+        res = universal_attack(k, batches, batches, cfg, max_steps=3, summary_dir=str(tmp_path))
         assert res["total_steps"] == 3 and res["perturbation"].shape == (T, 224, 224, 3)
+        from flickering_adversarial_video_b200.records import read_scalars
+        ev = [f for f in os.listdir(tmp_path / "train") if f.startswith("events.out.tfevents.")]
+        scal = read_scalars(str(tmp_path / "train" / ev[0]))
+        assert ("Loss/total" in {t for _, t, _ in scal}) and ("ACC: 1- FOOLING_RATIO" in {t for _, t, _ in scal})
         assert np.abs(res["perturbation"]).max() > 1e-6          # Adam moved the pixels
         step0 = dict((t, v[0][1]) for t, v in res["scalars"].items())
         assert abs(step0["Loss/total"] - (step0["Loss/adversarial_loss"] + step0["Loss/regularizer_loss"])) < 1e-5
