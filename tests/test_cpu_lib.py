@@ -41,3 +41,18 @@ def test_no_gpu_is_a_loud_error():
     desc = _lib.NetDesc(0, 1, 16, 224, 224, 400)
     st = lib.fav_create(ctypes.byref(h), 0, ctypes.byref(desc))
     assert st == -4 and b"no CUDA device" in lib.fav_last_error()
+
+
+def test_favio_header_symbols_are_exported():
+    """include/favio.h (host I/O helpers of the f1 / f4 rows): every declared symbol is exported by libfavio.so"""
+    text = open(os.path.join(ROOT, "include", "favio.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(favio_[a-z0-9_]+)\s*\(", text)))
+    assert declared == ["favio_crc32c", "favio_masked_crc32c", "favio_tfrecord_index"]
+    path = os.path.join(ROOT, "flickering_adversarial_video_b200", "libfavio.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), f"libfavio.so does not export {name}"
