@@ -242,6 +242,8 @@ def run_engine(args):
     for i in range(2):   # warm the staging path
         slot = atk.prefetch(host_clips[i % 2], host_labels[i % 2])
         atk.step_staged(slot)
+    if use_graph:
+        atk.capture_staged()   # the public API's own graph mode: one CUDA graph per staging slot
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

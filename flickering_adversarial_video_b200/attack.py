@@ -130,6 +130,8 @@ class FlickerAttack:
 
     # ---- end-to-end path: host buffers in, host scalars out ----------------------------------
     def _ensure_staging(self, like):
+        if self._stage is None and like is None:
+            raise RuntimeError("capture_staged: prefetch both staging slots first")
         if self._stage is None:
             self._stage = [torch.empty(like.shape, dtype=like.dtype, device=self.device) for _ in range(2)]
             self._stage_labels = [torch.empty((self.B,), dtype=torch.int64, device=self.device) for _ in range(2)]
@@ -153,12 +155,29 @@ class FlickerAttack:
         self._slot ^= 1
         return slot
 
+    def capture_staged(self, adv_flag=1.0, lr=None):
+        """CUDA graphs of the step bound to the two staging slots, so that `step_staged` replays ~110 launches as one
+        graph.  Call once after both slots have been prefetched (the capture itself runs no step; the slots' current
+        contents are only read if the caller replays)."""
+        self._ensure_staging(None)
+        torch.cuda.synchronize(self.device)
+        self._staged_graphs = []
+        for slot in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step(self._stage[slot], self._stage_labels[slot], adv_flag=adv_flag, lr=lr)
+            self._staged_graphs.append(g)
+        self._staged_cfg = (adv_flag, lr)
+
     def step_staged(self, slot, adv_flag=1.0, lr=None):
         """Run one step on a prefetched batch and start the device->host read of its scalars.
         Returns the pinned host tensor and the event that marks it valid."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._stage_events[slot])
-        self.step(self._stage[slot], self._stage_labels[slot], adv_flag=adv_flag, lr=lr)
+        if getattr(self, "_staged_graphs", None) and self._staged_cfg == (adv_flag, lr):
+            self._staged_graphs[slot].replay()
+        else:
+            self.step(self._stage[slot], self._stage_labels[slot], adv_flag=adv_flag, lr=lr)
         self._host_scalars[slot].copy_(self.scalars, non_blocking=True)
         self._done_events[slot].record(cur)
         return self._host_scalars[slot], self._done_events[slot]

@@ -172,3 +172,31 @@ def test_sparse_universal_driver_with_kinetics_i3d_L12(tmp_path):
         assert 0.0 <= res["fool_rate"][-1][1] <= 1.0
     finally:
         k.close()
+
+
+def test_staged_graph_replay_matches_eager_steps():
+    """End-to-end path (pinned host clips in, host scalars out): replaying the per-slot CUDA graphs of
+    `capture_staged()` must give the same perturbation as the eager launches."""
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.attack import FlickerAttack
+    w = synthetic.i3d_weights(0)
+    host = [synthetic.clips_u8(1, T, seed=3001 + i).pin_memory() for i in range(2)]
+    labels = [torch.tensor([5 + i], dtype=torch.int64).pin_memory() for i in range(2)]
+    deltas, losses = [], []
+    for graphs in (False, True):
+        atk = FlickerAttack(w, 1, T, {})
+        for i in range(2):
+            atk.step_staged(atk.prefetch(host[i], labels[i]))
+        if graphs:
+            atk.capture_staged()
+        ls = []
+        for i in range(4):
+            out, ev = atk.step_staged(atk.prefetch(host[i % 2], labels[i % 2]))
+            ev.synchronize()
+            ls.append(float(out[9]))
+        torch.cuda.synchronize()
+        deltas.append(atk.perturbation.detach().cpu().clone())
+        losses.append(ls)
+        atk.close()
+    assert torch.allclose(deltas[0], deltas[1], rtol=0, atol=1e-6), float((deltas[0] - deltas[1]).abs().max())
+    assert np.allclose(losses[0], losses[1], rtol=1e-4, atol=1e-6)

@@ -15,6 +15,10 @@ CASES = [  # name, (T,H,W), cin, cout
     ("4e.b1b", (16, 14, 14), 144, 288),
     ("4f.b1b", (16, 14, 14), 160, 320),
     ("4f.b2b", (16, 14, 14), 32, 128),
+    ("x.c32", (32, 28, 28), 32, 96),
+    ("x.c64", (32, 28, 28), 64, 96),
+    ("x.c128", (32, 28, 28), 128, 96),
+    ("x.c16", (32, 28, 28), 16, 96),
 ]
 only = sys.argv[1:] or None
 g = torch.Generator(device="cuda").manual_seed(0)
