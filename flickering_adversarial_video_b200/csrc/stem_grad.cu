@@ -10,7 +10,7 @@
 // For one output position the 7*7*7*3 = 1029 products P[o,(k,c)] = sum_co g1[o,co] w[k,c,co] are a GEMM row
 // (K = 64 output channels, N = 1029): 128 positions x 64 channels of g1 are the A tile (one TMA box of the flat
 // [positions, 64] matrix), the weights [N][64] stay resident in shared memory, and the N dimension is walked in 7 chunks
-// of 160 columns (one temporal tap kt each: 3 channels x 49 in-plane taps = 147 live columns).  Every column of a chunk
+// of 160 columns (one temporal tap kt each: 49 in-plane taps x 3 channels = 147 live columns).  Every column of a chunk
 // lands on the same frame t = 2*to + kt - pad_t, so the epilogue reduces a chunk to three numbers per row: it adds
 // P[o,col] where the pass bit of the input entry that column touches is set.  The pass bits come from the apply kernel as
 // one nibble per pixel (bit c = entry (pixel, c) was not range-clipped) in a zero-padded bitmap, so taps that fall into
@@ -74,8 +74,9 @@ __device__ __forceinline__ void sg_chunk(uint32_t taddr, const uint32_t (&m)[7],
     for (int i = 0; i < 32; ++i) {
       const int col = j * 32 + i;
       if (col < 147) {
-        const int c = col / 49, rem = col % 49, kh = rem / 7, kw = rem % 7;
-        if (m[kh] & (1u << (4 * kw + c))) ch[c][col & 3] += __uint_as_float(v[j & 1][i]);
+        // columns run (kh, kw, c): consecutive columns test consecutive bits of one mask word (R2P sets 7 predicates at once)
+        const int c = col % 3, kw = (col / 3) % 7, kh = col / 21;
+        if (m[kh] & (1u << (4 * kw + c))) ch[c][(col / 3) & 3] += __uint_as_float(v[j & 1][i]);
       }
     }
   }
@@ -178,7 +179,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_lo = umma_desc_lo(smem_u32(sA + stage * kSgABytes));
       for (int kt = kt_lo; kt <= kt_hi; ++kt) {
         if (prof) c0 = clock64();
-        mbar_spin(&t_empty[acc], acc_phase ^ 1);
+        mbar_wait(&t_empty[acc], acc_phase ^ 1);
         if (prof) w_t += clock64() - c0;
         tc_fence_after();
         if (elect_one()) {
@@ -288,7 +289,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 }  // namespace
 
-// wq: folded fp32 stem weights [KT*7*7][3][C]; dst: [KT][160][64] bf16 rows (kt, c*49 + kh*7 + kw), K = co (zero beyond C)
+// wq: folded fp32 stem weights [KT*7*7][3][C]; dst: [KT][160][64] bf16 rows (kt, (kh*7 + kw)*3 + c), K = co (zero beyond C)
 void stem_grad_pack_weights(uint16_t* dst, const float* wq, int KT, int C) {
   memset(dst, 0, static_cast<size_t>(KT) * kSgChunkN * 64 * sizeof(uint16_t));
   for (int kt = 0; kt < KT; ++kt)
@@ -296,7 +297,7 @@ void stem_grad_pack_weights(uint16_t* dst, const float* wq, int KT, int C) {
       for (int kh = 0; kh < 7; ++kh)
         for (int kw = 0; kw < 7; ++kw)
           for (int co = 0; co < C; ++co)
-            dst[(static_cast<size_t>(kt) * kSgChunkN + c * 49 + kh * 7 + kw) * 64 + co] =
+            dst[(static_cast<size_t>(kt) * kSgChunkN + (kh * 7 + kw) * 3 + c) * 64 + co] =
                 f32_to_bf16_bits(wq[(static_cast<size_t>((kt * 7 + kh) * 7 + kw) * 3 + c) * C + co]);
 }
 
