@@ -238,9 +238,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                   stage_all + (warp - 2) * 160, lane);
         }
       } else if (c_lo < c_hi) {
-        if (mask_row == nullptr && add_row == nullptr)
+        if (add_row == nullptr)
           epilogue_columns_staged(e, c_hi - c_lo, tc.n0 + c_lo, taddr + static_cast<uint32_t>(c_lo), valid, out_row, bias_row,
-                                  e.cout_store, stage_all + (warp - 2) * 160, lane);
+                                  e.cout_store, stage_all + (warp - 2) * 160, lane, mask_row);
         else
           epilogue_columns<2>(e, c_hi - c_lo, tc.n0 + c_lo, taddr + static_cast<uint32_t>(c_lo), valid, out_row, mask_row,
                               add_row, bias_row);

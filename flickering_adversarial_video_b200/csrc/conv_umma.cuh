@@ -156,18 +156,42 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
   }
 }
 
-// Same epilogue for launches without mask / addend operands, with warp-coalesced stores: every lane's 16-byte store to
+// Same epilogue for launches without an addend operand, with warp-coalesced stores: every lane's 16-byte store to
 // its own row is a separate L1 wavefront (32 per instruction; measured: the 1x1x1 launches were bound by exactly
 // that), so the warp stages 32 rows x 32 columns in shared memory and writes 8 rows x 64 contiguous bytes per
-// instruction instead.  `stage` = this warp's 32 x 5 uint4 scratch.
+// instruction instead.  A ReLU mask (data gradients) is loaded in the same coalesced pattern, before the TMEM loads are
+// waited for, and applied to the packed bf16 values (exact: the mask only zeroes).  `stage` = this warp's 32 x 5 uint4
+// scratch.
 __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, int ncols, int n0, uint32_t taddr,
                                                         bool valid, __nv_bfloat16* out_row, const float* bias_row,
-                                                        int cout_store, uint4* stage, int lane) {
+                                                        int cout_store, uint4* stage, int lane,
+                                                        const __nv_bfloat16* mask_row = nullptr) {
   const unsigned long long row_ptr = reinterpret_cast<unsigned long long>(out_row);
+  const unsigned long long mask_ptr = reinterpret_cast<unsigned long long>(mask_row);
+  const int k = lane & 3;
+  // the four (row, 16-byte column slot) pairs this lane stores per 32-column batch
+  unsigned long long p4[4], m4[4];
+  int ok4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rr = (lane >> 2) + 8 * j;
+    p4[j] = __shfl_sync(0xffffffffu, row_ptr, rr);
+    m4[j] = __shfl_sync(0xffffffffu, mask_ptr, rr);
+    ok4[j] = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr);
+  }
   for (int c0 = 0; c0 < ncols; c0 += 32) {
     uint32_t r[2][16];
     tmem_ld_32x16(taddr + static_cast<uint32_t>(c0), r[0]);
     if (c0 + 16 < ncols) tmem_ld_32x16(taddr + static_cast<uint32_t>(c0 + 16), r[1]);   // warp-uniform
+    const int cs = c0 + 8 * k;
+    const bool st_ok = cs < ncols && n0 + cs + 8 <= cout_store;
+    uint4 mk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mk[j] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      if (mask_row && ok4[j] && st_ok)
+        mk[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(m4[j]) + n0 + cs));
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -193,16 +217,18 @@ __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, i
                                                pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
     }
     __syncwarp();
-    const int k = lane & 3;
+    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.0f, 0.0f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int rr = (lane >> 2) + 8 * j;
-      const uint4 val = stage[rr * 5 + k];
-      const unsigned long long p = __shfl_sync(0xffffffffu, row_ptr, rr);
-      const int ok = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr);
-      const int c = c0 + 8 * k;
-      if (ok && c < ncols && n0 + c + 8 <= cout_store)
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + n0 + c) = val;
+      uint4 val = stage[rr * 5 + k];
+      if (mask_row) {
+        val.x &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].x), z2);
+        val.y &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].y), z2);
+        val.z &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].z), z2);
+        val.w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].w), z2);
+      }
+      if (ok4[j] && st_ok) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p4[j]) + n0 + cs) = val;
     }
     __syncwarp();
   }
