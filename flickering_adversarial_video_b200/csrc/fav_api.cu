@@ -115,6 +115,11 @@ struct fav_handle {
   const float* last_delta_px = nullptr;
   float* zero_delta = nullptr;     // [T,3] zeros: the stem bias table without a per-frame delta
   float* pix_partial = nullptr;
+  // side streams for the independent branches of an Inception block (FAV_BRANCH_STREAMS=0 disables): the persistent conv
+  // kernels end with a partial last wave, and a sibling branch's kernel fills the SMs that fall idle
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  bool branch_streams = false;
   uint32_t* pass_bits = nullptr;  // pass nibbles of the range clip (stem_grad.cu)
   uint16_t* stem_gw = nullptr;    // stem weights as the [KT*160][64] B operand of the gradient collapse
   StemGradLaunch stem_gd;         // tensor-core gradient collapse through the stem
@@ -531,6 +536,16 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
     for (void* p : h->allocs) cudaFree(p);
     return st;
   }
+  {
+    const char* ev = getenv("FAV_BRANCH_STREAMS");
+    h->branch_streams = desc->arch == FAV_NET_I3D && !(ev && atoi(ev) == 0);
+    if (h->branch_streams)
+      for (int i = 0; i < 2; ++i) {
+        FAV_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+        FAV_CUDA(cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming));
+        FAV_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+      }
+  }
   *out = h.release();
   return FAV_OK;
 }
@@ -540,6 +555,11 @@ extern "C" int fav_destroy(fav_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
   delete h;
   return FAV_OK;
 }
@@ -725,7 +745,27 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
   return FAV_OK;
 }
 
+// fork: the side stream continues from this point of the main stream; join: the main stream waits for it.  Both are plain
+// event edges, so a CUDA-graph capture of the step turns the branches into parallel graph nodes.
+static int branch_fork(fav_handle* h, cudaStream_t s, int i) {
+  FAV_CUDA(cudaEventRecord(h->ev_fork[i], s));
+  FAV_CUDA(cudaStreamWaitEvent(h->side[i], h->ev_fork[i], 0));
+  return FAV_OK;
+}
+static int branch_join(fav_handle* h, cudaStream_t s, int i) {
+  FAV_CUDA(cudaEventRecord(h->ev_join[i], h->side[i]));
+  FAV_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+  return FAV_OK;
+}
+
 static int run_block_fwd(fav_handle* h, const Block& b, cudaStream_t s) {
+  const bool par = h->branch_streams && !g_prof_on;   // per-family timing brackets every launch on one stream
+  cudaStream_t s_pool = par ? h->side[0] : s, s_b2 = par ? h->side[1] : s;
+  const PoolOp& p = h->pools[b.pool];
+  if (par) FAV_TRY(branch_fork(h, s, 0));
+  // Branch_3: pool -> 1x1x1 (reads only the block input)
+  FAV_TRY(launch_maxpool_fwd(h->bufs[p.in].p, h->bufs[p.out].p, h->bufs[p.out].idx, p.g, s_pool));
+  FAV_TRY(conv_launch(h->convs[b.b3b].fwd, s_pool));
   if (b.fused) {
     FAV_TRY(conv_launch(b.fwd, s));
   } else {
@@ -733,11 +773,13 @@ static int run_block_fwd(fav_handle* h, const Block& b, cudaStream_t s) {
     FAV_TRY(conv_launch(h->convs[b.b1a].fwd, s));
     FAV_TRY(conv_launch(h->convs[b.b2a].fwd, s));
   }
-  const PoolOp& p = h->pools[b.pool];
-  FAV_TRY(launch_maxpool_fwd(h->bufs[p.in].p, h->bufs[p.out].p, h->bufs[p.out].idx, p.g, s));
+  if (par) FAV_TRY(branch_fork(h, s, 1));
+  FAV_TRY(conv_launch(h->convs[b.b2b].fwd, s_b2));
   FAV_TRY(conv_launch(h->convs[b.b1b].fwd, s));
-  FAV_TRY(conv_launch(h->convs[b.b2b].fwd, s));
-  FAV_TRY(conv_launch(h->convs[b.b3b].fwd, s));
+  if (par) {
+    FAV_TRY(branch_join(h, s, 0));
+    FAV_TRY(branch_join(h, s, 1));
+  }
   return FAV_OK;
 }
 
@@ -788,9 +830,19 @@ extern "C" int fav_loss(fav_handle* h, const int64_t* labels, const fav_loss_par
 
 static int run_block_bwd(fav_handle* h, const Block& b, cudaStream_t s) {
   // gradient of the block output (already masked by out > 0) lives in bufs[b.out].g
+  const bool par = h->branch_streams && !g_prof_on;
+  cudaStream_t s_b2 = par ? h->side[0] : s, s_b3 = par ? h->side[1] : s;
+  if (par) {
+    FAV_TRY(branch_fork(h, s, 0));
+    FAV_TRY(branch_fork(h, s, 1));
+  }
+  FAV_TRY(run_dgrad(h, b.b2b, true, false, s_b2));                 // -> g(b2a), masked by b2a > 0
+  FAV_TRY(run_dgrad(h, b.b3b, false, false, s_b3));                // -> g(pool)
   FAV_TRY(run_dgrad(h, b.b1b, /*mask*/ true, /*acc*/ false, s));   // -> g(b1a), masked by b1a > 0
-  FAV_TRY(run_dgrad(h, b.b2b, true, false, s));                    // -> g(b2a)
-  FAV_TRY(run_dgrad(h, b.b3b, false, false, s));                   // -> g(pool)
+  if (par) {
+    FAV_TRY(branch_join(h, s, 0));
+    FAV_TRY(branch_join(h, s, 1));
+  }
   if (b.fused) {
     FAV_TRY(conv_launch(b.dg, s));                                 // -> g(in): the three 1x1x1 data gradients at once
   } else {
