@@ -142,6 +142,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();            // barriers of both CTAs are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue done; global memory only after the previous kernels of the stream have completed
 
   if (warp == 0) {
     // ===================== TMA producer: this CTA's activation slabs =====================
@@ -340,7 +341,7 @@ int conv_launch_halo_pair(const ConvLaunch& L, cudaStream_t stream) {
     FAV_COUNT_LAUNCH();
     return FAV_OK;
   }
-  conv_halo2_kernel<<<grid, kThreads2, L.smem_bytes, stream>>>(L.tmA[0], L.tmB, L.g, L.e, L.b_bytes);
+  FAV_CUDA(launch_pdl(conv_halo2_kernel, grid, kThreads2, L.smem_bytes, stream, L.tmA[0], L.tmB, L.g, L.e, L.b_bytes));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

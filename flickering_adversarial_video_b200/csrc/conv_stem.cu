@@ -73,6 +73,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue done; global memory only after the previous kernels of the stream have completed
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -293,8 +294,8 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   ProfScope ps(PK_STEM, stream, L.flops);
-  conv_stem_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.g,
-                                                                L.e);
+  FAV_CUDA(launch_pdl(conv_stem_kernel, L.grid, kThreads, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB,
+                      L.g, L.e));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

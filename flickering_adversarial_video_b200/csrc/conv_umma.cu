@@ -90,6 +90,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue done; global memory only after the previous kernels of the stream have completed
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -320,6 +321,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue done; global memory only after the previous kernels of the stream have completed
 
   if (warp == 0) {
     // ===================== TMA producer: activation slabs =====================
@@ -833,7 +835,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
       FAV_COUNT_LAUNCH();
       return FAV_OK;
     }
-    conv_halo_kernel<<<L.grid, kHaloThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmB, L.g, L.e, L.b_bytes);
+    FAV_CUDA(launch_pdl(conv_halo_kernel, L.grid, kHaloThreads, L.smem_bytes, stream, L.tmA[0], L.tmB, L.g, L.e, L.b_bytes));
     FAV_COUNT_LAUNCH();
     FAV_CUDA(cudaGetLastError());
     return FAV_OK;
@@ -858,9 +860,8 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
       return FAV_OK;
     }
   }
-  conv_umma_kernel<<<L.grid, kTapThreads, L.smem_bytes, stream>>>(
-      L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, L.g, L.e, L.stages, L.a_bytes, L.b_bytes,
-      L.stage_bytes);
+  FAV_CUDA(launch_pdl(conv_umma_kernel, L.grid, kTapThreads, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, L.g,
+                      L.e, L.stages, L.a_bytes, L.b_bytes, L.stage_bytes));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -120,6 +120,9 @@ struct fav_handle {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool branch_streams = false;
+  // programmatic dependent launch (fav_common.cuh): measured -1.5 % on r3d_18 (chains of persistent convs), +1 % on I3D
+  // (pools and side streams in between), hence on for the torchvision nets only; FAV_PDL=0/1 overrides
+  bool pdl = false;
   uint32_t* pass_bits = nullptr;  // pass nibbles of the range clip (stem_grad.cu)
   uint16_t* stem_gw = nullptr;    // stem weights as the [KT*160][64] B operand of the gradient collapse
   StemGradLaunch stem_gd;         // tensor-core gradient collapse through the stem
@@ -537,6 +540,10 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
     return st;
   }
   {
+    const char* pe = getenv("FAV_PDL");
+    h->pdl = pe ? atoi(pe) != 0 : desc->arch != FAV_NET_I3D;
+  }
+  {
     const char* ev = getenv("FAV_BRANCH_STREAMS");
     h->branch_streams = desc->arch == FAV_NET_I3D && !(ev && atoi(ev) == 0);
     if (h->branch_streams)
@@ -717,6 +724,7 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
                                  float adv_flag, float delta_clip, uint8_t* adv_u8, float* adv_f32,
                                  void* stream) {
   FAV_CHECK_ARG(h && clip && delta, "fav_apply_flicker: null argument");
+  g_pdl_on = h->pdl;
   FAV_CHECK_ARG(in_dtype == FAV_U8 || in_dtype == FAV_F32, "fav_apply_flicker: bad dtype");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   h->last_adv_flag = adv_flag;
@@ -790,6 +798,7 @@ static int run_pool_fwd(fav_handle* h, int pid, cudaStream_t s) {
 
 extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
   FAV_CHECK_ARG(h, "fav_forward: null handle");
+  g_pdl_on = h->pdl;
   if (!h->weights_loaded) {
     set_error("fav_forward: weights not loaded");
     return FAV_ERR_STATE;
@@ -867,6 +876,7 @@ static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s);
 
 extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   FAV_CHECK_ARG(h && grad, "fav_backward_delta: null argument");
+  g_pdl_on = h->pdl;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->d.arch != FAV_NET_I3D) return resnet_backward(h, grad, s);
   FAV_TRY(i3d_backward_to_stem(h, s));
@@ -914,6 +924,7 @@ extern "C" int fav_pixels_enable(fav_handle* h) {
 extern "C" int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float* delta_px, float adv_flag,
                                 float delta_clip, float* adv_f32, void* stream) {
   FAV_CHECK_ARG(h && clip_u8 && delta_px, "fav_apply_pixels: null argument");
+  g_pdl_on = h->pdl;
   if (!h->pixels_enabled) {
     set_error("fav_apply_pixels: call fav_pixels_enable first");
     return FAV_ERR_STATE;
@@ -944,6 +955,7 @@ extern "C" int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float*
 
 extern "C" int fav_backward_pixels(fav_handle* h, float* grad_px, void* stream) {
   FAV_CHECK_ARG(h && grad_px, "fav_backward_pixels: null argument");
+  g_pdl_on = h->pdl;
   if (!h->pixels_enabled || !h->last_delta_px || !h->last_clip_u8) {
     set_error("fav_backward_pixels: no per-pixel apply preceded this call");
     return FAV_ERR_STATE;

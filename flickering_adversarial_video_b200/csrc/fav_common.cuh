@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <utility>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -66,8 +67,39 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
                    const uint32_t* elem_strides = nullptr);
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Kernels of the step are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may
+// become resident (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) as soon as every CTA of
+// the previous kernel has *started* and an SM has room, instead of after the previous grid has drained.  Each such
+// kernel calls pdl_sync() — griddepcontrol.launch_dependents + griddepcontrol.wait — before its first global-memory
+// access; the wait returns when all prerequisite grids have completed and flushed, so the data flow is unchanged.
+// FAV_PDL=0 launches without the attribute (the device instructions are then no-ops).
+extern bool g_pdl_on;
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_on ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 // ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

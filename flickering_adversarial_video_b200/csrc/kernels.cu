@@ -22,6 +22,7 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
              float dclip, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
              uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
              uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
+  pdl_sync();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = gid < groups;
   const int gpr = W >> 4;
@@ -131,11 +132,11 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
   const int block = 256;
   const int grid = static_cast<int>(ceil_div64(groups, block));
   if (in_dtype == FAV_F32)
-    apply_kernel<true><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
-                                              adv_f32, pass_bits, T, H, W, groups);
+    FAV_CUDA(launch_pdl(apply_kernel<true>, grid, block, 0, s, clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8, adv_f32,
+                        pass_bits, T, H, W, groups));
   else
-    apply_kernel<false><<<grid, block, 0, s>>>(clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8,
-                                               adv_f32, pass_bits, T, H, W, groups);
+    FAV_CUDA(launch_pdl(apply_kernel<false>, grid, block, 0, s, clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8, adv_f32,
+                        pass_bits, T, H, W, groups));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -388,6 +389,7 @@ template <int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                    uint8_t* __restrict__ idx, const PoolGeom gg) {
+  pdl_sync();
   PoolGeom g = gg;
   if (KT > 0) { g.kt = KT; g.kh = KH; g.kw = KW; g.st = ST; g.sh = SH; g.sw = SW; }
   const int cg = g.C >> 3;
@@ -454,11 +456,11 @@ int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
   dim3 grid(g.B * g.To * g.Ho, ceil_div(g.Wo * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
   switch (key) {
-    case 133122: maxpool_fwd_kernel<1, 3, 3, 1, 2, 2><<<grid, 256, 0, s>>>(x, y, idx, g); break;
-    case 333111: maxpool_fwd_kernel<3, 3, 3, 1, 1, 1><<<grid, 256, 0, s>>>(x, y, idx, g); break;
-    case 333222: maxpool_fwd_kernel<3, 3, 3, 2, 2, 2><<<grid, 256, 0, s>>>(x, y, idx, g); break;
-    case 222222: maxpool_fwd_kernel<2, 2, 2, 2, 2, 2><<<grid, 256, 0, s>>>(x, y, idx, g); break;
-    default: maxpool_fwd_kernel<0, 0, 0, 0, 0, 0><<<grid, 256, 0, s>>>(x, y, idx, g); break;
+    case 133122: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<1, 3, 3, 1, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case 333111: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<3, 3, 3, 1, 1, 1>, grid, 256, 0, s, x, y, idx, g)); break;
+    case 333222: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<3, 3, 3, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case 222222: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<2, 2, 2, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    default: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<0, 0, 0, 0, 0, 0>, grid, 256, 0, s, x, y, idx, g)); break;
   }
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
@@ -471,6 +473,7 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
                    __nv_bfloat16* __restrict__ dx, const PoolGeom gg) {
+  pdl_sync();
   PoolGeom g = gg;
   if (KT > 0) { g.kt = KT; g.kh = KH; g.kw = KW; g.st = ST; g.sh = SH; g.sw = SW; }
   const int cg = g.C >> 3;
@@ -545,11 +548,11 @@ int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
   dim3 grid(g.B * g.T * g.H, ceil_div(g.W * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
   switch (key) {
-    case 133122: maxpool_bwd_kernel<1, 3, 3, 1, 2, 2><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
-    case 333111: maxpool_bwd_kernel<3, 3, 3, 1, 1, 1><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
-    case 333222: maxpool_bwd_kernel<3, 3, 3, 2, 2, 2><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
-    case 222222: maxpool_bwd_kernel<2, 2, 2, 2, 2, 2><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
-    default: maxpool_bwd_kernel<0, 0, 0, 0, 0, 0><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g); break;
+    case 133122: FAV_CUDA(launch_pdl(maxpool_bwd_kernel<1, 3, 3, 1, 2, 2>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g)); break;
+    case 333111: FAV_CUDA(launch_pdl(maxpool_bwd_kernel<3, 3, 3, 1, 1, 1>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g)); break;
+    case 333222: FAV_CUDA(launch_pdl(maxpool_bwd_kernel<3, 3, 3, 2, 2, 2>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g)); break;
+    case 222222: FAV_CUDA(launch_pdl(maxpool_bwd_kernel<2, 2, 2, 2, 2, 2>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g)); break;
+    default: FAV_CUDA(launch_pdl(maxpool_bwd_kernel<0, 0, 0, 0, 0, 0>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g)); break;
   }
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());

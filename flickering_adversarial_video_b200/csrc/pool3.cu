@@ -63,6 +63,7 @@ pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
   for (int i = threadIdx.x; i < (R + 2) * W * cgn; i += blockDim.x) M1[i] = ninf;
   __syncthreads();
+  pdl_sync();
   const int b = blockIdx.z;
   const int t_begin = blockIdx.y * tseg;
   const int t_end = min(t_begin + tseg, T);
@@ -176,6 +177,7 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   for (int i = threadIdx.x; i < n1; i += blockDim.x) { G1a[i] = z4; G1b[i] = z4; }   // incl. the border columns
   for (int i = threadIdx.x; i < 2 * nc; i += blockDim.x) CD[i] = make_uint2(0u, 0u);
   __syncthreads();
+  pdl_sync();
 
   const int b = blockIdx.z;
   const int t_begin = blockIdx.y * tseg;
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(256)
 pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
                    __nv_bfloat16* __restrict__ dx, const PoolGeom g, const int Qt, const int Qh, const int Qw) {
+  pdl_sync();
   constexpr int NA = KT == 3 ? 2 : 1;
   const int cg = g.C >> 3;
   const int i = blockIdx.y * blockDim.x + threadIdx.x;
@@ -413,7 +416,7 @@ int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
     attr = true;
   }
   dim3 grid(g.C / (8 * t.cgn) * t.nth, ceil_div(g.T, tseg), g.B);
-  pool3s1_fwd_kernel<<<grid, t.threads, smem, s>>>(x, y, idx, g.T, g.H, g.W, g.C, t.cgn, tseg, t.R, t.nth, t.halo);
+  FAV_CUDA(launch_pdl(pool3s1_fwd_kernel, grid, t.threads, smem, s, x, y, idx, g.T, g.H, g.W, g.C, t.cgn, tseg, t.R, t.nth, t.halo));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -432,8 +435,8 @@ int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
     attr = true;
   }
   dim3 grid(g.C / (8 * t.cgn) * t.nth, ceil_div(g.T, tseg), g.B);
-  pool3s1_bwd_kernel<<<grid, t.threads, smem, s>>>(dy, idx, addend, relu_src, dx, g.T, g.H, g.W, g.C, t.cgn, tseg, t.R,
-                                                   t.nth, t.halo);
+  FAV_CUDA(launch_pdl(pool3s1_bwd_kernel, grid, t.threads, smem, s, dy, idx, addend, relu_src, dx, g.T, g.H, g.W, g.C, t.cgn,
+                      tseg, t.R, t.nth, t.halo));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -450,8 +453,8 @@ int launch_pool_s2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
   const int Qt = g.kt == 3 ? (g.T - 1 + g.pt) / 2 + 1 : g.T;
   const int Qh = (g.H - 1 + g.ph) / 2 + 1, Qw = (g.W - 1 + g.pw) / 2 + 1;
   dim3 grid(g.B * Qt * Qh, ceil_div(Qw * (g.C / 8), 256));
-  if (g.kt == 3) pool_s2_bwd_kernel<3><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw);
-  else pool_s2_bwd_kernel<1><<<grid, 256, 0, s>>>(dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw);
+  if (g.kt == 3) FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<3>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw));
+  else FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<1>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -127,6 +127,7 @@ stem_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue done; global memory only after the previous kernels of the stream have completed
 
   if (warp == 0) {
     if (lane == 0) {
@@ -371,7 +372,7 @@ int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream) 
     FAV_COUNT_LAUNCH();
     return FAV_OK;
   }
-  stem_grad_kernel<<<L.grid, kSgThreads, L.smem_bytes, stream>>>(L.tmA, L.tmB, g, L.bits, grad);
+  FAV_CUDA(launch_pdl(stem_grad_kernel, L.grid, kSgThreads, L.smem_bytes, stream, L.tmA, L.tmB, g, L.bits, grad));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -1,5 +1,6 @@
 // util.cu — error string, device queries, TMA descriptor encoding.
 #include "fav_common.cuh"
+#include <stdlib.h>
 
 #include <stdarg.h>
 #include <mutex>
@@ -11,6 +12,7 @@ static thread_local char t_err[1024] = "";
 unsigned long long g_launch_count = 0;
 
 bool g_prof_on = false;
+bool g_pdl_on = false;   // set per API call from the handle (fav_api.cu): on for the torchvision nets, off for I3D (measured)
 namespace {
 struct ProfRec { int kind; cudaEvent_t e0, e1; double flops, bytes; };
 std::vector<ProfRec> g_prof_recs;
