@@ -481,6 +481,19 @@ int bn_fold(const NamedTensors& nt, const std::string& unit, int cout, std::vect
 
 }  // namespace
 
+// fork: the side stream continues from this point of the main stream; join: the main stream waits for it.  Both are plain
+// event edges, so a CUDA-graph capture of the step turns the branches into parallel graph nodes.
+static int branch_fork(fav_handle* h, cudaStream_t s, int i) {
+  FAV_CUDA(cudaEventRecord(h->ev_fork[i], s));
+  FAV_CUDA(cudaStreamWaitEvent(h->side[i], h->ev_fork[i], 0));
+  return FAV_OK;
+}
+static int branch_join(fav_handle* h, cudaStream_t s, int i) {
+  FAV_CUDA(cudaEventRecord(h->ev_join[i], h->side[i]));
+  FAV_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+  return FAV_OK;
+}
+
 #include "resnet_impl.cuh"
 
 namespace {
@@ -545,7 +558,7 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
   }
   {
     const char* ev = getenv("FAV_BRANCH_STREAMS");
-    h->branch_streams = desc->arch == FAV_NET_I3D && !(ev && atoi(ev) == 0);
+    h->branch_streams = !(ev && atoi(ev) == 0);
     if (h->branch_streams)
       for (int i = 0; i < 2; ++i) {
         FAV_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
@@ -753,19 +766,6 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
   return FAV_OK;
 }
 
-// fork: the side stream continues from this point of the main stream; join: the main stream waits for it.  Both are plain
-// event edges, so a CUDA-graph capture of the step turns the branches into parallel graph nodes.
-static int branch_fork(fav_handle* h, cudaStream_t s, int i) {
-  FAV_CUDA(cudaEventRecord(h->ev_fork[i], s));
-  FAV_CUDA(cudaStreamWaitEvent(h->side[i], h->ev_fork[i], 0));
-  return FAV_OK;
-}
-static int branch_join(fav_handle* h, cudaStream_t s, int i) {
-  FAV_CUDA(cudaEventRecord(h->ev_join[i], h->side[i]));
-  FAV_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));
-  return FAV_OK;
-}
-
 static int run_block_fwd(fav_handle* h, const Block& b, cudaStream_t s) {
   const bool par = h->branch_streams && !g_prof_on;   // per-family timing brackets every launch on one stream
   cudaStream_t s_pool = par ? h->side[0] : s, s_b2 = par ? h->side[1] : s;
@@ -966,7 +966,7 @@ extern "C" int fav_backward_pixels(fav_handle* h, float* grad_px, void* stream) 
     FAV_TRY(resnet_backward_to_dx(h, s));
   } else {
     FAV_TRY(i3d_backward_to_stem(h, s));
-    FAV_TRY(run_dgrad_classes(h->rn.stem_dg, nullptr, nullptr, s));
+    FAV_TRY(run_dgrad_classes(h->rn.stem_dg, nullptr, nullptr, s, h));
   }
   return launch_stem_dx_pixels(h->rn.dx, h->last_clip_u8, h->last_delta_px, h->last_adv_flag, h->last_delta_clip, h->nrm,
                                torch_mode, grad_px, h->B, h->T, h->H, h->W, s);

@@ -46,12 +46,28 @@ int plan_dgrad_classes(fav_handle* h, std::vector<DgradClass>* out, const __nv_b
   return FAV_OK;
 }
 
-int run_dgrad_classes(const std::vector<DgradClass>& cls, const Buf* mask, const Buf* addend, cudaStream_t s) {
+// The parity classes of a strided data gradient write disjoint output positions: with a handle they are spread over the
+// main and the two side streams (parallel nodes of a captured graph) — each class is a small launch that rarely fills
+// the GPU on its own.
+int run_dgrad_classes(const std::vector<DgradClass>& cls, const Buf* mask, const Buf* addend, cudaStream_t s,
+                      fav_handle* h = nullptr) {
+  const bool par = h && h->branch_streams && !g_prof_on && cls.size() >= 2;
+  if (par) {
+    FAV_TRY(branch_fork(h, s, 0));
+    if (cls.size() >= 3) FAV_TRY(branch_fork(h, s, 1));
+  }
+  const int nstreams = par ? (cls.size() >= 3 ? 3 : 2) : 1;
+  int i = 0;
   for (const DgradClass& d : cls) {
     ConvLaunch L = d.L;
     if (mask) { L.e.mask = mask->p; L.e.mask_cs = mask->cs; L.e.mask_coff = 0; }
     if (addend) { L.e.addend = addend->g; L.e.add_cs = addend->cs; L.e.add_coff = 0; }
-    FAV_TRY(conv_launch(L, s));
+    const int k = i++ % nstreams;
+    FAV_TRY(conv_launch(L, k == 0 ? s : h->side[k - 1]));
+  }
+  if (par) {
+    FAV_TRY(branch_join(h, s, 0));
+    if (cls.size() >= 3) FAV_TRY(branch_join(h, s, 1));
   }
   return FAV_OK;
 }
@@ -427,9 +443,16 @@ int resnet_forward(fav_handle* h, cudaStream_t s) {
   ResNet& rn = h->rn;
   FAV_TRY(stem_launch(h->stem_fwd, s));
   for (int id : rn.pre) FAV_TRY(conv_launch(rn.convs[id].fwd, s));
+  const bool par = h->branch_streams && !g_prof_on;
   for (const RBlock& b : rn.blocks) {
-    if (b.ds >= 0) FAV_TRY(conv_launch(rn.convs[b.ds].fwd, s));
-    for (int id : b.chain) FAV_TRY(conv_launch(rn.convs[id].fwd, s));
+    // the 1x1x1 downsample shortcut only meets the main branch in the epilogue of the block's last conv
+    const bool side = par && b.ds >= 0 && b.chain.size() >= 2;
+    if (side) FAV_TRY(branch_fork(h, s, 0));
+    if (b.ds >= 0) FAV_TRY(conv_launch(rn.convs[b.ds].fwd, side ? h->side[0] : s));
+    for (size_t i = 0; i < b.chain.size(); ++i) {
+      if (side && i + 1 == b.chain.size()) FAV_TRY(branch_join(h, s, 0));
+      FAV_TRY(conv_launch(rn.convs[b.chain[i]].fwd, s));
+    }
   }
   const Buf& fb = h->bufs[rn.final_buf];
   FAV_TRY(launch_head_fwd(fb.p, h->B, -fb.T, fb.H * fb.W, fb.C, h->feat, h->head_w, h->head_b, h->K, h->logits, s));
@@ -446,23 +469,23 @@ int resnet_backward_to_dx(fav_handle* h, cudaStream_t s, bool with_dx = true) {
     const Buf& bout = h->bufs[b.out];
     for (int i = static_cast<int>(b.chain.size()) - 1; i >= 1; --i) {
       const RConv& c = rn.convs[b.chain[i]];
-      FAV_TRY(run_dgrad_classes(c.dg, &h->bufs[c.in], nullptr, s));   // masked by the producer's ReLU
+      FAV_TRY(run_dgrad_classes(c.dg, &h->bufs[c.in], nullptr, s, h));   // masked by the producer's ReLU
     }
     const RConv& c0 = rn.convs[b.chain[0]];
     if (b.ds >= 0) {
       // shortcut gradient first (reaches the class-(0,0,0) positions only), everything else accumulates on it
       FAV_CUDA(cudaMemsetAsync(bin.g, 0, static_cast<size_t>(bin.npos(h->B)) * bin.cs * 2, s));
-      FAV_TRY(run_dgrad_classes(rn.convs[b.ds].dg, nullptr, nullptr, s));
-      FAV_TRY(run_dgrad_classes(c0.dg, &bin, &bin, s));
+      FAV_TRY(run_dgrad_classes(rn.convs[b.ds].dg, nullptr, nullptr, s, h));
+      FAV_TRY(run_dgrad_classes(c0.dg, &bin, &bin, s, h));
     } else {
-      FAV_TRY(run_dgrad_classes(c0.dg, &bin, &bout, s));   // identity shortcut: + g(out)
+      FAV_TRY(run_dgrad_classes(c0.dg, &bin, &bout, s, h));   // identity shortcut: + g(out)
     }
   }
   for (int i = static_cast<int>(rn.pre.size()) - 1; i >= 0; --i) {
     const RConv& c = rn.convs[rn.pre[i]];
-    FAV_TRY(run_dgrad_classes(c.dg, &h->bufs[c.in], nullptr, s));
+    FAV_TRY(run_dgrad_classes(c.dg, &h->bufs[c.in], nullptr, s, h));
   }
-  if (with_dx) FAV_TRY(run_dgrad_classes(rn.stem_dg, nullptr, nullptr, s));   // dense dL/d(adv) -> rn.dx
+  if (with_dx) FAV_TRY(run_dgrad_classes(rn.stem_dg, nullptr, nullptr, s, h));   // dense dL/d(adv) -> rn.dx
   return FAV_OK;
 }
 
