@@ -120,8 +120,8 @@ struct fav_handle {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool branch_streams = false;
-  // programmatic dependent launch (fav_common.cuh): measured -1.5 % on r3d_18 (chains of persistent convs), +1 % on I3D
-  // (pools and side streams in between), hence on for the torchvision nets only; FAV_PDL=0/1 overrides
+  // programmatic dependent launch (fav_common.cuh): measured -1.5 % on r3d_18 (chains of persistent convs), -2.6 % on I3D
+  // with one clip, +1 % on I3D with 8 clips (pools and side streams in between); FAV_PDL=0/1 overrides
   bool pdl = false;
   uint32_t* pass_bits = nullptr;  // pass nibbles of the range clip (stem_grad.cu)
   uint16_t* stem_gw = nullptr;    // stem weights as the [KT*160][64] B operand of the gradient collapse
@@ -554,7 +554,8 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
   }
   {
     const char* pe = getenv("FAV_PDL");
-    h->pdl = pe ? atoi(pe) != 0 : desc->arch != FAV_NET_I3D;
+    // I3D: -2.6 % for one 90-frame clip (small launches, prologues matter), +1 % for 8 x 64 frames
+    h->pdl = pe ? atoi(pe) != 0 : (desc->arch != FAV_NET_I3D || desc->batch * desc->frames <= 192);
   }
   {
     const char* ev = getenv("FAV_BRANCH_STREAMS");
