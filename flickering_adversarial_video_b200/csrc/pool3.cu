@@ -400,6 +400,25 @@ PoolTiling pick_tiling(int H, int W, int C, int max_threads, int max_tiled = 0) 
 
 }  // namespace
 
+// T segment length: one CTA streams `seg` output frames and reads seg + 2 input frames, and the grid runs in waves of
+// one CTA per SM, so the time is ~ waves x (seg + 2 + fixed cost).  Fewer, longer segments win whenever they remove a
+// mostly empty last wave (Mixed_3b backward: 192 CTAs = 2 waves of 10 frames -> 144 CTAs = 1 wave of 13).
+static int pick_tseg(int T, long long units_per_segment) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int sms = sm_count(dev);
+  double best = 1e30;
+  int best_seg = T;
+  for (int seg = 2; seg <= T; ++seg) {
+    const int nseg = ceil_div(T, seg);
+    const long long waves = ceil_div64(units_per_segment * nseg, sms);
+    const double cost = static_cast<double>(waves) * (seg + 2 + 1.5);
+    if (cost < best - 1e-9) { best = cost; best_seg = seg; }
+  }
+  if (const char* ev = getenv("FAV_POOL_TSEG")) best_seg = std::max(1, std::min(T, atoi(ev)));
+  return best_seg;
+}
+
 bool pool3s1_applicable(const PoolGeom& g) {
   return g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 &&
          pick_tiling(g.H, g.W, g.C, kPoolThreads).cgn > 0;
@@ -408,7 +427,7 @@ bool pool3s1_applicable(const PoolGeom& g) {
 int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
   const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads, 1024);
   FAV_CHECK_ARG(t.cgn > 0 && idx, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
-  const int tseg = g.T >= 8 ? 8 : g.T;
+  const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
   const size_t smem = (static_cast<size_t>(t.R + 2 * t.halo) * (g.W + 2) + static_cast<size_t>(t.R + 2) * g.W) * t.cgn * 16;
   static bool attr = false;
   if (!attr) {
@@ -426,7 +445,7 @@ int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
                        const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
   const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads);
   FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
-  const int tseg = g.T >= 32 ? 8 : (g.T >= 8 ? 4 : g.T);
+  const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
   const size_t smem = (static_cast<size_t>(t.R + 2) * g.W * 2 + static_cast<size_t>(t.R) * (g.W + 2) * 2) * t.cgn * 16 +
                       static_cast<size_t>(2) * (t.R + 2) * (g.W + 2) * t.cgn * 8;
   static bool attr = false;
