@@ -705,7 +705,7 @@ int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfl
 // softmax + adversarial loss + dloss/dlogits
 //   improve_adversarial_loss: utils/kinetics_i3d_utils.py:253-288 (TF) / model.py:216-250 (torch)
 //   ce_adversarial_loss:      utils/kinetics_i3d_utils.py:290-307 (TF) / model.py:177-196 (torch)
-// One block; clips are processed in order so the batch sums are deterministic.
+// One block, one warp per clip; the batch sums are added in clip order, so they are deterministic.
 // =============================================================================================
 template <typename T>
 __device__ __forceinline__ T block_reduce(T v, T* sh, bool is_max) {
@@ -747,45 +747,67 @@ __device__ __forceinline__ ArgMax block_argmax(float v, int i, ArgMax* sh) {
   return r;
 }
 
-__global__ void __launch_bounds__(512)
+// warp-level versions (one warp owns one clip)
+__device__ __forceinline__ float warp_reduce(float v, bool is_max) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(u, v) : v + u;
+  }
+  return v;
+}
+__device__ __forceinline__ ArgMax warp_argmax(float v, int i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float uv = __shfl_xor_sync(0xffffffffu, v, o);
+    const int ui = __shfl_xor_sync(0xffffffffu, i, o);
+    if (uv > v || (uv == v && ui < i)) { v = uv; i = ui; }
+  }
+  ArgMax r;
+  r.v = v; r.i = i;
+  return r;
+}
+
+constexpr int kLossWarps = 8;
+// One warp per clip (8 clips in flight, no block barriers inside a clip); the batch sums are added in clip order by one
+// thread at the end, so they stay deterministic.
+__global__ void __launch_bounds__(kLossWarps * 32)
 loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const fav_loss_params p,
             int B, int K, float* __restrict__ probs, float* __restrict__ dlogits,
             float* __restrict__ scalars) {
-  __shared__ float shf[16];
-  __shared__ float stash[4];
-  __shared__ ArgMax sha[16];
-  extern __shared__ float sp[];  // [K] probabilities, [K] dL/dp
-  float* prob = sp;
-  float* dp = sp + K;
-  float adv_sum = 0.0f, fooled = 0.0f, sum_min = 0.0f, sum_max = 0.0f;
+  extern __shared__ float sp[];  // per warp: [K] probabilities, [K] dL/dp; then per clip: 4 partial sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* prob = sp + warp * 2 * K;
+  float* dp = prob + K;
+  float* part = sp + kLossWarps * 2 * K;   // [B][4]
   const float bdiv = static_cast<float>(p.global_batch > 0 ? p.global_batch : B);
   const bool torch_stack = p.stack == FAV_STACK_TORCH;
-  for (int b = 0; b < B; ++b) {
+  for (int b = warp; b < B; b += kLossWarps) {
     const float* z = logits + static_cast<long long>(b) * K;
     const int y = static_cast<int>(labels[b]);
+    float adv_sum = 0.0f, fooled = 0.0f, sum_min = 0.0f, sum_max = 0.0f;
     float mx = -INFINITY;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, z[k]);
-    mx = block_reduce<float>(mx, shf, true);
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, z[k]);
+    mx = warp_reduce(mx, true);
     float se = 0.0f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = lane; k < K; k += 32) {
       const float e = expf(z[k] - mx);
       prob[k] = e;
       se += e;
     }
-    se = block_reduce<float>(se, shf, false);
+    se = warp_reduce(se, false);
     const float inv = 1.0f / se;
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = lane; k < K; k += 32) {
       prob[k] *= inv;
       dp[k] = 0.0f;
       if (probs) probs[static_cast<long long>(b) * K + k] = prob[k];
     }
-    __syncthreads();
+    __syncwarp();
     // selections
     float bv = -INFINITY; int bi = K;       // arg-max prob (prediction)
     float nv = -INFINITY; int ni = K;       // max non-label prob
     float lv = -INFINITY; int li = K;       // max "non-label" logit
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = lane; k < K; k += 32) {
       const float pk = prob[k];
       if (pk > bv) { bv = pk; bi = k; }
       const float pn = torch_stack ? (k == y ? -INFINITY : pk) : pk - (k == y ? 1.0f : 0.0f);
@@ -793,16 +815,15 @@ loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels
       const float zn = torch_stack ? (k == y ? -INFINITY : z[k]) : z[k] - (k == y ? 1.0f : 0.0f);
       if (zn > lv) { lv = zn; li = k; }
     }
-    const ArgMax pred = block_argmax(bv, bi, sha);
-    const ArgMax nonl = block_argmax(nv, ni, sha);
-    const ArgMax nonz = block_argmax(lv, li, sha);
+    const ArgMax pred = warp_argmax(bv, bi);
+    const ArgMax nonl = warp_argmax(nv, ni);
+    const ArgMax nonz = warp_argmax(lv, li);
     const float py = prob[y];
     const float pmaxnl = nonl.v;  // TF: value of (p - onehot) at its arg-max == p[k*] when k* != y
-
-    if (threadIdx.x == 0) {
+    float dd_logit = 0.0f;   // direct logit gradient: +dd at ia, -dd at ib (logits mode only)
+    int ia = -1, ib = -1;
+    if (lane == 0) {
       float loss = 0.0f;
-      float dd_logit = 0.0f;   // direct logit gradient: +dd at ia, -dd at ib (logits mode only)
-      int ia = -1, ib = -1;
       if (p.improve_loss) {
         float a, bb, mm;
         float dmm_dp = 0.0f; int mm_idx = -1;  // in logits mode the margin depends on one probability
@@ -861,27 +882,34 @@ loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels
         }
         adv_sum += loss / bdiv;
       }
-      stash[0] = dd_logit;
-      stash[1] = __int_as_float(ia);
-      stash[2] = __int_as_float(ib);
       const bool is_fooled = p.targeted ? (pred.i == y) : (pred.i != y);
       fooled += is_fooled ? 1.0f : 0.0f;
+      part[b * 4 + 0] = adv_sum;
+      part[b * 4 + 1] = fooled;
+      part[b * 4 + 2] = sum_min;
+      part[b * 4 + 3] = sum_max;
     }
-    __syncthreads();
+    __syncwarp();
+    const float ddl = __shfl_sync(0xffffffffu, dd_logit, 0);
+    ia = __shfl_sync(0xffffffffu, ia, 0);
+    ib = __shfl_sync(0xffffffffu, ib, 0);
     // softmax backward: dz_k = p_k * (dp_k - sum_j dp_j p_j)  (+ direct logit terms)
     float dot = 0.0f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) dot += dp[k] * prob[k];
-    const float ddl = stash[0];
-    const int ia = __float_as_int(stash[1]), ib = __float_as_int(stash[2]);
-    dot = block_reduce<float>(dot, shf, false);
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = lane; k < K; k += 32) dot += dp[k] * prob[k];
+    dot = warp_reduce(dot, false);
+    for (int k = lane; k < K; k += 32) {
       float g = prob[k] * (dp[k] - dot);
       if (p.use_logits && p.improve_loss) g += (k == ia ? ddl : 0.0f) - (k == ib ? ddl : 0.0f);
       dlogits[static_cast<long long>(b) * K + k] = g * p.grad_scale;
     }
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    float adv_sum = 0.0f, fooled = 0.0f, sum_min = 0.0f, sum_max = 0.0f;
+    for (int b = 0; b < B; ++b) {   // clip order: deterministic batch sums
+      adv_sum += part[b * 4 + 0]; fooled += part[b * 4 + 1]; sum_min += part[b * 4 + 2]; sum_max += part[b * 4 + 3];
+    }
     scalars[FAV_S_ADV_LOSS] = adv_sum;
     scalars[FAV_S_FOOLED] = fooled;
     scalars[FAV_S_SUM_P_MIN] = sum_min;
@@ -892,7 +920,10 @@ loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels
 int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
                 float* probs, float* dlogits, float* scalars, cudaStream_t s) {
   ProfScope ps(PK_HEAD_LOSS, s);
-  loss_kernel<<<1, 512, 2 * K * sizeof(float), s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
+  const size_t smem = (static_cast<size_t>(kLossWarps) * 2 * K + static_cast<size_t>(B) * 4) * sizeof(float);
+  FAV_CHECK_ARG(smem <= 200 * 1024, "loss: K=%d / B=%d need %zu bytes of shared memory", K, B, smem);
+  if (smem > 48 * 1024) FAV_CUDA(cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  loss_kernel<<<1, kLossWarps * 32, smem, s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
