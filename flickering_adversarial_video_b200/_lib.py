@@ -38,6 +38,10 @@ class Tensor(C.Structure):
                 ("dims", C.c_int64 * 5)]
 
 
+class NormParams(C.Structure):
+    _fields_ = [("mean", C.c_float * 3), ("std", C.c_float * 3), ("lo", C.c_float), ("hi", C.c_float)]
+
+
 class LossParams(C.Structure):
     _fields_ = [("improve_loss", C.c_int32), ("targeted", C.c_int32), ("use_logits", C.c_int32),
                 ("margin", C.c_float), ("grad_scale", C.c_float), ("global_batch", C.c_int32),
@@ -77,6 +81,7 @@ SIGNATURES = {
     "fav_op_maxpool3d_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fav_op_loss": (_i, [_i, _vp, _vp, C.POINTER(LossParams), _i, _i, _vp, _vp, _vp, _vp]),
     "fav_op_delta_update": (_i, [_i, _vp, _vp, _vp, _vp, _vp, C.POINTER(RegParams), C.POINTER(AdamParams), _f, _vp, _i, _vp]),
+    "fav_op_resize_crop": (_i, [_i, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fav_debug_read": (_i64, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "fav_profile_begin": (_i, []),
     "fav_profile_end": (_i, [C.POINTER(C.c_double), _i]),

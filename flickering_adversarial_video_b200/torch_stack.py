@@ -225,11 +225,20 @@ class VideoLearnerAdversarial:
         self.pert_model.from_engine(atk.delta)
 
     # ---- universal attack: fit (model.py:460-628) with train_an_epoch (:630-788) --------------------------
-    def fit(self, lr, epochs, train_batches, valid_batches, model_dir="checkpoints", model_name=None,
+    def fit(self, lr, epochs, train_batches=None, valid_batches=None, model_dir="checkpoints", model_name=None,
             loss_params_dict=None, save_model=True, start_epoch=0):
         """train_batches / valid_batches: callables returning an iterable of (uint8 clips [B,T,H,W,3] DEVICE,
-        labels [B] DEVICE) per epoch.  Writes `{model_name}_{epoch:03d}.npy` (pickled list of per-epoch
+        labels [B] DEVICE) per epoch; by default the `dataset` given to the constructor supplies them
+        (`video_dataset.VideoDataset.train_batches` / `.test_batches`, the reference's `dataset.train_dl` /
+        `.test_dl`, model.py:506-507).  Writes `{model_name}_{epoch:03d}.npy` (pickled list of per-epoch
         OrderedDicts, model.py:619-623) and returns it."""
+        if train_batches is None or valid_batches is None:
+            if self.dataset is None:
+                raise ValueError("fit needs train_batches / valid_batches or a dataset")
+            if self.dataset.batch_size != self.batch_size or self.dataset.sample_length != self.sample_length:
+                raise ValueError("dataset batch_size / sample_length differ from the learner's")
+            train_batches = train_batches or self.dataset.train_batches
+            valid_batches = valid_batches or self.dataset.test_batches
         lp = dict(loss_params_dict)
         metric = Adversarial_metrics(lp["targeted_attack"], lp.get("target_class_id"))
         atk = self._attack(lr, lp, self.batch_size)

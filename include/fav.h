@@ -217,6 +217,20 @@ int fav_op_delta_update(int device, float* delta, const float* grad, float* m, f
                         const fav_reg_params* reg, const fav_adam_params* adam, float adv_flag, float* scalars,
                         int T, void* stream);
 
+/* Clip loader of the torch stack: ToTensorVideo -> ResizeVideo(128, keep_ratio) -> CenterCropVideo(112)
+ * [-> NormalizeVideo] (utils_cv/action_recognition/dataset.py:84-123; references/transforms_video.py:23-53,182-200;
+ * references/functional_video.py:52-97) in one pass over decoded frames, the crop folded into the bilinear resize
+ * (torch interpolate, align_corners=False; arithmetic order of the CPU kernel, no FMA contraction).
+ *   frames_u8 DEVICE [n_frames,H,W,3];  resized_h/w: size after ResizeVideo;  ratio_h/w: float(1/scale_factor) as
+ *   interpolate uses it (input/output size when no scale factor is given);  crop_i/j, out_h/w: crop window in the
+ *   resized frame;  out_u8 DEVICE [n_frames,out_h,out_w,3] or NULL: nearest uint8 of the resized [0,1] clip (what
+ *   fav_apply_flicker consumes);  out_f32 DEVICE [n_frames/frames_per_clip,3,frames_per_clip,out_h,out_w] or NULL:
+ *   the reference's transform output (v - mean)/std, needs norm. */
+int fav_op_resize_crop(int device, const uint8_t* frames_u8, int n_frames, int H, int W, int resized_h,
+                       int resized_w, float ratio_h, float ratio_w, int crop_i, int crop_j, int out_h, int out_w,
+                       int frames_per_clip, const fav_norm_params* norm, uint8_t* out_u8, float* out_f32,
+                       void* stream);
+
 /* debug/introspection: copy a named internal activation (bf16 -> f32, NDHWC, unpadded channels)
  * to a DEVICE f32 buffer; returns element count or <0.  Names follow i3d.py end points
  * ("Conv3d_1a_7x7", "Mixed_3b", ...), prefix "grad:" for the gradient buffer. */
