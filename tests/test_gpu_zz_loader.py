@@ -88,11 +88,11 @@ def test_video_files_into_the_attack(tmp_path):
             for t in range(12):
                 wr.write(np.roll(base, 3 * t, axis=1))
             wr.release()
-    ds = vd.VideoDataset(str(root), seed=1, train_pct=1.0, sample_length=4, sample_step=2, batch_size=2)
+    ds = vd.VideoDataset(str(root), seed=1, train_pct=1.0, sample_length=8, sample_step=1, batch_size=2)
     batches = list(ds.train_batches())
     assert len(batches) == 2
     clips, labels = batches[0]
-    assert clips.shape == (2, 4, 112, 112, 3) and clips.dtype == torch.uint8 and clips.is_cuda
+    assert clips.shape == (2, 8, 112, 112, 3) and clips.dtype == torch.uint8 and clips.is_cuda
     assert labels.dtype == torch.int64 and labels.shape == (2,)
     # the batch equals the oracle's transform of the same decoded frames
     idx = ds.train_range[0]
@@ -103,7 +103,7 @@ def test_video_files_into_the_attack(tmp_path):
     cfg = {"LAMBDA": 1.0, "BETA_1": 0.5, "TARGETED_ATTACK": False, "IMPROVE_ADV_LOSS": True, "USE_LOGITS": False,
            "PROB_MARGIN": 0.05}
     model = synthetic.resnet_model("r3d_18", seed=0)
-    atk = FlickerAttack(model.state_dict(), 2, 4, cfg, arch="r3d_18", delta_clip=0.1)
+    atk = FlickerAttack(model.state_dict(), 2, 8, cfg, arch="r3d_18", delta_clip=0.1)
     pred = atk.predict(clips, adv_flag=0.0).argmax(-1)
     sc = atk.step(clips, pred)
     assert torch.isfinite(sc).all()
