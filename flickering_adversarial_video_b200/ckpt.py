@@ -18,7 +18,9 @@ LevelDB table format):
 
 PARITY UNPINNED: no TensorFlow and no checkpoint file are available in the build container, so this reader is
 checked against the published format (structure known answers: magic, footer layout, masked CRCs) and against the
-writer below, not against a file TensorFlow wrote.  Snappy-compressed index blocks (not what BundleWriter emits) are
+writer below, not against a file TensorFlow wrote; the BundleHeaderProto / BundleEntryProto encodings and the tensor
+CRCs are cross-checked against Google's protobuf runtime and TensorBoard's masked CRC-32C
+(tests/test_cpu_records_crosscheck.py), the LevelDB table framing is not.  Snappy-compressed index blocks (not what BundleWriter emits) are
 rejected with an error rather than guessed at."""
 import os
 import struct

@@ -1,10 +1,15 @@
 """ORACLE (test infrastructure, never the product path) — CPU restatement of the reference's
 I3D flickering-attack step in plain PyTorch fp32/fp64.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or checkpoints for this path
- and TensorFlow 1.15 / dm-sonnet 1.23 cannot be installed here, so this file
-restates the published semantics of those dependencies (TF `SAME` padding, snt.BatchNorm inference,
-tf.clip_by_value gradients, tf.train.AdamOptimizer) and follows the reference call sites line by line:
+PARITY: PARTLY PINNED.  The reference ships no tests, golden vectors or checkpoints for this path (SURVEY.md §4,
+§8c) and TensorFlow 1.15 / dm-sonnet 1.23 cannot be installed here, so this file restates the published semantics
+of those dependencies and follows the reference call sites line by line.  The FORWARD semantics (TF `SAME` padding
+of strided Conv3D and max_pool3d, snt.BatchNorm inference, the VALID average pool and the mean over T' of the head,
+the InceptionI3d topology) are pinned against an independent implementation: OpenCV's DNN module running the same
+network as an ONNX graph agrees to 1e-4 relative on the logits of a 17-frame clip, and per op exactly / to 1e-5
+(tests/test_cpu_oracle_opencv_pin.py).  The backward pass is torch autograd of that forward.  Still unpinned
+(restated from the TF documentation only): tf.clip_by_value's gradient at the bounds, tf.train.AdamOptimizer's
+epsilon placement, and the loss assembly of utils/kinetics_i3d_utils.py, which has no second implementation anywhere.
 
   i3d.py:32-71        Unit3D  = Conv3D(SAME, no bias) -> BatchNorm(inference, eps 1e-3, no gamma) -> ReLU
   i3d.py:144-479      InceptionI3d topology, TF SAME max-pools, VALID avg-pool head, mean over T'
