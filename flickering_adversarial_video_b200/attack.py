@@ -213,10 +213,17 @@ class SparseAttack:
     One `step()` = apply -> forward -> loss -> backward to every pixel -> L1,2 gradient + Adam."""
 
     def __init__(self, weights, batch, frames, attack_cfg=None, num_classes=400, device=0, lr=1e-3, arch="i3d",
-                 delta_clip=None, init=None):
+                 delta_clip=None, init=None, process_group=None):
         self.eng = FlickerEngine(batch, frames, None, None, num_classes, device, arch=arch)
         self.eng.load_weights(weights)
         self.eng.pixels_enable()
+        # sharded universal attack: clips split over ranks, the per-pixel gradient [T,H,W,3] is sum-all-reduced
+        # (SURVEY §8e: 54 MB for I3D, 2.4 MB for the 112x112 nets); one rank: no collective, nothing changes
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.global_batch = batch * self.world
         self.arch = arch
         self.device = self.eng.device
         self.B, self.T, self.H, self.W = batch, frames, self.eng.H, self.eng.W
@@ -257,8 +264,14 @@ class SparseAttack:
         e.apply_pixels(clips_u8, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
         e.forward()
         e.loss(labels, improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
-               margin=self.margin, stack=self.stack)
+               margin=self.margin, global_batch=self.global_batch if self.world > 1 else 0, stack=self.stack)
         e.backward_pixels(self.grad)
+        if self.world > 1:
+            # margin loss = sum over samples, CE = mean over the GLOBAL batch (fav_loss divides by global_batch): in
+            # both cases the global gradient is the plain sum of the rank gradients; the L1,2 term is added once,
+            # after the exchange, by update_pixels.  Scalars 0..3: adversarial loss, fooled count, probability sums.
+            fdist.allreduce_sum_(self.grad, self.pg)
+            fdist.allreduce_sum_(self.scalars[:4], self.pg)
         e.update_pixels(self.delta, self.grad, self.m, self.v, self.step_count, self.reg_weight,
                         delta_clip=self.delta_clip, lr=self.lr if lr is None else lr, stack=self.stack)
         return self.scalars

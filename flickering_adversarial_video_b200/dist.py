@@ -46,3 +46,13 @@ def ce_grad_divisor(local_batch, world):
     """The CE loss is a mean over the GLOBAL batch (utils/kinetics_i3d_utils.py:305): every rank
     divides its per-sample terms by local_batch*world so that the sum over ranks is the global mean."""
     return local_batch * world
+
+
+def sum_counts(values, device="cpu", group=None):
+    """Sum a few host counters (validation miss / total counts of the fooling ratio) over ranks; returns floats.
+    One rank: the values unchanged.  Every rank must call it the same number of times."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return [float(v) for v in values]
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.tolist()

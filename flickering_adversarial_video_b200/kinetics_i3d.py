@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import dist as fdist
 from .attack import FlickerAttack
 
 _IMAGE_SIZE = 224
@@ -216,7 +217,9 @@ class kinetics_i3d:
             else:
                 miss += int(miss_cond.sum())
                 total += int(miss_cond.shape[0])
-        return (miss / total if total else 0.0), total
+        # sharded validation: every rank evaluated its shard of the clips; the ratio is taken over all of them
+        miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
+        return (miss / total if total else 0.0), int(total)
 
     def close(self):
         self._atk.close()
@@ -343,7 +346,9 @@ class kinetics_i3d_L12:
             else:
                 miss += int(miss_cond.sum())
                 total += int(miss_cond.shape[0])
-        return (miss / total if total else 0.0), total
+        # sharded validation: every rank evaluated its shard of the clips; the ratio is taken over all of them
+        miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
+        return (miss / total if total else 0.0), int(total)
 
     def close(self):
         self._atk.close()

@@ -71,6 +71,68 @@ def test_sharded_gradient_equals_full_batch(loss_kind):
     assert rel < 1e-2, rel      # fp32 summation order (and a few ReLU masks) differ between the sharded and the full-batch run
 
 
+def _sparse_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(2)
+    from flickering_adversarial_video_b200 import dist as fdist, synthetic
+    from oracle import oracle_resnet as R
+    fdist.init_from_env("gloo")
+    T, GB = 4, 2
+    model = synthetic.resnet_model("r3d_18", seed=0)
+    clips = synthetic.clips_u8(GB, T, 112, 112, seed=1200)
+    labels = torch.tensor([3, 7])
+    delta = (torch.rand((T, 112, 112, 3), generator=torch.Generator().manual_seed(5)) - 0.5) * 0.1
+    lo, hi = fdist.shard_range(GB, rank, world)
+    ref = R.sparse_attack_step(model, clips[lo:hi], labels[lo:hi], delta, lambda_=1.0, max_norm=0.2)
+    g = ref["grad_data"].clone()                       # data term only; SparseAttack adds the L1,2 term after the exchange
+    sc = torch.tensor([ref["adv_loss"]])
+    fdist.allreduce_sum_(g)
+    fdist.allreduce_sum_(sc)
+    if rank == 0:
+        ret["grad"], ret["adv_loss"] = g, float(sc)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_per_pixel_gradient_equals_full_batch():
+    """the exchange SparseAttack.step performs when world > 1 (per-pixel gradient + adversarial loss, both plain sums)"""
+    from flickering_adversarial_video_b200 import synthetic
+    from oracle import oracle_resnet as R
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sparse_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    T = 4
+    model = synthetic.resnet_model("r3d_18", seed=0)
+    clips = synthetic.clips_u8(2, T, 112, 112, seed=1200)
+    delta = (torch.rand((T, 112, 112, 3), generator=torch.Generator().manual_seed(5)) - 0.5) * 0.1
+    full = R.sparse_attack_step(model, clips, torch.tensor([3, 7]), delta, lambda_=1.0, max_norm=0.2)
+    assert abs(ret["adv_loss"] - full["adv_loss"]) < 1e-5 * max(1.0, abs(full["adv_loss"]))
+    rel = float((ret["grad"] - full["grad_data"]).norm() / full["grad_data"].norm())
+    assert rel < 1e-4, rel
+
+
+def _counts_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from flickering_adversarial_video_b200 import dist as fdist
+    fdist.init_from_env("gloo")
+    got = fdist.sum_counts((3 + rank, 10 * (rank + 1)))        # rank 0: 3 of 10 fooled, rank 1: 4 of 20
+    ret[rank] = got
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_validation_counts_are_summed_over_ranks():
+    """kinetics_i3d.evaluate / VideoLearnerAdversarial.fit take the fooling ratio over all ranks' shards"""
+    from flickering_adversarial_video_b200 import dist as fdist
+    assert fdist.sum_counts((3, 10)) == [3.0, 10.0]            # no process group: unchanged
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_counts_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0] == ret[1] == [7.0, 30.0]
+
+
 def test_shard_range_rules():
     from flickering_adversarial_video_b200 import dist as fdist
     assert fdist.shard_range(64, 3, 8) == (24, 32)
