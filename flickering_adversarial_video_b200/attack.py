@@ -20,10 +20,12 @@ from .engine import FlickerEngine
 
 class FlickerAttack:
     def __init__(self, weights, batch, frames, attack_cfg=None, height=None, width=None, num_classes=400,
-                 device=0, lr=1e-3, stack=None, delta_clip=None, process_group=None, arch="i3d"):
+                 device=0, lr=1e-3, stack=None, delta_clip=None, process_group=None, arch="i3d", sharded=True):
         """arch "i3d": TF-stack rules, delta_clip 0.4 (utils/kinetics_i3d_utils.py:104-105).
         arch "r3d_18"/"mc3_18"/"r2plus1d_18": torch-stack rules (model.py:58-250): delta_clip is
-        l_inf_pert_norm, the regulariser is beta_1*thick + (1-beta_1)*(diff+lap) on the clamped delta."""
+        l_inf_pert_norm, the regulariser is beta_1*thick + (1-beta_1)*(diff+lap) on the clamped delta.
+        sharded=False: this attack is a per-rank replica (single-video attacks: every rank works on its own
+        video) and never joins a collective even when torch.distributed is initialised."""
         self.eng = FlickerEngine(batch, frames, height, width, num_classes, device, arch=arch)
         self.eng.load_weights(weights)
         self.arch = arch
@@ -51,7 +53,7 @@ class FlickerAttack:
         # distributed
         self.pg = process_group
         self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.global_batch = batch * self.world
         # state: delta (eps_rgb, utils/kinetics_i3d_utils.py:100 — zeros), Adam slots, step
@@ -213,7 +215,7 @@ class SparseAttack:
     One `step()` = apply -> forward -> loss -> backward to every pixel -> L1,2 gradient + Adam."""
 
     def __init__(self, weights, batch, frames, attack_cfg=None, num_classes=400, device=0, lr=1e-3, arch="i3d",
-                 delta_clip=None, init=None, process_group=None):
+                 delta_clip=None, init=None, process_group=None, sharded=True):
         self.eng = FlickerEngine(batch, frames, None, None, num_classes, device, arch=arch)
         self.eng.load_weights(weights)
         self.eng.pixels_enable()
@@ -221,7 +223,7 @@ class SparseAttack:
         # (54 MB for I3D, 2.4 MB for the 112x112 nets); one rank: no collective, nothing changes
         self.pg = process_group
         self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.global_batch = batch * self.world
         self.arch = arch

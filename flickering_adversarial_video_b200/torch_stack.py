@@ -206,19 +206,20 @@ class VideoLearnerAdversarial:
                                        cyclic_pert=cyclic_pert)
         self._atk = None
 
-    def _attack(self, lr, loss_params_dict, batch):
+    def _attack(self, lr, loss_params_dict, batch, sharded=True):
         cfg = {"LAMBDA": loss_params_dict["lambda_"], "BETA_1": loss_params_dict["beta_1"],
                "TARGETED_ATTACK": loss_params_dict["targeted_attack"], "IMPROVE_ADV_LOSS": loss_params_dict["improve_loss"],
                "USE_LOGITS": loss_params_dict["use_logits"], "PROB_MARGIN": 0.05}
         if self.attack_type == "flickering":
             atk = FlickerAttack(self._weights, batch, self.sample_length, cfg, num_classes=self.num_classes,
                                 device=self._device, lr=lr, arch=self.model_name,
-                                delta_clip=self.pert_model.dynamic_max_norm)
+                                delta_clip=self.pert_model.dynamic_max_norm, sharded=sharded)
             atk.delta.copy_(self.pert_model.as_engine())
         else:
             atk = SparseAttack(self._weights, batch, self.sample_length, cfg, num_classes=self.num_classes,
                                device=self._device, lr=lr, arch=self.model_name,
-                               delta_clip=self.pert_model.dynamic_max_norm, init=self.pert_model.as_engine())
+                               delta_clip=self.pert_model.dynamic_max_norm, init=self.pert_model.as_engine(),
+                               sharded=sharded)
         self.pert_model.bind(atk.eng)
         return atk
 
@@ -304,7 +305,7 @@ class VideoLearnerAdversarial:
         dynamic_max_norm *= 1.3 (at most `max_restarts` times, model.py:1061-1066).  Returns the result dict the
         reference saves as `{vid}_@{class}.npy` (:1194-1203), or None when the clean clip is misclassified."""
         lp = dict(loss_params_dict)
-        atk = self._attack(lr, lp, 1)
+        atk = self._attack(lr, lp, 1, sharded=False)      # single-video attacks are per-rank replicas (no collective)
         self._atk = atk
         clips = clip_u8.reshape(1, *clip_u8.shape[-4:]).contiguous()
         labels = torch.as_tensor([int(label)], dtype=torch.int64, device=atk.device)
@@ -345,3 +346,45 @@ class VideoLearnerAdversarial:
             np.save(os.path.join(model_dir, "{}_@{}.npy".format(video_name, class_name if class_name else label)), res,
                     allow_pickle=True)
         return res
+
+    # ---- single-video attack over a dataset (model.py:789-979) -----------------------------------------------
+    def fit_many_videos(self, lr, epochs=1, model_dir="checkpoints", model_name=None, save_model=False,
+                        loss_params_dict=None, n_iter=3000, videos=None):
+        """`fit_many_videos`: one single-video attack per video of the dataset's training split.  For each video the
+        result goes to `{model_dir}/{video}_@{class_name}.npy` (spaces in the class name replaced by `_`); a video whose
+        file already holds a successful attack is skipped, one whose file holds `None` (claimed by another run, or
+        clean-misclassified) too; with `save_model` a `None` placeholder is written before the attack starts
+        (model.py:925-946).  Before every video the perturbation is re-drawn as U(-1,1) * 0.005 and
+        `dynamic_max_norm` reset (:949-952).  `videos`: optional iterable of (uint8 DEVICE clip [T,H,W,3], label, path)
+        replacing the dataset.  With torch.distributed initialised the videos are dealt round-robin to the ranks
+        (replicas only: no collective).  Returns {video name: result dict or None}."""
+        lp = dict(loss_params_dict)
+        os.makedirs(model_dir, exist_ok=True)
+        if videos is None:
+            if self.dataset is None:
+                raise ValueError("fit_many_videos needs a dataset or `videos`")
+            videos = (self.dataset[i] for i in self.dataset.train_range)
+        rank, world = 0, 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        out = {}
+        for vid_num, (clip, target, vid_path) in enumerate(videos):
+            if vid_num % world != rank:
+                continue
+            target = int(target)
+            vid_name = str(vid_path).split("/")[-1]
+            class_name = str(self.label_id_to_text[target]) if self.label_id_to_text is not None else str(target)
+            dest_path = os.path.join(model_dir, "{}_@{}.npy".format(vid_name, class_name.replace(" ", "_")))
+            if os.path.exists(dest_path):
+                prev = np.load(dest_path, allow_pickle=True).tolist()
+                if prev is None or np.array(prev["is_adversarial"]).any():
+                    continue
+            elif save_model:
+                np.save(dest_path, None)
+            self.pert_model.perturbation = (torch.rand(self.pert_model.size, device=self.pert_model.device) * 2 - 1) * 0.005
+            self.pert_model.dynamic_max_norm = self.pert_model.max_norm
+            res = self.fit_single_video(lr, n_iter, clip, target, loss_params_dict=lp)
+            out[vid_name] = res
+            if res is not None and save_model:
+                np.save(dest_path, res, allow_pickle=True)
+        return out
