@@ -349,7 +349,7 @@ class VideoLearnerAdversarial:
 
     # ---- single-video attack over a dataset (model.py:789-979) -----------------------------------------------
     def fit_many_videos(self, lr, epochs=1, model_dir="checkpoints", model_name=None, save_model=False,
-                        loss_params_dict=None, n_iter=3000, videos=None):
+                        loss_params_dict=None, n_iter=3000, videos=None, max_restarts=4, restart_after=3000):
         """`fit_many_videos`: one single-video attack per video of the dataset's training split.  For each video the
         result goes to `{model_dir}/{video}_@{class_name}.npy` (spaces in the class name replaced by `_`); a video whose
         file already holds a successful attack is skipped, one whose file holds `None` (claimed by another run, or
@@ -383,7 +383,8 @@ class VideoLearnerAdversarial:
                 np.save(dest_path, None)
             self.pert_model.perturbation = (torch.rand(self.pert_model.size, device=self.pert_model.device) * 2 - 1) * 0.005
             self.pert_model.dynamic_max_norm = self.pert_model.max_norm
-            res = self.fit_single_video(lr, n_iter, clip, target, loss_params_dict=lp)
+            res = self.fit_single_video(lr, n_iter, clip, target, loss_params_dict=lp, max_restarts=max_restarts,
+                                        restart_after=restart_after)
             out[vid_name] = res
             if res is not None and save_model:
                 np.save(dest_path, res, allow_pickle=True)

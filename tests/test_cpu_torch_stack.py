@@ -68,6 +68,7 @@ def test_fit_many_videos_file_protocol(tmp_path):
             self.pert_model, self.dataset, self.label_id_to_text = Pert(), None, {0: "riding a bike", 1: "yoga"}
 
         def fit_single_video(self, lr, n_iter, clip_u8, label, **kw):
+            assert kw["max_restarts"] == 4 and kw["restart_after"] == 3000
             calls.append((label, float(self.pert_model.perturbation.abs().max()), self.pert_model.dynamic_max_norm))
             if label == 1:
                 return None                                  # clean clip misclassified

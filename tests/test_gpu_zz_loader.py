@@ -107,3 +107,48 @@ def test_video_files_into_the_attack(tmp_path):
     pred = atk.predict(clips, adv_flag=0.0).argmax(-1)
     sc = atk.step(clips, pred)
     assert torch.isfinite(sc).all()
+
+
+def test_fit_many_videos_over_a_video_folder(tmp_path):
+    """VideoDataset -> VideoLearnerAdversarial.fit_many_videos: one bounded single-video attack per file, results in
+    the reference's `{video}_@{class}.npy` layout (model.py:925-979)"""
+    cv2 = pytest.importorskip("cv2")
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.torch_stack import VideoLearnerAdversarial
+    root = tmp_path / "videos"
+    rng = np.random.RandomState(6)
+    for cls in ("a", "b"):
+        (root / cls).mkdir(parents=True)
+        wr = cv2.VideoWriter(str(root / cls / f"{cls}0.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 25.0, (160, 120))
+        if not wr.isOpened():
+            pytest.skip("OpenCV cannot encode mp4v here")
+        base = rng.randint(0, 255, (120, 160, 3)).astype(np.uint8)
+        for t in range(10):
+            wr.write(np.roll(base, 2 * t, axis=0))
+        wr.release()
+    ds = vd.VideoDataset(str(root), seed=1, train_pct=1.0, sample_length=8, batch_size=1)
+    model = synthetic.resnet_model("r3d_18", seed=0)
+    # label the videos with the model's own clean prediction so that the attacks start (clean-misclassified ones are skipped)
+    from oracle import oracle_resnet
+    names = {}
+    for i in ds.train_range:
+        clip, _, path = ds[i]
+        with torch.no_grad():
+            pred = int(model(oracle_resnet.normalize_u8(clip.cpu()[None])).argmax())
+        ds.video_records[i]._data[1] = pred
+        names[pred] = f"class {pred}"
+    learner = VideoLearnerAdversarial(dataset=ds, num_classes=400, base_model="r3d_18", sample_length=8,
+                                      l_inf_pert_norm=0.2, attack_type="flickering", labaels_id_to_text=names,
+                                      weights=model.state_dict(), batch_size=1)
+    lp = {"lambda_": 1.0, "beta_1": 0.5, "targeted_attack": False, "target_class_id": None, "target_class_name": None,
+          "improve_loss": True, "use_logits": False}
+    out = learner.fit_many_videos(1e-2, model_dir=str(tmp_path / "res"), save_model=True, loss_params_dict=lp, n_iter=2,
+                                  max_restarts=1, restart_after=40)
+    assert set(out) == {"a0", "b0"}
+    for name, res in out.items():
+        files = [f for f in os.listdir(str(tmp_path / "res")) if f.startswith(name + "_@class_")]
+        assert len(files) == 1
+        if res is not None:          # bf16 engine and fp32 torchvision can disagree on a near-tie clean prediction
+            assert len(res["is_adversarial"]) >= 2 and res["perturbation"][-1].shape == (3, 8, 1, 1)
+            saved = np.load(os.path.join(str(tmp_path / "res"), files[0]), allow_pickle=True).tolist()
+            assert saved["label"] == res["label"]
