@@ -219,7 +219,8 @@ class kinetics_i3d:
                 miss += int(miss_cond.sum())
                 total += int(miss_cond.shape[0])
         # sharded validation: every rank evaluated its shard of the clips; the ratio is taken over all of them
-        miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
+        if self._atk.world > 1:
+            miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
         return (miss / total if total else 0.0), int(total)
 
     def close(self):
@@ -349,7 +350,8 @@ class kinetics_i3d_L12:
                 miss += int(miss_cond.sum())
                 total += int(miss_cond.shape[0])
         # sharded validation: every rank evaluated its shard of the clips; the ratio is taken over all of them
-        miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
+        if self._atk.world > 1:
+            miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
         return (miss / total if total else 0.0), int(total)
 
     def close(self):

@@ -283,8 +283,9 @@ class VideoLearnerAdversarial:
                 self._sync_pert(atk)
                 pert = self.pert_model.get_perturbation()[0].detach().cpu().numpy()
                 # sharded epochs (one process per GPU, each over its shard of the clips): metrics over all ranks
-                miss_rate, total, loss_sum, n_seen = fdist.sum_counts((miss_rate, total, loss_sum, n_seen),
-                                                                     device=atk.device, group=atk.pg)
+                if atk.world > 1:
+                    miss_rate, total, loss_sum, n_seen = fdist.sum_counts((miss_rate, total, loss_sum, n_seen),
+                                                                         device=atk.device, group=atk.pg)
                 result[f"{phase}/time"] = time.time() - t0
                 result[f"{phase}/loss"] = loss_sum / max(n_seen, 1.0)
                 result[f"{phase}/fooling_ratio"] = miss_rate / max(total, 1.0)
