@@ -269,38 +269,60 @@ class VideoDataset:
         return (x[0] if self.num_samples == 1 else x), label, path
 
     # ---- batch sources for VideoLearnerAdversarial.fit --------------------------------------------------------
-    def _batches(self, indices, with_paths=False):
-        """yields (uint8 DEVICE clips [B,T,S,S,3], int64 DEVICE labels [B]) — full batches only, as the engine is
-        planned for a fixed batch; decode runs one batch ahead on a background thread"""
-        import torch
-        dev = torch.device("cuda", self.device)
-        B, S = self.batch_size, self.input_size
+    def _host_batches(self, indices):
+        """lists of `batch_size` decoded items (clips uint8 [num_samples,T,H,W,3], label, path) — full batches only, as
+        the engine is planned for a fixed batch; decoding runs up to `prefetch` batches ahead on a background thread,
+        which stops when the consumer abandons the iterator and whose exceptions are re-raised in the consumer"""
+        B = self.batch_size
         groups = [indices[i:i + B] for i in range(0, len(indices) - B + 1, B)]
         q = queue.Queue(maxsize=max(1, self.prefetch))
+        stop = threading.Event()
+
+        def put(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def work():
             try:
                 for grp in groups:
-                    q.put([self.load_frames(i) for i in grp])
-                q.put(None)
+                    if not put([self.load_frames(i) for i in grp]):
+                        return
+                put(None)
             except BaseException as e:       # surfaced in the consumer
-                q.put(e)
+                put(e)
 
         th = threading.Thread(target=work, daemon=True)
         th.start()
-        while True:
-            item = q.get()
-            if item is None:
-                break
-            if isinstance(item, BaseException):
-                raise item
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            th.join()
+
+    def _batches(self, indices, with_paths=False):
+        """yields (uint8 DEVICE clips [B,T,S,S,3], int64 DEVICE labels [B]): pinned upload of the decoded frames and the
+        resize / crop kernel per clip (clips of one batch may differ in frame size)"""
+        import torch
+        dev = torch.device("cuda", self.device)
+        B, S = self.batch_size, self.input_size
+        for item in self._host_batches(indices):
             out = torch.empty((B, self.sample_length, S, S, 3), dtype=torch.uint8, device=dev)
             for b, (clips, _, _) in enumerate(item):
                 fr = torch.from_numpy(clips[0]).pin_memory().to(dev, non_blocking=True)
                 transform(fr, self.im_scale, self.input_size, frames_per_clip=self.sample_length, out=out[b])
             labels = torch.tensor([lab for _, lab, _ in item], dtype=torch.int64, device=dev)
             yield (out, labels, [p for _, _, p in item]) if with_paths else (out, labels)
-        th.join()
 
     def train_batches(self):
         return self._batches(self.train_range)

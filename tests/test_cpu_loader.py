@@ -116,3 +116,27 @@ def test_transform_without_gpu_is_a_loud_error():
         pytest.skip("GPU present")
     with pytest.raises(ValueError):
         vd.transform(torch.zeros((2, 8, 8, 3), dtype=torch.uint8))
+
+
+def test_host_batches_prefetch_thread(tmp_path):
+    """full batches in order, early exit stops the decode thread, decode errors reach the consumer"""
+    import threading
+    root = tmp_path / "videos" / "c"
+    root.mkdir(parents=True)
+    for i in range(5):
+        _write_video(str(root / f"v{i}.mp4"), 10 + i)
+    split = tmp_path / "s.txt"
+    split.write_text("".join(f"c/v{i},{i}\n" for i in range(5)))
+    ds = vd.VideoDataset(str(tmp_path / "videos"), sample_length=4, batch_size=2, prefetch=1,
+                         train_split_file=str(split), test_split_file=str(split))
+    got = list(ds._host_batches(ds.train_range))
+    assert [[lab for _, lab, _ in b] for b in got] == [[0, 1], [2, 3]]              # the odd fifth video is dropped
+    assert all(c.shape == (1, 4, 48, 64, 3) for b in got for c, _, _ in b)
+    n0 = threading.active_count()
+    it = ds._host_batches(ds.train_range)
+    next(it)
+    it.close()                                                                     # consumer walks away
+    assert threading.active_count() <= n0
+    os.remove(str(root / "v2.mp4"))
+    with pytest.raises(IOError, match="v2"):
+        list(ds._host_batches(ds.train_range))
