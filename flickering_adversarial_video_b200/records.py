@@ -287,6 +287,66 @@ class ClipRecordDataset:
             yield b
 
 
+def read_video_frames(path):
+    """all frames of a video file as uint8 RGB [N,H,W,3] (`skvideo.io.vread` in the reference,
+    kinetics_to_tf_record_uint8.py:79; here OpenCV's FFmpeg backend)"""
+    import cv2
+    cap = cv2.VideoCapture(path)
+    if not cap.isOpened():
+        raise IOError(f"cannot open video {path}")
+    frames = []
+    try:
+        while True:
+            ok, bgr = cap.read()
+            if not ok:
+                break
+            frames.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
+    finally:
+        cap.release()
+    if not frames:
+        raise IOError(f"no frame decoded from {path}")
+    return np.stack(frames)
+
+
+def videos_to_tfrecords(videos_base_path, class_name, tf_dst_folder, kinetics_classes, n_frames=90, videos_per_file=100,
+                        video_ext="mp4"):
+    """The reference's conversion script (kinetics_to_tf_record_uint8.py:21-98): for every class folder (or all of
+    them when class_name == 'all') the LAST `n_frames` frames of each video, undecimated and unresized (the Kinetics
+    crawler already stores 224x224 files), one `tf.train.Example` {train/label, train/video} per video, 100 videos per
+    `<dst>/<class>/kinetics_<class>_<k:04>.tfrecords`.  Videos shorter than n_frames are skipped (:84-85).  Unlike the
+    reference an undecodable file is skipped, not deleted (:82).  Returns the list of files written."""
+    import glob
+    classes = sorted(os.listdir(videos_base_path)) if class_name == "all" else [class_name]
+    written = []
+    for c in classes:
+        src = os.path.join(videos_base_path, c)
+        if not os.path.isdir(src):
+            print("{} not exist".format(src))
+            continue
+        cls_id = list(kinetics_classes).index(c)
+        writer, k, in_file = None, 0, 0
+        for v in sorted(glob.glob(os.path.join(src, "*." + video_ext))):
+            try:
+                frames = read_video_frames(v)
+            except IOError:
+                continue
+            if frames.shape[0] < n_frames:
+                continue
+            if writer is None or in_file == videos_per_file:
+                if writer is not None:
+                    writer.close()
+                    k += 1
+                os.makedirs(os.path.join(tf_dst_folder, c), exist_ok=True)
+                path = os.path.join(tf_dst_folder, c, "kinetics_{}_{:04}.tfrecords".format(c, k))
+                writer, in_file = TFRecordWriter(path), 0
+                written.append(path)
+            write_clip_record(writer, frames[-n_frames:], cls_id)
+            in_file += 1
+        if writer is not None:
+            writer.close()
+    return written
+
+
 # ---- TensorBoard scalars -----------------------------------------------------------------------
 class SummaryWriter:
     """events.out.tfevents.* with scalar summaries: Event{wall_time = 1 (double), step = 2 (int64), file_version = 3,

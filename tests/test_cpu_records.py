@@ -104,3 +104,30 @@ def test_tensorboard_scalars(tmp_path):
     ev = [bytes(p) for p in R.tfrecord_iterator(w2.path)][1]
     assert ev == bytes([0x09]) + bytes(8) + bytes([0x10, 50, 0x2A, 0x0A, 0x0A, 0x08, 0x0A, 0x01]) + b"a" + \
         bytes([0x15]) + struct.pack("<f", 1.0)
+
+
+def test_videos_to_tfrecords(tmp_path):
+    """kinetics_to_tf_record_uint8.py: last n frames of every long-enough video, 100 (here 2) videos per file"""
+    cv2 = pytest.importorskip("cv2")
+    src = tmp_path / "val"
+    lengths = {"hula hooping": [12, 5, 9, 8], "yoga": [8]}
+    for cls, ns in lengths.items():
+        (src / cls).mkdir(parents=True)
+        for i, n in enumerate(ns):
+            wr = cv2.VideoWriter(str(src / cls / f"v{i}.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 25.0, (32, 24))
+            if not wr.isOpened():
+                pytest.skip("OpenCV cannot encode mp4v here")
+            for t in range(n):
+                wr.write(np.full((24, 32, 3), 10 * t + 5, np.uint8))
+            wr.release()
+    (src / "yoga" / "broken.mp4").write_bytes(b"not a video")
+    classes = ["abseiling", "hula hooping", "yoga"]
+    files = R.videos_to_tfrecords(str(src), "all", str(tmp_path / "rec"), classes, n_frames=8, videos_per_file=2)
+    names = [f[len(str(tmp_path / "rec")) + 1:] for f in files]
+    assert names == ["hula hooping/kinetics_hula hooping_0000.tfrecords", "hula hooping/kinetics_hula hooping_0001.tfrecords",
+                     "yoga/kinetics_yoga_0000.tfrecords"]
+    got = [R.parse_clip_example(p, height=24, width=32) for f in files for p in R.tfrecord_iterator(f)]
+    assert [lab for _, lab in got] == [1, 1, 1, 2]                       # the 5-frame video and the broken file are skipped
+    ids = [[int(round((float(fr.mean()) - 5) / 10)) for fr in v] for v, _ in got]
+    assert ids == [list(range(4, 12)), list(range(1, 9)), list(range(0, 8)), list(range(0, 8))]      # the LAST 8 frames
+    assert R.videos_to_tfrecords(str(src), "missing class", str(tmp_path / "rec2"), classes + ["missing class"]) == []
