@@ -141,7 +141,7 @@ def test_single_video_90_frames_parity():
           f"dL/d-delta cosine {cos:.5f}")
     assert rel <= 1e-2 and logits.argmax(-1).tolist() == ref["logits"].argmax(-1).tolist()
     # one clip, 270 gradient entries of ~1e-3: bf16 storage alone gives 0.91 here (the bf16-emulating CPU oracle has
-    # the same cosine against the fp32 oracle, tools/debug_t90.py); kernels are gated stage by stage elsewhere
+    # the same cosine against the fp32 oracle, tests/debug_t90.py); kernels are gated stage by stage elsewhere
     assert cos >= 0.85
     eng.close()
 
