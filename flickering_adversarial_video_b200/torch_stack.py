@@ -181,6 +181,22 @@ class Adversarial_metrics:
         return thickness, roughness
 
 
+def step_lr_schedule(lr, epochs, start_epoch=1, lr_gamma=0.1, lr_step_size=None):
+    """{epoch: learning rate} of the reference's `torch.optim.lr_scheduler.StepLR(optimizer, step_size, gamma)` stepped
+    once after every epoch of `range(start_epoch, epochs + 1)` (model.py:495-497, 571-573, 587-608).  The schedule is
+    produced by torch's own scheduler on a dummy optimizer, so its rounding and step rules are the reference's."""
+    if lr_step_size is None:
+        lr_step_size = np.ceil(2 / 3 * epochs)
+    dummy = torch.optim.Adam([torch.zeros(1, requires_grad=True)], lr=lr)
+    sched = torch.optim.lr_scheduler.StepLR(dummy, step_size=int(lr_step_size), gamma=lr_gamma)
+    out = {}
+    for e in range(start_epoch, epochs + 1):
+        out[e] = float(dummy.param_groups[0]["lr"])
+        dummy.step()
+        sched.step()
+    return out
+
+
 class VideoLearnerAdversarial:
     """model.py:337-347.  `weights` is the torchvision state_dict of `base_model` (the reference downloads the
     pretrained one, :421; there is no network here)."""
@@ -227,13 +243,22 @@ class VideoLearnerAdversarial:
         self.pert_model.from_engine(atk.delta)
 
     # ---- universal attack: fit (model.py:460-628) with train_an_epoch (:630-788) --------------------------
-    def fit(self, lr, epochs, train_batches=None, valid_batches=None, model_dir="checkpoints", model_name=None,
-            loss_params_dict=None, save_model=True, start_epoch=0):
-        """train_batches / valid_batches: callables returning an iterable of (uint8 clips [B,T,H,W,3] DEVICE,
-        labels [B] DEVICE) per epoch; by default the `dataset` given to the constructor supplies them
-        (`video_dataset.VideoDataset.train_batches` / `.test_batches`, the reference's `dataset.train_dl` /
-        `.test_dl`, model.py:506-507).  Writes `{model_name}_{epoch:03d}.npy` (pickled list of per-epoch
-        OrderedDicts, model.py:619-623) and returns it."""
+    def fit(self, lr, epochs, model_dir="checkpoints", model_name=None, momentum=0.95, weight_decay=0.0001,
+            mixed_prec=False, use_one_cycle_policy=False, warmup_pct=0.3, lr_gamma=0.1, lr_step_size=None, grad_steps=2,
+            save_model=False, loss_params_dict=None, devices_ids=None, start_epoch=1, *, train_batches=None,
+            valid_batches=None):
+        """Same signature as the reference's `fit` (model.py:460-478).  Epochs run from `start_epoch` to `epochs`
+        INCLUSIVE (:587) and epoch e is saved as `{model_name}_{e:03d}.npy` (pickled list of per-epoch OrderedDicts,
+        :619-623); the learning rate follows the reference's StepLR (step `lr_step_size`, default ceil(2/3 * epochs),
+        factor `lr_gamma`, stepped once per epoch and restarted at `lr` on every call, :495-497, 571-573, 608).
+        `momentum`, `weight_decay` and `grad_steps` are unused by the reference's Adam loop as well; `mixed_prec` and
+        `devices_ids` have no meaning here (bf16 tensor-core engine, one process per GPU).
+        train_batches / valid_batches (keyword only): callables returning an iterable of (uint8 clips [B,T,H,W,3]
+        DEVICE, labels [B] DEVICE) per epoch; by default the `dataset` given to the constructor supplies them
+        (`video_dataset.VideoDataset.train_batches` / `.test_batches`, the reference's `dataset.train_dl` / `.test_dl`,
+        model.py:506-507).  Returns `self.results`."""
+        if use_one_cycle_policy:
+            raise NotImplementedError("use_one_cycle_policy: only the StepLR schedule of the attack drivers is built")
         if train_batches is None or valid_batches is None:
             if self.dataset is None:
                 raise ValueError("fit needs train_batches / valid_batches or a dataset")
@@ -241,6 +266,7 @@ class VideoLearnerAdversarial:
                 raise ValueError("dataset batch_size / sample_length differ from the learner's")
             train_batches = train_batches or self.dataset.train_batches
             valid_batches = valid_batches or self.dataset.test_batches
+        lr_schedule = step_lr_schedule(lr, epochs, start_epoch, lr_gamma, lr_step_size)
         lp = dict(loss_params_dict)
         metric = Adversarial_metrics(lp["targeted_attack"], lp.get("target_class_id"))
         atk = self._attack(lr, lp, self.batch_size)
@@ -248,7 +274,8 @@ class VideoLearnerAdversarial:
         os.makedirs(model_dir, exist_ok=True)
         model_name = model_name or self.model_name
         target = lp.get("target_class_id")
-        for e in range(start_epoch, start_epoch + epochs):
+        for e in range(start_epoch, epochs + 1):
+            lr_e = lr_schedule[e]
             result = OrderedDict()
             for phase, batches in (("train", train_batches), ("valid", valid_batches)):
                 t0 = time.time()
@@ -258,7 +285,7 @@ class VideoLearnerAdversarial:
                     lab = labels if not lp["targeted_attack"] else torch.full_like(labels, int(target))
                     clean = atk.predict(clips, adv_flag=0.0).clone()
                     if phase == "train":
-                        sc = atk.step(clips, lab)
+                        sc = atk.step(clips, lab, lr=lr_e)
                         loss = float(sc[L.S_TOTAL_LOSS])
                         # scores of the delta the step was computed with are still in the engine
                         adv_logits = atk.eng.logits.clone()
@@ -295,7 +322,7 @@ class VideoLearnerAdversarial:
                 result[f"{phase}/perturbation"] = pert
             self.results.append(result)
             if save_model:
-                np.save(os.path.join(model_dir, "{}_{:03d}.npy".format(model_name, e + 1)),
+                np.save(os.path.join(model_dir, "{}_{:03d}.npy".format(model_name, e)),
                         np.array(self.results, dtype=object), allow_pickle=True)
         return self.results
 
@@ -349,9 +376,13 @@ class VideoLearnerAdversarial:
         return res
 
     # ---- single-video attack over a dataset (model.py:789-979) -----------------------------------------------
-    def fit_many_videos(self, lr, epochs=1, model_dir="checkpoints", model_name=None, save_model=False,
-                        loss_params_dict=None, n_iter=3000, videos=None, max_restarts=4, restart_after=3000):
-        """`fit_many_videos`: one single-video attack per video of the dataset's training split.  For each video the
+    def fit_many_videos(self, lr, epochs=1, model_dir="checkpoints", model_name=None, momentum=0.95,
+                        weight_decay=0.0001, mixed_prec=False, use_one_cycle_policy=False, warmup_pct=0.3, lr_gamma=0.1,
+                        lr_step_size=None, grad_steps=2, save_model=False, loss_params_dict=None, devices_ids=None, *,
+                        n_iter=3000, videos=None, max_restarts=4, restart_after=3000):
+        """`fit_many_videos` (same positional signature as the reference, model.py:789-806; the optimiser / schedule
+        arguments are accepted and unused — the reference creates a scheduler here but never steps it in the
+        single-video loop): one single-video attack per video of the dataset's training split.  For each video the
         result goes to `{model_dir}/{video}_@{class_name}.npy` (spaces in the class name replaced by `_`); a video whose
         file already holds a successful attack is skipped, one whose file holds `None` (claimed by another run, or
         clean-misclassified) too; with `save_model` a `None` placeholder is written before the attack starts

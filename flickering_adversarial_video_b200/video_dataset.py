@@ -62,6 +62,34 @@ class VideoRecord:
         return None if len(self._data) <= 2 else self._data[2]
 
 
+class TransformSpec:
+    """What `get_transforms(train=False)` stands for here: the parameters of the fixed chain ToTensorVideo ->
+    ResizeVideo(im_scale, keep_ratio) -> CenterCropVideo(input_size) -> NormalizeVideo(mean, std) (dataset.py:84-123,
+    212-243); resize + crop run in `fav_op_resize_crop`, the normalisation in the engine's apply kernel."""
+
+    def __init__(self, im_scale=128, input_size=112, mean=DEFAULT_MEAN, std=DEFAULT_STD):
+        if tuple(mean) != DEFAULT_MEAN or tuple(std) != DEFAULT_STD:
+            raise NotImplementedError("the engine normalises with the Kinetics mean / std of dataset.py:28-29")
+        self.im_scale, self.input_size, self.mean, self.std = im_scale, input_size, tuple(mean), tuple(std)
+
+    def __eq__(self, other):
+        return isinstance(other, TransformSpec) and vars(self) == vars(other)
+
+    def __repr__(self):
+        return f"TransformSpec(im_scale={self.im_scale}, input_size={self.input_size})"
+
+
+def get_transforms(train=True, tfms_config=None):
+    """dataset.py:84-123.  Only the test-time chain exists (flip ratio 0, centre crop): the attack drivers build both
+    splits with `get_transforms(train=False)`.  `tfms_config`: an object / dict with `im_scale` and `input_size`."""
+    if train:
+        raise NotImplementedError("training-split augmentation (random resized crop, flip) is not built")
+    if tfms_config is None:
+        return TransformSpec()
+    get = tfms_config.get if isinstance(tfms_config, dict) else lambda k, d=None: getattr(tfms_config, k, d)
+    return TransformSpec(get("im_scale", 128), get("input_size", 112), get("mean", DEFAULT_MEAN), get("std", DEFAULT_STD))
+
+
 # ---- geometry of ResizeVideo + CenterCropVideo -----------------------------------------------------------------
 def resize_geometry(H, W, size=128, keep_ratio=True):
     """(resized_h, resized_w, ratio_h, ratio_w): transforms_video.py:23-53 over torch interpolate's size / ratio rules
@@ -195,10 +223,22 @@ class VideoDataset:
 
     def __init__(self, root, seed=None, train_pct=0.75, num_samples=1, sample_length=8, sample_step=1,
                  temporal_jitter=False, temporal_jitter_step=2, random_shift=False, batch_size=8, video_ext="mp4",
-                 warning=False, train_split_file=None, test_split_file=None, im_scale=128, input_size=112,
-                 device=0, prefetch=2):
+                 warning=False, train_split_file=None, test_split_file=None, train_transforms=None, test_transforms=None,
+                 *, im_scale=None, input_size=None, device=0, prefetch=2):
+        """Positional arguments as in the reference (dataset.py:249-266), except that `temporal_jitter` / `random_shift`
+        default to False (the attack mains always pass False).  `train_transforms` / `test_transforms` take what
+        `get_transforms(train=False)` of this module returns (a `TransformSpec`); both splits use the test-time chain."""
         assert sample_step > 0
         assert num_samples > 0
+        spec = test_transforms if test_transforms is not None else train_transforms
+        if spec is not None and not isinstance(spec, TransformSpec):
+            raise TypeError("train_transforms / test_transforms: pass video_dataset.get_transforms(train=False) "
+                            "(the transform chain runs as one CUDA kernel, not as Python callables)")
+        if train_transforms is not None and test_transforms is not None and train_transforms != test_transforms:
+            raise NotImplementedError("different transforms for the two splits")
+        spec = spec or TransformSpec()
+        im_scale = spec.im_scale if im_scale is None else im_scale
+        input_size = spec.input_size if input_size is None else input_size
         if temporal_jitter or random_shift:
             raise NotImplementedError("training-split augmentation (temporal jitter / random shift) is not built: the "
                                       "attack drivers evaluate both splits with the test-time sampling")

@@ -140,3 +140,23 @@ def test_host_batches_prefetch_thread(tmp_path):
     os.remove(str(root / "v2.mp4"))
     with pytest.raises(IOError, match="v2"):
         list(ds._host_batches(ds.train_range))
+
+
+def test_dataset_accepts_the_reference_call(tmp_path):
+    """the constructor call of r2plus1d_main_universal_attack.py:153-169, argument for argument"""
+    root = tmp_path / "videos" / "c"
+    root.mkdir(parents=True)
+    _write_video(str(root / "v0.mp4"), 12)
+    split = tmp_path / "s.txt"
+    split.write_text("c/v0,0\n")
+    ds = vd.VideoDataset(str(tmp_path / "videos"), seed=None, train_pct=0.75, num_samples=1, sample_length=16,
+                         sample_step=1, temporal_jitter=False, temporal_jitter_step=2, random_shift=False, batch_size=1,
+                         warning=False, train_split_file=str(split), test_split_file=str(split), video_ext="mp4",
+                         train_transforms=vd.get_transforms(train=False), test_transforms=vd.get_transforms(train=False))
+    assert (ds.im_scale, ds.input_size) == (128, 112) and len(ds) == 2
+    assert vd.VideoDataset(str(tmp_path / "videos"), train_split_file=str(split), test_split_file=str(split),
+                           test_transforms=vd.get_transforms(False, {"im_scale": 64, "input_size": 56})).input_size == 56
+    with pytest.raises(NotImplementedError):
+        vd.get_transforms(train=True)
+    with pytest.raises(TypeError):
+        vd.VideoDataset(str(tmp_path / "videos"), test_transforms=lambda x: x)

@@ -25,7 +25,7 @@ def test_universal_fit_layout(tmp_path):
     batches = lambda: [(c.cuda(), l.cuda()) for c, l in zip(clips, labels)]
     learner = VideoLearnerAdversarial(num_classes=400, base_model="mc3_18", sample_length=T, l_inf_pert_norm=0.1,
                                       attack_type="flickering", weights=model.state_dict(), batch_size=B)
-    res = learner.fit(lr=1e-3, epochs=2, train_batches=batches, valid_batches=batches, model_dir=str(tmp_path),
+    res = learner.fit(lr=1e-3, epochs=2, train_batches=batches, valid_batches=batches, model_dir=str(tmp_path), save_model=True,
                       model_name="mc3_18", loss_params_dict=LP)
     assert len(res) == 2
     for key in ("time", "loss", "fooling_ratio", "pert_thickness", "pert_roughness", "inf_norm", "perturbation"):
