@@ -179,7 +179,16 @@ def read_clip(path, offset, sample_length, sample_step=1, out=None):
         raise IOError(f"cannot open video {path}")
     try:
         if offset > 0:
+            # decord's seek_accurate (dataset.py:557): position on exactly frame `offset`.  OpenCV's FFmpeg backend
+            # seeks to the preceding key frame and decodes forward; if a container reports another position, fall
+            # back to decoding from the start.
             cap.set(cv2.CAP_PROP_POS_FRAMES, int(offset))
+            if int(round(cap.get(cv2.CAP_PROP_POS_FRAMES))) != int(offset):
+                cap.release()
+                cap = cv2.VideoCapture(path)
+                for _ in range(int(offset)):
+                    if not cap.grab():
+                        break
         n = 0
         for k in range(sample_length):
             if k > 0:
