@@ -90,3 +90,69 @@ def test_fit_many_videos_file_protocol(tmp_path):
     calls.clear()
     assert Learner().fit_many_videos(1e-3, model_dir=str(tmp_path), save_model=True, loss_params_dict=lp, videos=vids) == {}
     assert calls == []
+
+
+def test_fit_loop_epochs_schedule_and_files(tmp_path):
+    """model.py:587-623 on a stub engine: epochs start_epoch..epochs inclusive, StepLR learning rates handed to the
+    step, `{model_name}_{e:03d}.npy` per epoch, result keys — host logic only (the engine is stubbed)."""
+    import numpy as np
+    import torch
+    from flickering_adversarial_video_b200 import _lib as L
+    from flickering_adversarial_video_b200 import torch_stack as ts
+    T, B, K = 4, 2, 10
+    lrs = []
+
+    class Eng:
+        logits = torch.zeros((B, K))
+
+        def loss(self, lab, **kw):
+            sc = torch.zeros(L.S_COUNT)
+            sc[L.S_ADV_LOSS] = 0.25
+            return sc
+
+    class Atk:
+        device, pg, world, delta_clip = "cpu", None, 1, 0.1
+
+        def __init__(self):
+            self.delta, self.eng = torch.zeros((T, 3)), Eng()
+
+        def predict(self, clips, adv_flag=1.0):
+            z = torch.zeros((B, K))
+            z[:, 3] = 5.0 if adv_flag == 0.0 else -5.0          # clean: class 3; perturbed: anything else
+            self.eng.logits = z
+            return torch.softmax(z, -1)
+
+        def step(self, clips, lab, lr=None):
+            lrs.append(lr)
+            self.delta += 0.01
+            self.predict(clips, 1.0)
+            sc = torch.zeros(L.S_COUNT)
+            sc[L.S_TOTAL_LOSS], sc[L.S_ADV_LOSS] = 1.5, 1.0
+            return sc
+
+    class Learner(ts.VideoLearnerAdversarial):
+        def __init__(self):
+            self.results, self.dataset, self.batch_size, self.sample_length = [], None, B, T
+            self.model_name, self.attack_type = "r3d_18", "flickering"
+            self.pert_model = ts.Perturbation((3, T, 1, 1), device="cpu", max_norm=0.1)
+
+        def _attack(self, lr, lp, batch, sharded=True):
+            return Atk()
+
+    batches = lambda: [(torch.zeros((B, T, 8, 8, 3), dtype=torch.uint8), torch.tensor([3, 3]))] * 3
+    lp = {"lambda_": 1.0, "beta_1": 0.5, "targeted_attack": False, "target_class_id": None, "improve_loss": True,
+          "use_logits": False}
+    lrn = Learner()
+    res = lrn.fit(1e-2, 6, str(tmp_path), None, save_model=True, loss_params_dict=lp, start_epoch=2,
+                  train_batches=batches, valid_batches=batches)
+    assert len(res) == 5                                                      # epochs 2..6 inclusive
+    assert sorted(os.listdir(str(tmp_path))) == [f"r3d_18_{e:03d}.npy" for e in range(2, 7)]
+    # StepLR(step_size=ceil(2/3*6)=4, gamma=0.1), restarted at lr on this call: 4 epochs at 1e-2, then 1e-3
+    assert np.allclose(lrs, [1e-2] * 12 + [1e-3] * 3)
+    last = np.load(str(tmp_path / "r3d_18_006.npy"), allow_pickle=True)[-1]
+    assert last["valid/perturbation"].shape == (3, T, 1, 1) and last["train/fooling_ratio"] == 1.0
+    assert abs(last["train/loss"] - 1.5) < 1e-6 and abs(last["valid/pert_thickness"] - 0.1) < 1e-6     # clamped at 0.1
+    with pytest.raises(NotImplementedError):
+        lrn.fit(1e-2, 1, use_one_cycle_policy=True, loss_params_dict=lp, train_batches=batches, valid_batches=batches)
+    with pytest.raises(ValueError):
+        lrn.fit(1e-2, 1, loss_params_dict=lp)                                 # neither batch sources nor a dataset
