@@ -160,3 +160,29 @@ def test_dataset_accepts_the_reference_call(tmp_path):
         vd.get_transforms(train=True)
     with pytest.raises(TypeError):
         vd.VideoDataset(str(tmp_path / "videos"), test_transforms=lambda x: x)
+
+
+def test_batch_cache_is_transparent(tmp_path):
+    """cache=True: a split's batches are produced once; an abandoned first pass caches nothing"""
+    import torch
+    split = tmp_path / "s.txt"
+    split.write_text("")
+    made = []
+
+    def make():
+        made.append(1)
+        for i in range(3):
+            yield torch.full((2, 4), i, dtype=torch.uint8), torch.tensor([i, i])
+
+    ds = vd.VideoDataset(str(tmp_path), train_split_file=str(split), test_split_file=str(split), cache=True)
+    it = ds._cached("train", make)
+    next(it)
+    it.close()
+    assert "train" not in ds._cache                                  # incomplete pass
+    a = [(x.clone(), y.clone()) for x, y in ds._cached("train", make)]
+    b = list(ds._cached("train", make))
+    assert len(made) == 2 and len(b) == 3 and all(torch.equal(p[0], q[0]) and torch.equal(p[1], q[1]) for p, q in zip(a, b))
+    assert ds.cached_bytes() == 3 * (8 + 16)
+    ds2 = vd.VideoDataset(str(tmp_path), train_split_file=str(split), test_split_file=str(split))
+    list(ds2._cached("train", make)), list(ds2._cached("train", make))
+    assert len(made) == 4 and ds2._cache == {}                       # cache off: decoded every epoch
