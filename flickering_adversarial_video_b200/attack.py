@@ -113,6 +113,25 @@ class FlickerAttack:
                  self.beta3, lr=self.lr if lr is None else lr, delta_clip=self.delta_clip, stack=self.stack)
         return self.scalars
 
+    def step_rolled(self, clips, labels, shift, adv_flag=1.0, lr=None):
+        """Cyclic perturbation attack: the network sees roll(delta, shift) along T (TF: `tf.roll(input_pert,
+        random_shift_2, axis=0)`, utils/kinetics_i3d_utils.py:130-131,137; torch: `torch.roll(perturbation_normalize,
+        shifts, dims=1)`, model.py:91-92) and the gradient is rolled back onto delta.  The clamp mask of the update
+        commutes with the roll, the regularisers are roll-invariant (circular differences)."""
+        e = self.eng
+        rolled = torch.roll(self.delta, int(shift), dims=0).contiguous()
+        e.apply(clips, rolled, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        e.forward()
+        e.loss(labels, improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
+               margin=self.margin, global_batch=self.global_batch, stack=self.stack)
+        e.backward()
+        self.grad.copy_(torch.roll(self.grad, -int(shift), dims=0))       # d/d(delta) = roll^-1 of d/d(rolled)
+        if self.world > 1:
+            fdist.allreduce_sum_(self.comm, self.pg)
+        e.update(self.delta, self.grad, self.m, self.v, self.step_count, self.beta0, self.beta1, self.beta2,
+                 self.beta3, lr=self.lr if lr is None else lr, delta_clip=self.delta_clip, stack=self.stack)
+        return self.scalars
+
     # ---- CUDA graph of the whole step ----------------------------------------------------------
     def capture(self, clips, labels, adv_flag=1.0, lr=None):
         """Capture one step (all libfav launches + the NCCL all-reduce) into a CUDA graph bound to the
@@ -185,10 +204,12 @@ class FlickerAttack:
         return self._host_scalars[slot], self._done_events[slot]
 
     # ---- evaluation helpers (forward only) ---------------------------------------------------
-    def predict(self, clips, adv_flag=1.0):
+    def predict(self, clips, adv_flag=1.0, shift=0):
         """softmax [B,K] for clean (adv_flag=0) or perturbed clips — the reference's
-        `k_i3d(inputs, adv_flag)` (utils/kinetics_i3d_utils.py:210-212)."""
-        self.eng.apply(clips, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        `k_i3d(inputs, adv_flag)` (utils/kinetics_i3d_utils.py:210-212); `shift`: evaluate with roll(delta, shift)
+        (cyclic perturbation)."""
+        delta = self.delta if not shift else torch.roll(self.delta, int(shift), dims=0).contiguous()
+        self.eng.apply(clips, delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
         logits = self.eng.forward()
         return torch.softmax(logits, dim=-1)
 

@@ -171,19 +171,7 @@ class kinetics_i3d:
 
     def _step_rolled(self, clips, lab, flag, lr, shift):
         """cyclic perturbation attack: the network sees roll(delta, shift); the gradient is rolled back."""
-        a, e = self._atk, self._atk.eng
-        rolled = torch.roll(a.delta, shift, dims=0).contiguous()
-        e.apply(clips, rolled, adv_flag=flag, delta_clip=a.delta_clip)
-        e.forward()
-        e.loss(lab, improve_loss=a.improve_loss, targeted=a.targeted, use_logits=a.use_logits, margin=a.margin,
-               global_batch=a.global_batch, stack=a.stack)
-        e.backward()
-        # d/d(delta) = roll^-1 of d/d(rolled); the +-0.4 clip mask commutes with the roll
-        a.grad.copy_(torch.roll(a.grad, -shift, dims=0))
-        if a.world > 1:
-            torch.distributed.all_reduce(a.comm, group=a.pg)
-        e.update(a.delta, a.grad, a.m, a.v, a.step_count, a.beta0, a.beta1, a.beta2, a.beta3, lr=lr,
-                 delta_clip=a.delta_clip, stack=a.stack)
+        self._atk.step_rolled(clips, lab, shift, adv_flag=flag, lr=lr)
 
     def adversarial_inputs_rgb_of(self, inputs):
         """sess.run(adversarial_inputs_rgb, {inputs: rgb_sample}) — fp32 [B,T,224,224,3]."""

@@ -203,7 +203,7 @@ class VideoLearnerAdversarial:
 
     def __init__(self, dataset=None, num_classes=400, base_model="r2plus1d_18", sample_length=16, cyclic_pert=False,
                  l_inf_pert_norm=1.0, attack_type="flickering", labaels_id_to_text=None, weights=None, batch_size=8,
-                 device=0):
+                 device=0, seed=None):
         if base_model not in ("r3d_18", "mc3_18", "r2plus1d_18"):
             raise ValueError(f"base_model {base_model!r}: the engine implements r3d_18 / mc3_18 / r2plus1d_18")
         if weights is None:
@@ -217,6 +217,7 @@ class VideoLearnerAdversarial:
         self.model_name = base_model
         self.batch_size = batch_size
         self._weights, self._device = weights, device
+        self._rng = np.random.RandomState(seed)          # random shifts of the cyclic perturbation attack
         pert_size = (3, sample_length, 1, 1) if attack_type == "flickering" else (3, sample_length, 112, 112)
         self.pert_model = Perturbation(size=pert_size, device=torch.device("cuda", device), max_norm=l_inf_pert_norm,
                                        cyclic_pert=cyclic_pert)
@@ -226,6 +227,8 @@ class VideoLearnerAdversarial:
         cfg = {"LAMBDA": loss_params_dict["lambda_"], "BETA_1": loss_params_dict["beta_1"],
                "TARGETED_ATTACK": loss_params_dict["targeted_attack"], "IMPROVE_ADV_LOSS": loss_params_dict["improve_loss"],
                "USE_LOGITS": loss_params_dict["use_logits"], "PROB_MARGIN": 0.05}
+        if self.pert_model.cyclic_pert and self.attack_type != "flickering":
+            raise NotImplementedError("cyclic_pert is built for the flickering attack only")
         if self.attack_type == "flickering":
             atk = FlickerAttack(self._weights, batch, self.sample_length, cfg, num_classes=self.num_classes,
                                 device=self._device, lr=lr, arch=self.model_name,
@@ -238,6 +241,13 @@ class VideoLearnerAdversarial:
                                sharded=sharded)
         self.pert_model.bind(atk.eng)
         return atk
+
+    def _cyclic_shift(self):
+        """Perturbation.forward draws `np.random.randint(0, T)` per adversarial forward when cyclic_pert (model.py:91-92)"""
+        if not self.pert_model.cyclic_pert:
+            return 0
+        rng = getattr(self, "_rng", None) or np.random
+        return int(rng.randint(0, self.sample_length))
 
     def _sync_pert(self, atk):
         self.pert_model.from_engine(atk.delta)
@@ -284,13 +294,14 @@ class VideoLearnerAdversarial:
                 for clips, labels in batches():
                     lab = labels if not lp["targeted_attack"] else torch.full_like(labels, int(target))
                     clean = atk.predict(clips, adv_flag=0.0).clone()
+                    shift = self._cyclic_shift()
                     if phase == "train":
-                        sc = atk.step(clips, lab, lr=lr_e)
+                        sc = atk.step_rolled(clips, lab, shift, lr=lr_e) if shift else atk.step(clips, lab, lr=lr_e)
                         loss = float(sc[L.S_TOTAL_LOSS])
                         # scores of the delta the step was computed with are still in the engine
                         adv_logits = atk.eng.logits.clone()
                     else:
-                        atk.predict(clips, adv_flag=1.0)
+                        atk.predict(clips, adv_flag=1.0, shift=shift) if shift else atk.predict(clips, adv_flag=1.0)
                         sc = atk.eng.loss(lab, improve_loss=lp["improve_loss"], targeted=lp["targeted_attack"],
                                           use_logits=lp["use_logits"], margin=0.05, stack=L.FAV_STACK_TORCH)
                         self._sync_pert(atk)
@@ -354,7 +365,8 @@ class VideoLearnerAdversarial:
                 step = 0
             if new_chance == max_restarts:
                 break
-            sc = atk.step(clips, tgt).clone()
+            shift = self._cyclic_shift()
+            sc = (atk.step_rolled(clips, tgt, shift) if shift else atk.step(clips, tgt)).clone()
             pred = int(atk.eng.logits.argmax())
             is_adv = (pred == int(lp["target_class_id"])) if lp["targeted_attack"] else (pred != int(label))
             self._sync_pert(atk)

@@ -152,6 +152,20 @@ def test_fit_loop_epochs_schedule_and_files(tmp_path):
     last = np.load(str(tmp_path / "r3d_18_006.npy"), allow_pickle=True)[-1]
     assert last["valid/perturbation"].shape == (3, T, 1, 1) and last["train/fooling_ratio"] == 1.0
     assert abs(last["train/loss"] - 1.5) < 1e-6 and abs(last["valid/pert_thickness"] - 0.1) < 1e-6     # clamped at 0.1
+    # cyclic_pert (model.py:91-92): every adversarial forward sees the perturbation rolled by a fresh random shift
+    rolled = []
+    Atk.step_rolled = lambda self, clips, lab, shift, lr=None: (rolled.append(("train", shift)), Atk.step(self, clips, lab, lr))[1]
+    plain_predict = Atk.predict
+    Atk.predict = lambda self, clips, adv_flag=1.0, shift=0: (rolled.append(("valid", shift)) if shift else None,
+                                                                plain_predict(self, clips, adv_flag))[1]
+    cyc = Learner()
+    cyc.pert_model.cyclic_pert, cyc._rng = True, np.random.RandomState(0)
+    lrs.clear()
+    cyc.fit(1e-2, 2, str(tmp_path / "cyc"), loss_params_dict=lp, train_batches=batches, valid_batches=batches)
+    want = np.random.RandomState(0).randint(0, T, size=1000)                  # one draw per batch, train and valid alike
+    drawn = [int(w) for w in want[:12]]
+    assert [s for _, s in rolled] == [d for d in drawn if d] and len(lrs) == 6
+    assert {p for p, _ in rolled} == {"train", "valid"}
     with pytest.raises(NotImplementedError):
         lrn.fit(1e-2, 1, use_one_cycle_policy=True, loss_params_dict=lp, train_batches=batches, valid_batches=batches)
     with pytest.raises(ValueError):
