@@ -339,12 +339,21 @@ class VideoLearnerAdversarial:
 
     # ---- single-video attack (model.py:918-1203) --------------------------------------------------------------
     def fit_single_video(self, lr, n_iter, clip_u8, label, video_name="video", class_name=None, model_dir=None,
-                         loss_params_dict=None, max_restarts=4, restart_after=3000):
+                         loss_params_dict=None, max_restarts=4, restart_after=3000, reuse_attack=None):
         """One clip until `step >= n_iter and adversarial`; every `restart_after` steps without success
         dynamic_max_norm *= 1.3 (at most `max_restarts` times, model.py:1061-1066).  Returns the result dict the
-        reference saves as `{vid}_@{class}.npy` (:1194-1203), or None when the clean clip is misclassified."""
+        reference saves as `{vid}_@{class}.npy` (:1194-1203), or None when the clean clip is misclassified.
+        `reuse_attack`: an attack object of an earlier call (same loss parameters) to continue with — engine, packed
+        weights AND Adam state are kept, only the perturbation is re-read from `pert_model`; this is what the
+        reference's `fit_many_videos` does with its single optimizer (model.py:868, 949-952)."""
         lp = dict(loss_params_dict)
-        atk = self._attack(lr, lp, 1, sharded=False)      # single-video attacks are per-rank replicas (no collective)
+        if reuse_attack is None:
+            atk = self._attack(lr, lp, 1, sharded=False)      # single-video attacks are per-rank replicas (no collective)
+        else:
+            atk = reuse_attack
+            atk.lr, atk.delta_clip = lr, self.pert_model.dynamic_max_norm
+            atk.delta.copy_(self.pert_model.as_engine())
+            self.pert_model.bind(atk.eng)
         self._atk = atk
         clips = clip_u8.reshape(1, *clip_u8.shape[-4:]).contiguous()
         labels = torch.as_tensor([int(label)], dtype=torch.int64, device=atk.device)
@@ -353,8 +362,9 @@ class VideoLearnerAdversarial:
             return None
         tgt = labels if not lp["targeted_attack"] else torch.full_like(labels, int(lp["target_class_id"]))
         res = {"loss/total": [], "loss/adv_loss": [], "loss/reg_loss": [], "perturbation/thickness": [],
-               "perturbation/roughness": [], "perturbation/inf_norm": [], "perturbation": [],
-               "prob_clean_input": clean.cpu().numpy(), "label": int(label), "is_adversarial": []}
+               "perturbation/roughness": [], "perturbation/inf_norm": 0.0, "perturbation": [],
+               "prob_clean_input": atk.eng.logits.clone().cpu().numpy(),      # `outputs_no_adv`: the clean LOGITS (:1193)
+               "label": np.asarray([int(label)]), "is_adversarial": []}
         step = new_chance = 0
         is_adv = False
         while step < n_iter or not is_adv:
@@ -377,7 +387,7 @@ class VideoLearnerAdversarial:
             res["loss/reg_loss"].append(float(sc[L.S_TOTAL_LOSS] - sc[L.S_ADV_LOSS]))
             res["perturbation/thickness"].append(np.abs(pert).mean())
             res["perturbation/roughness"].append(np.abs(np.roll(pert, 1, 1) - pert).mean())
-            res["perturbation/inf_norm"].append(np.abs(pert).max())
+            res["perturbation/inf_norm"] = np.abs(pert).max()          # the reference keeps the final value only (:1199)
             res["perturbation"].append(pert)
             res["is_adversarial"].append(bool(is_adv))
             step += 1
@@ -411,7 +421,7 @@ class VideoLearnerAdversarial:
         rank, world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        out = {}
+        out, shared = {}, None
         for vid_num, (clip, target, vid_path) in enumerate(videos):
             if vid_num % world != rank:
                 continue
@@ -428,7 +438,8 @@ class VideoLearnerAdversarial:
             self.pert_model.perturbation = (torch.rand(self.pert_model.size, device=self.pert_model.device) * 2 - 1) * 0.005
             self.pert_model.dynamic_max_norm = self.pert_model.max_norm
             res = self.fit_single_video(lr, n_iter, clip, target, loss_params_dict=lp, max_restarts=max_restarts,
-                                        restart_after=restart_after)
+                                        restart_after=restart_after, reuse_attack=shared)
+            shared = self._atk             # one engine and ONE optimizer state for all videos, like the reference
             out[vid_name] = res
             if res is not None and save_model:
                 np.save(dest_path, res, allow_pickle=True)
