@@ -339,7 +339,8 @@ class VideoLearnerAdversarial:
 
     # ---- single-video attack (model.py:918-1203) --------------------------------------------------------------
     def fit_single_video(self, lr, n_iter, clip_u8, label, video_name="video", class_name=None, model_dir=None,
-                         loss_params_dict=None, max_restarts=4, restart_after=3000, reuse_attack=None):
+                         loss_params_dict=None, max_restarts=4, restart_after=3000, reuse_attack=None,
+                         reset_optimizer=False):
         """One clip until `step >= n_iter and adversarial`; every `restart_after` steps without success
         dynamic_max_norm *= 1.3 (at most `max_restarts` times, model.py:1061-1066).  Returns the result dict the
         reference saves as `{vid}_@{class}.npy` (:1194-1203), or None when the clean clip is misclassified.
@@ -353,6 +354,10 @@ class VideoLearnerAdversarial:
             atk = reuse_attack
             atk.lr, atk.delta_clip = lr, self.pert_model.dynamic_max_norm
             atk.delta.copy_(self.pert_model.as_engine())
+            if reset_optimizer:               # a fresh Adam per video instead of the reference's carried-over moments
+                atk.m.zero_()
+                atk.v.zero_()
+                atk.step_count.zero_()
             self.pert_model.bind(atk.eng)
         self._atk = atk
         clips = clip_u8.reshape(1, *clip_u8.shape[-4:]).contiguous()
@@ -401,7 +406,7 @@ class VideoLearnerAdversarial:
     def fit_many_videos(self, lr, epochs=1, model_dir="checkpoints", model_name=None, momentum=0.95,
                         weight_decay=0.0001, mixed_prec=False, use_one_cycle_policy=False, warmup_pct=0.3, lr_gamma=0.1,
                         lr_step_size=None, grad_steps=2, save_model=False, loss_params_dict=None, devices_ids=None, *,
-                        n_iter=3000, videos=None, max_restarts=4, restart_after=3000):
+                        n_iter=3000, videos=None, max_restarts=4, restart_after=3000, share_optimizer_state=True):
         """`fit_many_videos` (same positional signature as the reference, model.py:789-806; the optimiser / schedule
         arguments are accepted and unused — the reference creates a scheduler here but never steps it in the
         single-video loop): one single-video attack per video of the dataset's training split.  For each video the
@@ -411,7 +416,10 @@ class VideoLearnerAdversarial:
         (model.py:925-946).  Before every video the perturbation is re-drawn as U(-1,1) * 0.005 and
         `dynamic_max_norm` reset (:949-952).  `videos`: optional iterable of (uint8 DEVICE clip [T,H,W,3], label, path)
         replacing the dataset.  With torch.distributed initialised the videos are dealt round-robin to the ranks
-        (replicas only: no collective).  Returns {video name: result dict or None}."""
+        (replicas only: no collective).  `share_optimizer_state` (default True, the reference's behaviour): the
+        Adam moments and step count carry over from one video to the next because the reference re-draws the parameter
+        under ONE optimizer (model.py:868, 946-948); False starts every video with a fresh Adam.  Returns
+        {video name: result dict or None}."""
         lp = dict(loss_params_dict)
         os.makedirs(model_dir, exist_ok=True)
         if videos is None:
@@ -438,7 +446,8 @@ class VideoLearnerAdversarial:
             self.pert_model.perturbation = (torch.rand(self.pert_model.size, device=self.pert_model.device) * 2 - 1) * 0.005
             self.pert_model.dynamic_max_norm = self.pert_model.max_norm
             res = self.fit_single_video(lr, n_iter, clip, target, loss_params_dict=lp, max_restarts=max_restarts,
-                                        restart_after=restart_after, reuse_attack=shared)
+                                        restart_after=restart_after, reuse_attack=shared,
+                                        reset_optimizer=not share_optimizer_state)
             shared = self._atk             # one engine and ONE optimizer state for all videos, like the reference
             out[vid_name] = res
             if res is not None and save_model:

@@ -71,7 +71,7 @@ def test_fit_many_videos_file_protocol(tmp_path):
         def fit_single_video(self, lr, n_iter, clip_u8, label, **kw):
             assert kw["max_restarts"] == 4 and kw["restart_after"] == 3000
             # one engine / one Adam state for all videos (model.py:868): the attack of the previous video is handed back
-            assert kw["reuse_attack"] is (None if not calls else self._atk)
+            assert kw["reuse_attack"] is (None if not calls else self._atk) and kw["reset_optimizer"] is False
             self._atk = getattr(self, "_atk", None) or object()
             calls.append((label, float(self.pert_model.perturbation.abs().max()), self.pert_model.dynamic_max_norm))
             if label == 1:
