@@ -20,12 +20,16 @@ from .engine import FlickerEngine
 
 class FlickerAttack:
     def __init__(self, weights, batch, frames, attack_cfg=None, height=None, width=None, num_classes=400,
-                 device=0, lr=1e-3, stack=None, delta_clip=None, process_group=None, arch="i3d", sharded=True):
+                 device=0, lr=1e-3, stack=None, delta_clip=None, process_group=None, arch="i3d", sharded=True,
+                 frame_range=None):
         """arch "i3d": TF-stack rules, delta_clip 0.4 (utils/kinetics_i3d_utils.py:104-105).
         arch "r3d_18"/"mc3_18"/"r2plus1d_18": torch-stack rules (model.py:58-250): delta_clip is
         l_inf_pert_norm, the regulariser is beta_1*thick + (1-beta_1)*(diff+lap) on the clamped delta.
         sharded=False: this attack is a per-rank replica (single-video attacks: every rank works on its own
-        video) and never joins a collective even when torch.distributed is initialised."""
+        video) and never joins a collective even when torch.distributed is initialised.
+        frame_range=(start, end): the reference's `_IND_START` / `_IND_END` frame mask (utils/kinetics_i3d_utils.py:14-15,
+        107-113: delta acts on frames start..end inclusive, the out-of-range index `end == T` is dropped by one_hot);
+        None = the reference's default, every frame."""
         self.eng = FlickerEngine(batch, frames, height, width, num_classes, device, arch=arch)
         self.eng.load_weights(weights)
         self.arch = arch
@@ -66,6 +70,11 @@ class FlickerAttack:
         self.comm = torch.zeros(n + L.S_COUNT, dtype=torch.float32, device=self.device)
         self.grad = self.comm[:n].view(frames, 3)
         self.scalars = self.comm[n:]
+        self.frame_mask = None
+        if frame_range is not None and tuple(frame_range) != (0, frames) and tuple(frame_range) != (0, frames - 1):
+            start, end = int(frame_range[0]), min(int(frame_range[1]), frames - 1)
+            self.frame_mask = torch.zeros((frames, 1), dtype=torch.float32, device=self.device)
+            self.frame_mask[start:end + 1] = 1.0
         self.eng.grad = self.grad
         self.eng.scalars = self.scalars
         # host staging for the end-to-end path
@@ -101,17 +110,23 @@ class FlickerAttack:
         """clips: DEVICE uint8/float32 [B,T,H,W,3]; labels: DEVICE int64 [B] (the target class ids
         for a targeted attack).  Asynchronous; returns the device scalar block (see _lib.S_*)."""
         e = self.eng
-        e.apply(clips, self.delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
+        e.apply(clips, self._applied_delta(), adv_flag=adv_flag, delta_clip=self.delta_clip)
         e.forward()
         gscale = 1.0
         e.loss(labels, improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
                margin=self.margin, grad_scale=gscale, global_batch=self.global_batch, stack=self.stack)
         e.backward()
+        if self.frame_mask is not None:
+            self.grad.mul_(self.frame_mask)
         if self.world > 1:
             fdist.allreduce_sum_(self.comm, self.pg)
         e.update(self.delta, self.grad, self.m, self.v, self.step_count, self.beta0, self.beta1, self.beta2,
                  self.beta3, lr=self.lr if lr is None else lr, delta_clip=self.delta_clip, stack=self.stack)
         return self.scalars
+
+    def _applied_delta(self):
+        """mask_rgb * eps_rgb (utils/kinetics_i3d_utils.py:128): delta as the network sees it"""
+        return self.delta if self.frame_mask is None else self.delta * self.frame_mask
 
     def step_rolled(self, clips, labels, shift, adv_flag=1.0, lr=None):
         """Cyclic perturbation attack: the network sees roll(delta, shift) along T (TF: `tf.roll(input_pert,
@@ -119,13 +134,15 @@ class FlickerAttack:
         shifts, dims=1)`, model.py:91-92) and the gradient is rolled back onto delta.  The clamp mask of the update
         commutes with the roll, the regularisers are roll-invariant (circular differences)."""
         e = self.eng
-        rolled = torch.roll(self.delta, int(shift), dims=0).contiguous()
+        rolled = torch.roll(self._applied_delta(), int(shift), dims=0).contiguous()
         e.apply(clips, rolled, adv_flag=adv_flag, delta_clip=self.delta_clip)
         e.forward()
         e.loss(labels, improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
                margin=self.margin, global_batch=self.global_batch, stack=self.stack)
         e.backward()
         self.grad.copy_(torch.roll(self.grad, -int(shift), dims=0))       # d/d(delta) = roll^-1 of d/d(rolled)
+        if self.frame_mask is not None:
+            self.grad.mul_(self.frame_mask)
         if self.world > 1:
             fdist.allreduce_sum_(self.comm, self.pg)
         e.update(self.delta, self.grad, self.m, self.v, self.step_count, self.beta0, self.beta1, self.beta2,
@@ -208,7 +225,9 @@ class FlickerAttack:
         """softmax [B,K] for clean (adv_flag=0) or perturbed clips — the reference's
         `k_i3d(inputs, adv_flag)` (utils/kinetics_i3d_utils.py:210-212); `shift`: evaluate with roll(delta, shift)
         (cyclic perturbation)."""
-        delta = self.delta if not shift else torch.roll(self.delta, int(shift), dims=0).contiguous()
+        delta = self._applied_delta()
+        if shift:
+            delta = torch.roll(delta, int(shift), dims=0).contiguous()
         self.eng.apply(clips, delta, adv_flag=adv_flag, delta_clip=self.delta_clip)
         logits = self.eng.forward()
         return torch.softmax(logits, dim=-1)
@@ -218,10 +237,10 @@ class FlickerAttack:
         ((adv+1.0)*127.5).astype(uint8) (utils/stats_and_plot/stats_plots.py:57)."""
         if as_uint8:
             out = torch.empty(clips.shape, dtype=torch.uint8, device=self.device)
-            self.eng.apply(clips, self.delta, delta_clip=self.delta_clip, adv_u8=out)
+            self.eng.apply(clips, self._applied_delta(), delta_clip=self.delta_clip, adv_u8=out)
         else:
             out = torch.empty(clips.shape, dtype=torch.float32, device=self.device)
-            self.eng.apply(clips, self.delta, delta_clip=self.delta_clip, adv_f32=out)
+            self.eng.apply(clips, self._applied_delta(), delta_clip=self.delta_clip, adv_f32=out)
         return out
 
     def close(self):

@@ -60,7 +60,7 @@ class kinetics_i3d:
     def __init__(self, ckpt_path="data/checkpoints/rgb_imagenet/model.ckpt", batch_size=1, init_model=True,
                  rgb_input=None, labels=None, cyclic_flag_default_c=0.0, cyclic_pert_flag_default_c=0.0,
                  default_adv_flag_c=1.0, frames=_SAMPLE_VIDEO_FRAMES, weights=None, device=0,
-                 label_map_path=_LABEL_MAP_PATH, seed=0, sharded=True):
+                 label_map_path=_LABEL_MAP_PATH, seed=0, sharded=True, frame_range=None):
         self.ckpt_path = ckpt_path
         self.batch_size = batch_size
         self.frames = frames
@@ -70,7 +70,8 @@ class kinetics_i3d:
         self.kinetics_classes = load_kinetics_classes(label_map_path=label_map_path)
         w = load_weights(weights if weights is not None else ckpt_path)
         # sharded=False: a per-rank replica (single-video attacks under torchrun), never joins a collective
-        self._atk = FlickerAttack(w, batch_size, frames, {}, device=device, sharded=sharded)
+        # frame_range = (_IND_START, _IND_END) of utils/kinetics_i3d_utils.py:14-15 (module constants there); None = all frames
+        self._atk = FlickerAttack(w, batch_size, frames, {}, device=device, sharded=sharded, frame_range=frame_range)
         self.device = self._atk.device
         self._rng = np.random.RandomState(seed)
         self._loss_cfg = dict(improve=True, margin=0.05, targeted=False, logits=False)

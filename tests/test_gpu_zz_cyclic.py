@@ -54,3 +54,26 @@ def test_step_rolled_matches_oracle():
     atk2 = FlickerAttack(model.state_dict(), B, T, cfg, arch="r3d_18", delta_clip=max_norm)
     atk2.delta.copy_(torch.roll(atk.delta, shift, 0))
     assert torch.allclose(p, atk2.predict(clip.cuda(), adv_flag=1.0).cpu(), rtol=0, atol=1e-6)
+
+
+def test_frame_range_mask():
+    """`_IND_START` / `_IND_END` (utils/kinetics_i3d_utils.py:14-15,107-113): delta acts on a frame range only"""
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.attack import FlickerAttack
+    T, lo, hi = 16, 4, 9
+    weights = synthetic.i3d_weights(seed=0)
+    clips = synthetic.clips_u8(1, T, seed=1001).cuda()
+    delta = synthetic.delta_uniform(T, seed=7, lo=-0.05, hi=0.05).cuda()
+    mask = torch.zeros((T, 1), device="cuda")
+    mask[lo:hi + 1] = 1.0
+    atk = FlickerAttack(weights, 1, T, {}, frame_range=(lo, hi))
+    atk.delta.copy_(delta)
+    plain = FlickerAttack(weights, 1, T, {})
+    plain.delta.copy_(delta * mask)
+    assert torch.equal(atk.adversarial_video(clips, as_uint8=True), plain.adversarial_video(clips, as_uint8=True))
+    assert FlickerAttack(weights, 1, T, {}, frame_range=(0, T)).frame_mask is None        # the reference's default
+    labels = plain.predict(clips, adv_flag=0.0).argmax(-1)
+    atk.step(clips, labels)
+    torch.cuda.synchronize()
+    g = atk.grad.cpu()
+    assert float(g[:lo].abs().max()) == 0.0 and float(g[hi + 1:].abs().max()) == 0.0 and float(g[lo:hi + 1].abs().sum()) > 0.0
