@@ -86,6 +86,22 @@ class kinetics_i3d:
 
     perturbation = eps_rgb
 
+    def _clips_of_last_run(self):
+        clips = self.__dict__.get("_last_clips")
+        if clips is None:
+            raise AttributeError("no input has been run yet (the reference fetches this handle with a feed_dict)")
+        return clips
+
+    @property
+    def softmax_clean(self):
+        """softmax of the unperturbed input of the last run (utils/kinetics_i3d_utils.py:146-149), evaluated on demand"""
+        return self._atk.predict(self._clips_of_last_run(), adv_flag=0.0).cpu().numpy()
+
+    @property
+    def adversarial_inputs_rgb(self):
+        """clip(input + adv_flag * perturbation, -1, 1) for the input of the last run (:139-142), fp32 [B,T,224,224,3]"""
+        return self._atk.adversarial_video(self._clips_of_last_run()).cpu().numpy()
+
     def set_perturbation(self, value):
         self._atk.delta.copy_(torch.as_tensor(np.asarray(value), dtype=torch.float32).reshape(self.frames, 3))
 
@@ -122,6 +138,7 @@ class kinetics_i3d:
     def __call__(self, inputs, adv_flag=0):
         """softmax for `inputs` (utils/kinetics_i3d_utils.py:210-212)."""
         clips = self._to_device_clip(inputs)
+        self._last_clips = clips
         self.prob = self._atk.predict(clips, adv_flag=float(adv_flag)).cpu().numpy()
         return self.prob
 
@@ -145,6 +162,7 @@ class kinetics_i3d:
         if cycp:      # tf.roll(input_pert, random_shift_2, axis=0) (:130-131,137)
             shift_p = int(self._rng.randint(0, self.frames))
         a.beta0, a.beta1, a.beta2, a.beta3 = float(beta_0), float(beta_1), float(beta_2), float(beta_3)
+        self._last_clips = clips
         if shift_p:
             self._step_rolled(clips, lab, flag, float(learning_rate), shift_p)
         else:

@@ -77,3 +77,26 @@ def test_frame_range_mask():
     torch.cuda.synchronize()
     g = atk.grad.cpu()
     assert float(g[:lo].abs().max()) == 0.0 and float(g[hi + 1:].abs().max()) == 0.0 and float(g[lo:hi + 1].abs().sum()) > 0.0
+
+
+def test_on_demand_handles_of_the_tf_mirror():
+    """`softmax_clean` and `adversarial_inputs_rgb` of kinetics_i3d (utils/kinetics_i3d_utils.py:139-149): evaluated for
+    the input of the last run"""
+    import numpy as np
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.kinetics_i3d import kinetics_i3d
+    T = 16
+    k = kinetics_i3d(ckpt_path="", batch_size=1, frames=T, weights=synthetic.i3d_weights(0))
+    with pytest.raises(AttributeError):
+        k.softmax_clean
+    clip = synthetic.clips_u8(1, T, seed=1001).numpy()
+    clean = k(clip, adv_flag=0)
+    k.improve_adversarial_loss(margin=0.05, targeted=False, logits=False)
+    k.train_step(clip, [int(clean.argmax())], learning_rate=1e-3, beta_0=1.0, beta_1=0.5, beta_2=0.5, beta_3=0.5)
+    assert np.allclose(k.softmax_clean, clean, atol=1e-6)
+    adv = k.adversarial_inputs_rgb
+    assert adv.shape == (1, T, 224, 224, 3) and adv.dtype == np.float32
+    x = clip.astype(np.float32) / 128.0 - 1.0
+    d = np.clip(k.eps_rgb.reshape(1, T, 1, 1, 3), -0.4, 0.4)
+    assert np.allclose(adv, np.clip(x + d, -1.0, 1.0), atol=1e-6)
+    k.close()
