@@ -267,24 +267,39 @@ class ClipRecordDataset:
             return
         import queue
         q = queue.Queue(maxsize=self.prefetch)
-        stop = object()
+        done, stop = object(), threading.Event()
+
+        def put(item):                     # gives up when the consumer abandoned the iterator
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def work():
             try:
                 for b in self._batches():
-                    q.put(b)
-                q.put(stop)
+                    if not put(b):
+                        return
+                put(done)
             except BaseException as e:     # surface reader errors in the consumer
-                q.put(e)
+                put(e)
 
-        threading.Thread(target=work, daemon=True).start()
-        while True:
-            b = q.get()
-            if b is stop:
-                return
-            if isinstance(b, BaseException):
-                raise b
-            yield b
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        try:
+            while True:
+                b = q.get()
+                if b is done:
+                    return
+                if isinstance(b, BaseException):
+                    raise b
+                yield b
+        finally:
+            stop.set()
+            th.join()
 
 
 def read_video_frames(path):

@@ -131,3 +131,22 @@ def test_videos_to_tfrecords(tmp_path):
     ids = [[int(round((float(fr.mean()) - 5) / 10)) for fr in v] for v, _ in got]
     assert ids == [list(range(4, 12)), list(range(1, 9)), list(range(0, 8)), list(range(0, 8))]      # the LAST 8 frames
     assert R.videos_to_tfrecords(str(src), "missing class", str(tmp_path / "rec2"), classes + ["missing class"]) == []
+
+
+def test_prefetch_thread_stops_with_the_consumer(tmp_path):
+    import threading
+    p = str(tmp_path / "k.tfrecords")
+    with R.TFRecordWriter(p) as w:
+        for i in range(6):
+            R.write_clip_record(w, np.full((2, 224, 224, 3), i, np.uint8), i)
+    n0 = threading.active_count()
+    it = iter(R.ClipRecordDataset([p], batch_size=1, prefetch=1))
+    v, l = next(it)
+    assert int(l[0]) == 0 and v.shape == (1, 2, 224, 224, 3)
+    it.close()
+    assert threading.active_count() <= n0
+    assert [int(l[0]) for _, l in R.ClipRecordDataset([p], batch_size=1, prefetch=2)] == list(range(6))
+    bad = str(tmp_path / "bad.tfrecords")
+    open(bad, "wb").write(open(p, "rb").read()[:-7])
+    with pytest.raises(IOError):
+        list(R.ClipRecordDataset([bad], batch_size=1, prefetch=2))
