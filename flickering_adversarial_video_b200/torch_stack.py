@@ -227,6 +227,12 @@ class VideoLearnerAdversarial:
         cfg = {"LAMBDA": loss_params_dict["lambda_"], "BETA_1": loss_params_dict["beta_1"],
                "TARGETED_ATTACK": loss_params_dict["targeted_attack"], "IMPROVE_ADV_LOSS": loss_params_dict["improve_loss"],
                "USE_LOGITS": loss_params_dict["use_logits"], "PROB_MARGIN": 0.05}
+        mean, std = np.array(DEFAULT_MEAN), np.array(DEFAULT_STD)
+        if not (np.isclose(self.pert_model.max_value, np.min((1 - mean) / std)) and
+                np.isclose(self.pert_model.min_value, np.max((0.0 - mean) / std))):
+            # the apply kernel clamps to the reference's default scalar bounds (model.py:72-75); other bounds are refused
+            # rather than silently ignored (the attack mains never pass them)
+            raise NotImplementedError("Perturbation max_value / min_value other than the defaults")
         if self.pert_model.cyclic_pert and self.attack_type != "flickering":
             raise NotImplementedError("cyclic_pert is built for the flickering attack only")
         if self.attack_type == "flickering":
