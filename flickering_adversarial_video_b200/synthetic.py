@@ -97,6 +97,40 @@ def delta_uniform(frames, seed=7, lo=-0.5, hi=0.5):
 
 
 # ---- torch stack: torchvision video ResNets (utils_cv/action_recognition/model.py:403-441) -------------
+def i3d_weights_framework_default(seed=0, num_classes=400):
+    """The second fixture of SURVEY §8(d): the frameworks' DEFAULT initialisers, "random-init" taken literally —
+    Sonnet's Conv3D default is a truncated normal (±2σ) with σ = 1/√fan_in and zero bias, snt.BatchNorm starts with
+    β = 0, moving mean 0, moving variance 1 [dep: dm-sonnet 1.23].  Through ~22 ReLU layers the activations shrink by
+    ≈ 2⁻¹¹ and the softmax is near-uniform, so this fixture probes the small-signal regime rather than parity margins."""
+    g = torch.Generator().manual_seed(seed)
+
+    def trunc(shape, std):
+        w = torch.empty(shape)
+        torch.nn.init.trunc_normal_(w, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=g)
+        return w
+
+    out = {}
+    for scope, k, cin, cout in i3d_units():
+        out[ROOT + scope + "/conv_3d/w"] = trunc((k, k, k, cin, cout), (k * k * k * cin) ** -0.5).numpy()
+        out[ROOT + scope + "/batch_norm/beta"] = np.zeros((1, 1, 1, 1, cout), np.float32)
+        out[ROOT + scope + "/batch_norm/moving_mean"] = np.zeros((1, 1, 1, 1, cout), np.float32)
+        out[ROOT + scope + "/batch_norm/moving_variance"] = np.ones((1, 1, 1, 1, cout), np.float32)
+    out[ROOT + "Logits/Conv3d_0c_1x1/conv_3d/w"] = trunc((1, 1, 1, 1024, num_classes), 1024 ** -0.5).numpy()
+    out[ROOT + "Logits/Conv3d_0c_1x1/conv_3d/b"] = np.zeros((num_classes,), np.float32)
+    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+
+
+def resnet_model_framework_default(arch, seed=0, num_classes=400):
+    """torchvision.models.video.<arch>(weights=None) exactly as torchvision initialises it (kaiming fan_out convs,
+    BatchNorm weight 1 / bias 0 / running stats 0 and 1, Linear N(0, 0.01)), eval mode — the torch half of the second
+    fixture of SURVEY §8(d)."""
+    import torchvision
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        model = getattr(torchvision.models.video, arch)(weights=None, num_classes=num_classes)
+    return model.eval()
+
+
 def resnet_model(arch, seed=0, num_classes=400, head_gain=10.0):
     """Random-init torchvision.models.video.<arch> in eval mode: torchvision's own initialisers under a
     fixed seed, plus non-trivial BatchNorm statistics (so the fold is exercised) and a head scaled so the

@@ -173,3 +173,17 @@ def test_split_stem_evaluation_equals_plain_evaluation(small):
                           m.w[O.ROOT + "Conv3d_1a_7x7/conv_3d/w"], (2, 2, 2))
         y_ref = O.conv3d_same(adv.permute(0, 4, 1, 2, 3), m.w[O.ROOT + "Conv3d_1a_7x7/conv_3d/w"], (2, 2, 2))
     assert float((y - y_ref).abs().max()) < 1e-9
+
+
+def test_framework_default_init_fixture():
+    """the second fixture of SURVEY §8(d): Sonnet / torchvision default initialisers (small-signal regime)"""
+    import numpy as np
+    from flickering_adversarial_video_b200 import synthetic
+    w, he = synthetic.i3d_weights_framework_default(0), synthetic.i3d_weights(0)
+    assert set(w) == set(he) and all(w[k].shape == he[k].shape for k in w)
+    k = "RGB/inception_i3d/Conv3d_2c_3x3/conv_3d/w"
+    sigma = (27 * 64) ** -0.5
+    assert np.abs(w[k]).max() <= 2 * sigma + 1e-7 and abs(w[k].std() / sigma - 0.880) < 0.01     # truncated at 2 sigma
+    assert (w["RGB/inception_i3d/Conv3d_2c_3x3/batch_norm/moving_variance"] == 1).all()
+    m = synthetic.resnet_model_framework_default("r3d_18")
+    assert not m.training and float(m.fc.weight.std()) < 0.05

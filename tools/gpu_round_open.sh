@@ -17,9 +17,10 @@ for a in "i3d 8 64" "r3d_18 16 16" "r2plus1d_18 16 16"; do
   run torch_ref_$n 600 python tests/gpu_torch_reference_timing.py $a
   run torch_ref_tf32_$n 600 python tests/gpu_torch_reference_timing.py $a --tf32
 done
+run default_init_check 600 python tests/gpu_default_init_check.py
 if timeout 300 python tools/profile_step.py > gpurun_out/plain.log 2>&1; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
   echo "ncu launch list exit $?" >> gpurun_out/summary.txt
 fi
-cat gpurun_out/summary.txt; tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json; tail -n 1 gpurun_out/torch_ref_*.log
+cat gpurun_out/summary.txt; tail -3 gpurun_out/pytest_gpu.log; grep init gpurun_out/default_init_check.log; cat gpurun_out/bench.json; tail -n 1 gpurun_out/torch_ref_*.log
