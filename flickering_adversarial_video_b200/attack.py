@@ -124,6 +124,12 @@ class FlickerAttack:
                  self.beta3, lr=self.lr if lr is None else lr, delta_clip=self.delta_clip, stack=self.stack)
         return self.scalars
 
+    def check_replicas(self):
+        """Raise if the replicated perturbation has diverged between ranks (sharded attacks only; a collective: every
+        rank must call it at the same step)."""
+        if self.world > 1 and not fdist.replicas_equal(self.delta, self.pg):
+            raise RuntimeError("the perturbation differs between ranks: the replicas have diverged")
+
     def _applied_delta(self):
         """mask_rgb * eps_rgb (utils/kinetics_i3d_utils.py:128): delta as the network sees it"""
         return self.delta if self.frame_mask is None else self.delta * self.frame_mask
@@ -295,6 +301,10 @@ class SparseAttack:
         self.grad = torch.zeros_like(self.delta)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.scalars = self.eng.scalars
+
+    def check_replicas(self):
+        if self.world > 1 and not fdist.replicas_equal(self.delta, self.pg):
+            raise RuntimeError("the perturbation differs between ranks: the replicas have diverged")
 
     @property
     def perturbation(self):

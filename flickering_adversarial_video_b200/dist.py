@@ -56,3 +56,16 @@ def sum_counts(values, device="cpu", group=None):
     t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.tolist()
+
+
+def replicas_equal(t, group=None):
+    """True when `t` (the replicated perturbation / Adam state) is bit-identical on every rank: one MAX all-reduce of
+    [t, -t] gives the element-wise max and min over ranks, which coincide only if all ranks agree.  The sharded attacks
+    rely on this (every rank applies the same update to its own copy after the gradient all-reduce); drivers call it
+    periodically.  One rank: trivially True."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return True
+    both = torch.cat([t.reshape(-1), -t.reshape(-1)]).contiguous()
+    dist.all_reduce(both, op=dist.ReduceOp.MAX, group=group)
+    n = t.numel()
+    return bool(torch.equal(both[:n], -both[n:]))

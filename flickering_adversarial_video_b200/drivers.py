@@ -168,6 +168,7 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
             labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
             out = k_i3d.train_step(rgb_sample, labels, **kw)
             if step % 50 == 0:      # SummarySaverHook(save_steps=50) universal.py:198-201
+                k_i3d._atk.check_replicas()       # sharded run: the replicated perturbation must be identical on all ranks
                 eps = k_i3d.eps_rgb
                 vals = (out["loss"], out["adversarial_loss"], out["regularizer_loss"], out.get("norm_reg", float("nan")),
                         out.get("diff_norm_reg", float("nan")), out.get("laplacian_norm_reg", float("nan")), out["thickness_relative"],

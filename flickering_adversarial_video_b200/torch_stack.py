@@ -325,6 +325,7 @@ class VideoLearnerAdversarial:
                     loss_sum += loss * labels.numel()
                     n_seen += labels.numel()
                 self._sync_pert(atk)
+                atk.check_replicas()          # sharded run: the replicated perturbation must be identical on all ranks
                 pert = self.pert_model.get_perturbation()[0].detach().cpu().numpy()
                 # sharded epochs (one process per GPU, each over its shard of the clips): metrics over all ranks
                 if atk.world > 1:

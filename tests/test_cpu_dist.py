@@ -133,6 +133,31 @@ def test_validation_counts_are_summed_over_ranks():
     assert ret[0] == ret[1] == [7.0, 30.0]
 
 
+def _replica_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from flickering_adversarial_video_b200 import dist as fdist
+    fdist.init_from_env("gloo")
+    same = torch.arange(48, dtype=torch.float32).reshape(16, 3) * 0.01 - 0.2
+    ok = fdist.replicas_equal(same)
+    drift = same.clone()
+    if rank == 1:
+        drift[5, 2] += 1e-7                                   # one ulp-scale difference on one rank
+    bad = fdist.replicas_equal(drift)
+    ret[rank] = (ok, bad)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replica_divergence_is_detected():
+    from flickering_adversarial_video_b200 import dist as fdist
+    assert fdist.replicas_equal(torch.zeros(3)) is True       # no process group
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_replica_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0] == ret[1] == (True, False)
+
+
 def test_shard_range_rules():
     from flickering_adversarial_video_b200 import dist as fdist
     assert fdist.shard_range(64, 3, 8) == (24, 32)
