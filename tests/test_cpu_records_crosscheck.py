@@ -229,3 +229,37 @@ def test_checkpoint_index_protos_against_protobuf_runtime(tmp_path):
     fields = {f: v for f, wt, v in ckpt._fields(got[b"v"])}
     assert fields[1] == 1 and fields[4] == 2 ** 33 and fields[5] == 140
     assert struct.unpack("<I", fields[6])[0] == 0xDEADBEEF and ckpt._shape_of(fields[2]) == (5, 7)
+
+
+def test_example_round_trips_property_based():
+    """random feature maps through both encoders / decoders (ours and the protobuf runtime's) — varint edges, negative
+    and 64-bit ints, empty lists, non-ASCII keys, large byte strings"""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    Example = _example_classes()
+    ints = st.lists(st.integers(min_value=-2 ** 63, max_value=2 ** 63 - 1), max_size=6)
+    floats = st.lists(st.floats(width=32, allow_nan=False), max_size=6)
+    blobs = st.lists(st.binary(max_size=300), max_size=3)
+    feats = st.dictionaries(st.text(min_size=1, max_size=12), st.one_of(ints, floats, blobs), max_size=5)
+
+    def kind(v):
+        return "bytes" if v and isinstance(v[0], bytes) else "float" if v and isinstance(v[0], float) else "int"
+
+    @hyp.settings(max_examples=150, deadline=None)
+    @hyp.given(feats)
+    def check(features):
+        features = {k: v for k, v in features.items() if v}               # an empty list carries no type
+        ours = R.encode_example(features)
+        ex = Example.FromString(ours)                                        # protobuf parses what we wrote
+        assert set(ex.features.feature) == set(features)
+        theirs = Example()
+        for k, v in features.items():
+            f = ex.features.feature[k]
+            got = {"bytes": list(f.bytes_list.value), "float": list(f.float_list.value), "int": list(f.int64_list.value)}[kind(v)]
+            assert got == v, (k, v, got)
+            dst = theirs.features.feature[k]
+            {"bytes": dst.bytes_list, "float": dst.float_list, "int": dst.int64_list}[kind(v)].value.extend(v)
+        back = R.decode_example(theirs.SerializeToString())                  # and we parse what protobuf wrote
+        assert {k: [bytes(x) if kind(features[k]) == "bytes" else x for x in vals] for k, vals in back.items()} == features
+
+    check()
