@@ -94,6 +94,36 @@ def single_video_attack(k_i3d, rgb_sample, correct_cls_id, cfg, result_path=None
         step += 1
 
 
+def record_batches_from_config(cfg, frames=None, rank=0, world=1, pinned=False, num_parallel_reads=None,
+                               train_repeat=1):
+    """(train_batches, val_batches) — the batch sources `class_gen_attack` / `universal_attack` take — from the
+    record keys of a run_config.yml section, as the mains build them (i3d_adversarial_main_single_class_gen.py:111-135,
+    i3d_adversarial_main_universal.py:205-245): `*.tfrecords` under every TF_RECORDS_{TRAIN,VAL}_PATH entry in sorted
+    order, cut to NUM_OF_{TRAIN,VAL}_TF_RECORDS files when those keys exist, batches of BATCH_SIZE with the remainder
+    dropped.  `num_parallel_reads` (the mains pass os.cpu_count()) selects tf.data's interleaved record order;
+    `train_repeat`: the universal main repeats the training set 1000 times (:241).  With world > 1 every rank takes
+    each world-th file (BATCH_SIZE is then the per-GPU batch)."""
+    import glob
+    from .records import ClipRecordDataset
+
+    def files(paths, limit):
+        paths = [paths] if isinstance(paths, str) else list(paths)
+        out = []
+        for p in paths:
+            out += sorted(glob.glob(os.path.join(p, "*.tfrecords")))
+        out = out[:int(limit)] if limit is not None else out
+        return out[rank::world]
+
+    train = files(cfg.TF_RECORDS_TRAIN_PATH, cfg.get("NUM_OF_TRAIN_TF_RECORDS"))
+    val = files(cfg.TF_RECORDS_VAL_PATH, cfg.get("NUM_OF_VAL_TF_RECORDS"))
+    if not train or not val:
+        raise FileNotFoundError("no *.tfrecords under TF_RECORDS_TRAIN_PATH / TF_RECORDS_VAL_PATH for this rank")
+    B = int(cfg.BATCH_SIZE)
+    kw = dict(frames=frames, pinned=pinned, num_parallel_reads=num_parallel_reads)
+    return (lambda: iter(ClipRecordDataset(train, B, repeat=train_repeat, **kw)),
+            lambda: iter(ClipRecordDataset(val, B, **kw)))
+
+
 def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, epochs=1, log_every=0):
     """One perturbation over batches of one class; fooling rate on the validation set after every
     pass; `res.pkl` layout of i3d_adversarial_main_single_class_gen.py:358-372.  `train_batches` /

@@ -229,16 +229,47 @@ class ClipRecordDataset:
     pinned=True they are page-locked torch tensors ready for `FlickerAttack.prefetch`, and a background thread keeps
     `prefetch` batches decoded ahead of the consumer."""
 
-    def __init__(self, filenames, batch_size, frames=None, repeat=1, verify=True, pinned=False, prefetch=2):
+    def __init__(self, filenames, batch_size, frames=None, repeat=1, verify=True, pinned=False, prefetch=2,
+                 num_parallel_reads=None):
+        """num_parallel_reads=N reproduces the record ORDER of `tf.data.TFRecordDataset(files, num_parallel_reads=N)`
+        (the reference passes os.cpu_count(), i3d_adversarial_main_universal.py:239): a deterministic interleave with
+        cycle length N and block length 1 — one record from each of N open files in turn; an exhausted file frees its
+        slot, which takes the next unopened file when the cycle comes back to it [dep: tf.data InterleaveDataset].
+        None reads the files one after the other."""
         self.filenames = [filenames] if isinstance(filenames, str) else list(filenames)
         self.batch_size, self.frames, self.repeat = int(batch_size), frames, int(repeat)
         self.verify, self.pinned, self.prefetch = verify, pinned, int(prefetch)
+        self.num_parallel_reads = None if not num_parallel_reads else max(1, int(num_parallel_reads))
+
+    def _payloads(self):
+        if self.num_parallel_reads is None or self.num_parallel_reads == 1:
+            for path in self.filenames:
+                yield from tfrecord_iterator(path, verify=self.verify)
+            return
+        pending = iter(self.filenames)
+        slots = [None] * self.num_parallel_reads
+        end_of_input, n_open, i = False, 0, 0
+        while not end_of_input or n_open > 0:
+            if slots[i] is not None:
+                try:
+                    yield next(slots[i])
+                    i = (i + 1) % len(slots)
+                except StopIteration:
+                    slots[i], n_open = None, n_open - 1
+                    i = (i + 1) % len(slots)
+            elif not end_of_input:
+                path = next(pending, None)
+                if path is None:
+                    end_of_input = True
+                else:
+                    slots[i], n_open = iter(tfrecord_iterator(path, verify=self.verify)), n_open + 1
+            else:
+                i = (i + 1) % len(slots)
 
     def _records(self):
         for _ in range(self.repeat):
-            for path in self.filenames:
-                for payload in tfrecord_iterator(path, verify=self.verify):
-                    yield parse_clip_example(payload)
+            for payload in self._payloads():
+                yield parse_clip_example(payload)
 
     def _batches(self):
         vids, labs = [], []

@@ -150,3 +150,53 @@ def test_prefetch_thread_stops_with_the_consumer(tmp_path):
     open(bad, "wb").write(open(p, "rb").read()[:-7])
     with pytest.raises(IOError):
         list(R.ClipRecordDataset([bad], batch_size=1, prefetch=2))
+
+
+def test_interleaved_record_order(tmp_path):
+    """TFRecordDataset(files, num_parallel_reads=N): deterministic interleave, cycle N, block 1"""
+    sizes = [3, 1, 4, 2]
+    paths = []
+    for f, n in enumerate(sizes):
+        p = str(tmp_path / f"f{f}.tfrecords")
+        with R.TFRecordWriter(p) as w:
+            for i in range(n):
+                R.write_clip_record(w, np.zeros((1, 224, 224, 3), np.uint8), 10 * f + i)
+        paths.append(p)
+
+    def order(n):
+        return [int(l[0]) for _, l in R.ClipRecordDataset(paths, batch_size=1, prefetch=0, num_parallel_reads=n)]
+
+    assert order(None) == order(1) == [0, 1, 2, 10, 20, 21, 22, 23, 30, 31]
+    # two slots (InterleaveDataset's loop by hand): f0 / f1 alternate; f1 is found exhausted on its second turn, which
+    # produces nothing and frees the slot; f2 is opened when the cycle returns to it; the same happens to f0 -> f3
+    assert order(2) == [0, 10, 1, 2, 20, 21, 30, 22, 31, 23]
+    # more slots than files: plain round robin until the short files run out
+    assert order(8) == [0, 10, 20, 30, 1, 21, 31, 2, 22, 23]
+    assert sorted(order(3)) == sorted(order(None))
+
+
+def test_record_batches_from_config(tmp_path):
+    """the mains' record lists (single_class_gen.py:111-120): sorted globs per path, NUM_OF_* cut, BATCH_SIZE batches"""
+    from flickering_adversarial_video_b200.config import AttrDict
+    from flickering_adversarial_video_b200.drivers import record_batches_from_config
+    for split, per_file in (("train_a", [2, 2]), ("train_b", [2]), ("val", [3, 2])):
+        (tmp_path / split).mkdir()
+        for f, n in enumerate(per_file):
+            with R.TFRecordWriter(str(tmp_path / split / f"kinetics_x_{f:04}.tfrecords")) as w:
+                for i in range(n):
+                    R.write_clip_record(w, np.zeros((3, 224, 224, 3), np.uint8), {"train_a": 0, "train_b": 50, "val": 90}[split] + 10 * f + i)
+    cfg = AttrDict(TF_RECORDS_TRAIN_PATH=[str(tmp_path / "train_a"), str(tmp_path / "train_b")],
+                   TF_RECORDS_VAL_PATH=[str(tmp_path / "val")], NUM_OF_TRAIN_TF_RECORDS=2, NUM_OF_VAL_TF_RECORDS=5,
+                   BATCH_SIZE=2)
+    train, val = record_batches_from_config(cfg, frames=2)
+    assert [l.tolist() for _, l in train()] == [[0, 1], [10, 11]]            # train_b is cut off by NUM_OF_TRAIN_TF_RECORDS
+    assert [l.tolist() for _, l in train()] == [[0, 1], [10, 11]]            # a fresh iterator per call
+    got = list(val())
+    assert [l.tolist() for _, l in got] == [[90, 91], [92, 100]] and got[0][0].shape == (2, 2, 224, 224, 3)     # remainder dropped
+    cfg.NUM_OF_TRAIN_TF_RECORDS = 3
+    r1, v1 = record_batches_from_config(cfg, rank=1, world=2)
+    assert [l.tolist() for _, l in r1()] == [[10, 11]]                       # rank 1 of 2 takes every second file
+    assert [l.tolist() for _, l in v1()] == [[100, 101]]
+    cfg.TF_RECORDS_VAL_PATH = [str(tmp_path / "nothing")]
+    with pytest.raises(FileNotFoundError):
+        record_batches_from_config(cfg)
