@@ -186,3 +186,15 @@ def test_batch_cache_is_transparent(tmp_path):
     ds2 = vd.VideoDataset(str(tmp_path), train_split_file=str(split), test_split_file=str(split))
     list(ds2._cached("train", make)), list(ds2._cached("train", make))
     assert len(made) == 4 and ds2._cache == {}                       # cache off: decoded every epoch
+
+
+def test_resized_size_equals_torch_interpolate():
+    """the output size ResizeVideo produces is torch's own floor(n * scale_factor) — checked against torch on a grid of
+    frame sizes (floating-point edge cases of 128 / min(H, W))"""
+    import torch
+    import torch.nn.functional as F
+    for H in list(range(112, 300, 7)) + [320, 360, 480, 540, 720, 1080]:
+        for W in list(range(112, 300, 11)) + [320, 340, 426, 480, 640, 854, 1280, 1920]:
+            out = F.interpolate(torch.zeros((1, 1, H, W)), scale_factor=128 / min(H, W), mode="bilinear",
+                                align_corners=False).shape[-2:]
+            assert tuple(out) == vd.resize_geometry(H, W, 128)[:2] == ol.resize_geometry(H, W, 128)[:2], (H, W)
