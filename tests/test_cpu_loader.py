@@ -198,3 +198,18 @@ def test_resized_size_equals_torch_interpolate():
             out = F.interpolate(torch.zeros((1, 1, H, W)), scale_factor=128 / min(H, W), mode="bilinear",
                                 align_corners=False).shape[-2:]
             assert tuple(out) == vd.resize_geometry(H, W, 128)[:2] == ol.resize_geometry(H, W, 128)[:2], (H, W)
+
+
+@pytest.mark.parametrize("H,W", [(256, 340), (240, 320), (360, 270), (128, 171), (171, 128), (113, 199), (480, 854)])
+def test_oracle_resize_against_torch_interpolate(H, W):
+    """the [dep] behind ResizeVideo is torch.nn.functional.interpolate itself: the restatement agrees with it to float32
+    rounding on full-size frames (torch's CPU kernel picks its summation order by thread count / memory format)"""
+    import torch
+    import torch.nn.functional as F
+    frames = (torch.rand((2, H, W, 3), generator=torch.Generator().manual_seed(H * 1000 + W)) * 255).round().to(torch.uint8)
+    x = frames.float().permute(3, 0, 1, 2) / 255.0                                   # to_tensor: [C,T,H,W]
+    r = F.interpolate(x, scale_factor=128 / min(H, W), mode="bilinear", align_corners=False)
+    i, j = ol.center_crop_origin(r.shape[-2], r.shape[-1], 112, 112)
+    ref = r[..., i:i + 112, j:j + 112].permute(1, 2, 3, 0).numpy()                    # back to [T,h,w,C]
+    got = ol.resize_crop(frames.numpy(), 128, 112)
+    assert got.shape == ref.shape and float(np.abs(got - ref).max()) <= 3e-7
