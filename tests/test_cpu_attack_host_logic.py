@@ -12,10 +12,10 @@ from flickering_adversarial_video_b200 import attack
 T, B, HW, K = 6, 2, 12, 7
 
 
-def _net():
+def _net(k=K):
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Conv3d(3, 5, (3, 3, 3), padding=1), torch.nn.ReLU(),
-                              torch.nn.AdaptiveAvgPool3d((T, 1, 1)), torch.nn.Flatten(), torch.nn.Linear(5 * T, K))
+                              torch.nn.AdaptiveAvgPool3d((T, 1, 1)), torch.nn.Flatten(), torch.nn.Linear(5 * T, k))
     for p in net.parameters():
         p.requires_grad_(False)
     return net.eval()
@@ -43,7 +43,7 @@ class StandInEngine:
     def __init__(self, batch, frames, height=None, width=None, num_classes=K, device=0, arch="r3d_18"):
         self.B, self.T, self.H, self.W, self.K = batch, frames, HW, HW, num_classes
         self.device, self.torch_stack, self.arch = torch.device("cpu"), True, arch
-        self.net = _net()
+        self.net = _net(num_classes)
         self.logits, self.probs = torch.zeros((batch, num_classes)), torch.zeros((batch, num_classes))
         self.scalars, self.grad = torch.zeros(L.S_COUNT), torch.zeros((frames, 3))
         self.applied = []

@@ -1,0 +1,149 @@
+"""not gpu: the host flows above the engine — kinetics_i3d (train_step, cyclic roll, on-demand handles, evaluate), the TF
+drivers (single video / class-gen / universal with TensorBoard scalars) and the torch learner's single-video loops — run
+end to end on the CPU with the stand-in engine of test_cpu_attack_host_logic.py.  Checks control flow, layouts and
+bookkeeping (every statement of these paths executes); numerics of the real engine are the GPU suite's business."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from flickering_adversarial_video_b200 import _lib as L
+from flickering_adversarial_video_b200 import attack
+from test_cpu_attack_host_logic import HW, K, StandInEngine, T
+
+
+class TFStandIn(StandInEngine):
+    """same double; fills the optional outputs of apply the TF-stack helpers ask for"""
+
+    def apply(self, clips, delta, adv_flag=1.0, delta_clip=0.4, adv_u8=None, adv_f32=None, stream=None):
+        super().apply(clips, delta, adv_flag, delta_clip)
+        x = clips.float() / 128.0 - 1.0 if clips.dtype == torch.uint8 else clips
+        adv = (x + adv_flag * delta.clamp(-delta_clip, delta_clip).reshape(1, -1, 1, 1, 3)).clamp(-1, 1)
+        if adv_f32 is not None:
+            adv_f32.copy_(adv)
+        if adv_u8 is not None:
+            adv_u8.copy_(((adv + 1.0) * 127.5).to(torch.uint8))
+
+
+@pytest.fixture()
+def standin(monkeypatch):
+    from flickering_adversarial_video_b200 import kinetics_i3d as ki
+    monkeypatch.setattr(attack, "FlickerEngine", TFStandIn)
+    monkeypatch.setattr(ki, "_IMAGE_SIZE", HW)
+    return ki
+
+
+def _clip(seed):
+    return torch.randint(0, 256, (1, T, HW, HW, 3), generator=torch.Generator().manual_seed(seed), dtype=torch.uint8).numpy()
+
+
+def test_kinetics_i3d_mirror_flow(standin):
+    k = standin.kinetics_i3d(ckpt_path="", batch_size=1, frames=T, weights={}, cyclic_pert_flag_default_c=0.0)
+    with pytest.raises(AttributeError):
+        k.softmax_clean
+    clip = _clip(1)
+    clean = k(clip, adv_flag=0)
+    label = int(clean.argmax())
+    k.improve_adversarial_loss(margin=0.05, targeted=False, logits=False)
+    out = k.train_step(clip, [label], learning_rate=1e-3, beta_0=1.0, beta_1=0.5, beta_2=0.5, beta_3=0.5)
+    for key in ("loss", "adversarial_loss", "regularizer_loss", "norm_reg", "diff_norm_reg", "thickness", "roughness",
+                "thickness_relative", "to_min_prob", "to_max_prob", "model_logits", "softmax"):
+        assert key in out
+    assert k.thickness == out["thickness"] and k.softmax.shape == (1, 400)          # attribute handles of the last run
+    assert np.allclose(k.softmax_clean, clean, atol=1e-6)
+    adv = k.adversarial_inputs_rgb
+    assert adv.shape == (1, T, HW, HW, 3) and np.abs(adv).max() <= 1.0
+    # cyclic perturbation: the engine sees the rolled delta
+    before = k._atk.delta.clone()
+    k._rng = np.random.RandomState(5)
+    k.train_step(clip, [label], cyclic_pert_flag=1.0)
+    shift = int(np.random.RandomState(5).randint(0, T))
+    assert torch.equal(k._atk.eng.applied[-1], torch.roll(before, shift, 0)) or shift == 0
+    miss, total = k.evaluate(iter([(clip, [label]), (_clip(2), [label])]), exclude_misclassify=True)
+    assert 0.0 <= miss <= 1.0 and isinstance(total, int) and total <= 2
+    miss, total = k.evaluate(iter([(clip, [label])]), exclude_misclassify=False)
+    assert total == 1
+    k.reset()
+    assert float(k._atk.delta.abs().max()) == 0.0
+    k.close()
+
+
+def test_tf_drivers_flow(standin, tmp_path):
+    from flickering_adversarial_video_b200 import config, drivers
+    from flickering_adversarial_video_b200.records import read_scalars
+    k = standin.kinetics_i3d(ckpt_path="", batch_size=1, frames=T, weights={})
+    clip = _clip(3)
+    label = int(k(clip, adv_flag=0).argmax())
+    cfg = config.default_config()
+    sv = cfg.SINGLE_VIDEO_ATTACK
+    sv.MAX_NUM_STEP = 2
+    res = drivers.single_video_attack(k, clip, label, sv, result_path=str(tmp_path / "sv"), max_extra_steps=3)
+    assert res is not None and res["total_steps"] >= 3 and os.path.exists(res["pkl_path"])
+    saved = pickle.load(open(res["pkl_path"], "rb"))
+    for key in ("correct_cls_prob", "correct_cls", "correct_cls_id", "softmax_init", "rgb_sample", "total_loss_l", "adv_loss_l",
+                "reg_loss_l", "norm_reg_loss_l", "diff_norm_reg_loss_l", "perturbation", "adv_video", "softmax", "total_steps",
+                "beta_0", "beta_1", "beta_2", "beta_3", "fatness", "smoothness"):
+        assert key in saved, key
+    assert saved["perturbation"][-1].shape == (T, 1, 1, 3) and saved["adv_video"].shape == (1, T, HW, HW, 3)
+    assert drivers.single_video_attack(k, clip, (label + 1) % 400, sv) is None      # clean-misclassified clips are skipped
+
+    batches = lambda: iter([(clip, [label]), (_clip(4), [label])])
+    cg = cfg.CLASS_GEN_ATTACK
+    cg.MAX_NUM_STEP = 3
+    res = drivers.class_gen_attack(k, batches, batches, cg, result_path=str(tmp_path / "cg"), epochs=5)
+    assert res["total_steps"] == 3 and os.path.exists(str(tmp_path / "cg" / "res.pkl")) and len(res["fool_rate"]) == 3
+
+    ua = cfg.UNIVERSAL_ATTACK
+    res = drivers.universal_attack(k, batches, batches, ua, max_steps=4, eval_every=2, summary_dir=str(tmp_path / "ua"))
+    assert res["total_steps"] == 4 and res["perturbation"].shape == (T, 1, 1, 3) and len(res["fool_rate"]) == 3
+    ev = [f for f in os.listdir(str(tmp_path / "ua" / "train")) if "tfevents" in f]
+    tags = {t for _, t, _ in read_scalars(os.path.join(str(tmp_path / "ua" / "train"), ev[0]))}
+    assert {"Loss/total", "Perturbation/thickness_%", "Probability/prob_to_min", "ACC: 1- FOOLING_RATIO"} <= tags
+    k.close()
+
+
+def test_torch_learner_single_video_flows(monkeypatch, tmp_path):
+    from flickering_adversarial_video_b200 import torch_stack as ts
+    monkeypatch.setattr(attack, "FlickerEngine", StandInEngine)
+
+    class Learner(ts.VideoLearnerAdversarial):
+        def __init__(self):
+            self.results, self.dataset, self.batch_size, self.sample_length = [], None, 1, T
+            self.model_name, self.attack_type, self.num_classes = "r3d_18", "flickering", K
+            self._weights, self._device, self._atk, self._rng = {}, 0, None, np.random.RandomState(0)
+            self.label_id_to_text = {i: f"class {i}" for i in range(K)}
+            self.pert_model = ts.Perturbation((3, T, 1, 1), device="cpu", max_norm=0.1)
+
+    lp = {"lambda_": 1.0, "beta_1": 0.5, "targeted_attack": False, "target_class_id": None, "improve_loss": True,
+          "use_logits": False}
+    lrn = Learner()
+    clip = torch.from_numpy(_clip(7))[0]                                       # [T,H,W,3]
+    probe = attack.FlickerAttack({}, 1, T, {}, num_classes=K, arch="r3d_18")
+    label = int(probe.predict(clip[None], adv_flag=0.0).argmax())
+    res = lrn.fit_single_video(1e-2, 3, clip, label, video_name="v", class_name="c", model_dir=str(tmp_path),
+                               loss_params_dict=lp, max_restarts=1, restart_after=6)
+    assert res is not None and 3 <= len(res["is_adversarial"]) <= 8 and res["perturbation"][-1].shape == (3, T, 1, 1)
+    assert res["prob_clean_input"].shape == (1, K) and res["label"].tolist() == [label]
+    assert isinstance(float(res["perturbation/inf_norm"]), float) and os.path.exists(str(tmp_path / "v_@c.npy"))
+    assert lrn.fit_single_video(1e-2, 3, clip, (label + 1) % K, loss_params_dict=lp) is None
+    # engine + Adam state reuse across videos (the reference's single optimizer), and the reset switch
+    first = lrn._atk
+    steps_before = int(first.step_count)
+    lrn.pert_model.perturbation = torch.zeros((3, T, 1, 1))
+    lrn.fit_single_video(1e-2, 2, clip, label, loss_params_dict=lp, max_restarts=1, restart_after=4, reuse_attack=first)
+    assert lrn._atk is first and int(first.step_count) > steps_before
+    lrn.fit_single_video(1e-2, 2, clip, label, loss_params_dict=lp, max_restarts=1, restart_after=4, reuse_attack=first,
+                         reset_optimizer=True)
+    assert int(first.step_count) <= 6
+    # cyclic perturbation inside the single-video loop
+    lrn.pert_model.cyclic_pert = True
+    lrn.fit_single_video(1e-2, 2, clip, label, loss_params_dict=lp, max_restarts=1, restart_after=4)
+    # the whole fit_many_videos protocol with the real per-video attack
+    lrn2 = Learner()
+    vids = [(clip, label, "root/c/vid_a"), (torch.from_numpy(_clip(8))[0], label, "root/c/vid_b")]
+    out = lrn2.fit_many_videos(1e-2, model_dir=str(tmp_path / "many"), save_model=True, loss_params_dict=lp, n_iter=2,
+                               videos=vids, max_restarts=1, restart_after=4)
+    assert set(out) == {"vid_a", "vid_b"}
+    assert sorted(os.listdir(str(tmp_path / "many"))) == [f"vid_a_@class_{label}.npy", f"vid_b_@class_{label}.npy"]
