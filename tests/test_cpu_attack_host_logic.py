@@ -42,7 +42,7 @@ class StandInEngine:
 
     def __init__(self, batch, frames, height=None, width=None, num_classes=K, device=0, arch="r3d_18"):
         self.B, self.T, self.H, self.W, self.K = batch, frames, HW, HW, num_classes
-        self.device, self.torch_stack, self.arch = torch.device("cpu"), True, arch
+        self.device, self.torch_stack, self.arch = torch.device("cpu"), arch != "i3d", arch
         self.net = _net(num_classes)
         self.logits, self.probs = torch.zeros((batch, num_classes)), torch.zeros((batch, num_classes))
         self.scalars, self.grad = torch.zeros(L.S_COUNT), torch.zeros((frames, 3))

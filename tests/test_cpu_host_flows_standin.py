@@ -147,3 +147,108 @@ def test_torch_learner_single_video_flows(monkeypatch, tmp_path):
                                videos=vids, max_restarts=1, restart_after=4)
     assert set(out) == {"vid_a", "vid_b"}
     assert sorted(os.listdir(str(tmp_path / "many"))) == [f"vid_a_@class_{label}.npy", f"vid_b_@class_{label}.npy"]
+
+
+class SparseStandIn(StandInEngine):
+    """the per-pixel entry points of FlickerEngine (pixels_enable / apply_pixels / backward_pixels / update_pixels)"""
+
+    def pixels_enable(self):
+        self.enabled = True
+
+    def apply_pixels(self, clip_u8, delta_px, adv_flag=1.0, delta_clip=0.0, adv_f32=None, stream=None):
+        self._clips, self._px, self._flag, self._clip = clip_u8, delta_px.detach().clone(), adv_flag, delta_clip
+
+    def forward(self, stream=None):
+        from test_cpu_attack_host_logic import _normalize
+        d = self._px.clone().requires_grad_(True)
+        self._d = d
+        pc = d.clamp(-self._clip, self._clip) if self._clip > 0 else d
+        x = _normalize(self._clips) if self.torch_stack else (self._clips.float() / 128.0 - 1.0).permute(0, 4, 1, 2, 3)
+        self._logits_graph = self.net(x + self._flag * pc.permute(3, 0, 1, 2)[None])
+        self.logits.copy_(self._logits_graph.detach())
+        return self.logits
+
+    def backward_pixels(self, grad_px, stream=None):
+        (g,) = torch.autograd.grad(self._loss, self._d)
+        grad_px.copy_(g)
+        return grad_px
+
+    def update_pixels(self, delta_px, grad_px, m, v, step, reg_weight, delta_clip=0.0, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8,
+                      stack=L.FAV_STACK_TF, stream=None):
+        step += 1
+        t = int(step)
+        m.mul_(b1).add_((1 - b1) * grad_px)
+        v.mul_(b2).add_((1 - b2) * grad_px * grad_px)
+        delta_px.sub_((lr / (1 - b1 ** t)) * m / (v.sqrt() / (1 - b2 ** t) ** 0.5 + eps))
+        self.scalars[L.S_NORM_REG] = float(delta_px.pow(2).mean((1, 2, 3)).sqrt().sum())
+        self.scalars[L.S_TOTAL_LOSS] = self.scalars[L.S_ADV_LOSS] + reg_weight * self.scalars[L.S_NORM_REG]
+        return self.scalars
+
+
+def test_sparse_flows(monkeypatch, tmp_path):
+    """kinetics_i3d_L12 behind the universal driver (FLICKERING_ATTACK = False) and the torch learner with
+    attack_type "L12": SparseAttack's host logic (initial values, step, predict, replica check, result layouts)"""
+    from flickering_adversarial_video_b200 import config, drivers, kinetics_i3d as ki, torch_stack as ts
+    monkeypatch.setattr(attack, "FlickerEngine", SparseStandIn)
+    monkeypatch.setattr(ki, "_IMAGE_SIZE", HW)
+    k = ki.kinetics_i3d_L12(ckpt_path="", batch_size=1, frames=T, weights={})
+    assert k.flickering is False and k.eps_rgb.shape == (T, HW, HW, 3) and np.allclose(k.eps_rgb, 1e-8)
+    clip = _clip(11)
+    label = int(k(clip, adv_flag=0).argmax())
+    batches = lambda: iter([(clip, [label]), (_clip(12), [label])])
+    res = drivers.universal_attack(k, batches, batches, config.default_config().UNIVERSAL_ATTACK, max_steps=3)
+    assert res["total_steps"] == 3 and res["perturbation"].shape == (T, HW, HW, 3)
+    assert k.loss_L12 >= 0 and not np.allclose(k.eps_rgb, 1e-8)
+    k.close()
+
+    class Learner(ts.VideoLearnerAdversarial):
+        def __init__(self):
+            self.results, self.dataset, self.batch_size, self.sample_length = [], None, 1, T
+            self.model_name, self.attack_type, self.num_classes = "r3d_18", "L12", K
+            self._weights, self._device, self._atk, self._rng = {}, 0, None, np.random.RandomState(0)
+            self.pert_model = ts.Perturbation((3, T, HW, HW), device="cpu", max_norm=0.2)
+
+    lp = {"lambda_": 1.0, "beta_1": 0.5, "targeted_attack": False, "target_class_id": None, "improve_loss": True,
+          "use_logits": False}
+    lrn = Learner()
+    vid = torch.from_numpy(clip)[0]
+    probe = attack.SparseAttack({}, 1, T, {}, num_classes=K, arch="r3d_18")
+    assert probe.world == 1 and probe.delta.shape == (T, HW, HW, 3) and float(probe.delta.abs().max()) <= 1e-6
+    probe.check_replicas()
+    lab = int(probe.predict(vid[None], adv_flag=0.0).argmax())
+    res = lrn.fit_single_video(1e-2, 2, vid, lab, loss_params_dict=lp, max_restarts=1, restart_after=4)
+    assert res is not None and res["perturbation"][-1].shape == (3, T, HW, HW)
+    lrn.pert_model.cyclic_pert = True
+    with pytest.raises(NotImplementedError):
+        lrn.fit_single_video(1e-2, 2, vid, lab, loss_params_dict=lp)
+
+
+def test_torch_fit_with_the_real_attack_factory(monkeypatch, tmp_path):
+    """VideoLearnerAdversarial.fit through the real `_attack` (value-bound check, sharded flag, delta hand-over)"""
+    from flickering_adversarial_video_b200 import torch_stack as ts
+    monkeypatch.setattr(attack, "FlickerEngine", StandInEngine)
+
+    class Learner(ts.VideoLearnerAdversarial):
+        def __init__(self):
+            self.results, self.dataset, self.batch_size, self.sample_length = [], None, 2, T
+            self.model_name, self.attack_type, self.num_classes = "r3d_18", "flickering", K
+            self._weights, self._device, self._atk, self._rng = {}, 0, None, np.random.RandomState(0)
+            self.pert_model = ts.Perturbation((3, T, 1, 1), device="cpu", max_norm=0.1)
+
+    lp = {"lambda_": 1.0, "beta_1": 0.5, "targeted_attack": False, "target_class_id": None, "improve_loss": True,
+          "use_logits": False}
+    g = torch.Generator().manual_seed(1)
+    clips = torch.randint(0, 256, (2, T, HW, HW, 3), generator=g, dtype=torch.uint8)
+    lrn = Learner()
+    probe = attack.FlickerAttack({}, 2, T, {}, num_classes=K, arch="r3d_18")
+    labels = probe.predict(clips, adv_flag=0.0).argmax(-1)
+    batches = lambda: [(clips, labels)] * 2
+    res = lrn.fit(1e-2, 2, str(tmp_path), save_model=True, loss_params_dict=lp, train_batches=batches, valid_batches=batches)
+    assert len(res) == 2 and sorted(os.listdir(str(tmp_path))) == ["r3d_18_001.npy", "r3d_18_002.npy"]
+    assert 0.0 <= res[-1]["valid/fooling_ratio"] <= 1.0 and res[-1]["train/pert_thickness"] > 0
+    lrn.pert_model.cyclic_pert = True
+    lrn.fit(1e-2, 1, str(tmp_path / "cyc"), loss_params_dict=lp, train_batches=batches, valid_batches=batches)
+    bad = Learner()
+    bad.pert_model.max_value = 1.0
+    with pytest.raises(NotImplementedError):
+        bad.fit(1e-2, 1, str(tmp_path), loss_params_dict=lp, train_batches=batches, valid_batches=batches)
