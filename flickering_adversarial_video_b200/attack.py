@@ -296,6 +296,10 @@ class SparseAttack:
                 self.delta = torch.full(shape, 1e-8, dtype=torch.float32, device=self.device)
         else:
             self.delta = init.to(self.device, torch.float32).contiguous()
+        if self.world > 1:
+            # the torch stack draws its initial perturbation at random (model.py:71): every rank must start from rank 0's
+            src = 0 if process_group is None else torch.distributed.get_global_rank(process_group, 0)
+            torch.distributed.broadcast(self.delta, src=src, group=process_group)
         self.m = torch.zeros_like(self.delta)
         self.v = torch.zeros_like(self.delta)
         self.grad = torch.zeros_like(self.delta)

@@ -158,6 +158,66 @@ def test_replica_divergence_is_detected():
     assert ret[0] == ret[1] == (True, False)
 
 
+def _attack_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from flickering_adversarial_video_b200 import attack, dist as fdist
+    from test_cpu_attack_host_logic import K, T, StandInEngine, _data
+    from test_cpu_host_flows_standin import SparseStandIn
+    fdist.init_from_env("gloo")
+    clips, delta, labels = _data()                                     # 2 clips: one per rank
+    lo, hi = fdist.shard_range(2, rank, world)
+    attack.FlickerEngine = StandInEngine
+    atk = attack.FlickerAttack({}, 1, T, {"LAMBDA": 1.0, "BETA_1": 0.5}, num_classes=K, arch="r3d_18", delta_clip=0.1)
+    assert atk.world == 2 and atk.global_batch == 2
+    atk.delta.copy_(delta)
+    for _ in range(3):
+        atk.step(clips[lo:hi], labels[lo:hi])
+    atk.check_replicas()
+    solo = attack.FlickerAttack({}, 1, T, {}, num_classes=K, arch="r3d_18", sharded=False)
+    assert solo.world == 1
+    attack.FlickerEngine = SparseStandIn
+    torch.manual_seed(100 + rank)                                      # ranks would draw different initial perturbations ...
+    sp = attack.SparseAttack({}, 1, T, {"LAMBDA": 1.0}, num_classes=K, arch="r3d_18")
+    assert sp.world == 2
+    sp.check_replicas()                                                # ... the constructor broadcasts rank 0's
+    for _ in range(2):
+        sp.step(clips[lo:hi], labels[lo:hi])
+    sp.check_replicas()
+    if rank == 0:
+        ret["delta"], ret["adv"], ret["sparse"] = atk.delta.clone(), float(atk.scalars[0]), sp.delta.clone()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_attack_objects_equal_the_full_batch():
+    """attack.FlickerAttack / SparseAttack with world_size 2 (gloo) on the stand-in engine: the packed all-reduce inside
+    step() makes two one-clip ranks walk the same trajectory as one process with both clips"""
+    from flickering_adversarial_video_b200 import attack
+    from test_cpu_attack_host_logic import K, T, StandInEngine, _data
+    from test_cpu_host_flows_standin import SparseStandIn
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_attack_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    clips, delta, labels = _data()
+    saved = attack.FlickerEngine
+    try:
+        attack.FlickerEngine = StandInEngine
+        full = attack.FlickerAttack({}, 2, T, {"LAMBDA": 1.0, "BETA_1": 0.5}, num_classes=K, arch="r3d_18", delta_clip=0.1)
+        full.delta.copy_(delta)
+        for _ in range(3):
+            full.step(clips, labels)
+        attack.FlickerEngine = SparseStandIn
+        torch.manual_seed(0)
+        sp = attack.SparseAttack({}, 2, T, {"LAMBDA": 1.0}, num_classes=K, arch="r3d_18", init=torch.zeros((T, 12, 12, 3)))
+    finally:
+        attack.FlickerEngine = saved
+    assert torch.allclose(ret["delta"], full.delta, rtol=1e-4, atol=1e-7)
+    assert abs(ret["adv"] - float(full.scalars[0])) < 1e-5 * max(1.0, abs(ret["adv"]))
+    assert ret["sparse"].shape == sp.delta.shape
+
+
 def test_shard_range_rules():
     from flickering_adversarial_video_b200 import dist as fdist
     assert fdist.shard_range(64, 3, 8) == (24, 32)
