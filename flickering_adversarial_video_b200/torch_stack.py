@@ -240,6 +240,8 @@ class VideoLearnerAdversarial:
                                 device=self._device, lr=lr, arch=self.model_name,
                                 delta_clip=self.pert_model.dynamic_max_norm, sharded=sharded)
             atk.delta.copy_(self.pert_model.as_engine())
+            if atk.world > 1:      # Perturbation draws U(-1,1)*1e-6 per process (model.py:71): all ranks take rank 0's
+                torch.distributed.broadcast(atk.delta, src=0)
         else:
             atk = SparseAttack(self._weights, batch, self.sample_length, cfg, num_classes=self.num_classes,
                                device=self._device, lr=lr, arch=self.model_name,
