@@ -69,3 +69,11 @@ def replicas_equal(t, group=None):
     dist.all_reduce(both, op=dist.ReduceOp.MAX, group=group)
     n = t.numel()
     return bool(torch.equal(both[:n], -both[n:]))
+
+
+def is_writer(world=None):
+    """True on the rank that writes result files / summaries of a sharded run (rank 0); always True for one rank or for
+    per-rank replicas (`world` = the attack object's world size: 1 when it does not take part in collectives)."""
+    if world is not None and world <= 1:
+        return True
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0

@@ -13,6 +13,8 @@ import pickle
 
 import numpy as np
 
+from . import dist as fdist
+
 
 def _attack_kwargs(cfg):
     return dict(learning_rate=0.001, beta_0=cfg.LAMBDA, beta_1=cfg.BETA_1, beta_2=cfg.BETA_2, beta_3=cfg.BETA_2,
@@ -158,7 +160,7 @@ def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, e
         miss_rate, _ = k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK, target_class_id=target_class_id)
         res["fool_rate"].append(miss_rate)
         res["total_steps"], res["beta_1"], res["beta_2"] = step, kw["beta_1"], kw["beta_2"]
-        if result_path:
+        if result_path and fdist.is_writer(k_i3d._atk.world):
             os.makedirs(result_path, exist_ok=True)
             with open(os.path.join(result_path, "res.pkl"), "wb") as f:
                 pickle.dump(res, f)
@@ -190,7 +192,7 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
     fool = []
     step = 0
     writer = None
-    if summary_dir:                 # <model_dir>/train/events.out.tfevents.* like SummarySaverHook (universal.py:198-201)
+    if summary_dir and fdist.is_writer(k_i3d._atk.world):      # <model_dir>/train/events.out.tfevents.* like SummarySaverHook (universal.py:198-201); sharded runs: rank 0 writes
         from .records import SummaryWriter
         writer = SummaryWriter(os.path.join(summary_dir, "train"))
     while step < max_steps:

@@ -341,7 +341,7 @@ class VideoLearnerAdversarial:
                 result[f"{phase}/inf_norm"] = np.abs(pert).max()
                 result[f"{phase}/perturbation"] = pert
             self.results.append(result)
-            if save_model:
+            if save_model and fdist.is_writer(atk.world):
                 np.save(os.path.join(model_dir, "{}_{:03d}.npy".format(model_name, e)),
                         np.array(self.results, dtype=object), allow_pickle=True)
         return self.results

@@ -118,6 +118,8 @@ def _counts_worker(rank, world, port, ret):
     from flickering_adversarial_video_b200 import dist as fdist
     fdist.init_from_env("gloo")
     got = fdist.sum_counts((3 + rank, 10 * (rank + 1)))        # rank 0: 3 of 10 fooled, rank 1: 4 of 20
+    # result files / summaries of a sharded run are written by rank 0 only; per-rank replicas (world 1) all write
+    assert fdist.is_writer(world=2) == (rank == 0) and fdist.is_writer(world=1) and fdist.is_writer() == (rank == 0)
     ret[rank] = got
     dist.barrier()
     dist.destroy_process_group()
@@ -127,6 +129,7 @@ def test_validation_counts_are_summed_over_ranks():
     """kinetics_i3d.evaluate / VideoLearnerAdversarial.fit take the fooling ratio over all ranks' shards"""
     from flickering_adversarial_video_b200 import dist as fdist
     assert fdist.sum_counts((3, 10)) == [3.0, 10.0]            # no process group: unchanged
+    assert fdist.is_writer() and fdist.is_writer(world=1)
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_counts_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
