@@ -7,7 +7,8 @@ of those dependencies and follows the reference call sites line by line.  The FO
 of strided Conv3D and max_pool3d, snt.BatchNorm inference, the VALID average pool and the mean over T' of the head,
 the InceptionI3d topology) are pinned against an independent implementation: OpenCV's DNN module running the same
 network as an ONNX graph agrees to 1e-4 relative on the logits of a 17-frame clip, and per op exactly / to 1e-5
-(tests/test_cpu_oracle_opencv_pin.py).  The backward pass is torch autograd of that forward.  The loss assembly is
+(tests/test_cpu_oracle_opencv_pin.py).  The backward pass is torch autograd of that forward, checked
+against central finite differences of the loss in float64 (tests/test_cpu_oracle.py).  The loss assembly is
 pinned where the reference's two stacks coincide: probability-mode margin loss, untargeted CE loss, the three
 regulariser terms and the Adam trajectory (up to the epsilon placement) against vectors produced by the reference's
 own torch classes (tests/test_cpu_golden.py).  Still unpinned (restated from the TF documentation only):

@@ -187,3 +187,32 @@ def test_framework_default_init_fixture():
     assert (w["RGB/inception_i3d/Conv3d_2c_3x3/batch_norm/moving_variance"] == 1).all()
     m = synthetic.resnet_model_framework_default("r3d_18")
     assert not m.training and float(m.fc.weight.std()) < 0.05
+
+
+def test_data_gradient_matches_finite_differences(small):
+    """the oracle's dL/d-delta (what every engine gradient is compared with) against central finite differences of its own
+    loss in float64 along two random directions: pins the backward chain (clip gradients, ReLU / max-pool routing, the
+    sum over H x W) independently of autograd"""
+    w, clip = small
+    x = O.normalize_u8(clip).double()
+    delta = synthetic.delta_uniform(16, seed=7, lo=-0.05, hi=0.05).double()
+    m64 = O.OracleI3D(w, dtype=torch.float64)
+    with torch.no_grad():
+        labels = m64.forward(x).argmax(-1)
+    cfg = dict(improve_loss=True, margin=0.05, beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5)
+    g = O.attack_step(m64, x, labels, delta, cfg, data_grad_only=True)["grad_data"]
+
+    def loss(d):
+        with torch.no_grad():
+            logits = m64.forward(O.apply_flicker(x, d))
+            return float(O.improve_adversarial_loss(logits, labels, 0.05, False, False)[0])
+
+    gen = torch.Generator().manual_seed(3)
+    for _ in range(2):
+        u = torch.randn((16, 3), generator=gen, dtype=torch.float64)
+        u /= u.norm()
+        h = 2e-6                     # few ReLU / pool / clip decisions flip between the two points; float64 keeps the difference exact enough
+        fd = (loss(delta + h * u) - loss(delta - h * u)) / (2 * h)
+        an = float((g * u).sum())
+        print(f"finite difference {fd:.6e} vs analytic {an:.6e}")
+        assert abs(fd - an) <= 1e-2 * max(abs(an), float(g.norm()) * 0.05), (fd, an)
