@@ -226,9 +226,9 @@ def video_num_frames(path):
 
 
 class VideoDataset:
-    """dataset.py:246-498.  Same constructor arguments (minus the transform objects: the chain is fixed to the
-    attack's test-time transforms, configured by `im_scale` / `input_size`); `train_batches` / `test_batches` are the
-    per-epoch batch sources `VideoLearnerAdversarial.fit` takes."""
+    """dataset.py:246-498.  Same constructor call as the reference's; the transform chain is fixed to the attack's
+    test-time transforms (`get_transforms(train=False)` -> `TransformSpec`); `train_batches` / `test_batches` are the
+    per-epoch batch sources `VideoLearnerAdversarial.fit` takes (the reference's `train_dl` / `test_dl`)."""
 
     def __init__(self, root, seed=None, train_pct=0.75, num_samples=1, sample_length=8, sample_step=1,
                  temporal_jitter=False, temporal_jitter_step=2, random_shift=False, batch_size=8, video_ext="mp4",
@@ -299,7 +299,12 @@ class VideoDataset:
         return list(range(train_len)), list(range(train_len, len(self.video_records)))
 
     def video_path(self, record):
-        return "{}.{}".format(os.path.join(self.root, record.path), self.video_ext)     # dataset.py:592-596
+        """dataset.py:592-596: `root/record.path.ext`.  Folder-split records already carry the root (:372-380); joining
+        it twice — harmless for the absolute roots the reference uses — is avoided for relative ones."""
+        p = record.path
+        if not (os.path.isabs(p) or os.path.normpath(p).startswith(os.path.normpath(self.root) + os.sep)):
+            p = os.path.join(self.root, p)
+        return "{}.{}".format(p, self.video_ext)
 
     def load_frames(self, idx):
         """decoded uint8 clips [num_samples, T, H, W, 3] (host), label, record path — `__getitem__` (:585-619) before

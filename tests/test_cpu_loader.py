@@ -213,3 +213,13 @@ def test_oracle_resize_against_torch_interpolate(H, W):
     ref = r[..., i:i + 112, j:j + 112].permute(1, 2, 3, 0).numpy()                    # back to [T,h,w,C]
     got = ol.resize_crop(frames.numpy(), 128, 112)
     assert got.shape == ref.shape and float(np.abs(got - ref).max()) <= 3e-7
+
+
+def test_relative_root_folder_split(tmp_path, monkeypatch):
+    """folder-split records carry the root already (dataset.py:372-380): a relative root must not be joined twice"""
+    (tmp_path / "vids" / "c").mkdir(parents=True)
+    _write_video(str(tmp_path / "vids" / "c" / "v0.mp4"), 10)
+    monkeypatch.chdir(tmp_path)
+    ds = vd.VideoDataset("vids", train_pct=1.0, sample_length=4)
+    assert ds.video_path(ds.video_records[0]) == os.path.join("vids", "c", "v0.mp4")
+    assert ds.load_frames(0)[0].shape == (1, 4, 48, 64, 3)
