@@ -86,6 +86,7 @@ SIGNATURES = {
     "fav_profile_begin": (_i, []),
     "fav_profile_end": (_i, [C.POINTER(C.c_double), _i]),
     "fav_launch_count": (_i64, []),
+    "fav_debug_f32_to_f16": (C.c_uint16, [_f]),
     "fav_build_info": (C.c_char_p, []),
 }
 

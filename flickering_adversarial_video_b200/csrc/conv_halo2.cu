@@ -118,6 +118,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = bars + 24;    // [2]
   uint64_t* tempty_bar = bars + 26;   // [2]  (used in the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 32);   // 4 epilogue warps x 32 rows x 5 uint4 (coalesced stores)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -190,7 +191,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA only =====================
     if (rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(256, g.bn);
+      const uint32_t idesc = umma_idesc(256, g.bn, g.f16 != 0);
       const uint32_t desc_hi = umma_desc_hi(128);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -287,12 +288,16 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int h = tc.h0 + i * g.nrows + hm;
         const bool valid = tile_valid && (wm < g.W) && (hm < g.nrows) && (h < g.H);
         const long long pos = valid ? ((static_cast<long long>(tc.b) * g.T + tc.t) * g.H + h) * g.W + wm : 0;
-        __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
-        const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
-        const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
+        h16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const h16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
+        const h16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * acc_cols + i * g.bn);
-        epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
+        if (add_row == nullptr)   // coalesced stores through shared memory (see conv_halo_kernel)
+          epilogue_columns_staged(e, g.bn, tc.n0, taddr, valid, out_row, e.bias, e.cout_store, stage_all + (warp - 2) * 160,
+                                  lane, mask_row);
+        else
+          epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
       }
       tc_fence_before();
       __syncwarp();

@@ -3,8 +3,8 @@
 // Replaces Conv3d_1a_7x7 (7x7x7, stride 2, SAME; i3d.py:168-171) and, with KT/st/pads as parameters,
 // the torchvision video stems ((3,7,7) and (1,7,7), stride (1,2,2), padding 3).
 //
-// Input is the RGBX buffer the apply kernel writes: [B,T,H,Wp,4] bf16 with W physically padded, so the
-// 7 W taps x RGB of output column wo are the 8 positions x 4 channels = 32 contiguous bf16 starting at
+// Input is the RGBX buffer the apply kernel writes: [B,T,H,Wp,4] fp16 with W physically padded, so the
+// 7 W taps x RGB of output column wo are the 8 positions x 4 channels = 32 contiguous fp16 starting at
 // column 2*wo: one 64-byte K row per output position per (kt,kh) tap.  A tensor map whose W stride is
 // 16 bytes (two positions) exposes those overlapping rows directly; four maps cover the (T,H)
 // parities, so that "input row 2*ho + kh - pad" is row ho + qh of the parity-(kh-pad)&1 map.
@@ -56,6 +56,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 2 * kMaxStages + 6);   // 4 epilogue warps x 32 rows x 5 uint4
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,7 +112,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+    const uint32_t idesc = umma_idesc(128, g.bn, true);   // fp16 clip operand x fp16 weights
     const uint32_t desc_hi = umma_desc_hi(64);
     const uint32_t b_sub = static_cast<uint32_t>(g.bn) * 64u;   // bytes per kh weight sub-tile
     int stage = 0;
@@ -169,8 +170,8 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int i = 0; i < g.mt; ++i) {
         const int h = tc.h0 + i * 8 + rh;
         const bool valid = (w < g.Wo) && (h < g.Ho);
-        const long long pos = ((static_cast<long long>(tc.b) * g.To + tc.t) * g.Ho + h) * g.Wo + w;
-        __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const long long pos = valid ? ((static_cast<long long>(tc.b) * g.To + tc.t) * g.Ho + h) * g.Wo + w : 0;
+        h16* out_row = e.out + pos * e.out_cs + e.out_coff;
         const float* bias_row = nullptr;
         if (e.bias) {
           int br = 0;
@@ -183,7 +184,8 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * acc_cols + i * g.bn);
-        epilogue_columns(e, g.bn, 0, taddr, valid, out_row, nullptr, nullptr, bias_row);
+        // coalesced stores through shared memory (the bias row differs per lane: border classes of the delta table)
+        epilogue_columns_staged(e, g.bn, 0, taddr, valid, out_row, bias_row, e.cout_store, stage_all + (warp - 2) * 160, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -238,9 +240,9 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
   g.a_bytes = off;
   g.b_bytes = KH * bn * 64;
   g.stage_bytes = round_up(g.a_bytes + g.b_bytes, 1024);
-  g.stages = std::max(2, std::min(kMaxStages, (216 * 1024) / g.stage_bytes));
-  FAV_CHECK_ARG(g.stages * g.stage_bytes <= 220 * 1024, "stem: stage of %d bytes does not fit", g.stage_bytes);
-  L->smem_bytes = static_cast<size_t>(g.stages) * g.stage_bytes + 1024 + 512;
+  g.stages = std::max(2, std::min(kMaxStages, (215 * 1024) / g.stage_bytes));
+  FAV_CHECK_ARG(g.stages * g.stage_bytes <= 215 * 1024, "stem: stage of %d bytes does not fit", g.stage_bytes);
+  L->smem_bytes = static_cast<size_t>(g.stages) * g.stage_bytes + 1024 + 512 + 4 * 32 * 5 * 16;   // + epilogue staging
   // border classes of the delta-bias table: output rows whose window touches the zero padding
   auto classes = [](int in, int out, int k, int s, int pad, int* nlo, int* nhi) {
     *nlo = ceil_div(pad, s);
@@ -290,7 +292,7 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
 int stem_launch(const StemLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    FAV_CUDA(cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    FAV_CUDA(cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   ProfScope ps(PK_STEM, stream, L.flops);

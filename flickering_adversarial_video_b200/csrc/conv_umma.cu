@@ -7,7 +7,7 @@
 // One persistent CTA per SM, 6 warps:
 //   warp 0    TMA producer  (one elected lane; A box + B box per k-block into a smem ring)
 //   warp 1    TMEM allocator + MMA issuer (one lane issues tcgen05.mma, commits to mbarriers)
-//   warps 2-5 epilogue (tcgen05.ld 32 lanes x 16 cols, bias/ReLU/mask, bf16 NDHWC stores)
+//   warps 2-5 epilogue (tcgen05.ld 32 lanes x 16 cols, bias/ReLU/mask, fp16 / bf16 NDHWC stores)
 // Two 256-column fp32 accumulators in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_umma.cuh"
 
@@ -134,7 +134,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // The whole warp walks the pipeline in lock-step (warp-uniform state stays in uniform registers);
     // one elected lane issues the tcgen05 instructions.  The issue loop is the critical resource for
     // small tiles: every instruction in it costs tensor-pipe idle time.
-    const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+    const uint32_t idesc = umma_idesc(128, g.bn, g.f16 != 0);
     const uint32_t desc_hi = umma_desc_hi(128);
     int stage = 0;
     uint32_t phase = 0;
@@ -213,9 +213,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // output position (identity for plain convs; strided scatter for the parity classes of a strided dgrad)
       const long long pos = ((static_cast<long long>(tc.b) * g.oT + (t * g.est + g.eot)) * g.oH + (h * g.esh + g.eoh)) * g.oW +
                             (w * g.esw + g.eow);
-      __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
-      const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
-      const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
+      h16* out_row = e.out + pos * e.out_cs + e.out_coff;
+      const h16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
+      const h16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
       const float* bias_row = e.bias;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -233,7 +233,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (sgi >= e.nseg) break;
           const int a = max(n_lo, e.seg_n0[sgi]), b = min(n_hi, e.seg_n0[sgi + 1]);
           if (a >= b) continue;   // warp-uniform
-          __nv_bfloat16* srow = e.seg_out[sgi] + pos * e.seg_cs[sgi] + e.seg_coff[sgi];
+          h16* srow = e.seg_out[sgi] + pos * e.seg_cs[sgi] + e.seg_coff[sgi];
           epilogue_columns_staged(e, b - a, a - e.seg_n0[sgi], taddr + static_cast<uint32_t>(a - tc.n0), valid, srow,
                                   bias_row ? bias_row + e.seg_n0[sgi] : nullptr, e.seg_n0[sgi + 1] - e.seg_n0[sgi],
                                   stage_all + (warp - 2) * 160, lane);
@@ -284,6 +284,7 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const ConvGeom& g, int tile
   return c;
 }
 
+constexpr int kHaloStageBytes = 4 * 32 * 5 * 16;   // epilogue staging: 4 warps x 32 rows x 5 uint4
 constexpr int kHaloThreads = 224;   // + warp 6: weight-tile producer (A slabs and B tiles must not block each other)
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -302,6 +303,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 24;    // [2]
   uint64_t* tempty_bar = bars + 26;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 32);   // 4 epilogue warps x 32 rows x 5 uint4 (coalesced stores)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -366,7 +368,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
-    const uint32_t idesc = umma_idesc_bf16(128, g.bn);
+    const uint32_t idesc = umma_idesc(128, g.bn, g.f16 != 0);
     const uint32_t desc_hi = umma_desc_hi(128);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
@@ -458,13 +460,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < g.mt; ++i) {
         const int h = tc.h0 + i * g.nrows + hm;
         const bool valid = (wm < g.W) && (hm < g.nrows) && (h < g.H);
-        const long long pos = ((static_cast<long long>(tc.b) * g.T + tc.t) * g.H + h) * g.W + wm;
-        __nv_bfloat16* out_row = e.out + pos * e.out_cs + e.out_coff;
-        const __nv_bfloat16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
-        const __nv_bfloat16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
+        const long long pos = valid ? ((static_cast<long long>(tc.b) * g.T + tc.t) * g.H + h) * g.W + wm : 0;
+        h16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const h16* mask_row = e.mask ? e.mask + pos * e.mask_cs + e.mask_coff : nullptr;
+        const h16* add_row = e.addend ? e.addend + pos * e.add_cs + e.add_coff : nullptr;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * acc_cols + i * g.bn);
-        epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
+        // ncu (profiles/r01_ncu_full_conv_halo_dgrad_2c.txt): per-lane 16-byte row stores used 16 of 32 bytes per
+        // sector and kept L1/TEX 78 % busy; the staged form stores 8 rows x 64 contiguous bytes per instruction
+        if (add_row == nullptr)
+          epilogue_columns_staged(e, g.bn, tc.n0, taddr, valid, out_row, e.bias, e.cout_store, stage_all + (warp - 2) * 160,
+                                  lane, mask_row);
+        else
+          epilogue_columns(e, g.bn, tc.n0, taddr, valid, out_row, mask_row, add_row, e.bias);
       }
       tc_fence_before();
       __syncwarp();
@@ -503,6 +511,28 @@ float bf16_bits_to_f32(uint16_t b) {
   float f;
   memcpy(&f, &u, 4);
   return f;
+}
+
+uint16_t f32_to_f16_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = static_cast<uint16_t>((u >> 16) & 0x8000u);
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return static_cast<uint16_t>(sign | 0x7e00u);          // NaN
+  if (a >= 0x477ff000u) return static_cast<uint16_t>(sign | 0x7bffu);         // >= 65520 rounds past the largest finite: saturate
+  if (a < 0x33000000u) return sign;                                            // < 2^-25: rounds to zero
+  const int e = static_cast<int>(a >> 23) - 127;                               // unbiased exponent
+  uint32_t mant = (a & 0x7fffffu) | 0x800000u;                                 // 24-bit significand
+  int shift;                                                                    // bits dropped from the significand
+  uint32_t base;
+  if (e >= -14) { shift = 13; base = static_cast<uint32_t>(e + 15) << 10; mant &= 0x7fffffu; }
+  else { shift = 13 + (-14 - e); base = 0; }                                   // subnormal: keep the leading 1
+  const uint32_t kept = mant >> shift;
+  const uint32_t rem = mant & ((1u << shift) - 1u);
+  const uint32_t half = 1u << (shift - 1);
+  uint32_t r = base + kept;                                                    // a carry out of the mantissa bumps the exponent
+  if (rem > half || (rem == half && (kept & 1u))) r += 1;
+  return static_cast<uint16_t>(sign | r);
 }
 
 void choose_box(int T, int H, int W, int kt, int kh, int kw, int* bw, int* bh, int* bt) {
@@ -677,7 +707,7 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   // kernels, not the tensor pipe.
   {
     const int groups = ceil_div(H, g.nrows);
-    const int budget = 222 * 1024;
+    const int budget = 212 * 1024;   // + 10 KB of epilogue staging + barriers = the 227 KB a CTA may have
     const int sms = sm_count(device);
     static int force_mt = -1, force_nt = -1;
     static double l2_rate = 70.0;   // B per cycle per SM; measured on whole steps (41 -> 70: 7.44 -> 7.35 ms/step)
@@ -752,7 +782,8 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
   L->a_bytes = g.slab_bytes;
   L->stages = g.nb;
   L->stage_bytes = b_bytes;
-  L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * b_bytes + 1024 + 512;
+  L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * b_bytes + 1024 + 512 +
+                  kHaloStageBytes;
 
   uint64_t dims[5], strides[4];
   uint32_t box[5];
@@ -788,13 +819,14 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     // half-size weight tiles: re-derive the ring depths (deeper rings hide the longer cross-CTA signalling latency)
     const int hb = (g.bn / 2) * 128;
     L->b_bytes = hb;
-    const int budget = 222 * 1024;
+    const int budget = 212 * 1024;
     int na = 3, bg = 3;
     int nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb));
     if (nb < 3) { na = 2; nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb)); }
     if (nb >= 2) {
       g.na = na; g.nb = nb; g.bgroup = bg;
-      L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * hb + 1024 + 512;
+      L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * hb + 1024 + 512 +
+                      kHaloStageBytes;
     }
     if (getenv("FAV_DEBUG_PLAN")) fprintf(stderr, "[fav]      pair rings: na=%d nb=%dx%d\n", g.na, g.nb, g.bgroup);
   }
@@ -879,7 +911,7 @@ void pack_weights_taps(uint16_t* dst, const float* w, const float* scale, const 
         const float v = wt[static_cast<size_t>(ci) * cout_real + co] * (scale ? scale[co] : 1.0f);
         const int kc = dgrad ? co : ci, n = dgrad ? ci : co;
         const size_t kidx = (static_cast<size_t>(j) * cblocks + kc / 64) * 64 + kc % 64;
-        dst[static_cast<size_t>(n) * K + kidx] = f32_to_bf16_bits(v);
+        dst[static_cast<size_t>(n) * K + kidx] = dgrad ? f32_to_bf16_bits(v) : f32_to_f16_bits(v);
       }
   }
 }
@@ -895,7 +927,7 @@ void pack_weights_fwd(uint16_t* dst, const float* w, const float* scale, int tap
       const float* src = w + (static_cast<size_t>(tap) * cin_real + ci) * cout_real;
       for (int co = 0; co < cout_real; ++co) {
         const float s = scale ? scale[co] : 1.0f;
-        dst[static_cast<size_t>(co) * K + kidx] = f32_to_bf16_bits(src[co] * s);
+        dst[static_cast<size_t>(co) * K + kidx] = f32_to_f16_bits(src[co] * s);
       }
     }
 }

@@ -1,6 +1,6 @@
 // conv_umma.cuh — launch description of the tcgen05 implicit-GEMM Conv3d kernel.
 //
-// GEMM view (NDHWC bf16 activations, fp32 accumulation in TMEM):
+// GEMM view (NDHWC 16-bit activations — fp16 forward, bf16 gradients — fp32 accumulation in TMEM):
 //   M = output positions (tiles of 128 = bw*bh*bt boxes inside one clip),
 //   N = output channels (tile bn <= 256),
 //   K = taps x input channels, walked in k-blocks of one tap x 64 channels (generic path) or one
@@ -12,6 +12,11 @@
 #include "fav_common.cuh"
 
 namespace fav {
+
+// One 16-bit storage element whose format depends on the role of the tensor: IEEE fp16 for forward activations and
+// forward weights, bf16 for gradients and data-gradient weights (fav_common.cuh).  ConvGeom::f16 / ConvEpilogue::out_f16 /
+// add_f16 say which one a launch reads and writes.
+typedef uint16_t h16;
 
 struct ConvGeom {
   int B, T, H, W;      // output positions (= input positions for the stride-1 path)
@@ -44,10 +49,12 @@ struct ConvGeom {
   int swz_base_offset; // 1: put (start>>7)&7 into the descriptor's base_offset field
   int prof;            // 1: the MMA warp records its barrier wait cycles (debug, FAV_HALO_PROF)
   int pair;            // 1: CTA-pair kernel (tcgen05 cta_group::2, conv_halo2.cu)
+  int f16;             // 1: A and B operands are fp16 (forward convs); 0: bf16 (data gradients)
 };
 
 struct ConvEpilogue {
-  __nv_bfloat16* out;        // [B,T,H,W,out_cs], channels out_coff .. out_coff+cout_store
+  h16* out;                  // [B,T,H,W,out_cs], channels out_coff .. out_coff+cout_store
+  int out_f16;               // 1: store fp16 (forward activations), 0: bf16 (gradients)
   long long out_cs;
   int out_coff;
   int cout_store;            // multiple of 8
@@ -55,16 +62,17 @@ struct ConvEpilogue {
   int bias_ld;
   int bias_stem;             // 1: bias row = t*16 + hclass*4 + wclass (delta-dependent stem bias)
   int relu;                  // max(.,0) after bias
-  const __nv_bfloat16* mask; // multiply by (mask > 0); same geometry as out
+  const h16* mask;           // multiply by (mask > 0); a forward activation (fp16), same geometry as out
   long long mask_cs;
   int mask_coff;
-  const __nv_bfloat16* addend;  // added before the mask (may alias out)
+  const h16* addend;         // added before the mask (may alias out): a forward residual (fp16) or a gradient (bf16)
+  int add_f16;
   long long add_cs;
   int add_coff;
   // GEMM column segments routed to different tensors (fused same-input 1x1x1 convs); nseg <= 1: `out` only
   int nseg;
   int seg_n0[4];             // first GEMM column of segment i; seg_n0[nseg] = total columns
-  __nv_bfloat16* seg_out[3];
+  h16* seg_out[3];
   long long seg_cs[3];
   int seg_coff[3];
 };
@@ -83,16 +91,17 @@ struct ConvLaunch {
 
 
 #ifdef __CUDACC__
-// Epilogue of one accumulator row: TMEM -> registers -> bias / addend / ReLU / ReLU-mask -> bf16 -> 16-byte
+// Epilogue of one accumulator row: TMEM -> registers -> bias / addend / ReLU / ReLU-mask -> fp16 or bf16 -> 16-byte
 // stores into the NDHWC channel slice.  Columns are processed 64 at a time with every load of the group
 // (4 tcgen05.ld, the mask / addend rows, the bias) issued before the first use: the epilogue is a chain of
 // memory latencies per group, so the fewer groups the better.
 template <int NQ = 4>   // 16-column chunks per batch (4: 64 columns; 2: 32 columns, for kernels with less register room)
 __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, int n0, uint32_t taddr, bool valid,
-                                                 __nv_bfloat16* out_row, const __nv_bfloat16* mask_row,
-                                                 const __nv_bfloat16* add_row, const float* bias_row,
+                                                 h16* out_row, const h16* mask_row,
+                                                 const h16* add_row, const float* bias_row,
                                                  int cout_store = -1) {
   if (cout_store < 0) cout_store = e.cout_store;
+  const bool of16 = e.out_f16 != 0, af16 = e.add_f16 != 0;
   for (int c0 = 0; c0 < bn; c0 += 16 * NQ) {
     uint32_t r[NQ][16];
     uint4 av[NQ][2], mv[NQ][2];
@@ -106,7 +115,7 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
         const int n = n0 + c + half * 8;
         live[q][half] = valid && c < bn && n + 8 <= cout_store;
         av[q][half] = make_uint4(0u, 0u, 0u, 0u);
-        mv[q][half] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        mv[q][half] = make_uint4(kF16One2, kF16One2, kF16One2, kF16One2);
         if (live[q][half]) {
           if (add_row) av[q][half] = *reinterpret_cast<const uint4*>(add_row + n);
           if (mask_row) mv[q][half] = __ldg(reinterpret_cast<const uint4*>(mask_row + n));
@@ -134,22 +143,18 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
         if (!live[q][half]) continue;
         float* vv = v + half * 8;
         const uint4 a = av[q][half];
-        vv[0] += bf16_lo(a.x); vv[1] += bf16_hi(a.x); vv[2] += bf16_lo(a.y); vv[3] += bf16_hi(a.y);
-        vv[4] += bf16_lo(a.z); vv[5] += bf16_hi(a.z); vv[6] += bf16_lo(a.w); vv[7] += bf16_hi(a.w);
+        vv[0] += lo16(a.x, af16); vv[1] += hi16(a.x, af16); vv[2] += lo16(a.y, af16); vv[3] += hi16(a.y, af16);
+        vv[4] += lo16(a.z, af16); vv[5] += hi16(a.z, af16); vv[6] += lo16(a.w, af16); vv[7] += hi16(a.w, af16);
         if (e.relu) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
         }
         const uint4 mk = mv[q][half];
-        vv[0] = bf16_lo(mk.x) > 0.0f ? vv[0] : 0.0f; vv[1] = bf16_hi(mk.x) > 0.0f ? vv[1] : 0.0f;
-        vv[2] = bf16_lo(mk.y) > 0.0f ? vv[2] : 0.0f; vv[3] = bf16_hi(mk.y) > 0.0f ? vv[3] : 0.0f;
-        vv[4] = bf16_lo(mk.z) > 0.0f ? vv[4] : 0.0f; vv[5] = bf16_hi(mk.z) > 0.0f ? vv[5] : 0.0f;
-        vv[6] = bf16_lo(mk.w) > 0.0f ? vv[6] : 0.0f; vv[7] = bf16_hi(mk.w) > 0.0f ? vv[7] : 0.0f;
         uint4 o;
-        o.x = pack_bf16x2(vv[0], vv[1]);
-        o.y = pack_bf16x2(vv[2], vv[3]);
-        o.z = pack_bf16x2(vv[4], vv[5]);
-        o.w = pack_bf16x2(vv[6], vv[7]);
+        o.x = pack16x2(vv[0], vv[1], of16) & relu_mask2(mk.x);   // the mask only zeroes: exact on the packed values
+        o.y = pack16x2(vv[2], vv[3], of16) & relu_mask2(mk.y);
+        o.z = pack16x2(vv[4], vv[5], of16) & relu_mask2(mk.z);
+        o.w = pack16x2(vv[6], vv[7], of16) & relu_mask2(mk.w);
         *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
       }
     }
@@ -160,12 +165,13 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
 // its own row is a separate L1 wavefront (32 per instruction; measured: the 1x1x1 launches were bound by exactly
 // that), so the warp stages 32 rows x 32 columns in shared memory and writes 8 rows x 64 contiguous bytes per
 // instruction instead.  A ReLU mask (data gradients) is loaded in the same coalesced pattern, before the TMEM loads are
-// waited for, and applied to the packed bf16 values (exact: the mask only zeroes).  `stage` = this warp's 32 x 5 uint4
-// scratch.
+// waited for, and applied to the packed 16-bit values (exact: the mask only zeroes).  `stage` = this warp's 32 x 5 uint4
+// scratch.  bias_row may differ per lane (the stem's border classes): it is applied by the row's owner before staging.
 __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, int ncols, int n0, uint32_t taddr,
-                                                        bool valid, __nv_bfloat16* out_row, const float* bias_row,
+                                                        bool valid, h16* out_row, const float* bias_row,
                                                         int cout_store, uint4* stage, int lane,
-                                                        const __nv_bfloat16* mask_row = nullptr) {
+                                                        const h16* mask_row = nullptr) {
+  const bool of16 = e.out_f16 != 0;
   const unsigned long long row_ptr = reinterpret_cast<unsigned long long>(out_row);
   const unsigned long long mask_ptr = reinterpret_cast<unsigned long long>(mask_row);
   const int k = lane & 3;
@@ -188,9 +194,9 @@ __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, i
     uint4 mk[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      mk[j] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      mk[j] = make_uint4(kF16One2, kF16One2, kF16One2, kF16One2);
       if (mask_row && ok4[j] && st_ok)
-        mk[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(m4[j]) + n0 + cs));
+        mk[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const h16*>(m4[j]) + n0 + cs));
     }
     tmem_ld_wait();
 #pragma unroll
@@ -200,7 +206,7 @@ __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, i
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[q][j]);
-      if (bias_row) {
+      if (bias_row && n0 + c < cout_store) {   // bias arrays are padded to 16 channels, not to the N tile
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_row + n0 + c + j));
@@ -211,24 +217,23 @@ __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, i
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
-      stage[lane * 5 + q * 2] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                           pack_bf16x2(v[6], v[7]));
-      stage[lane * 5 + q * 2 + 1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                               pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      stage[lane * 5 + q * 2] = make_uint4(pack16x2(v[0], v[1], of16), pack16x2(v[2], v[3], of16), pack16x2(v[4], v[5], of16),
+                                           pack16x2(v[6], v[7], of16));
+      stage[lane * 5 + q * 2 + 1] = make_uint4(pack16x2(v[8], v[9], of16), pack16x2(v[10], v[11], of16),
+                                               pack16x2(v[12], v[13], of16), pack16x2(v[14], v[15], of16));
     }
     __syncwarp();
-    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.0f, 0.0f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int rr = (lane >> 2) + 8 * j;
       uint4 val = stage[rr * 5 + k];
       if (mask_row) {
-        val.x &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].x), z2);
-        val.y &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].y), z2);
-        val.z &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].z), z2);
-        val.w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[j].w), z2);
+        val.x &= relu_mask2(mk[j].x);
+        val.y &= relu_mask2(mk[j].y);
+        val.z &= relu_mask2(mk[j].z);
+        val.w &= relu_mask2(mk[j].w);
       }
-      if (ok4[j] && st_ok) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p4[j]) + n0 + cs) = val;
+      if (ok4[j] && st_ok) *reinterpret_cast<uint4*>(reinterpret_cast<h16*>(p4[j]) + n0 + cs) = val;
     }
     __syncwarp();
   }
@@ -293,7 +298,7 @@ struct StemLaunch {
   int grid;
   double flops;
 };
-// x is the padded RGBX buffer [B,T,H,Wp,4]; wpk [KT*KH][bn][32] bf16
+// x is the padded RGBX buffer [B,T,H,Wp,4] fp16; wpk [KT*KH][bn][32] fp16
 int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
               int To, int Ho, int Wo, int KT, int KH, int st, int pt, int ph);
 int stem_launch(const StemLaunch& L, cudaStream_t stream);
@@ -318,7 +323,7 @@ int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, int g1_cs, con
                    int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3);
 int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream);
 
-// Host-side weight packing (bf16 bits in uint16_t).
+// Host-side weight packing (16-bit patterns in uint16_t): FORWARD operands are fp16, DATA-GRADIENT operands bf16.
 // fwd: w [taps][cin_real][cout_real] (TF layout flattened), scale[cout] (BN fold) or nullptr.
 void pack_weights_fwd(uint16_t* dst, const float* w, const float* scale, int taps, int cin_real,
                       int cin_k, int cout_real, int n_pad);
@@ -333,5 +338,6 @@ void pack_weights_taps(uint16_t* dst, const float* w, const float* scale, const 
 
 uint16_t f32_to_bf16_bits(float f);
 float bf16_bits_to_f32(uint16_t b);
+uint16_t f32_to_f16_bits(float f);   // round to nearest even, subnormals kept, saturating at +-65504
 
 }  // namespace fav

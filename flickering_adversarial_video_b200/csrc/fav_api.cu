@@ -25,8 +25,8 @@ namespace {
 struct Buf {
   std::string name;
   int T = 0, H = 0, W = 0, C = 0, cs = 0;   // C real channels, cs stored stride
-  __nv_bfloat16* p = nullptr;                // activation
-  __nv_bfloat16* g = nullptr;                // gradient w.r.t. the producer's pre-activation
+  __half* p = nullptr;                       // activation (fp16)
+  __nv_bfloat16* g = nullptr;                // gradient w.r.t. the producer's pre-activation (bf16)
   uint8_t* idx = nullptr;                    // arg-max taps when produced by a max-pool
   long long npos(int B) const { return static_cast<long long>(B) * T * H * W; }
 };
@@ -37,8 +37,8 @@ struct ConvOp {
   int in, in_coff, cin_real, cin_k;
   int out, out_coff, cout_real, cout_pad;
   bool relu = true, bn = true;
-  uint16_t* w_fwd = nullptr;   // device, packed [cout_pad][nkb*64]
-  uint16_t* w_dg = nullptr;    // device, packed [cin_k][nkb'*64]
+  uint16_t* w_fwd = nullptr;   // device, packed fp16 [cout_pad][nkb*64]
+  uint16_t* w_dg = nullptr;    // device, packed bf16 [cin_k][nkb'*64]
   float* bias = nullptr;       // device [cout_pad]
   size_t w_fwd_elems = 0, w_dg_elems = 0;
   ConvLaunch fwd, dg;
@@ -81,8 +81,8 @@ struct fav_handle {
   bool weights_loaded = false;
 
   // stem
-  __nv_bfloat16* xpad = nullptr;
-  uint16_t* stem_w = nullptr;     // packed bf16 [64][49*32]
+  __half* xpad = nullptr;         // stem operand x' [B,T,H,Wp,4] fp16 (RGBX)
+  uint16_t* stem_w = nullptr;     // packed fp16 [64][49*32]
   float* stem_wc = nullptr;       // class-summed folded weights [7][16][3][64]
   float* stem_bnbias = nullptr;   // [64]
   float* stem_bias_tab = nullptr; // [To][16][64]
@@ -206,6 +206,11 @@ int same_pad_before(int in, int k, int s) {
   return total / 2;
 }
 
+h16* as16(__half* p) { return reinterpret_cast<h16*>(p); }
+h16* as16(__nv_bfloat16* p) { return reinterpret_cast<h16*>(p); }
+const h16* as16(const __half* p) { return reinterpret_cast<const h16*>(p); }
+const h16* as16(const __nv_bfloat16* p) { return reinterpret_cast<const h16*>(p); }
+
 bool use_halo(int T, int H, int W, int kt, int kh, int kw) {
   static int disabled = -1;
   if (disabled < 0) {
@@ -232,8 +237,9 @@ int plan_conv(fav_handle* h, ConvOp& c) {
     else
       FAV_TRY(conv_plan_generic(&c.fwd, h->device, bi.p, bi.cs, c.in_coff, c.cin_k, c.w_fwd, c.cout_pad,
                                 h->B, bi.T, bi.H, bi.W, c.kt, c.kh, c.kw, flat));
+    c.fwd.g.f16 = 1;
     ConvEpilogue& e = c.fwd.e;
-    e.out = bo.p; e.out_cs = bo.cs; e.out_coff = c.out_coff; e.cout_store = c.cout_pad;
+    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = c.out_coff; e.cout_store = c.cout_pad;
     e.bias = c.bias; e.bias_ld = c.cout_pad; e.bias_stem = 0; e.relu = c.relu ? 1 : 0;
     e.mask = nullptr; e.addend = nullptr;
     c.fwd.flops = 2.0 * static_cast<double>(h->B) * bi.T * bi.H * bi.W * taps * c.cin_real * c.cout_real;
@@ -250,7 +256,7 @@ int plan_conv(fav_handle* h, ConvOp& c) {
       FAV_TRY(conv_plan_generic(&c.dg, h->device, bo.g, bo.cs, c.out_coff, c.cout_pad, c.w_dg, c.cin_k,
                                 h->B, bi.T, bi.H, bi.W, c.kt, c.kh, c.kw, flat));
     ConvEpilogue& e = c.dg.e;
-    e.out = bi.g; e.out_cs = bi.cs; e.out_coff = c.in_coff; e.cout_store = c.cin_k;
+    e.out = as16(bi.g); e.out_f16 = 0; e.out_cs = bi.cs; e.out_coff = c.in_coff; e.cout_store = c.cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0;
     e.mask = nullptr; e.addend = nullptr;
     c.dg.flops = 2.0 * static_cast<double>(h->B) * bi.T * bi.H * bi.W * taps * c.cin_real * c.cout_real;
@@ -258,7 +264,7 @@ int plan_conv(fav_handle* h, ConvOp& c) {
   return FAV_OK;
 }
 
-int make_flat_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long long cs, int coff, int cin, long long M) {
+int make_flat_tmap(CUtensorMap* tm, const void* base, long long cs, int coff, int cin, long long M) {
   uint64_t dims[5] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(M), 1, 1, 1};
   uint64_t strides[4] = {static_cast<uint64_t>(cs) * 2, static_cast<uint64_t>(cs) * 2 * M, static_cast<uint64_t>(cs) * 2 * M,
                          static_cast<uint64_t>(cs) * 2 * M};
@@ -289,15 +295,16 @@ int plan_block_fused(fav_handle* h, Block& b) {
   FAV_TRY(dev_alloc(h, &b.wf, b.wf_elems));
   FAV_TRY(dev_alloc(h, &b.bias, static_cast<size_t>(b.n_tot)));
   FAV_TRY(conv_plan_generic(&b.fwd, h->device, bi.p, bi.cs, 0, cin_k, b.wf, b.n_tot, h->B, bi.T, bi.H, bi.W, 1, 1, 1, 1));
+  b.fwd.g.f16 = 1;
   {
     ConvEpilogue& e = b.fwd.e;
-    e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = c0.cout_pad;
+    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = c0.cout_pad;
     e.bias = b.bias; e.bias_ld = b.n_tot; e.bias_stem = 0; e.relu = 1; e.mask = nullptr; e.addend = nullptr;
     e.nseg = 3;
     e.seg_n0[0] = 0; e.seg_n0[1] = c0.cout_pad; e.seg_n0[2] = c0.cout_pad + c1.cout_pad; e.seg_n0[3] = b.n_tot;
-    e.seg_out[0] = bo.p; e.seg_cs[0] = bo.cs; e.seg_coff[0] = c0.out_coff;
-    e.seg_out[1] = t1.p; e.seg_cs[1] = t1.cs; e.seg_coff[1] = 0;
-    e.seg_out[2] = t2.p; e.seg_cs[2] = t2.cs; e.seg_coff[2] = 0;
+    e.seg_out[0] = as16(bo.p); e.seg_cs[0] = bo.cs; e.seg_coff[0] = c0.out_coff;
+    e.seg_out[1] = as16(t1.p); e.seg_cs[1] = t1.cs; e.seg_coff[1] = 0;
+    e.seg_out[2] = as16(t2.p); e.seg_cs[2] = t2.cs; e.seg_coff[2] = 0;
     b.fwd.flops = c0.fwd.flops + c1.fwd.flops + c2.fwd.flops;
   }
   // ---- backward data: K = [g(out)[:, :c0] | g(t1) | g(t2)], N = cin ----
@@ -321,7 +328,7 @@ int plan_block_fused(fav_handle* h, Block& b) {
     uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
     FAV_TRY(make_tmap_bf16(&b.dg.tmB, b.wd, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
     ConvEpilogue& e = b.dg.e;
-    e.out = bi.g; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = cin_k;
+    e.out = as16(bi.g); e.out_f16 = 0; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr; e.nseg = 0;
     b.dg.flops = c0.dg.flops + c1.dg.flops + c2.dg.flops;
   }
@@ -335,10 +342,10 @@ int run_dgrad(fav_handle* h, int conv_id, bool mask_with_input, bool accumulate,
   const Buf& bi = h->bufs[c.in];
   ConvLaunch L = c.dg;
   if (mask_with_input) {
-    L.e.mask = bi.p; L.e.mask_cs = bi.cs; L.e.mask_coff = c.in_coff;
+    L.e.mask = as16(bi.p); L.e.mask_cs = bi.cs; L.e.mask_coff = c.in_coff;
   }
   if (accumulate) {
-    L.e.addend = bi.g; L.e.add_cs = bi.cs; L.e.add_coff = c.in_coff;
+    L.e.addend = as16(bi.g); L.e.add_f16 = 0; L.e.add_cs = bi.cs; L.e.add_coff = c.in_coff;
   }
   return conv_launch(L, s);
 }
@@ -368,7 +375,7 @@ int build_i3d(fav_handle* h) {
   {
     ConvEpilogue& e = h->stem_fwd.e;
     const Buf& bo = h->bufs[h->y1];
-    e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = 64;
+    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = 64;
     e.bias = h->stem_bias_tab; e.bias_ld = 64; e.bias_stem = 1; e.relu = 1;
     e.mask = nullptr; e.addend = nullptr;
     h->stem_fwd.flops = 2.0 * static_cast<double>(B) * h->To * h->Ho * h->Wo * 343.0 * 3.0 * 64.0;
@@ -640,9 +647,9 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
       FAV_TRY(bn_fold(nt, root + c.name, c.cout_real, &scale, &bias));
       for (int ci = 0; ci < cin_real; ++ci)
         for (int co = 0; co < c.cout_real; ++co) {
-          const uint16_t v = f32_to_bf16_bits(w->data[static_cast<size_t>(ci) * c.cout_real + co] * scale[co]);
-          wf[static_cast<size_t>(n0 + co) * Kf + (ci / 64) * 64 + ci % 64] = v;
-          wd[static_cast<size_t>(ci) * Kd + (static_cast<size_t>(kb0) + co / 64) * 64 + co % 64] = v;
+          const float v = w->data[static_cast<size_t>(ci) * c.cout_real + co] * scale[co];
+          wf[static_cast<size_t>(n0 + co) * Kf + (ci / 64) * 64 + ci % 64] = f32_to_f16_bits(v);
+          wd[static_cast<size_t>(ci) * Kd + (static_cast<size_t>(kb0) + co / 64) * 64 + co % 64] = f32_to_bf16_bits(v);
         }
       for (int co = 0; co < c.cout_real; ++co) bf[n0 + co] = bias[co];
       n0 += c.cout_pad;
@@ -667,7 +674,7 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
       for (int c = 0; c < 3; ++c)
         for (int co = 0; co < 64; ++co)
           wf[(tap * 3 + c) * 64 + co] = w->data[(tap * 3 + c) * 64 + co] * scale[co];
-    // packed bf16 B operand: [tap=(kt,kh)][co][j=(kw8,c4)], kw==7 and c==3 are zero columns
+    // packed fp16 B operand: [tap=(kt,kh)][co][j=(kw8,c4)], kw==7 and c==3 are zero columns
     std::vector<uint16_t> sp(static_cast<size_t>(64) * 49 * 32, 0);
     for (int kt = 0; kt < 7; ++kt)
       for (int kh = 0; kh < 7; ++kh)
@@ -675,10 +682,10 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
           for (int c = 0; c < 3; ++c)
             for (int co = 0; co < 64; ++co)
               sp[(static_cast<size_t>(kt * 7 + kh) * 64 + co) * 32 + kw * 4 + c] =
-                  f32_to_bf16_bits(wf[(((kt * 7 + kh) * 7 + kw) * 3 + c) * 64 + co]);
+                  f32_to_f16_bits(wf[(((kt * 7 + kh) * 7 + kw) * 3 + c) * 64 + co]);
     FAV_CUDA(cudaMemcpy(h->stem_w, sp.data(), sp.size() * 2, cudaMemcpyHostToDevice));
     // The delta path (bias table, gradient collapse, saturation corrections) keeps the folded
-    // weights in fp32: delta never passes through a bf16 rounding.
+    // weights in fp32: delta never passes through a 16-bit rounding.
     const std::vector<float>& wq = wf;
     h->stem_w_host = wf;
     {
@@ -748,7 +755,11 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
   if (h->d.arch != FAV_NET_I3D) {
     // torch stack: Perturbation.forward (model.py:80-96); adv_f32 is NCTHW like the reference's tensors
     FAV_CHECK_ARG(in_dtype == FAV_U8 && adv_u8 == nullptr, "torch-stack apply takes a uint8 clip and has no uint8 output");
-    FAV_TRY(launch_apply_torch(static_cast<const uint8_t*>(clip), delta, adv_flag, delta_clip, h->nrm, h->xpad, h->Wp,
+    // Perturbation.forward returns x untouched when `adversarial` is False (model.py:82-83): the clean forward has no
+    // range clamp (dark / bright pixels lie outside the scalar bounds [-1.735, 2.49])
+    fav_norm_params nrm = h->nrm;
+    if (adv_flag == 0.0f) { nrm.lo = -INFINITY; nrm.hi = INFINITY; }
+    FAV_TRY(launch_apply_torch(static_cast<const uint8_t*>(clip), delta, adv_flag, delta_clip, nrm, h->xpad, h->Wp,
                                h->pw, adv_f32, h->pass_bits, h->B, h->T, h->H, h->W, s));
     const int C1 = round_up(h->rn.stem_C, 16);
     float cst[3], ds[3];
@@ -937,7 +948,9 @@ extern "C" int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float*
   h->last_delta_px = delta_px;
   h->last_delta = nullptr;
   h->last_clip_u8 = static_cast<const uint8_t*>(clip_u8);
-  FAV_TRY(launch_apply_pixels(h->last_clip_u8, delta_px, adv_flag, delta_clip, h->nrm, torch_mode, h->xpad, h->Wp, h->pw,
+  fav_norm_params nrm = h->nrm;
+  if (torch_mode && adv_flag == 0.0f) { nrm.lo = -INFINITY; nrm.hi = INFINITY; }   // clean forward: no clamp (model.py:82-83)
+  FAV_TRY(launch_apply_pixels(h->last_clip_u8, delta_px, adv_flag, delta_clip, nrm, torch_mode, h->xpad, h->Wp, h->pw,
                               adv_f32, h->B, h->T, h->H, h->W, s));
   if (torch_mode) {
     const int C1 = round_up(h->rn.stem_C, 16);
@@ -993,6 +1006,8 @@ extern "C" int fav_delta_update(fav_handle* h, float* delta, const float* grad, 
                              static_cast<cudaStream_t>(stream));
 }
 
+extern "C" uint16_t fav_debug_f32_to_f16(float f) { return f32_to_f16_bits(f); }
+
 extern "C" int64_t fav_debug_read(fav_handle* h, const char* name, float* out, int64_t capacity, void* stream) {
   if (!h || !name || !out) {
     set_error("fav_debug_read: null argument");
@@ -1012,7 +1027,8 @@ extern "C" int64_t fav_debug_read(fav_handle* h, const char* name, float* out, i
       set_error("fav_debug_read: capacity %lld < %lld", (long long)capacity, (long long)count);
       return FAV_ERR_ARG;
     }
-    int st = launch_bf16_to_f32(grad ? b.g : b.p, b.cs, 0, b.C, npos, out, static_cast<cudaStream_t>(stream));
+    int st = grad ? launch_bf16_to_f32(b.g, b.cs, 0, b.C, npos, out, static_cast<cudaStream_t>(stream))
+                  : launch_f16_to_f32(b.p, b.cs, 0, b.C, npos, out, static_cast<cudaStream_t>(stream));
     return st == FAV_OK ? count : st;
   }
   set_error("fav_debug_read: unknown buffer '%s'", name);
@@ -1060,10 +1076,12 @@ extern "C" int fav_op_conv3d(int device, const void* x, int64_t x_cs, int64_t x_
     st = conv_plan_generic(&L, device, x, x_cs, static_cast<int>(x_coff), kc, dw, n_pad, B, T, H, W, kt, kh, kw,
                            taps == 1);
   if (st == FAV_OK) {
-    L.e.out = static_cast<__nv_bfloat16*>(y); L.e.out_cs = y_cs; L.e.out_coff = static_cast<int>(y_coff);
+    // forward: fp16 in / fp16 out; data gradient: bf16 in / bf16 out, ReLU mask from an fp16 activation
+    L.g.f16 = dgrad ? 0 : 1;
+    L.e.out = static_cast<h16*>(y); L.e.out_f16 = dgrad ? 0 : 1; L.e.out_cs = y_cs; L.e.out_coff = static_cast<int>(y_coff);
     L.e.cout_store = n_real;
     L.e.bias = db; L.e.bias_ld = n_pad; L.e.bias_stem = 0; L.e.relu = relu;
-    L.e.mask = static_cast<const __nv_bfloat16*>(relu_src); L.e.mask_cs = relu_cs; L.e.mask_coff = static_cast<int>(relu_coff);
+    L.e.mask = static_cast<const h16*>(relu_src); L.e.mask_cs = relu_cs; L.e.mask_coff = static_cast<int>(relu_coff);
     L.e.addend = nullptr;
     st = conv_launch(L, s);
   }
@@ -1083,7 +1101,7 @@ extern "C" int fav_op_maxpool3d(int device, const void* x, void* y, uint8_t* idx
   FAV_CHECK_ARG(x && y, "fav_op_maxpool3d: null argument");
   FAV_CUDA(cudaSetDevice(device));
   PoolGeom g = make_pool_geom(B, T, H, W, C, kt, kh, kw, st, sh, sw);
-  return launch_maxpool_fwd(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, g,
+  return launch_maxpool_fwd(static_cast<const __half*>(x), static_cast<__half*>(y), idx, g,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -1094,7 +1112,7 @@ extern "C" int fav_op_maxpool3d_bwd(int device, const void* dy, const uint8_t* i
   FAV_CUDA(cudaSetDevice(device));
   PoolGeom g = make_pool_geom(B, T, H, W, C, kt, kh, kw, st, sh, sw);
   return launch_maxpool_bwd(static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(add),
-                            static_cast<const __nv_bfloat16*>(relu_src), static_cast<__nv_bfloat16*>(dx), g,
+                            static_cast<const __half*>(relu_src), static_cast<__nv_bfloat16*>(dx), g,
                             static_cast<cudaStream_t>(stream));
 }
 

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <utility>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -110,6 +111,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// ---- 16-bit storage formats ------------------------------------------------------------------
+// FORWARD activations and forward weights are IEEE fp16 (10 mantissa bits: 8x less rounding noise than bf16, which is
+// what decides how many ReLU masks / pooling arg-maxes differ from the reference's fp32 run; tcgen05
+// kind::f16 runs fp16 and bf16 operands at the same rate).  GRADIENTS and the data-gradient weights stay bf16 (range).
+// fp32 -> fp16 saturates to +-65504 instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.0f), 65504.0f), fminf(fmaxf(hi, -65504.0f), 65504.0f));
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float f16_hi(uint32_t v) { return __high2float(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float lo16(uint32_t v, bool f16) { return f16 ? f16_lo(v) : bf16_lo(v); }
+__device__ __forceinline__ float hi16(uint32_t v, bool f16) { return f16 ? f16_hi(v) : bf16_hi(v); }
+// ReLU mask of a pair of forward activations (fp16): 0xffff per half whose value is > 0
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t act2) {
+  return __hgt2_mask(*reinterpret_cast<const __half2*>(&act2), __float2half2_rn(0.0f));
+}
+constexpr uint32_t kF16One2 = 0x3c003c00u;    // fp16x2 (1, 1): the "no mask" operand
+constexpr uint32_t kF16NegInf2 = 0xfc00fc00u; // fp16x2 (-inf, -inf)
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -244,7 +268,7 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]   (kind::f16: bf16 x bf16 -> f32)
+// D[tmem] (+)= A[smem] * B[smem]   (kind::f16: bf16 x bf16 or fp16 x fp16 -> f32; the instruction descriptor says which)
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -321,16 +345,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr, uin
   if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
   return d;
 }
-// Instruction descriptor for kind::f16, A=B=bf16, D=f32, both K-major (InstrDescriptor).
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+// Instruction descriptor for kind::f16, D=f32, both operands K-major (InstrDescriptor): a_format / b_format
+// 0 = F16, 1 = BF16 (forward convs run fp16 x fp16, data gradients bf16 x bf16).
+__host__ __device__ __forceinline__ uint32_t umma_idesc(int M, int N, bool f16) {
   uint32_t d = 0;
   d |= 1u << 4;                         // c_format = F32
-  d |= 1u << 7;                         // a_format = BF16
-  d |= 1u << 10;                        // b_format = BF16
+  if (!f16) {
+    d |= 1u << 7;                       // a_format = BF16
+    d |= 1u << 10;                      // b_format = BF16
+  }
   d |= static_cast<uint32_t>(N >> 3) << 17;
   d |= static_cast<uint32_t>(M >> 4) << 24;
   return d;
 }
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc(M, N, false); }
 #endif  // __CUDACC__
 
 }  // namespace fav

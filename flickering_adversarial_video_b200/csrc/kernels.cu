@@ -19,7 +19,7 @@ namespace fav {
 template <bool kF32>
 __global__ void __launch_bounds__(256)
 apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, float adv_flag,
-             float dclip, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
+             float dclip, __half* __restrict__ xpad, int Wp, int padl,
              uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
              uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
   pdl_sync();
@@ -62,7 +62,7 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
       }
     }
     float a[48];
-    uint32_t xq[32];  // 16 pixels x (RG, B0) bf16 pairs
+    uint32_t xq[32];  // 16 pixels x (RG, B0) fp16 pairs (u8/128 - 1 is exact in fp16)
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
       float q[3];
@@ -77,8 +77,8 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
         m |= sat ? (1u << c) : 0u;
       }
       sat_mask[p] = m;
-      xq[2 * p] = pack_bf16x2(q[0], q[1]);
-      xq[2 * p + 1] = pack_bf16x2(q[2], 0.0f);
+      xq[2 * p] = pack_f16x2(q[0], q[1]);
+      xq[2 * p + 1] = pack_f16x2(q[2], 0.0f);
     }
     uint4* dst = reinterpret_cast<uint4*>(xpad + (row * Wp + padl + wg * 16) * 4);
 #pragma unroll
@@ -123,7 +123,7 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
 }
 
 int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
-                 __nv_bfloat16* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
+                 __half* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
                  uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s) {
   ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 * (in_dtype == FAV_F32 ? 4 : 1) + 8.0 + (adv_u8 ? 3.0 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
@@ -197,13 +197,13 @@ int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, co
 // torch-stack flicker apply (Perturbation.forward, utils_cv/action_recognition/model.py:80-96):
 //   x = (u8/255 - mean_c)/std_c  (functional_video.py:65-97, dataset.py:28-29)
 //   adv = clamp(x + adv_flag*clamp(delta, +-max_norm)/std_c, min_value, max_value)   (scalar bounds :72-75)
-// The stem input is written in centred uint8 units (u - 128, exact in bf16): x' = u - 128 where the clamp did not
+// The stem input is written in centred uint8 units (u - 128, exact in fp16): x' = u - 128 where the clamp did not
 // fire, else the value that reproduces adv under the folded normalisation; delta and the -mean/std constant reach the
 // network through the fp32 stem bias table.
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ delta, float adv_flag, float dclip,
-                   const fav_norm_params nrm, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
+                   const fav_norm_params nrm, __half* __restrict__ xpad, int Wp, int padl,
                    float* __restrict__ adv_f32, uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= groups) return;
@@ -245,8 +245,8 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
       q[c] = (sat ? ((av - d[c]) * nrm.std[c] + nrm.mean[c]) * 255.0f : u) - 128.0f;   // centred uint8 units
       if (!sat) { if (p < 8) pw0 |= 1u << (4 * p + c); else pw1 |= 1u << (4 * (p - 8) + c); }
     }
-    xq[2 * p] = pack_bf16x2(q[0], q[1]);
-    xq[2 * p + 1] = pack_bf16x2(q[2], 0.0f);
+    xq[2 * p] = pack_f16x2(q[0], q[1]);
+    xq[2 * p + 1] = pack_f16x2(q[2], 0.0f);
   }
   // torch pads 3 columns on the left: positions are 8 bytes, so the run starts 8-byte (not 16-byte) aligned
   uint2* dst = reinterpret_cast<uint2*>(xpad + (row * Wp + padl + wg * 16) * 4);
@@ -269,7 +269,7 @@ apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ d
 }
 
 int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
-                       const fav_norm_params& nrm, __nv_bfloat16* xpad, int Wp, int padl, float* adv_f32,
+                       const fav_norm_params& nrm, __half* xpad, int Wp, int padl, float* adv_f32,
                        uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s) {
   ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
@@ -383,11 +383,11 @@ PoolGeom make_pool_geom(int B, int T, int H, int W, int C, int kt, int kh, int k
   return g;
 }
 
-// forward: one thread = one output position x 8 channels, packed bf16x2 compare/select
+// forward: one thread = one output position x 8 channels, packed fp16x2 compare/select
 // (3 ALU ops per tap per channel pair); 2-D grid so the only runtime division is by C/8.
 template <int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+maxpool_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                    uint8_t* __restrict__ idx, const PoolGeom gg) {
   pdl_sync();
   PoolGeom g = gg;
@@ -401,9 +401,9 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   const int ho = row % g.Ho; row /= g.Ho;
   const int to = row % g.To;
   const int b = row / g.To;
-  __nv_bfloat162 best[4];
+  __half2 best[4];
   uint32_t bidx[4];
-  const __nv_bfloat162 ninf = __halves2bfloat162(__ushort_as_bfloat16(0xFF80), __ushort_as_bfloat16(0xFF80));
+  const __half2 ninf = __halves2half2(__ushort_as_half(0xFC00), __ushort_as_half(0xFC00));
 #pragma unroll
   for (int j = 0; j < 4; ++j) { best[j] = ninf; bidx[j] = 0; }
   const int t0 = to * g.st - g.pt, h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
@@ -415,7 +415,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
     for (int dh = 0; dh < g.kh; ++dh) {
       const int h = h0 + dh;
       if (h < 0 || h >= g.H) continue;
-      const __nv_bfloat16* rowp = x + ((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W * g.C + c8 * 8;
+      const __half* rowp = x + ((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W * g.C + c8 * 8;
       const uint32_t tap0 = static_cast<uint32_t>((dt * g.kh + dh) * g.kw);
 #pragma unroll
       for (int dw = 0; dw < g.kw; ++dw) {
@@ -426,7 +426,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(&wv[j]);
+          const __half2 vv = *reinterpret_cast<const __half2*>(&wv[j]);
           const uint32_t m = __hgt2_mask(vv, best[j]);   // strict >: the first arg-max wins
           best[j] = __hmax2(best[j], vv);
           bidx[j] = (bidx[j] & ~m) | (tap2 & m);
@@ -447,7 +447,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
-int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g,
+int launch_maxpool_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s) {
   ProfScope ps(PK_POOL_FWD, s, 0.0, static_cast<double>(g.B) * g.C * (2.0 * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
@@ -471,7 +471,7 @@ int launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
 template <int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                   const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
+                   const __nv_bfloat16* __restrict__ addend, const __half* __restrict__ relu_src,
                    __nv_bfloat16* __restrict__ dx, const PoolGeom gg) {
   pdl_sync();
   PoolGeom g = gg;
@@ -525,21 +525,18 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
       }
     }
   }
-  if (relu_src) {
-    const uint4 r = __ldg(reinterpret_cast<const uint4*>(relu_src + eoff));
-    const float f[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
-                        bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = f[j] > 0.0f ? acc[j] : 0.0f;
-  }
   uint4 o;
   o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
   o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  if (relu_src) {   // the producer's ReLU mask, from its fp16 output
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(relu_src + eoff));
+    o.x &= relu_mask2(r.x); o.y &= relu_mask2(r.y); o.z &= relu_mask2(r.z); o.w &= relu_mask2(r.w);
+  }
   *reinterpret_cast<uint4*>(dx + eoff) = o;
 }
 
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
-                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
+                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
                        cudaStream_t s) {
   ProfScope ps(PK_POOL_BWD, s, 0.0, static_cast<double>(g.B) * g.C * ((addend ? 6.0 : 4.0) * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", g.C);
@@ -575,7 +572,7 @@ __device__ __forceinline__ float head_scale(int T5, int HW) {
 }
 
 __global__ void __launch_bounds__(256)
-head_feat_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ feat, int T5, int HW, int C) {
+head_feat_kernel(const __half* __restrict__ y, float* __restrict__ feat, int T5, int HW, int C) {
   __shared__ float red[8][32][8];
   const int b = blockIdx.y;
   const int cgp = blockIdx.x * 32 + (threadIdx.x & 31);  // 8-channel group
@@ -588,10 +585,10 @@ head_feat_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ feat, 
     for (int p = pl; p < npos; p += 8) {
       const float cf = head_coef(p / HW, T5);
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + (static_cast<long long>(b) * npos + p) * C + cgp * 8));
-      acc[0] += cf * bf16_lo(v.x); acc[1] += cf * bf16_hi(v.x);
-      acc[2] += cf * bf16_lo(v.y); acc[3] += cf * bf16_hi(v.y);
-      acc[4] += cf * bf16_lo(v.z); acc[5] += cf * bf16_hi(v.z);
-      acc[6] += cf * bf16_lo(v.w); acc[7] += cf * bf16_hi(v.w);
+      acc[0] += cf * f16_lo(v.x); acc[1] += cf * f16_hi(v.x);
+      acc[2] += cf * f16_lo(v.y); acc[3] += cf * f16_hi(v.y);
+      acc[4] += cf * f16_lo(v.z); acc[5] += cf * f16_hi(v.z);
+      acc[6] += cf * f16_lo(v.w); acc[7] += cf * f16_hi(v.w);
     }
   }
 #pragma unroll
@@ -634,7 +631,7 @@ head_logits_kernel(const float* __restrict__ feat, const float* __restrict__ wl,
   }
 }
 
-int launch_head_fwd(const __nv_bfloat16* y, int B, int T5, int HW, int C, float* feat, const float* wl,
+int launch_head_fwd(const __half* y, int B, int T5, int HW, int C, float* feat, const float* wl,
                     const float* bl, int K, float* logits, cudaStream_t s) {
   ProfScope ps(PK_HEAD_LOSS, s);
   FAV_CHECK_ARG(C % 8 == 0, "head: C must be a multiple of 8");
@@ -663,7 +660,7 @@ __global__ void head_dfeat_kernel(const float* __restrict__ dlogits, const float
 }
 
 __global__ void __launch_bounds__(256)
-head_gy_kernel(const float* __restrict__ dfeat, const __nv_bfloat16* __restrict__ y,
+head_gy_kernel(const float* __restrict__ dfeat, const __half* __restrict__ y,
                __nv_bfloat16* __restrict__ gy, int T5, int HW, int C, long long total) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -675,19 +672,17 @@ head_gy_kernel(const float* __restrict__ dfeat, const __nv_bfloat16* __restrict_
   const int t = static_cast<int>((p % npos) / HW);
   const float sc = head_scale(T5, HW) * head_coef(t, T5);
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + gid * 8));
-  const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                      bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
   const float* df = dfeat + static_cast<long long>(b) * C + c8 * 8;
   float o[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = f[j] > 0.0f ? sc * df[j] : 0.0f;
-  uint4 ov;
-  ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
-  ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+  for (int j = 0; j < 8; ++j) o[j] = sc * df[j];
+  uint4 ov;   // masked by the final block's ReLU (its fp16 output)
+  ov.x = pack_bf16x2(o[0], o[1]) & relu_mask2(v.x); ov.y = pack_bf16x2(o[2], o[3]) & relu_mask2(v.y);
+  ov.z = pack_bf16x2(o[4], o[5]) & relu_mask2(v.z); ov.w = pack_bf16x2(o[6], o[7]) & relu_mask2(v.w);
   *reinterpret_cast<uint4*>(gy + gid * 8) = ov;
 }
 
-int launch_head_bwd(const float* dlogits, const float* wl, int K, const __nv_bfloat16* y,
+int launch_head_bwd(const float* dlogits, const float* wl, int K, const __half* y,
                     __nv_bfloat16* gy, float* dfeat, int B, int T5, int HW, int C, cudaStream_t s) {
   ProfScope ps(PK_HEAD_LOSS, s);
   dim3 grid(ceil_div(C, 8), B);
@@ -1039,7 +1034,7 @@ int launch_delta_update(float* delta, const float* grad, float* m, float* v, int
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 apply_pixels_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ dpx, float adv_flag, float dclip,
-                    const fav_norm_params nrm, int torch_mode, __nv_bfloat16* __restrict__ xpad, int Wp, int padl,
+                    const fav_norm_params nrm, int torch_mode, __half* __restrict__ xpad, int Wp, int padl,
                     float* __restrict__ adv_f32, int T, int H, int W, long long groups) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= groups) return;
@@ -1072,7 +1067,7 @@ apply_pixels_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ 
       a[c] = av;
       q[c] = torch_mode ? (av * nrm.std[c] + nrm.mean[c]) * 255.0f - 128.0f : av;
     }
-    dst[p] = make_uint2(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], 0.0f));
+    dst[p] = make_uint2(pack_f16x2(q[0], q[1]), pack_f16x2(q[2], 0.0f));
     if (adv_f32) {
       if (torch_mode) {   // NCTHW
 #pragma unroll
@@ -1087,7 +1082,7 @@ apply_pixels_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ 
 }
 
 int launch_apply_pixels(const uint8_t* clip, const float* delta_px, float adv_flag, float delta_clip,
-                        const fav_norm_params& nrm, int torch_mode, __nv_bfloat16* xpad, int Wp, int padl,
+                        const fav_norm_params& nrm, int torch_mode, __half* xpad, int Wp, int padl,
                         float* adv_f32, int B, int T, int H, int W, cudaStream_t s) {
   ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (adv_f32 ? 12.0 : 0.0)) + static_cast<double>(T) * H * W * 12.0);
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
@@ -1281,6 +1276,21 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   const long long p = i / C;
   const int c = static_cast<int>(i % C);
   dst[p * cs + coff + c] = __float2bfloat16_rn(src[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* __restrict__ src, long long cs, int coff, int C, long long total,
+                                  float* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long p = i / C;
+  const int c = static_cast<int>(i % C);
+  dst[i] = __half2float(src[p * cs + coff + c]);
+}
+int launch_f16_to_f32(const __half* src, long long cs, int coff, int C, long long npos, float* dst, cudaStream_t s) {
+  const long long total = npos * C;
+  f16_to_f32_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, s>>>(src, cs, coff, C, total, dst);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
 }
 int launch_bf16_to_f32(const __nv_bfloat16* src, long long cs, int coff, int C, long long npos, float* dst,
                        cudaStream_t s) {

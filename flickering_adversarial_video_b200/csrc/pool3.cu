@@ -18,17 +18,17 @@
 namespace fav {
 namespace {
 
-constexpr uint32_t kNegInf2 = 0xFF80FF80u;   // bf16x2 (-inf, -inf)
+constexpr uint32_t kNegInf2 = kF16NegInf2;   // fp16x2 (-inf, -inf): the forward runs on fp16 activations
 constexpr int kPoolThreads = 800;
 
 __device__ __forceinline__ void first_max(uint32_t (&best)[4], uint32_t (&code)[4], const uint4 v, const uint32_t d2) {
   const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&vv[j]);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&best[j]);
+    const __half2 a = *reinterpret_cast<const __half2*>(&vv[j]);
+    const __half2 b = *reinterpret_cast<const __half2*>(&best[j]);
     const uint32_t m = __hgt2_mask(a, b);          // strict >: the earlier candidate keeps ties
-    const __nv_bfloat162 mx = __hmax2(b, a);
+    const __half2 mx = __hmax2(b, a);
     best[j] = *reinterpret_cast<const uint32_t*>(&mx);
     code[j] = (code[j] & ~m) | (d2 & m);
   }
@@ -38,7 +38,7 @@ __device__ __forceinline__ void first_max(uint32_t (&best)[4], uint32_t (&code)[
 // Small planes are owned whole (halo = 0, R = H); large ones are cut into tiles of R rows that also load one halo
 // row above and below (W stage only), so that cgn consecutive lanes cover 16*cgn contiguous bytes per position.
 __global__ void __launch_bounds__(1024)
-pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+pool3s1_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y, uint8_t* __restrict__ idx,
                    const int T, const int H, const int W, const int C, const int cgn, const int tseg, const int R,
                    const int nth, const int halo) {
   extern __shared__ uint4 smem4[];
@@ -69,8 +69,8 @@ pool3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   const int t_end = min(t_begin + tseg, T);
   const long long plane = static_cast<long long>(H) * W * C;
   const long long eoff = live ? (static_cast<long long>(h) * W + w) * C + (cblk * cgn + cgi) * 8 : 0;
-  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * plane + eoff;
-  __nv_bfloat16* yb = y + static_cast<long long>(b) * T * plane + eoff;
+  const __half* xb = x + static_cast<long long>(b) * T * plane + eoff;
+  __half* yb = y + static_cast<long long>(b) * T * plane + eoff;
   uint8_t* ib = idx + static_cast<long long>(b) * T * plane + eoff;
   const int xs = (lr * (W + 2) + w + 1) * cgn + cgi;       // own cell in X
   const int ms = ((lrow + 1) * W + w) * cgn + cgi;         // own cell in M1
@@ -151,7 +151,7 @@ __device__ __forceinline__ void acc_f32(float (&acc)[8], const float4 a, const f
 // backward.  dx = relu_mask(addend + pool^T(dy)); same grid / item mapping as the forward (halo rows run the T stage only).
 __global__ void __launch_bounds__(kPoolThreads)
 pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                   const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
+                   const __nv_bfloat16* __restrict__ addend, const __half* __restrict__ relu_src,
                    __nv_bfloat16* __restrict__ dx, const int T, const int H, const int W, const int C,
                    const int cgn, const int tseg, const int R, const int nth, const int halo) {
   extern __shared__ uint4 smem4[];
@@ -249,15 +249,10 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
         const int o1 = g1s + (1 - d) * cgn;
         acc_f32(g, G1a[o1], G1b[o1], code_match(cd[cds + (1 - d) * cgn], 0, static_cast<uint32_t>(d)));
       }
-      if (relu_src) {
-        const float f[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y),
-                            bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = f[j] > 0.0f ? g[j] : 0.0f;
-      }
       uint4 o;
       o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
       o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+      if (relu_src) { o.x &= relu_mask2(rv.x); o.y &= relu_mask2(rv.y); o.z &= relu_mask2(rv.z); o.w &= relu_mask2(rv.w); }
       *reinterpret_cast<uint4*>(dx + boff + t * plane) = o;
     }
     dA = dB; dB = dC; dC = dN;
@@ -277,7 +272,7 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 template <int KT>   // temporal kernel: 1 (stride 1) or 3 (stride 2)
 __global__ void __launch_bounds__(256)
 pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                   const __nv_bfloat16* __restrict__ addend, const __nv_bfloat16* __restrict__ relu_src,
+                   const __nv_bfloat16* __restrict__ addend, const __half* __restrict__ relu_src,
                    __nv_bfloat16* __restrict__ dx, const PoolGeom g, const int Qt, const int Qh, const int Qw) {
   pdl_sync();
   constexpr int NA = KT == 3 ? 2 : 1;
@@ -321,7 +316,7 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
         live[eh][ew] = h >= 0 && h < g.H && w >= 0 && w < g.W;
         eo[eh][ew] = ((((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * cg + c8) * 8;
         rv[eh][ew] = (live[eh][ew] && relu_src) ? __ldg(reinterpret_cast<const uint4*>(relu_src + eo[eh][ew]))
-                                                 : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+                                                 : make_uint4(kF16One2, kF16One2, kF16One2, kF16One2);
         av[eh][ew] = (live[eh][ew] && addend) ? __ldg(reinterpret_cast<const uint4*>(addend + eo[eh][ew]))
                                                : make_uint4(0u, 0u, 0u, 0u);
       }
@@ -355,13 +350,9 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
           }
         }
         const uint4 r = rv[eh][ew];
-        const float f[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
-                            bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = f[j] > 0.0f ? acc[j] : 0.0f;
         uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        o.x = pack_bf16x2(acc[0], acc[1]) & relu_mask2(r.x); o.y = pack_bf16x2(acc[2], acc[3]) & relu_mask2(r.y);
+        o.z = pack_bf16x2(acc[4], acc[5]) & relu_mask2(r.z); o.w = pack_bf16x2(acc[6], acc[7]) & relu_mask2(r.w);
         *reinterpret_cast<uint4*>(dx + eo[eh][ew]) = o;
       }
   }
@@ -424,7 +415,7 @@ bool pool3s1_applicable(const PoolGeom& g) {
          pick_tiling(g.H, g.W, g.C, kPoolThreads).cgn > 0;
 }
 
-int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
+int launch_pool3s1_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
   const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads, 1024);
   FAV_CHECK_ARG(t.cgn > 0 && idx, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
@@ -442,7 +433,7 @@ int launch_pool3s1_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, c
 }
 
 int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
-                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
+                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
   const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads);
   FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
@@ -467,7 +458,7 @@ bool pool_s2_applicable(const PoolGeom& g) {
 }
 
 int launch_pool_s2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
-                       const __nv_bfloat16* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
+                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
   FAV_CHECK_ARG(pool_s2_applicable(g), "pool_s2_bwd: unsupported geometry");
   const int Qt = g.kt == 3 ? (g.T - 1 + g.pt) / 2 + 1 : g.T;
   const int Qh = (g.H - 1 + g.ph) / 2 + 1, Qw = (g.W - 1 + g.pw) / 2 + 1;

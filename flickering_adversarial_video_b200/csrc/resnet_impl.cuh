@@ -38,7 +38,7 @@ int plan_dgrad_classes(fav_handle* h, std::vector<DgradClass>* out, const __nv_b
         sp.eot = a.par; sp.eoh = b.par; sp.eow = c.par;
         FAV_TRY(conv_plan_ex(&d.L, h->device, sp));
         ConvEpilogue& e = d.L.e;
-        e.out = gin; e.out_cs = gin_cs; e.out_coff = 0; e.cout_store = n_pad;
+        e.out = as16(gin); e.out_f16 = 0; e.out_cs = gin_cs; e.out_coff = 0; e.cout_store = n_pad;
         e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr;
         d.L.flops = 2.0 * static_cast<double>(h->B) * a.Q * b.Q * c.Q * ntaps * flops_cin * flops_cout;
         out->push_back(std::move(d));
@@ -60,8 +60,8 @@ int run_dgrad_classes(const std::vector<DgradClass>& cls, const Buf* mask, const
   int i = 0;
   for (const DgradClass& d : cls) {
     ConvLaunch L = d.L;
-    if (mask) { L.e.mask = mask->p; L.e.mask_cs = mask->cs; L.e.mask_coff = 0; }
-    if (addend) { L.e.addend = addend->g; L.e.add_cs = addend->cs; L.e.add_coff = 0; }
+    if (mask) { L.e.mask = as16(mask->p); L.e.mask_cs = mask->cs; L.e.mask_coff = 0; }
+    if (addend) { L.e.addend = as16(addend->g); L.e.add_f16 = 0; L.e.add_cs = addend->cs; L.e.add_coff = 0; }
     const int k = i++ % nstreams;
     FAV_TRY(conv_launch(L, k == 0 ? s : h->side[k - 1]));
   }
@@ -119,8 +119,9 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
     FAV_TRY(conv_plan_ex(&c.fwd, h->device, sp));
   }
   {
+    c.fwd.g.f16 = 1;
     ConvEpilogue& e = c.fwd.e;
-    e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = c.cout_pad;
+    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = c.cout_pad;
     e.bias = c.bias; e.bias_ld = c.cout_pad; e.bias_stem = 0;
     e.relu = (c.relu || c.residual >= 0) ? 1 : 0;
     e.mask = nullptr;
@@ -129,7 +130,7 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
       const Buf& br = h->bufs[c.residual];
       FAV_CHECK_ARG(br.T == bo.T && br.H == bo.H && br.W == bo.W && br.cs == bo.cs, "residual shape mismatch at %s",
                     c.wname.c_str());
-      e.addend = br.p; e.add_cs = br.cs; e.add_coff = 0;
+      e.addend = as16(br.p); e.add_f16 = 1; e.add_cs = br.cs; e.add_coff = 0;
     }
     c.fwd.flops = 2.0 * static_cast<double>(h->B) * bo.T * bo.H * bo.W * taps * c.cin_real * c.cout_real;
   }
@@ -143,7 +144,7 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
     FAV_TRY(dev_alloc(h, &d.w, d.elems));
     FAV_TRY(conv_plan_halo(&d.L, h->device, bg.g, bg.cs, 0, c.cout_pad, d.w, c.cin_k, h->B, bi.T, bi.H, bi.W, c.kt));
     ConvEpilogue& e = d.L.e;
-    e.out = bi.g; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = c.cin_k;
+    e.out = as16(bi.g); e.out_f16 = 0; e.out_cs = bi.cs; e.out_coff = 0; e.cout_store = c.cin_k;
     e.bias = nullptr; e.bias_ld = 0; e.bias_stem = 0; e.relu = 0; e.mask = nullptr; e.addend = nullptr;
     d.L.flops = 2.0 * static_cast<double>(h->B) * bo.T * bo.H * bo.W * taps * c.cin_real * c.cout_real;
     c.dg.push_back(std::move(d));
@@ -183,7 +184,7 @@ int build_resnet(fav_handle* h) {
   {
     ConvEpilogue& e = h->stem_fwd.e;
     const Buf& bo = h->bufs[rn.stem_out];
-    e.out = bo.p; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = C1;
+    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = C1;
     e.bias = h->stem_bias_tab; e.bias_ld = C1; e.bias_stem = 1; e.relu = 1;
     e.mask = nullptr; e.addend = nullptr;
     h->stem_fwd.flops = 2.0 * static_cast<double>(B) * h->To * h->Ho * h->Wo * rn.stem_KT * 49.0 * 3.0 * rn.stem_C;
@@ -377,11 +378,10 @@ int load_weights_resnet(fav_handle* h, const NamedTensors& nt) {
         for (int kw = 0; kw < 7; ++kw)
           for (int c = 0; c < 3; ++c)
             for (int co = 0; co < C; ++co)
-              sp[(static_cast<size_t>(kt * 7 + kh) * C1 + co) * 32 + kw * 4 + c] = f32_to_bf16_bits(
+              sp[(static_cast<size_t>(kt * 7 + kh) * C1 + co) * 32 + kw * 4 + c] = f32_to_f16_bits(
                   wt[(static_cast<size_t>((kt * 7 + kh) * 7 + kw) * 3 + c) * C + co] / (255.0f * h->nrm.std[c]));
     FAV_CUDA(cudaMemcpy(h->stem_w, sp.data(), sp.size() * 2, cudaMemcpyHostToDevice));
-    // class-summed weights for the (delta - mean)/std bias table.  The bf16-rounded operand is used for the
-    // constant part so that bias and GEMM agree on what "x' = u" contributes.
+    // class-summed weights for the (delta - mean)/std bias table (fp32)
     const StemGeom& sg = h->stem_fwd.g;
     auto first_of = [](int cls, int n, int nlo, int nhi) { return cls < nlo ? cls : (cls == nlo ? nlo : n - nhi + (cls - nlo - 1)); };
     std::vector<float> wcs(static_cast<size_t>(KT) * 16 * 3 * C1, 0.0f);

@@ -147,17 +147,24 @@ class FlickerEngine:
 
 
 # ---- op-level wrappers used by the parity tests ---------------------------------------------
-def op_conv3d(x_bf16, w_tf, bias=None, relu=False, dgrad=False, relu_src=None, y=None, y_coff=0, x_coff=0,
+def op_conv3d(x16, w_tf, bias=None, relu=False, dgrad=False, relu_src=None, y=None, y_coff=0, x_coff=0,
               cin=None, cout=None):
-    """x_bf16 [B,T,H,W,Cs] bf16 cuda; w_tf [kt,kh,kw,cin,cout] float32 (TF layout)."""
+    """x16 [B,T,H,W,Cs] cuda; w_tf [kt,kh,kw,cin,cout] float32 (TF layout).  Storage formats follow the engine's:
+    the forward conv reads and writes float16 (activations), the data gradient (dgrad=True) reads and writes
+    bfloat16 (gradients) and takes its ReLU mask `relu_src` from a float16 activation."""
     lib = L.load()
+    x_bf16 = x16
+    want = torch.bfloat16 if dgrad else torch.float16
+    assert x16.dtype == want, f"op_conv3d(dgrad={dgrad}) takes {want} input, got {x16.dtype}"
+    assert relu_src is None or relu_src.dtype == torch.float16
     B, T, H, W, xcs = x_bf16.shape
     kt, kh, kw, wcin, wcout = w_tf.shape
     cin = wcin if cin is None else cin
     cout = wcout if cout is None else cout
     n_out = cin if dgrad else cout
     if y is None:
-        y = torch.zeros((B, T, H, W, n_out), dtype=torch.bfloat16, device=x_bf16.device)
+        y = torch.zeros((B, T, H, W, n_out), dtype=want, device=x_bf16.device)
+    assert y.dtype == want
     w_host = np.ascontiguousarray(w_tf.detach().cpu().numpy(), dtype=np.float32)
     b_host = None if bias is None else np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
     st = lib.fav_op_conv3d(
@@ -169,11 +176,14 @@ def op_conv3d(x_bf16, w_tf, bias=None, relu=False, dgrad=False, relu_src=None, y
     return y
 
 
-def op_maxpool3d(x_bf16, k, s):
+def op_maxpool3d(x_f16, k, s):
+    """forward pool on float16 activations -> (y float16, arg-max codes uint8)"""
     lib = L.load()
+    x_bf16 = x_f16
+    assert x_f16.dtype == torch.float16
     B, T, H, W, Cc = x_bf16.shape
     To, Ho, Wo = -(-T // s[0]), -(-H // s[1]), -(-W // s[2])
-    y = torch.empty((B, To, Ho, Wo, Cc), dtype=torch.bfloat16, device=x_bf16.device)
+    y = torch.empty((B, To, Ho, Wo, Cc), dtype=torch.float16, device=x_bf16.device)
     idx = torch.empty((B, To, Ho, Wo, Cc), dtype=torch.uint8, device=x_bf16.device)
     L.check(lib.fav_op_maxpool3d(x_bf16.device.index or 0, L.ptr(x_bf16), L.ptr(y), L.ptr(idx), B, T, H, W, Cc,
                                  k[0], k[1], k[2], s[0], s[1], s[2], L.stream_ptr()), "fav_op_maxpool3d")
@@ -181,7 +191,10 @@ def op_maxpool3d(x_bf16, k, s):
 
 
 def op_maxpool3d_bwd(dy, idx, in_shape, k, s, add=None, relu_src=None):
+    """dy / add / result bfloat16 (gradients); relu_src float16 (the pool input's producer activation)"""
     lib = L.load()
+    assert dy.dtype == torch.bfloat16 and (add is None or add.dtype == torch.bfloat16)
+    assert relu_src is None or relu_src.dtype == torch.float16
     B, T, H, W, Cc = in_shape
     dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
     L.check(lib.fav_op_maxpool3d_bwd(dy.device.index or 0, L.ptr(dy), L.ptr(idx), L.ptr(add), L.ptr(relu_src),

@@ -18,7 +18,9 @@
  *   - the library owns only its activation/gradient arena and packed weights (allocated in
  *     fav_create / fav_load_weights).
  *
- * Activation layout inside the library: NDHWC bf16, channel stride padded to a multiple of 8.
+ * Activation layout inside the library: NDHWC, 16 bits per element, channel stride padded to a multiple of 16:
+ * FORWARD activations (and the forward weights) are IEEE fp16, GRADIENTS (and the data-gradient weights) bf16;
+ * every contraction accumulates in fp32 (DESIGN.md section 4 says why the forward is not bf16).
  */
 #ifndef FAV_H_
 #define FAV_H_
@@ -127,7 +129,8 @@ const char* fav_last_error(void);
 /* bytes of device memory owned by the handle (arena + weights) */
 int64_t fav_device_bytes(const fav_handle* h);
 
-/* Fold BN into conv weights, cast to bf16, pack for the tensor-core kernels.
+/* Fold BN into conv weights, cast to fp16 (forward operands) / bf16 (data-gradient operands), pack for the
+ * tensor-core kernels.
  * Replaces tf.train.Saver.restore (kinetics_i3d_utils.py:41-62) + snt.BatchNorm inference
  * (i3d.py:66-68). */
 int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n);
@@ -187,11 +190,12 @@ int fav_pixels_update(fav_handle* h, float* delta_px, const float* grad_px, floa
                       float reg_weight, float delta_clip, const fav_adam_params* adam, float* scalars, void* stream);
 
 /* ---- op-level entry points (layer-wise parity tests; same kernels the engine runs) ------- */
-/* stride-1 SAME Conv3d (+bias, +ReLU) on NDHWC bf16 via the tcgen05 implicit-GEMM kernel.
+/* stride-1 SAME Conv3d (+bias, +ReLU) on NDHWC 16-bit tensors via the tcgen05 implicit-GEMM kernel.
+ *   Formats follow the engine's: dgrad == 0 reads fp16 x and writes fp16 y; dgrad != 0 reads bf16 dY and writes bf16 dX.
  *   x [B,T,H,W,x_cs] (channels x_coff..x_coff+cin), w HOST f32 [kt,kh,kw,cin,cout] (TF layout),
  *   bias HOST f32 [cout] or NULL, y [B,T,H,W,y_cs] (channels y_coff..y_coff+cout).
  *   dgrad != 0: computes the data gradient instead (x is dY with cout channels, y is dX with cin);
- *   relu_src (DEVICE bf16, same geometry as y, stride relu_cs/offset relu_coff) != NULL multiplies
+ *   relu_src (DEVICE fp16 activation, same geometry as y, stride relu_cs/offset relu_coff) != NULL multiplies
  *   the result by (relu_src > 0). */
 int fav_op_conv3d(int device, const void* x, int64_t x_cs, int64_t x_coff,
                   const float* w, const float* bias, int kt, int kh, int kw, int cin, int cout,
@@ -199,10 +203,11 @@ int fav_op_conv3d(int device, const void* x, int64_t x_cs, int64_t x_coff,
                   int relu, int dgrad, const void* relu_src, int64_t relu_cs, int64_t relu_coff,
                   void* stream);
 
-/* tf.nn.max_pool3d SAME on NDHWC bf16 (i3d.py:174 etc.); idx receives the arg-max tap (u8). */
+/* tf.nn.max_pool3d SAME on NDHWC fp16 (i3d.py:174 etc.); idx receives the arg-max tap (u8). */
 int fav_op_maxpool3d(int device, const void* x, void* y, uint8_t* idx, int B, int T, int H, int W,
                      int C, int kt, int kh, int kw, int st, int sh, int sw, void* stream);
-/* its backward: dx = (add ? add : 0) + scatter(dy) ; then * (relu_src>0) if relu_src != NULL */
+/* its backward: dx = (add ? add : 0) + scatter(dy) ; then * (relu_src>0) if relu_src != NULL
+ * (dy, add, dx bf16 gradients; relu_src an fp16 activation) */
 int fav_op_maxpool3d_bwd(int device, const void* dy, const uint8_t* idx, const void* add,
                          const void* relu_src, void* dx, int B, int T, int H, int W, int C,
                          int kt, int kh, int kw, int st, int sh, int sw, void* stream);
@@ -231,7 +236,7 @@ int fav_op_resize_crop(int device, const uint8_t* frames_u8, int n_frames, int H
                        int frames_per_clip, const fav_norm_params* norm, uint8_t* out_u8, float* out_f32,
                        void* stream);
 
-/* debug/introspection: copy a named internal activation (bf16 -> f32, NDHWC, unpadded channels)
+/* debug/introspection: copy a named internal activation (fp16, or bf16 for "grad:" -> f32, NDHWC, unpadded channels)
  * to a DEVICE f32 buffer; returns element count or <0.  Names follow i3d.py end points
  * ("Conv3d_1a_7x7", "Mixed_3b", ...), prefix "grad:" for the gradient buffer. */
 int64_t fav_debug_read(fav_handle* h, const char* name, float* out, int64_t capacity, void* stream);
@@ -246,6 +251,10 @@ int fav_profile_end(double* out, int capacity);
 
 /* number of CUDA kernels libfav has launched in this process (bench.py `gpu_launches`) */
 int64_t fav_launch_count(void);
+
+/* host-side fp32 -> fp16 bit pattern used when packing the forward weights (round to nearest even, subnormals kept,
+ * saturating at +-65504); exported so that the conversion can be checked without a GPU */
+uint16_t fav_debug_f32_to_f16(float f);
 
 /* library build info: "sm_100a;<compile date>" */
 const char* fav_build_info(void);

@@ -89,24 +89,34 @@ def maxpool3d_same(x, k, s):
     return F.max_pool3d(_pad_ndhwc_as_ncdhw(x, k, s, value=float("-inf")), kernel_size=k, stride=s)
 
 
+STORAGE = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def _round_st(t, fmt=torch.bfloat16):
+    """value-rounding to a 16-bit storage format with a straight-through gradient (the engine rounds
+    activations between layers; its backward treats the rounding as identity)."""
+    return t + (t.to(fmt).to(t.dtype) - t).detach()
+
+
 def _bf16_round(t):
-    """value-rounding to bf16 with a straight-through gradient (the engine rounds activations to
-    bf16 between layers; its backward treats the rounding as identity)."""
-    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+    return _round_st(t, torch.bfloat16)
 
 
 class OracleI3D:
     """InceptionI3d(final_endpoint='Logits') forward, differentiable w.r.t. its input.
 
-    emulate_bf16=True restates the ENGINE's arithmetic instead of the reference's fp32: BN folded
-    into the weights, folded weights and every layer output rounded to bf16, fp32 accumulation,
-    delta entering the stem in fp32.  It exists to separate kernel correctness from the precision
-    effect of bf16 storage (ReLU masks of a random-init network flip under 0.5 % activation noise);
-    see DESIGN.md §Precision."""
+    emulate="fp16" (the engine's forward format since round 2) or "bf16" (round 1; `emulate_bf16=True` is
+    kept as an alias) restates the ENGINE's arithmetic instead of the reference's fp32: BN folded into the
+    weights, folded weights and every layer output rounded to the 16-bit storage format, fp32 accumulation,
+    delta entering the stem in fp32.  It exists to separate kernel correctness from the precision effect of
+    16-bit storage (ReLU masks of a random-init network flip under the rounding noise); see DESIGN.md §4."""
 
-    def __init__(self, weights, dtype=torch.float32, emulate_bf16=False):
+    def __init__(self, weights, dtype=torch.float32, emulate_bf16=False, emulate=None):
         self.dtype = dtype
-        self.emulate = emulate_bf16
+        if emulate is None and emulate_bf16:
+            emulate = "bf16"
+        self.emulate = emulate or False
+        self.fmt = STORAGE[emulate] if emulate else None
         self.w = {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in weights.items()}
 
     def folded(self, scope):
@@ -120,11 +130,11 @@ class OracleI3D:
     def unit(self, x, scope, stride=(1, 1, 1), delta_img=None):
         if self.emulate:
             wf, bias = self.folded(scope)
-            wq = wf.to(torch.bfloat16).to(self.dtype)
+            wq = wf.to(self.fmt).to(self.dtype)
             y = conv3d_same(x, wq, stride) + bias.reshape(1, -1, 1, 1, 1)
             if delta_img is not None:   # stem: delta contributes through the unrounded folded weights
                 y = y + conv3d_same(delta_img, wf, stride)
-            return _bf16_round(F.relu(y))
+            return _round_st(F.relu(y), self.fmt)
         w = self.w[ROOT + scope + "/conv_3d/w"]
         y = conv3d_same(x, w, stride)
         beta = self.w[ROOT + scope + "/batch_norm/beta"].reshape(1, -1, 1, 1, 1)
@@ -134,7 +144,7 @@ class OracleI3D:
         return F.relu(y)
 
     def forward_split(self, x_clean, delta, adv_flag=1.0, delta_clip=0.4, endpoints=None, raw_endpoints=None):
-        """Engine-style evaluation (emulate_bf16 only): the clean clip goes through the bf16 stem
+        """Engine-style evaluation (emulate modes only): the clean clip goes through the 16-bit stem
         operand, delta through the fp32 side path; saturated pixels carry clip(x+d)-d."""
         assert self.emulate
         d = adv_flag * torch.clamp(delta.reshape(-1, 1, 1, 3).to(self.dtype), -delta_clip, delta_clip)
@@ -143,7 +153,7 @@ class OracleI3D:
         sat = (s < -1.0) | (s > 1.0)
         # x' = x where the clip did not fire, clip(x+d) - d elsewhere; d/d(delta) of (x' + d) is the clip mask
         xprime = torch.where(sat, (adv - d).detach(), x_clean.to(self.dtype))
-        xprime = xprime.to(torch.bfloat16).to(self.dtype)
+        xprime = xprime.to(self.fmt).to(self.dtype)
         dimg = torch.where(sat, d.detach().expand_as(s), d.expand_as(s))
         return self.forward(xprime, endpoints=endpoints, delta_img=dimg, raw_endpoints=raw_endpoints)
 

@@ -12,8 +12,8 @@ def normalize_u8(clips_u8):
     """[B,T,H,W,3] uint8 -> [B,3,T,H,W] float32, (u/255 - mean)/std
     (references/functional_video.py:65-97 to_tensor + normalize; dataset.py:28-29)."""
     x = clips_u8.permute(0, 4, 1, 2, 3).to(torch.float32) / 255.0
-    mean = torch.tensor(ots.DEFAULT_MEAN, dtype=torch.float32).reshape(1, 3, 1, 1, 1)
-    std = torch.tensor(ots.DEFAULT_STD, dtype=torch.float32).reshape(1, 3, 1, 1, 1)
+    mean = torch.tensor(ots.DEFAULT_MEAN, dtype=torch.float32, device=x.device).reshape(1, 3, 1, 1, 1)
+    std = torch.tensor(ots.DEFAULT_STD, dtype=torch.float32, device=x.device).reshape(1, 3, 1, 1, 1)
     return (x - mean) / std
 
 

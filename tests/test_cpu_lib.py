@@ -56,3 +56,27 @@ def test_favio_header_symbols_are_exported():
     lib = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(lib, name), f"libfavio.so does not export {name}"
+
+
+def test_forward_weight_conversion_is_ieee_half_rne():
+    """fav_load_weights packs the forward operands as fp16 on the host: the conversion must be numpy's (IEEE
+    round-to-nearest-even incl. subnormals) everywhere below the saturation point, and saturate instead of inf."""
+    import numpy as np
+    from flickering_adversarial_video_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([
+        rng.standard_normal(20000).astype(np.float32) * np.float32(0.05),            # weight-like
+        (rng.standard_normal(5000) * 10.0 ** rng.uniform(-9, 4.5, 5000)).astype(np.float32),   # wide dynamic range
+        np.array([0.0, -0.0, 1.0, -1.0, 65504.0, -65504.0, 65519.9, 6.1035156e-05, 6.0975552e-05, 5.9604645e-08,
+                  2.9802322e-08, 2.98e-08, 3.0e-08, 8.9406967e-08, 1.0009765625, 1.00048828125, 1.00146484375],
+                 dtype=np.float32),
+    ])
+    got = np.array([lib.fav_debug_f32_to_f16(float(v)) for v in vals], dtype=np.uint16)
+    with np.errstate(over="ignore"):
+        ref = vals.astype(np.float16).view(np.uint16)
+    finite = np.abs(vals) < 65520.0
+    assert np.array_equal(got[finite], ref[finite]), np.flatnonzero(got[finite] != ref[finite])[:10]
+    big = np.array([70000.0, -1e9, 65520.0], dtype=np.float32)
+    sat = [lib.fav_debug_f32_to_f16(float(v)) for v in big]
+    assert sat == [0x7bff, 0xfbff, 0x7bff]

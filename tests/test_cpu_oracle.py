@@ -155,6 +155,28 @@ def test_bf16_storage_limits_gradient_cosine(small):
     assert 0.95 < cos < 0.9995
 
 
+def test_fp16_storage_gradient_cosine_bound(small):
+    """The engine's round-2 arithmetic restated on the CPU (fp16 forward storage and weights, fp32 accumulation):
+    10 mantissa bits put the end-to-end dL/d-delta cosine against the strict-fp32 gradient near 0.996 for one 16-frame
+    clip - ten times closer than bf16 storage (0.968 above) and where cuDNN's TF32 convolutions put the reference's own
+    network on a B200 (0.9955, profiles/r02_open_precision_1x16.txt) - but still short of 0.999: the direction of the
+    gradient is a small residual of a cancelling sum over H x W on this random-init fixture."""
+    w, clip = small
+    x = O.normalize_u8(clip)
+    delta = synthetic.delta_uniform(16, seed=7, lo=-0.05, hi=0.05)
+    m32, mq = O.OracleI3D(w), O.OracleI3D(w, emulate="fp16")
+    with torch.no_grad():
+        labels = m32.forward(x).argmax(-1)
+    cfg = dict(improve_loss=True, margin=0.05, beta0=1.0, beta1=0.5, beta2=0.5, beta3=0.5)
+    a = O.attack_step(m32, x, labels, delta, cfg, data_grad_only=True)
+    b = O.attack_step(mq, x, labels, delta, cfg, data_grad_only=True)
+    rel = float((a["logits"] - b["logits"]).abs().max() / a["logits"].abs().max())
+    cos = float((a["grad_data"] * b["grad_data"]).sum() / (a["grad_data"].norm() * b["grad_data"].norm()))
+    print(f"fp32 vs fp16-storage oracle: logits rel {rel:.3e}, gradient cosine {cos:.4f}")
+    assert rel < 2e-3
+    assert 0.99 < cos < 0.9995
+
+
 def test_split_stem_evaluation_equals_plain_evaluation(small):
     """conv(x' ) + conv_fp32(delta) == conv(clip(x+delta)) when nothing is rounded"""
     w, clip = small

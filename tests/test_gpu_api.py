@@ -140,9 +140,10 @@ def test_single_video_90_frames_parity():
     print(f"T=90 single video: logits rel err {rel:.3e}, top1 {logits.argmax(-1).tolist()} vs {ref['logits'].argmax(-1).tolist()}, "
           f"dL/d-delta cosine {cos:.5f}")
     assert rel <= 1e-2 and logits.argmax(-1).tolist() == ref["logits"].argmax(-1).tolist()
-    # one clip, 270 gradient entries of ~1e-3: bf16 storage alone gives 0.91 here (the bf16-emulating CPU oracle has
-    # the same cosine against the fp32 oracle, tests/debug_t90.py); kernels are gated stage by stage elsewhere
-    assert cos >= 0.85
+    # one clip, 270 gradient entries of ~1e-3: the reference's own network with TF32 convolutions on this GPU has
+    # 0.987 here (profiles/r02_open_precision_1x90.txt; bf16 storage in round 1: 0.881); kernels are gated stage by
+    # stage elsewhere
+    assert cos >= 0.97
     eng.close()
 
 

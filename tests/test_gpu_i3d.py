@@ -2,16 +2,18 @@
 seeded inputs and random-init weights (north_star gates: uint8 adversarial video bit-exact; logits
 within 1e-2 relative with identical top-1; dL/d-delta cosine >= 0.999).
 
-Gradient gate.  The engine stores activations in bf16 (north_star: bf16 tensor-core roofline).  On a
-random-init ReLU network ~0.5 % activation noise flips enough ReLU masks that ANY bf16-storage
-evaluation - including the fp32 oracle itself re-run with bf16-rounded activations on the CPU, see
-tests/test_cpu_oracle.py::test_bf16_storage_limits_gradient_cosine - has cosine ~0.98-0.99 against
-the fp32 gradient, and even two bf16 pipelines that differ only in fp32 accumulation order
-decorrelate at the ulp level and then pick different ReLU masks / pooling arg-maxes (~0.992).
+Gradient gate.  The engine stores forward activations and weights in fp16 (10 mantissa bits) and gradients in
+bf16, accumulating in fp32 on the tensor cores.  On this random-init ReLU network the direction of dL/d-delta is
+a small residual of a cancelling sum over H x W, and ANY evaluation whose convolution inputs carry <= 10 mantissa
+bits - the engine, the fp32 oracle re-run with fp16-rounded storage (tests/test_cpu_oracle.py), and the
+reference's own network run by cuDNN with TF32 convolutions on the same GPU (profiles/r02_open_precision_*.txt:
+0.9955 at 1x16, 0.9872 at 1x90, 0.9972 at 8x64) - lands at 0.99-0.998 against the strict-fp32 gradient, not at
+the 0.999 the north_star asks for (round 1, bf16 storage: 0.964 / 0.881 / 0.970 at those shapes).
 The >= 0.999 gate is therefore applied where it is well-posed: stage by stage on the engine's own
 activations and incoming gradients (test_backward_layer_local: every backward kernel of the plan
 against torch autograd of that stage), which is what detects kernel bugs.  The end-to-end cosines
-against the fp32 oracle (>= 0.97) and the precision-matched oracle (>= 0.985) are asserted and logged."""
+against the fp32 oracle and the precision-matched oracle are asserted at the bound measured for 10-bit formats
+and logged."""
 import os
 
 import numpy as np
@@ -44,7 +46,7 @@ def setup():
     eng = FlickerEngine(B, T_SMALL)
     eng.load_weights(weights)
     model = oracle_i3d.OracleI3D(weights)
-    model_q = oracle_i3d.OracleI3D(weights, emulate_bf16=True)   # the engine's arithmetic, restated on the CPU
+    model_q = oracle_i3d.OracleI3D(weights, emulate="fp16")   # the engine's arithmetic, restated on the CPU
     return dict(weights=weights, clip=clip, delta=delta, eng=eng, model=model, model_q=model_q, B=B)
 
 
@@ -113,13 +115,13 @@ def test_delta_gradient_cosine(setup, loss_kind):
     gr, gq = ref["grad_data"], refq["grad_data"]
     cos = float((g * gr).sum() / (g.norm() * gr.norm() + 1e-30))
     cosq = float((g * gq).sum() / (g.norm() * gq.norm() + 1e-30))
-    _report(f"[{loss_kind}] adv_loss engine {float(sc[0]):.6f} oracle {ref['adv_loss']:.6f} oracle_bf16 {refq['adv_loss']:.6f}; "
-            f"|g| engine {float(g.norm()):.4e} oracle {float(gr.norm()):.4e} oracle_bf16 {float(gq.norm()):.4e}; "
+    _report(f"[{loss_kind}] adv_loss engine {float(sc[0]):.6f} oracle {ref['adv_loss']:.6f} oracle_fp16 {refq['adv_loss']:.6f}; "
+            f"|g| engine {float(g.norm()):.4e} oracle {float(gr.norm()):.4e} oracle_fp16 {float(gq.norm()):.4e}; "
             f"cosine vs fp32 oracle {cos:.6f}, vs precision-matched oracle {cosq:.6f}")
     assert abs(float(sc[0]) - ref["adv_loss"]) <= 1e-2 * max(1e-3, abs(ref["adv_loss"]))
     assert abs(float(sc[0]) - refq["adv_loss"]) <= 2e-3 * max(1e-3, abs(refq["adv_loss"]))
-    assert cosq >= 0.985, "dL/d-delta cosine against the precision-matched oracle"
-    assert cos >= 0.97, "dL/d-delta cosine against the fp32 oracle (bf16 storage limit, see module docstring)"
+    assert cosq >= 0.995, "dL/d-delta cosine against the precision-matched oracle"
+    assert cos >= 0.99, "dL/d-delta cosine against the fp32 oracle (10-bit-mantissa bound, see module docstring)"
     assert abs(float(g.norm()) / float(gq.norm()) - 1.0) < 0.02
 
 
@@ -152,10 +154,10 @@ def test_backward_layers(setup):
         cos = float((got * ref).sum() / (got.norm() * ref.norm() + 1e-30))
         _report(f"grad {name:20s} cosine {cos:.6f} |engine| {float(got.norm()):.4e} |oracle| {float(ref.norm()):.4e}")
         worst = min(worst, cos)
-    # element-wise cosines decay with depth: two bf16 pipelines with different accumulation order pick
-    # different arg-max / ReLU masks for ~1 % of the units (see module docstring); the per-stage
+    # element-wise cosines decay with depth: two 16-bit pipelines with different accumulation order pick
+    # different arg-max / ReLU masks for a fraction of the units (see module docstring); the per-stage
     # kernels are pinned by test_backward_layer_local instead
-    assert worst >= 0.85
+    assert worst >= 0.95
 
 
 def _cos(a, b):
@@ -166,7 +168,7 @@ def test_backward_layer_local(setup):
     """Every backward kernel invocation of the plan, checked in isolation on the engine's OWN
     activations and incoming gradients (so ReLU-mask / arg-max chaos cannot amplify): for each
     stage the reference input gradient is torch autograd through that one stage, fed with the
-    engine's stage input (exact bf16 values) and the engine's output-gradient buffer."""
+    engine's stage input (exact fp16 values) and the engine's output-gradient buffer."""
     import torch.nn.functional as F
     eng, mq = setup["eng"], setup["model_q"]
     from oracle import oracle_i3d as O
@@ -198,12 +200,12 @@ def test_backward_layer_local(setup):
     def grad(name):
         return eng.read("grad:" + name, shape_of(name)).cpu().permute(0, 4, 1, 2, 3).contiguous()
 
-    def pre(xin, scope):   # pre-activation of one unit with the engine's arithmetic (folded bf16 weights)
+    def pre(xin, scope):   # pre-activation of one unit with the engine's arithmetic (folded fp16 weights)
         wf, bias = mq.folded(scope)
-        return O.conv3d_same(xin, wf.to(torch.bfloat16).float()) + bias.reshape(1, -1, 1, 1, 1)
+        return O.conv3d_same(xin, wf.to(torch.float16).float()) + bias.reshape(1, -1, 1, 1, 1)
 
     def unit(xin, scope):
-        return O._bf16_round(F.relu(pre(xin, scope)))
+        return O._round_st(F.relu(pre(xin, scope)), torch.float16)
 
     worst = 1.0
     order = ["Conv3d_1a_7x7", "MaxPool3d_2a_3x3", "Conv3d_2b_1x1", "Conv3d_2c_3x3", "MaxPool3d_3a_3x3", "Mixed_3b",
@@ -273,8 +275,8 @@ def test_saturated_pixels_gradient(setup):
     nsat = int(((s < -1) | (s > 1)).any(-1).sum())
     _report(f"[saturated] {nsat} saturated pixels ({100.0 * nsat / (s.numel() / 3):.2f} %); |g| engine {float(g.norm()):.4e} "
             f"oracle {float(gr.norm()):.4e}; cosine vs fp32 oracle {cos:.6f}, vs precision-matched oracle {cosq:.6f}")
-    assert cosq >= 0.98
-    assert cos >= 0.97
+    assert cosq >= 0.99
+    assert cos >= 0.985
 
 
 def test_delta_update_matches_oracle(setup):

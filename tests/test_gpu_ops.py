@@ -1,6 +1,8 @@
 """-m gpu: layer-wise parity of the CUDA kernels (through the C-ABI op entry points) against a torch
-fp32 reference of the same op on the same bf16-rounded inputs.  Tolerances: the kernels accumulate
-in fp32 and round the result to bf16, so |err| <= 2^-8 * |ref| + small absolute slack."""
+fp32 reference of the same op on the same 16-bit-rounded inputs (forward ops: float16 activations and weights;
+data gradients: bfloat16 gradients and weights, ReLU mask from a float16 activation).  Tolerances: the kernels
+accumulate in fp32 and round the result to the storage format, so |err| <= 2^-8 * |ref| (bf16) or 2^-10 * |ref|
+(fp16) + small absolute slack."""
 import numpy as np
 import pytest
 import torch
@@ -66,14 +68,14 @@ CONV_CASES = [
 def test_conv3d_forward(B, T, H, W, k, cin, cout):
     from flickering_adversarial_video_b200.engine import op_conv3d
     g = torch.Generator(device="cuda").manual_seed(1234 + cin + cout + k)
-    x = torch.randn((B, T, H, W, cin), generator=g, device="cuda").to(torch.bfloat16)
+    x = torch.randn((B, T, H, W, cin), generator=g, device="cuda").to(torch.float16)
     w = (torch.randn((k, k, k, cin, cout), generator=g, device="cuda") * (2.0 / (k ** 3 * cin)) ** 0.5)
-    w = w.to(torch.bfloat16).float()
+    w = w.to(torch.float16).float()
     bias = torch.randn((cout,), generator=g, device="cuda") * 0.1
     y = op_conv3d(x, w, bias=bias, relu=True)
     torch.cuda.synchronize()
     ref = _ref_conv(x, w, bias, relu=True)
-    _check(y, ref, f"conv fwd {B}x{T}x{H}x{W} k{k} {cin}->{cout}")
+    _check(y, ref, f"conv fwd {B}x{T}x{H}x{W} k{k} {cin}->{cout}", rtol=2 ** -9, atol=5e-3)
 
 
 @pytest.mark.parametrize("B,T,H,W,k,cin,cout", CONV_CASES)
@@ -82,7 +84,7 @@ def test_conv3d_dgrad(B, T, H, W, k, cin, cout):
     if cin % 16 or cout % 16:
         pytest.skip("dgrad GEMM-K needs cout % 16 == 0")
     g = torch.Generator(device="cuda").manual_seed(4321 + cin + cout + k)
-    xin = torch.randn((B, T, H, W, cin), generator=g, device="cuda").to(torch.bfloat16)   # relu source
+    xin = torch.randn((B, T, H, W, cin), generator=g, device="cuda").to(torch.float16)    # relu source (an activation)
     dy = torch.randn((B, T, H, W, cout), generator=g, device="cuda").to(torch.bfloat16)
     w = (torch.randn((k, k, k, cin, cout), generator=g, device="cuda") * (2.0 / (k ** 3 * cout)) ** 0.5)
     w = w.to(torch.bfloat16).float()
@@ -101,9 +103,9 @@ def test_conv3d_channel_slices():
     from flickering_adversarial_video_b200.engine import op_conv3d
     g = torch.Generator(device="cuda").manual_seed(99)
     B, T, H, W = 1, 3, 14, 14
-    xw = torch.randn((B, T, H, W, 256), generator=g, device="cuda").to(torch.bfloat16)
-    w = (torch.randn((3, 3, 3, 64, 32), generator=g, device="cuda") * 0.05).to(torch.bfloat16).float()
-    y = torch.full((B, T, H, W, 128), 7.0, dtype=torch.bfloat16, device="cuda")
+    xw = torch.randn((B, T, H, W, 256), generator=g, device="cuda").to(torch.float16)
+    w = (torch.randn((3, 3, 3, 64, 32), generator=g, device="cuda") * 0.05).to(torch.float16).float()
+    y = torch.full((B, T, H, W, 128), 7.0, dtype=torch.float16, device="cuda")
     op_conv3d(xw, w, relu=False, y=y, y_coff=64, x_coff=128, cin=64, cout=32)
     torch.cuda.synchronize()
     ref = _ref_conv(xw[..., 128:192], w)
@@ -136,8 +138,8 @@ POOL_CASES = [
 def test_maxpool_fwd_bwd(B, T, H, W, Cc, k, s):
     from flickering_adversarial_video_b200.engine import op_maxpool3d, op_maxpool3d_bwd
     g = torch.Generator(device="cuda").manual_seed(5)
-    # distinct values avoid bf16 ties, which the kernel resolves first-match like torch
-    x = torch.randn((B, T, H, W, Cc), generator=g, device="cuda").to(torch.bfloat16)
+    # distinct values avoid fp16 ties, which the kernel resolves first-match like torch
+    x = torch.randn((B, T, H, W, Cc), generator=g, device="cuda").to(torch.float16)
     y, idx = op_maxpool3d(x, k, s)
     xr = x.float().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
     yr = F.max_pool3d(_same_pad(xr, k, s, float("-inf")), k, s)
@@ -147,19 +149,19 @@ def test_maxpool_fwd_bwd(B, T, H, W, Cc, k, s):
     dx = op_maxpool3d_bwd(dy, idx, tuple(x.shape), k, s, add=add, relu_src=x)
     (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 4, 1, 2, 3))
     ref = (gx.permute(0, 2, 3, 4, 1) + add.float()) * (x.float() > 0)
-    # ties in bf16 inputs route to one element in both implementations but maybe a different one;
+    # ties in 16-bit inputs route to one element in both implementations but maybe a different one;
     # compare per-window sums instead of positions when they differ
     _check(dx, ref, f"maxpool bwd {k}/{s}", rtol=2 ** -7, atol=3e-2)
 
 
 def test_maxpool3_ties_route_like_torch():
-    """post-ReLU inputs are full of exact ties (zeros and repeated bf16 values): the separable
+    """post-ReLU inputs are full of exact ties (zeros and repeated fp16 values): the separable
     first-wins stages must route each window's gradient to the same element torch's scan picks."""
     from flickering_adversarial_video_b200.engine import op_maxpool3d, op_maxpool3d_bwd
     g = torch.Generator(device="cuda").manual_seed(11)
     k, s = (3, 3, 3), (1, 1, 1)
     # coarse quantisation -> many equal positive values inside every window
-    x = (torch.randn((1, 10, 14, 14, 64), generator=g, device="cuda").clamp_min(0) * 4).round().div(4).to(torch.bfloat16)
+    x = (torch.randn((1, 10, 14, 14, 64), generator=g, device="cuda").clamp_min(0) * 4).round().div(4).to(torch.float16)
     y, idx = op_maxpool3d(x, k, s)
     xr = x.float().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
     yr = F.max_pool3d(_same_pad(xr, k, s, float("-inf")), k, s)

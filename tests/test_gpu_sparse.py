@@ -45,7 +45,7 @@ def test_sparse_torch_stack_r3d():
             f"oracle {ref['reg_loss']:.5f}; per-pixel grad cosine {cos:.5f}; |g| {float(gd.norm()):.3e}/{float(ref['grad_data'].norm()):.3e}; "
             f"max |delta-oracle| {dd:.2e}, fraction off by > 5e-4: {frac:.4f}")
     assert abs(float(sc[4]) - ref["reg_loss"]) <= 1e-4 * ref["reg_loss"]
-    assert cos >= 0.95
+    assert cos >= 0.98
     # the first Adam step moves every element by ~lr*sign(g): elements whose tiny gradient changes sign differ by 2*lr
     assert dd <= 2.1e-3 and frac <= 0.05
     atk.close()
@@ -91,6 +91,6 @@ def test_sparse_tf_stack_i3d():
     assert cos_local >= 0.999
     # end to end the per-pixel gradient is not averaged over H x W, so the bf16-storage noise of the 20-layer chain
     # (ReLU-mask / arg-max flips) shows up undamped
-    assert cos >= 0.8
+    assert cos >= 0.9
     assert dd <= 2.1e-3
     atk.close()

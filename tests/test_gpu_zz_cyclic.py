@@ -33,7 +33,7 @@ def test_step_rolled_matches_oracle():
     # reported only: how different the un-rolled gradient is (a temporally smooth gradient can be close to its roll)
     cos_wrong = float((g * ref["grad_data"]).sum() / (g.norm() * ref["grad_data"].norm() + 1e-30))
     print(f"step_rolled: logits rel err {rel:.3e}, cosine {cos:.6f} (against the un-rolled gradient {cos_wrong:.3f})")
-    assert rel <= 1e-2 and cos >= 0.97
+    assert rel <= 1e-2 and cos >= 0.99
     # the updated delta: Adam's first step moves every unclamped entry by lr against the sign of its total gradient
     d_new = atk.delta.cpu()
     assert float((d_new - delta).abs().max()) <= 1e-3 * 1.001

@@ -9,7 +9,7 @@ for cin, cout, dgrad in [(64, 192, False), (64, 192, True), (128, 192, False)]:
     if cin == 128:
         H = W = 28
     kc = cout if dgrad else cin
-    x = torch.randn((B, T, H, W, kc), generator=g, device="cuda").to(torch.bfloat16)
+    x = torch.randn((B, T, H, W, kc), generator=g, device="cuda").to(torch.bfloat16 if dgrad else torch.float16)
     w = torch.randn((3, 3, 3, cin, cout), generator=g, device="cuda") * 0.05
     for _ in range(2):
         op_conv3d(x, w, relu=not dgrad, dgrad=dgrad)

@@ -28,7 +28,7 @@ for name, (T, H, W), cin, cout in CASES:
         continue
     for dgrad in (False, True):
         kc = cout if dgrad else cin
-        x = torch.randn((B, T, H, W, kc), generator=g, device="cuda").to(torch.bfloat16)
+        x = torch.randn((B, T, H, W, kc), generator=g, device="cuda").to(torch.bfloat16 if dgrad else torch.float16)
         w = torch.randn((3, 3, 3, cin, cout), generator=g, device="cuda") * 0.05
         sys.stderr.write(f"== {name} {'dgrad' if dgrad else 'fwd'} cin={cin} cout={cout}\n")
         sys.stderr.flush()
