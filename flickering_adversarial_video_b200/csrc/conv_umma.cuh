@@ -217,10 +217,17 @@ __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, i
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
-      stage[lane * 5 + q * 2] = make_uint4(pack16x2(v[0], v[1], of16), pack16x2(v[2], v[3], of16), pack16x2(v[4], v[5], of16),
-                                           pack16x2(v[6], v[7], of16));
-      stage[lane * 5 + q * 2 + 1] = make_uint4(pack16x2(v[8], v[9], of16), pack16x2(v[10], v[11], of16),
-                                               pack16x2(v[12], v[13], of16), pack16x2(v[14], v[15], of16));
+      if (of16) {   // warp-uniform: one conversion per pair, not both formats and a select
+        stage[lane * 5 + q * 2] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                                             pack_f16x2(v[6], v[7]));
+        stage[lane * 5 + q * 2 + 1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]),
+                                                 pack_f16x2(v[14], v[15]));
+      } else {
+        stage[lane * 5 + q * 2] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                             pack_bf16x2(v[6], v[7]));
+        stage[lane * 5 + q * 2 + 1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                                 pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      }
     }
     __syncwarp();
 #pragma unroll

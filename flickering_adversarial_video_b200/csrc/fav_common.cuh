@@ -118,7 +118,9 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 // kind::f16 runs fp16 and bf16 operands at the same rate).  GRADIENTS and the data-gradient weights stay bf16 (range).
 // fp32 -> fp16 saturates to +-65504 instead of overflowing to inf.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  const __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.0f), 65504.0f), fminf(fmaxf(hi, -65504.0f), 65504.0f));
+  // one conversion (overflow gives +-inf), then a packed clamp: two HMNMX2 instead of four scalar FMNMX
+  const __half2 lim = __float2half2_rn(65504.0f);
+  const __half2 v = __hmin2(__hmax2(__floats2half2_rn(lo, hi), __hneg2(lim)), lim);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 __device__ __forceinline__ float f16_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }

@@ -16,108 +16,250 @@ namespace fav {
 //   The stem input written here is x' = adv - delta' (== x wherever the range clip did not fire);
 //   delta' reaches the network as an fp32 per-frame bias of the stem (launch_stem_bias).
 // =============================================================================================
-template <bool kF32>
+// ---- per-lane arithmetic on 16 consecutive pixels (48 uint8 in wds[12]) ----------------------------------------------
+// TF stack.  a[48]: adversarial values; xq[32]: 16 x (RG, B0) fp16 pairs of x'; pw0 / pw1: pass nibbles of pixels 0-7 / 8-15
+__device__ __forceinline__ void apply_math_tf(const float (&x)[48], const float (&d)[3], float (&a)[48], uint32_t (&xq)[32],
+                                              uint32_t& pw0, uint32_t& pw1) {
+  pw0 = 0; pw1 = 0;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    float q[3];
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float s = __fadd_rn(x[3 * p + c], d[c]);
+      const float av = fminf(fmaxf(s, -1.0f), 1.0f);
+      a[3 * p + c] = av;
+      const bool sat = (s < -1.0f) || (s > 1.0f);
+      q[c] = sat ? __fsub_rn(av, d[c]) : x[3 * p + c];
+      m |= sat ? (1u << c) : 0u;
+    }
+    if (p < 8) pw0 |= (~m & 7u) << (4 * p); else pw1 |= (~m & 7u) << (4 * (p - 8));
+    xq[2 * p] = pack_f16x2(q[0], q[1]);
+    xq[2 * p + 1] = pack_f16x2(q[2], 0.0f);
+  }
+}
+
+// The I3D clip given as fp32 (the reference's .npy clips are stored normalised, single_video_npy.py:121): the original
+// one-thread-per-16-pixels form (a rare path: drivers upload uint8 whenever the floats are on the u8/128 - 1 grid).
 __global__ void __launch_bounds__(256)
-apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, float adv_flag,
-             float dclip, __half* __restrict__ xpad, int Wp, int padl,
-             uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
-             uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
+apply_f32in_kernel(const float* __restrict__ clip, const float* __restrict__ delta, float adv_flag,
+                   float dclip, __half* __restrict__ xpad, int Wp, int padl,
+                   uint8_t* __restrict__ adv_u8, float* __restrict__ adv_f32,
+                   uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
   pdl_sync();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool active = gid < groups;
+  if (gid >= groups) return;
   const int gpr = W >> 4;
-  uint32_t sat_mask[16];
-  long long row = 0;
-  int wg = 0;
-  if (active) {
-    wg = static_cast<int>(gid % gpr);
-    row = gid / gpr;  // (b*T + t)*H + h
-    const int t = static_cast<int>((row / H) % T);
-    float d[3];
+  const int wg = static_cast<int>(gid % gpr);
+  const long long row = gid / gpr;  // (b*T + t)*H + h
+  const int t = static_cast<int>((row / H) % T);
+  float d[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      d[c] = __fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip));
-
-    float x[48];
-    const long long e0 = (row * W + wg * 16) * 3;  // first element of this thread
-    if (kF32) {
-      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(clip) + e0);
+  for (int c = 0; c < 3; ++c)
+    d[c] = __fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip));
+  float x[48];
+  const long long e0 = (row * W + wg * 16) * 3;  // first element of this thread
+  const float4* src = reinterpret_cast<const float4*>(clip + e0);
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const float4 v = __ldg(src + i);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-      }
-    } else {
-      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(clip) + e0);
+  for (int i = 0; i < 12; ++i) {
+    const float4 v = __ldg(src + i);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+  float a[48];
+  uint32_t xq[32], pw0, pw1;
+  apply_math_tf(x, d, a, xq, pw0, pw1);
+  uint4* dst = reinterpret_cast<uint4*>(xpad + (row * Wp + padl + wg * 16) * 4);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const uint4 v = __ldg(src + i);
-        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+  for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xq[4 * i], xq[4 * i + 1], xq[4 * i + 2], xq[4 * i + 3]);
+  if (pass_bits) {
+    const long long bt = row / H;
+    const int hh = static_cast<int>(row - bt * H);
+    uint32_t* dstb = pass_bits + (bt * (H + 7) + hh + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + 2 * wg;
+    dstb[0] = pw0;
+    dstb[1] = pw1;
+  }
+  if (adv_u8) {
+    uint4* du = reinterpret_cast<uint4*>(adv_u8 + e0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 3; ++i) {
+      uint32_t o[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            x[16 * i + 4 * j + k] =
-                __fsub_rn(__fmul_rn(static_cast<float>((wds[j] >> (8 * k)) & 0xffu), 0.0078125f), 1.0f);
-      }
-    }
-    float a[48];
-    uint32_t xq[32];  // 16 pixels x (RG, B0) fp16 pairs (u8/128 - 1 is exact in fp16)
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-      float q[3];
-      uint32_t m = 0;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float s = __fadd_rn(x[3 * p + c], d[c]);
-        const float av = fminf(fmaxf(s, -1.0f), 1.0f);
-        a[3 * p + c] = av;
-        const bool sat = (s < -1.0f) || (s > 1.0f);
-        q[c] = sat ? __fsub_rn(av, d[c]) : x[3 * p + c];
-        m |= sat ? (1u << c) : 0u;
-      }
-      sat_mask[p] = m;
-      xq[2 * p] = pack_f16x2(q[0], q[1]);
-      xq[2 * p + 1] = pack_f16x2(q[2], 0.0f);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(xpad + (row * Wp + padl + wg * 16) * 4);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xq[4 * i], xq[4 * i + 1], xq[4 * i + 2], xq[4 * i + 3]);
-
-    if (pass_bits) {
-      // one nibble per pixel, bit c = entry (pixel, c) passes the gradient; 8 zero nibbles left of w = 0, 3 zero rows above h = 0
-      uint32_t w0 = 0, w1 = 0;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        w0 |= (~sat_mask[p] & 7u) << (4 * p);
-        w1 |= (~sat_mask[p + 8] & 7u) << (4 * p);
-      }
-      const long long bt = row / H;
-      const int hh = static_cast<int>(row - bt * H);
-      uint32_t* dstb = pass_bits + (bt * (H + 7) + hh + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + 2 * wg;
-      dstb[0] = w0;
-      dstb[1] = w1;
-    }
-    if (adv_u8) {
-      uint32_t o[12];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
+      for (int j = 0; j < 4; ++j) {
         uint32_t wv = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float f = __fmul_rn(__fadd_rn(a[4 * i + k], 1.0f), 127.5f);
-          wv |= (__float2uint_rz(f) & 0xffu) << (8 * k);
-        }
-        o[i] = wv;
+        for (int k = 0; k < 4; ++k)
+          wv |= (__float2uint_rz(__fmul_rn(__fadd_rn(a[16 * i + 4 * j + k], 1.0f), 127.5f)) & 0xffu) << (8 * k);
+        o[j] = wv;
       }
-      uint4* du = reinterpret_cast<uint4*>(adv_u8 + e0);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) du[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      du[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    if (adv_f32) {
-      float4* df = reinterpret_cast<float4*>(adv_f32 + e0);
+  }
+  if (adv_f32) {
+    float4* df = reinterpret_cast<float4*>(adv_f32 + e0);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) df[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+  }
+}
+
+// uint8 clips, both stacks.  One warp owns 512 consecutive pixels: the 1536 input bytes arrive as three fully coalesced
+// 512-byte loads and are re-dealt through shared memory so that every lane computes 16 whole pixels (conflict-free: a
+// lane's 48 bytes start 12 banks after its neighbour's); the 4 KB of fp16 RGBX output (and the uint8 adversarial video)
+// go back through shared memory the other way, so that every store instruction of the warp covers 512 (torch stack:
+// 256) contiguous bytes.  Round 1 had each lane store its own 128-byte run 16 bytes at a time: 32 half-used sectors
+// per instruction and 43 % of the HBM peak.
+// kAdv = false (the attack loop: neither adversarial-video output is requested) drops the 48 adversarial values per
+// lane from the register budget, which is what sets the occupancy of this latency-bound kernel.
+constexpr int kApplyWarps = 4;
+template <bool kTorch, bool kAdv>
+__global__ void __launch_bounds__(kApplyWarps * 32, kAdv ? 3 : 6)
+apply_u8_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ delta, float adv_flag, float dclip,
+                const fav_norm_params nrm, __half* __restrict__ xpad, int Wp, int padl, uint8_t* __restrict__ adv_u8,
+                float* __restrict__ adv_f32, uint32_t* __restrict__ pass_bits, int T, int H, int W, long long npix) {
+  __shared__ uint4 s_in[kApplyWarps][96];
+  __shared__ uint4 s_out[kApplyWarps][32 * 9];
+  pdl_sync();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p0 = (static_cast<long long>(blockIdx.x) * kApplyWarps + warp) * 512;
+  if (p0 >= npix) return;                                             // warp-uniform
+  const long long left = npix - p0;
+  const int nv = left < 512 ? static_cast<int>(left) : 512;           // valid pixels of the chunk (a multiple of 16)
+  uint4* in = s_in[warp];
+  uint4* out = s_out[warp];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(clip + p0 * 3);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = j * 32 + lane;
+      if (i * 16 < nv * 3) in[i] = __ldg(src + i);
+    }
+  }
+  __syncwarp();
+  const bool active = lane * 16 < nv;
+  const long long px = p0 + lane * 16;
+  const long long row = px / W;                                       // (b*T + t)*H + h
+  const int w0 = static_cast<int>(px - row * W);
+  const long long bt = row / H;
+  const int h = static_cast<int>(row - bt * H);
+  const int t = static_cast<int>(bt % T);
+  const long long b = bt / T;
+  const long long dst_off = (row * Wp + padl + w0) * 4;               // element offset of this lane's run in xpad
+  float a[48];
+  uint32_t xq[32], pw0 = 0, pw1 = 0;
+  if (active) {
+    uint32_t wds[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4 v = in[lane * 3 + i];
+      wds[4 * i] = v.x; wds[4 * i + 1] = v.y; wds[4 * i + 2] = v.z; wds[4 * i + 3] = v.w;
+    }
+    float d[3];
+    if (!kTorch) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) d[c] = __fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip));
+      float x[48];
+#pragma unroll
+      for (int e = 0; e < 48; ++e)
+        x[e] = __fsub_rn(__fmul_rn(static_cast<float>((wds[e >> 2] >> (8 * (e & 3))) & 0xffu), 0.0078125f), 1.0f);
+      apply_math_tf(x, d, a, xq, pw0, pw1);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        d[c] = __fdiv_rn(__fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip)), nrm.std[c]);
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        float q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int e = 3 * p + c;
+          const float u = static_cast<float>((wds[e >> 2] >> (8 * (e & 3))) & 0xffu);
+          const float x = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c]);
+          const float sv = __fadd_rn(x, d[c]);
+          const float av = fminf(fmaxf(sv, nrm.lo), nrm.hi);
+          a[e] = av;
+          const bool sat = (sv < nrm.lo) || (sv > nrm.hi);
+          q[c] = (sat ? ((av - d[c]) * nrm.std[c] + nrm.mean[c]) * 255.0f : u) - 128.0f;   // centred uint8 units
+          if (!sat) { if (p < 8) pw0 |= 1u << (4 * p + c); else pw1 |= 1u << (4 * (p - 8) + c); }
+        }
+        xq[2 * p] = pack_f16x2(q[0], q[1]);
+        xq[2 * p + 1] = pack_f16x2(q[2], 0.0f);
+      }
+    }
+  }
+  // ---- x' (fp16 RGBX): lane-major into shared memory, position-major out of it ----
+  if (!kTorch) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[lane * 9 + i] = make_uint4(xq[4 * i], xq[4 * i + 1], xq[4 * i + 2], xq[4 * i + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = j * 32 + lane;
+      const int L = i >> 3, part = i & 7;
+      const long long off = __shfl_sync(0xffffffffu, dst_off, L);
+      if (L * 16 < nv) *reinterpret_cast<uint4*>(xpad + off + part * 8) = out[L * 9 + part];
+    }
+  } else {
+    // torch pads 3 columns on the left: positions are 8 bytes, so the runs are 8-byte (not 16-byte) aligned
+    uint2* out2 = reinterpret_cast<uint2*>(out);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out2[lane * 17 + i] = make_uint2(xq[2 * i], xq[2 * i + 1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = j * 32 + lane;
+      const int L = i >> 4, part = i & 15;
+      const long long off = __shfl_sync(0xffffffffu, dst_off, L);
+      if (L * 16 < nv) *reinterpret_cast<uint2*>(xpad + off + part * 4) = out2[L * 17 + part];
+    }
+  }
+  if (pass_bits && active) {
+    // one nibble per pixel, bit c = entry (pixel, c) passes the gradient; 8 zero nibbles left of w = 0, 3 zero rows above h = 0
+    uint32_t* dstb = pass_bits + (bt * (H + 7) + h + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + (w0 >> 3);
+    dstb[0] = pw0;
+    dstb[1] = pw1;
+  }
+  if (kAdv && !kTorch && adv_u8) {
+    // uint8 view ((adv + 1.0) * 127.5).astype(uint8) (stats_plots.py:57): back through the input staging buffer
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t wv = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            wv |= (__float2uint_rz(__fmul_rn(__fadd_rn(a[16 * i + 4 * j + k], 1.0f), 127.5f)) & 0xffu) << (8 * k);
+          o[j] = wv;
+        }
+        in[lane * 3 + i] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncwarp();
+    uint4* du = reinterpret_cast<uint4*>(adv_u8 + p0 * 3);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = j * 32 + lane;
+      if (i * 16 < nv * 3) du[i] = in[i];
+    }
+  }
+  if (kAdv && adv_f32 && active) {
+    if (!kTorch) {           // NTHWC like the clip
+      float4* df = reinterpret_cast<float4*>(adv_f32 + px * 3);
 #pragma unroll
       for (int i = 0; i < 12; ++i) df[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    } else {                 // NCTHW like the torch tensors of the reference
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float* o = adv_f32 + (((b * 3 + c) * T + t) * H + h) * static_cast<long long>(W) + w0;
+#pragma unroll
+        for (int p = 0; p < 16; p += 4)
+          *reinterpret_cast<float4*>(o + p) = make_float4(a[3 * p + c], a[3 * (p + 1) + c], a[3 * (p + 2) + c], a[3 * (p + 3) + c]);
+      }
     }
   }
 }
@@ -125,18 +267,24 @@ apply_kernel(const void* __restrict__ clip, const float* __restrict__ delta, flo
 int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_flag, float delta_clip,
                  __half* xpad, int Wp, int padl, uint8_t* adv_u8, float* adv_f32,
                  uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s) {
-  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 * (in_dtype == FAV_F32 ? 4 : 1) + 8.0 + (adv_u8 ? 3.0 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
+  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 * (in_dtype == FAV_F32 ? 4 : 1) + 8.0 + (pass_bits ? 0.5 : 0.0) + (adv_u8 ? 3.0 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
   FAV_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 28), "apply: too many pixels per call");
-  const long long groups = static_cast<long long>(B) * T * H * (W / 16);
-  const int block = 256;
-  const int grid = static_cast<int>(ceil_div64(groups, block));
-  if (in_dtype == FAV_F32)
-    FAV_CUDA(launch_pdl(apply_kernel<true>, grid, block, 0, s, clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8, adv_f32,
-                        pass_bits, T, H, W, groups));
-  else
-    FAV_CUDA(launch_pdl(apply_kernel<false>, grid, block, 0, s, clip, delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8, adv_f32,
-                        pass_bits, T, H, W, groups));
+  const long long npix = static_cast<long long>(B) * T * H * W;
+  if (in_dtype == FAV_F32) {
+    const long long groups = npix / 16;
+    FAV_CUDA(launch_pdl(apply_f32in_kernel, static_cast<int>(ceil_div64(groups, 256)), 256, 0, s, static_cast<const float*>(clip),
+                        delta, adv_flag, delta_clip, xpad, Wp, padl, adv_u8, adv_f32, pass_bits, T, H, W, groups));
+  } else {
+    fav_norm_params none{};
+    const int grid = static_cast<int>(ceil_div64(npix, 512 * kApplyWarps));
+    if (adv_u8 || adv_f32)
+      FAV_CUDA(launch_pdl(apply_u8_kernel<false, true>, grid, kApplyWarps * 32, 0, s, static_cast<const uint8_t*>(clip), delta,
+                          adv_flag, delta_clip, none, xpad, Wp, padl, adv_u8, adv_f32, pass_bits, T, H, W, npix));
+    else
+      FAV_CUDA(launch_pdl(apply_u8_kernel<false, false>, grid, kApplyWarps * 32, 0, s, static_cast<const uint8_t*>(clip), delta,
+                          adv_flag, delta_clip, none, xpad, Wp, padl, adv_u8, adv_f32, pass_bits, T, H, W, npix));
+  }
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;
@@ -201,81 +349,20 @@ int launch_stem_bias_ex(const float* delta, float adv_flag, float delta_clip, co
 // fire, else the value that reproduces adv under the folded normalisation; delta and the -mean/std constant reach the
 // network through the fp32 stem bias table.
 // =============================================================================================
-__global__ void __launch_bounds__(256)
-apply_torch_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ delta, float adv_flag, float dclip,
-                   const fav_norm_params nrm, __half* __restrict__ xpad, int Wp, int padl,
-                   float* __restrict__ adv_f32, uint32_t* __restrict__ pass_bits, int T, int H, int W, long long groups) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= groups) return;
-  const int gpr = W >> 4;
-  const int wg = static_cast<int>(gid % gpr);
-  const long long row = gid / gpr;  // (b*T + t)*H + h
-  const int h = static_cast<int>(row % H);
-  const int t = static_cast<int>((row / H) % T);
-  const long long b = row / (static_cast<long long>(H) * T);
-  float d[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-    d[c] = __fdiv_rn(__fmul_rn(adv_flag, fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip)), nrm.std[c]);
-  const long long e0 = (row * W + wg * 16) * 3;
-  uint32_t wds[12];
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(clip + e0);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const uint4 v = __ldg(src + i);
-      wds[4 * i] = v.x; wds[4 * i + 1] = v.y; wds[4 * i + 2] = v.z; wds[4 * i + 3] = v.w;
-    }
-  }
-  uint32_t xq[32];
-  float a[48];
-  uint32_t pw0 = 0, pw1 = 0;   // pass nibbles of pixels 0-7 / 8-15
-#pragma unroll
-  for (int p = 0; p < 16; ++p) {
-    float q[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int e = 3 * p + c;
-      const float u = static_cast<float>((wds[e >> 2] >> (8 * (e & 3))) & 0xffu);
-      const float x = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c]);
-      const float sv = __fadd_rn(x, d[c]);
-      const float av = fminf(fmaxf(sv, nrm.lo), nrm.hi);
-      a[e] = av;
-      const bool sat = (sv < nrm.lo) || (sv > nrm.hi);
-      q[c] = (sat ? ((av - d[c]) * nrm.std[c] + nrm.mean[c]) * 255.0f : u) - 128.0f;   // centred uint8 units
-      if (!sat) { if (p < 8) pw0 |= 1u << (4 * p + c); else pw1 |= 1u << (4 * (p - 8) + c); }
-    }
-    xq[2 * p] = pack_f16x2(q[0], q[1]);
-    xq[2 * p + 1] = pack_f16x2(q[2], 0.0f);
-  }
-  // torch pads 3 columns on the left: positions are 8 bytes, so the run starts 8-byte (not 16-byte) aligned
-  uint2* dst = reinterpret_cast<uint2*>(xpad + (row * Wp + padl + wg * 16) * 4);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) dst[i] = make_uint2(xq[2 * i], xq[2 * i + 1]);
-  if (pass_bits) {   // same bitmap as apply_kernel (stem_grad.cu)
-    uint32_t* dstb = pass_bits + ((b * T + t) * (H + 7) + h + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + 2 * wg;
-    dstb[0] = pw0;
-    dstb[1] = pw1;
-  }
-  if (adv_f32) {   // NCTHW like the torch tensors of the reference
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float* o = adv_f32 + (((b * 3 + c) * T + t) * H + h) * static_cast<long long>(W) + wg * 16;
-#pragma unroll
-      for (int p = 0; p < 16; p += 4)
-        *reinterpret_cast<float4*>(o + p) = make_float4(a[3 * p + c], a[3 * (p + 1) + c], a[3 * (p + 2) + c], a[3 * (p + 3) + c]);
-    }
-  }
-}
-
 int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, float delta_clip,
                        const fav_norm_params& nrm, __half* xpad, int Wp, int padl, float* adv_f32,
                        uint32_t* pass_bits, int B, int T, int H, int W, cudaStream_t s) {
-  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (adv_f32 ? 12.0 : 0.0)));
+  ProfScope ps(PK_APPLY, s, 0.0, static_cast<double>(B) * T * H * W * (3.0 + 8.0 + (pass_bits ? 0.5 : 0.0) + (adv_f32 ? 12.0 : 0.0)));
   FAV_CHECK_ARG(W % 16 == 0, "apply: W=%d must be a multiple of 16", W);
-  const long long groups = static_cast<long long>(B) * T * H * (W / 16);
-  apply_torch_kernel<<<static_cast<int>(ceil_div64(groups, 256)), 256, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm,
-                                                                                xpad, Wp, padl, adv_f32, pass_bits, T, H, W, groups);
+  const long long npix = static_cast<long long>(B) * T * H * W;
+  // the same warp-per-512-pixels kernel as the TF stack (apply_u8_kernel above), with the torch normalisation
+  const int grid = static_cast<int>(ceil_div64(npix, 512 * kApplyWarps));
+  if (adv_f32)
+    apply_u8_kernel<true, true><<<grid, kApplyWarps * 32, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm, xpad, Wp, padl,
+                                                                  nullptr, adv_f32, pass_bits, T, H, W, npix);
+  else
+    apply_u8_kernel<true, false><<<grid, kApplyWarps * 32, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm, xpad, Wp, padl,
+                                                                   nullptr, nullptr, pass_bits, T, H, W, npix);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -58,6 +58,54 @@ def sum_counts(values, device="cpu", group=None):
     return t.tolist()
 
 
+def agree_min(value, device="cpu", group=None):
+    """MIN over ranks of one host integer (e.g. the number of batches every rank can supply this epoch)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return int(t.item())
+
+
+def lockstep(batches, world=1, device="cpu", group=None, num_batches=None):
+    """Iterate a per-rank batch source so that EVERY rank runs the same number of steps.  Sharded attacks exchange
+    their gradient with one collective per step: a rank whose shard holds fewer batches (record files of unequal
+    length — the conversion script skips videos shorter than 90 frames) would leave the loop early and issue a
+    different collective (the validation count sum) while the others still wait in the step's all-reduce.
+    With `num_batches` (the local batch count, when the source knows it) the ranks agree once on the minimum and every
+    rank stops there; otherwise one MIN all-reduce of a has-next flag precedes every batch.  One rank: plain iteration."""
+    if world <= 1 or not (dist.is_available() and dist.is_initialized()):
+        yield from batches
+        return
+    it = iter(batches)
+    if num_batches is not None:
+        n = agree_min(num_batches, device, group)
+        for _ in range(n):
+            yield next(it)
+        return
+    while True:
+        item = next(it, None)
+        if not agree_min(0 if item is None else 1, device, group):
+            return
+        yield item
+
+
+def shard_indices(indices, rank, world):
+    """Equal-count shard of an index list for one rank: every world-th entry starting at `rank`, cut to the common
+    length len(indices) // world (the remainder is dropped, like the reference's drop_remainder batching)."""
+    per = len(indices) // world
+    return list(indices[rank::world])[:per]
+
+
+def broadcast_ints(values, src=0, device="cpu", group=None):
+    """Rank `src`'s list of integers on every rank (e.g. the random train / test split permutation)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return [int(v) for v in values]
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+    dist.broadcast(t, src=src, group=group)
+    return t.tolist()
+
+
 def replicas_equal(t, group=None):
     """True when `t` (the replicated perturbation / Adam state) is bit-identical on every rank: one MAX all-reduce of
     [t, -t] gives the element-wise max and min over ranks, which coincide only if all ranks agree.  The sharded attacks

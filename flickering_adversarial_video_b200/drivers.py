@@ -53,10 +53,12 @@ def single_video_attack(k_i3d, rgb_sample, correct_cls_id, cfg, result_path=None
     k_i3d.reset()
     step, max_step = 0, int(cfg.MAX_NUM_STEP)
     hard_stop = None if max_extra_steps is None else max_step + int(max_extra_steps)
+    # the reference feeds the same host clip through feed_dict at every step; here it is uploaded once
+    dev_clip = k_i3d._to_device_clip(rgb_sample) if hasattr(k_i3d, "_to_device_clip") else rgb_sample
     while True:
-        out = k_i3d.train_step(rgb_sample, [target_class_id], **kw)
+        out = k_i3d.train_step(dev_clip, [target_class_id], **kw)
         # adversarial test on the UPDATED perturbation (the reference's second sess.run, :217)
-        soft = k_i3d(rgb_sample, adv_flag=1) if (step > max_step or keep_history) else out["softmax"]
+        soft = k_i3d(dev_clip, adv_flag=1) if (step > max_step or keep_history) else out["softmax"]
         pred = int(soft.argmax(-1)[0])
         is_adv = (pred == target_class_id) if cfg.TARGETED_ATTACK else (pred != target_class_id)
         if keep_history:
@@ -122,8 +124,24 @@ def record_batches_from_config(cfg, frames=None, rank=0, world=1, pinned=False, 
         raise FileNotFoundError("no *.tfrecords under TF_RECORDS_TRAIN_PATH / TF_RECORDS_VAL_PATH for this rank")
     B = int(cfg.BATCH_SIZE)
     kw = dict(frames=frames, pinned=pinned, num_parallel_reads=num_parallel_reads)
-    return (lambda: iter(ClipRecordDataset(train, B, repeat=train_repeat, **kw)),
-            lambda: iter(ClipRecordDataset(val, B, **kw)))
+    train_ds = ClipRecordDataset(train, B, repeat=train_repeat, **kw)
+
+    def train_batches():
+        return iter(train_ds)
+    # ranks of a sharded run hold different files: the drivers cut every pass to the shortest shard (dist.lockstep)
+    train_batches.num_batches = train_ds.num_batches
+    return train_batches, (lambda: iter(ClipRecordDataset(val, B, **kw)))
+
+
+def _train_iter(k_i3d, train_batches):
+    """One pass over this rank's training batches; sharded runs stay in lockstep (`dist.lockstep`): every rank runs the
+    number of steps the SHORTEST shard allows.  `train_batches.num_batches` (set by `record_batches_from_config`),
+    when present, lets the ranks agree once per pass instead of once per step."""
+    atk = k_i3d._atk
+    if atk.world <= 1:
+        return train_batches()
+    n = getattr(train_batches, "num_batches", None)
+    return fdist.lockstep(train_batches(), atk.world, atk.device, atk.pg, num_batches=n() if callable(n) else n)
 
 
 def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, epochs=1, log_every=0):
@@ -141,7 +159,7 @@ def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, e
     miss_rate, _ = k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK, target_class_id=target_class_id)
     res["fool_rate"].append(miss_rate)
     for _ in range(epochs):
-        for rgb_sample, sample_label in train_batches():
+        for rgb_sample, sample_label in _train_iter(k_i3d, train_batches):
             labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
             out = k_i3d.train_step(rgb_sample, labels, **kw)
             res["total_loss_l"].append(out["loss"])
@@ -196,7 +214,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
         from .records import SummaryWriter
         writer = SummaryWriter(os.path.join(summary_dir, "train"))
     while step < max_steps:
-        for rgb_sample, sample_label in train_batches():
+        n_before = step
+        for rgb_sample, sample_label in _train_iter(k_i3d, train_batches):
             labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
             out = k_i3d.train_step(rgb_sample, labels, **kw)
             if step % 50 == 0:      # SummarySaverHook(save_steps=50) universal.py:198-201
@@ -218,6 +237,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
                                                   target_class_id=target_class_id)[0]))
             if step >= max_steps:
                 break
+        if step == n_before:
+            raise RuntimeError("universal_attack: the training batch source is empty (on at least one rank)")
     fool.append((step, k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK,
                                       target_class_id=target_class_id)[0]))
     if writer is not None:

@@ -51,6 +51,21 @@ def load_weights(ckpt_path):
         "pass weights=<dict> (e.g. synthetic.i3d_weights()) — there is no network to fetch the Kinetics ckpt")
 
 
+def float_clip_to_u8(t, strict=True):
+    """Exact inverse of the reference's clip normalisation x = u8/128 - 1 (utils/pre_process_rgb_flow.py:234):
+    u8 = (x + 1) * 128, which is exact in fp32 for every grid value.  Returns the uint8 tensor, or — when some value
+    is off the grid or outside [0, 255] — raises ValueError (strict) / returns None."""
+    u = (t + 1.0) * 128.0
+    r = u.round()
+    ok = bool(torch.equal(u, r)) and float(r.min()) >= 0.0 and float(r.max()) <= 255.0
+    if not ok:
+        if strict:
+            raise ValueError("float clip is not on the reference's grid uint8/128 - 1 (utils/pre_process_rgb_flow.py:234); "
+                             "pass the uint8 video")
+        return None
+    return r.to(torch.uint8)
+
+
 class kinetics_i3d:
     """Drop-in for ki3du.kinetics_i3d(ckpt_path, batch_size, init_model, rgb_input, labels,
     cyclic_flag_default_c, cyclic_pert_flag_default_c, default_adv_flag_c)."""
@@ -128,9 +143,17 @@ class kinetics_i3d:
         a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
 
     def _to_device_clip(self, inputs):
+        """uint8 clips go to the device as they are.  Float clips that lie on the reference's grid u/128 - 1
+        (parse_example_uint8, utils/pre_process_rgb_flow.py:234 — every clip its loaders produce) are turned back
+        into that uint8 video exactly (4x less upload, the coalesced uint8 apply kernel); any other float clip takes
+        the engine's fp32 input path unchanged."""
         t = torch.as_tensor(inputs)
-        if t.dtype not in (torch.uint8, torch.float32):
+        if t.is_cuda and t.dtype in (torch.uint8, torch.float32):
+            return t.reshape(self.batch_size, self.frames, _IMAGE_SIZE, _IMAGE_SIZE, 3).contiguous()
+        if t.dtype != torch.uint8:
             t = t.to(torch.float32)
+            u8 = float_clip_to_u8(t, strict=False)
+            t = t if u8 is None else u8
         t = t.reshape(self.batch_size, self.frames, _IMAGE_SIZE, _IMAGE_SIZE, 3)
         return t.to(self.device, non_blocking=True).contiguous()
 
@@ -293,10 +316,13 @@ class kinetics_i3d_L12:
         a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
 
     def _to_device_clip(self, inputs):
-        """The sparse engine path takes uint8 clips (the reference feeds (u8/127.5 - 1) floats: pass the uint8 video)."""
+        """The sparse engine path takes uint8 clips (its backward re-derives the range-clip mask from them).  The
+        reference feeds float clips u8/128 - 1 (parse_example_uint8, utils/pre_process_rgb_flow.py:234): those are
+        inverted exactly with (x + 1) * 128; floats that are not on that grid are refused instead of being silently
+        re-quantised (round 1 inverted with 127.5 and moved most pixels by one level)."""
         t = torch.as_tensor(inputs)
         if t.dtype != torch.uint8:
-            t = ((t.to(torch.float32) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+            t = float_clip_to_u8(t.to(torch.float32), strict=True)
         t = t.reshape(self.batch_size, self.frames, _IMAGE_SIZE, _IMAGE_SIZE, 3)
         return t.to(self.device, non_blocking=True).contiguous()
 

@@ -241,6 +241,24 @@ class ClipRecordDataset:
         self.verify, self.pinned, self.prefetch = verify, pinned, int(prefetch)
         self.num_parallel_reads = None if not num_parallel_reads else max(1, int(num_parallel_reads))
 
+    def num_records(self):
+        """records of one pass over the files (framing scan only: lengths and length CRCs, no payload is touched)"""
+        lib = _lib()
+        n = 0
+        for path in self.filenames:
+            if os.path.getsize(path) == 0:
+                continue
+            mm = np.memmap(path, dtype=np.uint8, mode="r")
+            c = int(lib.favio_tfrecord_index(mm.ctypes.data, mm.nbytes, 0, None, None, 0))
+            if c < 0:
+                raise IOError(f"{path}: corrupt TFRecord framing")
+            n += c
+        return n
+
+    def num_batches(self):
+        """batches this dataset yields: repeat() precedes batch(drop_remainder=True) in the reference's pipeline"""
+        return (self.num_records() * self.repeat) // self.batch_size
+
     def _payloads(self):
         if self.num_parallel_reads is None or self.num_parallel_reads == 1:
             for path in self.filenames:

@@ -277,7 +277,8 @@ class VideoLearnerAdversarial:
         model.py:506-507).  Returns `self.results`."""
         if use_one_cycle_policy:
             raise NotImplementedError("use_one_cycle_policy: only the StepLR schedule of the attack drivers is built")
-        if train_batches is None or valid_batches is None:
+        from_dataset = train_batches is None or valid_batches is None
+        if from_dataset:
             if self.dataset is None:
                 raise ValueError("fit needs train_batches / valid_batches or a dataset")
             if self.dataset.batch_size != self.batch_size or self.dataset.sample_length != self.sample_length:
@@ -289,6 +290,10 @@ class VideoLearnerAdversarial:
         metric = Adversarial_metrics(lp["targeted_attack"], lp.get("target_class_id"))
         atk = self._attack(lr, lp, self.batch_size)
         self._atk = atk
+        if atk.world > 1 and from_dataset and hasattr(self.dataset, "set_shard"):
+            # the gradient is SUMMED over ranks: every rank must see different clips (else the data term is world x too
+            # large against the regulariser) and the same number of them (one collective per step)
+            self.dataset.set_shard(torch.distributed.get_rank(atk.pg), atk.world, atk.device, atk.pg)
         os.makedirs(model_dir, exist_ok=True)
         model_name = model_name or self.model_name
         target = lp.get("target_class_id")
@@ -299,7 +304,9 @@ class VideoLearnerAdversarial:
                 t0 = time.time()
                 miss_rate = total = 0.0
                 loss_sum = n_seen = 0.0
-                for clips, labels in batches():
+                # caller-supplied sharded sources may differ in length per rank: the training pass runs in lockstep
+                it = fdist.lockstep(batches(), atk.world, atk.device, atk.pg) if phase == "train" else batches()
+                for clips, labels in it:
                     lab = labels if not lp["targeted_attack"] else torch.full_like(labels, int(target))
                     clean = atk.predict(clips, adv_flag=0.0).clone()
                     shift = self._cyclic_shift()

@@ -276,6 +276,23 @@ class VideoDataset:
     def __len__(self):
         return len(self.video_records)
 
+    def set_shard(self, rank, world, device="cpu", group=None):
+        """Sharded `fit` (one process per GPU): every rank adopts RANK 0's train / test split (an unseeded
+        torch.randperm differs per process) and keeps an equal-count shard of each (every world-th video, remainder
+        dropped), so that the ranks attack different clips and run the same number of steps.  The reference trains
+        one process over all GPUs (nn.DataParallel, model.py:576-578), i.e. each video once per epoch."""
+        from . import dist as fdist
+        if world <= 1 or getattr(self, "_shard", None) == (rank, world):
+            return
+        full_train = getattr(self, "_full_train", None)
+        if full_train is None:
+            self._full_train, self._full_test = list(self.train_range), list(self.test_range)
+        tr = fdist.broadcast_ints(self._full_train, 0, device, group)
+        te = fdist.broadcast_ints(self._full_test, 0, device, group)
+        self.train_range, self.test_range = fdist.shard_indices(tr, rank, world), fdist.shard_indices(te, rank, world)
+        self._shard = (rank, world)
+        self._cache = {}
+
     def split_by_folder(self, train_pct=0.8):
         """dataset.py:337-399: one folder per class; torch.randperm split (seeded when `seed` is set)"""
         import torch

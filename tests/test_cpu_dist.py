@@ -227,3 +227,42 @@ def test_shard_range_rules():
     with pytest.raises(ValueError):
         fdist.shard_range(10, 0, 4)
     assert fdist.ce_grad_divisor(8, 8) == 64
+
+
+def _lockstep_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from flickering_adversarial_video_b200 import dist as fdist
+    fdist.init_from_env("gloo")
+    # unequal shards: rank 0 can supply 5 batches, rank 1 only 3 (record files of different length)
+    n_local = 5 if rank == 0 else 3
+    for mode in ("count", "flag"):
+        steps = 0
+        src = ((rank, i) for i in range(n_local))
+        for _ in fdist.lockstep(src, world, num_batches=n_local if mode == "count" else None):
+            t = torch.ones(1)
+            fdist.allreduce_sum_(t)            # the step's collective: must pair up on every rank
+            assert float(t) == world
+            steps += 1
+        c = fdist.sum_counts((steps,))         # the collective that FOLLOWS the loop (validation counts)
+        ret[(rank, mode)] = (steps, c[0])
+    # the split permutation of rank 0 reaches every rank; shards are disjoint and of equal length
+    perm = torch.randperm(11, generator=torch.Generator().manual_seed(100 + rank)).tolist()
+    same = fdist.broadcast_ints(perm)
+    ret[(rank, "perm")] = same
+    ret[(rank, "shard")] = fdist.shard_indices(same, rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_unequal_shards_stay_in_lockstep():
+    """ranks whose record files hold different numbers of batches must run the same number of steps (each
+    step is a collective) before they move on to the validation pass's count exchange."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_lockstep_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for mode in ("count", "flag"):
+        assert ret[(0, mode)] == (3, 6.0) and ret[(1, mode)] == (3, 6.0), dict(ret)
+    assert ret[(0, "perm")] == ret[(1, "perm")]
+    a, b = ret[(0, "shard")], ret[(1, "shard")]
+    assert len(a) == len(b) == 5 and not set(a) & set(b)
