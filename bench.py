@@ -1,15 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — attack iterations/s and clip-frames/s of the I3D flickering-attack loop.
+"""bench.py — attack iterations/s and clip-frames/s of the flickering-attack loop.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          engine arm (libfav, sm_100a)
-  python bench.py --impl reference [...]                        reference arm: the CPU restatement of
-                                                                the reference path on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2]     engine arm (libfav, sm_100a)
+  python bench.py --impl reference [...]                                 reference arm: the CPU restatement of
+                                                                         the reference path on the host cores
 For N > 1 launch with torchrun (one rank per GPU, NCCL); RANK/LOCAL_RANK/WORLD_SIZE come from the env.
 
-Workload at N=1 = BASELINE.json configs[1]: I3D single-class-generalisation flickering attack,
-batch 8 x 64x224x224x3 synthetic uint8 clips, random-init weights.  For N > 1 every rank keeps the
-same per-GPU batch (weak scaling, global batch 8N, one sum-all-reduce of the [T,3]+scalars buffer per
-step).  One "step" = apply delta -> forward -> loss -> backward to delta -> all-reduce -> Adam.
+Workloads (`--config`, BASELINE.json `configs`; the default at every N is c2, the configuration the metric is quoted on):
+  c1  configs[0]  I3D single-video flickering attack, 1 x 90x224x224x3
+  c2  configs[1]  I3D class-generalisation flickering attack, 8 x 64x224x224x3 per GPU            (default)
+  c3  configs[2]  I3D universal flickering attack, 8 x 90x224x224x3 per GPU (64 clips over 8 GPUs)
+  c4  configs[3]  R(2+1)D-18 universal attack (torch stack), 16 x 16x112x112x3 per GPU (128 clips over 8 GPUs)
+  c5  configs[4]  R3D-18 single-video sparse per-pixel attack (FLICKERING_ATTACK=False), 1 x 16x112x112x3
+  c5m             the same with MC3-18
+For N > 1 every rank keeps the same per-GPU batch (weak scaling, one sum-all-reduce of the packed gradient + scalars
+buffer per step).  One "step" = apply delta -> forward -> loss -> backward to delta -> all-reduce -> Adam.
 """
 import argparse
 import json
@@ -24,6 +29,23 @@ if ROOT not in sys.path:
 
 METRIC = "clip_frames_per_sec"
 UNIT = "clip-frames/s"
+
+CONFIGS = {
+    "c1": dict(arch="i3d", batch=1, frames=90, sparse=False,
+               what="I3D single-video flickering attack (BASELINE.json configs[0])"),
+    "c2": dict(arch="i3d", batch=8, frames=64, sparse=False,
+               what="I3D class-generalisation flickering attack (BASELINE.json configs[1])"),
+    "c3": dict(arch="i3d", batch=8, frames=90, sparse=False,
+               what="I3D universal flickering attack, per-GPU shard of 64 clips over 8 GPUs (BASELINE.json configs[2])"),
+    "c4": dict(arch="r2plus1d_18", batch=16, frames=16, sparse=False,
+               what="R(2+1)D-18 universal attack, torch stack, per-GPU shard of 128 clips over 8 GPUs (BASELINE.json configs[3])"),
+    "c5": dict(arch="r3d_18", batch=1, frames=16, sparse=True,
+               what="R3D-18 single-video sparse per-pixel attack, FLICKERING_ATTACK=False (BASELINE.json configs[4])"),
+    "c5m": dict(arch="mc3_18", batch=1, frames=16, sparse=True,
+                what="MC3-18 single-video sparse per-pixel attack, FLICKERING_ATTACK=False (BASELINE.json configs[4])"),
+}
+# forward conv + fc FLOPs x 2 (forward + data gradient) per clip-iteration at 16x112x112
+RESNET_GFLOP_PER_CLIP_ITER = {"r3d_18": 162.79, "mc3_18": 173.37, "r2plus1d_18": 162.08}
 
 
 def i3d_forward_macs(frames, height=224, width=224):
@@ -54,24 +76,34 @@ def i3d_forward_macs(frames, height=224, width=224):
     return macs
 
 
+def flop_per_clip_iter(arch, frames):
+    """ALGORITHMIC FLOPs of one clip-iteration: 4 x forward MACs (forward + data gradient, no weight gradient)."""
+    if arch == "i3d":
+        return 4.0 * i3d_forward_macs(frames)
+    return RESNET_GFLOP_PER_CLIP_ITER[arch] * 1e9 * frames / 16.0
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"tflops": float(d.get("bf16_tflops_sustained", 1391.3)), "hbm": float(d.get("hbm_gbs", 6548.2)),
-                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"tflops": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"tflops": float(d.get("bf16_tflops_sustained", 1391.3)), "tflops_burst": float(d.get("bf16_tflops", 1657.2)),
+                "hbm": float(d.get("hbm_gbs", 6548.2)),
+                "source": "measured (MEASURED_PEAKS.json: sustained and burst bf16, copy bandwidth)"}
+    return {"tflops": 1400.0, "tflops_burst": 1650.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi style clock/throttle sampling DURING the timed region (pynvml)."""
+    """nvidia-smi style clock / throttle / power sampling DURING a timed region (pynvml)."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.1):
         super().__init__(daemon=True)
         self.index = index
+        self.period = period
         self.samples = []
+        self.power = []
         self.reasons = set()
         self.max_mhz = None
         self._halt = threading.Event()
@@ -93,6 +125,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                except Exception:
+                    pass
+                try:
                     r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -101,7 +137,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.period)
 
     def stop(self):
         self._halt.set()
@@ -109,53 +145,80 @@ class ClockSampler(threading.Thread):
             self.join(timeout=2)
         s = sorted(self.samples)
         med = s[len(s) // 2] if s else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.power:
+            p = sorted(self.power)
+            out["power_w"] = p[len(p) // 2]
+            out["power_w_max"] = p[-1]
+        return out
 
 
-def cpu_reference_step_time(frames, steps, warmup, threads):
-    """Time the oracle's attack step (CPU restatement of the reference path) on one clip."""
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference path (oracle/), the one place besides tests/ and smoke() that
+# may execute it
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(cfg, frames, steps, warmup, threads):
+    """Seconds per attack iteration of the oracle on ONE clip of this configuration (a bounded sample of the workload)."""
     import torch
     from flickering_adversarial_video_b200 import synthetic
-    from oracle import oracle_i3d
     torch.set_num_threads(threads)
-    weights = synthetic.i3d_weights(seed=0)
-    model = oracle_i3d.OracleI3D(weights)
-    clip = synthetic.clips_u8(1, frames, seed=1000)
-    x = oracle_i3d.normalize_u8(clip)
-    labels = torch.zeros(1, dtype=torch.int64)
-    delta = torch.zeros((frames, 3))
-    opt = oracle_i3d.TFAdam((frames, 3))
-    cfg = dict(improve_loss=True, margin=0.05, beta0=10.0, beta1=0.5, beta2=0.5, beta3=0.5, lr=1e-3)
+    arch = cfg["arch"]
+    if arch == "i3d":
+        from oracle import oracle_i3d
+        model = oracle_i3d.OracleI3D(synthetic.i3d_weights(seed=0))
+        x = oracle_i3d.normalize_u8(synthetic.clips_u8(1, frames, seed=1000))
+        labels = torch.zeros(1, dtype=torch.int64)
+        state = {"delta": torch.zeros((frames, 3))}
+        opt = oracle_i3d.TFAdam((frames, 3))
+        acfg = dict(improve_loss=True, margin=0.05, beta0=10.0, beta1=0.5, beta2=0.5, beta3=0.5, lr=1e-3)
+
+        def step():
+            state["delta"] = oracle_i3d.attack_step(model, x, labels, state["delta"], acfg, opt=opt)["delta_new"]
+    else:
+        from oracle import oracle_resnet
+        model = synthetic.resnet_model(arch, seed=0)
+        clip = synthetic.clips_u8(1, frames, 112, 112, seed=1000)
+        labels = torch.zeros(1, dtype=torch.int64)
+        if cfg["sparse"]:
+            state = {"delta": torch.zeros((frames, 112, 112, 3))}
+
+            def step():
+                state["delta"] = oracle_resnet.sparse_attack_step(model, clip, labels, state["delta"], lambda_=1.0,
+                                                                  max_norm=0.2)["delta_new"]
+        else:
+            state = {"delta": torch.zeros((frames, 3))}
+
+            def step():
+                state["delta"] = oracle_resnet.attack_step(model, clip, labels, state["delta"], max_norm=0.1)["delta_new"]
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = oracle_i3d.attack_step(model, x, labels, delta, cfg, opt=opt)
-        delta = out["delta_new"]
+        step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     return sum(times) / len(times)
 
 
-def run_reference(args):
+def run_reference(args, cfg, B, T):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = len(os.sched_getaffinity(0))
-    sec = cpu_reference_step_time(args.frames, max(1, args.steps), max(1, min(args.warmup, 2)), threads)
-    value = args.frames / sec     # one clip per step
+    sec = cpu_reference_step_time(cfg, T, max(1, args.steps), max(1, min(args.warmup, 2)), threads)
+    value = T / sec     # one clip per step
+    side = 224 if cfg["arch"] == "i3d" else 112
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "iters_per_sec": 1.0 / sec,
-        "config": {"workload": f"I3D class-generalisation flickering attack, {args.frames}x224x224x3 clips "
-                               f"(BASELINE.json configs[1]); reference arm = CPU restatement of the TF1.15 path "
-                               f"(TF1.15 not installable: SURVEY D5), one clip per step",
-                   "batch_per_step": 1, "frames": args.frames},
+        "config": {"workload": f"{cfg['what']}: {T}x{side}x{side}x3 clips; reference arm = CPU restatement of the "
+                               f"reference path (oracle/; TF1.15 is not installable here: DESIGN.md section 8), one clip per step",
+                   "name": args.config, "arch": cfg["arch"], "batch_per_step": 1, "frames": T},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} attack iterations (fwd + bwd-to-input + Adam) on 1 clip of "
-                                   f"{args.frames} frames, torch CPU fp32, {threads} threads"},
+                                   f"{T} frames, torch CPU fp32, {threads} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,11 +226,45 @@ def run_reference(args):
     return 0
 
 
-def run_engine(args):
+# --------------------------------------------------------------------------------------------------------------------
+# engine arm
+# --------------------------------------------------------------------------------------------------------------------
+def build_attack(cfg, B, T, device):
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200.attack import FlickerAttack, SparseAttack
+    arch = cfg["arch"]
+    acfg = {"IMPROVE_ADV_LOSS": True, "TARGETED_ATTACK": False, "USE_LOGITS": False, "PROB_MARGIN": 0.05,
+            "LAMBDA": 10.0 if arch == "i3d" else 1.0, "BETA_1": 0.5, "BETA_2": 0.5}     # run_config.yml / the torch mains
+    weights = synthetic.i3d_weights(seed=0) if arch == "i3d" else synthetic.resnet_model(arch, seed=0).state_dict()
+    if cfg["sparse"]:
+        return SparseAttack(weights, B, T, acfg, device=device, arch=arch)
+    return FlickerAttack(weights, B, T, acfg, device=device, arch=arch)
+
+
+def traffic_for(dom, launches_per_step, config_name):
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu capture — refused when the capture's
+    launch count or workload differs from the live run (a stale file printed as if it were current is worse than none)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        return None, "profiles/r02_traffic.json missing"
+    d = json.load(open(path))
+    if d.get("config") != config_name:
+        return None, f"profiles/r02_traffic.json was captured for config {d.get('config')}, not {config_name}"
+    ent = d.get("families", {}).get(dom)
+    if not ent:
+        return None, f"no ncu traffic entry for {dom}"
+    if abs(ent["launches"] - launches_per_step) > 1e-6:
+        msg = (f"STALE profiles/r02_traffic.json: {dom} has {ent['launches']} launches per step in the ncu capture, "
+               f"{launches_per_step:g} live — re-run tools/make_traffic_json.py on a fresh capture")
+        print("bench.py: " + msg, file=sys.stderr)
+        return None, msg
+    return ent["dram_bytes_per_launch"], None
+
+
+def run_engine(args, cfg, B, T):
     import torch
     import torch.distributed as dist
     from flickering_adversarial_video_b200 import synthetic, _lib
-    from flickering_adversarial_video_b200.attack import FlickerAttack
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,17 +275,14 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-
-    B, T = args.batch, args.frames
-    cfg = {"IMPROVE_ADV_LOSS": True, "TARGETED_ATTACK": False, "USE_LOGITS": False, "PROB_MARGIN": 0.05,
-           "LAMBDA": 10.0, "BETA_1": 0.5, "BETA_2": 0.5}     # run_config.yml CLASS_GEN_ATTACK
-    weights = synthetic.i3d_weights(seed=0)
-    atk = FlickerAttack(weights, B, T, cfg, device=local_rank)
+    arch, sparse = cfg["arch"], cfg["sparse"]
+    side = 224 if arch == "i3d" else 112
+    atk = build_attack(cfg, B, T, local_rank)
     lib = _lib.load()
 
     # resident synthetic inputs: `pool` different batches per rank (each step sees a different batch)
     pool = args.pool
-    clips = [synthetic.clips_u8(B, T, seed=1000 + rank * 100 + i, device=dev) for i in range(pool)]
+    clips = [synthetic.clips_u8(B, T, side, side, seed=1000 + rank * 100 + i, device=dev) for i in range(pool)]
     labels = []
     for c in clips:
         labels.append(atk.predict(c, adv_flag=0.0).argmax(-1))   # reference attacks correctly classified clips
@@ -204,12 +298,22 @@ def run_engine(args):
     l0 = lib.fav_launch_count()
     atk.step(clips[0], labels[0])
     launches_per_step = lib.fav_launch_count() - l0       # kernels one step launches (a graph replays the same nodes)
+    graphs = []
     if use_graph:
         # one CUDA graph per resident batch (the graph is bound to the batch's device buffers)
-        graphs = []
         for i in range(pool):
-            graphs.append(atk.capture(clips[i], labels[i]))
-        atk.reset()
+            if hasattr(atk, "capture"):
+                graphs.append(atk.capture(clips[i], labels[i]))
+            else:
+                for _ in range(2):
+                    atk.step(clips[i], labels[i])
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    atk.step(clips[i], labels[i])
+                graphs.append(g)
+        if hasattr(atk, "reset"):
+            atk.reset()
         step_fn = lambda i: graphs[i % pool].replay()
     else:
         step_fn = lambda i: atk.step(clips[i % pool], labels[i % pool])
@@ -236,32 +340,72 @@ def run_engine(args):
     iters_per_sec = 1e3 / ms_per_step
     value = iters_per_sec * B * world * T
 
+    # ---------------- sustained segment: >= args.sustained_sec of back-to-back steps ----------------
+    sustained = None
+    if args.sustained_sec > 0:
+        n_sus = max(args.steps, int(args.sustained_sec * 1e3 / ms_per_step) + 1)
+        barrier()
+        s2 = ClockSampler(local_rank, period=0.05)
+        s2.start()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(n_sus):
+            step_fn(i)
+        a1.record()
+        barrier()
+        c2 = s2.stop()
+        ms_s = a0.elapsed_time(a1)
+        if world > 1:
+            t = torch.tensor([ms_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_s = float(t.item())
+        sustained = {"ms_per_step": ms_s / n_sus, "steps": n_sus, "seconds": ms_s / 1e3, "sm_mhz": c2.get("sm_mhz"),
+                     "power_w": c2.get("power_w"), "power_w_max": c2.get("power_w_max"), "reasons": c2.get("reasons")}
+
     # ---------------- end-to-end: pinned host clips in, host scalars out ----------------
     host_clips = [c.cpu().pin_memory() for c in clips[:2]]
     host_labels = [l.cpu().pin_memory() for l in labels[:2]]
-    for i in range(2):   # warm the staging path
-        slot = atk.prefetch(host_clips[i % 2], host_labels[i % 2])
-        atk.step_staged(slot)
-    if use_graph:
-        atk.capture_staged()   # the public API's own graph mode: one CUDA graph per staging slot
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    slot = atk.prefetch(host_clips[0], host_labels[0])
-    pending = None
     losses = []
-    for i in range(args.steps):
-        nxt = atk.prefetch(host_clips[(i + 1) % 2], host_labels[(i + 1) % 2]) if i + 1 < args.steps else None
-        out = atk.step_staged(slot)
-        if pending is not None:
-            pending[1].synchronize()
-            losses.append(float(pending[0][_lib.S_TOTAL_LOSS]))
-        pending = out
-        slot = nxt
-    pending[1].synchronize()
-    losses.append(float(pending[0][_lib.S_TOTAL_LOSS]))
-    e1.record()
-    barrier()
+    if hasattr(atk, "prefetch"):
+        for i in range(2):   # warm the staging path
+            slot = atk.prefetch(host_clips[i % 2], host_labels[i % 2])
+            atk.step_staged(slot)
+        if use_graph:
+            atk.capture_staged()   # the public API's own graph mode: one CUDA graph per staging slot
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        slot = atk.prefetch(host_clips[0], host_labels[0])
+        pending = None
+        for i in range(args.steps):
+            nxt = atk.prefetch(host_clips[(i + 1) % 2], host_labels[(i + 1) % 2]) if i + 1 < args.steps else None
+            out = atk.step_staged(slot)
+            if pending is not None:
+                pending[1].synchronize()
+                losses.append(float(pending[0][_lib.S_TOTAL_LOSS]))
+            pending = out
+            slot = nxt
+        pending[1].synchronize()
+        losses.append(float(pending[0][_lib.S_TOTAL_LOSS]))
+        e1.record()
+        barrier()
+    else:
+        # per-pixel attack: the public API is SparseAttack.step on device tensors; the host copies are explicit here
+        stage = torch.empty_like(clips[0])
+        stage_lab = torch.empty_like(labels[0])
+        host_sc = torch.empty(_lib.S_COUNT, dtype=torch.float32).pin_memory()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            stage.copy_(host_clips[i % 2], non_blocking=True)
+            stage_lab.copy_(host_labels[i % 2], non_blocking=True)
+            sc = atk.step(stage, stage_lab)
+            host_sc.copy_(sc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            losses.append(float(host_sc[_lib.S_TOTAL_LOSS]))
+        e1.record()
+        barrier()
     ms_e2e = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev)
@@ -289,39 +433,49 @@ def run_engine(args):
         if fl > 0:
             ent["tflops"] = fl / kms / 1e9
             ent["frac_of_tensor_peak"] = ent["tflops"] / peaks["tflops"]
+            ent["frac_of_tensor_peak_burst"] = ent["tflops"] / peaks["tflops_burst"]
         if by > 0:
             ent["gbs"] = by / kms / 1e6
             ent["frac_of_hbm_peak"] = ent["gbs"] / peaks["hbm"]
         kernels[name] = ent
 
-    # ---------------- roofline: the dominant kernel (conv_halo_kernel) + the whole step ----------------
-    flop_per_clip_iter = 4.0 * i3d_forward_macs(T)
-    step_tflops = iters_per_sec * B * flop_per_clip_iter / 1e12      # per GPU, whole step
+    # ---------------- roofline: the dominant kernel family + the whole step ----------------
+    fpc = flop_per_clip_iter(arch, T)
+    step_tflops = iters_per_sec * B * fpc / 1e12      # per GPU, whole step
     dom = max((k for k in kernels if "tflops" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+    traffic, traffic_err = traffic_for(dom, kernels[dom]["launches_per_step"], args.config)
+    step_roof = {"achieved": step_tflops, "frac": step_tflops / peaks["tflops"], "frac_burst": step_tflops / peaks["tflops_burst"]}
+    if sustained:
+        st = 1e3 / sustained["ms_per_step"] * B * fpc / 1e12
+        step_roof["sustained_achieved"] = st
+        step_roof["sustained_frac"] = st / peaks["tflops"]
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peaks["tflops"],
-                "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peaks["tflops"], "traffic": traffic,
+                "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peaks["tflops"],
+                "peak_burst": peaks["tflops_burst"], "frac_burst": kernels[dom]["tflops"] / peaks["tflops_burst"],
+                "traffic": traffic,
                 "avg_launch_us": kernels[dom]["avg_launch_us"], "launches_per_step": kernels[dom]["launches_per_step"],
                 "share_of_step": kernels[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
-                "step": {"achieved": step_tflops, "frac": step_tflops / peaks["tflops"]},
+                "step": step_roof,
                 "note": f"kernel: algorithmic FLOPs (2 x MACs, real channels) of its launches / their CUDA-event time, "
-                        f"{prof_steps} un-graphed steps; step: 4 x forward conv MACs = {flop_per_clip_iter / 1e9:.2f} "
-                        f"GFLOP per clip-iteration x {B} clips over the whole step time; peak = {peaks['source']}; "
-                        f"traffic = ncu dram bytes per launch (profiles/r01_traffic.json)"}
+                        f"{prof_steps} un-graphed steps; step: {fpc / 1e9:.2f} GFLOP per clip-iteration (4 x forward MACs) "
+                        f"x {B} clips over the whole step time; peak = {peaks['source']}: `frac` against the sustained "
+                        f"figure, `frac_burst` against the burst one (the timed region is short and runs at the burst "
+                        f"clock; `sustained` is a >= {args.sustained_sec:g} s segment); traffic = ncu dram bytes per launch "
+                        f"(profiles/r02_traffic.json, checked against the live launch count)"}
+    if traffic_err:
+        roofline["traffic_error"] = traffic_err
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "iters_per_sec": iters_per_sec,
-        "config": {"workload": f"I3D class-generalisation flickering attack (BASELINE.json configs[1]), "
-                               f"{B} x {T}x224x224x3 uint8 clips per GPU, random-init weights",
+        "dtype": "fp16/bf16", "data": "synthetic", "iters_per_sec": iters_per_sec,
+        "config": {"workload": f"{cfg['what']}, {B} x {T}x{side}x{side}x3 uint8 clips per GPU, random-init weights",
+                   "name": args.config, "arch": arch, "sparse": sparse,
                    "batch_per_gpu": B, "global_batch": B * world, "frames": T, "resident_batches": pool,
                    "cuda_graph": use_graph,
+                   "precision": "fp16 forward activations / weights, bf16 gradients, fp32 accumulation (tcgen05 kind::f16)",
                    "l2": f"each step touches ~{atk.eng.device_bytes / 2**30:.1f} GiB of activations/gradients "
-                         f"(>> 126 MB L2) and a different clip batch"},
+                         f"and a different clip batch (126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "last_total_loss": losses[-1]},
@@ -329,22 +483,33 @@ def run_engine(args):
         "roofline": roofline,
         "kernels": kernels,
     }
+    if sustained:
+        line["sustained"] = sustained
     if world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
-        sec = cpu_reference_step_time(T, 3, 1, threads)
+        sec = cpu_reference_step_time(cfg, T, 3, 1, threads)
         line["cpu_baseline"] = {"value": T / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"3 attack iterations on 1 clip of {T} frames (oracle/oracle_i3d.py, "
-                                          f"torch CPU fp32, {threads} threads), {sec:.2f} s/iter"}
+                                "sample": f"3 attack iterations on 1 clip of {T} frames (oracle/, torch CPU fp32, "
+                                          f"{threads} threads), {sec:.2f} s/iter"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     sys.stderr.flush()
-    if world > 1:
-        # all ranks are past their last collective; leave without the NCCL / CUDA-graph teardown,
-        # which can block on process-group destruction when captured collectives are still referenced
-        barrier()
+    # ---------------- teardown: graphs first (they hold the captured collectives), then the process group ----------------
+    # A watchdog ends the process if the teardown blocks (seen in round 1 with captured NCCL collectives): the JSON line
+    # is already out, so a forced exit loses nothing.
+    def _force_exit():
         os._exit(0)
+    wd = threading.Timer(30.0, _force_exit)
+    wd.daemon = True
+    wd.start()
+    graphs.clear()
     atk.close()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    wd.cancel()
     return 0
 
 
@@ -354,17 +519,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="clips per GPU per step")
-    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json workload (default c2 = configs[1])")
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU per step (default: the config's)")
+    ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--pool", type=int, default=3, help="resident clip batches per rank")
+    ap.add_argument("--sustained-sec", type=float, default=3.0, help="length of the sustained segment (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "engine":
-        args.warmup = max(args.warmup, 1)
+    cfg = CONFIGS[args.config]
+    B = cfg["batch"] if args.batch is None else args.batch
+    T = cfg["frames"] if args.frames is None else args.frames
+    if args.impl == "engine":
+        args.warmup = max(args.warmup, 3)      # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
-        return run_reference(args)
-    return run_engine(args)
+        return run_reference(args, cfg, B, T)
+    return run_engine(args, cfg, B, T)
 
 
 if __name__ == "__main__":

@@ -128,7 +128,9 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def stream_ptr(stream=None):
+def stream_ptr(stream=None, device=None):
+    """raw cudaStream_t of `stream`, or of torch's current stream ON `device` (the engine's device, which need not
+    be the process's current device)"""
     import torch
-    s = stream if stream is not None else torch.cuda.current_stream()
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return C.c_void_p(s.cuda_stream)

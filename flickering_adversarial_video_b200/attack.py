@@ -160,8 +160,14 @@ class FlickerAttack:
         """Capture one step (all libfav launches + the NCCL all-reduce) into a CUDA graph bound to the
         given device tensors; `replay()` re-runs it after the caller refreshed `clips`/`labels` in place.
         Removes ~150 launch gaps per step."""
-        for _ in range(2):                       # warm-up outside capture (lazy cudaFuncSetAttribute etc.)
+        # warm-up outside capture (lazy cudaFuncSetAttribute etc.); the two warm-up steps must not move the attack:
+        # perturbation, Adam moments and step counter are put back afterwards (the capture itself executes nothing)
+        saved = (self.delta.clone(), self.m.clone(), self.v.clone(), self.step_count.clone())
+        for _ in range(2):
             self.step(clips, labels, adv_flag=adv_flag, lr=lr)
+        torch.cuda.synchronize(self.device)
+        for dst, src in zip((self.delta, self.m, self.v, self.step_count), saved):
+            dst.copy_(src)
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
@@ -250,6 +256,12 @@ class FlickerAttack:
         return out
 
     def close(self):
+        """Drops the captured graphs first (they reference the engine's buffers and, in sharded runs, the process
+        group's communicator: the group can only be destroyed cleanly once no graph holds its collectives)."""
+        self._graph = None
+        self._staged_graphs = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
         self.eng.close()
 
 
@@ -302,9 +314,13 @@ class SparseAttack:
             torch.distributed.broadcast(self.delta, src=src, group=process_group)
         self.m = torch.zeros_like(self.delta)
         self.v = torch.zeros_like(self.delta)
-        self.grad = torch.zeros_like(self.delta)
+        # packed exchange buffer [T*H*W*3 gradient | FAV_S_COUNT scalars]: ONE all-reduce per step, like FlickerAttack
+        n = self.delta.numel()
+        self.comm = torch.zeros(n + L.S_COUNT, dtype=torch.float32, device=self.device)
+        self.grad = self.comm[:n].view(shape)
+        self.scalars = self.comm[n:]
+        self.eng.scalars = self.scalars
         self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.scalars = self.eng.scalars
 
     def check_replicas(self):
         if self.world > 1 and not fdist.replicas_equal(self.delta, self.pg):
@@ -325,9 +341,9 @@ class SparseAttack:
         if self.world > 1:
             # margin loss = sum over samples, CE = mean over the GLOBAL batch (fav_loss divides by global_batch): in
             # both cases the global gradient is the plain sum of the rank gradients; the L1,2 term is added once,
-            # after the exchange, by update_pixels.  Scalars 0..3: adversarial loss, fooled count, probability sums.
-            fdist.allreduce_sum_(self.grad, self.pg)
-            fdist.allreduce_sum_(self.scalars[:4], self.pg)
+            # after the exchange, by update_pixels.  Scalars 0..3 (adversarial loss, fooled count, probability sums)
+            # ride in the same buffer; the remaining scalar slots are rewritten by update_pixels after the exchange.
+            fdist.allreduce_sum_(self.comm, self.pg)
         e.update_pixels(self.delta, self.grad, self.m, self.v, self.step_count, self.reg_weight,
                         delta_clip=self.delta_clip, lr=self.lr if lr is None else lr, stack=self.stack)
         return self.scalars

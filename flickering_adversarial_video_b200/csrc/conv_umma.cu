@@ -37,6 +37,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGeom& g, int tile) {
   TileCoord c;
   int nt = tile % g.n_tiles;
   int m = tile / g.n_tiles;
+  if (g.m_tiles == g.tw) {   // flat 1x1x1 tiling (B = T = H = 1): no further divisions (they cost the epilogue warps ~60 instructions a tile)
+    c.b = 0; c.t0 = 0; c.h0 = 0;
+    c.w0 = m * g.bw;
+    c.n0 = nt * g.bn;
+    return c;
+  }
   int wi = m % g.tw;
   m /= g.tw;
   int hi = m % g.th;
@@ -822,6 +828,15 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     const int budget = 212 * 1024;
     int na = 3, bg = 3;
     int nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb));
+    // FAV_HALO_PROF: pairs spend 20-40 % of their time waiting for weight groups (every group crosses the pair: remote
+    // expect_tx, remote TMA completion, multicast commit), while a slab lives for 9 taps x k-steps x mt MMAs — so a
+    // third slab buys less than one or two more weight groups in flight (FAV_HALO_PAIR_NA=3 restores the old choice)
+    static int pair_na = -1;
+    if (pair_na < 0) { const char* ev = getenv("FAV_HALO_PAIR_NA"); pair_na = ev ? atoi(ev) : 2; }
+    if (nb < 5 && pair_na == 2) {
+      const int nb2 = std::min(6, (budget - 2 * g.slab_bytes) / (3 * hb));
+      if (nb2 > nb) { na = 2; nb = nb2; }
+    }
     if (nb < 3) { na = 2; nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb)); }
     if (nb >= 2) {
       g.na = na; g.nb = nb; g.bgroup = bg;

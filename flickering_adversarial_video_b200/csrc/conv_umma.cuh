@@ -145,16 +145,30 @@ __device__ __forceinline__ void epilogue_columns(const ConvEpilogue& e, int bn, 
         const uint4 a = av[q][half];
         vv[0] += lo16(a.x, af16); vv[1] += hi16(a.x, af16); vv[2] += lo16(a.y, af16); vv[3] += hi16(a.y, af16);
         vv[4] += lo16(a.z, af16); vv[5] += hi16(a.z, af16); vv[6] += lo16(a.w, af16); vv[7] += hi16(a.w, af16);
-        if (e.relu) {
+        uint32_t pk[4];   // warp-uniform format / ReLU choice: one conversion instruction per pair
+        if (of16) {
+          if (e.relu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
+            for (int j = 0; j < 4; ++j) pk[j] = pack_f16x2_relu(vv[2 * j], vv[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[j] = pack_f16x2(vv[2 * j], vv[2 * j + 1]);
+          }
+        } else {
+          if (e.relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2_relu(vv[2 * j], vv[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(vv[2 * j], vv[2 * j + 1]);
+          }
         }
         const uint4 mk = mv[q][half];
         uint4 o;
-        o.x = pack16x2(vv[0], vv[1], of16) & relu_mask2(mk.x);   // the mask only zeroes: exact on the packed values
-        o.y = pack16x2(vv[2], vv[3], of16) & relu_mask2(mk.y);
-        o.z = pack16x2(vv[4], vv[5], of16) & relu_mask2(mk.z);
-        o.w = pack16x2(vv[6], vv[7], of16) & relu_mask2(mk.w);
+        o.x = pk[0] & relu_mask2(mk.x);   // the mask only zeroes: exact on the packed values
+        o.y = pk[1] & relu_mask2(mk.y);
+        o.z = pk[2] & relu_mask2(mk.z);
+        o.w = pk[3] & relu_mask2(mk.w);
         *reinterpret_cast<uint4*>(out_row + n + half * 8) = o;
       }
     }
@@ -213,21 +227,27 @@ __device__ __forceinline__ void epilogue_columns_staged(const ConvEpilogue& e, i
           v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
         }
       }
-      if (e.relu) {
+      // warp-uniform format / ReLU choice: ONE conversion instruction per pair does round + (ReLU) + saturate
+      uint32_t pk[8];
+      if (of16) {
+        if (e.relu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-      }
-      if (of16) {   // warp-uniform: one conversion per pair, not both formats and a select
-        stage[lane * 5 + q * 2] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
-                                             pack_f16x2(v[6], v[7]));
-        stage[lane * 5 + q * 2 + 1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]),
-                                                 pack_f16x2(v[14], v[15]));
+          for (int j = 0; j < 8; ++j) pk[j] = pack_f16x2_relu(v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+        }
       } else {
-        stage[lane * 5 + q * 2] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                             pack_bf16x2(v[6], v[7]));
-        stage[lane * 5 + q * 2 + 1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                                 pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        if (e.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
       }
+      stage[lane * 5 + q * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      stage[lane * 5 + q * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
     __syncwarp();
 #pragma unroll
@@ -327,7 +347,8 @@ struct StemGradLaunch {
 size_t stem_grad_bitmap_words(int B, int T, int H, int W);
 void stem_grad_pack_weights(uint16_t* dst /*[KT][160][64]*/, const float* wq /*[KT*49][3][C]*/, int KT, int C);
 int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, int g1_cs, const void* wpk, const uint32_t* bits, int B,
-                   int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3);
+                   int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3,
+                   int c_real = 0);
 int stem_grad_launch(const StemGradLaunch& L, float* grad, cudaStream_t stream);
 
 // Host-side weight packing (16-bit patterns in uint16_t): FORWARD operands are fp16, DATA-GRADIENT operands bf16.

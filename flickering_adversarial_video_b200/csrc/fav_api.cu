@@ -519,7 +519,7 @@ int i3d_plan_dense_stem(fav_handle* h) {
   FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(h->B, h->T, h->H, h->W)));
   FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(7) * 160 * 64));
   FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, y1.cs, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
-                         h->Wo, 7, 2, h->pt, h->ph, h->pw, nullptr));
+                         h->Wo, 7, 2, h->pt, h->ph, h->pw, nullptr, 64));
   h->stem_grad_dense = getenv("FAV_STEM_GRAD_DENSE") != nullptr;
   return FAV_OK;
 }
@@ -745,6 +745,7 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
                                  float adv_flag, float delta_clip, uint8_t* adv_u8, float* adv_f32,
                                  void* stream) {
   FAV_CHECK_ARG(h && clip && delta, "fav_apply_flicker: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));   // a handle is bound to its device, whatever the caller's current device is
   g_pdl_on = h->pdl;
   FAV_CHECK_ARG(in_dtype == FAV_U8 || in_dtype == FAV_F32, "fav_apply_flicker: bad dtype");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -810,6 +811,7 @@ static int run_pool_fwd(fav_handle* h, int pid, cudaStream_t s) {
 
 extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
   FAV_CHECK_ARG(h, "fav_forward: null handle");
+  FAV_CUDA(cudaSetDevice(h->device));
   g_pdl_on = h->pdl;
   if (!h->weights_loaded) {
     set_error("fav_forward: weights not loaded");
@@ -845,6 +847,7 @@ extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
 extern "C" int fav_loss(fav_handle* h, const int64_t* labels, const fav_loss_params* p, float* probs,
                         float* scalars, void* stream) {
   FAV_CHECK_ARG(h && labels && p && scalars, "fav_loss: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));
   return launch_loss(h->logits, labels, *p, h->B, h->K, probs, h->dlogits, scalars,
                      static_cast<cudaStream_t>(stream));
 }
@@ -888,6 +891,7 @@ static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s);
 
 extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   FAV_CHECK_ARG(h && grad, "fav_backward_delta: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));
   g_pdl_on = h->pdl;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->d.arch != FAV_NET_I3D) return resnet_backward(h, grad, s);
@@ -936,6 +940,7 @@ extern "C" int fav_pixels_enable(fav_handle* h) {
 extern "C" int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float* delta_px, float adv_flag,
                                 float delta_clip, float* adv_f32, void* stream) {
   FAV_CHECK_ARG(h && clip_u8 && delta_px, "fav_apply_pixels: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));
   g_pdl_on = h->pdl;
   if (!h->pixels_enabled) {
     set_error("fav_apply_pixels: call fav_pixels_enable first");
@@ -969,6 +974,7 @@ extern "C" int fav_apply_pixels(fav_handle* h, const void* clip_u8, const float*
 
 extern "C" int fav_backward_pixels(fav_handle* h, float* grad_px, void* stream) {
   FAV_CHECK_ARG(h && grad_px, "fav_backward_pixels: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));
   g_pdl_on = h->pdl;
   if (!h->pixels_enabled || !h->last_delta_px || !h->last_clip_u8) {
     set_error("fav_backward_pixels: no per-pixel apply preceded this call");
@@ -990,6 +996,7 @@ extern "C" int fav_pixels_update(fav_handle* h, float* delta_px, const float* gr
                                  float reg_weight, float delta_clip, const fav_adam_params* adam, float* scalars,
                                  void* stream) {
   FAV_CHECK_ARG(h && delta_px && grad_px && m && v && step && adam && scalars, "fav_pixels_update: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));
   if (!h->pixels_enabled) {
     set_error("fav_pixels_update: call fav_pixels_enable first");
     return FAV_ERR_STATE;
@@ -1002,6 +1009,7 @@ extern "C" int fav_delta_update(fav_handle* h, float* delta, const float* grad, 
                                 int64_t* step, const fav_reg_params* reg, const fav_adam_params* adam,
                                 float* scalars, void* stream) {
   FAV_CHECK_ARG(h && delta && grad && m && v && step && reg && adam && scalars, "fav_delta_update: null argument");
+  FAV_CUDA(cudaSetDevice(h->device));
   return launch_delta_update(delta, grad, m, v, step, *reg, *adam, h->last_adv_flag, scalars, h->T,
                              static_cast<cudaStream_t>(stream));
 }

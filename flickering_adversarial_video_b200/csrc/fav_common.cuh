@@ -117,11 +117,22 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 // what decides how many ReLU masks / pooling arg-maxes differ from the reference's fp32 run; tcgen05
 // kind::f16 runs fp16 and bf16 operands at the same rate).  GRADIENTS and the data-gradient weights stay bf16 (range).
 // fp32 -> fp16 saturates to +-65504 instead of overflowing to inf.
+// One F2FP instruction per pair: round to nearest even, saturate to the largest finite value, optionally ReLU first
+// (ncu: the 1x1x1 conv launches are bound by the instruction count of their epilogue).
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  // one conversion (overflow gives +-inf), then a packed clamp: two HMNMX2 instead of four scalar FMNMX
-  const __half2 lim = __float2half2_rn(65504.0f);
-  const __half2 v = __hmin2(__hmax2(__floats2half2_rn(lo, hi), __hneg2(lim)), lim);
-  return *reinterpret_cast<const uint32_t*>(&v);
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 __device__ __forceinline__ float f16_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }
 __device__ __forceinline__ float f16_hi(uint32_t v) { return __high2float(*reinterpret_cast<const __half2*>(&v)); }

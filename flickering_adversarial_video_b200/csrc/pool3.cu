@@ -3,13 +3,19 @@
 //
 // max over a 3x3x3 window = max_t(max_h(max_w x)), and "first arg-max in (t,h,w) scan order" (where TF
 // and torch route the gradient) is exactly what three first-wins 1-D stages select.  The forward
-// therefore keeps three 2-bit codes per element (a1 | a2<<2 | a3<<4: which of the 3 W / H / T
-// candidates won the stage *centred on this element*), and the backward pulls through three 3-tap
-// stages: 9 masked accumulates per element instead of 27.
+// therefore keeps one code byte per element describing the three stages *centred on this element*:
+// bits 0-2 one-hot W-stage winner, bits 3-5 one-hot H-stage winner, bits 6-7 the T-stage winner (0..2);
+// the backward pulls through three 3-tap stages: 9 masked accumulates per element instead of 27.
 //
 // One CTA owns a whole HxW plane of a channel group and streams over T: the W and H stages go through
 // shared memory once per frame, the T stage is a register ring, so nothing is re-read from global
 // memory except the two frames at the ends of a T segment.
+//
+// ncu (profiles/r02_c1_ncu_full_details.txt): round 1's kernels were ISSUE bound, not memory bound — the backward ran
+// 413 instructions per 8-channel item and frame (emulated __vcmpeq4 code tests, fp32 unpack + predicated adds) at 65 %
+// issue-slot utilisation and 29 % of DRAM.  Now a code test is one shift + one PRMT in sign-replication mode per channel
+// pair (the one-hot bit moved to the byte's MSB becomes a halfword mask), and the stage sums are packed bf16x2 adds
+// (at most three terms per stage; an element that wins a single window — the usual case — is exact).
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -33,6 +39,16 @@ __device__ __forceinline__ void first_max(uint32_t (&best)[4], uint32_t (&code)[
     code[j] = (code[j] & ~m) | (d2 & m);
   }
 }
+// the first candidate of a stage needs no compare: it is the running maximum and its code until a later one beats it
+__device__ __forceinline__ void first_set(uint32_t (&best)[4], uint32_t (&code)[4], const uint4 v, const uint32_t d2) {
+  best[0] = v.x; best[1] = v.y; best[2] = v.z; best[3] = v.w;
+  code[0] = code[1] = code[2] = code[3] = d2;
+}
+
+// per-halfword code constants (two channels per 32-bit word; the low byte of each halfword is the channel's code byte)
+constexpr uint32_t kCW0 = 0x00010001u, kCW1 = 0x00020002u, kCW2 = 0x00040004u;   // W stage, one-hot bits 0-2
+constexpr uint32_t kCH0 = 0x00080008u, kCH1 = 0x00100010u, kCH2 = 0x00200020u;   // H stage, one-hot bits 3-5
+constexpr uint32_t kCT0 = 0x00000000u, kCT1 = 0x00400040u, kCT2 = 0x00800080u;   // T stage, value in bits 6-7
 
 // forward.  grid (channel blocks x row tiles, T segments, B); one thread = one (row, w, 8-channel group) item.
 // Small planes are owned whole (halo = 0, R = H); large ones are cut into tiles of R rows that also load one halo
@@ -77,7 +93,7 @@ pool3s1_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y, uint8_t
 
   uint32_t p2[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};   // in-plane max of frame to-1
   uint32_t p1[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};   // in-plane max of frame to
-  uint2 pcode = make_uint2(0u, 0u);                             // a1|a2<<2 bytes of frame to
+  uint2 pcode = make_uint2(0u, 0u);                             // W | H code bytes of frame to
   uint4 nxt = ninf;
   if (live && t_begin - 1 >= 0) nxt = __ldg(reinterpret_cast<const uint4*>(xb + (t_begin - 1) * plane));
   for (int tt = t_begin - 1; tt <= t_end; ++tt) {
@@ -90,28 +106,27 @@ pool3s1_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y, uint8_t
       __syncthreads();
       uint32_t cw[4] = {0u, 0u, 0u, 0u}, ch[4] = {0u, 0u, 0u, 0u};
       if (live) {
-        uint32_t m1[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
-        first_max(m1, cw, X[xs - cgn], 0x00000000u);
-        first_max(m1, cw, cur, 0x00010001u);
-        first_max(m1, cw, X[xs + cgn], 0x00020002u);
+        uint32_t m1[4];
+        first_set(m1, cw, X[xs - cgn], kCW0);
+        first_max(m1, cw, cur, kCW1);
+        first_max(m1, cw, X[xs + cgn], kCW2);
         M1[ms] = make_uint4(m1[0], m1[1], m1[2], m1[3]);
       }
       __syncthreads();
       if (core) {
-        first_max(m2, ch, M1[ms - W * cgn], 0x00000000u);
-        first_max(m2, ch, M1[ms], 0x00040004u);
-        first_max(m2, ch, M1[ms + W * cgn], 0x00080008u);
+        first_set(m2, ch, M1[ms - W * cgn], kCH0);
+        first_max(m2, ch, M1[ms], kCH1);
+        first_max(m2, ch, M1[ms + W * cgn], kCH2);
       }
       ccode.x = __byte_perm(cw[0] | ch[0], cw[1] | ch[1], 0x6420);
       ccode.y = __byte_perm(cw[2] | ch[2], cw[3] | ch[3], 0x6420);
     }
     const int to = tt - 1;
     if (core && to >= t_begin && to < t_end) {
-      uint32_t best[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2};
-      uint32_t c3[4] = {0u, 0u, 0u, 0u};
-      first_max(best, c3, make_uint4(p2[0], p2[1], p2[2], p2[3]), 0x00000000u);
-      first_max(best, c3, make_uint4(p1[0], p1[1], p1[2], p1[3]), 0x00100010u);
-      first_max(best, c3, make_uint4(m2[0], m2[1], m2[2], m2[3]), 0x00200020u);
+      uint32_t best[4], c3[4];
+      first_set(best, c3, make_uint4(p2[0], p2[1], p2[2], p2[3]), kCT0);
+      first_max(best, c3, make_uint4(p1[0], p1[1], p1[2], p1[3]), kCT1);
+      first_max(best, c3, make_uint4(m2[0], m2[1], m2[2], m2[3]), kCT2);
       *reinterpret_cast<uint4*>(yb + to * plane) = make_uint4(best[0], best[1], best[2], best[3]);
       uint2 o;
       o.x = pcode.x | __byte_perm(c3[0], c3[1], 0x6420);
@@ -124,28 +139,31 @@ pool3s1_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y, uint8_t
   }
 }
 
-// ---- backward helpers: acc[j] += v[j] where the 2-bit code field of channel j equals d ----------
-__device__ __forceinline__ uint2 code_match(const uint2 code, const int shift, const uint32_t d) {
-  uint2 m;
-  m.x = __vcmpeq4((code.x >> shift) & 0x03030303u, d * 0x01010101u);
-  m.y = __vcmpeq4((code.y >> shift) & 0x03030303u, d * 0x01010101u);
-  return m;
+// ---- backward helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t sel) {   // generic PRMT: selector bit 3 = replicate the byte's MSB
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
 }
-__device__ __forceinline__ void acc_bf16(float (&acc)[8], const uint4 v, const uint2 m) {
-  const uint32_t d0 = v.x & __byte_perm(m.x, 0, 0x1100), d1 = v.y & __byte_perm(m.x, 0, 0x3322);
-  const uint32_t d2 = v.z & __byte_perm(m.y, 0, 0x1100), d3 = v.w & __byte_perm(m.y, 0, 0x3322);
-  acc[0] += bf16_lo(d0); acc[1] += bf16_hi(d0); acc[2] += bf16_lo(d1); acc[3] += bf16_hi(d1);
-  acc[4] += bf16_lo(d2); acc[5] += bf16_hi(d2); acc[6] += bf16_lo(d3); acc[7] += bf16_hi(d3);
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
-__device__ __forceinline__ void acc_f32(float (&acc)[8], const float4 a, const float4 b, const uint2 m) {
-  if (m.x & 0x00000001u) acc[0] += a.x;
-  if (m.x & 0x00000100u) acc[1] += a.y;
-  if (m.x & 0x00010000u) acc[2] += a.z;
-  if (m.x & 0x01000000u) acc[3] += a.w;
-  if (m.y & 0x00000001u) acc[4] += b.x;
-  if (m.y & 0x00000100u) acc[5] += b.y;
-  if (m.y & 0x00010000u) acc[6] += b.z;
-  if (m.y & 0x01000000u) acc[7] += b.w;
+// acc (8 channels, packed bf16x2) += v where the code bytes' MSB is set: `sx`, `sy` hold the tested bit of every code
+// byte in bit 7 (channels 0-3 / 4-7)
+__device__ __forceinline__ void acc_msb(uint32_t (&acc)[4], const uint4 v, const uint32_t sx, const uint32_t sy) {
+  acc[0] = bf2_add(acc[0], v.x & prmt_b32(sx, 0x9988u));
+  acc[1] = bf2_add(acc[1], v.y & prmt_b32(sx, 0xbbaau));
+  acc[2] = bf2_add(acc[2], v.z & prmt_b32(sy, 0x9988u));
+  acc[3] = bf2_add(acc[3], v.w & prmt_b32(sy, 0xbbaau));
+}
+template <int BIT>   // one-hot / single-bit test: bit BIT of every code byte
+__device__ __forceinline__ void acc_bit(uint32_t (&acc)[4], const uint4 v, const uint2 code) {
+  acc_msb(acc, v, code.x << (7 - BIT), code.y << (7 - BIT));
+}
+// T-stage value 0: neither bit 6 nor bit 7
+__device__ __forceinline__ void acc_t0(uint32_t (&acc)[4], const uint4 v, const uint2 code) {
+  acc_msb(acc, v, ~(code.x | (code.x << 1)), ~(code.y | (code.y << 1)));
 }
 
 // backward.  dx = relu_mask(addend + pool^T(dy)); same grid / item mapping as the forward (halo rows run the T stage only).
@@ -157,11 +175,9 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   extern __shared__ uint4 smem4[];
   const int Rt = R + 2 * halo;
   const int n2 = (R + 2) * W * cgn, n1 = R * (W + 2) * cgn, nc = (R + 2) * (W + 2) * cgn;
-  float4* G2a = reinterpret_cast<float4*>(smem4);     // [R+2][W][cgn]   channels 0-3, row index = local row + 1
-  float4* G2b = G2a + n2;                             //                 channels 4-7
-  float4* G1a = G2b + n2;                             // [R][W+2][cgn]
-  float4* G1b = G1a + n1;
-  uint2* CD = reinterpret_cast<uint2*>(G1b + n1);     // [2][R+2][W+2][cgn]
+  uint4* G2 = smem4;                                  // [R+2][W][cgn]   T-stage sums (bf16 x 8), row index = local row + 1
+  uint4* G1 = G2 + n2;                                // [R][W+2][cgn]   H-stage sums
+  uint2* CD = reinterpret_cast<uint2*>(G1 + n1);      // [2][R+2][W+2][cgn] code bytes
   const int tile = blockIdx.x % nth, cblk = blockIdx.x / nth;
   const int r0 = tile * R;
   const int it = threadIdx.x;
@@ -172,10 +188,10 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   const int h = r0 + lrow;
   const bool live = lr < Rt && h >= 0 && h < H;
   const bool core = live && lrow >= 0 && lrow < R;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) { G2a[i] = z4; G2b[i] = z4; }   // rows outside the image stay 0
-  for (int i = threadIdx.x; i < n1; i += blockDim.x) { G1a[i] = z4; G1b[i] = z4; }   // incl. the border columns
-  for (int i = threadIdx.x; i < 2 * nc; i += blockDim.x) CD[i] = make_uint2(0u, 0u);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) G2[i] = z;                       // rows outside the image stay 0
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) G1[i] = z;                       // incl. the border columns
+  for (int i = threadIdx.x; i < 2 * nc; i += blockDim.x) CD[i] = make_uint2(0u, 0u);  // code 0: no one-hot bit set
   __syncthreads();
   pdl_sync();
 
@@ -192,7 +208,6 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   const int cds = ((lrow + 1) * (W + 2) + w + 1) * cgn + cgi;
   const int crow = (W + 2) * cgn;
 
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   auto ld_dy = [&](int t) { return (live && t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint4*>(dyb + t * plane)) : z; };
   auto ld_cd = [&](int t) {
     return (live && t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint2*>(ib + t * plane)) : make_uint2(0u, 0u);
@@ -209,49 +224,32 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
       if (relu_src) rv = __ldg(reinterpret_cast<const uint4*>(relu_src + boff + t * plane));
     }
     uint2* cd = CD + (t & 1) * nc;
-    // T stage: the window centred on frame t+1-d selected frame t iff its a3 == d
-    float g[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.0f;
-    acc_bf16(g, dC, code_match(cC, 4, 0u));
-    acc_bf16(g, dB, code_match(cB, 4, 1u));
-    acc_bf16(g, dA, code_match(cA, 4, 2u));
+    // T stage: the window centred on frame t+1-d selected frame t iff its T code == d
+    uint32_t g2[4] = {0u, 0u, 0u, 0u};
+    acc_t0(g2, dC, cC);
+    acc_bit<6>(g2, dB, cB);
+    acc_bit<7>(g2, dA, cA);
     if (live) {
-      G2a[g2s] = make_float4(g[0], g[1], g[2], g[3]);
-      G2b[g2s] = make_float4(g[4], g[5], g[6], g[7]);
+      G2[g2s] = make_uint4(g2[0], g2[1], g2[2], g2[3]);
       cd[cds] = cB;
     }
     __syncthreads();
-    // H stage: the window centred on row h+1-d selected row h iff its a2 == d
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.0f;
+    // H stage: the window centred on row h+1-d selected row h iff its H one-hot bit d is set
+    uint32_t g1[4] = {0u, 0u, 0u, 0u};
     if (core) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int o2 = g2s + (1 - d) * W * cgn;
-        acc_f32(g, G2a[o2], G2b[o2], code_match(cd[cds + (1 - d) * crow], 2, static_cast<uint32_t>(d)));
-      }
-      G1a[g1s] = make_float4(g[0], g[1], g[2], g[3]);
-      G1b[g1s] = make_float4(g[4], g[5], g[6], g[7]);
+      acc_bit<3>(g1, G2[g2s + W * cgn], cd[cds + crow]);
+      acc_bit<4>(g1, make_uint4(g2[0], g2[1], g2[2], g2[3]), cB);     // own row: still in registers
+      acc_bit<5>(g1, G2[g2s - W * cgn], cd[cds - crow]);
+      G1[g1s] = make_uint4(g1[0], g1[1], g1[2], g1[3]);
     }
     __syncthreads();
-    // W stage: the window centred on column w+1-d selected column w iff its a1 == d
+    // W stage: the window centred on column w+1-d selected column w iff its W one-hot bit d is set
     if (core) {
-      if (addend) {
-        g[0] = bf16_lo(av.x); g[1] = bf16_hi(av.x); g[2] = bf16_lo(av.y); g[3] = bf16_hi(av.y);
-        g[4] = bf16_lo(av.z); g[5] = bf16_hi(av.z); g[6] = bf16_lo(av.w); g[7] = bf16_hi(av.w);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = 0.0f;
-      }
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int o1 = g1s + (1 - d) * cgn;
-        acc_f32(g, G1a[o1], G1b[o1], code_match(cd[cds + (1 - d) * cgn], 0, static_cast<uint32_t>(d)));
-      }
-      uint4 o;
-      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
-      o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+      uint32_t g0[4] = {av.x, av.y, av.z, av.w};                      // the sibling branches' gradient (zeros without one)
+      acc_bit<0>(g0, G1[g1s + cgn], cd[cds + cgn]);
+      acc_bit<1>(g0, make_uint4(g1[0], g1[1], g1[2], g1[3]), cB);
+      acc_bit<2>(g0, G1[g1s - cgn], cd[cds - cgn]);
+      uint4 o = make_uint4(g0[0], g0[1], g0[2], g0[3]);
       if (relu_src) { o.x &= relu_mask2(rv.x); o.y &= relu_mask2(rv.y); o.z &= relu_mask2(rv.z); o.w &= relu_mask2(rv.w); }
       *reinterpret_cast<uint4*>(dx + boff + t * plane) = o;
     }
@@ -269,6 +267,13 @@ pool3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 // padded coordinate hp = h + pad_before; patch q holds hp = 2q, 2q+1; window ho = q contains both
 // (tap dh = 0 / 1), window ho = q-1 contains only hp = 2q (tap dh = 2).
 // ---------------------------------------------------------------------------------------------
+// bit 7 of every byte of the result is set iff that arg-max byte equals the tap (exact per byte: no borrow between
+// bytes); acc_msb turns those bits into halfword masks with PRMT
+__device__ __forceinline__ uint32_t eq_msb(uint32_t iv, uint32_t tap4) {
+  const uint32_t x = iv ^ tap4;
+  return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x);
+}
+
 template <int KT>   // temporal kernel: 1 (stride 1) or 3 (stride 2)
 __global__ void __launch_bounds__(256)
 pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
@@ -325,10 +330,8 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 #pragma unroll
       for (int ew = 0; ew < 2; ++ew) {
         if (!live[eh][ew]) continue;
-        float acc[8];
         const uint4 a4 = av[eh][ew];
-        acc[0] = bf16_lo(a4.x); acc[1] = bf16_hi(a4.x); acc[2] = bf16_lo(a4.y); acc[3] = bf16_hi(a4.y);
-        acc[4] = bf16_lo(a4.z); acc[5] = bf16_hi(a4.z); acc[6] = bf16_lo(a4.w); acc[7] = bf16_hi(a4.w);
+        uint32_t acc[4] = {a4.x, a4.y, a4.z, a4.w};   // packed bf16x2 sums (at most 4 / 8 windows cover an element)
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
           if (a == 1 && et != 0) continue;
@@ -342,17 +345,14 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
               if (c == 1 && ew != 0) continue;
               const int dw = c ? 2 : ew;
               const uint32_t tap4 = static_cast<uint32_t>((dt * 3 + dh) * 3 + dw) * 0x01010101u;
-              uint2 m;
-              m.x = __vcmpeq4(iv[a][bb][c].x, tap4);
-              m.y = __vcmpeq4(iv[a][bb][c].y, tap4);
-              acc_bf16(acc, dv[a][bb][c], m);
+              acc_msb(acc, dv[a][bb][c], eq_msb(iv[a][bb][c].x, tap4), eq_msb(iv[a][bb][c].y, tap4));
             }
           }
         }
         const uint4 r = rv[eh][ew];
         uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]) & relu_mask2(r.x); o.y = pack_bf16x2(acc[2], acc[3]) & relu_mask2(r.y);
-        o.z = pack_bf16x2(acc[4], acc[5]) & relu_mask2(r.z); o.w = pack_bf16x2(acc[6], acc[7]) & relu_mask2(r.w);
+        o.x = acc[0] & relu_mask2(r.x); o.y = acc[1] & relu_mask2(r.y);
+        o.z = acc[2] & relu_mask2(r.z); o.w = acc[3] & relu_mask2(r.w);
         *reinterpret_cast<uint4*>(dx + eo[eh][ew]) = o;
       }
   }
@@ -437,7 +437,7 @@ int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
   const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads);
   FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
-  const size_t smem = (static_cast<size_t>(t.R + 2) * g.W * 2 + static_cast<size_t>(t.R) * (g.W + 2) * 2) * t.cgn * 16 +
+  const size_t smem = (static_cast<size_t>(t.R + 2) * g.W + static_cast<size_t>(t.R) * (g.W + 2)) * t.cgn * 16 +
                       static_cast<size_t>(2) * (t.R + 2) * (g.W + 2) * t.cgn * 8;
   static bool attr = false;
   if (!attr) {

@@ -279,7 +279,7 @@ int build_resnet(fav_handle* h) {
     FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(B, T, H, W)));
     FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(rn.stem_KT) * 160 * 64));
     FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, bs.g, bs.cs, h->stem_gw, h->pass_bits, B, T, H, W, h->To, h->Ho, h->Wo,
-                           rn.stem_KT, 1, rn.stem_pt, 3, 3, sc));
+                           rn.stem_KT, 1, rn.stem_pt, 3, 3, sc, rn.stem_C));
     h->stem_grad_dense = getenv("FAV_STEM_GRAD_DENSE") != nullptr;
   }
   // ---- head: AdaptiveAvgPool3d(1) + Linear(512, K) ----

@@ -303,7 +303,8 @@ void stem_grad_pack_weights(uint16_t* dst, const float* wq, int KT, int C) {
 }
 
 int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, int g1_cs, const void* wpk, const uint32_t* bits, int B,
-                   int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3) {
+                   int T, int H, int W, int To, int Ho, int Wo, int KT, int st, int pt, int ph, int pw, const float* scale3,
+                   int c_real) {
   memset(L, 0, sizeof(*L));
   FAV_CHECK_ARG(KT >= 1 && KT <= 7 && (st == 1 || st == 2), "stem grad: unsupported temporal kernel %d / stride %d", KT, st);
   FAV_CHECK_ARG(g1_cs % 8 == 0 && g1_cs <= 64, "stem grad: at most 64 stem channels (row stride %d)", g1_cs);
@@ -335,7 +336,8 @@ int stem_grad_plan(StemGradLaunch* L, int device, const void* g1, int g1_cs, con
                   kSgSets * 4 * 4 * 3 * 32 * 4 + 1024 + 64;
   FAV_CHECK_ARG(L->smem_bytes <= 227 * 1024, "stem grad: Wo=%d needs %zu bytes of shared memory", Wo, L->smem_bytes);
   L->grid = std::max(1, std::min(L->m_tiles, sm_count(device)));   // contiguous tile ranges: every CTA gets >= 1 tile
-  L->flops = 2.0 * static_cast<double>(B) * To * Ho * Wo * 64.0 * KT * kSgChunkN;
+  // algorithmic: the KT*49*3 live columns and the real stem channels (the MMAs run 160 columns x 64 channels)
+  L->flops = 2.0 * static_cast<double>(B) * To * Ho * Wo * static_cast<double>(c_real > 0 ? c_real : g1_cs) * KT * 147.0;
   L->bytes = static_cast<double>(B) * To * Ho * Wo * g1_cs * 2.0;
   L->ready = 1;
   return FAV_OK;

@@ -83,10 +83,10 @@ class FlickerEngine:
         if dt == L.FAV_F32:
             assert clip.dtype == torch.float32
         L.check(self.lib.fav_apply_flicker(self.h, L.ptr(clip), dt, L.ptr(delta), adv_flag, delta_clip,
-                                           L.ptr(adv_u8), L.ptr(adv_f32), L.stream_ptr(stream)), "fav_apply_flicker")
+                                           L.ptr(adv_u8), L.ptr(adv_f32), L.stream_ptr(stream, self.device)), "fav_apply_flicker")
 
     def forward(self, stream=None):
-        L.check(self.lib.fav_forward(self.h, L.ptr(self.logits), L.stream_ptr(stream)), "fav_forward")
+        L.check(self.lib.fav_forward(self.h, L.ptr(self.logits), L.stream_ptr(stream, self.device)), "fav_forward")
         return self.logits
 
     def loss(self, labels, improve_loss=True, targeted=False, use_logits=False, margin=0.05, grad_scale=1.0,
@@ -94,11 +94,11 @@ class FlickerEngine:
         assert labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == self.B
         p = L.LossParams(int(improve_loss), int(targeted), int(use_logits), margin, grad_scale, global_batch, stack)
         L.check(self.lib.fav_loss(self.h, L.ptr(labels), C.byref(p), L.ptr(self.probs), L.ptr(self.scalars),
-                                  L.stream_ptr(stream)), "fav_loss")
+                                  L.stream_ptr(stream, self.device)), "fav_loss")
         return self.scalars
 
     def backward(self, stream=None):
-        L.check(self.lib.fav_backward_delta(self.h, L.ptr(self.grad), L.stream_ptr(stream)), "fav_backward_delta")
+        L.check(self.lib.fav_backward_delta(self.h, L.ptr(self.grad), L.stream_ptr(stream, self.device)), "fav_backward_delta")
         return self.grad
 
     def update(self, delta, grad, m, v, step, beta0, beta1, beta2, beta3, lr=1e-3, delta_clip=0.4,
@@ -106,7 +106,7 @@ class FlickerEngine:
         reg = L.RegParams(beta0, beta1, beta2, beta3, delta_clip)
         adam = L.AdamParams(lr, b1, b2, eps, stack)
         L.check(self.lib.fav_delta_update(self.h, L.ptr(delta), L.ptr(grad), L.ptr(m), L.ptr(v), L.ptr(step),
-                                          C.byref(reg), C.byref(adam), L.ptr(self.scalars), L.stream_ptr(stream)),
+                                          C.byref(reg), C.byref(adam), L.ptr(self.scalars), L.stream_ptr(stream, self.device)),
                 "fav_delta_update")
         return self.scalars
 
@@ -121,11 +121,11 @@ class FlickerEngine:
         assert tuple(clip_u8.shape) == (self.B, self.T, self.H, self.W, 3)
         assert delta_px.is_cuda and delta_px.dtype == torch.float32 and tuple(delta_px.shape) == (self.T, self.H, self.W, 3)
         L.check(self.lib.fav_apply_pixels(self.h, L.ptr(clip_u8), L.ptr(delta_px), adv_flag, delta_clip, L.ptr(adv_f32),
-                                          L.stream_ptr(stream)), "fav_apply_pixels")
+                                          L.stream_ptr(stream, self.device)), "fav_apply_pixels")
 
     def backward_pixels(self, grad_px, stream=None):
         assert grad_px.is_cuda and grad_px.dtype == torch.float32 and tuple(grad_px.shape) == (self.T, self.H, self.W, 3)
-        L.check(self.lib.fav_backward_pixels(self.h, L.ptr(grad_px), L.stream_ptr(stream)), "fav_backward_pixels")
+        L.check(self.lib.fav_backward_pixels(self.h, L.ptr(grad_px), L.stream_ptr(stream, self.device)), "fav_backward_pixels")
         return grad_px
 
     def update_pixels(self, delta_px, grad_px, m, v, step, reg_weight, delta_clip=0.0, lr=1e-3, b1=0.9, b2=0.999,
@@ -133,13 +133,13 @@ class FlickerEngine:
         adam = L.AdamParams(lr, b1, b2, eps, stack)
         L.check(self.lib.fav_pixels_update(self.h, L.ptr(delta_px), L.ptr(grad_px), L.ptr(m), L.ptr(v), L.ptr(step),
                                            reg_weight, delta_clip, C.byref(adam), L.ptr(self.scalars),
-                                           L.stream_ptr(stream)), "fav_pixels_update")
+                                           L.stream_ptr(stream, self.device)), "fav_pixels_update")
         return self.scalars
 
     def read(self, name, shape):
         """Debug read of an internal activation / gradient buffer as fp32 [B,T,H,W,C]."""
         out = torch.empty(shape, dtype=torch.float32, device=self.device)
-        n = self.lib.fav_debug_read(self.h, name.encode(), L.ptr(out), out.numel(), L.stream_ptr())
+        n = self.lib.fav_debug_read(self.h, name.encode(), L.ptr(out), out.numel(), L.stream_ptr(None, self.device))
         if n < 0:
             raise L.FavError(f"fav_debug_read({name}): {L.last_error()}")
         assert n == out.numel(), (name, n, out.numel())

@@ -38,3 +38,13 @@ def test_engine_arm_needs_a_gpu():
     r = _run("--steps", "1", "--warmup", "0", "--no-cpu-baseline")
     assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]      # no number is ever printed from a fallback
+
+
+def test_reference_arm_other_configs():
+    """--config selects the BASELINE.json workload for both arms: the torch-stack flicker (c4) and sparse (c5) configs"""
+    for cfgname, arch in (("c4", "r2plus1d_18"), ("c5", "r3d_18")):
+        r = _run("--impl", "reference", "--config", cfgname, "--steps", "1", "--warmup", "0", "--frames", "4")
+        assert r.returncode == 0, r.stderr[-2000:]
+        j = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+        assert j["impl"] == "reference" and j["config"]["name"] == cfgname and j["config"]["arch"] == arch
+        assert j["value"] > 0 and j["config"]["frames"] == 4

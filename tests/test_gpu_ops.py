@@ -29,10 +29,11 @@ def _ref_conv(x_ndhwc, w_tf, bias=None, relu=False):
     return y.permute(0, 2, 3, 4, 1).contiguous()
 
 
-def _check(got, ref, what, rtol=2 ** -7, atol=2e-2):
+def _check(got, ref, what, rtol=2 ** -7, atol=2e-2, scale=None):
+    """|got - ref| <= rtol * scale + atol element-wise; scale defaults to |ref|"""
     got = got.float()
     err = (got - ref).abs()
-    tol = rtol * ref.abs() + atol
+    tol = rtol * (ref.abs() if scale is None else scale) + atol
     bad = (err > tol)
     nbad = int(bad.sum())
     rel = float(err.max() / (ref.abs().max() + 1e-12))
@@ -147,11 +148,14 @@ def test_maxpool_fwd_bwd(B, T, H, W, Cc, k, s):
     dy = torch.randn(y.shape, generator=g, device="cuda").to(torch.bfloat16)
     add = torch.randn(x.shape, generator=g, device="cuda").to(torch.bfloat16)
     dx = op_maxpool3d_bwd(dy, idx, tuple(x.shape), k, s, add=add, relu_src=x)
-    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 4, 1, 2, 3))
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 4, 1, 2, 3), retain_graph=True)
+    (gabs,) = torch.autograd.grad(yr, xr, dy.float().abs().permute(0, 4, 1, 2, 3))
     ref = (gx.permute(0, 2, 3, 4, 1) + add.float()) * (x.float() > 0)
-    # ties in 16-bit inputs route to one element in both implementations but maybe a different one;
-    # compare per-window sums instead of positions when they differ
-    _check(dx, ref, f"maxpool bwd {k}/{s}", rtol=2 ** -7, atol=3e-2)
+    # The kernels sum the windows an element wins in packed bf16 (one rounding per add, at most three adds per
+    # separable stage): the error is bounded by 2^-7 of the MAGNITUDES routed to the element, not of their (possibly
+    # cancelling) sum.  With random inputs an element wins up to 27 windows; in the network it rarely wins more than one.
+    mag = gabs.permute(0, 2, 3, 4, 1) + add.float().abs()
+    _check(dx, ref, f"maxpool bwd {k}/{s}", rtol=2 ** -7, atol=3e-2, scale=mag)
 
 
 def test_maxpool3_ties_route_like_torch():
@@ -168,5 +172,6 @@ def test_maxpool3_ties_route_like_torch():
     assert torch.equal(y.float(), yr.permute(0, 2, 3, 4, 1))
     dy = torch.randn(y.shape, generator=g, device="cuda").to(torch.bfloat16)
     dx = op_maxpool3d_bwd(dy, idx, tuple(x.shape), k, s, add=None, relu_src=None)
-    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 4, 1, 2, 3))
-    _check(dx, gx.permute(0, 2, 3, 4, 1), "maxpool3 ties", rtol=2 ** -7, atol=3e-2)
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 4, 1, 2, 3), retain_graph=True)
+    (gabs,) = torch.autograd.grad(yr, xr, dy.float().abs().permute(0, 4, 1, 2, 3))
+    _check(dx, gx.permute(0, 2, 3, 4, 1), "maxpool3 ties", rtol=2 ** -7, atol=3e-2, scale=gabs.permute(0, 2, 3, 4, 1))

@@ -6,6 +6,7 @@ import torch
 from flickering_adversarial_video_b200.engine import op_conv3d
 
 CASES = [  # name, (T,H,W), cin, cout
+    ("2c", (32, 56, 56), 64, 192),
     ("3b.b1b", (32, 28, 28), 96, 128),
     ("3b.b2b", (32, 28, 28), 16, 32),
     ("3c.b1b", (32, 28, 28), 128, 192),
