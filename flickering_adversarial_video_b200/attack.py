@@ -326,6 +326,15 @@ class SparseAttack:
         if self.world > 1 and not fdist.replicas_equal(self.delta, self.pg):
             raise RuntimeError("the perturbation differs between ranks: the replicas have diverged")
 
+    def state_dict(self):
+        return {"delta": self.delta.cpu(), "m": self.m.cpu(), "v": self.v.cpu(), "step": int(self.step_count.item())}
+
+    def load_state_dict(self, sd):
+        self.delta.copy_(sd["delta"])
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.step_count.fill_(int(sd["step"]))
+
     @property
     def perturbation(self):
         """[T,H,W,3] (I3D, the reference's eps_rgb) or [3,T,H,W] (torch stack, Perturbation.perturbation)"""

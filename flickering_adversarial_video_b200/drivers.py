@@ -13,6 +13,7 @@ import pickle
 
 import numpy as np
 
+from . import checkpoint as fckpt
 from . import dist as fdist
 
 
@@ -144,11 +145,15 @@ def _train_iter(k_i3d, train_batches):
     return fdist.lockstep(train_batches(), atk.world, atk.device, atk.pg, num_batches=n() if callable(n) else n)
 
 
-def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, epochs=1, log_every=0):
+def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, epochs=1, log_every=0, ckpt_prefix=None,
+                     save_every=0):
     """One perturbation over batches of one class; fooling rate on the validation set after every
     pass; `res.pkl` layout of i3d_adversarial_main_single_class_gen.py:358-372.  `train_batches` /
     `val_batches` are callables returning a fresh iterator of (clips, labels) (the reference re-inits
-    its tf.data iterators on OutOfRangeError, :334-337).  Stops at MAX_NUM_STEP."""
+    its tf.data iterators on OutOfRangeError, :334-337).  Stops at MAX_NUM_STEP.
+    ckpt_prefix (the reference's `ckpt_dst`, :192-197,214,373): the run restores the newest
+    `<ckpt_prefix>model_step_XXXXX.npz` (perturbation, Adam moments, step) before it starts, saves one at the start and
+    after every pass over the training batches, and additionally every `save_every` steps when that is > 0."""
     classes = k_i3d.get_kinetics_classes()
     _select_loss(k_i3d, cfg)
     kw = _attack_kwargs(cfg)
@@ -156,9 +161,14 @@ def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, e
     res = {k: [] for k in ("total_loss_l", "adv_loss_l", "reg_loss_l", "norm_reg_loss_l", "diff_norm_reg_loss_l",
                            "perturbation", "fatness", "smoothness", "fool_rate")}
     step, max_step = 0, int(cfg.MAX_NUM_STEP)
+    if ckpt_prefix:
+        step = fckpt.resume(ckpt_prefix, k_i3d._atk)
+        fckpt.save_checkpoint(ckpt_prefix, k_i3d._atk, step)
     miss_rate, _ = k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK, target_class_id=target_class_id)
     res["fool_rate"].append(miss_rate)
     for _ in range(epochs):
+        if step >= max_step:
+            break
         for rgb_sample, sample_label in _train_iter(k_i3d, train_batches):
             labels = [target_class_id] * k_i3d.batch_size if cfg.TARGETED_ATTACK else sample_label
             out = k_i3d.train_step(rgb_sample, labels, **kw)
@@ -173,10 +183,14 @@ def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, e
             if log_every and step % log_every == 0:
                 print("Step: {:05d}, Total Loss: {:.5f}, Cls Loss: {:.5f}".format(step, out["loss"], out["adversarial_loss"]))
             step += 1
+            if ckpt_prefix and save_every and step % int(save_every) == 0:
+                fckpt.save_checkpoint(ckpt_prefix, k_i3d._atk, step)
             if step >= max_step:
                 break
         miss_rate, _ = k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK, target_class_id=target_class_id)
         res["fool_rate"].append(miss_rate)
+        if ckpt_prefix:
+            fckpt.save_checkpoint(ckpt_prefix, k_i3d._atk, step)
         res["total_steps"], res["beta_1"], res["beta_2"] = step, kw["beta_1"], kw["beta_2"]
         if result_path and fdist.is_writer(k_i3d._atk.world):
             os.makedirs(result_path, exist_ok=True)
@@ -188,10 +202,13 @@ def class_gen_attack(k_i3d, train_batches, val_batches, cfg, result_path=None, e
 
 
 def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eval_every=None, log_every=0,
-                     summary_dir=None):
+                     summary_dir=None, model_dir=None, save_checkpoints_steps=100, keep_checkpoint_max=5):
     """UNIVERSAL_ATTACK with FLICKERING_ATTACK=True: same step as class-gen over all classes; returns
     {'perturbation': [T,1,1,3], 'fool_rate': [...], 'scalars': TensorBoard-tag -> list}
-    (tags of i3d_adversarial_main_universal.py:176-196)."""
+    (tags of i3d_adversarial_main_universal.py:176-196).
+    model_dir: the estimator's checkpoint directory (universal.py:300-348) — the perturbation, the Adam moments and the
+    global step are saved there every `save_checkpoints_steps` steps (newest `keep_checkpoint_max` kept, RunConfig :313-320)
+    and a run started on a directory that holds a checkpoint continues from it (`tf.train.latest_checkpoint`, :334-348)."""
     sparse = not getattr(k_i3d, "flickering", True)     # FLICKERING_ATTACK=False: kinetics_i3d_L12, loss = adv + beta_0*beta_1*L12
     classes = k_i3d.get_kinetics_classes()
     _select_loss(k_i3d, cfg)
@@ -209,6 +226,9 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
                             "Perturbation/min", "Probability/prob_to_min", "Probability/prob_to_max")}
     fool = []
     step = 0
+    ckpt_prefix = os.path.join(model_dir, "") if model_dir else None
+    if ckpt_prefix:
+        step = fckpt.resume(ckpt_prefix, k_i3d._atk)
     writer = None
     if summary_dir and fdist.is_writer(k_i3d._atk.world):      # <model_dir>/train/events.out.tfevents.* like SummarySaverHook (universal.py:198-201); sharded runs: rank 0 writes
         from .records import SummaryWriter
@@ -232,6 +252,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
             if log_every and step % log_every == 0:
                 print("step {:05d} loss {:.5f}".format(step, out["loss"]))
             step += 1
+            if ckpt_prefix and save_checkpoints_steps and step % int(save_checkpoints_steps) == 0:
+                fckpt.save_checkpoint(ckpt_prefix, k_i3d._atk, step, keep_max=keep_checkpoint_max)
             if eval_every and step % eval_every == 0:
                 fool.append((step, k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK,
                                                   target_class_id=target_class_id)[0]))
@@ -241,6 +263,8 @@ def universal_attack(k_i3d, train_batches, val_batches, cfg, max_steps=None, eva
             raise RuntimeError("universal_attack: the training batch source is empty (on at least one rank)")
     fool.append((step, k_i3d.evaluate(val_batches(), targeted_attack=cfg.TARGETED_ATTACK,
                                       target_class_id=target_class_id)[0]))
+    if ckpt_prefix:
+        fckpt.save_checkpoint(ckpt_prefix, k_i3d._atk, step, keep_max=keep_checkpoint_max)
     if writer is not None:
         for st, fr in fool:        # eval metric 'ACC: 1- FOOLING_RATIO' (universal.py:160-161) is 1 - fool rate
             writer.add_scalar("ACC: 1- FOOLING_RATIO", 1.0 - fr, st)

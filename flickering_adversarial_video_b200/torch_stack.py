@@ -250,6 +250,25 @@ class VideoLearnerAdversarial:
         self.pert_model.bind(atk.eng)
         return atk
 
+    # ---- resume (r2plus1d_main_universal_attack.py:197-216) -------------------------------------------------
+    def resume_from(self, model_dir, model_name=None, init_pert=True, continue_train=True):
+        """The two restart switches of the reference's main.  INIT_PERT_FROM_LAST_CKPT (`init_pert`): the perturbation is
+        re-read from `valid/perturbation` of the newest `{model_name}_{epoch:03d}.npy` in `model_dir`; CONTINUE_TRAIN
+        (`continue_train`): the returned `start_epoch` continues that file's epoch number (1 when there is none).  When the
+        epoch also left a `.state.npz` next to it (written by `fit(save_model=True)`), the following `fit(start_epoch=...)`
+        restores the Adam moments and step as well, so that the continued run is bit-identical to an uninterrupted one —
+        the reference restarts its optimizer here."""
+        import glob
+        files = sorted(glob.glob(os.path.join(model_dir, "{}_[0-9][0-9][0-9].npy".format(model_name or self.model_name))))
+        if not files:
+            return 1
+        last = files[-1]
+        if init_pert:
+            pert = np.load(last, allow_pickle=True)[-1]["valid/perturbation"]
+            self.pert_model.init_perturbation(pert)
+        self._resume_state = last[:-4] + ".state.npz"
+        return int(last[:-4].split("_")[-1]) + 1 if continue_train else 1
+
     def _cyclic_shift(self):
         """Perturbation.forward draws `np.random.randint(0, T)` per adversarial forward when cyclic_pert (model.py:91-92)"""
         if not self.pert_model.cyclic_pert:
@@ -297,6 +316,12 @@ class VideoLearnerAdversarial:
         os.makedirs(model_dir, exist_ok=True)
         model_name = model_name or self.model_name
         target = lp.get("target_class_id")
+        state_path = getattr(self, "_resume_state", None)
+        if state_path and start_epoch > 1 and os.path.exists(state_path):
+            from . import checkpoint as fckpt       # continue exactly: perturbation, Adam moments and Adam step
+            fckpt.restore_checkpoint(state_path, atk)
+            self._sync_pert(atk)
+        self._resume_state = None
         for e in range(start_epoch, epochs + 1):
             lr_e = lr_schedule[e]
             result = OrderedDict()
@@ -351,6 +376,9 @@ class VideoLearnerAdversarial:
             if save_model and fdist.is_writer(atk.world):
                 np.save(os.path.join(model_dir, "{}_{:03d}.npy".format(model_name, e)),
                         np.array(self.results, dtype=object), allow_pickle=True)
+                sd = atk.state_dict()          # sidecar for an exact restart (resume_from)
+                np.savez(os.path.join(model_dir, "{}_{:03d}.state.npz".format(model_name, e)), delta=sd["delta"].numpy(),
+                         m=sd["m"].numpy(), v=sd["v"].numpy(), adam_step=np.int64(sd["step"]), step=np.int64(e))
         return self.results
 
     # ---- single-video attack (model.py:918-1203) --------------------------------------------------------------

@@ -244,7 +244,26 @@ def test_torch_fit_with_the_real_attack_factory(monkeypatch, tmp_path):
     labels = probe.predict(clips, adv_flag=0.0).argmax(-1)
     batches = lambda: [(clips, labels)] * 2
     res = lrn.fit(1e-2, 2, str(tmp_path), save_model=True, loss_params_dict=lp, train_batches=batches, valid_batches=batches)
-    assert len(res) == 2 and sorted(os.listdir(str(tmp_path))) == ["r3d_18_001.npy", "r3d_18_002.npy"]
+    assert len(res) == 2 and sorted(f for f in os.listdir(str(tmp_path)) if f.endswith(".npy")) == ["r3d_18_001.npy", "r3d_18_002.npy"]
+    final = lrn._atk.state_dict()
+    # restart after epoch 1 (r2plus1d_main_universal_attack.py:197-216: INIT_PERT_FROM_LAST_CKPT + CONTINUE_TRAIN) from a fresh
+    # learner: the epoch numbering continues and, with the state sidecar, so do the Adam moments -> bit-identical end state
+    d2 = tmp_path / "resume"
+    first = Learner()
+    first.fit(1e-2, 1, str(d2), save_model=True, loss_params_dict=lp, train_batches=batches, valid_batches=batches)
+    cont = Learner()
+    start = cont.resume_from(str(d2))
+    assert start == 2
+    res2 = cont.fit(1e-2, 2, str(d2), save_model=True, loss_params_dict=lp, train_batches=batches, valid_batches=batches,
+                    start_epoch=start, lr_step_size=100)
+    assert len(res2) == 1 and os.path.exists(str(d2 / "r3d_18_002.npy"))
+    got = cont._atk.state_dict()
+    ref_run = Learner()
+    ref_run.fit(1e-2, 2, str(tmp_path / "ref"), loss_params_dict=lp, train_batches=batches, valid_batches=batches, lr_step_size=100)
+    ref = ref_run._atk.state_dict()
+    for key in ("delta", "m", "v"):
+        assert torch.equal(got[key], ref[key]), key
+    assert got["step"] == ref["step"] == final["step"]
     assert 0.0 <= res[-1]["valid/fooling_ratio"] <= 1.0 and res[-1]["train/pert_thickness"] > 0
     lrn.pert_model.cyclic_pert = True
     lrn.fit(1e-2, 1, str(tmp_path / "cyc"), loss_params_dict=lp, train_batches=batches, valid_batches=batches)
@@ -252,3 +271,59 @@ def test_torch_fit_with_the_real_attack_factory(monkeypatch, tmp_path):
     bad.pert_model.max_value = 1.0
     with pytest.raises(NotImplementedError):
         bad.fit(1e-2, 1, str(tmp_path), loss_params_dict=lp, train_batches=batches, valid_batches=batches)
+
+
+def test_universal_and_class_gen_resume_bit_identically(standin, tmp_path):
+    """Checkpoint / resume of the TF drivers (i3d_adversarial_main_universal.py:310-348: model_dir with
+    save_checkpoints_steps / keep_checkpoint_max / latest_checkpoint; single_class_gen.py:192-197,214,373: `model_step_XXXXX`
+    files): a run interrupted at a checkpoint and restarted in a NEW process state continues bit-identically."""
+    from flickering_adversarial_video_b200 import checkpoint as fckpt, config, drivers
+    cfg = config.default_config()
+    clips = [_clip(10 + i) for i in range(4)]
+
+    def make():
+        k = standin.kinetics_i3d(ckpt_path="", batch_size=1, frames=T, weights={})
+        label = 7
+        return k, (lambda: iter([(c, [label]) for c in clips]))
+
+    ua = cfg.UNIVERSAL_ATTACK
+    k, batches = make()
+    full = drivers.universal_attack(k, batches, batches, ua, max_steps=8)
+    ref = k._atk.state_dict()
+    k.close()
+    md = str(tmp_path / "ua_model")
+    k, batches = make()
+    drivers.universal_attack(k, batches, batches, ua, max_steps=4, model_dir=md, save_checkpoints_steps=2, keep_checkpoint_max=2)
+    k.close()
+    saved = sorted(os.listdir(md))
+    assert saved == ["model_step_00002.npz", "model_step_00004.npz"], saved          # keep_checkpoint_max pruned nothing yet
+    k, batches = make()                                                               # fresh object: zero delta, zero Adam
+    res = drivers.universal_attack(k, batches, batches, ua, max_steps=8, model_dir=md, save_checkpoints_steps=2,
+                                   keep_checkpoint_max=2)
+    got = k._atk.state_dict()
+    assert res["total_steps"] == 8 and got["step"] == ref["step"] == 8
+    for key in ("delta", "m", "v"):
+        assert torch.equal(got[key], ref[key]), key
+    assert np.array_equal(res["perturbation"], full["perturbation"])
+    assert sorted(os.listdir(md)) == ["model_step_00006.npz", "model_step_00008.npz"]   # newest two kept
+    k.close()
+
+    # class-generalisation driver: checkpoint at the start and after every pass; restart continues from the file's step
+    cg = cfg.CLASS_GEN_ATTACK
+    cg.MAX_NUM_STEP = 8
+    k, batches = make()
+    drivers.class_gen_attack(k, batches, batches, cg, epochs=2)
+    ref = k._atk.state_dict()
+    k.close()
+    prefix = str(tmp_path / "cg") + os.sep
+    k, batches = make()
+    drivers.class_gen_attack(k, batches, batches, cg, epochs=1, ckpt_prefix=prefix)
+    k.close()
+    assert fckpt.latest_checkpoint(prefix)[0] == 4
+    k, batches = make()
+    res = drivers.class_gen_attack(k, batches, batches, cg, epochs=5, ckpt_prefix=prefix)
+    got = k._atk.state_dict()
+    assert res["total_steps"] == 8
+    for key in ("delta", "m", "v"):
+        assert torch.equal(got[key], ref[key]), key
+    k.close()
