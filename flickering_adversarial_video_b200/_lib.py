@@ -62,6 +62,8 @@ class AdamParams(C.Structure):
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "fav_create": (_i, [C.POINTER(_vp), _i, C.POINTER(NetDesc)]),
+    "fav_create_eval": (_i, [C.POINTER(_vp), _i, C.POINTER(NetDesc)]),
+    "fav_eval_batch": (_i, [_vp, _vp, _vp, _i, _vp, _f, _vp, _i, _i, _i64, _i, C.POINTER(LossParams), _vp, _vp, _vp, _vp]),
     "fav_destroy": (_i, [_vp]),
     "fav_last_error": (C.c_char_p, []),
     "fav_device_bytes": (_i64, [_vp]),

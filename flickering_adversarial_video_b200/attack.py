@@ -15,7 +15,7 @@ import torch
 
 from . import _lib as L
 from . import dist as fdist
-from .engine import FlickerEngine
+from .engine import EvalEngine, FlickerEngine
 
 
 class FlickerAttack:
@@ -32,6 +32,8 @@ class FlickerAttack:
         None = the reference's default, every frame."""
         self.eng = FlickerEngine(batch, frames, height, width, num_classes, device, arch=arch)
         self.eng.load_weights(weights)
+        self._weights = weights      # the evaluation handle (evaluator()) packs its own forward weights from these
+        self._eval = None
         self.arch = arch
         if stack is None:
             stack = "torch" if self.eng.torch_stack else "tf"
@@ -244,6 +246,39 @@ class FlickerAttack:
         logits = self.eng.forward()
         return torch.softmax(logits, dim=-1)
 
+    def evaluator(self):
+        """The forward-only evaluation handle of this attack (same network, batch and device), created on first use."""
+        if self._eval is None:
+            e = self.eng
+            self._eval = EvalEngine(e.B, e.T, e.H, e.W, e.K, e.device.index or 0, arch=self.arch)
+            self._eval.load_weights(self._weights)
+        return self._eval
+
+    def eval_batch(self, clips, labels, clips_adv=None, n_clips=None, targeted=False, target_class=None,
+                   exclude_misclassify=True, shift=0, with_loss=False, want_probs=False):
+        """One validation batch through the fused evaluation pass (row f3): clean and perturbed clips in one forward,
+        `evaluator().counts` += [miss, valid] on the device.  `shift`: the network sees roll(delta, shift) (cyclic
+        perturbation); with_loss: the adversarial-loss scalars of the perturbed rows go to `evaluator().scalars`."""
+        ev = self.evaluator()
+        delta = self._applied_delta()
+        if shift:
+            delta = torch.roll(delta, int(shift), dims=0)
+        loss = None
+        if with_loss:
+            loss = dict(improve_loss=self.improve_loss, targeted=self.targeted, use_logits=self.use_logits,
+                        margin=self.margin, stack=self.stack)
+        return ev.eval_batch(clips, delta.contiguous(), labels, clips_adv=clips_adv, n_clips=n_clips,
+                             delta_clip=self.delta_clip, targeted=targeted, target_class=target_class,
+                             exclude_misclassify=exclude_misclassify, loss=loss, want_probs=want_probs)
+
+    def eval_counts(self, reset=True):
+        """(miss, valid) accumulated by eval_batch since the last reset — one device-to-host read per validation pass."""
+        ev = self.evaluator()
+        miss, valid = (int(x) for x in ev.counts.cpu())
+        if reset:
+            ev.reset_counts()
+        return miss, valid
+
     def adversarial_video(self, clips, as_uint8=False):
         """`adversarial_inputs_rgb` (fp32, utils/kinetics_i3d_utils.py:139-142) or its uint8 view
         ((adv+1.0)*127.5).astype(uint8) (utils/stats_and_plot/stats_plots.py:57)."""
@@ -263,6 +298,9 @@ class FlickerAttack:
         if torch.cuda.is_available():
             torch.cuda.synchronize(self.device)
         self.eng.close()
+        if self._eval is not None:
+            self._eval.close()
+            self._eval = None
 
 
 class SparseAttack:

@@ -127,7 +127,25 @@ struct fav_handle {
   uint16_t* stem_gw = nullptr;    // stem weights as the [KT*160][64] B operand of the gradient collapse
   StemGradLaunch stem_gd;         // tensor-core gradient collapse through the stem
   bool stem_grad_dense = false;   // FAV_STEM_GRAD_DENSE=1 (tests): dense stem data gradient + masked reduce instead
+
+  // forward-only evaluation handle (fav_create_eval): the plan runs 2 * Bu clips — rows [0, Bu) the clean clips, rows
+  // [Bu, 2 Bu) the perturbed ones — through one set of packed forward weights; no gradient buffers, pool codes,
+  // data-gradient weights or stem-gradient plans exist.  The two halves see different stem bias tables (delta = 0 /
+  // delta), so the stem runs as two half-batch launches.
+  bool eval = false;
+  int Bu = 0;                       // clips per validation batch (h->B == 2 * Bu)
+  StemLaunch stem_fwd2;             // stem of the perturbed half
+  float* stem_bias_tab2 = nullptr;  // its delta bias table
 };
+
+// an evaluation handle (fav_create_eval) owns no gradient state: the training entry points refuse it
+#define FAV_NOT_EVAL(h, what)                                                                        \
+  do {                                                                                               \
+    if ((h)->eval) {                                                                                 \
+      set_error("%s: this is a forward-only evaluation handle (fav_create_eval); use fav_eval_batch", what); \
+      return FAV_ERR_STATE;                                                                          \
+    }                                                                                                \
+  } while (0)
 
 namespace {
 
@@ -150,8 +168,10 @@ int add_buf(fav_handle* h, const std::string& name, int T, int H, int W, int C, 
   b.cs = round_up(C, 16);
   const size_t n = static_cast<size_t>(b.npos(h->B)) * b.cs;
   if (dev_alloc(h, &b.p, n) != FAV_OK) return -1;
-  if (dev_alloc(h, &b.g, n) != FAV_OK) return -1;
-  if (with_idx && dev_alloc(h, &b.idx, n) != FAV_OK) return -1;
+  if (!h->eval) {   // a forward-only plan keeps neither gradients nor pool codes
+    if (dev_alloc(h, &b.g, n) != FAV_OK) return -1;
+    if (with_idx && dev_alloc(h, &b.idx, n) != FAV_OK) return -1;
+  }
   h->bufs.push_back(b);
   return static_cast<int>(h->bufs.size()) - 1;
 }
@@ -245,7 +265,7 @@ int plan_conv(fav_handle* h, ConvOp& c) {
     c.fwd.flops = 2.0 * static_cast<double>(h->B) * bi.T * bi.H * bi.W * taps * c.cin_real * c.cout_real;
   }
   // ---- backward data: A = grad of out slice, N = cin_k ----
-  {
+  if (!h->eval) {
     const int cblocks = ceil_div(c.cout_pad, 64);
     c.w_dg_elems = static_cast<size_t>(c.cin_k) * taps * cblocks * 64;
     FAV_TRY(dev_alloc(h, &c.w_dg, c.w_dg_elems));
@@ -307,6 +327,8 @@ int plan_block_fused(fav_handle* h, Block& b) {
     e.seg_out[2] = as16(t2.p); e.seg_cs[2] = t2.cs; e.seg_coff[2] = 0;
     b.fwd.flops = c0.fwd.flops + c1.fwd.flops + c2.fwd.flops;
   }
+  b.fused = true;
+  if (h->eval) return FAV_OK;
   // ---- backward data: K = [g(out)[:, :c0] | g(t1) | g(t2)], N = cin ----
   const int nb0 = ceil_div(c0.cout_pad, 64), nb1 = ceil_div(c1.cout_pad, 64), nb2 = ceil_div(c2.cout_pad, 64);
   b.wd_elems = static_cast<size_t>(cin_k) * (nb0 + nb1 + nb2) * 64;
@@ -352,6 +374,27 @@ int run_dgrad(fav_handle* h, int conv_id, bool mask_with_input, bool accumulate,
 
 int i3d_plan_dense_stem(fav_handle* h);   // below (needs plan_dgrad_classes)
 
+// Stem launch plan(s) over the padded RGBX operand.  A training handle runs the whole batch in one launch; an evaluation
+// handle runs the clean half and the perturbed half as two launches with their own delta bias tables.
+int plan_stem(fav_handle* h, int out_buf, int C1, int KT, int st, int pt, int ph, double flops_per_pos) {
+  const Buf& bo = h->bufs[out_buf];
+  const int nb = h->eval ? h->Bu : h->B;
+  const size_t tab = static_cast<size_t>(h->To) * 16 * C1;
+  if (h->eval) FAV_TRY(dev_alloc(h, &h->stem_bias_tab2, tab));
+  for (int half = 0; half < (h->eval ? 2 : 1); ++half) {
+    StemLaunch& L = half ? h->stem_fwd2 : h->stem_fwd;
+    const __half* xin = h->xpad + static_cast<size_t>(half) * nb * h->T * h->H * h->Wp * 4;
+    FAV_TRY(stem_plan(&L, h->device, xin, nb, h->T, h->H, h->Wp, h->stem_w, C1, h->To, h->Ho, h->Wo, KT, 7, st, pt, ph));
+    ConvEpilogue& e = L.e;
+    e.out = as16(bo.p + static_cast<size_t>(half) * bo.npos(nb) * bo.cs); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0;
+    e.cout_store = C1;
+    e.bias = half ? h->stem_bias_tab2 : h->stem_bias_tab; e.bias_ld = C1; e.bias_stem = 1; e.relu = 1;
+    e.mask = nullptr; e.addend = nullptr;
+    L.flops = 2.0 * static_cast<double>(nb) * h->To * h->Ho * h->Wo * flops_per_pos;
+  }
+  return FAV_OK;
+}
+
 int build_i3d(fav_handle* h) {
   const int B = h->B, T = h->T, H = h->H, W = h->W;
   FAV_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && W % 16 == 0, "I3D engine needs even H and W %% 16 == 0 (got %dx%d)", H, W);
@@ -370,16 +413,7 @@ int build_i3d(fav_handle* h) {
 
   h->y1 = add_buf(h, "Conv3d_1a_7x7", h->To, h->Ho, h->Wo, 64, false);
   if (h->y1 < 0) return FAV_ERR_CUDA;
-  FAV_TRY(stem_plan(&h->stem_fwd, h->device, h->xpad, B, T, H, h->Wp, h->stem_w, 64, h->To, h->Ho, h->Wo, 7, 7, 2,
-                    h->pt, h->ph));
-  {
-    ConvEpilogue& e = h->stem_fwd.e;
-    const Buf& bo = h->bufs[h->y1];
-    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = 64;
-    e.bias = h->stem_bias_tab; e.bias_ld = 64; e.bias_stem = 1; e.relu = 1;
-    e.mask = nullptr; e.addend = nullptr;
-    h->stem_fwd.flops = 2.0 * static_cast<double>(B) * h->To * h->Ho * h->Wo * 343.0 * 3.0 * 64.0;
-  }
+  FAV_TRY(plan_stem(h, h->y1, 64, 7, 2, h->pt, h->ph, 343.0 * 3.0 * 64.0));
   // ---- MaxPool3d_2a_3x3 [1,3,3]/[1,2,2] (i3d.py:173-175) ----
   const Buf y1 = h->bufs[h->y1];
   int p2a = add_buf(h, "MaxPool3d_2a_3x3", y1.T, same_out(y1.H, 2), same_out(y1.W, 2), 64, true);
@@ -509,13 +543,14 @@ namespace {
 // (stem_grad.cu); FAV_STEM_GRAD_DENSE=1 routes it through this path + the masked reduce as an independent check.
 int i3d_plan_dense_stem(fav_handle* h) {
   ResNet& rn = h->rn;
+  h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
+  for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
+  if (h->eval) return FAV_OK;
   FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(h->B) * h->T * h->H * h->W * 16));
   const Buf& y1 = h->bufs[h->y1];
   FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, y1.g, y1.cs, 64, y1.T, y1.H, y1.W, rn.dx, 16, 16, h->T, h->H, h->W, 7, 7, 7, 2,
                              2, 2, h->pt, h->ph, h->pw, 3.0, 64.0));
   FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(h->B) * h->T * stem_dx_reduce_chunks(h->H) * 3));
-  h->nrm.lo = -1.0f; h->nrm.hi = 1.0f;
-  for (int c = 0; c < 3; ++c) { h->nrm.mean[c] = 0.0f; h->nrm.std[c] = 1.0f; }
   FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(h->B, h->T, h->H, h->W)));
   FAV_TRY(dev_alloc(h, &h->stem_gw, static_cast<size_t>(7) * 160 * 64));
   FAV_TRY(stem_grad_plan(&h->stem_gd, h->device, y1.g, y1.cs, h->stem_gw, h->pass_bits, h->B, h->T, h->H, h->W, h->To, h->Ho,
@@ -528,7 +563,7 @@ int i3d_plan_dense_stem(fav_handle* h) {
 // =============================================================================================
 // C-ABI
 // =============================================================================================
-extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc) {
+static int create_impl(fav_handle** out, int device, const fav_net_desc* desc, bool eval) {
   if (!out || !desc) {
     set_error("fav_create: null argument");
     return FAV_ERR_ARG;
@@ -554,6 +589,11 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
   h->device = device;
   h->d = *desc;
   h->B = desc->batch; h->T = desc->frames; h->H = desc->height; h->W = desc->width; h->K = desc->num_classes;
+  if (eval) {   // clean | perturbed halves of every validation batch in one pass
+    h->eval = true;
+    h->Bu = desc->batch;
+    h->B = 2 * desc->batch;
+  }
   int st = desc->arch == FAV_NET_I3D ? build_i3d(h.get()) : build_resnet(h.get());
   if (st != FAV_OK) {
     for (void* p : h->allocs) cudaFree(p);
@@ -562,7 +602,7 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
   {
     const char* pe = getenv("FAV_PDL");
     // I3D: -2.6 % for one 90-frame clip (small launches, prologues matter), +1 % for 8 x 64 frames
-    h->pdl = pe ? atoi(pe) != 0 : (desc->arch != FAV_NET_I3D || desc->batch * desc->frames <= 192);
+    h->pdl = pe ? atoi(pe) != 0 : (desc->arch != FAV_NET_I3D || h->B * desc->frames <= 192);
   }
   {
     const char* ev = getenv("FAV_BRANCH_STREAMS");
@@ -576,6 +616,13 @@ extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc
   }
   *out = h.release();
   return FAV_OK;
+}
+
+extern "C" int fav_create(fav_handle** out, int device, const fav_net_desc* desc) {
+  return create_impl(out, device, desc, false);
+}
+extern "C" int fav_create_eval(fav_handle** out, int device, const fav_net_desc* desc) {
+  return create_impl(out, device, desc, true);
 }
 
 extern "C" int fav_destroy(fav_handle* h) {
@@ -623,9 +670,11 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
     pk.resize(c.w_fwd_elems);
     pack_weights_fwd(pk.data(), w->data, scale.data(), taps, c.cin_real, c.cin_k, c.cout_real, c.cout_pad);
     FAV_CUDA(cudaMemcpy(c.w_fwd, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
-    pk.resize(c.w_dg_elems);
-    pack_weights_dgrad(pk.data(), w->data, scale.data(), taps, c.cin_real, c.cout_real, c.cout_pad, c.cin_k);
-    FAV_CUDA(cudaMemcpy(c.w_dg, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    if (c.w_dg) {
+      pk.resize(c.w_dg_elems);
+      pack_weights_dgrad(pk.data(), w->data, scale.data(), taps, c.cin_real, c.cout_real, c.cout_pad, c.cin_k);
+      FAV_CUDA(cudaMemcpy(c.w_dg, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    }
     std::vector<float> bpad(c.cout_pad, 0.0f);
     for (int i = 0; i < c.cout_real; ++i) bpad[i] = bias[i];
     FAV_CUDA(cudaMemcpy(c.bias, bpad.data(), bpad.size() * 4, cudaMemcpyHostToDevice));
@@ -639,7 +688,7 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
     const size_t Kf = static_cast<size_t>(cbl) * 64;
     std::vector<uint16_t> wf(b.wf_elems, 0), wd(b.wd_elems, 0);
     std::vector<float> bf(b.n_tot, 0.0f);
-    const size_t Kd = b.wd_elems / cin_k;
+    const size_t Kd = b.wd ? b.wd_elems / cin_k : 0;
     int n0 = 0, kb0 = 0;
     for (int i = 0; i < 3; ++i) {
       const ConvOp& c = h->convs[ids[i]];
@@ -649,14 +698,14 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
         for (int co = 0; co < c.cout_real; ++co) {
           const float v = w->data[static_cast<size_t>(ci) * c.cout_real + co] * scale[co];
           wf[static_cast<size_t>(n0 + co) * Kf + (ci / 64) * 64 + ci % 64] = f32_to_f16_bits(v);
-          wd[static_cast<size_t>(ci) * Kd + (static_cast<size_t>(kb0) + co / 64) * 64 + co % 64] = f32_to_bf16_bits(v);
+          if (b.wd) wd[static_cast<size_t>(ci) * Kd + (static_cast<size_t>(kb0) + co / 64) * 64 + co % 64] = f32_to_bf16_bits(v);
         }
       for (int co = 0; co < c.cout_real; ++co) bf[n0 + co] = bias[co];
       n0 += c.cout_pad;
       kb0 += ceil_div(c.cout_pad, 64);
     }
     FAV_CUDA(cudaMemcpy(b.wf, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
-    FAV_CUDA(cudaMemcpy(b.wd, wd.data(), wd.size() * 2, cudaMemcpyHostToDevice));
+    if (b.wd) FAV_CUDA(cudaMemcpy(b.wd, wd.data(), wd.size() * 2, cudaMemcpyHostToDevice));
     FAV_CUDA(cudaMemcpy(b.bias, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice));
   }
   // ---- stem ----
@@ -696,7 +745,7 @@ extern "C" int fav_load_weights(fav_handle* h, const fav_tensor* tensors, int n)
         FAV_CUDA(cudaMemcpy(d.w, dpk.data(), dpk.size() * 2, cudaMemcpyHostToDevice));
       }
     }
-    {
+    if (h->stem_gw) {
       std::vector<uint16_t> gw(static_cast<size_t>(7) * 160 * 64);
       stem_grad_pack_weights(gw.data(), wq.data(), 7, 64);
       FAV_CUDA(cudaMemcpy(h->stem_gw, gw.data(), gw.size() * 2, cudaMemcpyHostToDevice));
@@ -745,6 +794,7 @@ extern "C" int fav_apply_flicker(fav_handle* h, const void* clip, int in_dtype, 
                                  float adv_flag, float delta_clip, uint8_t* adv_u8, float* adv_f32,
                                  void* stream) {
   FAV_CHECK_ARG(h && clip && delta, "fav_apply_flicker: null argument");
+  FAV_NOT_EVAL(h, "fav_apply_flicker");
   FAV_CUDA(cudaSetDevice(h->device));   // a handle is bound to its device, whatever the caller's current device is
   g_pdl_on = h->pdl;
   FAV_CHECK_ARG(in_dtype == FAV_U8 || in_dtype == FAV_F32, "fav_apply_flicker: bad dtype");
@@ -825,6 +875,7 @@ extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
     return FAV_OK;
   }
   FAV_TRY(stem_launch(h->stem_fwd, s));
+  if (h->eval) FAV_TRY(stem_launch(h->stem_fwd2, s));
   FAV_TRY(run_pool_fwd(h, h->pool2a, s));
   FAV_TRY(conv_launch(h->convs[h->conv2b].fwd, s));
   FAV_TRY(conv_launch(h->convs[h->conv2c].fwd, s));
@@ -847,9 +898,71 @@ extern "C" int fav_forward(fav_handle* h, float* logits, void* stream) {
 extern "C" int fav_loss(fav_handle* h, const int64_t* labels, const fav_loss_params* p, float* probs,
                         float* scalars, void* stream) {
   FAV_CHECK_ARG(h && labels && p && scalars, "fav_loss: null argument");
+  FAV_NOT_EVAL(h, "fav_loss");
   FAV_CUDA(cudaSetDevice(h->device));
   return launch_loss(h->logits, labels, *p, h->B, h->K, probs, h->dlogits, scalars,
                      static_cast<cudaStream_t>(stream));
+}
+
+// ---- fused evaluation pass -------------------------------------------------------------
+// kinetics_i3d.evaluate (utils/kinetics_i3d_utils.py:217-250) and the torch stack's validation phase (model.py:697-713)
+// run every validation batch through the network twice (adv_flag 0 and 1); here both versions of the batch go through
+// one forward-only pass and the miss / valid counters are accumulated on the device.
+extern "C" int fav_eval_batch(fav_handle* h, const void* clip_clean, const void* clip_adv, int in_dtype, const float* delta,
+                              float delta_clip, const int64_t* labels, int n_clips, int targeted, int64_t target_class,
+                              int exclude_misclassify, const fav_loss_params* loss, int64_t* counts, float* probs,
+                              float* scalars, void* stream) {
+  FAV_CHECK_ARG(h && clip_clean && delta && labels && counts, "fav_eval_batch: null argument");
+  if (!h->eval) {
+    set_error("fav_eval_batch: needs a handle from fav_create_eval");
+    return FAV_ERR_STATE;
+  }
+  if (!h->weights_loaded) {
+    set_error("fav_eval_batch: weights not loaded");
+    return FAV_ERR_STATE;
+  }
+  FAV_CHECK_ARG(in_dtype == FAV_U8 || in_dtype == FAV_F32, "fav_eval_batch: bad dtype");
+  FAV_CHECK_ARG(n_clips >= 0 && n_clips <= h->Bu, "fav_eval_batch: n_clips %d outside [0, %d]", n_clips, h->Bu);
+  FAV_CHECK_ARG((loss == nullptr) == (scalars == nullptr), "fav_eval_batch: loss and scalars go together");
+  FAV_CUDA(cudaSetDevice(h->device));
+  g_pdl_on = h->pdl;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!clip_adv) clip_adv = clip_clean;
+  const int Bu = h->Bu;
+  __half* x_adv = h->xpad + static_cast<size_t>(Bu) * h->T * h->H * h->Wp * 4;
+  if (h->d.arch != FAV_NET_I3D) {
+    FAV_CHECK_ARG(in_dtype == FAV_U8, "torch-stack evaluation takes uint8 clips");
+    fav_norm_params clean = h->nrm;   // Perturbation.forward returns x untouched when adversarial is False (model.py:82-83)
+    clean.lo = -INFINITY; clean.hi = INFINITY;
+    FAV_TRY(launch_apply_torch(static_cast<const uint8_t*>(clip_clean), delta, 0.0f, delta_clip, clean, h->xpad, h->Wp, h->pw,
+                               nullptr, nullptr, Bu, h->T, h->H, h->W, s));
+    FAV_TRY(launch_apply_torch(static_cast<const uint8_t*>(clip_adv), delta, 1.0f, delta_clip, h->nrm, x_adv, h->Wp, h->pw,
+                               nullptr, nullptr, Bu, h->T, h->H, h->W, s));
+    const int C1 = round_up(h->rn.stem_C, 16);
+    float cst[3], ds[3];
+    for (int c = 0; c < 3; ++c) {
+      cst[c] = (128.0f / 255.0f - h->nrm.mean[c]) / h->nrm.std[c];
+      ds[c] = 1.0f / h->nrm.std[c];
+    }
+    FAV_TRY(launch_stem_bias_ex(delta, 0.0f, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T, h->To, h->pt,
+                                h->rn.stem_KT, 1, C1, cst, ds, s));
+    FAV_TRY(launch_stem_bias_ex(delta, 1.0f, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab2, h->T, h->To, h->pt,
+                                h->rn.stem_KT, 1, C1, cst, ds, s));
+  } else {
+    FAV_TRY(launch_apply(clip_clean, in_dtype, delta, 0.0f, delta_clip, h->xpad, h->Wp, h->pw, nullptr, nullptr, nullptr, Bu,
+                         h->T, h->H, h->W, s));
+    FAV_TRY(launch_apply(clip_adv, in_dtype, delta, 1.0f, delta_clip, x_adv, h->Wp, h->pw, nullptr, nullptr, nullptr, Bu,
+                         h->T, h->H, h->W, s));
+    FAV_TRY(launch_stem_bias(delta, 0.0f, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab, h->T, h->To, h->pt, s));
+    FAV_TRY(launch_stem_bias(delta, 1.0f, delta_clip, h->stem_wc, h->stem_bnbias, h->stem_bias_tab2, h->T, h->To, h->pt, s));
+  }
+  FAV_TRY(fav_forward(h, nullptr, stream));
+  FAV_TRY(launch_eval_counts(h->logits, labels, Bu, n_clips, h->K, targeted, target_class, exclude_misclassify, counts, probs,
+                             s));
+  // the validation phase also logs the adversarial loss of the perturbed rows (model.py:706)
+  if (loss)
+    FAV_TRY(launch_loss(h->logits + static_cast<size_t>(Bu) * h->K, labels, *loss, Bu, h->K, nullptr, h->dlogits, scalars, s));
+  return FAV_OK;
 }
 
 static int run_block_bwd(fav_handle* h, const Block& b, cudaStream_t s) {
@@ -891,6 +1004,7 @@ static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s);
 
 extern "C" int fav_backward_delta(fav_handle* h, float* grad, void* stream) {
   FAV_CHECK_ARG(h && grad, "fav_backward_delta: null argument");
+  FAV_NOT_EVAL(h, "fav_backward_delta");
   FAV_CUDA(cudaSetDevice(h->device));
   g_pdl_on = h->pdl;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -925,6 +1039,7 @@ static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s) {
 // ---- sparse per-pixel attack (kinetics_i3d_L12, utils/kinetics_i3d_utils.py:308-521; torch attack_type "L12") ----
 extern "C" int fav_pixels_enable(fav_handle* h) {
   FAV_CHECK_ARG(h, "fav_pixels_enable: null handle");
+  FAV_NOT_EVAL(h, "fav_pixels_enable");
   if (h->pixels_enabled) return FAV_OK;
   if (!h->weights_loaded) {
     set_error("fav_pixels_enable: weights not loaded");
@@ -1029,6 +1144,10 @@ extern "C" int64_t fav_debug_read(fav_handle* h, const char* name, float* out, i
   }
   for (const Buf& b : h->bufs) {
     if (b.name != n) continue;
+    if (grad && !b.g) {
+      set_error("fav_debug_read: '%s' has no gradient buffer (evaluation handle)", name);
+      return FAV_ERR_STATE;
+    }
     const long long npos = b.npos(h->B);
     const int64_t count = npos * b.C;
     if (count > capacity) {

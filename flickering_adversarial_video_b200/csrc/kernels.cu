@@ -539,7 +539,7 @@ int launch_maxpool_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom&
   ProfScope ps(PK_POOL_FWD, s, 0.0, static_cast<double>(g.B) * g.C * (2.0 * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool: C=%d must be a multiple of 8", g.C);
   FAV_CHECK_ARG(g.kt * g.kh * g.kw <= 255, "maxpool: window too large");
-  if (idx && pool3s1_applicable(g)) return launch_pool3s1_fwd(x, y, idx, g, s);
+  if (pool3s1_applicable(g)) return launch_pool3s1_fwd(x, y, idx, g, s);   // idx == nullptr: forward-only plan, no codes
   dim3 grid(g.B * g.To * g.Ho, ceil_div(g.Wo * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
   switch (key) {
@@ -1006,6 +1006,75 @@ int launch_loss(const float* logits, const int64_t* labels, const fav_loss_param
   FAV_CHECK_ARG(smem <= 200 * 1024, "loss: K=%d / B=%d need %zu bytes of shared memory", K, B, smem);
   if (smem > 48 * 1024) FAV_CUDA(cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   loss_kernel<<<1, kLossWarps * 32, smem, s>>>(logits, labels, p, B, K, probs, dlogits, scalars);
+  FAV_COUNT_LAUNCH();
+  FAV_CUDA(cudaGetLastError());
+  return FAV_OK;
+}
+
+// =============================================================================================
+// Fused evaluation pass: the fooling-ratio counts of one validation batch from the logits of
+// its clean rows [0, Bu) and perturbed rows [Bu, 2 Bu).
+//   kinetics_i3d.evaluate (utils/kinetics_i3d_utils.py:226-243): miss_cond = argmax(prob_adv) != label (targeted: ==
+//   target class); exclude_misclassify: valid = argmax(prob_clean) == label, miss += (miss_cond & valid).sum(), total +=
+//   valid.sum(); otherwise miss += miss_cond.sum(), total += batch.  Adversarial_metrics.accuracy_for_eval
+//   (model.py:293-323, untargeted) counts the same two numbers.  argmax keeps the first maximum, like numpy / topk.
+// One warp per clip; counts[0] += miss, counts[1] += total (int64, atomics: the counters run over all batches).
+// =============================================================================================
+__device__ __forceinline__ int warp_argmax_first(const float* __restrict__ row, int K, int lane, float* vmax) {
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < K; k += 32) {
+    const float v = row[k];
+    if (v > best || bi == 0x7fffffff) { best = v; bi = k; }   // strict >: the earlier index keeps ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  *vmax = best;
+  return bi;
+}
+
+__global__ void __launch_bounds__(256)
+eval_count_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int Bu, int n, int K,
+                  int targeted, long long target, int exclude, unsigned long long* __restrict__ counts,
+                  float* __restrict__ probs) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= Bu) return;
+  int am[2];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float* row = logits + static_cast<size_t>(half * Bu + b) * K;
+    float mx;
+    am[half] = warp_argmax_first(row, K, lane, &mx);
+    if (probs) {   // softmax of both halves (the reference fetches `softmax` / `scores_no_adv` next to the counts)
+      float sum = 0.0f;
+      for (int k = lane; k < K; k += 32) sum += __expf(row[k] - mx);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / sum;
+      float* prow = probs + static_cast<size_t>(half * Bu + b) * K;
+      for (int k = lane; k < K; k += 32) prow[k] = __expf(row[k] - mx) * inv;
+    }
+  }
+  if (lane == 0 && b < n) {
+    const long long lab = labels[b];
+    const bool valid = !exclude || am[0] == lab;
+    const bool miss = targeted ? am[1] == target : am[1] != lab;
+    if (valid) atomicAdd(counts + 1, 1ull);
+    if (valid && miss) atomicAdd(counts + 0, 1ull);
+  }
+}
+
+int launch_eval_counts(const float* logits, const int64_t* labels, int Bu, int n, int K, int targeted, long long target,
+                       int exclude, int64_t* counts, float* probs, cudaStream_t s) {
+  ProfScope ps(PK_HEAD_LOSS, s);
+  FAV_CHECK_ARG(n >= 0 && n <= Bu, "eval counts: n_clips %d outside [0, %d]", n, Bu);
+  eval_count_kernel<<<ceil_div(Bu, 8), 256, 0, s>>>(logits, labels, Bu, n, K, targeted, target, exclude,
+                                                    reinterpret_cast<unsigned long long*>(counts), probs);
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -78,6 +78,10 @@ int launch_head_bwd(const float* dlogits, const float* wl, int K, const __half* 
 int launch_loss(const float* logits, const int64_t* labels, const fav_loss_params& p, int B, int K,
                 float* probs, float* dlogits, float* scalars, cudaStream_t s);
 
+// fooling-ratio counts of one validation batch (clean rows [0,Bu), perturbed rows [Bu,2Bu) of `logits`)
+int launch_eval_counts(const float* logits, const int64_t* labels, int Bu, int n, int K, int targeted, long long target,
+                       int exclude, int64_t* counts, float* probs, cudaStream_t s);
+
 int launch_delta_update(float* delta, const float* grad, float* m, float* v, int64_t* step,
                         const fav_reg_params& reg, const fav_adam_params& adam, float adv_flag,
                         float* scalars, int T, cudaStream_t s);

@@ -128,10 +128,12 @@ pool3s1_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y, uint8_t
       first_max(best, c3, make_uint4(p1[0], p1[1], p1[2], p1[3]), kCT1);
       first_max(best, c3, make_uint4(m2[0], m2[1], m2[2], m2[3]), kCT2);
       *reinterpret_cast<uint4*>(yb + to * plane) = make_uint4(best[0], best[1], best[2], best[3]);
-      uint2 o;
-      o.x = pcode.x | __byte_perm(c3[0], c3[1], 0x6420);
-      o.y = pcode.y | __byte_perm(c3[2], c3[3], 0x6420);
-      *reinterpret_cast<uint2*>(ib + to * plane) = o;
+      if (idx) {   // nullptr: forward-only (evaluation) plan, no backward will read the stage codes
+        uint2 o;
+        o.x = pcode.x | __byte_perm(c3[0], c3[1], 0x6420);
+        o.y = pcode.y | __byte_perm(c3[2], c3[3], 0x6420);
+        *reinterpret_cast<uint2*>(ib + to * plane) = o;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { p2[j] = p1[j]; p1[j] = m2[j]; }
@@ -417,7 +419,7 @@ bool pool3s1_applicable(const PoolGeom& g) {
 
 int launch_pool3s1_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
   const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads, 1024);
-  FAV_CHECK_ARG(t.cgn > 0 && idx, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
+  FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
   const size_t smem = (static_cast<size_t>(t.R + 2 * t.halo) * (g.W + 2) + static_cast<size_t>(t.R + 2) * g.W) * t.cgn * 16;
   static bool attr = false;

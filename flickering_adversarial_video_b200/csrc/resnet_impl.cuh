@@ -136,6 +136,7 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
   }
   // ---- backward data ----
   c.halo_dg = halo;
+  if (h->eval) return FAV_OK;
   if (halo) {
     DgradClass d;
     d.class0 = true;
@@ -179,16 +180,7 @@ int build_resnet(fav_handle* h) {
   FAV_TRY(dev_alloc(h, &h->stem_bias_tab, static_cast<size_t>(h->To) * 16 * C1));
   rn.stem_out = add_buf(h, "stem.conv", h->To, h->Ho, h->Wo, rn.stem_C, false);
   if (rn.stem_out < 0) return FAV_ERR_CUDA;
-  FAV_TRY(stem_plan(&h->stem_fwd, h->device, h->xpad, B, T, H, h->Wp, h->stem_w, C1, h->To, h->Ho, h->Wo, rn.stem_KT, 7, 1,
-                    rn.stem_pt, 3));
-  {
-    ConvEpilogue& e = h->stem_fwd.e;
-    const Buf& bo = h->bufs[rn.stem_out];
-    e.out = as16(bo.p); e.out_f16 = 1; e.out_cs = bo.cs; e.out_coff = 0; e.cout_store = C1;
-    e.bias = h->stem_bias_tab; e.bias_ld = C1; e.bias_stem = 1; e.relu = 1;
-    e.mask = nullptr; e.addend = nullptr;
-    h->stem_fwd.flops = 2.0 * static_cast<double>(B) * h->To * h->Ho * h->Wo * rn.stem_KT * 49.0 * 3.0 * rn.stem_C;
-  }
+  FAV_TRY(plan_stem(h, rn.stem_out, C1, rn.stem_KT, 1, rn.stem_pt, 3, rn.stem_KT * 49.0 * 3.0 * rn.stem_C));
   int x = rn.stem_out;
   if (r21) {   // R2Plus1dStem: Conv3d(45, 64, (3,1,1), padding (1,0,0)) + BN + ReLU
     const int id = rn_add_conv(h, "stem.3", "stem.4", 3, 1, 1, 1, 1, 1, 1, 0, 0, x, 64, true, "stem");
@@ -256,13 +248,13 @@ int build_resnet(fav_handle* h) {
   h->final_buf = x;
   for (auto& c : rn.convs) FAV_TRY(rn_plan_conv(h, c));
   // ---- dense stem data gradient: dX [B,T,H,W,16] ----
-  FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(B) * T * H * W * 16));
-  {
+  if (!h->eval) {
+    FAV_TRY(dev_alloc(h, &rn.dx, static_cast<size_t>(B) * T * H * W * 16));
     const Buf& bs = h->bufs[rn.stem_out];
     FAV_TRY(plan_dgrad_classes(h, &rn.stem_dg, bs.g, bs.cs, C1, bs.T, bs.H, bs.W, rn.dx, 16, 16, T, H, W, rn.stem_KT, 7, 7,
                                1, 2, 2, rn.stem_pt, 3, 3, 3.0, rn.stem_C));
+    FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(B) * T * stem_dx_reduce_chunks(H) * 3));
   }
-  FAV_TRY(dev_alloc(h, &rn.partial, static_cast<size_t>(B) * T * stem_dx_reduce_chunks(H) * 3));
   // torch-stack defaults (dataset.py:28-29; Perturbation scalar bounds model.py:72-75)
   const float mean[3] = {0.43216f, 0.394666f, 0.37645f}, sd[3] = {0.22803f, 0.22145f, 0.216989f};
   float lo = -1e30f, hi = 1e30f;
@@ -273,7 +265,7 @@ int build_resnet(fav_handle* h) {
   }
   h->nrm.lo = lo; h->nrm.hi = hi;
   // ---- flicker gradient through the stem without dX (stem_grad.cu); delta enters the network as delta / std_c ----
-  {
+  if (!h->eval) {
     const Buf& bs = h->bufs[rn.stem_out];
     const float sc[3] = {1.0f / h->nrm.std[0], 1.0f / h->nrm.std[1], 1.0f / h->nrm.std[2]};
     FAV_TRY(dev_alloc(h, &h->pass_bits, stem_grad_bitmap_words(B, T, H, W)));
@@ -407,7 +399,7 @@ int load_weights_resnet(fav_handle* h, const NamedTensors& nt) {
     std::vector<float> bpad(C1, 0.0f);
     for (int i = 0; i < C; ++i) bpad[i] = bias[i];
     FAV_CUDA(cudaMemcpy(h->stem_bnbias, bpad.data(), bpad.size() * 4, cudaMemcpyHostToDevice));
-    {
+    if (h->stem_gw) {
       std::vector<uint16_t> gw(static_cast<size_t>(KT) * 160 * 64);
       stem_grad_pack_weights(gw.data(), wt.data(), KT, C);
       FAV_CUDA(cudaMemcpy(h->stem_gw, gw.data(), gw.size() * 2, cudaMemcpyHostToDevice));
@@ -442,6 +434,7 @@ int load_weights_resnet(fav_handle* h, const NamedTensors& nt) {
 int resnet_forward(fav_handle* h, cudaStream_t s) {
   ResNet& rn = h->rn;
   FAV_TRY(stem_launch(h->stem_fwd, s));
+  if (h->eval) FAV_TRY(stem_launch(h->stem_fwd2, s));
   for (int id : rn.pre) FAV_TRY(conv_launch(rn.convs[id].fwd, s));
   const bool par = h->branch_streams && !g_prof_on;
   for (const RBlock& b : rn.blocks) {

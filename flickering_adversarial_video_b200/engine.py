@@ -12,6 +12,8 @@ from . import _lib as L
 
 
 class FlickerEngine:
+    _EVAL = False   # EvalEngine: forward-only handle (fav_create_eval)
+
     def __init__(self, batch, frames, height=None, width=None, num_classes=400, device=0, arch="i3d"):
         """arch: "i3d" (TF stack, 224x224) or "r3d_18" / "mc3_18" / "r2plus1d_18" (torch stack, 112x112)."""
         if not torch.cuda.is_available():
@@ -28,10 +30,13 @@ class FlickerEngine:
         self.B, self.T, self.H, self.W, self.K = batch, frames, height, width, num_classes
         desc = L.NetDesc(L.ARCHS[arch], batch, frames, height, width, num_classes)
         h = C.c_void_p()
+        create = self.lib.fav_create_eval if self._EVAL else self.lib.fav_create
         with torch.cuda.device(self.device):
-            L.check(self.lib.fav_create(C.byref(h), device, C.byref(desc)), "fav_create")
+            L.check(create(C.byref(h), device, C.byref(desc)), "fav_create_eval" if self._EVAL else "fav_create")
         self.h = h
         self.scalars = torch.zeros(L.S_COUNT, dtype=torch.float32, device=self.device)
+        if self._EVAL:
+            return
         self.logits = torch.zeros((batch, num_classes), dtype=torch.float32, device=self.device)
         self.probs = torch.zeros((batch, num_classes), dtype=torch.float32, device=self.device)
         self.grad = torch.zeros((frames, 3), dtype=torch.float32, device=self.device)
@@ -144,6 +149,50 @@ class FlickerEngine:
             raise L.FavError(f"fav_debug_read({name}): {L.last_error()}")
         assert n == out.numel(), (name, n, out.numel())
         return out
+
+
+class EvalEngine(FlickerEngine):
+    """Forward-only evaluation handle (include/fav.h `fav_create_eval` / `fav_eval_batch`): the
+    clean and the perturbed version of every validation batch run through the network in ONE pass and the fooling-ratio
+    counters stay on the device.  Replaces the two `sess.run` per batch of `kinetics_i3d.evaluate`
+    (utils/kinetics_i3d_utils.py:217-250) and the two `model(...)` calls of the torch stack's validation phase
+    (utils_cv/action_recognition/model.py:697-713).  No gradient buffers: ~40 % of a training handle's memory per clip."""
+    _EVAL = True
+
+    def __init__(self, batch, frames, height=None, width=None, num_classes=400, device=0, arch="i3d"):
+        super().__init__(batch, frames, height, width, num_classes, device, arch)
+        self.counts = torch.zeros(2, dtype=torch.int64, device=self.device)          # [miss, valid], accumulates
+        self.probs = torch.zeros((2 * batch, num_classes), dtype=torch.float32, device=self.device)
+
+    def reset_counts(self):
+        self.counts.zero_()
+
+    def eval_batch(self, clips, delta, labels, clips_adv=None, n_clips=None, delta_clip=0.4, targeted=False,
+                   target_class=0, exclude_misclassify=True, loss=None, want_probs=False, stream=None):
+        """clips [B,T,H,W,3] uint8 (float32 allowed for I3D); clips_adv: the clips the perturbation is added to (None =
+        the same); labels int64 [B]; n_clips: how many clips of a ragged last batch count; loss: None or the keyword
+        dict of `FlickerEngine.loss` (the loss scalars of the perturbed rows land in `self.scalars`).  Asynchronous:
+        `self.counts` += [miss, valid]; with want_probs `self.probs[:B]` / `[B:]` hold the clean / perturbed softmax."""
+        shape = (self.B, self.T, self.H, self.W, 3)
+        for c in (clips, clips_adv):
+            assert c is None or (c.is_cuda and c.is_contiguous() and tuple(c.shape) == shape)
+        assert clips_adv is None or clips_adv.dtype == clips.dtype
+        assert delta.is_cuda and delta.dtype == torch.float32 and delta.numel() == self.T * 3 and delta.is_contiguous()
+        assert labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == self.B
+        dt = L.FAV_U8 if clips.dtype == torch.uint8 else L.FAV_F32
+        assert dt == L.FAV_U8 or clips.dtype == torch.float32
+        lp = None
+        if loss is not None:
+            lp = L.LossParams(int(loss.get("improve_loss", True)), int(loss.get("targeted", False)),
+                              int(loss.get("use_logits", False)), float(loss.get("margin", 0.05)),
+                              float(loss.get("grad_scale", 1.0)), int(loss.get("global_batch", 0)),
+                              int(loss.get("stack", L.FAV_STACK_TF)))
+        L.check(self.lib.fav_eval_batch(
+            self.h, L.ptr(clips), L.ptr(clips_adv), dt, L.ptr(delta), delta_clip, L.ptr(labels),
+            self.B if n_clips is None else int(n_clips), int(targeted), int(target_class or 0), int(exclude_misclassify),
+            None if lp is None else C.byref(lp), L.ptr(self.counts), L.ptr(self.probs) if want_probs else None,
+            L.ptr(self.scalars) if lp is not None else None, L.stream_ptr(stream, self.device)), "fav_eval_batch")
+        return self.counts
 
 
 # ---- op-level wrappers used by the parity tests ---------------------------------------------

@@ -231,26 +231,24 @@ class kinetics_i3d:
                  exclude_misclassify=True):
         """Fooling ratio over a validation iterable of (rgb_sample, sample_label) batches
         (utils/kinetics_i3d_utils.py:217-250).  Returns (miss_rate, total_val_vid)."""
-        miss, total = 0, 0
+        # Fused evaluation pass (SURVEY section 8 row f3): the clean clips and the perturbed (possibly rolled) clips of a
+        # batch go through ONE forward of the evaluation handle, the two counters stay on the device and are read once
+        # after the last batch — the reference runs two sess.run per batch and counts on the host.
+        self._configure()
+        a = self._atk
+        a.eval_counts(reset=True)
         for rgb_sample, sample_label in next_element_val:
             clips = self._to_device_clip(rgb_sample)
+            clips_adv = None
             if cyclic:
-                clips = torch.roll(clips, int(self._rng.randint(0, self.frames)), dims=1).contiguous()
-            sample_label = np.asarray(sample_label).reshape(-1)
-            prob = self._atk.predict(clips, adv_flag=1.0).cpu().numpy()
-            pred = prob.argmax(-1)
-            miss_cond = (pred == target_class_id) if targeted_attack else (pred != sample_label)
-            if exclude_misclassify:
-                prob_clean = self._atk.predict(self._to_device_clip(rgb_sample), adv_flag=0.0).cpu().numpy()
-                valid = prob_clean.argmax(-1) == sample_label
-                miss += int(np.logical_and(miss_cond, valid).sum())
-                total += int(valid.sum())
-            else:
-                miss += int(miss_cond.sum())
-                total += int(miss_cond.shape[0])
+                clips_adv = torch.roll(clips, int(self._rng.randint(0, self.frames)), dims=1).contiguous()
+            lab = torch.as_tensor(np.asarray(sample_label), dtype=torch.int64).reshape(-1).to(self.device)
+            a.eval_batch(clips, lab, clips_adv=clips_adv, targeted=targeted_attack, target_class=target_class_id,
+                         exclude_misclassify=exclude_misclassify)
+        miss, total = a.eval_counts(reset=True)
         # sharded validation: every rank evaluated its shard of the clips; the ratio is taken over all of them
-        if self._atk.world > 1:
-            miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
+        if a.world > 1:
+            miss, total = fdist.sum_counts((miss, total), device=a.device, group=a.pg)
         return (miss / total if total else 0.0), int(total)
 
     def close(self):

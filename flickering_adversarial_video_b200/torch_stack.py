@@ -331,8 +331,24 @@ class VideoLearnerAdversarial:
                 loss_sum = n_seen = 0.0
                 # caller-supplied sharded sources may differ in length per rank: the training pass runs in lockstep
                 it = fdist.lockstep(batches(), atk.world, atk.device, atk.pg) if phase == "train" else batches()
+                # validation (model.py:697-713 runs model([x, False]) and model([x, True]) per batch): the fused
+                # evaluation pass forwards both versions at once and keeps the miss / valid counters on the device
+                fused_valid = phase == "valid" and not lp["targeted_attack"]
+                if fused_valid:
+                    atk.eval_counts(reset=True)
+                    reg_valid = None
                 for clips, labels in it:
                     lab = labels if not lp["targeted_attack"] else torch.full_like(labels, int(target))
+                    if fused_valid:
+                        atk.eval_batch(clips, labels, shift=self._cyclic_shift(), with_loss=True)
+                        if reg_valid is None:          # the perturbation does not change during validation
+                            self._sync_pert(atk)
+                            reg_valid = float(Losses(lp["beta_1"], lp["lambda_"], attack_type=self.attack_type)
+                                              .regularization_loss(self.pert_model.get_perturbation()[0]))
+                        loss = float(atk.evaluator().scalars[L.S_ADV_LOSS]) + lp["lambda_"] * reg_valid
+                        loss_sum += loss * labels.numel()
+                        n_seen += labels.numel()
+                        continue
                     clean = atk.predict(clips, adv_flag=0.0).clone()
                     shift = self._cyclic_shift()
                     if phase == "train":
@@ -358,6 +374,8 @@ class VideoLearnerAdversarial:
                         total += float(out[1])
                     loss_sum += loss * labels.numel()
                     n_seen += labels.numel()
+                if fused_valid:
+                    miss_rate, total = (float(x) for x in atk.eval_counts(reset=True))
                 self._sync_pert(atk)
                 atk.check_replicas()          # sharded run: the replicated perturbation must be identical on all ranks
                 pert = self.pert_model.get_perturbation()[0].detach().cpu().numpy()

@@ -189,6 +189,31 @@ int fav_backward_pixels(fav_handle* h, float* grad_px, void* stream);
 int fav_pixels_update(fav_handle* h, float* delta_px, const float* grad_px, float* m, float* v, int64_t* step,
                       float reg_weight, float delta_clip, const fav_adam_params* adam, float* scalars, void* stream);
 
+/* ---- fused evaluation pass ---------------------------------------------
+ * kinetics_i3d.evaluate (utils/kinetics_i3d_utils.py:217-250: two sess.run per validation batch, adv_flag 1 and 0), the
+ * EVAL branch of model_fn (i3d_adversarial_main_universal.py:139-161) and the torch stack's validation phase
+ * (utils_cv/action_recognition/model.py:697-713 + Adversarial_metrics.accuracy_for_eval :293-323) forward the clean and
+ * the perturbed version of every validation batch and count
+ *     valid = argmax(clean) == label          (all clips when exclude_misclassify == 0)
+ *     miss  = valid && (targeted ? argmax(adv) == target_class : argmax(adv) != label)
+ * An evaluation handle is forward-only: desc->batch = Bu clips per validation batch; its plan runs 2*Bu clips (clean
+ * rows [0,Bu), perturbed rows [Bu,2Bu)) through one set of packed forward weights in ONE pass and owns no gradient
+ * buffers, pool codes or data-gradient weights (about 40 % of a training handle's arena per resident clip).  The training
+ * entry points (fav_apply_flicker, fav_loss, fav_backward_*, fav_pixels_*) return FAV_ERR_STATE on it. */
+int fav_create_eval(fav_handle** out, int device, const fav_net_desc* desc);
+/* One validation batch.
+ *   clip_clean  DEVICE [Bu,T,H,W,3] u8 (or f32 for I3D);  clip_adv: the clips the perturbation is added to, or NULL for
+ *               the same ones (the reference's cyclic evaluation rolls only the perturbed input, kinetics_i3d_utils.py:228)
+ *   delta       DEVICE [T,3] f32;  labels DEVICE [Bu] i64;  n_clips <= Bu: clips of a ragged last batch that count
+ *   loss/scalars: both NULL, or the adversarial-loss selection and a DEVICE [FAV_S_COUNT] block that receives the loss
+ *               scalars of the perturbed rows (what the validation phase logs, model.py:706); labels must hold Bu entries
+ *   counts      DEVICE int64[2]: counts[0] += miss, counts[1] += valid (accumulates over batches; zero it once)
+ *   probs       DEVICE [2*Bu,num_classes] f32 or NULL: softmax of the clean rows, then of the perturbed rows */
+int fav_eval_batch(fav_handle* h, const void* clip_clean, const void* clip_adv, int in_dtype, const float* delta,
+                   float delta_clip, const int64_t* labels, int n_clips, int targeted, int64_t target_class,
+                   int exclude_misclassify, const fav_loss_params* loss, int64_t* counts, float* probs, float* scalars,
+                   void* stream);
+
 /* ---- op-level entry points (layer-wise parity tests; same kernels the engine runs) ------- */
 /* stride-1 SAME Conv3d (+bias, +ReLU) on NDHWC 16-bit tensors via the tcgen05 implicit-GEMM kernel.
  *   Formats follow the engine's: dgrad == 0 reads fp16 x and writes fp16 y; dgrad != 0 reads bf16 dY and writes bf16 dX.

@@ -95,9 +95,43 @@ class StandInEngine:
         return self.scalars
 
 
+class StandInEvalEngine(StandInEngine):
+    """EvalEngine's interface (engine.py; fav_create_eval / fav_eval_batch): clean + perturbed rows of one validation
+    batch, counters accumulated in `counts` = [miss, valid]"""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.counts = torch.zeros(2, dtype=torch.int64)
+        self.probs2 = torch.zeros((2 * self.B, self.K))
+        self.calls = []
+
+    def reset_counts(self):
+        self.counts.zero_()
+
+    def eval_batch(self, clips, delta, labels, clips_adv=None, n_clips=None, delta_clip=0.4, targeted=False,
+                   target_class=0, exclude_misclassify=True, loss=None, want_probs=False, stream=None):
+        self.calls.append(dict(delta=delta.clone(), clips_adv=clips_adv, n_clips=n_clips, loss=loss))
+        n = self.B if n_clips is None else n_clips
+        self.apply(clips, delta, adv_flag=0.0, delta_clip=delta_clip)
+        clean = self.forward().clone()
+        self.apply(clips if clips_adv is None else clips_adv, delta, adv_flag=1.0, delta_clip=delta_clip)
+        adv = self.forward().clone()
+        if loss is not None:
+            self.loss(labels, improve_loss=loss["improve_loss"], targeted=loss["targeted"], use_logits=loss["use_logits"],
+                      margin=loss["margin"], stack=loss["stack"])
+        valid = (clean.argmax(-1) == labels) if exclude_misclassify else torch.ones_like(labels, dtype=torch.bool)
+        miss = (adv.argmax(-1) == int(target_class or 0)) if targeted else (adv.argmax(-1) != labels)
+        self.counts[0] += int((valid & miss)[:n].sum())
+        self.counts[1] += int(valid[:n].sum())
+        if want_probs:
+            self.probs2.copy_(torch.softmax(torch.cat([clean, adv]), -1))
+        return self.counts
+
+
 @pytest.fixture()
 def make_attack(monkeypatch):
     monkeypatch.setattr(attack, "FlickerEngine", StandInEngine)
+    monkeypatch.setattr(attack, "EvalEngine", StandInEvalEngine)
 
     def make(**kw):
         return attack.FlickerAttack({}, B, T, {"LAMBDA": 1.0, "BETA_1": 0.5}, num_classes=K, arch="r3d_18", delta_clip=0.1, **kw)
@@ -163,3 +197,31 @@ def test_replica_attacks_never_join_a_collective(make_attack):
     atk = make_attack(sharded=False)
     assert atk.world == 1 and atk.global_batch == B
     atk.check_replicas()                                                              # no-op without ranks
+
+
+def test_eval_batch_host_logic(make_attack):
+    """FlickerAttack.eval_batch / eval_counts (row f3): the evaluation handle is created lazily with the attack's shape,
+    sees the masked / rolled perturbation, and its device counters are read and reset by eval_counts."""
+    clips, delta, labels = _data()
+    atk = make_attack(frame_range=(1, 4))
+    atk.delta.copy_(delta)
+    assert atk._eval is None
+    atk.eval_batch(clips, labels, shift=2, with_loss=True)
+    ev = atk.evaluator()
+    assert (ev.B, ev.T, ev.K) == (B, T, K) and ev is atk.evaluator()
+    mask = torch.zeros((T, 1))
+    mask[1:5] = 1
+    assert torch.equal(ev.calls[-1]["delta"], torch.roll(delta * mask, 2, 0))
+    assert ev.calls[-1]["loss"]["stack"] == L.FAV_STACK_TORCH and ev.calls[-1]["loss"]["margin"] == atk.margin
+    # independent count for the same perturbation
+    with torch.no_grad():
+        adv_logits, _ = _adv_loss(_net(), clips, torch.roll(delta * mask, 2, 0), labels, 0.1)
+        clean_pred = _net()(_normalize(clips)).argmax(-1)
+    valid = clean_pred == labels
+    want = (int((valid & (adv_logits.argmax(-1) != labels)).sum()), int(valid.sum()))
+    atk.eval_batch(clips, labels, shift=2, n_clips=1)                    # ragged batch: only the first clip counts
+    want2 = (want[0] + int((valid & (adv_logits.argmax(-1) != labels))[:1].sum()), want[1] + int(valid[:1].sum()))
+    assert atk.eval_counts(reset=True) == want2
+    assert atk.eval_counts() == (0, 0)
+    atk.close()
+    assert atk._eval is None

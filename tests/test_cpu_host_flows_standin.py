@@ -11,7 +11,7 @@ import torch
 
 from flickering_adversarial_video_b200 import _lib as L
 from flickering_adversarial_video_b200 import attack
-from test_cpu_attack_host_logic import HW, K, StandInEngine, T
+from test_cpu_attack_host_logic import HW, K, StandInEngine, StandInEvalEngine, T
 
 
 class TFStandIn(StandInEngine):
@@ -27,10 +27,15 @@ class TFStandIn(StandInEngine):
             adv_u8.copy_(((adv + 1.0) * 127.5).to(torch.uint8))
 
 
+class TFEvalStandIn(StandInEvalEngine, TFStandIn):
+    pass
+
+
 @pytest.fixture()
 def standin(monkeypatch):
     from flickering_adversarial_video_b200 import kinetics_i3d as ki
     monkeypatch.setattr(attack, "FlickerEngine", TFStandIn)
+    monkeypatch.setattr(attack, "EvalEngine", TFEvalStandIn)
     monkeypatch.setattr(ki, "_IMAGE_SIZE", HW)
     return ki
 
@@ -107,6 +112,7 @@ def test_tf_drivers_flow(standin, tmp_path):
 def test_torch_learner_single_video_flows(monkeypatch, tmp_path):
     from flickering_adversarial_video_b200 import torch_stack as ts
     monkeypatch.setattr(attack, "FlickerEngine", StandInEngine)
+    monkeypatch.setattr(attack, "EvalEngine", StandInEvalEngine)
 
     class Learner(ts.VideoLearnerAdversarial):
         def __init__(self):
@@ -227,6 +233,7 @@ def test_torch_fit_with_the_real_attack_factory(monkeypatch, tmp_path):
     """VideoLearnerAdversarial.fit through the real `_attack` (value-bound check, sharded flag, delta hand-over)"""
     from flickering_adversarial_video_b200 import torch_stack as ts
     monkeypatch.setattr(attack, "FlickerEngine", StandInEngine)
+    monkeypatch.setattr(attack, "EvalEngine", StandInEvalEngine)
 
     class Learner(ts.VideoLearnerAdversarial):
         def __init__(self):

@@ -104,10 +104,11 @@ def test_fit_loop_epochs_schedule_and_files(tmp_path):
     from flickering_adversarial_video_b200 import _lib as L
     from flickering_adversarial_video_b200 import torch_stack as ts
     T, B, K = 4, 2, 10
-    lrs = []
+    lrs, evals = [], []
 
     class Eng:
         logits = torch.zeros((B, K))
+        scalars = torch.zeros(L.S_COUNT)
 
         def loss(self, lab, **kw):
             sc = torch.zeros(L.S_COUNT)
@@ -128,6 +129,26 @@ def test_fit_loop_epochs_schedule_and_files(tmp_path):
 
         def check_replicas(self):
             pass
+
+        # fused validation pass (row f3): counters on the "device", read once per phase
+        def eval_batch(self, clips, labels, shift=0, with_loss=False, **kw):
+            self._counts = getattr(self, "_counts", [0, 0])
+            self._counts[0] += B
+            self._counts[1] += B
+            evals.append(shift)
+
+        def eval_counts(self, reset=True):
+            c = tuple(getattr(self, "_counts", [0, 0]))
+            if reset:
+                self._counts = [0, 0]
+            return c
+
+        def evaluator(self):
+            return self.eng
+
+        def state_dict(self):
+            z = torch.zeros((T, 3))
+            return {"delta": self.delta.clone(), "m": z, "v": z, "step": len(lrs)}
 
         def step(self, clips, lab, lr=None):
             lrs.append(lr)
@@ -153,18 +174,25 @@ def test_fit_loop_epochs_schedule_and_files(tmp_path):
     res = lrn.fit(1e-2, 6, str(tmp_path), None, save_model=True, loss_params_dict=lp, start_epoch=2,
                   train_batches=batches, valid_batches=batches)
     assert len(res) == 5                                                      # epochs 2..6 inclusive
-    assert sorted(os.listdir(str(tmp_path))) == [f"r3d_18_{e:03d}.npy" for e in range(2, 7)]
+    # per epoch: the reference's result file and the sidecar for an exact restart (delta, Adam moments, Adam step)
+    assert sorted(os.listdir(str(tmp_path))) == sorted([f"r3d_18_{e:03d}.npy" for e in range(2, 7)] +
+                                                       [f"r3d_18_{e:03d}.state.npz" for e in range(2, 7)])
+    assert int(np.load(str(tmp_path / "r3d_18_006.state.npz"))["adam_step"]) == 15
     # StepLR(step_size=ceil(2/3*6)=4, gamma=0.1), restarted at lr on this call: 4 epochs at 1e-2, then 1e-3
     assert np.allclose(lrs, [1e-2] * 12 + [1e-3] * 3)
     last = np.load(str(tmp_path / "r3d_18_006.npy"), allow_pickle=True)[-1]
     assert last["valid/perturbation"].shape == (3, T, 1, 1) and last["train/fooling_ratio"] == 1.0
     assert abs(last["train/loss"] - 1.5) < 1e-6 and abs(last["valid/pert_thickness"] - 0.1) < 1e-6     # clamped at 0.1
+    assert last["valid/fooling_ratio"] == 1.0 and len(evals) == 15            # every validation batch: one fused pass
     # cyclic_pert (model.py:91-92): every adversarial forward sees the perturbation rolled by a fresh random shift
     rolled = []
     Atk.step_rolled = lambda self, clips, lab, shift, lr=None: (rolled.append(("train", shift)), Atk.step(self, clips, lab, lr))[1]
     plain_predict = Atk.predict
     Atk.predict = lambda self, clips, adv_flag=1.0, shift=0: (rolled.append(("valid", shift)) if shift else None,
                                                                 plain_predict(self, clips, adv_flag))[1]
+    plain_eval = Atk.eval_batch
+    Atk.eval_batch = lambda self, clips, labels, shift=0, **kw: (rolled.append(("valid", shift)) if shift else None,
+                                                                  plain_eval(self, clips, labels, shift=shift, **kw))[1]
     cyc = Learner()
     cyc.pert_model.cyclic_pert, cyc._rng = True, np.random.RandomState(0)
     lrs.clear()
