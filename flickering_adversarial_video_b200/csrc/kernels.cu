@@ -534,6 +534,81 @@ maxpool_fwd_kernel(const __half* __restrict__ x, __half* __restrict__ y,
   }
 }
 
+// Loads-first variant for the pools of the I3D trunk (compile-time window).  ncu on the generic kernel above
+// (profiles/r02_c1_ncu_full_details.txt, MaxPool3d_2a): 346 instructions per thread, 70 % of the warp cycles stalled on
+// L1TEX with one load outstanding at a time — the bounds tests around each tap keep the compiler from hoisting the
+// loads, so the kernel ran at the memory latency (46 % of HBM).  Here every tap of one temporal slice is loaded
+// unconditionally from a clamped (always valid) address before the first compare; taps outside the input become -inf,
+// which a strict > never selects, so the first-arg-max rule and the tap numbering are unchanged.
+template <int KT, int KH, int KW, int ST, int SH, int SW>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_win_kernel(const __half* __restrict__ x, __half* __restrict__ y, uint8_t* __restrict__ idx, const PoolGeom g) {
+  pdl_sync();
+  const int cg = g.C >> 3;
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= g.Wo * cg) return;
+  const int wo = i / cg;
+  const int c8 = i - wo * cg;
+  int row = blockIdx.x;
+  const int ho = row % g.Ho; row /= g.Ho;
+  const int to = row % g.To;
+  const int b = row / g.To;
+  const int t0 = to * ST - g.pt, h0 = ho * SH - g.ph, w0 = wo * SW - g.pw;
+  uint32_t best[4] = {kF16NegInf2, kF16NegInf2, kF16NegInf2, kF16NegInf2};
+  uint32_t bidx[4] = {0u, 0u, 0u, 0u};
+  int woff[KW];
+  bool wok[KW];
+#pragma unroll
+  for (int dw = 0; dw < KW; ++dw) {
+    const int w = w0 + dw;
+    wok[dw] = w >= 0 && w < g.W;
+    woff[dw] = min(max(w, 0), g.W - 1) * g.C;
+  }
+#pragma unroll
+  for (int dt = 0; dt < KT; ++dt) {
+    const int t = t0 + dt;
+    const bool tok = t >= 0 && t < g.T;
+    const int tc = min(max(t, 0), g.T - 1);
+    uint4 v[KH][KW];
+    bool hok[KH];
+#pragma unroll
+    for (int dh = 0; dh < KH; ++dh) {
+      const int h = h0 + dh;
+      hok[dh] = tok && h >= 0 && h < g.H;
+      const int hc = min(max(h, 0), g.H - 1);
+      const __half* rowp = x + ((static_cast<long long>(b) * g.T + tc) * g.H + hc) * g.W * g.C + c8 * 8;
+#pragma unroll
+      for (int dw = 0; dw < KW; ++dw) v[dh][dw] = __ldg(reinterpret_cast<const uint4*>(rowp + woff[dw]));
+    }
+#pragma unroll
+    for (int dh = 0; dh < KH; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < KW; ++dw) {
+        const bool ok = hok[dh] && wok[dw];
+        const uint32_t tap2 = static_cast<uint32_t>((dt * KH + dh) * KW + dw) * 0x00010001u;
+        const uint32_t wv[4] = {v[dh][dw].x, v[dh][dw].y, v[dh][dw].z, v[dh][dw].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t u = ok ? wv[j] : kF16NegInf2;
+          const __half2 vv = *reinterpret_cast<const __half2*>(&u);
+          const __half2 bb = *reinterpret_cast<const __half2*>(&best[j]);
+          const uint32_t m = __hgt2_mask(vv, bb);   // strict >: the first arg-max wins
+          const __half2 mx = __hmax2(bb, vv);
+          best[j] = *reinterpret_cast<const uint32_t*>(&mx);
+          bidx[j] = (bidx[j] & ~m) | (tap2 & m);
+        }
+      }
+  }
+  const long long ooff = ((static_cast<long long>(blockIdx.x) * g.Wo + wo) * cg + c8) * 8;
+  *reinterpret_cast<uint4*>(y + ooff) = make_uint4(best[0], best[1], best[2], best[3]);
+  if (idx) {
+    uint2 iv;
+    iv.x = __byte_perm(bidx[0], bidx[1], 0x6420);
+    iv.y = __byte_perm(bidx[2], bidx[3], 0x6420);
+    *reinterpret_cast<uint2*>(idx + ooff) = iv;
+  }
+}
+
 int launch_maxpool_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s) {
   ProfScope ps(PK_POOL_FWD, s, 0.0, static_cast<double>(g.B) * g.C * (2.0 * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
@@ -542,11 +617,19 @@ int launch_maxpool_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom&
   if (pool3s1_applicable(g)) return launch_pool3s1_fwd(x, y, idx, g, s);   // idx == nullptr: forward-only plan, no codes
   dim3 grid(g.B * g.To * g.Ho, ceil_div(g.Wo * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
-  switch (key) {
-    case 133122: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<1, 3, 3, 1, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
-    case 333111: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<3, 3, 3, 1, 1, 1>, grid, 256, 0, s, x, y, idx, g)); break;
-    case 333222: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<3, 3, 3, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
-    case 222222: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<2, 2, 2, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+  static int win = -1;   // FAV_POOL_FWD_WIN=0: the generic tap-by-tap kernel (A/B)
+  if (win < 0) {
+    const char* ev = getenv("FAV_POOL_FWD_WIN");
+    win = (ev && atoi(ev) == 0) ? 0 : 1;
+  }
+  switch (win ? key : -key) {
+    case 133122: FAV_CUDA(launch_pdl(maxpool_fwd_win_kernel<1, 3, 3, 1, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case 333222: FAV_CUDA(launch_pdl(maxpool_fwd_win_kernel<3, 3, 3, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case 222222: FAV_CUDA(launch_pdl(maxpool_fwd_win_kernel<2, 2, 2, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case -133122: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<1, 3, 3, 1, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case 333111: case -333111: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<3, 3, 3, 1, 1, 1>, grid, 256, 0, s, x, y, idx, g)); break;
+    case -333222: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<3, 3, 3, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
+    case -222222: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<2, 2, 2, 2, 2, 2>, grid, 256, 0, s, x, y, idx, g)); break;
     default: FAV_CUDA(launch_pdl(maxpool_fwd_kernel<0, 0, 0, 0, 0, 0>, grid, 256, 0, s, x, y, idx, g)); break;
   }
   FAV_COUNT_LAUNCH();
