@@ -997,7 +997,7 @@ static int run_block_bwd(fav_handle* h, const Block& b, cudaStream_t s) {
 static int run_pool_bwd(fav_handle* h, int pid, cudaStream_t s) {
   const PoolOp& p = h->pools[pid];
   const Buf& bi = h->bufs[p.in];
-  return launch_maxpool_bwd(h->bufs[p.out].g, h->bufs[p.out].idx, nullptr, bi.p, bi.g, p.g, s);
+  return launch_maxpool_bwd(h->bufs[p.out].g, h->bufs[p.out].idx, nullptr, bi.p, bi.g, p.g, s, h->bufs[p.out].p);
 }
 
 static int i3d_backward_to_stem(fav_handle* h, cudaStream_t s);

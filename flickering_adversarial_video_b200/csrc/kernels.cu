@@ -707,11 +707,17 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
                        const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
-                       cudaStream_t s) {
-  ProfScope ps(PK_POOL_BWD, s, 0.0, static_cast<double>(g.B) * g.C * ((addend ? 6.0 : 4.0) * g.T * g.H * g.W + 3.0 * g.To * g.Ho * g.Wo));
+                       cudaStream_t s, const __half* pooled) {
+  // FAV_POOL_BWD_POOLED=0: always mask with the full-resolution producer output (A/B and the bit-identity test; read at
+  // every call — 13 per step, once per graph capture)
+  const char* ev = getenv("FAV_POOL_BWD_POOLED");
+  if ((ev && atoi(ev) == 0) || addend || !relu_src) pooled = nullptr;
+  const bool s2 = !pool3s1_applicable(g) && pool_s2_applicable(g);
+  const double in_bytes = (addend ? 6.0 : (pooled && s2 ? 2.0 : 4.0));
+  ProfScope ps(PK_POOL_BWD, s, 0.0, static_cast<double>(g.B) * g.C * (in_bytes * g.T * g.H * g.W + (pooled && s2 ? 5.0 : 3.0) * g.To * g.Ho * g.Wo));
   FAV_CHECK_ARG(g.C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", g.C);
   if (pool3s1_applicable(g)) return launch_pool3s1_bwd(dy, idx, addend, relu_src, dx, g, s);
-  if (pool_s2_applicable(g)) return launch_pool_s2_bwd(dy, idx, addend, relu_src, dx, g, s);
+  if (pool_s2_applicable(g)) return launch_pool_s2_bwd(dy, idx, addend, relu_src, dx, g, s, pooled);
   dim3 grid(g.B * g.T * g.H, ceil_div(g.W * (g.C / 8), 256));
   const int key = ((g.kt * 10 + g.kh) * 10 + g.kw) * 1000 + (g.st * 10 + g.sh) * 10 + g.sw;
   switch (key) {

@@ -53,9 +53,12 @@ int pixels_partial_floats(int T, int H, int W);
 // pools: forward on fp16 activations; backward on bf16 gradients, ReLU mask from the producer's fp16 output
 int launch_maxpool_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom& g,
                        cudaStream_t s);
+// `pooled` (optional): the pool's forward OUTPUT.  Without an addend the strided kernels then take the ReLU mask of the
+// input from it (an element that receives gradient is the arg-max of that window, so input > 0 <=> pooled > 0) and never
+// read the full-resolution `relu_src`; results are bit-identical.
 int launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
                        const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g,
-                       cudaStream_t s);
+                       cudaStream_t s, const __half* pooled = nullptr);
 
 // 3x3x3 / stride 1 / SAME pools: separable streaming kernels (pool3.cu).  idx holds three 2-bit stage
 // codes per element instead of a 27-tap index; launch_maxpool_fwd/bwd dispatch to them when applicable.
@@ -67,7 +70,8 @@ int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_b
 // stride-2 pools ([1,3,3]/[1,2,2], 3x3x3/2x2x2): patch-per-thread backward (pool3.cu), standard 27-tap idx
 bool pool_s2_applicable(const PoolGeom& g);
 int launch_pool_s2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
-                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s);
+                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s,
+                       const __half* pooled = nullptr);
 
 // head: feat[b,c] = sum_t coef[t]*sum_hw Y / (HW*2*(T5-1)); logits = feat @ Wl + bl
 int launch_head_fwd(const __half* y, int B, int T5, int HW, int C, float* feat,

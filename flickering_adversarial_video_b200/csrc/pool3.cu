@@ -276,10 +276,16 @@ __device__ __forceinline__ uint32_t eq_msb(uint32_t iv, uint32_t tap4) {
   return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x);
 }
 
-template <int KT>   // temporal kernel: 1 (stride 1) or 3 (stride 2)
+// ReLU mask of the pool INPUT from the pool OUTPUT (`pooled`, used when there is no addend): an input element only
+// receives gradient from windows it won, and for those the pooled value IS its own value, so (input > 0) == (pooled > 0)
+// on every element whose gradient is non-zero.  Masking dy by (pooled > 0) window by window gives bit-identical results
+// and replaces the read of the full-resolution producer output (4x / 8x the pooled tensor: 411 MB at MaxPool3d_2a)
+// by a read of the pooled tensor — a third of the kernel's DRAM traffic (ncu r02_c3: 5.3 TB/s, already HBM-bound).
+template <int KT, bool POOLED>   // temporal kernel: 1 (stride 1) or 3 (stride 2); POOLED: ReLU mask from the pool output
 __global__ void __launch_bounds__(256)
 pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    const __nv_bfloat16* __restrict__ addend, const __half* __restrict__ relu_src,
+                   const __half* __restrict__ pooled,
                    __nv_bfloat16* __restrict__ dx, const PoolGeom g, const int Qt, const int Qh, const int Qw) {
   pdl_sync();
   constexpr int NA = KT == 3 ? 2 : 1;
@@ -295,6 +301,7 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   // ---- all window loads first ----
   uint2 iv[NA][2][2];
   uint4 dv[NA][2][2];
+  uint4 pv[POOLED ? NA : 1][2][2];
 #pragma unroll
   for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -306,7 +313,19 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
         const long long off = ((((static_cast<long long>(b) * g.To + to) * g.Ho + ho) * g.Wo + wo) * cg + c8) * 8;
         iv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint2*>(idx + off)) : make_uint2(0xffffffffu, 0xffffffffu);
         dv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint4*>(dy + off)) : make_uint4(0u, 0u, 0u, 0u);
+        if (POOLED) pv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint4*>(pooled + off)) : make_uint4(0u, 0u, 0u, 0u);
       }
+  if (POOLED) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          dv[a][bb][c].x &= relu_mask2(pv[a][bb][c].x); dv[a][bb][c].y &= relu_mask2(pv[a][bb][c].y);
+          dv[a][bb][c].z &= relu_mask2(pv[a][bb][c].z); dv[a][bb][c].w &= relu_mask2(pv[a][bb][c].w);
+        }
+  }
 #pragma unroll
   for (int et = 0; et < NA; ++et) {
     const int t = KT == 3 ? 2 * qt - g.pt + et : qt;
@@ -322,7 +341,7 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
         const int h = 2 * qh - g.ph + eh, w = 2 * qw - g.pw + ew;
         live[eh][ew] = h >= 0 && h < g.H && w >= 0 && w < g.W;
         eo[eh][ew] = ((((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * cg + c8) * 8;
-        rv[eh][ew] = (live[eh][ew] && relu_src) ? __ldg(reinterpret_cast<const uint4*>(relu_src + eo[eh][ew]))
+        rv[eh][ew] = (!POOLED && live[eh][ew] && relu_src) ? __ldg(reinterpret_cast<const uint4*>(relu_src + eo[eh][ew]))
                                                  : make_uint4(kF16One2, kF16One2, kF16One2, kF16One2);
         av[eh][ew] = (live[eh][ew] && addend) ? __ldg(reinterpret_cast<const uint4*>(addend + eo[eh][ew]))
                                                : make_uint4(0u, 0u, 0u, 0u);
@@ -352,9 +371,8 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
           }
         }
         const uint4 r = rv[eh][ew];
-        uint4 o;
-        o.x = acc[0] & relu_mask2(r.x); o.y = acc[1] & relu_mask2(r.y);
-        o.z = acc[2] & relu_mask2(r.z); o.w = acc[3] & relu_mask2(r.w);
+        uint4 o = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        if (!POOLED) { o.x &= relu_mask2(r.x); o.y &= relu_mask2(r.y); o.z &= relu_mask2(r.z); o.w &= relu_mask2(r.w); }
         *reinterpret_cast<uint4*>(dx + eo[eh][ew]) = o;
       }
   }
@@ -460,13 +478,17 @@ bool pool_s2_applicable(const PoolGeom& g) {
 }
 
 int launch_pool_s2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
-                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
+                       const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s, const __half* pooled) {
   FAV_CHECK_ARG(pool_s2_applicable(g), "pool_s2_bwd: unsupported geometry");
+  if (pooled && !addend) relu_src = nullptr;   // the window masks carry the ReLU
+  else pooled = nullptr;
   const int Qt = g.kt == 3 ? (g.T - 1 + g.pt) / 2 + 1 : g.T;
   const int Qh = (g.H - 1 + g.ph) / 2 + 1, Qw = (g.W - 1 + g.pw) / 2 + 1;
   dim3 grid(g.B * Qt * Qh, ceil_div(Qw * (g.C / 8), 256));
-  if (g.kt == 3) FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<3>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw));
-  else FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<1>, grid, 256, 0, s, dy, idx, addend, relu_src, dx, g, Qt, Qh, Qw));
+  if (g.kt == 3 && pooled) FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<3, true>, grid, 256, 0, s, dy, idx, addend, relu_src, pooled, dx, g, Qt, Qh, Qw));
+  else if (g.kt == 3) FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<3, false>, grid, 256, 0, s, dy, idx, addend, relu_src, pooled, dx, g, Qt, Qh, Qw));
+  else if (pooled) FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<1, true>, grid, 256, 0, s, dy, idx, addend, relu_src, pooled, dx, g, Qt, Qh, Qw));
+  else FAV_CUDA(launch_pdl(pool_s2_bwd_kernel<1, false>, grid, 256, 0, s, dy, idx, addend, relu_src, pooled, dx, g, Qt, Qh, Qw));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -344,3 +344,30 @@ def test_stem_gradient_collapse_matches_dense_data_gradient(setup, monkeypatch, 
     rel = float((a - b).norm() / a.norm())
     _report(f"stem gradient collapse vs dense data gradient + masked reduce (T={T_here}): cosine {cos:.6f}, rel L2 {rel:.3e}")
     assert cos >= 0.9999 and rel <= 1e-2
+
+
+def test_pool_backward_mask_from_pooled_output_is_bit_identical(setup, monkeypatch):
+    """The strided max-pool backward takes the ReLU mask of its input from the POOLED output (an element that receives
+    gradient is the arg-max of that window, so input > 0 <=> pooled > 0) instead of reading the full-resolution producer
+    output.  FAV_POOL_BWD_POOLED=0 restores the direct mask: the stem-output gradient and dL/d-delta must not change
+    by a single bit."""
+    eng, B = setup["eng"], setup["B"]
+    clip, delta = setup["clip"].cuda(), setup["delta"].cuda()
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FAV_POOL_BWD_POOLED", flag)
+        eng.apply(clip, delta)
+        labels = eng.forward().argmax(-1).clone()
+        eng.loss(labels, improve_loss=True, margin=0.05)
+        g = eng.backward().clone()
+        g1 = eng.read("grad:Conv3d_1a_7x7", (B, T_SMALL // 2, 112, 112, 64)).clone()
+        g3 = eng.read("grad:Conv3d_2c_3x3", (B, T_SMALL // 2, 56, 56, 192)).clone()
+        g4 = eng.read("grad:Mixed_3c", (B, T_SMALL // 2, 28, 28, 480)).clone()
+        out.append((g, g1, g3, g4))
+    assert float(out[0][1].abs().max()) > 0
+    names = ("dL/d-delta", "grad:Conv3d_1a_7x7", "grad:Conv3d_2c_3x3", "grad:Mixed_3c")
+    for name, a, b in zip(names, *out):
+        if name == "dL/d-delta":       # the collapse flushes per-plane partial sums with atomics: not run-to-run bitwise
+            assert float((a - b).norm() / b.norm()) < 1e-5, name
+        else:
+            assert torch.equal(a, b), f"{name}: {int((a != b).sum())} of {a.numel()} entries differ"
