@@ -16,6 +16,7 @@
 #include "conv_umma.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace fav {
@@ -203,6 +204,195 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Raw-row variant.  ncu on the kernel above (profiles/r02_c1_ncu_full_details.txt): tensor pipe busy 74 % of the time
+// but at 66 cycles per 128x64x16 MMA instead of the 48 the operand reads need — the TMA writes of the im2col'd A tiles
+// (every input pixel 4x, 66 KB per stage, 7 GB of L2 -> SM traffic per step) share the 128 B/clk shared-memory port
+// with the MMA's operand reads.  Here the producer brings RAW input rows (40 RGBX pixels = 320 B per row) and the MMA
+// reads the im2col windows straight out of them: a no-swizzle descriptor with LBO = 16 B, SBO = 320 B makes row r of
+// the M tile the 32-byte window at 16*(r%8) + 320*(r/8), i.e. M tile = 8 output columns x 16 output rows (the K = 32
+// of a (kt,kh) tap = pixels 2w..2w+7 x RGBX; second K = 16 half at +32 B).  A stage holds, per H parity, the rows of
+// nf = 2 output frames (24 KB instead of 76) next to the 28 KB of weights, and the 2*nf = 4 M tiles
+// ((8-column half, frame)) share every weight sub-tile: the TMA write share per MMA drops from 2.4 KB to 0.9 KB.
+// ---------------------------------------------------------------------------------------------------------------------
+struct RawTile {
+  int b, t0, h0, w0;
+};
+__device__ __forceinline__ RawTile decode_raw_tile(const StemGeom& g, int tile) {
+  RawTile c;
+  const int wi = tile % g.tw;
+  int m = tile / g.tw;
+  const int hi = m % g.th;
+  m /= g.th;
+  c.t0 = (m % g.tp) * g.nf;
+  c.b = m / g.tp;
+  c.h0 = hi * 16;
+  c.w0 = wi * 16;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stem_raw_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                     const __grid_constant__ CUtensorMap tmB, const StemGeom g, const ConvEpilogue e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(g.stages) * g.stage_bytes);
+  uint64_t* full_bar = bars;                    // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;      // [stages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 2 * kMaxStages + 6);   // 4 epilogue warps x 32 rows x 5 uint4
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int acc_cols = g.mt * g.bn;             // TMEM columns per accumulator stage
+  // stage layout: [weights KH x bn x 64 B (SW64)] [parity-0 slab: nf x rows[0] x pitch] [parity-1 slab]
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_tx = static_cast<uint32_t>((g.rows[0] + g.rows[1]) * g.nf * g.pitch);
+      for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+        const RawTile tc = decode_raw_tile(g, tile);
+        for (int kt = 0; kt < g.KT; ++kt) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sb = smem + static_cast<size_t>(stage) * g.stage_bytes;
+          mbar_expect_tx(&full_bar[stage], a_tx + static_cast<uint32_t>(g.b_bytes));
+          // input frame of output frame t: st*t + kt - pt = st*(t + qt) + parity; the nf frames are consecutive in the map
+          int par_t = 0, tcoord;
+          if (g.st == 2) {
+            const int offt = kt - g.pt;
+            par_t = offt & 1;
+            tcoord = tc.t0 + ((offt - par_t) >> 1);
+          } else {
+            tcoord = tc.t0 + kt - g.pt;
+          }
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if ((p ? g.rows[1] : g.rows[0]) == 0) continue;
+            const int mi = par_t * 2 + p;
+            const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+            tma_load_5d(sb + (p ? g.slab_off[1] : g.slab_off[0]), tm, &full_bar[stage], 8 * tc.w0,
+                        tc.h0 + (p ? g.qmin[1] : g.qmin[0]), tcoord, tc.b, 0);
+          }
+          tma_load_3d(sb, &tmB, &full_bar[stage], 0, 0, kt * g.KH);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc(128, g.bn, true);
+    const uint32_t hi_a = umma_desc_hi_nosw(static_cast<uint32_t>(g.pitch));   // SBO = one raw row; LBO = 16 B (in the low word)
+    const uint32_t hi_b = umma_desc_hi(64);
+    const uint32_t b_sub = static_cast<uint32_t>(g.bn) * 64u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
+      for (int kt = 0; kt < g.KT; ++kt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+        if (elect_one()) {
+          for (int kh = 0; kh < g.KH; ++kh) {
+            const int offh = kh - g.ph;
+            const int p = offh & 1;
+            const int qh = (offh - p) >> 1;
+            const uint32_t slab = sb + static_cast<uint32_t>((p ? g.slab_off[1] : g.slab_off[0]) +
+                                                             (qh - (p ? g.qmin[1] : g.qmin[0])) * g.pitch);
+            const uint32_t fstep = static_cast<uint32_t>((p ? g.rows[1] : g.rows[0]) * g.pitch);
+            const uint32_t b_lo = umma_desc_lo(sb + kh * b_sub);
+            const uint32_t accum = (kt | kh) ? 1u : 0u;
+            for (int i = 0; i < g.mt; ++i) {
+              // M tile i: frame i >> 1, 8-column half i & 1 (128 B = 8 output columns x 16 B)
+              const uint32_t a_lo = umma_desc_lo(slab + static_cast<uint32_t>(i >> 1) * fstep + static_cast<uint32_t>(i & 1) * 128u);
+              const uint32_t d_i = d_tmem + static_cast<uint32_t>(i * g.bn);
+              umma_bf16(d_i, make_desc(hi_a, a_lo), make_desc(hi_b, b_lo), idesc, accum);
+              umma_bf16(d_i, make_desc(hi_a, a_lo + 2), make_desc(hi_b, b_lo + 2), idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kt == g.KT - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rw = row & 7;
+    const int rh = row >> 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      const RawTile tc = decode_raw_tile(g, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int h = tc.h0 + rh;
+      for (int i = 0; i < g.mt; ++i) {
+        const int t = tc.t0 + (i >> 1);
+        const int w = tc.w0 + (i & 1) * 8 + rw;
+        const bool valid = (w < g.Wo) && (h < g.Ho) && (t < g.To);
+        const long long pos = valid ? ((static_cast<long long>(tc.b) * g.To + t) * g.Ho + h) * g.Wo + w : 0;
+        h16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const float* bias_row = nullptr;
+        if (e.bias) {
+          int br = 0;
+          if (e.bias_stem) {
+            const int hc = border_cls(min(h, g.Ho - 1), g.Ho, g.nlo_h, g.nhi_h);
+            const int wc = border_cls(min(w, g.Wo - 1), g.Wo, g.nlo_w, g.nhi_w);
+            br = (min(t, g.To - 1) * 4 + hc) * 4 + wc;
+          }
+          bias_row = e.bias + static_cast<long long>(br) * e.bias_ld;
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * acc_cols + i * g.bn);
+        epilogue_columns_staged(e, g.bn, 0, taddr, valid, out_row, bias_row, e.cout_store, stage_all + (warp - 2) * 160, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
@@ -214,6 +404,74 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
   StemGeom& g = L->g;
   g.B = B; g.To = To; g.Ho = Ho; g.Wo = Wo;
   g.KT = KT; g.KH = KH; g.st = st; g.pt = pt; g.ph = ph; g.bn = bn;
+  {
+    const char* ev = getenv("FAV_STEM_RAW");   // 0: the im2col-tile kernel (A/B)
+    g.raw = (ev && atoi(ev) == 0) ? 0 : 1;
+    if (bn > 128) g.raw = 0;                    // four accumulators of bn columns, double-buffered
+  }
+  if (g.raw) {
+    g.nf = To >= 2 ? 2 : 1;
+    if (2 * 2 * g.nf * bn > 512) g.nf = 1;
+    g.mt = 2 * g.nf;
+    g.tp = ceil_div(To, g.nf);
+    g.th = ceil_div(Ho, 16);
+    g.tw = ceil_div(Wo, 16);
+    g.m_tiles = B * g.tp * g.th * g.tw;
+    g.pitch = 320;                              // 2*15 + 8 = 38 pixels of 8 B, padded to a multiple of 64 B
+    int qlo[2] = {1 << 20, 1 << 20}, qhi[2] = {-(1 << 20), -(1 << 20)};
+    for (int kh = 0; kh < KH; ++kh) {
+      const int offh = kh - ph;
+      const int p = offh & 1;
+      const int qh = (offh - p) / 2;
+      qlo[p] = std::min(qlo[p], qh);
+      qhi[p] = std::max(qhi[p], qh);
+    }
+    g.b_bytes = KH * bn * 64;
+    int off = round_up(g.b_bytes, 1024);
+    for (int p = 0; p < 2; ++p) {
+      if (qhi[p] < qlo[p]) { g.qmin[p] = 0; g.rows[p] = 0; g.slab_off[p] = off; continue; }
+      g.qmin[p] = qlo[p];
+      g.rows[p] = 16 + (qhi[p] - qlo[p]);
+      g.slab_off[p] = off;
+      off += round_up(g.nf * g.rows[p] * g.pitch, 128);
+    }
+    g.a_bytes = off - round_up(g.b_bytes, 1024);
+    g.stage_bytes = round_up(off, 1024);
+    g.stages = std::max(2, std::min(kMaxStages, (215 * 1024) / g.stage_bytes));
+    FAV_CHECK_ARG(g.stages * g.stage_bytes <= 215 * 1024, "stem: stage of %d bytes does not fit", g.stage_bytes);
+    L->smem_bytes = static_cast<size_t>(g.stages) * g.stage_bytes + 1024 + 512 + 4 * 32 * 5 * 16;
+    auto classes = [](int in, int out, int k, int s, int pad, int* nlo, int* nhi) {
+      *nlo = ceil_div(pad, s);
+      const int pad_after = std::max(0, (out - 1) * s + k - pad - in);
+      *nhi = ceil_div(pad_after, s);
+    };
+    classes(H, Ho, KH, 2, ph, &g.nlo_h, &g.nhi_h);
+    classes(2 * Wo, Wo, 7, 2, ph, &g.nlo_w, &g.nhi_w);
+    FAV_CHECK_ARG(g.nlo_h + g.nhi_h <= 3 && g.nlo_w + g.nhi_w <= 3, "stem: more than 4 border classes");
+    const uint64_t pos_bytes = 8;
+    const uint64_t row_pitch = static_cast<uint64_t>(Wp) * pos_bytes;
+    const uint64_t frame_pitch = row_pitch * H;
+    const uint64_t clip_pitch = frame_pitch * T;
+    for (int p_t = 0; p_t < 2; ++p_t)
+      for (int p_h = 0; p_h < 2; ++p_h) {
+        if (g.rows[p_h] == 0 || (st == 1 && p_t == 1)) { L->tmA[p_t * 2 + p_h] = L->tmA[0]; continue; }
+        // raw rows of one (T, H) parity: [Wp*4 elements][rows of this parity][frames of this parity][B][1]
+        uint64_t dims[5] = {static_cast<uint64_t>(Wp) * 4, static_cast<uint64_t>((H - p_h + 1) / 2),
+                            static_cast<uint64_t>(st == 2 ? (T - p_t + 1) / 2 : T), static_cast<uint64_t>(B), 1};
+        uint64_t strides[4] = {2 * row_pitch, st * frame_pitch, clip_pitch, clip_pitch * B};
+        uint32_t box[5] = {static_cast<uint32_t>(g.pitch / 2), static_cast<uint32_t>(g.rows[p_h]),
+                           static_cast<uint32_t>(g.nf), 1, 1};
+        const char* base = static_cast<const char*>(xpad) + (st == 2 ? p_t : 0) * frame_pitch + p_h * row_pitch;
+        FAV_TRY(make_tmap_bf16(&L->tmA[p_t * 2 + p_h], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+      }
+    if (g.rows[0] == 0) L->tmA[0] = L->tmA[1];
+    uint64_t bd[3] = {32, static_cast<uint64_t>(bn), static_cast<uint64_t>(KT) * KH};
+    uint64_t bs[2] = {64, static_cast<uint64_t>(bn) * 64};
+    uint32_t bb[3] = {32, static_cast<uint32_t>(bn), static_cast<uint32_t>(KH)};
+    FAV_TRY(make_tmap_bf16(&L->tmB, wpk, 3, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_64B));
+    L->grid = std::max(1, std::min(g.m_tiles, sm_count(device)));
+    return FAV_OK;
+  }
   // M tiles per CTA tile: two accumulator stages of mt*bn columns must fit the 512 TMEM columns
   g.mt = std::max(1, std::min(2, 256 / bn));
   if (Ho <= 8) g.mt = 1;
@@ -296,6 +554,18 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   ProfScope ps(PK_STEM, stream, L.flops);
+  if (L.g.raw) {
+    static bool attr_raw = false;
+    if (!attr_raw) {
+      FAV_CUDA(cudaFuncSetAttribute(conv_stem_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_raw = true;
+    }
+    FAV_CUDA(launch_pdl(conv_stem_raw_kernel, L.grid, kThreads, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3],
+                        L.tmB, L.g, L.e));
+    FAV_COUNT_LAUNCH();
+    FAV_CUDA(cudaGetLastError());
+    return FAV_OK;
+  }
   FAV_CUDA(launch_pdl(conv_stem_kernel, L.grid, kThreads, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB,
                       L.g, L.e));
   FAV_COUNT_LAUNCH();

@@ -68,10 +68,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* full_bar = bars;                    // [stages]
   uint64_t* empty_bar = bars + kMaxStages;      // [stages]
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint4* stage_all = reinterpret_cast<uint4*>(bars + 2 * kMaxStages + 8);   // 8 epilogue warps x 32 rows x 5 uint4
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [nacc <= 8]
+  uint64_t* tempty_bar = tfull_bar + 8;         // [nacc <= 8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 8);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 2 * kMaxStages + 24);   // 8 epilogue warps x 32 rows x 5 uint4
+  // Accumulator ring: 512 TMEM columns hold nacc = 8 / 4 / 2 accumulators of 64 / 128 / 256 columns.  FAV_TAP_PROF showed
+  // the narrow 1x1x1 launches bound by the LATENCY of one epilogue pass (Conv3d_2b: 55 of 95 kcycles waiting for a free
+  // accumulator, ~2 kcycles per pass with all 8 warps on one tile), so with nacc >= 4 the two warp groups drain
+  // ALTERNATE tiles (each warp all columns of its 32 rows) and two passes are in flight; with nacc == 2 both groups share
+  // every tile as before (each drains half of the columns).
+  const int nacc = g.acc_stages;
+  const int acc_stride = 512 / nacc;
+  const bool alt_groups = nacc >= 4;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,9 +93,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < nacc; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[s], alt_groups ? 4 : 8);  // one arrival per epilogue warp that drains the stage
     }
     mbar_fence_init();
   }
@@ -153,7 +161,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       if (g.prof) { w_te += clock64() - c0; ++ntile; }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_stride);
       uint32_t accum = 0;
       int cb = 0;
       for (int kb = 0; kb < g.nkb; ++kb) {
@@ -191,8 +199,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           phase ^= 1;
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
     if (g.prof && lane == 0) {
       atomicAdd(&g_halo_prof[0], static_cast<unsigned long long>(w_te));
@@ -210,9 +217,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int rw = row % g.bw;
     const int rh = (row / g.bw) % g.bh;
     const int rt = row / (g.bw * g.bh);
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int acc = -1;
+    uint32_t acc_phase = 1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (++acc == nacc) acc = 0;
+      if (acc == 0) acc_phase ^= 1;
+      if (alt_groups && (acc & 1) != chalf) continue;   // the other warp group's tile (nacc is even: a stage keeps its group)
       const TileCoord tc = decode_tile(g, tile);
       const int w = tc.w0 + rw, h = tc.h0 + rh, t = tc.t0 + rt;
       const bool valid = (w < g.W) && (h < g.H) && (t < g.T);
@@ -227,10 +237,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(acc * kAccCols);
-      // this warp's column range of the tile (multiples of 16)
+                             static_cast<uint32_t>(acc * acc_stride);
+      // this warp's column range of the tile (multiples of 16): everything, or its half when both groups share a tile
       const int half_cols = ((g.bn >> 4) + 1) / 2 * 16;
-      const int c_lo = chalf * half_cols, c_hi = min(g.bn, c_lo + half_cols);
+      const int c_lo = alt_groups ? 0 : chalf * half_cols, c_hi = alt_groups ? g.bn : min(g.bn, c_lo + half_cols);
       if (e.nseg > 1) {
         // column segments of this N tile go to different tensors (fused same-input 1x1x1 convs)
         const int n_lo = tc.n0 + c_lo, n_hi = tc.n0 + c_hi;
@@ -255,8 +265,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -581,6 +589,12 @@ static void finish_plan(ConvLaunch* L, int device) {
   L->smem_bytes = static_cast<size_t>(L->stages) * L->stage_bytes + 1024 + 512 + 8 * 32 * 5 * 16;   // + epilogue staging
   const int tiles = g.m_tiles * g.n_tiles;
   L->grid = std::max(1, std::min(tiles, sm_count(device)));
+  // accumulator ring of the per-tap kernel (conv_umma_kernel): 8 x 64, 4 x 128 or 2 x 256 TMEM columns
+  g.acc_stages = g.bn <= 64 ? 8 : (g.bn <= 128 ? 4 : 2);
+  if (const char* ev = getenv("FAV_TAP_ACC")) {   // A/B: FAV_TAP_ACC=2 restores the double-buffered pair
+    const int v = atoi(ev);
+    if ((v == 2 || v == 4 || v == 8) && g.bn * v <= 512) g.acc_stages = v;
+  }
 }
 
 int conv_plan_ex(ConvLaunch* L, int device, const ConvSpec& sp) {

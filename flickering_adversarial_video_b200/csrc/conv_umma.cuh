@@ -315,6 +315,12 @@ struct StemGeom {
   int slab_off[2];        // byte offset of each slab inside a stage
   int a_bytes, b_bytes, stage_bytes, stages;
   int nlo_h, nhi_h, nlo_w, nhi_w;   // border classes of the delta-bias table (rows touching the zero padding)
+  // raw-row variant (conv_stem_raw_kernel): the A operand is read straight from raw RGBX input rows through a
+  // no-swizzle descriptor whose 16-byte leading-dimension offset makes consecutive M rows overlapping windows
+  int raw;                // 1: raw-row kernel
+  int nf;                 // output frames per CTA tile (the mt = 2*nf M tiles of 8 columns x 16 rows share every weight load)
+  int pitch;              // bytes per raw slab row (40 pixels x 8 B)
+  int tp;                 // frame groups: ceil(To / nf)
 };
 struct StemLaunch {
   CUtensorMap tmA[4];     // [T-parity][H-parity]

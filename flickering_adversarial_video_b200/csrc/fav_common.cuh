@@ -351,6 +351,13 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((sadd
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
+// NO-SWIZZLE K-major descriptor (canonical interleaved layout): element (r, k) of the operand sits at
+//   start + 16*(r % 8) + SBO*(r / 8) + 2*(k % 8) + LBO*(k / 8)   bytes.
+// With LBO = 16 the eight rows of a group are 16-byte-SHIFTED, overlapping 32-byte windows of the same raw bytes — the
+// W-direction im2col of a stride-2 convolution over 8-byte RGBX pixels (output column w reads pixels 2w .. 2w+7) comes
+// for free from raw input rows (verified on B200 by tools/ubench/umma_overlap.cu).  high word: SBO, version, layout 0.
+__device__ __forceinline__ uint32_t umma_desc_hi_nosw(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+
 // Same, for an operand whose start is 128-byte aligned but not 1024-byte aligned (a row window of a
 // larger swizzled slab): base_offset (bits [49,52)) carries the phase of the swizzle pattern.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr, uint32_t use_base_offset) {

@@ -302,6 +302,11 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   uint2 iv[NA][2][2];
   uint4 dv[NA][2][2];
   uint4 pv[POOLED ? NA : 1][2][2];
+  // one 64-bit offset per tensor, the windows / patch elements are 32-bit strides away from it (the SASS of the first
+  // version spent 40 % of its 650 instructions on 64-bit index arithmetic; the kernel is issue bound)
+  const long long woff0 = (((static_cast<long long>(b) * g.To + qt) * g.Ho + qh) * g.Wo + qw) * g.C + c8 * 8;
+  const int wsW = g.C, wsH = g.Wo * g.C;
+  const long long wsT = static_cast<long long>(g.Ho) * wsH;
 #pragma unroll
   for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -310,7 +315,7 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
       for (int c = 0; c < 2; ++c) {
         const int to = qt - a, ho = qh - bb, wo = qw - c;
         const bool ok = to >= 0 && to < g.To && ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo;
-        const long long off = ((((static_cast<long long>(b) * g.To + to) * g.Ho + ho) * g.Wo + wo) * cg + c8) * 8;
+        const long long off = woff0 - (a ? wsT : 0) - (bb ? wsH : 0) - (c ? wsW : 0);
         iv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint2*>(idx + off)) : make_uint2(0xffffffffu, 0xffffffffu);
         dv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint4*>(dy + off)) : make_uint4(0u, 0u, 0u, 0u);
         if (POOLED) pv[a][bb][c] = ok ? __ldg(reinterpret_cast<const uint4*>(pooled + off)) : make_uint4(0u, 0u, 0u, 0u);
@@ -334,13 +339,14 @@ pool_s2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
     uint4 rv[2][2], av[2][2];
     long long eo[2][2];
     bool live[2][2];
+    const long long eo00 = (((static_cast<long long>(b) * g.T + t) * g.H + (2 * qh - g.ph)) * g.W + (2 * qw - g.pw)) * g.C + c8 * 8;
 #pragma unroll
     for (int eh = 0; eh < 2; ++eh)
 #pragma unroll
       for (int ew = 0; ew < 2; ++ew) {
         const int h = 2 * qh - g.ph + eh, w = 2 * qw - g.pw + ew;
         live[eh][ew] = h >= 0 && h < g.H && w >= 0 && w < g.W;
-        eo[eh][ew] = ((((static_cast<long long>(b) * g.T + t) * g.H + h) * g.W + w) * cg + c8) * 8;
+        eo[eh][ew] = eo00 + (eh ? g.W * g.C : 0) + (ew ? g.C : 0);
         rv[eh][ew] = (!POOLED && live[eh][ew] && relu_src) ? __ldg(reinterpret_cast<const uint4*>(relu_src + eo[eh][ew]))
                                                  : make_uint4(kF16One2, kF16One2, kF16One2, kF16One2);
         av[eh][ew] = (live[eh][ew] && addend) ? __ldg(reinterpret_cast<const uint4*>(addend + eo[eh][ew]))
