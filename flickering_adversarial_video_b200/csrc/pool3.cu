@@ -420,10 +420,11 @@ PoolTiling pick_tiling(int H, int W, int C, int max_threads, int max_tiled = 0) 
 // T segment length: one CTA streams `seg` output frames and reads seg + 2 input frames, and the grid runs in waves of
 // one CTA per SM, so the time is ~ waves x (seg + 2 + fixed cost).  Fewer, longer segments win whenever they remove a
 // mostly empty last wave (Mixed_3b backward: 192 CTAs = 2 waves of 10 frames -> 144 CTAs = 1 wave of 13).
+static int pool_threads();
 static int pick_tseg(int T, long long units_per_segment) {
   int dev = 0;
   cudaGetDevice(&dev);
-  const int sms = sm_count(dev);
+  const int sms = sm_count(dev) * (pool_threads() <= kPoolThreads / 2 ? 2 : 1);   // CTAs resident at once
   double best = 1e30;
   int best_seg = T;
   for (int seg = 2; seg <= T; ++seg) {
@@ -436,13 +437,24 @@ static int pick_tseg(int T, long long units_per_segment) {
   return best_seg;
 }
 
+// threads per CTA of the streaming kernels (<= kPoolThreads).  FAV_POOL_THREADS=400 lets two CTAs share an SM (each
+// waits at its own barriers) at the price of narrower tiles.
+static int pool_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* ev = getenv("FAV_POOL_THREADS");
+    v = ev ? std::max(128, std::min(kPoolThreads, atoi(ev))) : kPoolThreads;
+  }
+  return v;
+}
+
 bool pool3s1_applicable(const PoolGeom& g) {
   return g.kt == 3 && g.kh == 3 && g.kw == 3 && g.st == 1 && g.sh == 1 && g.sw == 1 &&
          pick_tiling(g.H, g.W, g.C, kPoolThreads).cgn > 0;
 }
 
 int launch_pool3s1_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom& g, cudaStream_t s) {
-  const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads, 1024);
+  const PoolTiling t = pick_tiling(g.H, g.W, g.C, pool_threads(), pool_threads() < kPoolThreads ? pool_threads() : 1024);
   FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
   const size_t smem = (static_cast<size_t>(t.R + 2 * t.halo) * (g.W + 2) + static_cast<size_t>(t.R + 2) * g.W) * t.cgn * 16;
@@ -460,7 +472,7 @@ int launch_pool3s1_fwd(const __half* x, __half* y, uint8_t* idx, const PoolGeom&
 
 int launch_pool3s1_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* addend,
                        const __half* relu_src, __nv_bfloat16* dx, const PoolGeom& g, cudaStream_t s) {
-  const PoolTiling t = pick_tiling(g.H, g.W, g.C, kPoolThreads);
+  const PoolTiling t = pick_tiling(g.H, g.W, g.C, pool_threads());
   FAV_CHECK_ARG(t.cgn > 0, "pool3s1: plane %dx%d with C=%d not supported", g.H, g.W, g.C);
   const int tseg = pick_tseg(g.T, static_cast<long long>(g.C / (8 * t.cgn)) * t.nth * g.B);
   const size_t smem = (static_cast<size_t>(t.R + 2) * g.W + static_cast<size_t>(t.R) * (g.W + 2)) * t.cgn * 16 +
