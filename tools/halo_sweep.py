@@ -20,6 +20,12 @@ CASES = [  # name, (T,H,W), cin, cout
     ("x.c64", (32, 28, 28), 64, 96),
     ("x.c128", (32, 28, 28), 128, 96),
     ("x.c16", (32, 28, 28), 16, 96),
+    ("y.n32", (32, 28, 28), 32, 32),
+    ("y.n64", (32, 28, 28), 32, 64),
+    ("y.n128", (32, 28, 28), 32, 128),
+    ("y.n192", (32, 28, 28), 32, 192),
+    ("y.k64n32", (32, 28, 28), 64, 32),
+    ("y.k64n192", (32, 28, 28), 64, 192),
 ]
 only = sys.argv[1:] or None
 g = torch.Generator(device="cuda").manual_seed(0)
