@@ -166,7 +166,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 6) {
     // ===================== TMA producer: this CTA's half (bn/2 rows) of every weight tile =====================
-    if (lane == 0) {
+    // The whole warp walks the ring; lanes 0..bgroup-1 issue the group's weight-tile loads in ONE instruction slot (a
+    // single lane pays ~100-150 cycles per cp.async.bulk.tensor it issues — tools/ubench/tma_rate.cu — and the pair
+    // kernel's MMA warp waited up to 40 % of its time for weight groups).
+    {
       int sb = 0;
       uint32_t pb = 0;
       for (int pt = pair; pt < total; pt += npairs) {
@@ -175,12 +178,15 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int cb = sidx / g.kt;
           const int dt = sidx - cb * g.kt;
           for (int j = 0; j < 9; j += g.bgroup) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
             const uint32_t lead = mapa_u32(smem_u32(&b_full[sb]), 0);
-            mbar_expect_tx_cluster(lead, static_cast<uint32_t>(b_bytes * g.bgroup));
-            for (int u = 0; u < g.bgroup; ++u) {
-              const int tap = dt * 9 + j + u;
-              tma_load_2d_pair(smem_b + (static_cast<size_t>(sb) * g.bgroup + u) * b_bytes, &tmB, lead,
+            if (lane == 0) {   // one lane polls (32 spinning lanes would compete with the MMA warp for issue slots)
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx_cluster(lead, static_cast<uint32_t>(b_bytes * g.bgroup));
+            }
+            __syncwarp();
+            if (lane < g.bgroup) {
+              const int tap = dt * 9 + j + lane;
+              tma_load_2d_pair(smem_b + (static_cast<size_t>(sb) * g.bgroup + lane) * b_bytes, &tmB, lead,
                                (tap * g.cblocks + cb) * 64, n0);
             }
             if (++sb == g.nb) { sb = 0; pb ^= 1; }

@@ -359,7 +359,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 6) {
     // ===================== TMA producer: weight tiles =====================
-    if (lane == 0) {
+    // the whole warp walks the ring; lanes 0..bgroup-1 issue the group's tile loads in one instruction slot (a single
+    // lane pays ~100-150 cycles per cp.async.bulk.tensor it issues: tools/ubench/tma_rate.cu)
+    {
       int sb = 0;
       uint32_t pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -368,11 +370,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int cb = sidx / g.kt;
           const int dt = sidx - cb * g.kt;
           for (int j = 0; j < 9; j += g.bgroup) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes * g.bgroup));
-            for (int u = 0; u < g.bgroup; ++u) {
-              const int tap = dt * 9 + j + u;
-              tma_load_2d(smem_b + (static_cast<size_t>(sb) * g.bgroup + u) * b_bytes, &tmB, &b_full[sb],
+            if (lane == 0) {   // one lane polls (32 spinning lanes would compete with the MMA warp for issue slots)
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes * g.bgroup));
+            }
+            __syncwarp();
+            if (lane < g.bgroup) {
+              const int tap = dt * 9 + j + lane;
+              tma_load_2d(smem_b + (static_cast<size_t>(sb) * g.bgroup + lane) * b_bytes, &tmB, &b_full[sb],
                           (tap * g.cblocks + cb) * 64, n0);
             }
             if (++sb == g.nb) { sb = 0; pb ^= 1; }
