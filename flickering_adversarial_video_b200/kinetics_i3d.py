@@ -66,7 +66,78 @@ def float_clip_to_u8(t, strict=True):
     return r.to(torch.uint8)
 
 
-class kinetics_i3d:
+class _KineticsGraph:
+    """What the two reference graph classes share (utils/kinetics_i3d_utils.py:76-307 and :308-521 repeat it verbatim):
+    the attribute handles of the last run, the loss selection, the clean / perturbed forward."""
+
+    def _init_common(self, ckpt_path, batch_size, frames, default_adv_flag_c, cyclic_flag_default_c, label_map_path,
+                     weights, seed, rgb_input, labels):
+        self.ckpt_path = ckpt_path
+        self.batch_size = batch_size
+        self.frames = frames
+        self.adv_flag = float(default_adv_flag_c)
+        self.cyclic_flag = float(cyclic_flag_default_c)
+        self.kinetics_classes = load_kinetics_classes(label_map_path=label_map_path)
+        self._rng = np.random.RandomState(seed)
+        self._loss_cfg = dict(improve=True, margin=0.05, targeted=False, logits=False)
+        self._last = {}
+        self.rgb_input = rgb_input
+        self.labels = labels
+        return load_weights(weights if weights is not None else ckpt_path)
+
+    # ---- the handles the drivers read (values of the last run) ------------------------------
+    @property
+    def eps_rgb(self):
+        return self._atk.perturbation.detach().cpu().numpy()
+
+    perturbation = eps_rgb
+
+    def __getattr__(self, name):
+        last = self.__dict__.get("_last", {})
+        if name in last:
+            return last[name]
+        raise AttributeError(name)
+
+    def get_kinetics_classes(self):
+        return self.kinetics_classes
+
+    # ---- loss selection (utils/kinetics_i3d_utils.py:253-307 / :467-521) ---------------------
+    def improve_adversarial_loss(self, margin=0.05, targeted=False, logits=False):
+        self._loss_cfg = dict(improve=True, margin=float(margin), targeted=bool(targeted), logits=bool(logits))
+        return "adversarial_loss_total"
+
+    def ce_adversarial_loss(self, targeted=False):
+        self._loss_cfg = dict(improve=False, margin=0.05, targeted=bool(targeted), logits=False)
+        return "adversarial_loss_total"
+
+    def _configure(self):
+        a, c = self._atk, self._loss_cfg
+        a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
+
+    def _prob_handles(self, probs, lab_np):
+        """label_prob, max_non_label_prob, to_min_prob, to_max_prob (utils/kinetics_i3d_utils.py:152-167)"""
+        label_prob = probs[np.arange(probs.shape[0]), lab_np]
+        onehot = np.eye(probs.shape[1], dtype=np.float32)[lab_np]
+        max_non_label_prob = (probs - onehot).max(-1)
+        tmin, tmax = (max_non_label_prob, label_prob) if self._loss_cfg["targeted"] else (label_prob, max_non_label_prob)
+        return label_prob, max_non_label_prob, tmin, tmax
+
+    def __call__(self, inputs, adv_flag=0):
+        """softmax for `inputs` (utils/kinetics_i3d_utils.py:210-212 / :424-426)."""
+        clips = self._to_device_clip(inputs)
+        self._last_clips = clips
+        self.prob = self._atk.predict(clips, adv_flag=float(adv_flag)).cpu().numpy()
+        return self.prob
+
+    def reset(self):
+        """sess.run(eps_rgb.initializer); sess.run(tf.variables_initializer(optimizer.variables()))"""
+        self._atk.reset()
+
+    def close(self):
+        self._atk.close()
+
+
+class kinetics_i3d(_KineticsGraph):
     """Drop-in for ki3du.kinetics_i3d(ckpt_path, batch_size, init_model, rgb_input, labels,
     cyclic_flag_default_c, cyclic_pert_flag_default_c, default_adv_flag_c)."""
 
@@ -76,30 +147,13 @@ class kinetics_i3d:
                  rgb_input=None, labels=None, cyclic_flag_default_c=0.0, cyclic_pert_flag_default_c=0.0,
                  default_adv_flag_c=1.0, frames=_SAMPLE_VIDEO_FRAMES, weights=None, device=0,
                  label_map_path=_LABEL_MAP_PATH, seed=0, sharded=True, frame_range=None):
-        self.ckpt_path = ckpt_path
-        self.batch_size = batch_size
-        self.frames = frames
-        self.adv_flag = float(default_adv_flag_c)
-        self.cyclic_flag = float(cyclic_flag_default_c)
+        w = self._init_common(ckpt_path, batch_size, frames, default_adv_flag_c, cyclic_flag_default_c, label_map_path,
+                              weights, seed, rgb_input, labels)
         self.cyclic_pert_flag = float(cyclic_pert_flag_default_c)
-        self.kinetics_classes = load_kinetics_classes(label_map_path=label_map_path)
-        w = load_weights(weights if weights is not None else ckpt_path)
         # sharded=False: a per-rank replica (single-video attacks under torchrun), never joins a collective
         # frame_range = (_IND_START, _IND_END) of utils/kinetics_i3d_utils.py:14-15 (module constants there); None = all frames
         self._atk = FlickerAttack(w, batch_size, frames, {}, device=device, sharded=sharded, frame_range=frame_range)
         self.device = self._atk.device
-        self._rng = np.random.RandomState(seed)
-        self._loss_cfg = dict(improve=True, margin=0.05, targeted=False, logits=False)
-        self._last = {}
-        self.rgb_input = rgb_input
-        self.labels = labels
-
-    # ---- the handles the drivers read (values of the last run) ------------------------------
-    @property
-    def eps_rgb(self):
-        return self._atk.perturbation.detach().cpu().numpy()
-
-    perturbation = eps_rgb
 
     def _clips_of_last_run(self):
         clips = self.__dict__.get("_last_clips")
@@ -120,28 +174,6 @@ class kinetics_i3d:
     def set_perturbation(self, value):
         self._atk.delta.copy_(torch.as_tensor(np.asarray(value), dtype=torch.float32).reshape(self.frames, 3))
 
-    def __getattr__(self, name):
-        last = self.__dict__.get("_last", {})
-        if name in last:
-            return last[name]
-        raise AttributeError(name)
-
-    def get_kinetics_classes(self):
-        return self.kinetics_classes
-
-    # ---- loss selection (utils/kinetics_i3d_utils.py:253-307) --------------------------------
-    def improve_adversarial_loss(self, margin=0.05, targeted=False, logits=False):
-        self._loss_cfg = dict(improve=True, margin=float(margin), targeted=bool(targeted), logits=bool(logits))
-        return "adversarial_loss_total"
-
-    def ce_adversarial_loss(self, targeted=False):
-        self._loss_cfg = dict(improve=False, margin=0.05, targeted=bool(targeted), logits=False)
-        return "adversarial_loss_total"
-
-    def _configure(self):
-        a, c = self._atk, self._loss_cfg
-        a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
-
     def _to_device_clip(self, inputs):
         """uint8 clips go to the device as they are.  Float clips that lie on the reference's grid u/128 - 1
         (parse_example_uint8, utils/pre_process_rgb_flow.py:234 — every clip its loaders produce) are turned back
@@ -158,13 +190,6 @@ class kinetics_i3d:
         return t.to(self.device, non_blocking=True).contiguous()
 
     # ---- sess.run equivalents ----------------------------------------------------------------
-    def __call__(self, inputs, adv_flag=0):
-        """softmax for `inputs` (utils/kinetics_i3d_utils.py:210-212)."""
-        clips = self._to_device_clip(inputs)
-        self._last_clips = clips
-        self.prob = self._atk.predict(clips, adv_flag=float(adv_flag)).cpu().numpy()
-        return self.prob
-
     def train_step(self, inputs, labels, learning_rate=1e-3, beta_0=1.0, beta_1=0.1, beta_2=0.1, beta_3=0.1,
                    cyclic_flag=None, cyclic_pert_flag=None, adv_flag=None):
         """One `sess.run([train_op, loss, adversarial_loss, regularizer_loss, norm_reg, diff_norm_reg,
@@ -196,10 +221,7 @@ class kinetics_i3d:
         probs = a.eng.probs.cpu().numpy()
         reg = beta_1 * sc[L.S_NORM_REG] + beta_2 * sc[L.S_DIFF_REG] + beta_3 * sc[L.S_LAP_REG]
         lab_np = lab.cpu().numpy()
-        label_prob = probs[np.arange(B), lab_np]
-        onehot = np.eye(probs.shape[1], dtype=np.float32)[lab_np]
-        max_non_label_prob = (probs - onehot).max(-1)
-        tmin, tmax = (max_non_label_prob, label_prob) if self._loss_cfg["targeted"] else (label_prob, max_non_label_prob)
+        label_prob, max_non_label_prob, tmin, tmax = self._prob_handles(probs, lab_np)
         self._last = dict(
             loss=float(sc[L.S_ADV_LOSS] + beta_0 * reg), adversarial_loss=float(sc[L.S_ADV_LOSS]),
             adversarial_loss_total=float(sc[L.S_ADV_LOSS]), regularizer_loss=float(reg),
@@ -222,10 +244,6 @@ class kinetics_i3d:
     def adversarial_video_uint8(self, inputs):
         """((adv+1.0)*127.5).astype(uint8) — utils/stats_and_plot/stats_plots.py:57, bit-exact."""
         return self._atk.adversarial_video(self._to_device_clip(inputs), as_uint8=True).cpu().numpy()
-
-    def reset(self):
-        """sess.run(eps_rgb.initializer); sess.run(tf.variables_initializer(optimizer.variables()))"""
-        self._atk.reset()
 
     def evaluate(self, next_element_val, targeted_attack=False, target_class_id=None, cyclic=0,
                  exclude_misclassify=True):
@@ -251,11 +269,8 @@ class kinetics_i3d:
             miss, total = fdist.sum_counts((miss, total), device=a.device, group=a.pg)
         return (miss / total if total else 0.0), int(total)
 
-    def close(self):
-        self._atk.close()
 
-
-class kinetics_i3d_L12:
+class kinetics_i3d_L12(_KineticsGraph):
     """Drop-in for ki3du.kinetics_i3d_L12(ckpt_path, batch_size, init_model, rgb_input, labels,
     cyclic_flag_default_c, default_adv_flag_c): the sparse per-pixel baseline (utils/kinetics_i3d_utils.py:308-521,
     FLICKERING_ATTACK=False).  eps_rgb is [T,224,224,3], initialised to 1e-8 (:333), not clipped (:336); the drivers
@@ -269,49 +284,10 @@ class kinetics_i3d_L12:
                  frames=_SAMPLE_VIDEO_FRAMES, weights=None, device=0, label_map_path=_LABEL_MAP_PATH, seed=0,
                  sharded=True):
         from .attack import SparseAttack
-        self.ckpt_path = ckpt_path
-        self.batch_size = batch_size
-        self.frames = frames
-        self.adv_flag = float(default_adv_flag_c)
-        self.cyclic_flag = float(cyclic_flag_default_c)
-        self.kinetics_classes = load_kinetics_classes(label_map_path=label_map_path)
-        w = load_weights(weights if weights is not None else ckpt_path)
+        w = self._init_common(ckpt_path, batch_size, frames, default_adv_flag_c, cyclic_flag_default_c, label_map_path,
+                              weights, seed, rgb_input, labels)
         self._atk = SparseAttack(w, batch_size, frames, {}, device=device, sharded=sharded)
         self.device = self._atk.device
-        self._rng = np.random.RandomState(seed)
-        self._loss_cfg = dict(improve=True, margin=0.05, targeted=False, logits=False)
-        self._last = {}
-        self.rgb_input = rgb_input
-        self.labels = labels
-
-    @property
-    def eps_rgb(self):
-        return self._atk.perturbation.detach().cpu().numpy()
-
-    perturbation = eps_rgb
-
-    def __getattr__(self, name):
-        last = self.__dict__.get("_last", {})
-        if name in last:
-            return last[name]
-        raise AttributeError(name)
-
-    def get_kinetics_classes(self):
-        return self.kinetics_classes
-
-    def improve_adversarial_loss(self, margin=0.05, targeted=False, logits=False):
-        """utils/kinetics_i3d_utils.py:467-493"""
-        self._loss_cfg = dict(improve=True, margin=float(margin), targeted=bool(targeted), logits=bool(logits))
-        return "adversarial_loss_total"
-
-    def ce_adversarial_loss(self, targeted=False):
-        """utils/kinetics_i3d_utils.py:495-521"""
-        self._loss_cfg = dict(improve=False, margin=0.05, targeted=bool(targeted), logits=False)
-        return "adversarial_loss_total"
-
-    def _configure(self):
-        a, c = self._atk, self._loss_cfg
-        a.improve_loss, a.margin, a.targeted, a.use_logits = c["improve"], c["margin"], c["targeted"], c["logits"]
 
     def _to_device_clip(self, inputs):
         """The sparse engine path takes uint8 clips (its backward re-derives the range-clip mask from them).  The
@@ -323,11 +299,6 @@ class kinetics_i3d_L12:
             t = float_clip_to_u8(t.to(torch.float32), strict=True)
         t = t.reshape(self.batch_size, self.frames, _IMAGE_SIZE, _IMAGE_SIZE, 3)
         return t.to(self.device, non_blocking=True).contiguous()
-
-    def __call__(self, inputs, adv_flag=0):
-        """softmax for `inputs` (utils/kinetics_i3d_utils.py:424-426)."""
-        self.prob = self._atk.predict(self._to_device_clip(inputs), adv_flag=float(adv_flag)).cpu().numpy()
-        return self.prob
 
     def train_step(self, inputs, labels, learning_rate=1e-3, beta_1=0.5, cyclic_flag=None, adv_flag=None):
         """One `sess.run([train_op, loss, adversarial_loss, regularizer_loss, thickness, roughness, ...])` with
@@ -346,10 +317,7 @@ class kinetics_i3d_L12:
         logits = a.eng.logits.cpu().numpy()
         probs = a.eng.probs.cpu().numpy()
         lab_np = lab.cpu().numpy()
-        label_prob = probs[np.arange(B), lab_np]
-        onehot = np.eye(probs.shape[1], dtype=np.float32)[lab_np]
-        max_non_label_prob = (probs - onehot).max(-1)
-        tmin, tmax = (max_non_label_prob, label_prob) if self._loss_cfg["targeted"] else (label_prob, max_non_label_prob)
+        label_prob, max_non_label_prob, tmin, tmax = self._prob_handles(probs, lab_np)
         l12 = float(sc[L.S_NORM_REG])            # fav_pixels_update: FAV_S_NORM_REG <- loss_L12
         self._last = dict(
             loss=float(sc[L.S_TOTAL_LOSS]), adversarial_loss=float(sc[L.S_ADV_LOSS]),
@@ -384,6 +352,3 @@ class kinetics_i3d_L12:
         if self._atk.world > 1:
             miss, total = fdist.sum_counts((miss, total), device=self._atk.device, group=self._atk.pg)
         return (miss / total if total else 0.0), int(total)
-
-    def close(self):
-        self._atk.close()
