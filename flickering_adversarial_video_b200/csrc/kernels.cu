@@ -3,6 +3,8 @@
 #include "kernels.cuh"
 
 #include <math.h>
+#include <algorithm>
+#include <stdlib.h>
 
 namespace fav {
 
@@ -100,6 +102,153 @@ apply_f32in_kernel(const float* __restrict__ clip, const float* __restrict__ del
 #pragma unroll
     for (int i = 0; i < 12; ++i) df[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
   }
+}
+
+// ---- table-driven variant of the hot path (uint8 clip, no adversarial-video output) -------------------------------
+// ncu on apply_u8_kernel (profiles/r02_final_ncu_table.md): 60 % of the HBM peak with 68 % of the issue slots busy —
+// ~50 instructions per pixel of float arithmetic on values that only depend on (frame, channel, uint8 level).  One
+// CTA works inside ONE frame, so the whole map level -> (fp16 stem operand, pass bit) is a 3 x 256-entry table it
+// builds once with exactly the arithmetic of the direct kernel (the two formulas below are the ones above, entry by
+// entry); a pixel then costs three shared-memory lookups and a handful of byte permutes.  Entry: fp16 bits of x' in
+// the low half, pass bit of channel c at bit 16 + c.
+template <bool kTorch>
+__device__ __forceinline__ uint32_t apply_lut_entry(int u8, int c, float dc, const fav_norm_params& nrm) {
+  const float u = static_cast<float>(u8);
+  float q;
+  bool sat;
+  if (!kTorch) {
+    const float x = __fsub_rn(__fmul_rn(u, 0.0078125f), 1.0f);
+    const float s = __fadd_rn(x, dc);
+    const float av = fminf(fmaxf(s, -1.0f), 1.0f);
+    sat = (s < -1.0f) || (s > 1.0f);
+    q = sat ? __fsub_rn(av, dc) : x;
+  } else {
+    const float x = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), nrm.mean[c]), nrm.std[c]);
+    const float sv = __fadd_rn(x, dc);
+    const float av = fminf(fmaxf(sv, nrm.lo), nrm.hi);
+    sat = (sv < nrm.lo) || (sv > nrm.hi);
+    q = (sat ? ((av - dc) * nrm.std[c] + nrm.mean[c]) * 255.0f : u) - 128.0f;   // centred uint8 units
+  }
+  return (pack_f16x2(q, 0.0f) & 0xffffu) | (sat ? 0u : (1u << (16 + c)));
+}
+
+constexpr int kLutWarps = 6;
+template <bool kTorch>
+__global__ void __launch_bounds__(kLutWarps * 32, 4)
+apply_u8_lut_kernel(const uint8_t* __restrict__ clip, const float* __restrict__ delta, float adv_flag, float dclip,
+                    const fav_norm_params nrm, __half* __restrict__ xpad, int Wp, int padl,
+                    uint32_t* __restrict__ pass_bits, int T, int H, int W, int chunks_per_frame) {
+  __shared__ uint32_t lut[3 * 256];
+  __shared__ uint4 s_in[kLutWarps][96];
+  __shared__ uint4 s_out[kLutWarps][32 * 9];
+  pdl_sync();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bt = blockIdx.y;                      // frame index b*T + t
+  const int t = static_cast<int>(bt % T);
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    const int c = i >> 8;
+    const float dcl = fminf(fmaxf(__ldg(delta + t * 3 + c), -dclip), dclip);
+    const float dc = kTorch ? __fdiv_rn(__fmul_rn(adv_flag, dcl), nrm.std[c]) : __fmul_rn(adv_flag, dcl);
+    lut[i] = apply_lut_entry<kTorch>(i & 255, c, dc, nrm);
+  }
+  __syncthreads();
+  const int HW = H * W;
+  uint4* in = s_in[warp];
+  uint4* out = s_out[warp];
+  const uint32_t lut_base = static_cast<uint32_t>(__cvta_generic_to_shared(lut));
+  // chunks of 512 pixels of this frame, dealt round-robin to the warps of the CTAs that share the frame
+  for (int chunk = blockIdx.x * kLutWarps + warp; chunk < chunks_per_frame; chunk += gridDim.x * kLutWarps) {
+    const int q0 = chunk * 512;                          // first pixel of the chunk inside the frame
+    const int left = HW - q0;
+    const int nv = left < 512 ? left : 512;              // a multiple of 16 (W % 16 == 0)
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(clip + (bt * HW + q0) * 3);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int i = j * 32 + lane;
+        if (i * 16 < nv * 3) in[i] = __ldg(src + i);
+      }
+    }
+    __syncwarp();
+    const bool active = lane * 16 < nv;
+    const int qp = q0 + lane * 16;
+    const int h = qp / W;
+    const int w0 = qp - h * W;
+    const long long dst_off = ((bt * H + h) * Wp + padl + w0) * 4;
+    uint32_t xq[32], pw0 = 0, pw1 = 0;
+    if (active) {
+      uint32_t wds[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint4 v = in[lane * 3 + i];
+        wds[4 * i] = v.x; wds[4 * i + 1] = v.y; wds[4 * i + 2] = v.z; wds[4 * i + 3] = v.w;
+      }
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        uint32_t ent[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int e = 3 * p + c;
+          const uint32_t byte4 = ((wds[e >> 2] >> (8 * (e & 3))) & 0xffu) << 2;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ent[c]) : "r"(lut_base + c * 1024u + byte4));
+        }
+        xq[2 * p] = __byte_perm(ent[0], ent[1], 0x5410);
+        xq[2 * p + 1] = ent[2] & 0xffffu;
+        const uint32_t nib = ((ent[0] | ent[1] | ent[2]) >> 16) & 7u;
+        if (p < 8) pw0 |= nib << (4 * p); else pw1 |= nib << (4 * (p - 8));
+      }
+    }
+    if (!kTorch) {
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[lane * 9 + i] = make_uint4(xq[4 * i], xq[4 * i + 1], xq[4 * i + 2], xq[4 * i + 3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = j * 32 + lane;
+        const int L = i >> 3, part = i & 7;
+        const long long off = __shfl_sync(0xffffffffu, dst_off, L);
+        if (L * 16 < nv) *reinterpret_cast<uint4*>(xpad + off + part * 8) = out[L * 9 + part];
+      }
+    } else {
+      uint2* out2 = reinterpret_cast<uint2*>(out);
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out2[lane * 17 + i] = make_uint2(xq[2 * i], xq[2 * i + 1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = j * 32 + lane;
+        const int L = i >> 4, part = i & 15;
+        const long long off = __shfl_sync(0xffffffffu, dst_off, L);
+        if (L * 16 < nv) *reinterpret_cast<uint2*>(xpad + off + part * 4) = out2[L * 17 + part];
+      }
+    }
+    if (pass_bits && active) {
+      uint32_t* dstb = pass_bits + (bt * (H + 7) + h + 3) * ((((W + 16) >> 3) + 3) & ~3) + 1 + (w0 >> 3);
+      dstb[0] = pw0;
+      dstb[1] = pw1;
+    }
+    __syncwarp();
+  }
+}
+
+// grid of the table-driven kernel: enough CTAs per frame that the table (768 entries) costs < 10 % of the pixel work
+static dim3 apply_lut_grid(int B, int T, int H, int W, int* chunks_per_frame) {
+  const int chunks = ceil_div(H * W, 512);
+  *chunks_per_frame = chunks;
+  const int per_cta = 2 * kLutWarps;                    // two 512-pixel chunks per warp
+  return dim3(static_cast<unsigned>(std::max(1, ceil_div(chunks, per_cta))), static_cast<unsigned>(B * T), 1);
+}
+// Measured (B200, bench.py kernels.apply): torch stack 16 x 16 x 112^2: 36 -> 25 us (its normalisation has three
+// divisions per entry); TF stack 8 x 64 x 224^2: 69 -> 75 us (the direct arithmetic is cheap there and the lookups pay
+// ~3-way bank conflicts) — so the table is the default for the torch stack only.  FAV_APPLY_LUT=0 / 1 forces either
+// kernel (bit-identity test); read per call.
+static bool apply_use_lut(bool torch_stack) {
+  const char* ev = getenv("FAV_APPLY_LUT");
+  return ev ? atoi(ev) != 0 : torch_stack;
 }
 
 // uint8 clips, both stacks.  One warp owns 512 consecutive pixels: the 1536 input bytes arrive as three fully coalesced
@@ -281,7 +430,12 @@ int launch_apply(const void* clip, int in_dtype, const float* delta, float adv_f
     if (adv_u8 || adv_f32)
       FAV_CUDA(launch_pdl(apply_u8_kernel<false, true>, grid, kApplyWarps * 32, 0, s, static_cast<const uint8_t*>(clip), delta,
                           adv_flag, delta_clip, none, xpad, Wp, padl, adv_u8, adv_f32, pass_bits, T, H, W, npix));
-    else
+    else if (apply_use_lut(false) && B * T <= 65535) {
+      int cpf = 0;
+      const dim3 g2 = apply_lut_grid(B, T, H, W, &cpf);
+      FAV_CUDA(launch_pdl(apply_u8_lut_kernel<false>, g2, kLutWarps * 32, 0, s, static_cast<const uint8_t*>(clip), delta, adv_flag,
+                          delta_clip, none, xpad, Wp, padl, pass_bits, T, H, W, cpf));
+    } else
       FAV_CUDA(launch_pdl(apply_u8_kernel<false, false>, grid, kApplyWarps * 32, 0, s, static_cast<const uint8_t*>(clip), delta,
                           adv_flag, delta_clip, none, xpad, Wp, padl, adv_u8, adv_f32, pass_bits, T, H, W, npix));
   }
@@ -360,7 +514,12 @@ int launch_apply_torch(const uint8_t* clip, const float* delta, float adv_flag, 
   if (adv_f32)
     apply_u8_kernel<true, true><<<grid, kApplyWarps * 32, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm, xpad, Wp, padl,
                                                                   nullptr, adv_f32, pass_bits, T, H, W, npix);
-  else
+  else if (apply_use_lut(true) && B * T <= 65535) {
+    int cpf = 0;
+    const dim3 g2 = apply_lut_grid(B, T, H, W, &cpf);
+    apply_u8_lut_kernel<true><<<g2, kLutWarps * 32, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm, xpad, Wp, padl, pass_bits, T,
+                                                            H, W, cpf);
+  } else
     apply_u8_kernel<true, false><<<grid, kApplyWarps * 32, 0, s>>>(clip, delta, adv_flag, delta_clip, nrm, xpad, Wp, padl,
                                                                    nullptr, nullptr, pass_bits, T, H, W, npix);
   FAV_COUNT_LAUNCH();

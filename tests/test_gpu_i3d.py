@@ -371,3 +371,38 @@ def test_pool_backward_mask_from_pooled_output_is_bit_identical(setup, monkeypat
             assert float((a - b).norm() / b.norm()) < 1e-5, name
         else:
             assert torch.equal(a, b), f"{name}: {int((a != b).sum())} of {a.numel()} entries differ"
+
+
+@pytest.mark.parametrize("arch", ["i3d", "r3d_18"])
+def test_table_driven_apply_is_bit_identical(setup, monkeypatch, arch):
+    """The hot-path apply kernel looks the stem operand and the pass bit of every (frame, channel, uint8 level) up in
+    a 3 x 256 table built per CTA with the arithmetic of the direct kernel.  FAV_APPLY_LUT=0 runs the direct float
+    kernel: stem output and dL/d-delta must agree bit for bit on a heavily saturated clip, both stacks."""
+    from flickering_adversarial_video_b200 import synthetic
+    from flickering_adversarial_video_b200 import _lib as L
+    from flickering_adversarial_video_b200.engine import FlickerEngine
+    B, T = 2, 16
+    if arch == "i3d":
+        eng, side, name, C, stride_t = setup["eng"], 224, "Conv3d_1a_7x7", 64, 2
+        clip = synthetic.clips_u8_extreme(B, T).cuda()
+        delta, clipv, kw = synthetic.delta_uniform(T, seed=8).cuda(), 0.4, {}
+    else:
+        eng, side, name, C, stride_t = FlickerEngine(B, T, arch=arch), 112, "stem.conv", 64, 1
+        eng.load_weights(synthetic.resnet_model(arch, seed=0).state_dict())
+        clip = synthetic.clips_u8_extreme(B, T, 112, 112).cuda()
+        delta, clipv, kw = synthetic.delta_uniform(T, seed=8, lo=-0.15, hi=0.15).cuda(), 0.1, dict(stack=L.FAV_STACK_TORCH)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FAV_APPLY_LUT", flag)
+        eng.apply(clip, delta, delta_clip=clipv)
+        labels = eng.forward().argmax(-1).clone()
+        y1 = eng.read(name, (B, T // stride_t, side // 2, side // 2, C)).clone()
+        eng.loss(labels, improve_loss=True, margin=0.05, **kw)
+        g = eng.backward().clone()
+        outs.append((y1, eng.logits.clone(), g))
+    assert float(outs[0][0].abs().max()) > 0 and float(outs[0][2].abs().max()) > 0
+    assert torch.equal(outs[0][0], outs[1][0]), "stem output differs between the table-driven and the direct apply kernel"
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert float((outs[0][2] - outs[1][2]).norm() / outs[1][2].norm()) < 1e-5     # collapse flushes with atomics
+    if arch != "i3d":
+        eng.close()
