@@ -18,16 +18,18 @@ def normalize_u8(clips_u8):
 
 
 def attack_step(model, clips_u8, labels, delta_t3, max_norm=0.1, beta_1=0.5, lambda_=1.0, margin=0.05,
-                improve_loss=True, use_logits=False, lr=1e-3, opt=None, endpoints=None):
+                improve_loss=True, use_logits=False, lr=1e-3, opt=None, endpoints=None, data_grad_only=False):
     """One iteration of the reference's loop (model.py:697-735): adversarial forward, Losses, backward
-    to the perturbation, Adam.  delta_t3 is [T,3] (the engine's layout of the reference's [3,T,1,1])."""
+    to the perturbation, Adam.  delta_t3 is [T,3] (the engine's layout of the reference's [3,T,1,1]).  Runs on the
+    device of its inputs (the BASELINE-shape GPU tests run this same code in strict fp32 on cuda); data_grad_only skips
+    the regulariser backward and the Adam step."""
     T = delta_t3.shape[0]
     x = normalize_u8(clips_u8)
     pert = delta_t3.t().reshape(3, T, 1, 1).clone().requires_grad_(True)
     pc = pert.clamp(-max_norm, max_norm)
     pc.retain_grad()
     lo, hi = ots.value_bounds()
-    std = torch.tensor(ots.DEFAULT_STD, dtype=torch.float32).reshape(3, 1, 1, 1)
+    std = torch.tensor(ots.DEFAULT_STD, dtype=torch.float32, device=x.device).reshape(3, 1, 1, 1)
     adv = (x + pc / std).clamp(lo, hi)
     hooks = []
     if endpoints is not None:
@@ -46,6 +48,9 @@ def attack_step(model, clips_u8, labels, delta_t3, max_norm=0.1, beta_1=0.5, lam
     loss, adv_loss, reg_loss = ots.losses(labels, logits, prob, pc, beta_1, lambda_, margin, improve_loss, use_logits)
     adv_loss.backward(retain_graph=True)
     grad_data = pc.grad.detach().reshape(3, T).t().clone()          # d adv_loss / d clamped delta, [T,3]
+    if data_grad_only:
+        return dict(adv=adv.detach(), logits=logits.detach(), prob=prob.detach(), adv_loss=float(adv_loss),
+                    grad_data=grad_data)
     pert.grad = None
     pc.grad = None
     loss.backward()
