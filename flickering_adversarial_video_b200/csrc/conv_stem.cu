@@ -393,6 +393,264 @@ conv_stem_raw_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Temporal-sharing variant.  The raw-row kernel above is bound by its A-operand reads: a 128x64x16 MMA needs 32 cycles of
+// the tensor pipe but reads 4 KB of A + 2 KB of B through the 128 B/clk shared-memory port (48 cycles; ncu: tensor pipe
+// 49 % busy).  An input frame feeds up to ceil(KT/st) output frames (t_in = st*t_o + kt - pt), each with its own kt tap —
+// so here ONE MMA multiplies a frame's row windows by the stacked weight sub-tiles of all those taps (N = up to 4 x 64)
+// and writes the TMEM accumulators of all those output frames at once: 4 KB of A per 128x256x16 MMA instead of per
+// 128x64x16, tensor-bound (128 cycles) instead of port-bound (4 x 48).
+//   tile       = 8 output columns x 16 output rows x G = 4 consecutive output frames (G accumulators of bn columns, x2 stages)
+//   A set      = the raw rows of the tile's input frames of one class c (frame index mod st; st*(G-1)+KT frames in all),
+//                loaded once per tile; two sets in flight
+//   weight ring= blocks of one (class, kh): the class's kt sub-tiles stacked by DESCENDING kt, so the sub-tiles of
+//                consecutive output frames j, j+1, ... (kt = dd - st*j) are consecutive rows of the B operand
+//   loop       = class -> kh -> frame -> K half; every weight block (12-16 KB from L2) serves 2 * frames MMAs
+// The first MMA that touches accumulator j is (class 0, kh 0, frame dd = st*j, K half 0) with j the TOP of the frame's
+// range: that MMA is split into an accumulating part and a fresh (accumulate = 0) part of N = bn.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kThreadsTs = 224;
+constexpr int kMaxW = 8;
+constexpr int kTsMaxFr = 7;   // input frames of one class per tile (st*(G-1)+KT frames over st classes)
+
+struct TsTile {
+  int b, t0, h0, w0;
+};
+__device__ __forceinline__ TsTile decode_ts_tile(const StemGeom& g, int tile) {
+  TsTile c;
+  const int wi = tile % g.tw;
+  int m = tile / g.tw;
+  const int hi = m % g.th;
+  m /= g.th;
+  c.t0 = (m % g.tp) * g.tsG;
+  c.b = m / g.tp;
+  c.h0 = hi * 16;
+  c.w0 = wi * 8;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreadsTs, 1)
+conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                    const __grid_constant__ CUtensorMap tmB1, const StemGeom g, const ConvEpilogue e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  // [weight ring: ts_nw x ts_wblk_bytes][A sets: 2 x ts_set_bytes][barriers][staging]
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + static_cast<size_t>(g.ts_nw) * g.ts_wblk_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * static_cast<size_t>(g.ts_set_bytes));
+  uint64_t* a_full = bars;                 // [2]
+  uint64_t* a_empty = bars + 2;            // [2]
+  uint64_t* w_full = bars + 4;             // [kMaxW]
+  uint64_t* w_empty = bars + 4 + kMaxW;    // [kMaxW]
+  uint64_t* tfull_bar = bars + 4 + 2 * kMaxW;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 4 + 2 * kMaxW + 6);   // 4 epilogue warps x 32 rows x 5 uint4
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int acc_cols = g.tsG * g.bn;
+  const int nclass = g.st;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&tmB1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < g.ts_nw; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer: the input frames of one class = one A set =====================
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pa = 0;
+      const uint32_t frame_tx = static_cast<uint32_t>((g.rows[0] + g.rows[1]) * g.pitch);
+      for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+        const TsTile tc = decode_ts_tile(g, tile);
+        for (int c = 0; c < nclass; ++c) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], frame_tx * static_cast<uint32_t>(g.ts_nfr[c]));
+          uint8_t* set = smem_a + static_cast<size_t>(sa) * g.ts_set_bytes;
+          for (int f = 0; f < g.ts_nfr[c]; ++f) {
+            const int t_in = g.st * tc.t0 - g.pt + c + f * g.st;   // may be < 0 or >= T: TMA zero fill
+            int par_t = 0, tcoord = t_in;
+            if (g.st == 2) {
+              par_t = t_in & 1;
+              tcoord = (t_in - par_t) >> 1;
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              if ((p ? g.rows[1] : g.rows[0]) == 0) continue;
+              const int mi = par_t * 2 + p;
+              const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+              tma_load_5d(set + static_cast<size_t>(f) * g.ts_slot_bytes + (p ? g.slab_off[1] : g.slab_off[0]), tm,
+                          &a_full[sa], 8 * tc.w0, tc.h0 + (p ? g.qmin[1] : g.qmin[0]), tcoord, tc.b, 0);
+            }
+          }
+          sa ^= 1;
+          if (sa == 0) pa ^= 1;
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== TMA producer: weight blocks, one per (class, kh) =====================
+    int sb = 0;
+    uint32_t pb = 0;
+    const uint32_t sub = static_cast<uint32_t>(g.bn) * 64u;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      for (int c = 0; c < nclass; ++c) {
+        for (int kh = 0; kh < g.KH; ++kh) {
+          if (lane == 0) {
+            mbar_wait(&w_empty[sb], pb ^ 1);
+            mbar_expect_tx(&w_full[sb], sub * static_cast<uint32_t>(g.ts_nslot[c]));
+          }
+          __syncwarp();
+          if (lane < g.ts_nslot[c]) {   // slot s holds tap kt = ktmax - s*st
+            const int kt = g.ts_ktmax[c] - lane * g.st;
+            tma_load_3d(smem_w + static_cast<size_t>(sb) * g.ts_wblk_bytes + static_cast<size_t>(lane) * sub, &tmB1,
+                        &w_full[sb], 0, 0, kt * g.KH + kh);
+          }
+          if (++sb == g.ts_nw) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The issuing thread is the critical resource (~45 cycles per tcgen05.mma, ~110 per barrier wait): the per-frame
+    // schedule (first output frame, top output frame, weight-row and accumulator-column offsets) comes from a table
+    // built by stem_plan, one packed word per frame, held in registers for the whole class.
+    const uint32_t hi_a = umma_desc_hi_nosw(static_cast<uint32_t>(g.pitch));
+    const uint32_t hi_b = umma_desc_hi(64);
+    const uint32_t sub16 = (static_cast<uint32_t>(g.bn) * 64u) >> 4;   // weight sub-tile in descriptor units
+    const uint32_t slot16 = static_cast<uint32_t>(g.ts_slot_bytes) >> 4;
+    const uint32_t idesc0 = umma_idesc(128, 0, true);
+    const uint32_t bn_n = static_cast<uint32_t>(g.bn >> 3) << 17;      // N field of the instruction descriptor per output frame
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      const int t0 = ((tile / (g.tw * g.th)) % g.tp) * g.tsG;
+      const int geff = min(g.tsG, g.To - t0);   // output frames of this tile that exist
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
+      for (int c = 0; c < nclass; ++c) {
+        uint32_t tab[kTsMaxFr];
+#pragma unroll
+        for (int f = 0; f < kTsMaxFr; ++f) tab[f] = g.ts_tab[c][f];
+        const int nfr = g.ts_nfr[c];
+        mbar_wait(&a_full[sa], pa);
+        const uint32_t set_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.ts_set_bytes));
+        for (int kh = 0; kh < g.KH; ++kh) {
+          const int offh = kh - g.ph;
+          const int p = offh & 1;
+          const int qh = (offh - p) >> 1;
+          const uint32_t a_kh = set_lo + (static_cast<uint32_t>((p ? g.slab_off[1] : g.slab_off[0]) +
+                                                                (qh - (p ? g.qmin[1] : g.qmin[0])) * g.pitch) >> 4);
+          const bool first = (c == 0) && (kh == 0);
+          mbar_wait(&w_full[sb], pb);
+          tc_fence_after();
+          const uint32_t wblk = umma_desc_lo(smem_u32(smem_w + static_cast<size_t>(sb) * g.ts_wblk_bytes));
+          if (elect_one()) {
+#pragma unroll
+            for (int f = 0; f < kTsMaxFr; ++f) {
+              if (f < nfr) {
+                // tab: jlo [0,4) | jtop [4,8) | accumulator column of jlo [8,18) | weight-row offset of jlo, 16-B units [18,32)
+                const int jlo = static_cast<int>(tab[f] & 15u);
+                const int jtop = static_cast<int>((tab[f] >> 4) & 15u);
+                const int n = min(jtop, geff - 1) - jlo + 1;
+                if (n > 0) {
+                  const uint32_t a_lo = a_kh + static_cast<uint32_t>(f) * slot16;
+                  const uint32_t b_lo = wblk + (tab[f] >> 18);
+                  const uint32_t d0 = d_tmem + ((tab[f] >> 8) & 1023u);
+                  const uint32_t idn = idesc0 + static_cast<uint32_t>(n) * bn_n;
+                  if (first && jtop <= geff - 1) {   // the top output frame's first tap (kt = 0): fresh accumulator
+                    if (n > 1) umma_bf16(d0, make_desc(hi_a, a_lo), make_desc(hi_b, b_lo), idn - bn_n, 1u);
+                    umma_bf16(d0 + static_cast<uint32_t>((n - 1) * g.bn), make_desc(hi_a, a_lo),
+                              make_desc(hi_b, b_lo + static_cast<uint32_t>(n - 1) * sub16), idesc0 + bn_n, 0u);
+                  } else {
+                    umma_bf16(d0, make_desc(hi_a, a_lo), make_desc(hi_b, b_lo), idn, 1u);
+                  }
+                  umma_bf16(d0, make_desc(hi_a, a_lo + 2), make_desc(hi_b, b_lo + 2), idn, 1u);
+                }
+              }
+            }
+            umma_commit(&w_empty[sb]);
+            if (kh == g.KH - 1) {
+              umma_commit(&a_empty[sa]);
+              if (c == nclass - 1) umma_commit(&tfull_bar[acc]);
+            }
+          }
+          __syncwarp();
+          if (++sb == g.ts_nw) { sb = 0; pb ^= 1; }
+        }
+        sa ^= 1;
+        if (sa == 0) pa ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5): G M tiles = G output frames of the 8 x 16 patch =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rw = row & 7;
+    const int rh = row >> 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
+      const TsTile tc = decode_ts_tile(g, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int h = tc.h0 + rh;
+      const int w = tc.w0 + rw;
+      for (int j = 0; j < g.tsG; ++j) {
+        const int t = tc.t0 + j;
+        if (t >= g.To) break;   // warp-uniform
+        const bool valid = (w < g.Wo) && (h < g.Ho);
+        const long long pos = valid ? ((static_cast<long long>(tc.b) * g.To + t) * g.Ho + h) * g.Wo + w : 0;
+        h16* out_row = e.out + pos * e.out_cs + e.out_coff;
+        const float* bias_row = nullptr;
+        if (e.bias) {
+          int br = 0;
+          if (e.bias_stem) {
+            const int hc = border_cls(min(h, g.Ho - 1), g.Ho, g.nlo_h, g.nhi_h);
+            const int wc = border_cls(min(w, g.Wo - 1), g.Wo, g.nlo_w, g.nhi_w);
+            br = (t * 4 + hc) * 4 + wc;
+          }
+          bias_row = e.bias + static_cast<long long>(br) * e.bias_ld;
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * acc_cols + j * g.bn);
+        epilogue_columns_staged(e, g.bn, 0, taddr, valid, out_row, bias_row, e.cout_store, stage_all + (warp - 2) * 160, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
@@ -408,6 +666,98 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
     const char* ev = getenv("FAV_STEM_RAW");   // 0: the im2col-tile kernel (A/B)
     g.raw = (ev && atoi(ev) == 0) ? 0 : 1;
     if (bn > 128) g.raw = 0;                    // four accumulators of bn columns, double-buffered
+  }
+  {
+    const char* ev = getenv("FAV_STEM_TS");    // 0: keep the raw-row kernel (A/B)
+    g.ts = (g.raw && !(ev && atoi(ev) == 0) && 4 * bn <= 256 && KT >= 2 * st && To >= 2) ? 1 : 0;
+  }
+  if (g.ts) {
+    g.tsG = 4;
+    g.tp = ceil_div(To, g.tsG);
+    g.th = ceil_div(Ho, 16);
+    g.tw = ceil_div(Wo, 8);
+    g.m_tiles = B * g.tp * g.th * g.tw;
+    g.mt = g.tsG;
+    {
+      const char* ev = getenv("FAV_STEM_TS_PITCH");
+      g.pitch = ev ? atoi(ev) : 176;            // 2*7 + 8 = 22 pixels of 8 B
+      FAV_CHECK_ARG(g.pitch >= 176 && g.pitch % 16 == 0 && g.pitch <= 512, "stem: bad FAV_STEM_TS_PITCH");
+    }
+    int qlo[2] = {1 << 20, 1 << 20}, qhi[2] = {-(1 << 20), -(1 << 20)};
+    for (int kh = 0; kh < KH; ++kh) {
+      const int offh = kh - ph;
+      const int p = offh & 1;
+      const int qh = (offh - p) / 2;
+      qlo[p] = std::min(qlo[p], qh);
+      qhi[p] = std::max(qhi[p], qh);
+    }
+    int off = 0;
+    for (int p = 0; p < 2; ++p) {
+      if (qhi[p] < qlo[p]) { g.qmin[p] = 0; g.rows[p] = 0; g.slab_off[p] = off; continue; }
+      g.qmin[p] = qlo[p];
+      g.rows[p] = 16 + (qhi[p] - qlo[p]);
+      g.slab_off[p] = off;
+      off += round_up(g.rows[p] * g.pitch, 128);
+    }
+    g.ts_slot_bytes = off;
+    const int nd = st * (g.tsG - 1) + KT;        // input frames per tile
+    int max_nfr = 0, max_slot = 0;
+    for (int c = 0; c < st; ++c) {
+      g.ts_nfr[c] = (nd - c + st - 1) / st;
+      g.ts_ktmax[c] = c + ((KT - 1 - c) / st) * st;
+      g.ts_nslot[c] = (g.ts_ktmax[c] - c) / st + 1;
+      max_nfr = std::max(max_nfr, g.ts_nfr[c]);
+      max_slot = std::max(max_slot, g.ts_nslot[c]);
+    }
+    FAV_CHECK_ARG(max_nfr <= kTsMaxFr, "stem: %d input frames per class", max_nfr);
+    for (int c = 0; c < st; ++c)
+      for (int f = 0; f < g.ts_nfr[c]; ++f) {
+        const int dd = c + f * st;                       // frame index inside the tile: kt of output frame j = dd - st*j
+        const int jtop = dd / st;
+        const int num = dd - KT + 1;
+        const int jlo = num > 0 ? (num + st - 1) / st : 0;
+        const int slot0 = (g.ts_ktmax[c] - dd) / st + jlo;   // exact: dd and ktmax are in the same class
+        g.ts_tab[c][f] = static_cast<uint32_t>(jlo) | (static_cast<uint32_t>(jtop) << 4) |
+                         (static_cast<uint32_t>(jlo * bn) << 8) | (static_cast<uint32_t>(slot0 * bn * 4) << 18);
+      }
+    g.ts_set_bytes = round_up(max_nfr * g.ts_slot_bytes, 1024);
+    g.ts_wblk_bytes = round_up(max_slot * bn * 64, 1024);
+    g.b_bytes = bn * 64;
+    const int fixed = 1024 + 2 * g.ts_set_bytes + 512 + 4 * 32 * 5 * 16;
+    g.ts_nw = std::min(kMaxW, (227 * 1024 - fixed) / g.ts_wblk_bytes);
+    FAV_CHECK_ARG(g.ts_nw >= 2, "stem: temporal-sharing stages do not fit (%d + %d x n)", fixed, g.ts_wblk_bytes);
+    L->smem_bytes = static_cast<size_t>(fixed) + static_cast<size_t>(g.ts_nw) * g.ts_wblk_bytes;
+    auto classes = [](int in, int out, int k, int s, int pad, int* nlo, int* nhi) {
+      *nlo = ceil_div(pad, s);
+      const int pad_after = std::max(0, (out - 1) * s + k - pad - in);
+      *nhi = ceil_div(pad_after, s);
+    };
+    classes(H, Ho, KH, 2, ph, &g.nlo_h, &g.nhi_h);
+    classes(2 * Wo, Wo, 7, 2, ph, &g.nlo_w, &g.nhi_w);
+    FAV_CHECK_ARG(g.nlo_h + g.nhi_h <= 3 && g.nlo_w + g.nhi_w <= 3, "stem: more than 4 border classes");
+    const uint64_t pos_bytes = 8;
+    const uint64_t row_pitch = static_cast<uint64_t>(Wp) * pos_bytes;
+    const uint64_t frame_pitch = row_pitch * H;
+    const uint64_t clip_pitch = frame_pitch * T;
+    for (int p_t = 0; p_t < 2; ++p_t)
+      for (int p_h = 0; p_h < 2; ++p_h) {
+        if (g.rows[p_h] == 0 || (st == 1 && p_t == 1)) { L->tmA[p_t * 2 + p_h] = L->tmA[0]; continue; }
+        // raw rows of one (T, H) parity: [Wp*4 elements][rows of this parity][frames of this parity][B][1]; one frame per box
+        uint64_t dims[5] = {static_cast<uint64_t>(Wp) * 4, static_cast<uint64_t>((H - p_h + 1) / 2),
+                            static_cast<uint64_t>(st == 2 ? (T - p_t + 1) / 2 : T), static_cast<uint64_t>(B), 1};
+        uint64_t strides[4] = {2 * row_pitch, st * frame_pitch, clip_pitch, clip_pitch * B};
+        uint32_t box[5] = {static_cast<uint32_t>(g.pitch / 2), static_cast<uint32_t>(g.rows[p_h]), 1, 1, 1};
+        const char* base = static_cast<const char*>(xpad) + (st == 2 ? p_t : 0) * frame_pitch + p_h * row_pitch;
+        FAV_TRY(make_tmap_bf16(&L->tmA[p_t * 2 + p_h], base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+      }
+    if (g.rows[0] == 0) L->tmA[0] = L->tmA[1];
+    uint64_t bd[3] = {32, static_cast<uint64_t>(bn), static_cast<uint64_t>(KT) * KH};
+    uint64_t bs[2] = {64, static_cast<uint64_t>(bn) * 64};
+    uint32_t bb[3] = {32, static_cast<uint32_t>(bn), 1};
+    FAV_TRY(make_tmap_bf16(&L->tmB1, wpk, 3, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_64B));
+    L->tmB = L->tmB1;
+    L->grid = std::max(1, std::min(g.m_tiles, sm_count(device)));
+    return FAV_OK;
   }
   if (g.raw) {
     g.nf = To >= 2 ? 2 : 1;
@@ -554,6 +904,18 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   ProfScope ps(PK_STEM, stream, L.flops);
+  if (L.g.ts) {
+    static bool attr_ts = false;
+    if (!attr_ts) {
+      FAV_CUDA(cudaFuncSetAttribute(conv_stem_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_ts = true;
+    }
+    FAV_CUDA(launch_pdl(conv_stem_ts_kernel, L.grid, kThreadsTs, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3],
+                        L.tmB1, L.g, L.e));
+    FAV_COUNT_LAUNCH();
+    FAV_CUDA(cudaGetLastError());
+    return FAV_OK;
+  }
   if (L.g.raw) {
     static bool attr_raw = false;
     if (!attr_raw) {

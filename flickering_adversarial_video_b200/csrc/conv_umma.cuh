@@ -321,10 +321,24 @@ struct StemGeom {
   int nf;                 // output frames per CTA tile (the mt = 2*nf M tiles of 8 columns x 16 rows share every weight load)
   int pitch;              // bytes per raw slab row (40 pixels x 8 B)
   int tp;                 // frame groups: ceil(To / nf)
+  // temporal-sharing variant (conv_stem_ts_kernel): one M tile = 8 columns x 16 rows of `tsG` consecutive output frames;
+  // every input frame's raw rows are read ONCE per (kh, K half) by an MMA whose N spans all output frames the frame
+  // feeds (N = up to tsG*bn <= 256).  Input frames of a tile fall into `st` classes (frame index mod st = kt mod st).
+  int ts;                 // 1: temporal-sharing kernel
+  int tsG;                // output frames per tile
+  int ts_nfr[2];          // input frames of each class per tile
+  int ts_nslot[2];        // kt taps of each class
+  int ts_ktmax[2];        // largest kt of each class
+  int ts_slot_bytes;      // bytes per input-frame slot (both H-parity slabs)
+  int ts_set_bytes;       // bytes per A set (the frames of one class)
+  int ts_wblk_bytes;      // bytes per weight block = the taps of one (class, kh): nslot x bn x 64 B
+  int ts_nw;              // weight ring depth
+  uint32_t ts_tab[2][8];  // per (class, frame): first / top output frame, accumulator column, weight-row offset (packed)
 };
 struct StemLaunch {
   CUtensorMap tmA[4];     // [T-parity][H-parity]
   CUtensorMap tmB;        // [32][cout][taps]
+  CUtensorMap tmB1;       // same tensor, one (kt,kh) sub-tile per box (temporal-sharing kernel)
   StemGeom g;
   ConvEpilogue e;
   size_t smem_bytes;
