@@ -20,6 +20,7 @@
 #include <algorithm>
 
 namespace fav {
+extern __device__ unsigned long long g_halo_prof[8];
 namespace {
 
 constexpr int kThreads = 192;
@@ -409,13 +410,19 @@ conv_stem_raw_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 // The first MMA that touches accumulator j is (class 0, kh 0, frame dd = st*j, K half 0) with j the TOP of the frame's
 // range: that MMA is split into an accumulating part and a fresh (accumulate = 0) part of N = bn.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kThreadsTs = 224;
+constexpr int kThreadsTs = 352;   // warp 0: A producer, 1: MMA issuer, 6: weight producer, 2..5 and 7..10: two epilogue sets
 constexpr int kMaxW = 8;
 constexpr int kTsMaxFr = 7;   // input frames of one class per tile (st*(G-1)+KT frames over st classes)
 
 struct TsTile {
   int b, t0, h0, w0;
 };
+// 64-bit descriptor from its two words without 64-bit arithmetic in the issue loop
+__device__ __forceinline__ uint64_t pack_desc(uint32_t hi, uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 __device__ __forceinline__ TsTile decode_ts_tile(const StemGeom& g, int tile) {
   TsTile c;
   const int wi = tile % g.tw;
@@ -447,7 +454,7 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* tfull_bar = bars + 4 + 2 * kMaxW;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint4* stage_all = reinterpret_cast<uint4*>(bars + 4 + 2 * kMaxW + 6);   // 4 epilogue warps x 32 rows x 5 uint4
+  uint4* stage_all = reinterpret_cast<uint4*>(bars + 4 + 2 * kMaxW + 6);   // 8 epilogue warps x 32 rows x 5 uint4
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -459,7 +466,7 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tma_prefetch_desc(&tmB1);
     for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < g.ts_nw; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -503,22 +510,25 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else if (warp == 6) {
-    // ===================== TMA producer: weight blocks, one per (class, kh) =====================
+    // ===================== TMA producer: weight blocks of ts_khg kh taps of one class =====================
     int sb = 0;
     uint32_t pb = 0;
     const uint32_t sub = static_cast<uint32_t>(g.bn) * 64u;
     for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
       for (int c = 0; c < nclass; ++c) {
-        for (int kh = 0; kh < g.KH; ++kh) {
+        const int nslot = g.ts_nslot[c];
+        for (int kh0 = 0; kh0 < g.KH; kh0 += g.ts_khg) {
+          const int nsub = min(g.ts_khg, g.KH - kh0) * nslot;   // sub-tiles of this block: [kh][slot], <= 32
           if (lane == 0) {
             mbar_wait(&w_empty[sb], pb ^ 1);
-            mbar_expect_tx(&w_full[sb], sub * static_cast<uint32_t>(g.ts_nslot[c]));
+            mbar_expect_tx(&w_full[sb], sub * static_cast<uint32_t>(nsub));
           }
           __syncwarp();
-          if (lane < g.ts_nslot[c]) {   // slot s holds tap kt = ktmax - s*st
-            const int kt = g.ts_ktmax[c] - lane * g.st;
+          if (lane < nsub) {   // slot s holds tap kt = ktmax - s*st
+            const int khi = lane / nslot;
+            const int kt = g.ts_ktmax[c] - (lane - khi * nslot) * g.st;
             tma_load_3d(smem_w + static_cast<size_t>(sb) * g.ts_wblk_bytes + static_cast<size_t>(lane) * sub, &tmB1,
-                        &w_full[sb], 0, 0, kt * g.KH + kh);
+                        &w_full[sb], 0, 0, kt * g.KH + kh0 + khi);
           }
           if (++sb == g.ts_nw) { sb = 0; pb ^= 1; }
         }
@@ -539,55 +549,94 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t pa = 0, pb = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_te = 0, w_a = 0, w_w = 0, c0 = 0;   // FAV_STEM_PROF: barrier wait cycles of this warp
+    const long long t_start = clock64();
     for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
       const int t0 = ((tile / (g.tw * g.th)) % g.tp) * g.tsG;
       const int geff = min(g.tsG, g.To - t0);   // output frames of this tile that exist
+      c0 = g.prof ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (g.prof) w_te += clock64() - c0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
       for (int c = 0; c < nclass; ++c) {
-        uint32_t tab[kTsMaxFr];
-#pragma unroll
-        for (int f = 0; f < kTsMaxFr; ++f) tab[f] = g.ts_tab[c][f];
+        // per-frame operands of this (tile, class), in registers: N (output frames fed), weight-row offset, accumulator
+        // address and instruction descriptor — the block loop below only adds the block's base addresses
+        int f_n[kTsMaxFr];
+        uint32_t f_b[kTsMaxFr], f_d[kTsMaxFr], f_i[kTsMaxFr];
+        bool f_fresh[kTsMaxFr];
         const int nfr = g.ts_nfr[c];
-        mbar_wait(&a_full[sa], pa);
-        const uint32_t set_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.ts_set_bytes));
-        for (int kh = 0; kh < g.KH; ++kh) {
-          const int offh = kh - g.ph;
-          const int p = offh & 1;
-          const int qh = (offh - p) >> 1;
-          const uint32_t a_kh = set_lo + (static_cast<uint32_t>((p ? g.slab_off[1] : g.slab_off[0]) +
-                                                                (qh - (p ? g.qmin[1] : g.qmin[0])) * g.pitch) >> 4);
-          const bool first = (c == 0) && (kh == 0);
-          mbar_wait(&w_full[sb], pb);
-          tc_fence_after();
-          const uint32_t wblk = umma_desc_lo(smem_u32(smem_w + static_cast<size_t>(sb) * g.ts_wblk_bytes));
-          if (elect_one()) {
 #pragma unroll
-            for (int f = 0; f < kTsMaxFr; ++f) {
-              if (f < nfr) {
-                // tab: jlo [0,4) | jtop [4,8) | accumulator column of jlo [8,18) | weight-row offset of jlo, 16-B units [18,32)
-                const int jlo = static_cast<int>(tab[f] & 15u);
-                const int jtop = static_cast<int>((tab[f] >> 4) & 15u);
-                const int n = min(jtop, geff - 1) - jlo + 1;
-                if (n > 0) {
-                  const uint32_t a_lo = a_kh + static_cast<uint32_t>(f) * slot16;
-                  const uint32_t b_lo = wblk + (tab[f] >> 18);
-                  const uint32_t d0 = d_tmem + ((tab[f] >> 8) & 1023u);
-                  const uint32_t idn = idesc0 + static_cast<uint32_t>(n) * bn_n;
-                  if (first && jtop <= geff - 1) {   // the top output frame's first tap (kt = 0): fresh accumulator
-                    if (n > 1) umma_bf16(d0, make_desc(hi_a, a_lo), make_desc(hi_b, b_lo), idn - bn_n, 1u);
-                    umma_bf16(d0 + static_cast<uint32_t>((n - 1) * g.bn), make_desc(hi_a, a_lo),
-                              make_desc(hi_b, b_lo + static_cast<uint32_t>(n - 1) * sub16), idesc0 + bn_n, 0u);
-                  } else {
-                    umma_bf16(d0, make_desc(hi_a, a_lo), make_desc(hi_b, b_lo), idn, 1u);
+        for (int f = 0; f < kTsMaxFr; ++f) {
+          // tab: jlo [0,4) | jtop [4,8) | accumulator column of jlo [8,18) | weight-row offset of jlo, 16-B units [18,32)
+          const uint32_t tab = g.ts_tab[c][f];
+          const int jlo = static_cast<int>(tab & 15u);
+          const int jtop = static_cast<int>((tab >> 4) & 15u);
+          const int n = f < nfr ? min(jtop, geff - 1) - jlo + 1 : 0;
+          f_n[f] = n;
+          f_b[f] = tab >> 18;
+          f_d[f] = d_tmem + ((tab >> 8) & 1023u);
+          f_i[f] = idesc0 + static_cast<uint32_t>(max(n, 1)) * bn_n;
+          f_fresh[f] = jtop <= geff - 1;   // at (class 0, kh 0) the top output frame's tap is kt = 0: fresh accumulator
+        }
+        c0 = g.prof ? clock64() : 0;
+        mbar_wait(&a_full[sa], pa);
+        if (g.prof) w_a += clock64() - c0;
+        const uint32_t set_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.ts_set_bytes));
+        const uint32_t kh16 = static_cast<uint32_t>(g.ts_nslot[c]) * sub16;   // one kh's sub-tiles inside a weight block
+        for (int kh0 = 0; kh0 < g.KH; kh0 += g.ts_khg) {
+          const int kh1 = min(g.KH, kh0 + g.ts_khg);
+          c0 = g.prof ? clock64() : 0;
+          mbar_wait(&w_full[sb], pb);
+          if (g.prof) w_w += clock64() - c0;
+          tc_fence_after();
+          uint32_t wblk = umma_desc_lo(smem_u32(smem_w + static_cast<size_t>(sb) * g.ts_wblk_bytes));
+          if (elect_one()) {
+            for (int kh = kh0; kh < kh1; ++kh, wblk += kh16) {
+              const int offh = kh - g.ph;
+              const int p = offh & 1;
+              const int qh = (offh - p) >> 1;
+              const uint32_t a_kh = set_lo + (static_cast<uint32_t>((p ? g.slab_off[1] : g.slab_off[0]) +
+                                                                    (qh - (p ? g.qmin[1] : g.qmin[0])) * g.pitch) >> 4);
+              if (g.prof & 4) {
+                // prof bit 2: timing without the MMAs
+              } else if (c == 0 && kh == 0) {
+                uint32_t a_lo = a_kh;
+#pragma unroll
+                for (int f = 0; f < kTsMaxFr; ++f) {
+                  const int n = f_n[f];
+                  if (n > 0) {
+                    const uint32_t b_lo = wblk + f_b[f];
+                    if (f_fresh[f]) {
+                      if (n > 1) umma_bf16(f_d[f], pack_desc(hi_a, a_lo), pack_desc(hi_b, b_lo), f_i[f] - bn_n, 1u);
+                      umma_bf16(f_d[f] + static_cast<uint32_t>((n - 1) * g.bn), pack_desc(hi_a, a_lo),
+                                pack_desc(hi_b, b_lo + static_cast<uint32_t>(n - 1) * sub16), idesc0 + bn_n, 0u);
+                    } else {
+                      umma_bf16(f_d[f], pack_desc(hi_a, a_lo), pack_desc(hi_b, b_lo), f_i[f], 1u);
+                    }
+                    umma_bf16(f_d[f], pack_desc(hi_a, a_lo + 2), pack_desc(hi_b, b_lo + 2), f_i[f], 1u);
                   }
-                  umma_bf16(d0, make_desc(hi_a, a_lo + 2), make_desc(hi_b, b_lo + 2), idn, 1u);
+                  a_lo += slot16;
+                }
+              } else {
+                // Narrow frames first, the widest last: between two blocks this thread spends ~400 cycles on the barrier
+                // hand-offs, and the MMAs still queued must keep the tensor pipe busy meanwhile (N = 256: 128 cycles
+                // each, N = 64: 51).  Any order is legal: every accumulator was initialised by the (class 0, kh 0) pass.
+                constexpr int order[kTsMaxFr] = {0, 6, 1, 5, 2, 4, 3};
+#pragma unroll
+                for (int u = 0; u < kTsMaxFr; ++u) {
+                  const int f = order[u];
+                  if (f_n[f] > 0) {
+                    const uint32_t a_lo = a_kh + static_cast<uint32_t>(f) * slot16;
+                    const uint32_t b_lo = wblk + f_b[f];
+                    umma_bf16(f_d[f], pack_desc(hi_a, a_lo), pack_desc(hi_b, b_lo), f_i[f], 1u);
+                    umma_bf16(f_d[f], pack_desc(hi_a, a_lo + 2), pack_desc(hi_b, b_lo + 2), f_i[f], 1u);
+                  }
                 }
               }
             }
             umma_commit(&w_empty[sb]);
-            if (kh == g.KH - 1) {
+            if (kh1 == g.KH) {
               umma_commit(&a_empty[sa]);
               if (c == nclass - 1) umma_commit(&tfull_bar[acc]);
             }
@@ -601,23 +650,36 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (g.prof && lane == 0) {
+      atomicAdd(&g_halo_prof[0], static_cast<unsigned long long>(w_te));
+      atomicAdd(&g_halo_prof[1], static_cast<unsigned long long>(w_a));
+      atomicAdd(&g_halo_prof[2], static_cast<unsigned long long>(w_w));
+      atomicAdd(&g_halo_prof[3], static_cast<unsigned long long>(clock64() - t_start));
+    }
   } else {
-    // ===================== epilogue (warps 2..5): G M tiles = G output frames of the 8 x 16 patch =====================
+    // ===================== epilogue: G M tiles = G output frames of the 8 x 16 patch =====================
+    // Two sets of four warps (one warp per TMEM lane quarter each): set 0 drains the even output frames, set 1 the odd
+    // ones (FAV_STEM_PROF: one set needs ~13 kcycles per tile, as long as the tile's MMAs).
+    const int eset = warp >= 7 ? 1 : 0;
+    const int ew = eset ? warp - 3 : warp - 2;   // staging slot 0..7
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int rw = row & 7;
     const int rh = row >> 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_tf = 0;
     for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
       const TsTile tc = decode_ts_tile(g, tile);
+      const long long c0 = g.prof ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (g.prof) w_tf += clock64() - c0;
       tc_fence_after();
       const int h = tc.h0 + rh;
       const int w = tc.w0 + rw;
-      for (int j = 0; j < g.tsG; ++j) {
+      for (int j = eset; j < g.tsG; j += 2) {
         const int t = tc.t0 + j;
-        if (t >= g.To) break;   // warp-uniform
+        if (t >= g.To || (g.prof & 2)) break;   // warp-uniform (prof bit 1: timing without the epilogue's work)
         const bool valid = (w < g.Wo) && (h < g.Ho);
         const long long pos = valid ? ((static_cast<long long>(tc.b) * g.To + t) * g.Ho + h) * g.Wo + w : 0;
         h16* out_row = e.out + pos * e.out_cs + e.out_coff;
@@ -633,7 +695,7 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * acc_cols + j * g.bn);
-        epilogue_columns_staged(e, g.bn, 0, taddr, valid, out_row, bias_row, e.cout_store, stage_all + (warp - 2) * 160, lane);
+        epilogue_columns_staged(e, g.bn, 0, taddr, valid, out_row, bias_row, e.cout_store, stage_all + ew * 160, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -641,6 +703,7 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (g.prof && warp == 2 && lane == 0) atomicAdd(&g_halo_prof[4], static_cast<unsigned long long>(w_tf));
   }
 
   tc_fence_before();
@@ -721,10 +784,18 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
                          (static_cast<uint32_t>(jlo * bn) << 8) | (static_cast<uint32_t>(slot0 * bn * 4) << 18);
       }
     g.ts_set_bytes = round_up(max_nfr * g.ts_slot_bytes, 1024);
-    g.ts_wblk_bytes = round_up(max_slot * bn * 64, 1024);
+    {
+      const char* ev = getenv("FAV_STEM_TS_KHG");   // kh taps per weight block (one barrier hand-off per block)
+      g.ts_khg = ev ? atoi(ev) : 3;      // measured (I3D 8 x 64): 1: 826, 2: 749, 3: 730 kcycles per CTA
+      FAV_CHECK_ARG(g.ts_khg >= 1 && g.ts_khg <= KH && g.ts_khg * max_slot <= 32, "stem: bad FAV_STEM_TS_KHG");
+    }
     g.b_bytes = bn * 64;
-    const int fixed = 1024 + 2 * g.ts_set_bytes + 512 + 4 * 32 * 5 * 16;
-    g.ts_nw = std::min(kMaxW, (227 * 1024 - fixed) / g.ts_wblk_bytes);
+    const int fixed = 1024 + 2 * g.ts_set_bytes + 512 + 8 * 32 * 5 * 16;   // alignment, A sets, barriers, epilogue staging
+    for (;; --g.ts_khg) {   // at least a double-buffered ring
+      g.ts_wblk_bytes = round_up(g.ts_khg * max_slot * bn * 64, 1024);
+      g.ts_nw = std::min(kMaxW, (227 * 1024 - fixed) / g.ts_wblk_bytes);
+      if (g.ts_nw >= 2 || g.ts_khg == 1) break;
+    }
     FAV_CHECK_ARG(g.ts_nw >= 2, "stem: temporal-sharing stages do not fit (%d + %d x n)", fixed, g.ts_wblk_bytes);
     L->smem_bytes = static_cast<size_t>(fixed) + static_cast<size_t>(g.ts_nw) * g.ts_wblk_bytes;
     auto classes = [](int in, int out, int k, int s, int pad, int* nlo, int* nhi) {
@@ -909,6 +980,23 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream) {
     if (!attr_ts) {
       FAV_CUDA(cudaFuncSetAttribute(conv_stem_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_ts = true;
+    }
+    static int prof = -1;
+    if (prof < 0) prof = getenv("FAV_STEM_PROF") ? atoi(getenv("FAV_STEM_PROF")) : 0;
+    if (prof) {   // debug: wait-cycle breakdown of the MMA warp (not capturable: synchronises the stream)
+      StemGeom gp = L.g;
+      gp.prof = prof | 1;   // 1: breakdown; +2: no epilogue work; +4: no MMAs (results are then wrong: timing only)
+      unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
+      cudaMemcpyToSymbol(g_halo_prof, z, sizeof(z));
+      conv_stem_ts_kernel<<<L.grid, kThreadsTs, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB1, gp, L.e);
+      cudaStreamSynchronize(stream);
+      cudaMemcpyFromSymbol(r, g_halo_prof, sizeof(r));
+      const double n = L.grid;
+      fprintf(stderr, "[fav] stem ts prof=%d tiles=%d grid=%d nw=%d pitch=%d: per-CTA kclk total %.0f, MMA warp waits: tempty %.0f, a_full %.0f, "
+              "w_full %.0f; epilogue warp waits tfull %.0f\n", gp.prof, L.g.m_tiles, L.grid, L.g.ts_nw, L.g.pitch, r[3] / n / 1e3, r[0] / n / 1e3,
+              r[1] / n / 1e3, r[2] / n / 1e3, r[4] / n / 1e3);
+      FAV_COUNT_LAUNCH();
+      return FAV_OK;
     }
     FAV_CUDA(launch_pdl(conv_stem_ts_kernel, L.grid, kThreadsTs, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3],
                         L.tmB1, L.g, L.e));

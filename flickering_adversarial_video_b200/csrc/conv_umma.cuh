@@ -331,8 +331,10 @@ struct StemGeom {
   int ts_ktmax[2];        // largest kt of each class
   int ts_slot_bytes;      // bytes per input-frame slot (both H-parity slabs)
   int ts_set_bytes;       // bytes per A set (the frames of one class)
-  int ts_wblk_bytes;      // bytes per weight block = the taps of one (class, kh): nslot x bn x 64 B
+  int ts_khg;             // kh taps per weight block
+  int ts_wblk_bytes;      // bytes per weight block = the taps of ts_khg kh's of one class: khg x nslot x bn x 64 B
   int ts_nw;              // weight ring depth
+  int prof;               // 1: the MMA / epilogue warps record their barrier wait cycles (debug, FAV_STEM_PROF)
   uint32_t ts_tab[2][8];  // per (class, frame): first / top output frame, accumulator column, weight-row offset (packed)
 };
 struct StemLaunch {
