@@ -60,12 +60,18 @@ __global__ void __launch_bounds__(kTapThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
                  const ConvEpilogue e,
-                 const int stages, const int a_bytes, const int b_bytes, const int stage_bytes) {
+                 const int stages, const int a_bytes, const int b_bytes, const int stage_bytes, const int kg) {
+  // `stages` ring entries of `kg` k-blocks each: ONE barrier hand-off per kg k-blocks.  FAV_TAP_PROF on the (3,1,1) and
+  // strided convs of r2plus1d_18 (N = 64: 204 cycles of MMA per k-block) showed 870 cycles per k-block with one hand-off
+  // each: ~450 on the producer lane (empty wait + expect_tx + two cp.async.bulk.tensor at ~150 cycles per issue) and
+  // ~490 on the MMA-issuing thread (full wait + commit), and the tensor pipe only queues ~2 instructions behind the
+  // running one, so it idles through every hand-off.  Now the 2*kg loads of a group are issued by 2*kg lanes in one
+  // instruction slot, and the MMA warp waits / commits once per group.
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * kg * stage_bytes);
   uint64_t* full_bar = bars;                    // [stages]
   uint64_t* empty_bar = bars + kMaxStages;      // [stages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [nacc <= 8]
@@ -108,40 +114,87 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(g, tile);
-        for (int kb = 0; kb < g.nkb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(a_bytes + b_bytes));
-          if (g.nsrc > 1) {
-            // 1x1x1 with K concatenated from several tensors: k-block -> (source, local block)
-            int src = 0, cb = kb;
-            if (cb >= g.src_blocks[0]) { cb -= g.src_blocks[0]; src = 1; }
-            if (src == 1 && cb >= g.src_blocks[1]) { cb -= g.src_blocks[1]; src = 2; }
-            const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : &tmA2);
-            tma_load_5d(sa, tm, &full_bar[stage], cb * 64, tc.w0, tc.h0, tc.t0, tc.b);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
-          } else {
-            const int tap = kb / g.cblocks;
-            const int cb = kb - tap * g.cblocks;
-            const int dw = tap % g.kw;
-            const int dh = (tap / g.kw) % g.kh;
-            const int dt = tap / (g.kw * g.kh);
-            tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 * g.sw + dw + g.ow, tc.h0 * g.sh + dh + g.oh,
-                        tc.t0 * g.st + dt + g.ot, tc.b);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
-          }
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
+    if (kg == 1) {
+        // one k-block per hand-off (1x1x1 convs: memory-bound, few k-blocks per tile): a single lane issues both loads
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const TileCoord tc = decode_tile(g, tile);
+          for (int kb = 0; kb < g.nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            uint8_t* sb = sa + a_bytes;
+            mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(a_bytes + b_bytes));
+            if (g.nsrc > 1) {
+              // 1x1x1 with K concatenated from several tensors: k-block -> (source, local block)
+              int src = 0, cb = kb;
+              if (cb >= g.src_blocks[0]) { cb -= g.src_blocks[0]; src = 1; }
+              if (src == 1 && cb >= g.src_blocks[1]) { cb -= g.src_blocks[1]; src = 2; }
+              const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : &tmA2);
+              tma_load_5d(sa, tm, &full_bar[stage], cb * 64, tc.w0, tc.h0, tc.t0, tc.b);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
+            } else {
+              const int tap = kb / g.cblocks;
+              const int cb = kb - tap * g.cblocks;
+              const int dw = tap % g.kw;
+              const int dh = (tap / g.kw) % g.kh;
+              const int dt = tap / (g.kw * g.kh);
+              tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 * g.sw + dw + g.ow, tc.h0 * g.sh + dh + g.oh,
+                          tc.t0 * g.st + dt + g.ot, tc.b);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * 64, tc.n0);
+            }
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
+    } else {
+      // the whole warp walks the ring; lane 0 polls, lanes 0 .. 2*nk-1 issue the group's loads (even: A box, odd: B tile)
+      {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const TileCoord tc = decode_tile(g, tile);
+          for (int kb0 = 0; kb0 < g.nkb; kb0 += kg) {
+            const int nk = min(kg, g.nkb - kb0);
+            if (lane == 0) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(nk * (a_bytes + b_bytes)));
+            }
+            __syncwarp();
+            if (lane < 2 * nk) {
+              const int i = lane >> 1;
+              const int kb = kb0 + i;
+              uint8_t* sa = smem + static_cast<size_t>(stage * kg + i) * stage_bytes;
+              if (lane & 1) {
+                tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * 64, tc.n0);
+              } else if (g.nsrc > 1) {
+                // 1x1x1 with K concatenated from several tensors: k-block -> (source, local block)
+                int src = 0, cb = kb;
+                if (cb >= g.src_blocks[0]) { cb -= g.src_blocks[0]; src = 1; }
+                if (src == 1 && cb >= g.src_blocks[1]) { cb -= g.src_blocks[1]; src = 2; }
+                const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : &tmA2);
+                tma_load_5d(sa, tm, &full_bar[stage], cb * 64, tc.w0, tc.h0, tc.t0, tc.b);
+              } else {
+                const int tap = kb / g.cblocks;
+                const int cb = kb - tap * g.cblocks;
+                const int dw = tap % g.kw;
+                const int dh = (tap / g.kw) % g.kh;
+                const int dt = tap / (g.kw * g.kh);
+                tma_load_5d(sa, &tmA0, &full_bar[stage], cb * 64, tc.w0 * g.sw + dw + g.ow, tc.h0 * g.sh + dh + g.oh,
+                            tc.t0 * g.st + dt + g.ot, tc.b);
+              }
+            }
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+    }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -164,40 +217,85 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_stride);
       uint32_t accum = 0;
       int cb = 0;
-      for (int kb = 0; kb < g.nkb; ++kb) {
-        c0 = g.prof ? clock64() : 0;
-        mbar_wait(&full_bar[stage], phase);
-        if (g.prof) w_f += clock64() - c0;
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-        const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
-        int ksteps = min(4, (g.cin - cb * 64) >> 4);
-        if (g.nsrc > 1) {
-          int src = 0, lb = kb;
-          if (lb >= g.src_blocks[0]) { lb -= g.src_blocks[0]; src = 1; }
-          if (src == 1 && lb >= g.src_blocks[1]) { lb -= g.src_blocks[1]; src = 2; }
-          const int cs_ = src == 0 ? g.src_cin[0] : (src == 1 ? g.src_cin[1] : g.src_cin[2]);
-          ksteps = min(4, (cs_ - lb * 64) >> 4);
-        }
-        if (elect_one()) {
-          const uint32_t a_lo = umma_desc_lo(sa);
-          const uint32_t b_lo = umma_desc_lo(sb);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < ksteps) {
-              umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
-              accum = 1;
-            }
+      if (kg == 1) {
+        for (int kb = 0; kb < g.nkb; ++kb) {
+          c0 = g.prof ? clock64() : 0;
+          mbar_wait(&full_bar[stage], phase);
+          if (g.prof) w_f += clock64() - c0;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + static_cast<uint32_t>(a_bytes);
+          int ksteps = min(4, (g.cin - cb * 64) >> 4);
+          if (g.nsrc > 1) {
+            int src = 0, lb = kb;
+            if (lb >= g.src_blocks[0]) { lb -= g.src_blocks[0]; src = 1; }
+            if (src == 1 && lb >= g.src_blocks[1]) { lb -= g.src_blocks[1]; src = 2; }
+            const int cs_ = src == 0 ? g.src_cin[0] : (src == 1 ? g.src_cin[1] : g.src_cin[2]);
+            ksteps = min(4, (cs_ - lb * 64) >> 4);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == g.nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          if (elect_one()) {
+            const uint32_t a_lo = umma_desc_lo(sa);
+            const uint32_t b_lo = umma_desc_lo(sb);
+  #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
+                accum = 1;
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (kb == g.nkb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          }
+          __syncwarp();
+          if (++cb == g.cblocks) cb = 0;
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++cb == g.cblocks) cb = 0;
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      } else {
+        for (int kb0 = 0; kb0 < g.nkb; kb0 += kg) {
+          const int nk = min(kg, g.nkb - kb0);
+          c0 = g.prof ? clock64() : 0;
+          mbar_wait(&full_bar[stage], phase);
+          if (g.prof) w_f += clock64() - c0;
+          tc_fence_after();
+          const uint32_t sa0 = smem_u32(smem + static_cast<size_t>(stage * kg) * stage_bytes);
+          if (elect_one()) {
+            int cbl = cb;
+            for (int i = 0; i < nk; ++i) {
+              const int kb = kb0 + i;
+              int ksteps = min(4, (g.cin - cbl * 64) >> 4);
+              if (g.nsrc > 1) {
+                int src = 0, lb = kb;
+                if (lb >= g.src_blocks[0]) { lb -= g.src_blocks[0]; src = 1; }
+                if (src == 1 && lb >= g.src_blocks[1]) { lb -= g.src_blocks[1]; src = 2; }
+                const int cs_ = src == 0 ? g.src_cin[0] : (src == 1 ? g.src_cin[1] : g.src_cin[2]);
+                ksteps = min(4, (cs_ - lb * 64) >> 4);
+              }
+              const uint32_t sa = sa0 + static_cast<uint32_t>(i * stage_bytes);
+              const uint32_t a_lo = umma_desc_lo(sa);
+              const uint32_t b_lo = umma_desc_lo(sa + static_cast<uint32_t>(a_bytes));
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
+                  accum = 1;
+                }
+              }
+              if (++cbl == g.cblocks) cbl = 0;
+            }
+            umma_commit(&empty_bar[stage]);  // frees the group's smem slots when these MMAs retire
+            if (kb0 + nk == g.nkb) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          }
+          __syncwarp();
+          cb += nk;
+          while (cb >= g.cblocks) cb -= g.cblocks;
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+      }
       }
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
@@ -589,9 +687,21 @@ static void finish_plan(ConvLaunch* L, int device) {
   L->a_bytes = 128 * 128;
   L->b_bytes = g.bn * 128;
   L->stage_bytes = round_up(L->a_bytes + L->b_bytes, 1024);
-  const int budget = 180 * 1024;
-  L->stages = std::max(2, std::min(kMaxStages, budget / L->stage_bytes));
-  L->smem_bytes = static_cast<size_t>(L->stages) * L->stage_bytes + 1024 + 512 + 8 * 32 * 5 * 16;   // + epilogue staging
+  // ring: `stages` groups of `kg` k-blocks (one barrier hand-off per group, see conv_umma_kernel)
+  const int budget = 200 * 1024;
+  const int slots = std::max(2, std::min(16, budget / L->stage_bytes));
+  {
+    // ~800 cycles of MMA per group hide a hand-off; at least three groups in the ring keep the loads ahead of the MMAs
+    const int mma_clk = 4 * std::max(g.bn / 2, 32 + g.bn / 4);
+    int kg = std::max(1, std::min(4, ceil_div(800, mma_clk)));
+    if (const char* ev = getenv("FAV_TAP_KG")) kg = std::max(1, std::min(8, atoi(ev)));
+    if (g.kt * g.kh * g.kw == 1 && !getenv("FAV_TAP_KG")) kg = 1;   // 1x1x1: memory-bound, measured slightly slower grouped (I3D conv_tap 0.98 -> 1.02 ms)
+    kg = std::min(kg, std::max(1, g.nkb));
+    while (kg > 1 && slots / kg < 3) --kg;
+    L->kg = kg;
+  }
+  L->stages = std::max(2, std::min(kMaxStages, slots / L->kg));
+  L->smem_bytes = static_cast<size_t>(L->stages) * L->kg * L->stage_bytes + 1024 + 512 + 8 * 32 * 5 * 16;   // + epilogue staging
   const int tiles = g.m_tiles * g.n_tiles;
   L->grid = std::max(1, std::min(tiles, sm_count(device)));
   // accumulator ring of the per-tap kernel (conv_umma_kernel): 8 x 64, 4 x 128 or 2 x 256 TMEM columns
@@ -873,7 +983,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     FAV_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  220 * 1024));
+                                  227 * 1024));
     attr_set = true;
   }
   ProfScope ps(L.g.halo ? PK_CONV_HALO : PK_CONV_TAP, stream, L.flops);
@@ -915,19 +1025,19 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
       unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
       cudaMemcpyToSymbol(g_halo_prof, z, sizeof(z));
       conv_umma_kernel<<<L.grid, kTapThreads, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, gp, L.e, L.stages,
-                                                                   L.a_bytes, L.b_bytes, L.stage_bytes);
+                                                                   L.a_bytes, L.b_bytes, L.stage_bytes, L.kg);
       cudaStreamSynchronize(stream);
       cudaMemcpyFromSymbol(r, g_halo_prof, sizeof(r));
       const double n = L.grid;
-      fprintf(stderr, "[fav] tap prof M %dx%dx%dx%d k%dx%dx%d cin=%d nkb=%d bn=%dx%d stages=%d grid=%d: per-CTA kclk total %.1f, wait tempty %.1f, full %.1f, tiles %.1f\n",
-              L.g.B, L.g.T, L.g.H, L.g.W, L.g.kt, L.g.kh, L.g.kw, L.g.cin, L.g.nkb, L.g.bn, L.g.n_tiles, L.stages, L.grid,
+      fprintf(stderr, "[fav] tap prof M %dx%dx%dx%d k%dx%dx%d cin=%d nkb=%d bn=%dx%d stages=%dx%d grid=%d: per-CTA kclk total %.1f, wait tempty %.1f, full %.1f, tiles %.1f\n",
+              L.g.B, L.g.T, L.g.H, L.g.W, L.g.kt, L.g.kh, L.g.kw, L.g.cin, L.g.nkb, L.g.bn, L.g.n_tiles, L.stages, L.kg, L.grid,
               r[3] / n / 1e3, r[0] / n / 1e3, r[1] / n / 1e3, r[4] / n);
       FAV_COUNT_LAUNCH();
       return FAV_OK;
     }
   }
   FAV_CUDA(launch_pdl(conv_umma_kernel, L.grid, kTapThreads, L.smem_bytes, stream, L.tmA[0], L.tmA[1], L.tmA[2], L.tmB, L.g,
-                      L.e, L.stages, L.a_bytes, L.b_bytes, L.stage_bytes));
+                      L.e, L.stages, L.a_bytes, L.b_bytes, L.stage_bytes, L.kg));
   FAV_COUNT_LAUNCH();
   FAV_CUDA(cudaGetLastError());
   return FAV_OK;

@@ -82,7 +82,8 @@ struct ConvLaunch {
   CUtensorMap tmB;
   ConvGeom g;
   ConvEpilogue e;
-  int stages;
+  int stages;             // ring entries (per-tap kernel: groups of kg k-blocks)
+  int kg;                 // per-tap kernel: k-blocks per barrier hand-off
   int a_bytes, b_bytes, stage_bytes;
   size_t smem_bytes;
   int grid;
