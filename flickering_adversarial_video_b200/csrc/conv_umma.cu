@@ -986,6 +986,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
                                   227 * 1024));
     attr_set = true;
   }
+  if (L.use_t3) return conv_t3_launch(L.t3, L.e, L.flops, stream);
   ProfScope ps(L.g.halo ? PK_CONV_HALO : PK_CONV_TAP, stream, L.flops);
   if (L.g.halo && L.g.pair) return conv_launch_halo_pair(L, stream);
   if (L.g.halo) {

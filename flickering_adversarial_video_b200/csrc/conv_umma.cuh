@@ -77,11 +77,34 @@ struct ConvEpilogue {
   int seg_coff[3];
 };
 
+// (3,1,1) stride-1 convs with cout <= 64: input frames shared over the taps (conv_t3.cu)
+struct T3Geom {
+  int B, T, HW;           // output (= input) positions: frames x flat plane
+  int cin, cblocks;       // input channels, 64-channel blocks
+  int tail_bytes;         // row bytes of the last block's A tile: 128 (full 64-channel box), 64 or 32 (SW64 / SW32 box)
+  int ktail;              // k-steps (16 channels) of the last block
+  int bn;                 // output channels (padded), <= 64
+  int tp, ptiles, m_tiles;   // frame groups per clip, 128-position tiles per plane, tiles
+  int nst;                // A ring entries (one input frame each)
+  int grp_bytes, grp_tx;  // shared-memory bytes / TMA bytes per ring entry
+  int w_bytes;            // resident weights
+  int f16;                // 1: fp16 operands (forward), 0: bf16
+  int prof;
+};
+struct T3Plan {
+  CUtensorMap tmA, tmAt, tmB;
+  T3Geom g;
+  size_t smem_bytes;
+  int grid;
+};
+
 struct ConvLaunch {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
   ConvGeom g;
   ConvEpilogue e;
+  int use_t3;             // 1: conv_launch runs conv_t3_kernel with `t3` (and this launch's epilogue)
+  T3Plan t3;
   int stages;             // ring entries (per-tap kernel: groups of kg k-blocks)
   int kg;                 // per-tap kernel: k-blocks per barrier hand-off
   int a_bytes, b_bytes, stage_bytes;
@@ -300,6 +323,11 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
 bool conv_halo_applicable(int T, int H, int W, int kt, int kh, int kw);
 
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
+// conv_t3.cu: x [B,T,HW,x_cs] (channels 0 .. cin), wpk = the per-tap kernel's packed weights [cout_pad][3 * cblocks * 64]
+bool conv_t3_applicable(int cin, int cout_pad, int T);
+int conv_t3_plan(T3Plan* P, int device, const void* x, long long x_cs, int cin, const void* wpk, int cout_pad, int B, int T,
+                 int HW, bool f16);
+int conv_t3_launch(const T3Plan& P, const ConvEpilogue& e, double flops, cudaStream_t stream);
 int conv_launch_halo_pair(const ConvLaunch& L, cudaStream_t stream);   // conv_halo2.cu
 
 // ---- stem (strided 7x7 spatial, Cin = 3): shared-memory halo reuse over kh, see conv_stem.cu ----

@@ -117,6 +117,12 @@ int rn_plan_conv(fav_handle* h, RConv& c) {
     sp.oT = bo.T; sp.oH = bo.H; sp.oW = bo.W;
     sp.est = sp.esh = sp.esw = 1;
     FAV_TRY(conv_plan_ex(&c.fwd, h->device, sp));
+    // Conv2Plus1D's temporal half with few output channels (the stem's 45 -> 64, layer1's 144 -> 64): every input frame
+    // is loaded once for its three taps (conv_t3.cu) instead of three times through L2
+    if (c.kt == 3 && c.kh == 1 && c.kw == 1 && s1 && c.pt == 1 && conv_t3_applicable(c.cin_k, c.cout_pad, bo.T)) {
+      FAV_TRY(conv_t3_plan(&c.fwd.t3, h->device, bi.p, bi.cs, c.cin_k, c.w_fwd, c.cout_pad, h->B, bo.T, bo.H * bo.W, true));
+      c.fwd.use_t3 = 1;
+    }
   }
   {
     c.fwd.g.f16 = 1;
