@@ -250,11 +250,8 @@ static int t3_group_bytes(int cin) {
 }
 
 bool conv_t3_applicable(int cin, int cout_pad, int T) {
-  static int on = -1;
-  if (on < 0) {
-    const char* ev = getenv("FAV_T3");   // 0: keep the per-tap kernel (A/B)
-    on = (ev && atoi(ev) == 0) ? 0 : 1;
-  }
+  const char* ev = getenv("FAV_T3");   // 0: keep the per-tap kernel (A/B, tests); read at plan time
+  const bool on = !(ev && atoi(ev) == 0);
   if (!on || cout_pad > 64 || cout_pad % 16 != 0 || cin % 16 != 0 || T < 2) return false;
   const int cblocks = ceil_div(cin, 64);
   const int w_bytes = round_up(cblocks * 3 * cout_pad * 128, 1024);

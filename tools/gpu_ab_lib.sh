@@ -7,6 +7,7 @@ for r in 1 2; do
   for v in base ab; do
     if [ $v = ab ]; then cp $P/libfav_ab.so $P/libfav.so; else cp /tmp/libfav_base.so $P/libfav.so; fi
     for c in ${CONFIGS:-c2 c4}; do echo -n "$v $c: "; run $c; done
+    for a in $ARCHS; do echo -n "$v "; timeout 300 python tools/bench_arch.py $a 2>&1 | tail -1 | cut -c1-140; done
   done
 done
 cp /tmp/libfav_base.so $P/libfav.so
