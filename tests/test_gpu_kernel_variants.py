@@ -100,10 +100,11 @@ def test_r2plus1d_shared_frame_temporal_conv_matches_per_tap(T, monkeypatch):
 @pytest.mark.parametrize("arch", ["r2plus1d_18", "mc3_18"])
 def test_grouped_k_blocks_match_single_hand_offs(arch, monkeypatch):
     """Per-tap kernel: k-blocks handed over in groups (planner's choice) vs one per barrier (FAV_TAP_KG=1); the MMA order is
-    the same, so the results are bit-identical."""
+    the same, so the network's results are bit-identical (the [T,3] gradient is summed with atomics by the stem gradient
+    kernel: equal up to the order of those fp32 additions)."""
     B, T, H, W = 2, 8, 112, 112
     a = _run(arch, B, T, H, W, {"FAV_T3": "0"}, monkeypatch)
     b = _run(arch, B, T, H, W, {"FAV_T3": "0", "FAV_TAP_KG": "1"}, monkeypatch, labels=a["labels"])
     assert float(a["grad"].norm()) > 0
     assert torch.equal(a["logits"], b["logits"])
-    assert torch.equal(a["grad"], b["grad"])
+    assert torch.allclose(a["grad"], b["grad"], rtol=1e-4, atol=1e-6 * float(a["grad"].abs().max()))

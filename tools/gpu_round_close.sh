@@ -1,15 +1,16 @@
 # Round-end verification on one box: the -m gpu suite, smoke(), the default bench line (with its CPU baseline and the
 # sustained segment), the reference arm, every other BASELINE configuration.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -rf > gpurun_out/close_pytest.log 2>&1; echo "pytest exit $?"
-tail -3 gpurun_out/close_pytest.log
-timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('__SMOKE_OK__')" > gpurun_out/close_smoke.log 2>&1; echo "smoke exit $?"; grep -E "smoke|SMOKE" gpurun_out/close_smoke.log
-timeout 900 python bench.py > gpurun_out/close_bench.json 2> gpurun_out/close_bench.err; echo "bench exit $?"; tail -2 gpurun_out/close_bench.err
-timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/close_bench_reference.json 2> gpurun_out/close_bench_reference.err; echo "reference exit $?"; tail -c 400 gpurun_out/close_bench_reference.json
-for c in c1 c3 c4 c5 c5m; do timeout 600 python bench.py --config $c --steps 20 --warmup 3 --sustained-sec 0 --no-cpu-baseline > gpurun_out/close_bench_$c.json 2> gpurun_out/close_bench_$c.err; echo "bench $c exit $?"; done
+export TAG=${TAG:-close}
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -rf > gpurun_out/${TAG:-close}_pytest.log 2>&1; echo "pytest exit $?"
+tail -3 gpurun_out/${TAG:-close}_pytest.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('__SMOKE_OK__')" > gpurun_out/${TAG:-close}_smoke.log 2>&1; echo "smoke exit $?"; grep -E "smoke|SMOKE" gpurun_out/${TAG:-close}_smoke.log
+timeout 900 python bench.py > gpurun_out/${TAG:-close}_bench.json 2> gpurun_out/${TAG:-close}_bench.err; echo "bench exit $?"; tail -2 gpurun_out/${TAG:-close}_bench.err
+timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG:-close}_bench_reference.json 2> gpurun_out/${TAG:-close}_bench_reference.err; echo "reference exit $?"; tail -c 400 gpurun_out/${TAG:-close}_bench_reference.json
+for c in c1 c3 c4 c5 c5m; do timeout 600 python bench.py --config $c --steps 20 --warmup 3 --sustained-sec 0 --no-cpu-baseline > gpurun_out/${TAG:-close}_bench_$c.json 2> gpurun_out/${TAG:-close}_bench_$c.err; echo "bench $c exit $?"; done
 python - <<'PY'
-import json, glob
-for f in sorted(glob.glob("gpurun_out/close_bench*.json")):
+import json, glob, os
+for f in sorted(glob.glob("gpurun_out/%s_bench*.json" % os.environ.get("TAG", "close"))):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         if d.get("impl") == "reference":
