@@ -222,41 +222,40 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&a_full[sa], pa);
           if (g.prof) w_a += clock64() - c0;
           const uint32_t slab_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.slab_bytes));
-          uint32_t row_lo = slab_lo;
-          for (int dh = 0; dh < 3; ++dh) {
-            for (int dw0 = 0; dw0 < 3; dw0 += g.bgroup) {
-              c0 = g.prof ? clock64() : 0;
-              mbar_wait(&b_full[sb], pb);
-              if (g.prof) w_b += clock64() - c0;
-              tc_fence_after();
-              const uint32_t b_grp = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * g.bgroup * b_bytes));
-              if (elect_one()) {
-                for (int u = 0; u < g.bgroup; ++u) {
-                  const uint32_t b_lo = b_grp + static_cast<uint32_t>(u) * static_cast<uint32_t>(b_bytes >> 4);
-                  uint32_t a_i = row_lo + 8u * static_cast<uint32_t>(dw0 + u);
-                  uint32_t d_i = d_tmem;
-                  for (int i = 0; i < g.mt; ++i) {
+          for (int j0 = 0; j0 < 9; j0 += g.bgroup) {   // weight groups of 1, 3 (one dh row) or 9 (the whole slab) taps
+            c0 = g.prof ? clock64() : 0;
+            mbar_wait(&b_full[sb], pb);
+            if (g.prof) w_b += clock64() - c0;
+            tc_fence_after();
+            const uint32_t b_grp = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * g.bgroup * b_bytes));
+            if (elect_one()) {
+              for (int u = 0; u < g.bgroup; ++u) {
+                const int tap = j0 + u;
+                const int dh = (tap >= 3) + (tap >= 6);
+                const int dw = tap - 3 * dh;
+                const uint32_t b_lo = b_grp + static_cast<uint32_t>(u) * static_cast<uint32_t>(b_bytes >> 4);
+                uint32_t a_i = slab_lo + static_cast<uint32_t>(dh) * wp16 + 8u * static_cast<uint32_t>(dw);
+                uint32_t d_i = d_tmem;
+                for (int i = 0; i < g.mt; ++i) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      if (k < ksteps)
-                        umma_bf16_pair(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc,
-                                       accum | (k > 0 ? 1u : 0u));
-                    }
-                    a_i += tile16;
-                    d_i += static_cast<uint32_t>(g.bn);
+                  for (int k = 0; k < 4; ++k) {
+                    if (k < ksteps)
+                      umma_bf16_pair(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc,
+                                     accum | (k > 0 ? 1u : 0u));
                   }
-                  accum = 1;
+                  a_i += tile16;
+                  d_i += static_cast<uint32_t>(g.bn);
                 }
-                umma_commit_pair(&b_empty[sb]);
-                if (dh == 2 && dw0 + g.bgroup == 3) {
-                  umma_commit_pair(&a_empty[sa]);
-                  if (sidx == slabs_per_tile - 1) umma_commit_pair(&tfull_bar[acc]);
-                }
+                accum = 1;
               }
-              __syncwarp();
-              if (++sb == g.nb) { sb = 0; pb ^= 1; }
+              umma_commit_pair(&b_empty[sb]);
+              if (j0 + g.bgroup == 9) {
+                umma_commit_pair(&a_empty[sa]);
+                if (sidx == slabs_per_tile - 1) umma_commit_pair(&tfull_bar[acc]);
+              }
             }
-            row_lo += wp16;
+            __syncwarp();
+            if (++sb == g.nb) { sb = 0; pb ^= 1; }
           }
           if (++sa == g.na) { sa = 0; pa ^= 1; }
           if (++dt == g.kt) { dt = 0; ++cb; }

@@ -510,39 +510,39 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&a_full[sa], pa);
         if (g.prof) w_a += clock64() - c0;
         const uint32_t slab_lo = umma_desc_lo(smem_u32(smem_a + static_cast<size_t>(sa) * g.slab_bytes));
-        uint32_t row_lo = slab_lo;     // + dh * Wp rows
-        for (int dh = 0; dh < 3; ++dh) {
-          for (int dw0 = 0; dw0 < 3; dw0 += g.bgroup) {
-            c0 = g.prof ? clock64() : 0;
-            mbar_wait(&b_full[sb], pb);
-            if (g.prof) w_b += clock64() - c0;
-            tc_fence_after();
-            const uint32_t b_grp = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * g.bgroup * b_bytes));
-            if (elect_one()) {
-              for (int u = 0; u < g.bgroup; ++u) {
-                const uint32_t b_lo = b_grp + static_cast<uint32_t>(u) * static_cast<uint32_t>(b_bytes >> 4);
-                uint32_t a_i = row_lo + 8u * static_cast<uint32_t>(dw0 + u);   // one position = 128 B = 8 x 16 B
-                uint32_t d_i = d_tmem;
-                for (int i = 0; i < g.mt; ++i) {
+        for (int j0 = 0; j0 < 9; j0 += g.bgroup) {   // weight groups of 1, 3 (one dh row) or 9 (the whole slab) taps
+          c0 = g.prof ? clock64() : 0;
+          mbar_wait(&b_full[sb], pb);
+          if (g.prof) w_b += clock64() - c0;
+          tc_fence_after();
+          const uint32_t b_grp = umma_desc_lo(smem_u32(smem_b + static_cast<size_t>(sb) * g.bgroup * b_bytes));
+          if (elect_one()) {
+            for (int u = 0; u < g.bgroup; ++u) {
+              const int tap = j0 + u;
+              const int dh = (tap >= 3) + (tap >= 6);
+              const int dw = tap - 3 * dh;
+              const uint32_t b_lo = b_grp + static_cast<uint32_t>(u) * static_cast<uint32_t>(b_bytes >> 4);
+              // row window of tap (dh, dw): dh padded rows down, dw positions right (one position = 128 B = 8 x 16 B)
+              uint32_t a_i = slab_lo + static_cast<uint32_t>(dh) * wp16 + 8u * static_cast<uint32_t>(dw);
+              uint32_t d_i = d_tmem;
+              for (int i = 0; i < g.mt; ++i) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (k < ksteps) umma_bf16(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum | (k > 0 ? 1u : 0u));
-                  }
-                  a_i += tile16;                       // next M tile: nrows padded rows further down the slab
-                  d_i += static_cast<uint32_t>(g.bn);
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) umma_bf16(d_i, make_desc(desc_hi, a_i + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum | (k > 0 ? 1u : 0u));
                 }
-                accum = 1;
+                a_i += tile16;                       // next M tile: nrows padded rows further down the slab
+                d_i += static_cast<uint32_t>(g.bn);
               }
-              umma_commit(&b_empty[sb]);
-              if (dh == 2 && dw0 + g.bgroup == 3) {
-                umma_commit(&a_empty[sa]);
-                if (sidx == slabs_per_tile - 1) umma_commit(&tfull_bar[acc]);
-              }
+              accum = 1;
             }
-            __syncwarp();
-            if (++sb == g.nb) { sb = 0; pb ^= 1; }
+            umma_commit(&b_empty[sb]);
+            if (j0 + g.bgroup == 9) {
+              umma_commit(&a_empty[sa]);
+              if (sidx == slabs_per_tile - 1) umma_commit(&tfull_bar[acc]);
+            }
           }
-          row_lo += wp16;
+          __syncwarp();
+          if (++sb == g.nb) { sb = 0; pb ^= 1; }
         }
         if (++sa == g.na) { sa = 0; pa ^= 1; }
         if (++dt == g.kt) { dt = 0; ++cb; }
@@ -855,6 +855,8 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     }
     double best = 1e30;
     int best_nt = 0, best_mt = 0, best_na = 0, best_nb = 0, best_bg = 1;
+    const char* ev9 = getenv("FAV_HALO_BG9");   // 0: at most 3 taps per weight group (A/B)
+    const bool bg9 = !(ev9 && atoi(ev9) == 0);
     for (int nt = 1; nt <= 6; ++nt) {
       const int bn = round_up(ceil_div(cout_pad, nt), 16);   // the last N tile may be partial (TMA zero fill)
       if (bn > 256 || bn * (nt - 1) >= cout_pad) continue;
@@ -870,6 +872,13 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
         int na = 3, bgroup = 3;
         int nb = std::min(4, (budget - na * slab_bytes) / (3 * b_bytes));
         if (nb < 2) { na = 2; nb = std::min(4, (budget - na * slab_bytes) / (3 * b_bytes)); }
+        // narrow weight tiles: all 9 taps of a slab per barrier (FAV_HALO_PROF on the Branch_2 convs: ~250 cycles per
+        // (tap, M tile) against ~50 of MMA — the issuing thread's hand-offs, not the tensor pipe)
+        if (bg9 && b_bytes <= 8 * 1024 && (budget - 2 * slab_bytes) / (9 * b_bytes) >= 2) {
+          bgroup = 9;
+          na = (budget - 3 * slab_bytes) / (9 * b_bytes) >= 2 ? 3 : 2;
+          nb = std::min(3, (budget - na * slab_bytes) / (9 * b_bytes));
+        }
         if (nb < 2) {
           bgroup = 1; na = 3;
           nb = std::min(8, (budget - na * slab_bytes) / b_bytes);
@@ -957,6 +966,8 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
     const int budget = 212 * 1024;
     int na = 3, bg = 3;
     int nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb));
+    const char* ev9 = getenv("FAV_HALO_BG9");
+    const bool bg9 = !(ev9 && atoi(ev9) == 0) && hb <= 4 * 1024 && (budget - 2 * g.slab_bytes) / (9 * hb) >= 2;
     // FAV_HALO_PROF: pairs spend 20-40 % of their time waiting for weight groups (every group crosses the pair: remote
     // expect_tx, remote TMA completion, multicast commit), while a slab lives for 9 taps x k-steps x mt MMAs — so a
     // third slab buys less than one or two more weight groups in flight (FAV_HALO_PAIR_NA=3 restores the old choice)
@@ -967,6 +978,11 @@ int conv_plan_halo(ConvLaunch* L, int device, const void* x, long long x_cs, int
       if (nb2 > nb) { na = 2; nb = nb2; }
     }
     if (nb < 3) { na = 2; nb = std::min(6, (budget - na * g.slab_bytes) / (3 * hb)); }
+    if (bg9) {   // narrow tiles: the 9 taps of a slab per (cross-CTA) weight hand-off
+      bg = 9;
+      na = (budget - 3 * g.slab_bytes) / (9 * hb) >= 2 ? 3 : 2;
+      nb = std::min(3, (budget - na * g.slab_bytes) / (9 * hb));
+    }
     if (nb >= 2) {
       g.na = na; g.nb = nb; g.bgroup = bg;
       L->smem_bytes = static_cast<size_t>(g.na) * g.slab_bytes + static_cast<size_t>(g.nb) * g.bgroup * hb + 1024 + 512 +
