@@ -89,6 +89,7 @@ SIGNATURES = {
     "fav_profile_end": (_i, [C.POINTER(C.c_double), _i]),
     "fav_launch_count": (_i64, []),
     "fav_debug_f32_to_f16": (C.c_uint16, [_f]),
+    "fav_debug_stem_ts_schedule": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "fav_build_info": (C.c_char_p, []),
 }
 

@@ -716,6 +716,40 @@ conv_stem_ts_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
 }  // namespace
 
+// Frame schedule of conv_stem_ts_kernel: a tile of G = tsG output frames reads st*(G-1)+KT input frames; frame dd
+// (relative to the tile's first input frame st*t0 - pt) feeds output frame j through tap kt = dd - st*j, so it belongs to
+// class dd % st (= kt % st) and serves the consecutive output frames jlo .. jtop.  The class's kt sub-tiles are stacked by
+// descending kt (slot s holds kt = ktmax - s*st): output frame jlo reads slot (ktmax - dd)/st + jlo, jlo+1 the next one.
+int stem_ts_schedule(StemGeom* gp, int KT, int st, int bn, int* max_nfr_out, int* max_slot_out) {
+  StemGeom& g = *gp;
+  FAV_CHECK_ARG(st >= 1 && st <= 2 && KT >= 1 && KT <= 7 && g.tsG >= 1 && g.tsG <= 8, "stem schedule: KT=%d st=%d G=%d", KT,
+                st, g.tsG);
+  const int nd = st * (g.tsG - 1) + KT;        // input frames per tile
+  int max_nfr = 0, max_slot = 0;
+  for (int c = 0; c < st; ++c) {
+    g.ts_nfr[c] = (nd - c + st - 1) / st;
+    g.ts_ktmax[c] = c + ((KT - 1 - c) / st) * st;
+    g.ts_nslot[c] = (g.ts_ktmax[c] - c) / st + 1;
+    max_nfr = std::max(max_nfr, g.ts_nfr[c]);
+    max_slot = std::max(max_slot, g.ts_nslot[c]);
+  }
+  FAV_CHECK_ARG(max_nfr <= kTsMaxFr, "stem: %d input frames per class", max_nfr);
+  for (int c = 0; c < st; ++c)
+    for (int f = 0; f < g.ts_nfr[c]; ++f) {
+      const int dd = c + f * st;                       // frame index inside the tile: kt of output frame j = dd - st*j
+      const int jtop = dd / st;
+      const int num = dd - KT + 1;
+      const int jlo = num > 0 ? (num + st - 1) / st : 0;
+      const int slot0 = (g.ts_ktmax[c] - dd) / st + jlo;   // exact: dd and ktmax are in the same class
+      // jlo [0,4) | jtop [4,8) | accumulator column of jlo [8,18) | weight-row offset of jlo in 16-byte units [18,32)
+      g.ts_tab[c][f] = static_cast<uint32_t>(jlo) | (static_cast<uint32_t>(jtop) << 4) |
+                       (static_cast<uint32_t>(jlo * bn) << 8) | (static_cast<uint32_t>(slot0 * bn * 4) << 18);
+    }
+  *max_nfr_out = max_nfr;
+  *max_slot_out = max_slot;
+  return FAV_OK;
+}
+
 int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
               int To, int Ho, int Wo, int KT, int KH, int st, int pt, int ph) {
   FAV_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "stem: cout=%d must be a multiple of 16 <= 256", bn);
@@ -763,26 +797,8 @@ int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, 
       off += round_up(g.rows[p] * g.pitch, 128);
     }
     g.ts_slot_bytes = off;
-    const int nd = st * (g.tsG - 1) + KT;        // input frames per tile
     int max_nfr = 0, max_slot = 0;
-    for (int c = 0; c < st; ++c) {
-      g.ts_nfr[c] = (nd - c + st - 1) / st;
-      g.ts_ktmax[c] = c + ((KT - 1 - c) / st) * st;
-      g.ts_nslot[c] = (g.ts_ktmax[c] - c) / st + 1;
-      max_nfr = std::max(max_nfr, g.ts_nfr[c]);
-      max_slot = std::max(max_slot, g.ts_nslot[c]);
-    }
-    FAV_CHECK_ARG(max_nfr <= kTsMaxFr, "stem: %d input frames per class", max_nfr);
-    for (int c = 0; c < st; ++c)
-      for (int f = 0; f < g.ts_nfr[c]; ++f) {
-        const int dd = c + f * st;                       // frame index inside the tile: kt of output frame j = dd - st*j
-        const int jtop = dd / st;
-        const int num = dd - KT + 1;
-        const int jlo = num > 0 ? (num + st - 1) / st : 0;
-        const int slot0 = (g.ts_ktmax[c] - dd) / st + jlo;   // exact: dd and ktmax are in the same class
-        g.ts_tab[c][f] = static_cast<uint32_t>(jlo) | (static_cast<uint32_t>(jtop) << 4) |
-                         (static_cast<uint32_t>(jlo * bn) << 8) | (static_cast<uint32_t>(slot0 * bn * 4) << 18);
-      }
+    FAV_TRY(stem_ts_schedule(&g, KT, st, bn, &max_nfr, &max_slot));
     g.ts_set_bytes = round_up(max_nfr * g.ts_slot_bytes, 1024);
     {
       const char* ev = getenv("FAV_STEM_TS_KHG");   // kh taps per weight block (one barrier hand-off per block)
@@ -1024,3 +1040,24 @@ int stem_launch(const StemLaunch& L, cudaStream_t stream) {
 }
 
 }  // namespace fav
+
+// host-only view of the schedule for the CPU tests (include/fav.h)
+extern "C" int fav_debug_stem_ts_schedule(int KT, int st, int bn, int* nfr, int* nslot, int* ktmax, uint32_t* tab) {
+  if (!nfr || !nslot || !ktmax || !tab) {
+    fav::set_error("fav_debug_stem_ts_schedule: null argument");
+    return FAV_ERR_ARG;
+  }
+  fav::StemGeom g;
+  memset(&g, 0, sizeof(g));
+  g.tsG = 4;
+  int a = 0, b = 0;
+  const int s = fav::stem_ts_schedule(&g, KT, st, bn, &a, &b);
+  if (s != FAV_OK) return s;
+  for (int c = 0; c < 2; ++c) {
+    nfr[c] = c < st ? g.ts_nfr[c] : 0;
+    nslot[c] = c < st ? g.ts_nslot[c] : 0;
+    ktmax[c] = c < st ? g.ts_ktmax[c] : 0;
+    for (int f = 0; f < 8; ++f) tab[c * 8 + f] = c < st ? g.ts_tab[c][f] : 0u;
+  }
+  return g.tsG;
+}

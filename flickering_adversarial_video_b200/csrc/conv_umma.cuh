@@ -380,6 +380,8 @@ struct StemLaunch {
 int stem_plan(StemLaunch* L, int device, const void* xpad, int B, int T, int H, int Wp, const void* wpk, int bn,
               int To, int Ho, int Wo, int KT, int KH, int st, int pt, int ph);
 int stem_launch(const StemLaunch& L, cudaStream_t stream);
+// frame schedule of the temporal-sharing kernel (fills ts_nfr / ts_nslot / ts_ktmax / ts_tab from g->tsG)
+int stem_ts_schedule(StemGeom* g, int KT, int st, int bn, int* max_nfr, int* max_slot);
 
 
 // ---- stem gradient collapse on the tensor cores (stem_grad.cu) ----

@@ -281,6 +281,13 @@ int64_t fav_launch_count(void);
  * saturating at +-65504); exported so that the conversion can be checked without a GPU */
 uint16_t fav_debug_f32_to_f16(float f);
 
+/* host-only: the frame schedule the temporal-sharing stem kernel runs for a KT-tap stem of temporal stride st and bn output
+ * channels (csrc/conv_stem.cu).  Per class c < st (frame index mod st = tap index mod st): nfr[c] input frames per tile,
+ * nslot[c] taps, ktmax[c] the largest tap; tab[c*8 + f] for frame f of the class packs the first / top output frame it
+ * feeds, the accumulator column and the weight-row offset.  Returns the output frames per tile (4) or < 0.  Exported so
+ * that the schedule's invariants can be checked without a GPU (tests/test_cpu_lib.py). */
+int fav_debug_stem_ts_schedule(int KT, int st, int bn, int* nfr, int* nslot, int* ktmax, uint32_t* tab);
+
 /* library build info: "sm_100a;<compile date>" */
 const char* fav_build_info(void);
 
