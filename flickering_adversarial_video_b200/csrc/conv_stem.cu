@@ -404,11 +404,17 @@ conv_stem_raw_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 //   tile       = 8 output columns x 16 output rows x G = 4 consecutive output frames (G accumulators of bn columns, x2 stages)
 //   A set      = the raw rows of the tile's input frames of one class c (frame index mod st; st*(G-1)+KT frames in all),
 //                loaded once per tile; two sets in flight
-//   weight ring= blocks of one (class, kh): the class's kt sub-tiles stacked by DESCENDING kt, so the sub-tiles of
-//                consecutive output frames j, j+1, ... (kt = dd - st*j) are consecutive rows of the B operand
-//   loop       = class -> kh -> frame -> K half; every weight block (12-16 KB from L2) serves 2 * frames MMAs
+//   weight ring= blocks of ts_khg (3) kh taps of one class: per kh the class's kt sub-tiles stacked by DESCENDING kt, so
+//                the sub-tiles of consecutive output frames j, j+1, ... (kt = dd - st*j) are consecutive rows of the B
+//                operand; 36-48 KB per block from L2, one barrier hand-off per block
+//   loop       = class -> weight block -> kh -> frame -> K half; the frames of a kh are issued narrowest first, widest last
 // The first MMA that touches accumulator j is (class 0, kh 0, frame dd = st*j, K half 0) with j the TOP of the frame's
 // range: that MMA is split into an accumulating part and a fresh (accumulate = 0) part of N = bn.
+// Measured (FAV_STEM_PROF, profiles/r02b_stem_ts_prof.txt; I3D 8 x 64: 0.58 -> 0.44 ms): the kernel now sits on the
+// shared-memory / L1 port — per tile 1.5 MB of operand reads + 0.28 MB of TMA writes + 0.3 MB of epilogue traffic = 16.5
+// kcycles at 128 B/clk against 13.4 k of tensor time; 17.2 k measured.  The tensor pipe queues only ~2 MMAs behind the
+// running one, so what is queued when the issuing thread goes through a barrier hand-off decides how long the pipe idles:
+// hence the widest-last order (894 -> 798 kcycles per CTA) and 3 kh taps per block (826 / 749 / 730 at 1 / 2 / 3).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kThreadsTs = 352;   // warp 0: A producer, 1: MMA issuer, 6: weight producer, 2..5 and 7..10: two epilogue sets
 constexpr int kMaxW = 8;
