@@ -115,7 +115,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (kg == 1) {
-        // one k-block per hand-off (1x1x1 convs: memory-bound, few k-blocks per tile): a single lane issues both loads
+      // one k-block per hand-off (1x1x1 convs: memory-bound, few k-blocks per tile): a single lane issues both loads
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
@@ -194,7 +194,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
         }
-    }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -236,7 +236,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (elect_one()) {
             const uint32_t a_lo = umma_desc_lo(sa);
             const uint32_t b_lo = umma_desc_lo(sb);
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (k < ksteps) {
                 umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
@@ -276,7 +276,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const uint32_t sa = sa0 + static_cast<uint32_t>(i * stage_bytes);
               const uint32_t a_lo = umma_desc_lo(sa);
               const uint32_t b_lo = umma_desc_lo(sa + static_cast<uint32_t>(a_bytes));
-  #pragma unroll
+#pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < ksteps) {
                   umma_bf16(d_tmem, make_desc(desc_hi, a_lo + 2 * k), make_desc(desc_hi, b_lo + 2 * k), idesc, accum);
@@ -295,7 +295,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             stage = 0;
             phase ^= 1;
           }
-      }
+        }
       }
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
